@@ -1,0 +1,156 @@
+"""ctypes mirror of include/dtof.h (the C ABI of libdtof_b200.so) and of the oracle's entry points.
+
+Nothing here computes: it only lays out the plain structs the boundary takes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+ABI_VERSION = 1
+
+# enums (include/dtof.h)
+TIME_UNIFORM, TIME_STRATIFIED, TIME_ANTITHETIC, TIME_ANTITHETIC_MIRROR = range(4)
+WAVE_SINUSOIDAL, WAVE_RECTANGULAR, WAVE_TRIANGULAR, WAVE_TRAPEZOIDAL = range(4)
+RFILTER_BOX, RFILTER_TENT, RFILTER_GAUSSIAN = range(3)
+SHAPE_MESH, SHAPE_RECTANGLE = range(2)
+BSDF_DIFFUSE, BSDF_NULL_BLACK = range(2)
+EMITTER_POINT, EMITTER_AREA = range(2)
+
+OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED, ERR_STATE = range(6)
+
+_fp = C.POINTER(C.c_float)
+_up = C.POINTER(C.c_uint32)
+
+
+class Mesh(C.Structure):
+    _fields_ = [
+        ("n_vertices", C.c_uint32), ("n_faces", C.c_uint32),
+        ("positions", _fp), ("normals", _fp), ("texcoords", _fp), ("faces", _up),
+        ("bsdf", C.c_uint32), ("emitter", C.c_int32), ("flip_normals", C.c_uint32), ("kind", C.c_uint32),
+        ("rect_to_world", C.c_float * 12),
+    ]
+
+
+class Instance(C.Structure):
+    _fields_ = [
+        ("first_mesh", C.c_uint32), ("n_meshes", C.c_uint32), ("animated", C.c_uint32),
+        ("t0", C.c_float), ("t1", C.c_float),
+        ("m0", C.c_float * 12), ("m1", C.c_float * 12),
+    ]
+
+
+class Bsdf(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("twosided", C.c_uint32), ("reflectance", C.c_float * 3)]
+
+
+class Emitter(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("mesh", C.c_uint32), ("position", C.c_float * 3), ("value", C.c_float * 3)]
+
+
+class Camera(C.Structure):
+    _fields_ = [
+        ("to_world", C.c_float * 12), ("sample_to_camera", C.c_float * 16),
+        ("near_clip", C.c_float), ("far_clip", C.c_float),
+        ("shutter_open", C.c_float), ("shutter_open_time", C.c_float),
+    ]
+
+
+class Film(C.Structure):
+    _fields_ = [
+        ("width", C.c_uint32), ("height", C.c_uint32),
+        ("crop_offset_x", C.c_uint32), ("crop_offset_y", C.c_uint32),
+        ("rfilter", C.c_uint32), ("rfilter_radius", C.c_float), ("gaussian_stddev", C.c_float),
+    ]
+
+
+class SceneDesc(C.Structure):
+    _fields_ = [
+        ("n_meshes", C.c_uint32), ("meshes", C.POINTER(Mesh)),
+        ("n_instances", C.c_uint32), ("instances", C.POINTER(Instance)),
+        ("n_bsdfs", C.c_uint32), ("bsdfs", C.POINTER(Bsdf)),
+        ("n_emitters", C.c_uint32), ("emitters", C.POINTER(Emitter)),
+        ("camera", Camera), ("film", Film),
+    ]
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("time", C.c_float), ("w_g", C.c_float), ("g_1", C.c_float), ("g_0", C.c_float),
+        ("sensor_phase_offset", C.c_float), ("hetero_frequency", C.c_float),
+        ("wave_function_type", C.c_uint32), ("low_frequency_component_only", C.c_uint32),
+        ("max_depth", C.c_int32), ("rr_depth", C.c_int32), ("hide_emitters", C.c_uint32),
+        ("time_sampling_method", C.c_uint32), ("antithetic_shift", C.c_float),
+        ("use_stratified_sampling_for_each_interval", C.c_uint32), ("path_correlation_depth", C.c_uint32),
+        ("sample_count", C.c_uint32), ("base_seed", C.c_uint32),
+        ("time_correlate_number", C.c_uint32), ("path_correlate_number", C.c_uint32),
+        ("seed", C.c_uint32),
+        ("lane_begin", C.c_uint64), ("lane_end", C.c_uint64),
+    ]
+
+
+class SampleRecord(C.Structure):
+    _fields_ = [
+        ("sample_pos", C.c_float * 2), ("time", C.c_float),
+        ("ray_o", C.c_float * 3), ("ray_d", C.c_float * 3), ("ray_maxt", C.c_float),
+        ("rgb", C.c_float * 3), ("path_length", C.c_float),
+        ("depth", C.c_uint32), ("rng_draws", C.c_uint32),
+    ]
+
+
+SAMPLE_RECORD_DTYPE = np.dtype([
+    ("sample_pos", np.float32, 2), ("time", np.float32),
+    ("ray_o", np.float32, 3), ("ray_d", np.float32, 3), ("ray_maxt", np.float32),
+    ("rgb", np.float32, 3), ("path_length", np.float32),
+    ("depth", np.uint32), ("rng_draws", np.uint32),
+])
+assert SAMPLE_RECORD_DTYPE.itemsize == C.sizeof(SampleRecord)
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("samples", C.c_uint64), ("rays_closest", C.c_uint64), ("rays_shadow", C.c_uint64),
+        ("nodes_visited", C.c_uint64), ("tris_tested", C.c_uint64), ("inst_visits", C.c_uint64),
+    ]
+
+
+class PassInfo(C.Structure):
+    _fields_ = [("spp_per_pass", C.c_uint32), ("n_passes", C.c_uint32), ("wavefront_size", C.c_uint64)]
+
+
+# every symbol include/dtof.h declares: name -> (restype, argtypes)
+_ctx = C.c_void_p
+DTOF_SYMBOLS = {
+    "dtof_abi_version": (C.c_uint32, []),
+    "dtof_create": (C.c_int, [C.POINTER(_ctx), C.c_int]),
+    "dtof_destroy": (None, [_ctx]),
+    "dtof_last_error": (C.c_char_p, [_ctx]),
+    "dtof_upload_scene": (C.c_int, [_ctx, C.POINTER(SceneDesc)]),
+    "dtof_update_instances": (C.c_int, [_ctx, C.c_uint32, C.c_uint32, C.POINTER(Instance)]),
+    "dtof_pass_info_for": (C.c_int, [_ctx, C.POINTER(Params), C.POINTER(PassInfo)]),
+    "dtof_render": (C.c_int, [_ctx, C.POINTER(Params), _fp, _fp]),
+    "dtof_render_device": (C.c_int, [_ctx, C.POINTER(Params), C.c_void_p, C.c_void_p]),
+    "dtof_develop_device": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dtof_trace_samples": (C.c_int, [_ctx, C.POINTER(Params), C.POINTER(C.c_uint64), C.c_uint32,
+                                     C.POINTER(SampleRecord)]),
+    "dtof_set_stats": (C.c_int, [_ctx, C.c_int]),
+    "dtof_get_stats": (C.c_int, [_ctx, C.POINTER(Stats)]),
+    "dtof_launch_count": (C.c_uint64, [_ctx]),
+    "dtof_last_kernel_ms": (C.c_int, [_ctx, C.POINTER(C.c_float)]),
+}
+
+
+def bind(lib: C.CDLL, symbols=DTOF_SYMBOLS) -> None:
+    for name, (res, args) in symbols.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export it
+        fn.restype = res
+        fn.argtypes = args
+
+
+def as_fp(a: np.ndarray):
+    return a.ctypes.data_as(_fp)
+
+
+def as_up(a: np.ndarray):
+    return a.ctypes.data_as(_up)

@@ -1,0 +1,146 @@
+"""`dopplertofpath` integrator: the reference's plugin surface over the CUDA library.
+
+Property names, defaults and derived values follow
+  src/integrators/dopplertofpath.cpp:19-57      (time, w_g, g_1, g_0, w_s, sensor_phase_offset, hetero_offset,
+                                                 hetero_frequency, wave_function_type, low_frequency_component_only)
+  src/render/integrator.cpp:24-27,54-100,568-585 (timeout, hide_emitters, is_doppler_integrator,
+                                                 time_sampling_method, antithetic_shift,
+                                                 use_stratified_sampling_for_each_interval, path_correlation_depth,
+                                                 block_size, samples_per_pass, max_depth, rr_depth)
+`render(scene, seed=0, spp=0, develop=True)` mirrors `Integrator::render` (src/render/integrator.cpp:104-347;
+python usage doppler_tutorials/src/program_runner.py:11-31). Unknown `time_sampling_method` /
+`wave_function_type` strings raise (the reference leaves the enum uninitialised).
+Unknown properties raise like the XML loader's "unreferenced property" check (src/core/xml.cpp:1204-1223).
+
+The product path is CUDA only: `render` raises if libdtof_b200.so or a GPU is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional
+
+import numpy as np
+
+from . import _abi
+
+__all__ = ["DopplerToFPathIntegrator", "DTOFError"]
+
+f32 = np.float32
+
+_TIME = {"uniform": _abi.TIME_UNIFORM, "stratified": _abi.TIME_STRATIFIED, "antithetic": _abi.TIME_ANTITHETIC,
+         "antithetic_mirror": _abi.TIME_ANTITHETIC_MIRROR}
+_WAVE = {"sinusoidal": _abi.WAVE_SINUSOIDAL, "rectangular": _abi.WAVE_RECTANGULAR,
+         "triangular": _abi.WAVE_TRIANGULAR, "trapezoidal": _abi.WAVE_TRAPEZOIDAL}
+
+_KNOWN = {
+    "time", "w_g", "g_1", "g_0", "w_s", "sensor_phase_offset", "hetero_offset", "hetero_frequency",
+    "wave_function_type", "low_frequency_component_only", "max_depth", "rr_depth", "hide_emitters", "timeout",
+    "is_doppler_integrator", "time_sampling_method", "antithetic_shift", "use_stratified_sampling_for_each_interval",
+    "path_correlation_depth", "block_size", "samples_per_pass",
+}
+
+
+class DTOFError(RuntimeError):
+    pass
+
+
+class DopplerToFPathIntegrator:
+    def __init__(self, **props):
+        unknown = set(props) - _KNOWN
+        if unknown:
+            raise ValueError(f"dopplertofpath: unreferenced propert{'ies' if len(unknown) > 1 else 'y'} {sorted(unknown)}")
+        g = props.get
+        # --- DopplerToFPathIntegrator ctor (all ScalarFloat = float32)
+        self.time = f32(g("time", 0.0015))
+        self.w_g = f32(g("w_g", 30.0))
+        self.g_1 = f32(g("g_1", 0.5))
+        self.g_0 = f32(g("g_0", 0.5))
+        self.w_s = f32(g("w_s", 30.0))
+        self.sensor_phase_offset = f32(g("sensor_phase_offset", 0.0))
+        if "hetero_offset" in props:      # :32-34  (float * int * double -> double -> float)
+            self.sensor_phase_offset = f32(float(f32(props["hetero_offset"])) * 2 * math.pi)
+        if "hetero_frequency" in props:   # :35-37
+            self.hetero_frequency = f32(props["hetero_frequency"])
+            self.w_s = f32(float(self.w_g) + float(f32(self.hetero_frequency / self.time)) * 1e-6)
+        else:                             # :38-40
+            self.hetero_frequency = f32(float(f32(self.w_s - self.w_g)) * 1e6 * float(self.time))
+        wave = g("wave_function_type", "sinusoidal")
+        if wave not in _WAVE:
+            raise ValueError(f"dopplertofpath: unknown wave_function_type '{wave}'")
+        self.wave_function_type = wave
+        self.low_frequency_component_only = bool(g("low_frequency_component_only", True))
+        # --- SamplingIntegrator ctor
+        self.is_doppler_integrator = True
+        method = g("time_sampling_method", "antithetic")
+        if method not in _TIME:
+            raise ValueError(f"dopplertofpath: unknown time_sampling_method '{method}'")
+        self.time_sampling_method = method
+        default_shift = 0.5 if method == "antithetic" else 0.0
+        self.antithetic_shift = f32(g("antithetic_shift", default_shift))
+        self.use_stratified_sampling_for_each_interval = bool(g("use_stratified_sampling_for_each_interval", True))
+        self.path_correlation_depth = int(g("path_correlation_depth", 0))
+        self.block_size = int(g("block_size", 0))
+        self.samples_per_pass = g("samples_per_pass", None)
+        if self.samples_per_pass is not None:
+            raise ValueError("'samples_per_pass' is deprecated in the reference and unsupported here")
+        # --- MonteCarloIntegrator ctor (:568-585)
+        max_depth = int(g("max_depth", -1))
+        if max_depth < 0 and max_depth != -1:
+            raise ValueError("\"max_depth\" must be set to -1 (infinite) or a value >= 0")
+        self.max_depth = max_depth
+        rr_depth = int(g("rr_depth", 5))
+        if rr_depth <= 0:
+            raise ValueError("\"rr_depth\" must be set to a value greater than zero!")
+        self.rr_depth = rr_depth
+        # --- Integrator ctor
+        self.hide_emitters = bool(g("hide_emitters", False))
+        self.timeout = float(g("timeout", -1.0))
+        self._stop = False
+
+    # ---------------------------------------------------------------------------------------
+    def params(self, sampler, seed: int = 0, spp: int = 0, lane_begin: int = 0, lane_end: int = 0) -> _abi.Params:
+        """Pack the C-ABI parameter block for one render() call."""
+        p = _abi.Params()
+        p.time, p.w_g, p.g_1, p.g_0 = float(self.time), float(self.w_g), float(self.g_1), float(self.g_0)
+        p.sensor_phase_offset = float(self.sensor_phase_offset)
+        p.hetero_frequency = float(self.hetero_frequency)
+        p.wave_function_type = _WAVE[self.wave_function_type]
+        p.low_frequency_component_only = int(self.low_frequency_component_only)
+        p.max_depth, p.rr_depth, p.hide_emitters = self.max_depth, self.rr_depth, int(self.hide_emitters)
+        p.time_sampling_method = _TIME[self.time_sampling_method]
+        p.antithetic_shift = float(self.antithetic_shift)
+        p.use_stratified_sampling_for_each_interval = int(self.use_stratified_sampling_for_each_interval)
+        p.path_correlation_depth = self.path_correlation_depth
+        p.sample_count = int(spp) if spp else int(sampler.sample_count)   # integrator.cpp:121-124
+        p.base_seed = int(sampler.seed) & 0xFFFFFFFF
+        p.time_correlate_number = int(sampler.time_correlate_number)
+        p.path_correlate_number = int(sampler.path_correlate_number)
+        p.seed = int(seed) & 0xFFFFFFFF
+        p.lane_begin, p.lane_end = int(lane_begin), int(lane_end)
+        if self.time_sampling_method == "antithetic_mirror" and p.time_correlate_number != 2:
+            raise ValueError("antithetic_mirror requires time_correlate_number == 2")  # correlated.cpp:141-142
+        if p.time_correlate_number < 1 or p.path_correlate_number < 1:
+            raise ValueError("correlate numbers must be >= 1")
+        return p
+
+    def cancel(self) -> None:
+        self._stop = True
+
+    def should_stop(self) -> bool:
+        return self._stop
+
+    def render(self, scene, seed: int = 0, spp: int = 0, develop: bool = True, evaluate: bool = True,
+               device: Optional[int] = None) -> np.ndarray:
+        """Render `scene` (a scene.Scene) on the GPU; returns the developed (H, W, 3) image, or the raw
+        (H, W, 4) RGBW accumulation tensor when ``develop=False``. Host buffers in, host buffers out."""
+        from .runtime import get_context   # deferred: importing the package must not need a GPU
+        self._stop = False
+        ctx = get_context(device)
+        flat = ctx.upload(scene)
+        p = self.params(scene.sensor.sampler, seed, spp)
+        return ctx.render(flat, p, develop=develop)
+
+    def __repr__(self):
+        return (f"DopplerToFPathIntegrator[\n  max_depth = {self.max_depth & 0xFFFFFFFF},\n"
+                f"  rr_depth = {self.rr_depth}\n]")

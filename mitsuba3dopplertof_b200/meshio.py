@@ -1,0 +1,149 @@
+"""PLY / OBJ readers for the host-side scene ingest.
+
+Behaviour follows the reference loaders for the parts the hot path observes:
+  * src/shapes/ply.cpp: vertex x/y/z, optional nx/ny/nz, optional u/v (or s/t), faces as lists, polygons fan-
+    triangulated; when the file has no normals and `face_normals` is false the reference computes smooth
+    vertex normals (Mesh::recompute_vertex_normals, src/render/mesh.cpp:283-345) -- done here with the
+    same angle weighting.
+  * src/shapes/obj.cpp: v / vt / vn / f with index triplets, vertices de-duplicated per (v,vt,vn) key.
+"""
+from __future__ import annotations
+
+import struct
+from typing import Optional, Tuple
+
+import numpy as np
+
+__all__ = ["load_mesh", "load_ply", "load_obj", "vertex_normals"]
+
+_PLY_TYPES = {
+    "char": "b", "int8": "b", "uchar": "B", "uint8": "B", "short": "h", "int16": "h", "ushort": "H", "uint16": "H",
+    "int": "i", "int32": "i", "uint": "I", "uint32": "I", "float": "f", "float32": "f", "double": "d", "float64": "d",
+}
+
+
+def vertex_normals(pos: np.ndarray, faces: np.ndarray) -> np.ndarray:
+    """Angle-weighted smooth normals ("Computing Vertex Normals from Polygonal Facets", Thuermer & Wuethrich),
+    as Mesh::recompute_vertex_normals does."""
+    p = pos.astype(np.float64)
+    n = np.zeros_like(p)
+    v0, v1, v2 = p[faces[:, 0]], p[faces[:, 1]], p[faces[:, 2]]
+    fn = np.cross(v1 - v0, v2 - v0)
+    ln = np.linalg.norm(fn, axis=1, keepdims=True)
+    fn = np.where(ln > 0, fn / np.maximum(ln, 1e-300), 0)
+    for k in range(3):
+        a = p[faces[:, k]]
+        d0 = p[faces[:, (k + 1) % 3]] - a
+        d1 = p[faces[:, (k + 2) % 3]] - a
+        d0 /= np.maximum(np.linalg.norm(d0, axis=1, keepdims=True), 1e-300)
+        d1 /= np.maximum(np.linalg.norm(d1, axis=1, keepdims=True), 1e-300)
+        ang = np.arccos(np.clip((d0 * d1).sum(1), -1, 1))
+        np.add.at(n, faces[:, k], fn * ang[:, None])
+    ln = np.linalg.norm(n, axis=1, keepdims=True)
+    n = np.where(ln > 0, n / np.maximum(ln, 1e-300), np.array([1.0, 0.0, 0.0]))
+    return n.astype(np.float32)
+
+
+def load_ply(path: str):
+    with open(path, "rb") as f:
+        if f.readline().strip() != b"ply":
+            raise ValueError(f"{path}: not a PLY file")
+        fmt = None
+        elements = []
+        while True:
+            line = f.readline()
+            if not line:
+                raise ValueError(f"{path}: truncated PLY header")
+            tok = line.decode("ascii", "replace").split()
+            if not tok or tok[0] == "comment":
+                continue
+            if tok[0] == "format":
+                fmt = tok[1]
+            elif tok[0] == "element":
+                elements.append([tok[1], int(tok[2]), []])
+            elif tok[0] == "property":
+                elements[-1][2].append(tok[1:])
+            elif tok[0] == "end_header":
+                break
+        endian = {"ascii": None, "binary_little_endian": "<", "binary_big_endian": ">"}[fmt]
+        verts = {}
+        faces = []
+        for name, count, props in elements:
+            scalar = all(p[0] != "list" for p in props)
+            if endian is None:
+                rows = [f.readline().split() for _ in range(count)]
+                if name == "vertex":
+                    arr = np.array(rows, dtype=np.float64)
+                    for i, p in enumerate(props):
+                        verts[p[-1]] = arr[:, i]
+                elif name == "face":
+                    for r in rows:
+                        k = int(r[0])
+                        idx = [int(x) for x in r[1:1 + k]]
+                        faces += [(idx[0], idx[i], idx[i + 1]) for i in range(1, k - 1)]
+            else:
+                if scalar:
+                    dt = np.dtype([(p[-1], endian + _PLY_TYPES[p[0]]) for p in props])
+                    arr = np.frombuffer(f.read(dt.itemsize * count), dtype=dt)
+                    if name == "vertex":
+                        for p in props:
+                            verts[p[-1]] = arr[p[-1]].astype(np.float64)
+                else:
+                    for _ in range(count):
+                        for p in props:
+                            if p[0] == "list":
+                                ct, it = _PLY_TYPES[p[1]], _PLY_TYPES[p[2]]
+                                k = struct.unpack(endian + ct, f.read(struct.calcsize(ct)))[0]
+                                idx = struct.unpack(endian + it * k, f.read(struct.calcsize(it) * k))
+                                if name == "face" and p[-1] in ("vertex_indices", "vertex_index"):
+                                    faces += [(idx[0], idx[i], idx[i + 1]) for i in range(1, k - 1)]
+                            else:
+                                f.read(struct.calcsize(_PLY_TYPES[p[0]]))
+    pos = np.stack([verts["x"], verts["y"], verts["z"]], 1).astype(np.float32)
+    nrm = np.stack([verts["nx"], verts["ny"], verts["nz"]], 1).astype(np.float32) if "nx" in verts else None
+    uv = None
+    for a, b in (("u", "v"), ("s", "t"), ("texture_u", "texture_v")):
+        if a in verts:
+            uv = np.stack([verts[a], verts[b]], 1).astype(np.float32)
+            break
+    return pos, np.asarray(faces, np.uint32).reshape(-1, 3), nrm, uv
+
+
+def load_obj(path: str):
+    v, vt, vn, keys, faces = [], [], [], {}, []
+    out_p, out_t, out_n = [], [], []
+    with open(path, "r") as f:
+        for line in f:
+            tok = line.split()
+            if not tok:
+                continue
+            if tok[0] == "v":
+                v.append([float(x) for x in tok[1:4]])
+            elif tok[0] == "vt":
+                vt.append([float(tok[1]), float(tok[2])])   # obj.cpp keeps v as is (no flip)
+            elif tok[0] == "vn":
+                vn.append([float(x) for x in tok[1:4]])
+            elif tok[0] == "f":
+                idx = []
+                for t in tok[1:]:
+                    parts = (t.split("/") + ["", ""])[:3]
+                    key = tuple((int(p) if p else 0) for p in parts)
+                    key = tuple((k + (len(a) + 1) if k < 0 else k) for k, a in zip(key, (v, vt, vn)))
+                    if key not in keys:
+                        keys[key] = len(out_p)
+                        out_p.append(v[key[0] - 1])
+                        out_t.append(vt[key[1] - 1] if key[1] else None)
+                        out_n.append(vn[key[2] - 1] if key[2] else None)
+                    idx.append(keys[key])
+                faces += [(idx[0], idx[i], idx[i + 1]) for i in range(1, len(idx) - 1)]
+    pos = np.asarray(out_p, np.float32)
+    uv = np.asarray(out_t, np.float32) if out_t and all(t is not None for t in out_t) else None
+    nrm = np.asarray(out_n, np.float32) if out_n and all(n is not None for n in out_n) else None
+    return pos, np.asarray(faces, np.uint32).reshape(-1, 3), nrm, uv
+
+
+def load_mesh(path: str, face_normals: bool = False) -> Tuple[np.ndarray, np.ndarray, Optional[np.ndarray], Optional[np.ndarray]]:
+    pos, faces, nrm, uv = load_ply(path) if path.lower().endswith(".ply") else load_obj(path)
+    if nrm is None and not face_normals:
+        nrm = vertex_normals(pos, faces)
+    return pos, faces, nrm, uv

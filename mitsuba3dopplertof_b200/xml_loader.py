@@ -1,0 +1,271 @@
+"""Minimal scene-XML reader for the subset the hot path needs, so a reference `scene.xml`
+(e.g. configs_example/scene.xml) loads unchanged.
+
+Follows src/core/xml.cpp: `<default>` + `$name` substitution (:300-330, command-line `-Dk=v` overrides),
+`<transform>` ops composed by LEFT-multiplication in double precision (:820-1007), `<animation>` with
+`<transform time=..>` keyframes (:520-524,882-900,996-1007), `<ref id>` resolution, and the rewrite of a
+shape with an animated `to_world` into shapegroup + instance (:1166-1192; done in scene.Scene.flatten).
+Anything outside the hot-path scope raises.
+"""
+from __future__ import annotations
+
+import os
+import re
+import xml.etree.ElementTree as ET
+from typing import Dict, Optional
+
+import numpy as np
+
+from .integrator import DopplerToFPathIntegrator
+from .scene import (Bsdf, CorrelatedSampler, Film, PerspectiveSensor, PointLight, Scene, Shape)
+from .transform import AnimatedTransform, Transform4
+
+__all__ = ["load_file", "load_string"]
+
+
+def _floats(s: str):
+    return [float(t) for t in re.split(r"[\s,]+", s.strip()) if t]
+
+
+class _Loader:
+    def __init__(self, params: Optional[Dict[str, str]], base_dir: str):
+        self.defaults: Dict[str, str] = dict(params or {})
+        self.cli = set(self.defaults)
+        self.base_dir = base_dir
+        self.bsdfs: Dict[str, Bsdf] = {}
+
+    def sub(self, s: str) -> str:
+        def rep(m):
+            k = m.group(1)
+            if k not in self.defaults:
+                raise ValueError(f"undefined parameter ${k}")
+            return self.defaults[k]
+        return re.sub(r"\$(\w+)", rep, s)
+
+    def attr(self, node, name, default=None):
+        v = node.get(name)
+        return default if v is None else self.sub(v)
+
+    # ---- values -----------------------------------------------------------------------------------
+    def props(self, node, skip=()):
+        out = {}
+        for ch in node:
+            if ch.tag in skip:
+                continue
+            n = ch.get("name")
+            if ch.tag == "float":
+                out[n] = float(self.attr(ch, "value"))
+            elif ch.tag == "integer":
+                out[n] = int(self.attr(ch, "value"))
+            elif ch.tag == "boolean":
+                out[n] = self.attr(ch, "value").strip().lower() == "true"
+            elif ch.tag == "string":
+                out[n] = self.attr(ch, "value")
+            elif ch.tag in ("rgb", "spectrum"):
+                v = _floats(self.attr(ch, "value"))
+                if len(v) not in (1, 3):
+                    raise ValueError(f"<{ch.tag}> '{n}': only constant / RGB values are in scope")
+                out[n] = tuple(v * 3) if len(v) == 1 else tuple(v)
+            elif ch.tag in ("point", "vector"):
+                out[n] = self.vec(ch)
+        return out
+
+    def vec(self, node, default=0.0):
+        if node.get("value") is not None:
+            v = _floats(self.attr(node, "value"))
+            return tuple(v * 3) if len(v) == 1 else tuple(v)
+        return tuple(float(self.attr(node, k, default)) for k in "xyz")
+
+    def transform(self, node) -> Transform4:
+        t = Transform4.identity(np.float64)
+        for op in node:
+            if op.tag == "matrix":
+                v = _floats(self.attr(op, "value"))
+                if len(v) == 9:
+                    m = np.eye(4)
+                    m[:3, :3] = np.array(v).reshape(3, 3)
+                    v = m.reshape(16)
+                if len(v) != 16:
+                    raise ValueError("matrix: expected 16 or 9 values")
+                # stof<Float=double> then Transform4f(matrix) in double
+                o = Transform4.from_matrix(v)
+            elif op.tag == "translate":
+                o = Transform4.translate(self.vec(op))
+            elif op.tag == "scale":
+                o = Transform4.scale(self.vec(op, 1.0))
+            elif op.tag == "rotate":
+                o = Transform4.rotate(self.vec(op), float(self.attr(op, "angle")))
+            elif op.tag in ("lookat", "look_at"):
+                origin, target = _floats(self.attr(op, "origin")), _floats(self.attr(op, "target"))
+                up = _floats(self.attr(op, "up", "0,0,0"))
+                if not any(up):
+                    raise ValueError("lookat without 'up' is outside the supported subset")
+                o = Transform4.look_at(origin, target, up)
+            else:
+                raise ValueError(f"unsupported transform op <{op.tag}>")
+            t = o @ t
+        return t
+
+    def animation(self, node) -> AnimatedTransform:
+        at = AnimatedTransform()
+        for kf in node:
+            if kf.tag != "transform":
+                raise ValueError("<animation> may only contain <transform time=..> keyframes")
+            at.append(float(self.attr(kf, "time")), self.transform(kf))
+        return at
+
+    # ---- objects ----------------------------------------------------------------------------------
+    def bsdf(self, node) -> Bsdf:
+        typ = self.attr(node, "type")
+        if typ == "twosided":
+            inner = [c for c in node if c.tag in ("bsdf", "ref")]
+            if len(inner) != 1:
+                raise ValueError("twosided with two different BRDFs is outside the hot-path scope")
+            b = self.bsdf_or_ref(inner[0])
+            return Bsdf(b.reflectance, True, b.kind)
+        if typ == "diffuse":
+            p = self.props(node)
+            unknown = set(p) - {"reflectance"}
+            if unknown:
+                raise ValueError(f"diffuse: unreferenced property {sorted(unknown)}")
+            return Bsdf(p.get("reflectance", (0.5, 0.5, 0.5)), False)
+        raise ValueError(f"bsdf type '{typ}' is outside the hot-path scope (diffuse|twosided)")
+
+    def bsdf_or_ref(self, node) -> Bsdf:
+        if node.tag == "ref":
+            rid = self.attr(node, "id")
+            if rid not in self.bsdfs:
+                raise ValueError(f"reference to unknown id '{rid}'")
+            return self.bsdfs[rid]
+        return self.bsdf(node)
+
+    def shape(self, node) -> Shape:
+        typ = self.attr(node, "type")
+        p = self.props(node)
+        sh = Shape({"rectangle": "rectangle", "cube": "cube", "obj": "mesh", "ply": "mesh"}.get(typ, typ),
+                   id=node.get("id", ""))
+        sh.flip_normals = bool(p.pop("flip_normals", False))
+        for ch in node:
+            if ch.tag == "transform" and ch.get("name") == "to_world":
+                sh.to_world = self.transform(ch)
+            elif ch.tag == "animation" and ch.get("name") == "to_world":
+                sh.to_world = self.animation(ch)
+            elif ch.tag in ("bsdf", "ref"):
+                sh.bsdf = self.bsdf_or_ref(ch)
+            elif ch.tag == "emitter":
+                if self.attr(ch, "type") != "area":
+                    raise ValueError("only 'area' emitters can be attached to shapes")
+                sh.radiance = self.props(ch).get("radiance", (1.0, 1.0, 1.0))
+        if typ in ("obj", "ply"):
+            from .meshio import load_mesh
+            fn = p.pop("filename")
+            face_normals = bool(p.pop("face_normals", False))
+            pos, faces, nrm, uv = load_mesh(os.path.join(self.base_dir, fn), face_normals=face_normals)
+            if face_normals:
+                nrm = None
+            sh.positions, sh.faces, sh.normals, sh.texcoords = pos, faces, nrm, uv
+        elif typ not in ("rectangle", "cube"):
+            raise ValueError(f"shape type '{typ}' is outside the hot-path scope (rectangle|cube|obj|ply)")
+        if p:
+            raise ValueError(f"shape '{typ}': unreferenced property {sorted(p)}")
+        return sh
+
+    def sensor(self, node) -> PerspectiveSensor:
+        if self.attr(node, "type") != "perspective":
+            raise ValueError("only the 'perspective' sensor is in the hot-path scope")
+        p = self.props(node)
+        s = PerspectiveSensor()
+        for ch in node:
+            if ch.tag == "transform" and ch.get("name") == "to_world":
+                s.to_world = self.transform(ch)
+            elif ch.tag == "sampler":
+                if self.attr(ch, "type") != "correlated":
+                    raise ValueError("dopplertofpath is driven by the 'correlated' sampler (README.md:61)")
+                sp = self.props(ch)
+                s.sampler = CorrelatedSampler(int(sp.pop("sample_count", 4)), int(sp.pop("seed", 0)),
+                                              int(sp.pop("time_correlate_number", 2)), sp.pop("path_correlate_number", None))
+                if sp:   # e.g. use_stratified_sampling_for_each_interval is an INTEGRATOR property
+                    raise ValueError(f"correlated sampler: unreferenced property {sorted(sp)}")
+            elif ch.tag == "film":
+                fp = self.props(ch)
+                f = Film(int(fp.pop("width", 768)), int(fp.pop("height", 576)))
+                if "crop_width" in fp or "crop_height" in fp:
+                    f.crop_size = (int(fp.pop("crop_width", f.width)), int(fp.pop("crop_height", f.height)))
+                    f.crop_offset = (int(fp.pop("crop_offset_x", 0)), int(fp.pop("crop_offset_y", 0)))
+                for k in ("file_format", "pixel_format", "component_format", "sample_border", "compensate"):
+                    fp.pop(k, None)
+                if fp:
+                    raise ValueError(f"hdrfilm: unreferenced property {sorted(fp)}")
+                for rf in ch:
+                    if rf.tag == "rfilter":
+                        f.rfilter = self.attr(rf, "type")
+                        rp = self.props(rf)
+                        f.rfilter_radius = rp.get("radius")
+                        f.gaussian_stddev = float(rp.get("stddev", 0.5))
+                s.film = f
+        s.fov = float(p.pop("fov", 45.0)) if "fov" in p else s.fov
+        s.fov_axis = p.pop("fov_axis", "x")
+        s.near_clip = float(p.pop("near_clip", 1e-2))
+        s.far_clip = float(p.pop("far_clip", 1e4))
+        s.shutter_open = float(p.pop("shutter_open", 0.0))
+        s.shutter_close = float(p.pop("shutter_close", 0.0))
+        if p:
+            raise ValueError(f"perspective: unreferenced property {sorted(p)}")
+        return s
+
+    def load(self, root) -> Scene:
+        if root.tag != "scene":
+            raise ValueError("root element must be <scene>")
+        sc = Scene()
+        order = []
+        for node in root:
+            if node.tag == "default":
+                k = node.get("name")
+                if k not in self.cli:
+                    self.defaults[k] = self.sub(node.get("value"))
+            elif node.tag == "integrator":
+                typ = self.attr(node, "type")
+                if typ != "dopplertofpath":
+                    raise ValueError(f"integrator '{typ}' is outside the hot-path scope (dopplertofpath)")
+                sc.integrator = DopplerToFPathIntegrator(**self.props(node))
+            elif node.tag == "sensor":
+                sc.sensor = self.sensor(node)
+            elif node.tag == "bsdf":
+                b = self.bsdf(node)
+                if node.get("id"):
+                    self.bsdfs[node.get("id")] = b
+            elif node.tag == "shape":
+                order.append(("shape", len(sc.shapes)))
+                sc.shapes.append(self.shape(node))
+            elif node.tag == "emitter":
+                typ = self.attr(node, "type")
+                if typ != "point":
+                    raise ValueError(f"emitter '{typ}' is outside the hot-path scope (point|area)")
+                p = self.props(node)
+                pos = p.get("position")
+                for ch in node:
+                    if ch.tag == "transform" and ch.get("name") == "to_world":
+                        if pos is not None:
+                            raise ValueError("Only one of the parameters 'position' and 'to_world' can be specified")
+                        pos = tuple(self.transform(ch).astype(np.float32).matrix[:3, 3].tolist())
+                order.append(("emitter", len(sc.emitters)))
+                sc.emitters.append(PointLight(pos if pos is not None else (0.0, 0.0, 0.0), p.get("intensity", (1.0,) * 3)))
+            else:
+                raise ValueError(f"unsupported top-level element <{node.tag}>")
+        unused = self.cli - set(re.findall(r"\$(\w+)", ET.tostring(root, encoding="unicode")))
+        if unused:   # xml.cpp:1069 'Unused parameter'
+            raise ValueError(f"Unused parameter \"{sorted(unused)[0]}\"!")
+        sc.scene_order = order
+        if sc.integrator is None:
+            raise ValueError("scene has no integrator")
+        return sc
+
+
+def load_file(path: str, **params) -> Scene:
+    """`mi.load_file(path, **params)`: params override `<default>` values like `-Dkey=value`."""
+    tree = ET.parse(path)
+    return _Loader({k: str(v) for k, v in params.items()}, os.path.dirname(os.path.abspath(path))).load(tree.getroot())
+
+
+def load_string(xml: str, base_dir: str = ".", **params) -> Scene:
+    return _Loader({k: str(v) for k, v in params.items()}, base_dir).load(ET.fromstring(xml))

@@ -264,6 +264,19 @@ int main(int argc, char **argv) {
                                                   integ->m_use_stratified_sampling_for_each_interval) *
                             sensor->shutter_open_time();
                 auto [ray, ray_weight] = sensor->sample_ray_differential(time, 0.f, Point2f(adjusted), Point2f(.5f));
+                if (getenv("DTOF_DEBUG")) {
+                    // debug aid: primary surface interaction + emitter sample as the reference computes them
+                    mi::Ray<mi::Point<float, 3>, S> r2(ray);
+                    r2.time = time < 0.0015f ? time : time - 0.0015f;
+                    auto si = scene->ray_intersect(r2, +mi::RayFlags::All, true);
+                    fprintf(stderr, "  si.t=%.9g p=(%.9g %.9g %.9g) n=(%.9g %.9g %.9g) shn=(%.9g %.9g %.9g) s=(%.9g %.9g %.9g) wi=(%.9g %.9g %.9g)\n",
+                            si.t, si.p.x(), si.p.y(), si.p.z(), si.n.x(), si.n.y(), si.n.z(), si.sh_frame.n.x(),
+                            si.sh_frame.n.y(), si.sh_frame.n.z(), si.sh_frame.s.x(), si.sh_frame.s.y(), si.sh_frame.s.z(),
+                            si.wi.x(), si.wi.y(), si.wi.z());
+                    auto [ds, w] = scene->sample_emitter_direction(si, Point2f(0.3f, 0.6f), true, true);
+                    fprintf(stderr, "  ds.p=(%.9g %.9g %.9g) d=(%.9g %.9g %.9g) dist=%.9g pdf=%.9g w=(%.9g %.9g %.9g)\n", ds.p.x(),
+                            ds.p.y(), ds.p.z(), ds.d.x(), ds.d.y(), ds.d.z(), ds.dist, ds.pdf, w.x(), w.y(), w.z());
+                }
                 auto [spec, valid] = integ->sample(scene, sampler.get(), ray, nullptr, aovs, true);
                 S rgb = ray_weight * spec;
                 printf("%u %u %u %u %.9g %.9g %.9g %.9g %.9g %.9g %.9g %.9g %.9g %.9g %.9g %.9g %.9g\n", idx, pass, px, py,

@@ -1,0 +1,133 @@
+#!/usr/bin/env python
+"""Fixture generator (runs only in the build container; NOT a test).
+
+Produces tests/golden/lanes_<case>.json by running the REFERENCE's own compiled code
+(oracle/_ref: libmitsuba.so + plugins built from /root/reference, scalar_rgb + Embree) through
+oracle/ref_harness/replay_harness.cpp, which feeds `DopplerToFPathIntegrator::sample()` the sample
+streams of the reference's JIT variants lane by lane.
+
+Time scaling. The scalar Embree glue stores ray.time in the ray's *tnear* slot
+(src/render/scene_embree.inl:226,369) and the user-geometry callback (rectangles) returns a hit
+distance shortened by tnear (src/render/shape.cpp:141-147). The JIT variants pass mint = 0
+(scene_embree.inl:287,405), so this is a scalar-only artefact. To get JIT-faithful numbers out of
+the scalar build the reference is run with ALL times (integrator `time`, shutter, keyframes)
+multiplied by 2^-20: every quantity the path computes is invariant under a power-of-two time scale
+(w_d*t, the keyframe fraction, ...) bit for bit, while the artefact shrinks below half an ulp of t.
+Full-waveform mode (low_frequency_component_only=false) is not scale invariant (w_g*t) and is
+therefore generated unscaled on `c5_slabroom.xml`, whose walls are triangle meshes (no user geometry).
+
+Also writes header_vectors.json (reference header templates) and scene_exr.npy (the reference's
+committed configs_example/scene.exr) when the inputs are available.
+"""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF_RT = os.path.join(ROOT, "oracle", "_ref")
+SCENES = os.path.join(ROOT, "tests", "scenes")
+T = np.float32(0.0015)
+SCALE = np.float32(2.0 ** -20)
+
+# name -> (scene, xml params, harness seed, time-scaled?)   [tcn/pcn/spp/res live in the xml params]
+CASES = {
+    "c1_hetero": ("c1_example", {}, 0, True),
+    "c1_homodyne": ("c1_example", {"hetero_frequency": 0.0}, 0, True),
+    "c1_rect_strat_pcn4": ("c1_example", {"wave": "rectangular", "tsm": "stratified", "shift": 0.0, "pcn": 4}, 0, True),
+    "c1_trap_mirror": ("c1_example", {"wave": "trapezoidal", "tsm": "antithetic_mirror", "shift": 0.0, "w_g": 150}, 0, True),
+    "c1_tri_uniform": ("c1_example", {"wave": "triangular", "tsm": "uniform", "shift": 0.0, "strat": "false"}, 3, True),
+    "c1_rr": ("c1_example", {"max_depth": 16, "pcd": 16, "rr_depth": 2}, 0, True),
+    "c1_seed7_spp64_tcn4": ("c1_example", {"spp": 64, "tcn": 4, "pcn": 4, "resx": 128, "resy": 128}, 7, True),
+    "c1_strat_nointerval": ("c1_example", {"tsm": "stratified", "shift": 0.0, "strat": "false", "wave": "triangular"}, 1, True),
+    "c1_pcd0_offset": ("c1_example", {"pcd": 0, "hetero_offset": 0.25, "tsm": "antithetic", "shift": 0.25}, 0, True),
+    "c2_arealight": ("c2_arealight", {"resx": 512, "resy": 512}, 0, True),
+    "c2b_two_emitters": ("c2b_two_emitters", {"max_depth": 6, "pcd": 6}, 0, True),
+    "c3_rotor": ("c3_rotor", {"wave": "rectangular", "tsm": "stratified", "shift": 0.0, "pcn": 4, "resx": 512, "resy": 512}, 0, True),
+    "c4_domino": ("c4_domino", {"wave": "trapezoidal", "tsm": "antithetic_mirror", "shift": 0.0, "w_g": 150,
+                                "resx": 1024, "resy": 1024, "spp": 4096}, 0, True),
+    "c5_slabroom_full": ("c5_slabroom", {"lowpass": "false", "wave": "rectangular"}, 0, False),
+    "c5_slabroom_full_sin": ("c5_slabroom", {"lowpass": "false", "wave": "sinusoidal", "hetero_frequency": 0.0}, 2, False),
+    "c5_slabroom_lowpass": ("c5_slabroom", {}, 0, True),
+}
+DEFAULTS = {"spp": 1024, "resx": 256, "resy": 256, "max_depth": 4, "tcn": 2, "pcn": 2}
+N_PIXELS = 48
+
+
+def lanes_for(case, params, rng):
+    p = dict(DEFAULTS, **params)
+    spp, w, h = int(p["spp"]), int(p["resx"]), int(p["resy"])
+    spp_pp = spp
+    wave = w * h * spp_pp
+    if wave > 0xFFFFFFFF:   # integrator.cpp:231-238
+        spp_pp //= (wave + 0xFFFFFFFF - 1) // 0xFFFFFFFF
+    group = 4
+    px = rng.integers(w // 8, w - w // 8, N_PIXELS)
+    py = rng.integers(h // 8, h - h // 8, N_PIXELS)
+    slot = rng.integers(0, spp_pp // group, N_PIXELS) * group
+    lanes = []
+    for x, y, s in zip(px, py, slot):
+        base = (int(y) * w + int(x)) * spp_pp + int(s)
+        lanes += [base + k for k in range(group)]
+    return lanes
+
+
+def run_case(name):
+    scene, params, seed, scaled = CASES[name]
+    rng = np.random.default_rng(abs(hash(name)) % (2 ** 31) if False else sum(map(ord, name)))
+    lanes = lanes_for(name, params, rng)
+    lanes_file = f"/tmp/_dtof_lanes_{name}.txt"
+    with open(lanes_file, "w") as f:
+        f.write("\n".join(map(str, lanes)) + "\n")
+    p = dict(DEFAULTS, **params)
+    tval = T * SCALE if scaled else T
+    cmd = [os.path.join(REF_RT, "replay_harness"), os.path.join(SCENES, scene + ".xml"), "--seed", str(seed),
+           "--tcn", str(p["tcn"]), "--pcn", str(p["pcn"]), "--lanes", lanes_file, f"-DT={tval:.9g}"]
+    for k, v in params.items():
+        cmd.append(f"-D{k}={v}")
+    env = dict(os.environ, LD_LIBRARY_PATH=REF_RT, DTOF_REF_DIR=REF_RT)
+    out = subprocess.run(cmd, check=True, capture_output=True, text=True, env=env).stdout.splitlines()
+    rows = [l.split() for l in out if l and l[0].isdigit()]
+    rows = [r for r in rows if int(r[1]) == 0]    # pass 0 only (later passes are not JIT-faithful in scalar mode)
+    assert len(rows) == len(lanes), (len(rows), len(lanes))
+    rec = {
+        "scene": scene + ".xml", "xml_params": params, "seed": seed, "time_scale": float(SCALE) if scaled else 1.0,
+        "header": [l for l in out if l.startswith("#")][0],
+        "columns": "idx px py sample_pos.x sample_pos.y time ray_o(3) ray_d(3) ray_maxt R G B",
+        "lanes": [int(r[0]) for r in rows],
+        "rows": [[int(r[2]), int(r[3])] + [float(np.float32(v)) for v in r[4:]] for r in rows],
+    }
+    with open(os.path.join(HERE, f"lanes_{name}.json"), "w") as f:
+        json.dump(rec, f, separators=(",", ":"))
+    nz = sum(1 for r in rec["rows"] if any(abs(v) > 0 for v in r[-3:]))
+    print(f"{name}: {len(rows)} lanes, {nz} non-zero")
+
+
+def main():
+    if not os.path.exists(os.path.join(REF_RT, "replay_harness")):
+        sys.exit("oracle/_ref/replay_harness missing: run `make -C oracle/ref_harness` in the build container")
+    names = sys.argv[1:] or list(CASES)
+    for n in names:
+        run_case(n)
+    hv = os.path.join(REF_RT, "header_vectors")
+    if not sys.argv[1:] and os.path.exists(hv):
+        with open(os.path.join(HERE, "header_vectors.json"), "w") as f:
+            f.write(subprocess.run([hv], check=True, capture_output=True, text=True).stdout)
+        print("header_vectors.json written")
+    exr = "/root/reference/configs_example/scene.exr"
+    if not sys.argv[1:] and os.path.exists(exr):
+        try:
+            os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
+            import cv2
+            img = cv2.imread(exr, cv2.IMREAD_UNCHANGED)[..., ::-1]   # BGR -> RGB
+            np.save(os.path.join(HERE, "scene_exr.npy"), np.ascontiguousarray(img.astype(np.float16)))
+            print("scene_exr.npy written", img.shape, img.dtype)
+        except Exception as e:   # noqa: BLE001
+            print("scene.exr not converted:", e)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,53 @@
+"""Helpers shared by the CPU (oracle) and GPU (CUDA) parity tests: load a lane fixture, build the scene
++ parameter block for it, and compare per-lane records against the reference's values."""
+import glob
+import json
+import os
+
+import numpy as np
+
+import mitsuba3dopplertof_b200 as dt
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = os.path.join(HERE, "golden")
+SCENES = os.path.join(HERE, "scenes")
+
+# north_star tolerance: per-sample radiance within 1e-4 relative. A sample is a signed sum of contributions of
+# magnitude ~1e-2..1e-1 that partly cancel, so "relative" needs a floor at the contribution scale:
+# |d| <= REL * max(|ref|, FLOOR), FLOOR = 1e-2 (i.e. never tighter than 1e-6 absolute, ~ float32 phase noise).
+REL_TOL = 1e-4
+ABS_FLOOR = 1e-2
+
+
+def case_names():
+    return sorted(os.path.basename(p)[len("lanes_"):-len(".json")] for p in glob.glob(os.path.join(GOLDEN, "lanes_*.json")))
+
+
+def load_case(name):
+    with open(os.path.join(GOLDEN, f"lanes_{name}.json")) as f:
+        g = json.load(f)
+    scene = dt.load_file(os.path.join(SCENES, g["scene"]), **g["xml_params"])
+    params = scene.integrator.params(scene.sensor.sampler, seed=g["seed"])
+    rows = np.asarray(g["rows"], np.float64)
+    ref = {
+        "lanes": np.asarray(g["lanes"], np.uint64),
+        "pixel": rows[:, 0:2].astype(np.int64),
+        "sample_pos": rows[:, 2:4], "time": rows[:, 4] / g["time_scale"],
+        "ray_o": rows[:, 5:8], "ray_d": rows[:, 8:11], "ray_maxt": rows[:, 11], "rgb": rows[:, 12:15],
+    }
+    return scene, params, ref
+
+
+def compare(rec, ref):
+    """Returns (fraction of lanes whose rgb matches within tolerance, max error over matching lanes).
+    Camera-side quantities must match on every lane."""
+    np.testing.assert_allclose(rec["sample_pos"], ref["sample_pos"], rtol=0, atol=1e-4)   # ~ulp of 1024.x
+    np.testing.assert_allclose(rec["time"], ref["time"], rtol=2e-6, atol=1e-12)
+    np.testing.assert_allclose(rec["ray_o"], ref["ray_o"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(rec["ray_d"], ref["ray_d"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(rec["ray_maxt"], ref["ray_maxt"], rtol=1e-6)
+    d = np.abs(rec["rgb"].astype(np.float64) - ref["rgb"])
+    tol = REL_TOL * np.maximum(np.abs(ref["rgb"]), ABS_FLOOR)
+    ok = (d <= tol).all(axis=1)
+    rel = (d / np.maximum(np.abs(ref["rgb"]), ABS_FLOOR)).max(axis=1)
+    return ok.mean(), (rel[ok].max() if ok.any() else np.inf), np.nonzero(~ok)[0]
