@@ -1,0 +1,807 @@
+// libdtof_b200.so -- C ABI (include/dtof.h) + render kernels for sm_100a.
+//
+// Kernel design: a persistent, register-resident "fused wavefront": one thread per
+// wavefront lane, CTAs of 256 lanes pull 256-lane chunks (= part of ONE pixel when spp_per_pass >= 256)
+// from an atomic work counter. Scenes whose traversal data (nodes + triangles + instances) fit in shared
+// memory are staged there once per CTA with 128-bit copies; larger scenes are read through L1/L2 with
+// 128-bit loads. Film accumulation is warp-aggregated (36 atomics per warp instead of 36 per lane).
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/dtof.h"
+#include "dtof_bvh.h"
+#include "dtof_device.cuh"
+#include "dtof_layout.h"
+
+using namespace dtof;
+
+namespace {
+
+constexpr int kBlock = 256;
+constexpr size_t kSmemSceneLimit = 96 * 1024;   // traversal data up to this size is staged in shared memory
+
+struct RenderArgs {
+    DeviceScene scene;
+    dtof_camera cam;
+    FilmParams film;
+    dtof_params p;
+    Modulation mod;
+    uint32_t spp_per_pass, n_passes;
+    unsigned long long lane_begin, lane_end;     // lanes of every pass handled by this launch
+    unsigned long long *work_counter;            // chunk dispenser
+    Counters *stats;
+    // record mode
+    const unsigned long long *rec_lanes;
+    dtof_sample_record *rec_out;
+    uint32_t n_rec;
+    uint32_t smem_nodes_bytes, smem_tris_bytes, smem_insts_bytes;
+};
+
+template <bool STATS, bool SMEM, bool RECORD>
+__global__ void __launch_bounds__(kBlock, 2) render_kernel(const __grid_constant__ RenderArgs A) {
+    extern __shared__ float4 smem[];
+    __shared__ unsigned long long s_chunk;
+    const float4 *N = A.scene.nodes, *T = A.scene.tris, *I = A.scene.insts;
+    if (SMEM) {
+        // stage nodes | tris | instances into shared memory (128-bit copies)
+        uint32_t nn = A.smem_nodes_bytes / 16, nt = A.smem_tris_bytes / 16, ni = A.smem_insts_bytes / 16;
+        float4 *sN = smem, *sT = smem + nn, *sI = smem + nn + nt;
+        for (uint32_t i = threadIdx.x; i < nn; i += kBlock) sN[i] = A.scene.nodes[i];
+        for (uint32_t i = threadIdx.x; i < nt; i += kBlock) sT[i] = A.scene.tris[i];
+        for (uint32_t i = threadIdx.x; i < ni; i += kBlock) sI[i] = A.scene.insts[i];
+        __syncthreads();
+        N = sN;
+        T = sT;
+        I = sI;
+    }
+    const int lane = threadIdx.x & 31;
+    Counters st = {};
+    const unsigned long long n_lanes = RECORD ? (unsigned long long) A.n_rec : (A.lane_end - A.lane_begin);
+    const unsigned long long n_chunks = (n_lanes + kBlock - 1) / kBlock;
+
+    for (;;) {
+        if (threadIdx.x == 0)
+            s_chunk = atomicAdd(A.work_counter, 1ull);
+        __syncthreads();
+        const unsigned long long chunk = s_chunk;
+        __syncthreads();
+        if (chunk >= n_chunks)
+            break;
+        const unsigned long long li = chunk * kBlock + threadIdx.x;
+        const bool lane_on = li < n_lanes;
+        unsigned long long idx64 = 0;
+        if (lane_on)
+            idx64 = RECORD ? A.rec_lanes[li] : (A.lane_begin + li);
+        const uint32_t idx = (uint32_t) idx64;
+        const uint32_t pixel = idx / A.spp_per_pass;
+        const uint32_t py = pixel / A.film.width, px = pixel - py * A.film.width;
+        LaneSampler smp;
+        if (lane_on)
+            smp.seed(A.p, idx, A.spp_per_pass);
+
+        for (uint32_t pass = 0; pass < (RECORD ? 1u : A.n_passes); ++pass) {
+            V3 rgb = v3(0, 0, 0);
+            float spx = 0.f, spy = 0.f;
+            if (lane_on) {
+                // render_sample(), Doppler branch (src/render/integrator.cpp:476-542)
+                const bool correlate_pixel = A.p.path_correlation_depth > 0;
+                const float scale_x = 1.f / (float) A.film.width, scale_y = 1.f / (float) A.film.height;
+                const float off_x = -(float) A.film.crop_x * scale_x, off_y = -(float) A.film.crop_y * scale_y;
+                const float posx = (float) (px + A.film.crop_x), posy = (float) (py + A.film.crop_y);
+                float jx = smp.next_1d(correlate_pixel), jy = smp.next_1d(correlate_pixel);
+                spx = posx + jx;
+                spy = posy + jy;
+                float ax = fmaf(spx, scale_x, off_x), ay = fmaf(spy, scale_y, off_y);
+                float time = A.cam.shutter_open;
+                if (A.cam.shutter_open_time > 0.f)
+                    time += smp.next_time(A.p, A.spp_per_pass) * A.cam.shutter_open_time;
+                V3 o, d;
+                float maxt;
+                camera_ray(A.cam, ax, ay, o, d, maxt);
+                PathOut r = trace_path<STATS>(A.scene, N, T, I, A.p, A.mod, smp, o, d, maxt, time, st);
+                rgb = r.rgb;
+                if (A.film.rfilter == DTOF_RFILTER_BOX) {
+                    spx = posx;
+                    spy = posy;
+                }
+                if (STATS) st.samples++;
+                if (RECORD) {
+                    dtof_sample_record &rec = A.rec_out[li];
+                    rec.sample_pos[0] = spx, rec.sample_pos[1] = spy;
+                    rec.time = time;
+                    rec.ray_o[0] = o.x, rec.ray_o[1] = o.y, rec.ray_o[2] = o.z;
+                    rec.ray_d[0] = d.x, rec.ray_d[1] = d.y, rec.ray_d[2] = d.z;
+                    rec.ray_maxt = maxt;
+                    rec.rgb[0] = rgb.x, rec.rgb[1] = rgb.y, rec.rgb[2] = rgb.z;
+                    rec.path_length = r.path_length;
+                    rec.depth = r.depth;
+                    rec.rng_draws = smp.draws;
+                }
+                smp.advance();
+            }
+            if (!RECORD) {
+                // ---- film: warp-aggregated when the whole warp splats the same 3x3 footprint
+                const int ix = (int) floorf(spx), iy = (int) floorf(spy);
+                const unsigned on_mask = __ballot_sync(kFullMask, lane_on);
+                if (on_mask) {
+                    const int leader = __ffs(on_mask) - 1;
+                    const int lx = __shfl_sync(kFullMask, ix, leader), ly = __shfl_sync(kFullMask, iy, leader);
+                    const bool uniform = __all_sync(kFullMask, !lane_on || (ix == lx && iy == ly));
+                    if (uniform && A.film.rfilter == DTOF_RFILTER_TENT && A.film.n == 1)
+                        splat_tent3_warp(A.film, lx, ly, spx, spy, rgb, lane_on, lane);
+                    else if (lane_on)
+                        splat_generic(A.film, spx, spy, rgb);
+                }
+            }
+        }
+    }
+    if (STATS) {
+        atomicAdd(&A.stats->rays_closest, st.rays_closest);
+        atomicAdd(&A.stats->rays_shadow, st.rays_shadow);
+        atomicAdd(&A.stats->nodes, st.nodes);
+        atomicAdd(&A.stats->tris, st.tris);
+        atomicAdd(&A.stats->inst, st.inst);
+        atomicAdd(&A.stats->samples, st.samples);
+    }
+}
+
+// HDRFilm::develop (src/films/hdrfilm.cpp:305-419): RGB / W, W == 0 -> divide by 1
+__global__ void develop_kernel(const float4 *__restrict__ rgbw, float *__restrict__ img, size_t n) {
+    size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    float4 v = rgbw[i];
+    float w = v.w == 0.f ? 1.f : v.w;
+    img[3 * i + 0] = v.x / w;
+    img[3 * i + 1] = v.y / w;
+    img[3 * i + 2] = v.z / w;
+}
+
+} // namespace
+
+// ==================================================================================================
+struct dtof_ctx {
+    int device = 0;
+    std::string error;
+    // scene
+    bool has_scene = false;
+    dtof_camera cam{};
+    dtof_film film{};
+    DeviceScene ds{};
+    void *d_nodes = nullptr, *d_tris = nullptr, *d_shade = nullptr, *d_insts = nullptr, *d_meshes = nullptr,
+         *d_bsdfs = nullptr, *d_emitters = nullptr, *d_cdf = nullptr, *d_pmf = nullptr;
+    std::vector<InstRec> h_insts;
+    size_t nodes_bytes = 0, tris_bytes = 0, insts_bytes = 0;
+    int bvh_depth = 0;
+    // render state
+    unsigned long long *d_counter = nullptr;
+    Counters *d_stats = nullptr;
+    float *d_rgbw = nullptr, *d_img = nullptr;
+    size_t film_px = 0;
+    bool stats_enabled = false;
+    dtof_stats last_stats{};
+    uint64_t launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool have_timing = false;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+};
+
+namespace {
+
+dtof_status fail(dtof_ctx *c, dtof_status s, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (c)
+        c->error = buf;
+    return s;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(ctx, DTOF_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));       \
+    } while (0)
+
+void free_scene(dtof_ctx *c) {
+    void **ptrs[] = { &c->d_nodes, &c->d_tris, &c->d_shade, &c->d_insts, &c->d_meshes, &c->d_bsdfs,
+                      &c->d_emitters, &c->d_cdf, &c->d_pmf };
+    for (void **p : ptrs) {
+        if (*p)
+            cudaFree(*p);
+        *p = nullptr;
+    }
+    if (c->d_rgbw) cudaFree(c->d_rgbw);
+    if (c->d_img) cudaFree(c->d_img);
+    c->d_rgbw = c->d_img = nullptr;
+    c->has_scene = false;
+}
+
+template <typename Tv> dtof_status upload_vec(dtof_ctx *ctx, const std::vector<Tv> &v, void **dst) {
+    size_t bytes = std::max<size_t>(v.size() * sizeof(Tv), 16);
+    CU(cudaMalloc(dst, bytes));
+    CU(cudaMemset(*dst, 0, bytes));
+    if (!v.empty())
+        CU(cudaMemcpy(*dst, v.data(), v.size() * sizeof(Tv), cudaMemcpyHostToDevice));
+    return DTOF_OK;
+}
+
+// host copies of the oracle-identical float helpers needed at upload time (rectangle frame, areas)
+struct HV3 {
+    float x, y, z;
+};
+inline float hdot(HV3 a, HV3 b) { return std::fmaf(a.z, b.z, std::fmaf(a.y, b.y, a.x * b.x)); }
+inline HV3 hcross(HV3 a, HV3 b) {
+    return HV3{ std::fmaf(a.y, b.z, -(a.z * b.y)), std::fmaf(a.z, b.x, -(a.x * b.z)), std::fmaf(a.x, b.y, -(a.y * b.x)) };
+}
+
+int pass_info(const dtof_film &film, const dtof_params &p, dtof_pass_info *out) {
+    // src/render/integrator.cpp:121-134,227-245
+    uint32_t spp = p.sample_count;
+    if (spp == 0)
+        return 1;
+    uint32_t spp_per_pass = spp, n_passes = 1;
+    uint64_t wavefront = (uint64_t) film.width * film.height * spp_per_pass, limit = 0xffffffffull;
+    if (wavefront > limit) {
+        spp_per_pass /= (uint32_t) ((wavefront + limit - 1) / limit);
+        if (spp_per_pass == 0)
+            return 1;
+        n_passes = spp / spp_per_pass;
+        wavefront = (uint64_t) film.width * film.height * spp_per_pass;
+    }
+    if (spp % spp_per_pass != 0)   // Sampler::set_samples_per_wavefront, src/render/sampler.cpp:81-82
+        return 2;
+    out->spp_per_pass = spp_per_pass;
+    out->n_passes = n_passes;
+    out->wavefront_size = wavefront;
+    return 0;
+}
+
+dtof_status check_params(dtof_ctx *ctx, const dtof_params *p) {
+    if (!p)
+        return fail(ctx, DTOF_ERR_INVALID, "params is NULL");
+    if (p->time_sampling_method > DTOF_TIME_ANTITHETIC_MIRROR)
+        return fail(ctx, DTOF_ERR_INVALID, "unknown time_sampling_method %u", p->time_sampling_method);
+    if (p->wave_function_type > DTOF_WAVE_TRAPEZOIDAL)
+        return fail(ctx, DTOF_ERR_INVALID, "unknown wave_function_type %u", p->wave_function_type);
+    if (p->time_correlate_number == 0 || p->path_correlate_number == 0)
+        return fail(ctx, DTOF_ERR_INVALID, "correlate numbers must be >= 1");
+    if (p->time_sampling_method == DTOF_TIME_ANTITHETIC_MIRROR && p->time_correlate_number != 2)
+        return fail(ctx, DTOF_ERR_INVALID, "antithetic_mirror requires time_correlate_number == 2 (correlated.cpp:141-142)");
+    if (p->max_depth < -1)
+        return fail(ctx, DTOF_ERR_INVALID, "max_depth must be -1 or >= 0");
+    if (p->rr_depth <= 0)
+        return fail(ctx, DTOF_ERR_INVALID, "rr_depth must be > 0");
+    if (p->sample_count == 0)
+        return fail(ctx, DTOF_ERR_INVALID, "sample_count must be > 0");
+    if (p->use_stratified_sampling_for_each_interval && p->time_sampling_method != DTOF_TIME_UNIFORM &&
+        p->sample_count / p->time_correlate_number == 0)
+        return fail(ctx, DTOF_ERR_INVALID, "sample_count < time_correlate_number");
+    if (!(p->time > 0.f))
+        return fail(ctx, DTOF_ERR_INVALID, "time must be > 0");
+    return DTOF_OK;
+}
+
+Modulation make_modulation(const dtof_params &p) {
+    Modulation m;
+    double mhz = (double) p.w_g;
+    m.w_g = (float) (2.0 * M_PI * mhz * 1e6);
+    m.w_d = (float) (2.0 * M_PI / (double) p.time * (double) p.hetero_frequency);
+    m.k_phi = (float) ((2.0 * M_PI * mhz) / 300.0);
+    m.phase = p.sensor_phase_offset;
+    m.half_g1 = (float) (0.5 * (double) p.g_1);
+    m.g1 = p.g_1;
+    m.g0 = p.g_0;
+    m.w_gd = m.w_g + m.w_d;
+    m.type = p.wave_function_type;
+    m.lowpass = p.low_frequency_component_only != 0;
+    return m;
+}
+
+template <bool STATS, bool RECORD>
+dtof_status launch_variant(dtof_ctx *ctx, RenderArgs &A, bool use_smem, int grid, cudaStream_t stream) {
+    size_t smem = use_smem ? (size_t) A.smem_nodes_bytes + A.smem_tris_bytes + A.smem_insts_bytes : 0;
+    if (use_smem) {
+        auto k = render_kernel<STATS, true, RECORD>;
+        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        k<<<grid, kBlock, smem, stream>>>(A);
+    } else {
+        render_kernel<STATS, false, RECORD><<<grid, kBlock, 0, stream>>>(A);
+    }
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return DTOF_OK;
+}
+
+dtof_status launch_render(dtof_ctx *ctx, const dtof_params *p, float *d_rgbw, cudaStream_t stream,
+                          const unsigned long long *d_lanes, dtof_sample_record *d_rec, uint32_t n_rec) {
+    dtof_pass_info pi;
+    int rc = pass_info(ctx->film, *p, &pi);
+    if (rc)
+        return fail(ctx, DTOF_ERR_INVALID,
+                    rc == 2 ? "sample_count should be a multiple of samples_per_wavefront!" : "invalid sample_count");
+    RenderArgs A{};
+    A.scene = ctx->ds;
+    A.cam = ctx->cam;
+    A.p = *p;
+    A.mod = make_modulation(*p);
+    A.spp_per_pass = pi.spp_per_pass;
+    A.n_passes = pi.n_passes;
+    A.lane_begin = p->lane_begin;
+    A.lane_end = p->lane_end ? p->lane_end : pi.wavefront_size;
+    if (A.lane_end > pi.wavefront_size || A.lane_begin > A.lane_end)
+        return fail(ctx, DTOF_ERR_INVALID, "lane range [%llu, %llu) outside the wavefront of %llu lanes", A.lane_begin,
+                    A.lane_end, (unsigned long long) pi.wavefront_size);
+    FilmParams &F = A.film;
+    F.rgbw = d_rgbw;
+    F.width = ctx->film.width, F.height = ctx->film.height;
+    F.crop_x = ctx->film.crop_offset_x, F.crop_y = ctx->film.crop_offset_y;
+    F.rfilter = ctx->film.rfilter;
+    F.radius = ctx->film.rfilter_radius;
+    F.inv_radius = 1.f / F.radius;
+    F.g_alpha = -1.f / (2.f * ctx->film.gaussian_stddev * ctx->film.gaussian_stddev);
+    F.g_bias = expf(F.g_alpha * F.radius * F.radius);
+    F.n = (int) ceilf(F.radius - .5f);
+    A.work_counter = ctx->d_counter;
+    A.stats = ctx->d_stats;
+    A.rec_lanes = d_lanes;
+    A.rec_out = d_rec;
+    A.n_rec = n_rec;
+    A.smem_nodes_bytes = (uint32_t) ctx->nodes_bytes;
+    A.smem_tris_bytes = (uint32_t) ctx->tris_bytes;
+    A.smem_insts_bytes = (uint32_t) ctx->insts_bytes;
+    const bool record = d_rec != nullptr;
+    const size_t trav_bytes = ctx->nodes_bytes + ctx->tris_bytes + ctx->insts_bytes;
+    const bool use_smem = trav_bytes <= kSmemSceneLimit && trav_bytes + 1024 <= ctx->smem_optin && !getenv("DTOF_NO_SMEM");
+    unsigned long long n_lanes = record ? n_rec : (A.lane_end - A.lane_begin);
+    unsigned long long n_chunks = (n_lanes + kBlock - 1) / kBlock;
+    int grid = (int) std::min<unsigned long long>(std::max<unsigned long long>(n_chunks, 1), (unsigned long long) ctx->sm_count * 2);
+    CU(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), stream));
+    if (ctx->stats_enabled)
+        CU(cudaMemsetAsync(ctx->d_stats, 0, sizeof(Counters), stream));
+    CU(cudaEventRecord(ctx->ev0, stream));
+    dtof_status s;
+    if (record)
+        s = ctx->stats_enabled ? launch_variant<true, true>(ctx, A, use_smem, grid, stream)
+                               : launch_variant<false, true>(ctx, A, use_smem, grid, stream);
+    else
+        s = ctx->stats_enabled ? launch_variant<true, false>(ctx, A, use_smem, grid, stream)
+                               : launch_variant<false, false>(ctx, A, use_smem, grid, stream);
+    if (s != DTOF_OK)
+        return s;
+    CU(cudaEventRecord(ctx->ev1, stream));
+    ctx->last_stream = stream;
+    ctx->have_timing = true;
+    return DTOF_OK;
+}
+
+} // namespace
+
+// ==================================================================================================
+extern "C" {
+
+uint32_t dtof_abi_version(void) { return DTOF_ABI_VERSION; }
+
+dtof_status dtof_create(dtof_ctx **out, int device) {
+    if (!out)
+        return DTOF_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || device < 0 || device >= n)
+        return e != cudaSuccess ? DTOF_ERR_CUDA : DTOF_ERR_INVALID;
+    dtof_ctx *ctx = new dtof_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess ||
+        cudaMalloc(&ctx->d_counter, sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMalloc(&ctx->d_stats, sizeof(Counters)) != cudaSuccess || cudaEventCreate(&ctx->ev0) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+        delete ctx;
+        return DTOF_ERR_CUDA;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    *out = ctx;
+    return DTOF_OK;
+}
+
+void dtof_destroy(dtof_ctx *ctx) {
+    if (!ctx)
+        return;
+    cudaSetDevice(ctx->device);
+    free_scene(ctx);
+    if (ctx->d_counter) cudaFree(ctx->d_counter);
+    if (ctx->d_stats) cudaFree(ctx->d_stats);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    delete ctx;
+}
+
+const char *dtof_last_error(const dtof_ctx *ctx) { return ctx ? ctx->error.c_str() : "null context"; }
+
+dtof_status dtof_upload_scene(dtof_ctx *ctx, const dtof_scene_desc *sc) {
+    if (!ctx || !sc)
+        return DTOF_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    if (sc->film.width == 0 || sc->film.height == 0)
+        return fail(ctx, DTOF_ERR_INVALID, "empty film");
+    if (sc->film.rfilter > DTOF_RFILTER_GAUSSIAN)
+        return fail(ctx, DTOF_ERR_INVALID, "unknown rfilter %u", sc->film.rfilter);
+    if (sc->film.rfilter != DTOF_RFILTER_BOX && !(sc->film.rfilter_radius > 0.f && sc->film.rfilter_radius <= 7.5f))
+        return fail(ctx, DTOF_ERR_INVALID, "rfilter radius out of range");
+    // ---- validate + flatten
+    std::vector<MeshRec> meshes(sc->n_meshes);
+    std::vector<BsdfRec> bsdfs(sc->n_bsdfs);
+    std::vector<EmitterRec> emitters(sc->n_emitters);
+    std::vector<TriShade> shade;
+    std::vector<float> cdf, pmf;
+    std::vector<GroupInput> groups(sc->n_instances);
+    std::vector<uint32_t> mesh_first_gid(sc->n_meshes, 0xffffffffu);
+    for (uint32_t i = 0; i < sc->n_bsdfs; ++i) {
+        const dtof_bsdf &b = sc->bsdfs[i];
+        if (b.kind > DTOF_BSDF_NULL_BLACK)
+            return fail(ctx, DTOF_ERR_UNSUPPORTED, "bsdf kind %u is outside the hot-path scope", b.kind);
+        bsdfs[i] = BsdfRec{ b.reflectance[0], b.reflectance[1], b.reflectance[2],
+                            (b.twosided ? 1u : 0u) | (b.kind == DTOF_BSDF_DIFFUSE ? 2u : 0u) };
+    }
+    uint32_t gid = 0;
+    for (uint32_t g = 0; g < sc->n_instances; ++g) {
+        const dtof_instance &in = sc->instances[g];
+        if ((uint64_t) in.first_mesh + in.n_meshes > sc->n_meshes)
+            return fail(ctx, DTOF_ERR_INVALID, "instance %u references meshes out of range", g);
+        if (in.animated && !(in.t1 > in.t0))
+            return fail(ctx, DTOF_ERR_INVALID, "instance %u: keyframe times must be increasing", g);
+        GroupInput &G = groups[g];
+        G.animated = in.animated != 0;
+        memcpy(G.m0, in.m0, sizeof(G.m0));
+        memcpy(G.m1, in.m1, sizeof(G.m1));
+        for (uint32_t mi = in.first_mesh; mi < in.first_mesh + in.n_meshes; ++mi) {
+            const dtof_mesh &m = sc->meshes[mi];
+            if (mesh_first_gid[mi] != 0xffffffffu)
+                return fail(ctx, DTOF_ERR_UNSUPPORTED, "mesh %u belongs to more than one instance", mi);
+            if (!m.positions || !m.faces)
+                return fail(ctx, DTOF_ERR_INVALID, "mesh %u has no positions/faces", mi);
+            if (m.bsdf >= sc->n_bsdfs)
+                return fail(ctx, DTOF_ERR_INVALID, "mesh %u: bsdf index out of range", mi);
+            if (m.emitter >= (int32_t) sc->n_emitters)
+                return fail(ctx, DTOF_ERR_INVALID, "mesh %u: emitter index out of range", mi);
+            if (m.emitter >= 0 && in.animated)
+                return fail(ctx, DTOF_ERR_UNSUPPORTED, "Instancing of emitters is not supported (shapegroup.cpp:27-30)");
+            mesh_first_gid[mi] = gid;
+            uint32_t flags = (m.normals ? TRI_HAS_NORMALS : 0u) | (m.texcoords ? TRI_HAS_UV : 0u) | (m.flip_normals ? TRI_FLIP : 0u);
+            for (uint32_t f = 0; f < m.n_faces; ++f, ++gid) {
+                uint32_t i0 = m.faces[3 * f], i1 = m.faces[3 * f + 1], i2 = m.faces[3 * f + 2];
+                if (i0 >= m.n_vertices || i1 >= m.n_vertices || i2 >= m.n_vertices)
+                    return fail(ctx, DTOF_ERR_INVALID, "mesh %u face %u: vertex index out of range", mi, f);
+                const float *p0 = m.positions + 3 * i0, *p1 = m.positions + 3 * i1, *p2 = m.positions + 3 * i2;
+                TriIsect t{};
+                t.p0x = p0[0], t.p0y = p0[1], t.p0z = p0[2];
+                t.gid = gid;
+                t.e1x = p1[0] - p0[0], t.e1y = p1[1] - p0[1], t.e1z = p1[2] - p0[2];
+                t.e2x = p2[0] - p0[0], t.e2y = p2[1] - p0[1], t.e2z = p2[2] - p0[2];
+                G.tris.push_back(t);
+                G.p1.insert(G.p1.end(), p1, p1 + 3);
+                G.p2.insert(G.p2.end(), p2, p2 + 3);
+                TriShade s{};
+                s.p0x = p0[0], s.p0y = p0[1], s.p0z = p0[2];
+                s.mesh = mi;
+                s.p1x = p1[0], s.p1y = p1[1], s.p1z = p1[2];
+                s.flags = flags;
+                s.p2x = p2[0], s.p2y = p2[1], s.p2z = p2[2];
+                if (m.normals) {
+                    const float *n0 = m.normals + 3 * i0, *n1 = m.normals + 3 * i1, *n2 = m.normals + 3 * i2;
+                    s.n0x = n0[0], s.n0y = n0[1], s.n0z = n0[2];
+                    s.n1x = n1[0], s.n1y = n1[1], s.n1z = n1[2];
+                    s.n2x = n2[0], s.n2y = n2[1], s.n2z = n2[2];
+                }
+                if (m.texcoords) {
+                    const float *u0 = m.texcoords + 2 * i0, *u1 = m.texcoords + 2 * i1, *u2 = m.texcoords + 2 * i2;
+                    s.uv0x = u0[0], s.uv0y = u0[1], s.uv1x = u1[0], s.uv1y = u1[1], s.uv2x = u2[0], s.uv2y = u2[1];
+                }
+                shade.push_back(s);
+            }
+        }
+    }
+    if ((uint64_t) gid >= (1ull << 27))
+        return fail(ctx, DTOF_ERR_UNSUPPORTED, "more than 2^27 triangles");
+    for (uint32_t mi = 0; mi < sc->n_meshes; ++mi) {
+        const dtof_mesh &m = sc->meshes[mi];
+        MeshRec &r = meshes[mi];
+        memset(&r, 0, sizeof(r));
+        r.bsdf = m.bsdf;
+        r.emitter = m.emitter;
+        r.kind = m.kind;
+        r.n_faces = m.n_faces;
+        r.first_gid = mesh_first_gid[mi];
+        if (m.emitter >= 0 && mesh_first_gid[mi] == 0xffffffffu)
+            return fail(ctx, DTOF_ERR_INVALID, "emitter mesh %u is not part of any instance", mi);
+        if (m.kind == DTOF_SHAPE_RECTANGLE) {   // Rectangle::update, src/shapes/rectangle.cpp:101-113
+            memcpy(r.rect_to_world, m.rect_to_world, sizeof(r.rect_to_world));
+            const float *M = m.rect_to_world;
+            HV3 s{ M[0] * 2.f, M[4] * 2.f, M[8] * 2.f }, t{ M[1] * 2.f, M[5] * 2.f, M[9] * 2.f };
+            // normal = normalize(inverse_transpose * (0,0,1)) = normalize(third row of the cofactor matrix)
+            float c02 = std::fmaf(M[4], M[9], -(M[5] * M[8])), c12 = std::fmaf(M[1], M[8], -(M[0] * M[9])),
+                  c22 = std::fmaf(M[0], M[5], -(M[1] * M[4]));
+            float c00 = std::fmaf(M[5], M[10], -(M[6] * M[9])), c01 = std::fmaf(M[6], M[8], -(M[4] * M[10]));
+            float det = std::fmaf(M[0], c00, std::fmaf(M[1], c01, M[2] * c02));
+            float id = 1.f / det;
+            HV3 nn{ c02 * id, c12 * id, c22 * id };
+            float il = 1.f / std::sqrt(hdot(nn, nn));
+            r.rect_n[0] = nn.x * il, r.rect_n[1] = nn.y * il, r.rect_n[2] = nn.z * il;
+            HV3 c = hcross(s, t);
+            r.inv_area = 1.f / std::sqrt(hdot(c, c));
+        } else if (m.emitter >= 0) {   // Mesh::build_pmf (mesh.cpp:361-393) + DiscreteDistribution::compute_cdf
+            r.cdf_offset = (uint32_t) cdf.size();
+            double sum = 0.0;
+            bool any = false;
+            for (uint32_t f = 0; f < m.n_faces; ++f) {
+                const float *p0 = m.positions + 3 * m.faces[3 * f], *p1 = m.positions + 3 * m.faces[3 * f + 1],
+                            *p2 = m.positions + 3 * m.faces[3 * f + 2];
+                HV3 a{ p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2] }, b{ p2[0] - p0[0], p2[1] - p0[1], p2[2] - p0[2] };
+                HV3 c = hcross(a, b);
+                float area = .5f * std::sqrt(hdot(c, c));
+                pmf.push_back(area);
+                sum += (double) area;
+                cdf.push_back((float) sum);
+                if (area > 0.f) {
+                    if (!any)
+                        r.valid_lo = f;
+                    r.valid_hi = f;
+                    any = true;
+                }
+            }
+            if (!any)
+                return fail(ctx, DTOF_ERR_INVALID, "emitter mesh %u has no surface area", mi);
+            r.area_sum = (float) sum;
+            r.inv_area = (float) (1.0 / sum);
+        }
+    }
+    bool all_point = true;
+    for (uint32_t i = 0; i < sc->n_emitters; ++i) {
+        const dtof_emitter &e = sc->emitters[i];
+        if (e.kind > DTOF_EMITTER_AREA)
+            return fail(ctx, DTOF_ERR_UNSUPPORTED, "emitter kind %u is outside the hot-path scope", e.kind);
+        if (e.kind == DTOF_EMITTER_AREA && (e.mesh >= sc->n_meshes || sc->meshes[e.mesh].emitter != (int32_t) i))
+            return fail(ctx, DTOF_ERR_INVALID, "area emitter %u and its mesh do not reference each other", i);
+        all_point = all_point && e.kind == DTOF_EMITTER_POINT;
+        emitters[i] = EmitterRec{ e.kind, e.mesh, e.position[0], e.position[1], e.position[2], e.value[0], e.value[1], e.value[2] };
+    }
+    (void) all_point;
+
+    // ---- BVH
+    BuiltScene built;
+    build_scene_bvh(groups, built);
+    if (built.max_depth + built.tlas_depth + 4 > kStackSize)
+        return fail(ctx, DTOF_ERR_UNSUPPORTED, "BVH too deep for the traversal stack (%d + %d)", built.max_depth, built.tlas_depth);
+    std::vector<InstRec> insts(sc->n_instances);
+    for (uint32_t g = 0; g < sc->n_instances; ++g) {
+        const dtof_instance &in = sc->instances[g];
+        InstRec &r = insts[g];
+        memcpy(r.m0, in.m0, sizeof(r.m0));
+        memcpy(r.m1, in.m1, sizeof(r.m1));
+        r.t0 = in.t0, r.t1 = in.t1;
+        r.root = built.inst_root[g];
+        r.animated = in.animated ? 1u : 0u;
+    }
+
+    // ---- upload
+    free_scene(ctx);
+    dtof_status s;
+    if ((s = upload_vec(ctx, built.nodes, &ctx->d_nodes)) != DTOF_OK) return s;
+    if ((s = upload_vec(ctx, built.tris, &ctx->d_tris)) != DTOF_OK) return s;
+    if ((s = upload_vec(ctx, shade, &ctx->d_shade)) != DTOF_OK) return s;
+    if ((s = upload_vec(ctx, insts, &ctx->d_insts)) != DTOF_OK) return s;
+    if ((s = upload_vec(ctx, meshes, &ctx->d_meshes)) != DTOF_OK) return s;
+    if ((s = upload_vec(ctx, bsdfs, &ctx->d_bsdfs)) != DTOF_OK) return s;
+    if ((s = upload_vec(ctx, emitters, &ctx->d_emitters)) != DTOF_OK) return s;
+    if ((s = upload_vec(ctx, cdf, &ctx->d_cdf)) != DTOF_OK) return s;
+    if ((s = upload_vec(ctx, pmf, &ctx->d_pmf)) != DTOF_OK) return s;
+    ctx->h_insts = insts;
+    ctx->nodes_bytes = built.nodes.size() * sizeof(BvhNode);
+    ctx->tris_bytes = built.tris.size() * sizeof(TriIsect);
+    ctx->insts_bytes = insts.size() * sizeof(InstRec);
+    ctx->bvh_depth = built.max_depth + built.tlas_depth;
+    DeviceScene &D = ctx->ds;
+    D.nodes = (const float4 *) ctx->d_nodes;
+    D.tris = (const float4 *) ctx->d_tris;
+    D.shade = (const float4 *) ctx->d_shade;
+    D.insts = (const float4 *) ctx->d_insts;
+    D.meshes = (const MeshRec *) ctx->d_meshes;
+    D.bsdfs = (const BsdfRec *) ctx->d_bsdfs;
+    D.emitters = (const EmitterRec *) ctx->d_emitters;
+    D.area_cdf = (const float *) ctx->d_cdf;
+    D.area_pmf = (const float *) ctx->d_pmf;
+    D.root = built.root;
+    D.n_emitters = sc->n_emitters;
+    D.n_insts = sc->n_instances;
+    D.n_nodes = (uint32_t) built.nodes.size();
+    D.n_tris = (uint32_t) built.tris.size();
+    D.has_geometry = built.has_geometry ? 1u : 0u;
+    ctx->cam = sc->camera;
+    ctx->film = sc->film;
+    ctx->film_px = (size_t) sc->film.width * sc->film.height;
+    CU(cudaMalloc(&ctx->d_rgbw, ctx->film_px * 4 * sizeof(float)));
+    CU(cudaMalloc(&ctx->d_img, ctx->film_px * 3 * sizeof(float)));
+    ctx->has_scene = true;
+    return DTOF_OK;
+}
+
+dtof_status dtof_update_instances(dtof_ctx *ctx, uint32_t first, uint32_t n, const dtof_instance *instances) {
+    if (!ctx || !instances)
+        return DTOF_ERR_INVALID;
+    if (!ctx->has_scene)
+        return fail(ctx, DTOF_ERR_STATE, "no scene uploaded");
+    if ((uint64_t) first + n > ctx->h_insts.size())
+        return fail(ctx, DTOF_ERR_INVALID, "instance range out of bounds");
+    CU(cudaSetDevice(ctx->device));
+    // Only the keyframes move; the TLAS bounds are kept, so the new motion must stay inside the bounds
+    // the scene was uploaded with (re-upload otherwise).
+    for (uint32_t i = 0; i < n; ++i) {
+        InstRec &r = ctx->h_insts[first + i];
+        if ((r.animated != 0) != (instances[i].animated != 0))
+            return fail(ctx, DTOF_ERR_INVALID, "cannot change the animated flag of instance %u", first + i);
+        memcpy(r.m0, instances[i].m0, sizeof(r.m0));
+        memcpy(r.m1, instances[i].m1, sizeof(r.m1));
+        r.t0 = instances[i].t0, r.t1 = instances[i].t1;
+    }
+    CU(cudaMemcpy((char *) ctx->d_insts + first * sizeof(InstRec), ctx->h_insts.data() + first, n * sizeof(InstRec),
+                  cudaMemcpyHostToDevice));
+    return DTOF_OK;
+}
+
+dtof_status dtof_pass_info_for(const dtof_ctx *cctx, const dtof_params *params, dtof_pass_info *out) {
+    dtof_ctx *ctx = const_cast<dtof_ctx *>(cctx);
+    if (!ctx || !params || !out)
+        return DTOF_ERR_INVALID;
+    if (!ctx->has_scene)
+        return fail(ctx, DTOF_ERR_STATE, "no scene uploaded");
+    int rc = pass_info(ctx->film, *params, out);
+    if (rc)
+        return fail(ctx, DTOF_ERR_INVALID,
+                    rc == 2 ? "sample_count should be a multiple of samples_per_wavefront!" : "invalid sample_count");
+    return DTOF_OK;
+}
+
+dtof_status dtof_render_device(dtof_ctx *ctx, const dtof_params *params, float *d_rgbw, void *stream) {
+    if (!ctx)
+        return DTOF_ERR_INVALID;
+    if (!ctx->has_scene)
+        return fail(ctx, DTOF_ERR_STATE, "no scene uploaded");
+    if (!d_rgbw)
+        return fail(ctx, DTOF_ERR_INVALID, "d_rgbw is NULL");
+    dtof_status s = check_params(ctx, params);
+    if (s != DTOF_OK)
+        return s;
+    CU(cudaSetDevice(ctx->device));
+    return launch_render(ctx, params, d_rgbw, (cudaStream_t) stream, nullptr, nullptr, 0);
+}
+
+dtof_status dtof_develop_device(dtof_ctx *ctx, const float *d_rgbw, float *d_image, void *stream) {
+    if (!ctx)
+        return DTOF_ERR_INVALID;
+    if (!ctx->has_scene)
+        return fail(ctx, DTOF_ERR_STATE, "no scene uploaded");
+    if (!d_rgbw || !d_image)
+        return fail(ctx, DTOF_ERR_INVALID, "NULL tensor");
+    CU(cudaSetDevice(ctx->device));
+    size_t n = ctx->film_px;
+    develop_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, (cudaStream_t) stream>>>((const float4 *) d_rgbw, d_image, n);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return DTOF_OK;
+}
+
+dtof_status dtof_render(dtof_ctx *ctx, const dtof_params *params, float *rgbw_out, float *image_out) {
+    if (!ctx)
+        return DTOF_ERR_INVALID;
+    if (!ctx->has_scene)
+        return fail(ctx, DTOF_ERR_STATE, "no scene uploaded");
+    dtof_status s = check_params(ctx, params);
+    if (s != DTOF_OK)
+        return s;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemsetAsync(ctx->d_rgbw, 0, ctx->film_px * 4 * sizeof(float), 0));
+    if ((s = launch_render(ctx, params, ctx->d_rgbw, 0, nullptr, nullptr, 0)) != DTOF_OK)
+        return s;
+    if (image_out && (s = dtof_develop_device(ctx, ctx->d_rgbw, ctx->d_img, nullptr)) != DTOF_OK)
+        return s;
+    if (rgbw_out)
+        CU(cudaMemcpyAsync(rgbw_out, ctx->d_rgbw, ctx->film_px * 4 * sizeof(float), cudaMemcpyDeviceToHost, 0));
+    if (image_out)
+        CU(cudaMemcpyAsync(image_out, ctx->d_img, ctx->film_px * 3 * sizeof(float), cudaMemcpyDeviceToHost, 0));
+    CU(cudaStreamSynchronize(0));
+    return DTOF_OK;
+}
+
+dtof_status dtof_trace_samples(dtof_ctx *ctx, const dtof_params *params, const uint64_t *lanes, uint32_t n,
+                               dtof_sample_record *out) {
+    if (!ctx)
+        return DTOF_ERR_INVALID;
+    if (!ctx->has_scene)
+        return fail(ctx, DTOF_ERR_STATE, "no scene uploaded");
+    if (n == 0)
+        return DTOF_OK;
+    if (!lanes || !out)
+        return fail(ctx, DTOF_ERR_INVALID, "NULL lanes/out");
+    dtof_status s = check_params(ctx, params);
+    if (s != DTOF_OK)
+        return s;
+    dtof_pass_info pi;
+    if (pass_info(ctx->film, *params, &pi))
+        return fail(ctx, DTOF_ERR_INVALID, "sample_count should be a multiple of samples_per_wavefront!");
+    for (uint32_t i = 0; i < n; ++i)
+        if (lanes[i] >= pi.wavefront_size)
+            return fail(ctx, DTOF_ERR_INVALID, "lane %llu outside the wavefront", (unsigned long long) lanes[i]);
+    CU(cudaSetDevice(ctx->device));
+    unsigned long long *d_lanes = nullptr;
+    dtof_sample_record *d_rec = nullptr;
+    CU(cudaMalloc(&d_lanes, n * sizeof(unsigned long long)));
+    cudaError_t e = cudaMalloc(&d_rec, n * sizeof(dtof_sample_record));
+    if (e != cudaSuccess) {
+        cudaFree(d_lanes);
+        return fail(ctx, DTOF_ERR_NOMEM, "cudaMalloc failed");
+    }
+    cudaMemcpy(d_lanes, lanes, n * sizeof(unsigned long long), cudaMemcpyHostToDevice);
+    dtof_params p = *params;
+    p.lane_begin = 0;
+    p.lane_end = 0;
+    s = launch_render(ctx, &p, ctx->d_rgbw, 0, d_lanes, d_rec, n);
+    if (s == DTOF_OK) {
+        e = cudaMemcpy(out, d_rec, n * sizeof(dtof_sample_record), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess)
+            s = fail(ctx, DTOF_ERR_CUDA, "readback failed: %s", cudaGetErrorString(e));
+    }
+    cudaFree(d_lanes);
+    cudaFree(d_rec);
+    return s;
+}
+
+dtof_status dtof_set_stats(dtof_ctx *ctx, int enabled) {
+    if (!ctx)
+        return DTOF_ERR_INVALID;
+    ctx->stats_enabled = enabled != 0;
+    return DTOF_OK;
+}
+
+dtof_status dtof_get_stats(dtof_ctx *ctx, dtof_stats *out) {
+    if (!ctx || !out)
+        return DTOF_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    Counters c;
+    CU(cudaMemcpy(&c, ctx->d_stats, sizeof(c), cudaMemcpyDeviceToHost));
+    out->samples = c.samples;
+    out->rays_closest = c.rays_closest;
+    out->rays_shadow = c.rays_shadow;
+    out->nodes_visited = c.nodes;
+    out->tris_tested = c.tris;
+    out->inst_visits = c.inst;
+    return DTOF_OK;
+}
+
+uint64_t dtof_launch_count(const dtof_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+dtof_status dtof_last_kernel_ms(dtof_ctx *ctx, float *ms) {
+    if (!ctx || !ms)
+        return DTOF_ERR_INVALID;
+    if (!ctx->have_timing)
+        return fail(ctx, DTOF_ERR_STATE, "no render has been launched");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventSynchronize(ctx->ev1));
+    CU(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return DTOF_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,263 @@
+// Host-side BVH construction for the flattened scene: one binned-SAH BLAS per shape group in the
+// group's own space, and a TLAS over instances whose bounds are the union of the two keyframe boxes
+// (Instance::bbox, src/shapes/instance.cpp:101-114 -- exact for a linearly interpolated affine map).
+// Replaces Embree's builder (ext/embree) for this path; output layout: dtof_layout.h.
+#include "dtof_bvh.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <thread>
+
+namespace dtof {
+
+namespace {
+
+struct Box {
+    float lo[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, hi[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+    void grow(const float *p) {
+        for (int a = 0; a < 3; ++a) {
+            lo[a] = std::min(lo[a], p[a]);
+            hi[a] = std::max(hi[a], p[a]);
+        }
+    }
+    void grow(const Box &b) {
+        for (int a = 0; a < 3; ++a) {
+            lo[a] = std::min(lo[a], b.lo[a]);
+            hi[a] = std::max(hi[a], b.hi[a]);
+        }
+    }
+    float half_area() const {
+        float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        return dx * dy + dy * dz + dz * dx;
+    }
+    bool valid() const { return lo[0] <= hi[0]; }
+};
+
+struct Ref {
+    Box box;
+    float c[3];
+    uint32_t id;
+};
+
+// Conservative padding: Moeller-Trumbore accepts hits a few ulp outside the exact triangle, and the slab test
+// (b - o) * idir carries ~3 ulp of relative error (absorbed by the widened far side in the kernel).
+inline void pad_box(Box &b) {
+    for (int a = 0; a < 3; ++a) {
+        float m = std::max(std::fabs(b.lo[a]), std::fabs(b.hi[a]));
+        float pad = 1e-5f * m + 1e-6f * (b.hi[a] - b.lo[a]) + 1e-30f;
+        b.lo[a] -= pad;
+        b.hi[a] += pad;
+    }
+}
+
+inline void set_child(BvhNode &n, int which, const Box &b, int32_t ref) {
+    if (which == 0) {
+        n.c0_lox = b.lo[0], n.c0_hix = b.hi[0], n.c0_loy = b.lo[1], n.c0_hiy = b.hi[1];
+        n.c0_loz = b.lo[2], n.c0_hiz = b.hi[2];
+        n.child0 = ref;
+    } else {
+        n.c1_lox = b.lo[0], n.c1_hix = b.hi[0], n.c1_loy = b.lo[1], n.c1_hiy = b.hi[1];
+        n.c1_loz = b.lo[2], n.c1_hiz = b.hi[2];
+        n.child1 = ref;
+    }
+}
+
+constexpr int kBins = 16;
+constexpr uint32_t kMaxLeaf = 4;
+constexpr int kSahDepthLimit = 40;   // beyond this depth fall back to median splits (bounds the traversal stack)
+
+// Generic top-down builder over `refs[lo,hi)`. `make_leaf(lo, hi)` returns the leaf reference.
+// Returns the child reference of the subtree root and its (padded) box.
+template <typename MakeLeaf>
+int32_t build_range(std::vector<Ref> &refs, uint32_t lo, uint32_t hi, std::vector<BvhNode> &nodes, int depth,
+                    uint32_t max_leaf, MakeLeaf &make_leaf, Box &out_box, int &max_depth) {
+    max_depth = std::max(max_depth, depth);
+    Box bounds, cbounds;
+    for (uint32_t i = lo; i < hi; ++i) {
+        bounds.grow(refs[i].box);
+        cbounds.grow(refs[i].c);
+    }
+    out_box = bounds;
+    uint32_t n = hi - lo;
+    if (n <= max_leaf) {
+        return make_leaf(lo, hi);
+    }
+    int axis = 0;
+    float ext[3] = { cbounds.hi[0] - cbounds.lo[0], cbounds.hi[1] - cbounds.lo[1], cbounds.hi[2] - cbounds.lo[2] };
+    if (ext[1] > ext[axis]) axis = 1;
+    if (ext[2] > ext[axis]) axis = 2;
+    uint32_t mid = lo;
+    bool split_done = false;
+    if (ext[axis] > 0.f && depth < kSahDepthLimit) {
+        // binned SAH over all three axes
+        float best_cost = FLT_MAX;
+        int best_axis = -1, best_bin = -1;
+        for (int a = 0; a < 3; ++a) {
+            if (!(ext[a] > 0.f))
+                continue;
+            Box bb[kBins];
+            uint32_t cnt[kBins] = {};
+            float k = kBins * (1.f - 1e-6f) / ext[a];
+            for (uint32_t i = lo; i < hi; ++i) {
+                int b = std::min(kBins - 1, std::max(0, (int) ((refs[i].c[a] - cbounds.lo[a]) * k)));
+                cnt[b]++;
+                bb[b].grow(refs[i].box);
+            }
+            float right_area[kBins];
+            uint32_t right_cnt[kBins];
+            Box acc;
+            uint32_t c = 0;
+            for (int b = kBins - 1; b > 0; --b) {
+                acc.grow(bb[b]);
+                c += cnt[b];
+                right_area[b] = acc.valid() ? acc.half_area() : 0.f;
+                right_cnt[b] = c;
+            }
+            Box accl;
+            uint32_t cl = 0;
+            for (int b = 0; b < kBins - 1; ++b) {
+                accl.grow(bb[b]);
+                cl += cnt[b];
+                if (cl == 0 || right_cnt[b + 1] == 0)
+                    continue;
+                float cost = accl.half_area() * (float) cl + right_area[b + 1] * (float) right_cnt[b + 1];
+                if (cost < best_cost) {
+                    best_cost = cost;
+                    best_axis = a;
+                    best_bin = b;
+                }
+            }
+        }
+        if (best_axis >= 0) {
+            float k = kBins * (1.f - 1e-6f) / ext[best_axis];
+            float clo = cbounds.lo[best_axis];
+            auto it = std::partition(refs.begin() + lo, refs.begin() + hi, [&](const Ref &r) {
+                int b = std::min(kBins - 1, std::max(0, (int) ((r.c[best_axis] - clo) * k)));
+                return b <= best_bin;
+            });
+            mid = (uint32_t) (it - refs.begin());
+            split_done = mid > lo && mid < hi;
+        }
+    }
+    if (!split_done) {   // object median along the widest centroid axis
+        mid = lo + n / 2;
+        std::nth_element(refs.begin() + lo, refs.begin() + mid, refs.begin() + hi,
+                         [axis](const Ref &a, const Ref &b) { return a.c[axis] < b.c[axis]; });
+    }
+    int32_t me = (int32_t) nodes.size();
+    nodes.push_back(BvhNode{});
+    Box b0, b1;
+    int32_t r0 = build_range(refs, lo, mid, nodes, depth + 1, max_leaf, make_leaf, b0, max_depth);
+    int32_t r1 = build_range(refs, mid, hi, nodes, depth + 1, max_leaf, make_leaf, b1, max_depth);
+    pad_box(b0);
+    pad_box(b1);
+    BvhNode nd{};
+    set_child(nd, 0, b0, r0);
+    set_child(nd, 1, b1, r1);
+    nodes[me] = nd;
+    return me;
+}
+
+inline void xf_point(const float *m, const float *p, float *o) {
+    for (int r = 0; r < 3; ++r)
+        o[r] = m[4 * r + 0] * p[0] + m[4 * r + 1] * p[1] + m[4 * r + 2] * p[2] + m[4 * r + 3];
+}
+
+} // namespace
+
+void build_scene_bvh(const std::vector<GroupInput> &groups, BuiltScene &out) {
+    out.nodes.clear();
+    out.tris.clear();
+    out.inst_root.assign(groups.size(), 0);
+    out.max_depth = 0;
+    std::vector<Box> inst_boxes(groups.size());
+
+    // ---- BLAS per group
+    for (size_t g = 0; g < groups.size(); ++g) {
+        const GroupInput &G = groups[g];
+        uint32_t n = (uint32_t) G.tris.size();
+        std::vector<Ref> refs(n);
+        Box gb;
+        for (uint32_t i = 0; i < n; ++i) {
+            const TriIsect &t = G.tris[i];
+            float p0[3] = { t.p0x, t.p0y, t.p0z };
+            float p1[3] = { G.p1[3 * i], G.p1[3 * i + 1], G.p1[3 * i + 2] };
+            float p2[3] = { G.p2[3 * i], G.p2[3 * i + 1], G.p2[3 * i + 2] };
+            refs[i].box.grow(p0);
+            refs[i].box.grow(p1);
+            refs[i].box.grow(p2);
+            for (int a = 0; a < 3; ++a)
+                refs[i].c[a] = 0.5f * (refs[i].box.lo[a] + refs[i].box.hi[a]);
+            refs[i].id = i;
+            gb.grow(refs[i].box);
+        }
+        uint32_t tri_base = (uint32_t) out.tris.size();
+        auto make_leaf = [&](uint32_t lo, uint32_t hi) -> int32_t {
+            uint32_t first = (uint32_t) out.tris.size();
+            for (uint32_t i = lo; i < hi; ++i)
+                out.tris.push_back(G.tris[refs[i].id]);
+            return ~(int32_t) ((first << 4) | (hi - lo));
+        };
+        (void) tri_base;
+        Box bb;
+        int depth = 0;
+        int32_t root;
+        if (n == 0) {
+            // empty group: a leaf with zero triangles is not encodable -> point at an empty range via count 0
+            root = ~(int32_t) (((uint32_t) out.tris.size()) << 4);
+        } else {
+            root = build_range(refs, 0, n, out.nodes, 1, kMaxLeaf, make_leaf, bb, depth);
+        }
+        out.inst_root[g] = root;
+        out.max_depth = std::max(out.max_depth, depth);
+        // world bounds of the instance: union of the group's box corners under both keyframes
+        Box wb;
+        if (n) {
+            if (!G.animated) {
+                wb = gb;
+            } else {
+                for (int c = 0; c < 8; ++c) {
+                    float p[3] = { (c & 1) ? gb.hi[0] : gb.lo[0], (c & 2) ? gb.hi[1] : gb.lo[1], (c & 4) ? gb.hi[2] : gb.lo[2] };
+                    float q[3];
+                    xf_point(G.m0, p, q);
+                    wb.grow(q);
+                    xf_point(G.m1, p, q);
+                    wb.grow(q);
+                }
+            }
+        }
+        inst_boxes[g] = wb;
+    }
+
+    // ---- TLAS over instances (one instance per leaf)
+    std::vector<Ref> irefs;
+    for (size_t g = 0; g < groups.size(); ++g) {
+        if (!inst_boxes[g].valid())
+            continue;
+        Ref r;
+        r.box = inst_boxes[g];
+        for (int a = 0; a < 3; ++a)
+            r.c[a] = 0.5f * (r.box.lo[a] + r.box.hi[a]);
+        r.id = (uint32_t) g;
+        irefs.push_back(r);
+    }
+    int tdepth = 0;
+    if (irefs.empty()) {
+        out.root = ~(int32_t) 0x7fffffff;   // never dereferenced: has_geometry = false
+        out.has_geometry = false;
+    } else {
+        auto make_ileaf = [&](uint32_t lo, uint32_t) -> int32_t { return ~(int32_t) irefs[lo].id; };
+        Box bb;
+        out.root = build_range(irefs, 0, (uint32_t) irefs.size(), out.nodes, 1, 1, make_ileaf, bb, tdepth);
+        out.has_geometry = true;
+        for (int a = 0; a < 3; ++a) {
+            out.scene_lo[a] = bb.lo[a];
+            out.scene_hi[a] = bb.hi[a];
+        }
+    }
+    out.tlas_depth = tdepth;
+}
+
+} // namespace dtof

@@ -1,0 +1,983 @@
+// Device-side building blocks of the B200 Doppler-ToF path tracer (sm_100a).
+//
+// One thread owns one wavefront lane (pixel, sample slot) for its whole life: the three PCG32
+// streams, the ray, the path state and the traversal stack live in registers / L1-resident local
+// memory, so nothing of the per-lane state ever round-trips through HBM ("fused wavefront").
+// Stages (all __device__ functions below, fused by the render kernel in dtof_api.cu):
+//   sampler      LaneSampler            <- src/samplers/correlated.cpp:38-167, src/render/sampler.cpp:85-134
+//   camera       camera_ray()           <- src/sensors/perspective.cpp:238-279
+//   traversal    trace<ANY>()           <- Scene::ray_intersect / ray_test (src/render/scene.cpp:125-154),
+//                                          Embree motion instances (ext/embree/kernels/common/scene_instance.h:133-206)
+//   interaction  compute_si()           <- src/render/mesh.cpp:633-789, src/shapes/instance.cpp:155-250,
+//                                          include/mitsuba/render/interaction.h:258-268,493-516
+//   shading      trace_path()           <- src/integrators/dopplertofpath.cpp:79-283
+//   modulation   Modulation::eval()     <- dopplertofpath.cpp:60-77, include/mitsuba/render/waveform_utils.h:24-62
+//   film         splat_*()              <- src/render/imageblock.cpp:206-232,418-477
+//
+// Floating point: compiled with -fmad=false; every fused multiply-add is an explicit fmaf() placed where the
+// reference fuses (dr::fmadd / Dr.Jit's dot, cross, transform helpers), IEEE division and square root.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/dtof.h"
+#include "dtof_layout.h"
+
+namespace dtof {
+
+#define DTOF_DEV __device__ __forceinline__
+
+constexpr int kStackSize = 96;
+constexpr int kSentinel = (int) 0x80000000;
+constexpr unsigned kFullMask = 0xffffffffu;
+
+// ------------------------------------------------------------------------------------------------
+struct V3 {
+    float x, y, z;
+};
+DTOF_DEV V3 v3(float x, float y, float z) { return V3{ x, y, z }; }
+DTOF_DEV V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+DTOF_DEV V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+DTOF_DEV V3 operator-(V3 a) { return v3(-a.x, -a.y, -a.z); }
+DTOF_DEV V3 operator*(V3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
+DTOF_DEV V3 operator*(V3 a, V3 b) { return v3(a.x * b.x, a.y * b.y, a.z * b.z); }
+DTOF_DEV V3 operator/(V3 a, float s) { return v3(a.x / s, a.y / s, a.z / s); }
+DTOF_DEV V3 fma3(V3 a, float s, V3 b) { return v3(fmaf(a.x, s, b.x), fmaf(a.y, s, b.y), fmaf(a.z, s, b.z)); }
+DTOF_DEV float dot3(V3 a, V3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
+DTOF_DEV V3 cross3(V3 a, V3 b) {
+    return v3(fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x)));
+}
+DTOF_DEV float rsqrt_ieee(float x) { return 1.f / sqrtf(x); }
+DTOF_DEV V3 normalize3(V3 a) { return a * rsqrt_ieee(dot3(a, a)); }
+DTOF_DEV float mulsign(float v, float s) {
+    return __uint_as_float(__float_as_uint(v) ^ (__float_as_uint(s) & 0x80000000u));
+}
+DTOF_DEV float max3(V3 a) { return fmaxf(fmaxf(a.x, a.y), a.z); }
+
+struct M34 {
+    float m[12];
+};
+DTOF_DEV V3 xf_point(const M34 &M, V3 p) {
+    return v3(fmaf(M.m[2], p.z, fmaf(M.m[1], p.y, fmaf(M.m[0], p.x, M.m[3]))),
+              fmaf(M.m[6], p.z, fmaf(M.m[5], p.y, fmaf(M.m[4], p.x, M.m[7]))),
+              fmaf(M.m[10], p.z, fmaf(M.m[9], p.y, fmaf(M.m[8], p.x, M.m[11]))));
+}
+DTOF_DEV V3 xf_vector(const M34 &M, V3 v) {
+    return v3(fmaf(M.m[2], v.z, fmaf(M.m[1], v.y, M.m[0] * v.x)), fmaf(M.m[6], v.z, fmaf(M.m[5], v.y, M.m[4] * v.x)),
+              fmaf(M.m[10], v.z, fmaf(M.m[9], v.y, M.m[8] * v.x)));
+}
+// (M^-1)^T n given Minv
+DTOF_DEV V3 xf_normal(const M34 &Minv, V3 n) {
+    return v3(fmaf(Minv.m[8], n.z, fmaf(Minv.m[4], n.y, Minv.m[0] * n.x)),
+              fmaf(Minv.m[9], n.z, fmaf(Minv.m[5], n.y, Minv.m[1] * n.x)),
+              fmaf(Minv.m[10], n.z, fmaf(Minv.m[6], n.y, Minv.m[2] * n.x)));
+}
+DTOF_DEV M34 inverse_m34(const M34 &M) {
+    const float *a = M.m;
+    float c00 = fmaf(a[5], a[10], -(a[6] * a[9])), c01 = fmaf(a[6], a[8], -(a[4] * a[10])),
+          c02 = fmaf(a[4], a[9], -(a[5] * a[8]));
+    float det = fmaf(a[0], c00, fmaf(a[1], c01, a[2] * c02));
+    float id = 1.f / det;
+    M34 r;
+    r.m[0] = c00 * id;
+    r.m[1] = fmaf(a[2], a[9], -(a[1] * a[10])) * id;
+    r.m[2] = fmaf(a[1], a[6], -(a[2] * a[5])) * id;
+    r.m[4] = c01 * id;
+    r.m[5] = fmaf(a[0], a[10], -(a[2] * a[8])) * id;
+    r.m[6] = fmaf(a[2], a[4], -(a[0] * a[6])) * id;
+    r.m[8] = c02 * id;
+    r.m[9] = fmaf(a[1], a[8], -(a[0] * a[9])) * id;
+    r.m[10] = fmaf(a[0], a[5], -(a[1] * a[4])) * id;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+        r.m[4 * i + 3] = -fmaf(r.m[4 * i + 2], a[11], fmaf(r.m[4 * i + 1], a[7], r.m[4 * i + 0] * a[3]));
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// RNG
+DTOF_DEV void tea32(uint32_t v0, uint32_t v1, uint32_t &o0, uint32_t &o1) {
+    uint32_t sum = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        sum += 0x9e3779b9u;
+        v0 += ((v1 << 4) + 0xa341316cu) ^ (v1 + sum) ^ ((v1 >> 5) + 0xc8013ea4u);
+        v1 += ((v0 << 4) + 0xad90777du) ^ (v0 + sum) ^ ((v0 >> 5) + 0x7e95761eu);
+    }
+    o0 = v0;
+    o1 = v1;
+}
+
+constexpr uint64_t kPcgMult = 0x5851f42d4c957f2dull;
+
+DTOF_DEV uint32_t pcg_output(uint64_t old) {
+    uint32_t xorshifted = (uint32_t) (((old >> 18u) ^ old) >> 27u);
+    uint32_t rot = (uint32_t) (old >> 59u);
+    return __funnelshift_r(xorshifted, xorshifted, rot);   // rotate right
+}
+DTOF_DEV float u32_to_float(uint32_t u) { return __uint_as_float((u >> 9) | 0x3f800000u) - 1.f; }
+
+struct Pcg {
+    uint64_t state, inc;
+    DTOF_DEV uint64_t step() {
+        uint64_t old = state;
+        state = old * kPcgMult + inc;
+        return old;
+    }
+    DTOF_DEV void seed(uint32_t initstate, uint32_t initseq) {
+        state = 0;
+        inc = ((uint64_t) initseq << 1) | 1u;
+        step();
+        state += initstate;
+        step();
+    }
+    DTOF_DEV float next_f32() { return u32_to_float(pcg_output(step())); }
+};
+
+DTOF_DEV uint32_t permute_kensler(uint32_t index, uint32_t sample_count, uint32_t seed) {
+    if (sample_count == 1)
+        return 0;
+    uint32_t w = sample_count - 1;
+    w |= w >> 1;
+    w |= w >> 2;
+    w |= w >> 4;
+    w |= w >> 8;
+    w |= w >> 16;
+    do {
+        uint32_t tmp = index;
+        tmp ^= seed;
+        tmp *= 0xe170893d;
+        tmp ^= seed >> 16;
+        tmp ^= (tmp & w) >> 4;
+        tmp ^= seed >> 8;
+        tmp *= 0x0929eb3f;
+        tmp ^= seed >> 23;
+        tmp ^= (tmp & w) >> 1;
+        tmp *= 1 | seed >> 27;
+        tmp *= 0x6935fa69;
+        tmp ^= (tmp & w) >> 11;
+        tmp *= 0x74dcb303;
+        tmp ^= (tmp & w) >> 2;
+        tmp *= 0x9e501cc3;
+        tmp ^= (tmp & w) >> 2;
+        tmp *= 0xc860a3df;
+        tmp &= w;
+        tmp ^= tmp >> 5;
+        index = tmp;
+    } while (index >= sample_count);
+    return (index + seed) % sample_count;
+}
+
+// CorrelatedSampler (JIT branch). The time stream is consumed once per pass, so only its state is kept.
+struct LaneSampler {
+    Pcg rng, rng_path, rng_time;
+    uint32_t perm_seed, dim, pass, idx_mod_spp;
+    uint32_t draws;
+
+    DTOF_DEV void seed(const dtof_params &p, uint32_t idx, uint32_t spp_pp) {
+        uint32_t S = p.base_seed + p.seed, a, b;
+        tea32(S, idx, a, b);
+        rng.seed(a, b);
+        tea32(S + 1, idx / p.time_correlate_number, a, b);
+        rng_time.seed(a, b);
+        tea32(S + 2, idx / p.path_correlate_number, a, b);
+        rng_path.seed(a, b);
+        uint32_t sequence_idx = spp_pp * (idx / spp_pp);
+        tea32(p.base_seed, sequence_idx + p.seed, a, b);
+        perm_seed = a;
+        dim = 0;
+        pass = 0;
+        idx_mod_spp = spp_pp > 1 ? idx % spp_pp : 0;
+        draws = 0;
+    }
+    DTOF_DEV void advance() {
+        dim = 0;
+        pass++;
+    }
+    // next_1d_correlate: both streams step, one output is formed
+    DTOF_DEV float next_1d(bool correlate) {
+        uint64_t a = rng_path.step(), b = rng.step();
+        draws++;
+        return u32_to_float(pcg_output(correlate ? a : b));
+    }
+    // a draw whose value is never used: only the states move
+    DTOF_DEV void skip_1d() {
+        rng_path.step();
+        rng.step();
+        draws++;
+    }
+    DTOF_DEV float next_time(const dtof_params &p, uint32_t spp_pp) {
+        uint32_t strategy = p.time_sampling_method, tcn = p.time_correlate_number;
+        if (strategy == DTOF_TIME_UNIFORM) {
+            draws++;
+            return rng.next_f32();
+        }
+        uint32_t si = pass * spp_pp + idx_mod_spp;
+        float r;
+        if (strategy == DTOF_TIME_STRATIFIED) {
+            r = rng.next_f32();
+            draws++;
+        } else {
+            r = rng_time.next_f32();
+        }
+        if (p.use_stratified_sampling_for_each_interval) {
+            uint32_t n_stratum = p.sample_count / tcn;
+            uint32_t pp;
+            if (strategy == DTOF_TIME_STRATIFIED) {
+                uint32_t p1 = permute_kensler(si / tcn, n_stratum, perm_seed + dim);
+                uint32_t p2 = permute_kensler(si / tcn, n_stratum, perm_seed + dim + 1);
+                dim += 2;
+                pp = (si % tcn != 0) ? p1 : p2;
+            } else {
+                pp = si / tcn;
+            }
+            r = ((float) pp + r) / (float) (int) n_stratum;
+        }
+        uint32_t rem = si % tcn;
+        if (strategy == DTOF_TIME_STRATIFIED)
+            return ((float) rem + r) * (1.f / (float) tcn);
+        if (strategy == DTOF_TIME_ANTITHETIC) {
+            if (tcn == 2)
+                return rem != 1 ? r : r + p.antithetic_shift;
+            return r + (float) rem / (float) tcn;
+        }
+        float r2 = 1.0f - r + p.antithetic_shift;   // ANTITHETIC_MIRROR
+        return rem != 1 ? r : r2;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Math: Dr.Jit's Cephes sincos (ext/drjit/include/drjit/math.h:76-176) and fmod (array_router.h:484-486)
+DTOF_DEV void dr_sincos(float x, float &s_out, float &c_out) {
+    float xa = fabsf(x);
+    int32_t j = (int32_t) (xa * 1.2732395447351626862f);
+    j = (j + 1) & ~1;
+    float y = (float) j;
+    uint32_t sign_sin = ((uint32_t) j << 29) ^ __float_as_uint(x);
+    uint32_t sign_cos = (uint32_t) (~(j - 2)) << 29;
+    y = xa - y * 0.78515625f - y * 2.4187564849853515625e-4f - y * 3.77489497744594108e-8f;
+    float z = y * y;
+    if (xa == __int_as_float(0x7f800000))
+        z = __int_as_float(0x7fc00000);
+    float z2 = z * z;
+    float s = fmaf(z2, -1.9515295891e-4f, fmaf(z, 8.3321608736e-3f, -1.6666654611e-1f)) * z;
+    float c = fmaf(z2, 2.443315711809948e-5f, fmaf(z, -1.388731625493765e-3f, 4.166664568298827e-2f)) * z;
+    s = fmaf(s, y, y);
+    c = fmaf(c, z, fmaf(z, -0.5f, 1.f));
+    bool polymask = (j & 2) == 0;
+    float rs = polymask ? s : c, rc = polymask ? c : s;
+    s_out = __uint_as_float(__float_as_uint(rs) ^ (sign_sin & 0x80000000u));
+    c_out = __uint_as_float(__float_as_uint(rc) ^ (sign_cos & 0x80000000u));
+}
+DTOF_DEV float dr_cos(float x) {
+    float s, c;
+    dr_sincos(x, s, c);
+    return c;
+}
+DTOF_DEV float dr_fmod(float x, float y) { return fmaf(-truncf(x / y), y, x); }
+
+constexpr float kPi = 3.14159265358979323846f;
+constexpr float kTwoPi = 6.28318530717958647692f;
+constexpr float kInvPi = 0.31830988618379067154f;
+
+DTOF_DEV float waveform_lowpass(float t_, uint32_t type) {
+    float t = dr_fmod(t_, kTwoPi);
+    if (type == DTOF_WAVE_SINUSOIDAL)
+        return dr_cos(t);
+    float a = t / kPi, b = 2.f - a, c = a < b ? a : b;
+    if (type == DTOF_WAVE_RECTANGULAR)
+        return 2.f - 4.f * c;
+    if (type == DTOF_WAVE_TRIANGULAR)
+        return (4.f * c * c * c - 6.f * c * c + 1.f) * 2.f / 3.f;
+    float r = 2.f - 4.f * c;
+    return fminf(fmaxf(2.f * r, -2.f), 2.f);
+}
+DTOF_DEV float waveform_full(float t_, uint32_t type) {
+    float t = dr_fmod(t_, kTwoPi);
+    if (type == DTOF_WAVE_RECTANGULAR)
+        return fabsf(t - kPi) > 0.5f * kPi ? 1.f : -1.f;
+    if (type == DTOF_WAVE_TRIANGULAR)
+        return t < kPi ? 1.f - 2.f * t / kPi : -3.f + 2.f * t / kPi;
+    return dr_cos(t);   // sinusoidal, and trapezoidal falls through (waveform_utils.h:27-32)
+}
+
+// constants derived on the host in double, then narrowed (dopplertofpath.cpp:60-65)
+struct Modulation {
+    float w_g, w_d, k_phi, phase, half_g1, g1, g0, w_gd;
+    uint32_t type, lowpass;
+    DTOF_DEV float eval(float ray_time, float path_length) const {
+        float phi = k_phi * path_length;
+        if (lowpass) {
+            float t = w_d * ray_time + phase + phi;
+            return half_g1 * waveform_lowpass(t, type);
+        }
+        float t1 = fmaf(w_g, ray_time, -phi);
+        float t2 = fmaf(w_gd, ray_time, phase);
+        float g_t = g1 * waveform_full(t1, type) + g0;
+        float s_t = waveform_full(t2, type);
+        return s_t * g_t;
+    }
+};
+
+DTOF_DEV V3 square_to_cosine_hemisphere(float sx, float sy) {
+    float x = fmaf(2.f, sx, -1.f), y = fmaf(2.f, sy, -1.f);
+    bool is_zero = x == 0.f && y == 0.f, q13 = fabsf(x) < fabsf(y);
+    float r = q13 ? y : x, rp = q13 ? x : y;
+    float phi = 0.25f * kPi * rp / r;
+    if (q13)
+        phi = 0.5f * kPi - phi;
+    if (is_zero)
+        phi = 0.f;
+    float s, c;
+    dr_sincos(phi, s, c);
+    float px = r * c, py = r * s;
+    float z = sqrtf(fmaxf(1.f - fmaf(py, py, px * px), 0.f));
+    return v3(px, py, z);
+}
+DTOF_DEV void coordinate_system(V3 n, V3 &s, V3 &t) {
+    float sign = copysignf(1.f, n.z);
+    float a = -1.f / (sign + n.z), b = n.x * n.y * a;
+    s = v3(mulsign(n.x * n.x * a, n.z) + 1.f, mulsign(b, n.z), mulsign(-n.x, n.z));
+    t = v3(b, fmaf(n.y, n.y * a, sign), -n.y);
+}
+DTOF_DEV void square_to_uniform_triangle(float sx, float sy, float &bx, float &by) {
+    float t = sqrtf(fmaxf(1.f - sx, 0.f));
+    bx = 1.f - t;
+    by = t * sy;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Scene access
+struct DeviceScene {
+    const float4 *nodes;    // BvhNode  = 4 x float4
+    const float4 *tris;     // TriIsect = 3 x float4
+    const float4 *shade;    // TriShade = 7 x float4
+    const float4 *insts;    // InstRec  = 7 x float4
+    const MeshRec *meshes;
+    const BsdfRec *bsdfs;
+    const EmitterRec *emitters;
+    const float *area_cdf, *area_pmf;
+    int32_t root;
+    uint32_t n_emitters, n_insts, n_nodes, n_tris, has_geometry;
+};
+
+struct Counters {
+    unsigned long long rays_closest, rays_shadow, nodes, tris, inst, samples;
+};
+
+struct Hit {
+    float t, u, v;
+    uint32_t gid;
+    int32_t inst;
+};
+
+DTOF_DEV void load_inst_matrix(const float4 *ip, float time, bool clamp, M34 &M) {
+    // AnimatedTransform::eval (clamped, transform.h:451-456) or Embree's unclamped fraction (default.h:225-231)
+    float4 q6 = ip[6];
+    float f = (time - q6.x) / (q6.y - q6.x);
+    if (clamp)
+        f = fminf(fmaxf(f, 0.f), 1.f);
+    float s = 1.f - f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float4 a = ip[k], b = ip[3 + k];
+        M.m[4 * k + 0] = fmaf(b.x, f, a.x * s);
+        M.m[4 * k + 1] = fmaf(b.y, f, a.y * s);
+        M.m[4 * k + 2] = fmaf(b.z, f, a.z * s);
+        M.m[4 * k + 3] = fmaf(b.w, f, a.w * s);
+    }
+}
+
+// Closest-hit (ANY=false) or any-hit (ANY=true) traversal of the two-level BVH with per-ray time.
+// `N`, `T`, `I` are the node / triangle / instance arrays (global memory, or their shared-memory copies).
+template <bool ANY, bool STATS>
+DTOF_DEV bool trace(const float4 *__restrict__ N, const float4 *__restrict__ T, const float4 *__restrict__ I,
+                    int32_t root, V3 o, V3 d, float tmax, float time, Hit &hit, Counters &st) {
+    int stack[kStackSize];
+    int sp = 0;
+    int node = root;
+    bool in_blas = false;
+    int cur_inst = -1;
+    V3 ro = o, rd = d;                                       // ray in the current (world / object) space
+    V3 id = v3(1.f / d.x, 1.f / d.y, 1.f / d.z);
+    float best = tmax;
+    bool found = false;
+    if (STATS) {
+        if (ANY) st.rays_shadow++; else st.rays_closest++;
+    }
+    for (;;) {
+        // ---- descend through inner nodes
+        while (node >= 0) {
+            const float4 *np = N + 4 * (size_t) node;
+            float4 n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3];
+            if (STATS) st.nodes++;
+            // slab test in (b - o) * idir form: purely relative rounding error, absorbed by the widened far side
+            float c0lx = (n0.x - ro.x) * id.x, c0hx = (n0.y - ro.x) * id.x;
+            float c0ly = (n0.z - ro.y) * id.y, c0hy = (n0.w - ro.y) * id.y;
+            float c0lz = (n2.x - ro.z) * id.z, c0hz = (n2.y - ro.z) * id.z;
+            float c1lx = (n1.x - ro.x) * id.x, c1hx = (n1.y - ro.x) * id.x;
+            float c1ly = (n1.z - ro.y) * id.y, c1hy = (n1.w - ro.y) * id.y;
+            float c1lz = (n2.z - ro.z) * id.z, c1hz = (n2.w - ro.z) * id.z;
+            float t0n = fmaxf(fmaxf(fminf(c0lx, c0hx), fminf(c0ly, c0hy)), fmaxf(fminf(c0lz, c0hz), 0.f));
+            float t0f = fminf(fminf(fmaxf(c0lx, c0hx), fmaxf(c0ly, c0hy)), fmaxf(c0lz, c0hz)) * 1.0000005f;
+            float t1n = fmaxf(fmaxf(fminf(c1lx, c1hx), fminf(c1ly, c1hy)), fmaxf(fminf(c1lz, c1hz), 0.f));
+            float t1f = fminf(fminf(fmaxf(c1lx, c1hx), fmaxf(c1ly, c1hy)), fmaxf(c1lz, c1hz)) * 1.0000005f;
+            bool h0 = t0n <= fminf(t0f, best), h1 = t1n <= fminf(t1f, best);
+            int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+            if (h0 && h1) {
+                bool swap = t1n < t0n;
+                int nearc = swap ? c1 : c0, farc = swap ? c0 : c1;
+                stack[sp++] = farc;
+                node = nearc;
+            } else if (h0) {
+                node = c0;
+            } else if (h1) {
+                node = c1;
+            } else {
+                goto pop;
+            }
+        }
+        // ---- leaf
+        if (!in_blas) {
+            // TLAS leaf: enter the instance (Embree: world->local = rcp(lerp(M0, M1, f)), unclamped f)
+            cur_inst = ~node;
+            const float4 *ip = I + 7 * (size_t) cur_inst;
+            float4 q6 = ip[6];
+            if (__float_as_uint(q6.w) != 0u) {
+                if (STATS) st.inst++;
+                M34 M;
+                load_inst_matrix(ip, time, false, M);
+                M34 inv = inverse_m34(M);
+                ro = xf_point(inv, o);
+                rd = xf_vector(inv, d);
+                id = v3(1.f / rd.x, 1.f / rd.y, 1.f / rd.z);
+            }
+            stack[sp++] = kSentinel;
+            in_blas = true;
+            node = __float_as_int(q6.z);
+            continue;
+        } else {
+            uint32_t code = (uint32_t) ~node;
+            uint32_t first = code >> 4, count = code & 15u;
+            for (uint32_t i = 0; i < count; ++i) {
+                const float4 *tp = T + 3 * (size_t) (first + i);
+                float4 a = tp[0], b = tp[1], c = tp[2];
+                if (STATS) st.tris++;
+                // moeller_trumbore, include/mitsuba/render/mesh.h:342-365
+                V3 e1 = v3(b.x, b.y, b.z), e2 = v3(c.x, c.y, c.z);
+                V3 pvec = cross3(rd, e2);
+                float inv_det = 1.f / dot3(e1, pvec);
+                V3 tvec = ro - v3(a.x, a.y, a.z);
+                float u = dot3(tvec, pvec) * inv_det;
+                V3 qvec = cross3(tvec, e1);
+                float v = dot3(rd, qvec) * inv_det;
+                float t = dot3(e2, qvec) * inv_det;
+                bool ok = u >= 0.f && u <= 1.f && v >= 0.f && u + v <= 1.f && t >= 0.f && t <= best;
+                if (ok) {
+                    if (ANY)
+                        return true;
+                    uint32_t gid = __float_as_uint(a.w);
+                    if (t < best || !found || gid < hit.gid) {
+                        best = t;
+                        hit.t = t;
+                        hit.u = u;
+                        hit.v = v;
+                        hit.gid = gid;
+                        hit.inst = cur_inst;
+                        found = true;
+                    }
+                }
+            }
+        }
+    pop:
+        if (sp == 0)
+            break;
+        node = stack[--sp];
+        if (node == kSentinel) {   // leave the instance: back to the world-space ray
+            in_blas = false;
+            ro = o;
+            rd = d;
+            id = v3(1.f / d.x, 1.f / d.y, 1.f / d.z);
+            if (sp == 0)
+                break;
+            node = stack[--sp];
+        }
+    }
+    return found;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct SI {
+    V3 p, n, sh_n, sh_s, sh_t, wi;
+    uint32_t mesh;
+};
+
+DTOF_DEV void compute_si(const DeviceScene &S, const float4 *__restrict__ I, const Hit &h, V3 ray_d, float ray_time,
+                         SI &si) {
+    const float4 *sp = S.shade + 7 * (size_t) h.gid;
+    float4 s0 = __ldg(sp + 0), s1 = __ldg(sp + 1), s2 = __ldg(sp + 2);
+    V3 p0 = v3(s0.x, s0.y, s0.z), p1 = v3(s1.x, s1.y, s1.z), p2 = v3(s2.x, s2.y, s2.z);
+    uint32_t flags = __float_as_uint(s1.w);
+    si.mesh = __float_as_uint(s0.w);
+    float b1 = h.u, b2 = h.v, b0 = 1.f - b1 - b2;
+    V3 dp0 = p1 - p0, dp1 = p2 - p0;
+    si.p = fma3(p0, b0, fma3(p1, b1, p2 * b2));
+    si.n = normalize3(cross3(dp0, dp1));
+    V3 dp_du, dp_dv;
+    coordinate_system(si.n, dp_du, dp_dv);
+    float4 s3, s4, s5, s6;
+    if (flags & (TRI_HAS_NORMALS | TRI_HAS_UV)) {
+        s3 = __ldg(sp + 3), s4 = __ldg(sp + 4), s5 = __ldg(sp + 5), s6 = __ldg(sp + 6);
+    }
+    if (flags & TRI_HAS_UV) {
+        float u0x = s5.y, u0y = s5.z, u1x = s5.w, u1y = s6.x, u2x = s6.y, u2y = s6.z;
+        float d0x = u1x - u0x, d0y = u1y - u0y, d1x = u2x - u0x, d1y = u2y - u0y;
+        float det = fmaf(d0x, d1y, -(d0y * d1x));
+        if (det != 0.f) {
+            float inv_det = 1.f / det;
+            dp_du = v3(fmaf(d1y, dp0.x, -(d0y * dp1.x)), fmaf(d1y, dp0.y, -(d0y * dp1.y)),
+                       fmaf(d1y, dp0.z, -(d0y * dp1.z))) *
+                    inv_det;
+        }
+    }
+    if (flags & TRI_HAS_NORMALS) {
+        V3 n0 = v3(s3.x, s3.y, s3.z), n1 = v3(s3.w, s4.x, s4.y), n2 = v3(s4.z, s4.w, s5.x);
+        V3 n = fma3(n2, b2, fma3(n1, b1, n0 * b0));
+        si.sh_n = n * rsqrt_ieee(dot3(n, n));
+    } else {
+        si.sh_n = si.n;
+    }
+    if (flags & TRI_FLIP) {
+        si.n = -si.n;
+        si.sh_n = -si.sh_n;
+    }
+    const float4 *ip = I + 7 * (size_t) h.inst;
+    if (__float_as_uint(ip[6].w) != 0u) {
+        M34 to_world;
+        load_inst_matrix(ip, ray_time, true, to_world);
+        M34 to_object = inverse_m34(to_world);
+        si.p = xf_point(to_world, si.p);
+        si.n = normalize3(xf_normal(to_object, si.n));
+        si.sh_n = normalize3(xf_normal(to_object, si.sh_n));
+        dp_du = xf_vector(to_world, dp_du);
+    }
+    si.sh_s = normalize3(fma3(si.sh_n, -dot3(si.sh_n, dp_du), dp_du));
+    if (dp_du.x == 0.f && dp_du.y == 0.f && dp_du.z == 0.f) {
+        V3 tmp;
+        coordinate_system(si.sh_n, si.sh_s, tmp);
+    }
+    si.sh_t = cross3(si.sh_n, si.sh_s);
+    V3 md = -ray_d;
+    si.wi = v3(dot3(md, si.sh_s), dot3(md, si.sh_t), dot3(md, si.sh_n));
+}
+
+constexpr float kRayEps = 1500.f * 5.9604644775390625e-08f;
+constexpr float kShadowEps = kRayEps * 10.f;
+
+DTOF_DEV V3 offset_p(V3 p, V3 n, V3 d) {
+    float mag = (1.f + fmaxf(fmaxf(fabsf(p.x), fabsf(p.y)), fabsf(p.z))) * kRayEps;
+    mag = mulsign(mag, dot3(n, d));
+    return fma3(n, mag, p);
+}
+DTOF_DEV float mis_weight(float a, float b) {
+    a *= a;
+    b *= b;
+    float w = a / (a + b);
+    return isfinite(w) ? w : 0.f;
+}
+
+DTOF_DEV void sample_position(const DeviceScene &S, const MeshRec &m, float sx, float sy, V3 &p, V3 &n, float &pdf) {
+    if (m.kind == DTOF_SHAPE_RECTANGLE) {
+        M34 tw;
+#pragma unroll
+        for (int i = 0; i < 12; ++i)
+            tw.m[i] = m.rect_to_world[i];
+        p = xf_point(tw, v3(sx * 2.f - 1.f, sy * 2.f - 1.f, 0.f));
+        n = v3(m.rect_n[0], m.rect_n[1], m.rect_n[2]);
+        pdf = m.inv_area;
+        return;
+    }
+    const float *cdf = S.area_cdf + m.cdf_offset, *pmf = S.area_pmf + m.cdf_offset;
+    float value = sy * m.area_sum;
+    uint32_t lo = m.valid_lo, hi = m.valid_hi;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) / 2;
+        if (cdf[mid] < value)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    uint32_t face = lo;
+    float pmf_n = pmf[face] * m.inv_area;
+    float cdf_n = face > 0 ? cdf[face - 1] * m.inv_area : 0.f;
+    sy = (sy - cdf_n) / pmf_n;
+    const float4 *sp = S.shade + 7 * (size_t) (m.first_gid + face);
+    float4 s0 = __ldg(sp + 0), s1 = __ldg(sp + 1), s2 = __ldg(sp + 2);
+    V3 p0 = v3(s0.x, s0.y, s0.z), p1 = v3(s1.x, s1.y, s1.z), p2 = v3(s2.x, s2.y, s2.z);
+    uint32_t flags = __float_as_uint(s1.w);
+    V3 e0 = p1 - p0, e1 = p2 - p0;
+    float bx, by;
+    square_to_uniform_triangle(sx, sy, bx, by);
+    p = fma3(e0, bx, fma3(e1, by, p0));
+    pdf = m.inv_area;
+    if (flags & TRI_HAS_NORMALS) {
+        float4 s3 = __ldg(sp + 3), s4 = __ldg(sp + 4), s5 = __ldg(sp + 5);
+        V3 n0 = v3(s3.x, s3.y, s3.z), n1 = v3(s3.w, s4.x, s4.y), n2 = v3(s4.z, s4.w, s5.x);
+        n = fma3(n0, 1.f - bx - by, fma3(n1, bx, n2 * by));
+    } else {
+        n = cross3(e0, e1);
+    }
+    n = normalize3(n);
+    if (flags & TRI_FLIP)
+        n = -n;
+}
+
+struct PathOut {
+    V3 rgb;
+    float path_length;
+    uint32_t depth;
+};
+
+// DopplerToFPathIntegrator::sample (JIT semantics), see the oracle for the line-by-line citations
+template <bool STATS>
+DTOF_DEV PathOut trace_path(const DeviceScene &S, const float4 *__restrict__ N, const float4 *__restrict__ T,
+                            const float4 *__restrict__ I, const dtof_params &P, const Modulation &mod,
+                            LaneSampler &smp, V3 ray_o, V3 ray_d, float ray_maxt, float time_in, Counters &st) {
+    PathOut out{ v3(0, 0, 0), 0.f, 0 };
+    if (P.max_depth == 0)
+        return out;
+    const uint32_t max_depth = (uint32_t) P.max_depth, rr_depth = (uint32_t) P.rr_depth;
+    const float ray_time = time_in < P.time ? time_in : time_in - P.time;
+    V3 throughput = v3(1, 1, 1), result = v3(0, 0, 0);
+    float path_length = 0.f, eta = 1.f;
+    uint32_t depth = 0;
+    bool valid_ray = false;
+    V3 prev_p = v3(0, 0, 0);
+    float prev_bsdf_pdf = 1.f;
+    bool prev_bsdf_delta = true;
+    bool active = true;
+    const uint32_t n_em = S.n_emitters;
+    const float emitter_pmf = n_em ? 1.f / (float) n_em : 0.f;
+
+    while (active) {
+        const bool correlate = (depth + 1) < P.path_correlation_depth;
+        Hit h;
+        h.gid = 0;
+        bool valid = S.has_geometry && trace<false, STATS>(N, T, I, S.root, ray_o, ray_d, ray_maxt, ray_time, h, st);
+        SI si;
+        uint32_t bsdf_flags = 0;
+        V3 refl = v3(0, 0, 0);
+        int32_t mesh_emitter = -1;
+        if (valid) {
+            compute_si(S, I, h, ray_d, ray_time, si);
+            const MeshRec &mr = S.meshes[si.mesh];
+            mesh_emitter = mr.emitter;
+            const BsdfRec br = S.bsdfs[mr.bsdf];
+            bsdf_flags = br.flags;
+            refl = v3(br.r, br.g, br.b);
+            path_length += h.t * eta;
+        }
+        // ---- direct emission
+        if (valid && mesh_emitter >= 0) {
+            const MeshRec &em_mesh = S.meshes[si.mesh];
+            const EmitterRec em = S.emitters[mesh_emitter];
+            V3 rel = si.p - prev_p;
+            float dist = sqrtf(dot3(rel, rel));
+            V3 dsd = rel / dist;
+            float em_pdf = 0.f;
+            if (!prev_bsdf_delta) {
+                float dp = dot3(dsd, si.sh_n);
+                float pdf = em_mesh.inv_area, adp = fabsf(dp);
+                pdf *= adp != 0.f ? (dist * dist) / adp : 0.f;
+                em_pdf = (dp < 0.f ? pdf : 0.f) * emitter_pmf;
+            }
+            float mis_bsdf = mis_weight(prev_bsdf_pdf, em_pdf);
+            float lw = mod.eval(ray_time, path_length);
+            V3 Le = (si.wi.z > 0.f && prev_bsdf_pdf > 0.f) ? v3(em.vr, em.vg, em.vb) : v3(0, 0, 0);
+            V3 c = Le * mis_bsdf * lw;
+            result = v3(fmaf(throughput.x, c.x, result.x), fmaf(throughput.y, c.y, result.y),
+                        fmaf(throughput.z, c.z, result.z));
+        }
+        const bool active_next = (depth + 1 < max_depth) && valid;
+        const bool smooth = (bsdf_flags & 2u) != 0;
+        const bool twosided = (bsdf_flags & 1u) != 0;
+
+        // ---- emitter sampling: the 2D sample is always consumed
+        uint64_t e1a = smp.rng_path.step(), e1b = smp.rng.step();
+        uint64_t e2a = smp.rng_path.step(), e2b = smp.rng.step();
+        smp.draws += 2;
+        bool active_em = active_next && smooth && n_em > 0;
+        V3 ds_d = v3(0, 0, 0), em_weight = v3(0, 0, 0), wo = v3(0, 0, 0);
+        float ds_dist = 0.f, ds_pdf = 0.f;
+        bool ds_delta = false;
+        if (active_em) {
+            uint32_t index = 0;
+            float sx = 0.f, sy = 0.f;
+            V3 ds_p, ds_n, spec;
+            EmitterRec em = S.emitters[0];
+            if (n_em > 1 || em.kind != DTOF_EMITTER_POINT) {
+                sx = u32_to_float(pcg_output(correlate ? e1a : e1b));
+                sy = u32_to_float(pcg_output(correlate ? e2a : e2b));
+            }
+            if (n_em > 1) {
+                float scaled = sx * (float) n_em;
+                index = min((uint32_t) scaled, n_em - 1u);
+                sx = scaled - (float) index;
+                em = S.emitters[index];
+            }
+            if (em.kind == DTOF_EMITTER_POINT) {
+                ds_p = v3(em.px, em.py, em.pz);
+                ds_pdf = 1.f;
+                ds_delta = true;
+                ds_d = ds_p - si.p;
+                float dist2 = dot3(ds_d, ds_d), inv_dist = rsqrt_ieee(dist2);
+                ds_dist = sqrtf(dist2);
+                ds_d = ds_d * inv_dist;
+                float f = inv_dist * inv_dist;
+                spec = v3(em.vr * f, em.vg * f, em.vb * f);
+            } else {
+                sample_position(S, S.meshes[em.mesh], sx, sy, ds_p, ds_n, ds_pdf);
+                ds_d = ds_p - si.p;
+                float dist2 = dot3(ds_d, ds_d);
+                ds_dist = sqrtf(dist2);
+                ds_d = ds_d / ds_dist;
+                float dp = fabsf(dot3(ds_d, ds_n));
+                float x = dist2 / dp;
+                ds_pdf *= isfinite(x) ? x : 0.f;
+                bool em_active = dot3(ds_d, ds_n) < 0.f && ds_pdf != 0.f;
+                spec = em_active ? v3(em.vr / ds_pdf, em.vg / ds_pdf, em.vb / ds_pdf) : v3(0, 0, 0);
+            }
+            if (n_em > 1) {
+                ds_pdf *= emitter_pmf;
+                spec = spec * (float) n_em;
+            }
+            if (ds_pdf != 0.f) {
+                V3 so = offset_p(si.p, si.n, ds_p - si.p);
+                V3 sd = ds_p - so;
+                float dist = sqrtf(dot3(sd, sd));
+                sd = sd / dist;
+                Hit dummy;
+                if (trace<true, STATS>(N, T, I, S.root, so, sd, dist * (1.f - kShadowEps), ray_time, dummy, st)) {
+                    spec = v3(0, 0, 0);
+                    ds_pdf = 0.f;
+                }
+            }
+            em_weight = spec;
+            active_em = ds_pdf != 0.f;
+            wo = v3(dot3(ds_d, si.sh_s), dot3(ds_d, si.sh_t), dot3(ds_d, si.sh_n));
+        }
+
+        // ---- BSDF eval + sample; sample_1 is drawn but unused by the diffuse lobe
+        smp.skip_1d();
+        float s2x = smp.next_1d(correlate), s2y = smp.next_1d(correlate);
+        V3 bsdf_val = v3(0, 0, 0), bsdf_weight = v3(0, 0, 0), bs_wo = v3(0, 0, 0);
+        float bsdf_pdf = 0.f, bs_pdf = 0.f, bs_eta = 0.f;
+        if (valid && smooth) {
+            float wi_z = si.wi.z, wo_z = wo.z;
+            if (twosided) {
+                wo_z = mulsign(wo_z, wi_z);
+                wi_z = fabsf(wi_z);
+            }
+            if (wi_z > 0.f && wo_z > 0.f) {
+                bsdf_val = refl * kInvPi * wo_z;
+                bsdf_pdf = kInvPi * wo_z;
+            }
+            if (wi_z > 0.f) {
+                bs_wo = square_to_cosine_hemisphere(s2x, s2y);
+                bs_pdf = kInvPi * bs_wo.z;
+                bs_eta = 1.f;
+                if (bs_pdf > 0.f)
+                    bsdf_weight = refl;
+                if (twosided)
+                    bs_wo.z = mulsign(bs_wo.z, si.wi.z);
+            }
+        }
+        if (active_em) {
+            float mis_em = ds_delta ? 1.f : mis_weight(ds_pdf, bsdf_pdf);
+            float lw = mod.eval(ray_time, path_length + ds_dist);
+            V3 c = bsdf_val * em_weight * mis_em * lw;
+            result = v3(fmaf(throughput.x, c.x, result.x), fmaf(throughput.y, c.y, result.y),
+                        fmaf(throughput.z, c.z, result.z));
+        }
+        if (valid) {
+            V3 wd = fma3(si.sh_n, bs_wo.z, fma3(si.sh_t, bs_wo.y, si.sh_s * bs_wo.x));
+            ray_o = offset_p(si.p, si.n, wd);
+            ray_d = wd;
+            ray_maxt = 3.402823466e+38f;
+            prev_p = si.p;
+        }
+        throughput = throughput * bsdf_weight;
+        eta *= bs_eta;
+        valid_ray = valid_ray || valid;
+        prev_bsdf_pdf = bs_pdf;
+        prev_bsdf_delta = false;
+        if (valid)
+            depth += 1;
+        float tmax = max3(throughput);
+        float rr_prob = fminf(tmax * (eta * eta), 0.95f);
+        bool rr_active = depth >= rr_depth;
+        float q = smp.next_1d(correlate);
+        bool rr_continue = q < rr_prob;
+        if (rr_active)
+            throughput = throughput * (1.f / rr_prob);
+        active = active_next && (!rr_active || rr_continue) && tmax != 0.f;
+    }
+    out.rgb = valid_ray ? result : v3(0, 0, 0);
+    out.path_length = path_length;
+    out.depth = depth;
+    return out;
+}
+
+DTOF_DEV void camera_ray(const dtof_camera &c, float u, float v, V3 &o, V3 &d, float &maxt) {
+    const float *m = c.sample_to_camera;
+    float r[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        r[i] = fmaf(m[4 * i + 2], 0.f, fmaf(m[4 * i + 1], v, fmaf(m[4 * i + 0], u, m[4 * i + 3])));
+    V3 near_p = v3(r[0] / r[3], r[1] / r[3], r[2] / r[3]);
+    V3 dl = normalize3(near_p);
+    M34 tw;
+#pragma unroll
+    for (int i = 0; i < 12; ++i)
+        tw.m[i] = c.to_world[i];
+    o = v3(tw.m[3], tw.m[7], tw.m[11]);
+    d = xf_vector(tw, dl);
+    float inv_z = 1.f / dl.z;
+    float near_t = c.near_clip * inv_z, far_t = c.far_clip * inv_z;
+    o = o + d * near_t;
+    maxt = far_t - near_t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Film
+struct FilmParams {
+    float *rgbw;               // (H, W, 4) accumulation tensor
+    uint32_t width, height, crop_x, crop_y, rfilter;
+    float radius, inv_radius, g_alpha, g_bias;
+    int n;                     // ceil(radius - .5)
+};
+
+DTOF_DEV float rfilter_eval(const FilmParams &F, float x) {
+    if (F.rfilter == DTOF_RFILTER_TENT)
+        return fmaxf(0.f, 1.f - fabsf(x * F.inv_radius));
+    return fmaxf(0.f, expf(F.g_alpha * x * x) - F.g_bias);
+}
+
+// generic path: per-lane atomics (any filter, lanes of a warp on different pixels)
+DTOF_DEV void splat_generic(const FilmParams &F, float px, float py, V3 rgb) {
+    if (F.rfilter == DTOF_RFILTER_BOX) {
+        int x = (int) floorf(px) - (int) F.crop_x, y = (int) floorf(py) - (int) F.crop_y;
+        if ((uint32_t) x < F.width && (uint32_t) y < F.height) {
+            float *dst = F.rgbw + ((size_t) y * F.width + x) * 4;
+            atomicAdd(dst + 0, rgb.x);
+            atomicAdd(dst + 1, rgb.y);
+            atomicAdd(dst + 2, rgb.z);
+            atomicAdd(dst + 3, 1.f);
+        }
+        return;
+    }
+    int n = F.n, count = 2 * n + 1;
+    int pix = (int) floorf(px) - n, piy = (int) floorf(py) - n;
+    float rx = (float) pix + .5f - px, ry0 = (float) piy + .5f - py;
+    int lx = pix - (int) F.crop_x, ly = piy - (int) F.crop_y;
+    for (int xs = 0; xs < count; ++xs) {
+        float wx = rfilter_eval(F, rx);
+        rx += 1.f;
+        uint32_t x = (uint32_t) (lx + xs);
+        if (x >= F.width)
+            continue;
+        float ry = ry0;
+        for (int ys = 0; ys < count; ++ys) {
+            float wy = rfilter_eval(F, ry);
+            ry += 1.f;
+            uint32_t y = (uint32_t) (ly + ys);
+            if (y >= F.height)
+                continue;
+            float w = wy * wx;
+            float *dst = F.rgbw + ((size_t) y * F.width + x) * 4;
+            atomicAdd(dst + 0, rgb.x * w);
+            atomicAdd(dst + 1, rgb.y * w);
+            atomicAdd(dst + 2, rgb.z * w);
+            atomicAdd(dst + 3, w);
+        }
+    }
+}
+
+// Transposing butterfly: every lane contributes v[0..31]; afterwards lane l holds sum over lanes of v[l].
+// 31 shuffles instead of 32 x 5.
+DTOF_DEV float warp_transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            float keep = up ? v[i + off] : v[i];
+            float send = up ? v[i] : v[i + off];
+            v[i] = keep + __shfl_xor_sync(kFullMask, send, off);
+        }
+    }
+    return v[0];
+}
+// 16-value variant: lane l (and l ^ 16) ends with the sum over all 32 lanes of v[l & 15]
+DTOF_DEV float warp_transpose_reduce16(float (&v)[16], int lane) {
+#pragma unroll
+    for (int off = 8; off >= 1; off >>= 1) {
+        bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            float keep = up ? v[i + off] : v[i];
+            float send = up ? v[i] : v[i + off];
+            v[i] = keep + __shfl_xor_sync(kFullMask, send, off);
+        }
+    }
+    return v[0] + __shfl_xor_sync(kFullMask, v[0], 16);
+}
+
+// Warp-aggregated 3x3 tent splat: all lanes of the warp belong to pixel (ix, iy) (pixel-major lanes), so the
+// 9 taps x 4 channels are reduced across the warp first and only 36 atomics per warp reach L2.
+DTOF_DEV void splat_tent3_warp(const FilmParams &F, int ix, int iy, float px, float py, V3 rgb, bool lane_on, int lane) {
+    // ix, iy = floor(sample_pos) (identical on all lanes); taps ix-1..ix+1
+    float rx = (float) (ix - 1) + .5f - px, ry = (float) (iy - 1) + .5f - py;
+    float wx[3], wy[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        wx[i] = lane_on ? rfilter_eval(F, rx) : 0.f;
+        wy[i] = lane_on ? rfilter_eval(F, ry) : 0.f;
+        rx += 1.f;
+        ry += 1.f;
+    }
+    float vc[32], vw[16];
+#pragma unroll
+    for (int ys = 0; ys < 3; ++ys)
+#pragma unroll
+        for (int xs = 0; xs < 3; ++xs) {
+            float w = wy[ys] * wx[xs];
+            int tap = ys * 3 + xs;
+            vc[tap * 3 + 0] = rgb.x * w;
+            vc[tap * 3 + 1] = rgb.y * w;
+            vc[tap * 3 + 2] = rgb.z * w;
+            vw[tap] = w;
+        }
+#pragma unroll
+    for (int i = 27; i < 32; ++i)
+        vc[i] = 0.f;
+#pragma unroll
+    for (int i = 9; i < 16; ++i)
+        vw[i] = 0.f;
+    float c = warp_transpose_reduce32(vc, lane);
+    float w = warp_transpose_reduce16(vw, lane);
+    int lx = ix - 1 - (int) F.crop_x, ly = iy - 1 - (int) F.crop_y;
+    if (lane < 27) {
+        int tap = lane / 3, ch = lane - tap * 3;
+        uint32_t x = (uint32_t) (lx + tap % 3), y = (uint32_t) (ly + tap / 3);
+        if (x < F.width && y < F.height)
+            atomicAdd(F.rgbw + ((size_t) y * F.width + x) * 4 + ch, c);
+    }
+    if (lane < 9) {
+        uint32_t x = (uint32_t) (lx + lane % 3), y = (uint32_t) (ly + lane / 3);
+        if (x < F.width && y < F.height)
+            atomicAdd(F.rgbw + ((size_t) y * F.width + x) * 4 + 3, w);
+    }
+}
+
+} // namespace dtof

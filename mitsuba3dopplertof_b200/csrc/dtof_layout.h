@@ -1,0 +1,85 @@
+// Device-memory layout of a flattened scene (shared by the host builder and the CUDA kernels).
+//
+// Everything a ray touches during traversal is a 16-byte-aligned record fetched with 128-bit loads:
+//   BvhNode   64 B  binary BVH node holding BOTH children's boxes (so one fetch decides both sides)
+//   TriIsect  48 B  p0 + the two edges + the triangle's global id (Moeller-Trumbore inputs, mesh.h:342-365)
+//   InstRec  112 B  per-instance motion: two 3x4 keyframes, key times, BLAS root
+// and, once per hit,
+//   TriShade  96 B  p1, p2, vertex normals, uvs, mesh id/flags (Mesh::compute_surface_interaction inputs)
+// These sizes are the per-unit figures of the traversal roofline.
+#pragma once
+#include <stdint.h>
+
+namespace dtof {
+
+// Child reference encoding: ref >= 0 -> inner node index; ref < 0 -> leaf.
+//   TLAS leaf: ~ref = instance index.   BLAS leaf: ~ref = (first_tri << 4) | count, count in [1, 15].
+struct alignas(16) BvhNode {
+    float c0_lox, c0_hix, c0_loy, c0_hiy;   // child 0 box x/y
+    float c1_lox, c1_hix, c1_loy, c1_hiy;   // child 1 box x/y
+    float c0_loz, c0_hiz, c1_loz, c1_hiz;   // z of both
+    int32_t child0, child1, pad0, pad1;
+};
+static_assert(sizeof(BvhNode) == 64, "BvhNode must be 64 bytes");
+
+struct alignas(16) TriIsect {
+    float p0x, p0y, p0z;
+    uint32_t gid;          // global triangle id (order of the scene description) -> deterministic tie-break + shading lookup
+    float e1x, e1y, e1z, pad1;
+    float e2x, e2y, e2z, pad2;
+};
+static_assert(sizeof(TriIsect) == 48, "TriIsect must be 48 bytes");
+
+enum : uint32_t { TRI_HAS_NORMALS = 1u, TRI_HAS_UV = 2u, TRI_FLIP = 4u };
+
+struct alignas(16) TriShade {   // indexed by gid
+    float p0x, p0y, p0z;
+    uint32_t mesh;
+    float p1x, p1y, p1z;
+    uint32_t flags;
+    float p2x, p2y, p2z, pad;
+    float n0x, n0y, n0z, n1x;
+    float n1y, n1z, n2x, n2y;
+    float n2z, uv0x, uv0y, uv1x;
+    float uv1y, uv2x, uv2y, pad2;
+};
+static_assert(sizeof(TriShade) == 112, "TriShade must be 112 bytes");
+
+struct alignas(16) InstRec {
+    float m0[12];
+    float m1[12];
+    float t0, t1;
+    int32_t root;          // child reference of the BLAS root
+    uint32_t animated;
+};
+static_assert(sizeof(InstRec) == 112, "InstRec must be 112 bytes");
+
+struct MeshRec {
+    uint32_t bsdf;
+    int32_t emitter;
+    uint32_t kind;         // dtof_shape_kind
+    uint32_t n_faces;
+    // area-emitter sampling (Rectangle::sample_position / Mesh::sample_position)
+    float rect_to_world[12];
+    float rect_n[3];
+    float inv_area;        // rectangle: 1/area; mesh: area pmf normalisation
+    float area_sum;
+    uint32_t cdf_offset;   // into the area cdf/pmf arrays (mesh emitters)
+    uint32_t valid_lo, valid_hi;
+    uint32_t first_gid;    // global id of the mesh's face 0
+    uint32_t pad[3];
+};
+
+struct BsdfRec {
+    float r, g, b;
+    uint32_t flags;        // bit0: twosided, bit1: smooth diffuse lobe present
+};
+
+struct EmitterRec {
+    uint32_t kind;         // dtof_emitter_kind
+    uint32_t mesh;
+    float px, py, pz;
+    float vr, vg, vb;
+};
+
+} // namespace dtof

@@ -137,7 +137,10 @@ class DopplerToFPathIntegrator:
         from .runtime import get_context   # deferred: importing the package must not need a GPU
         self._stop = False
         ctx = get_context(device)
-        flat = ctx.upload(scene)
+        cached = getattr(scene, "_dtof_uploaded", None)
+        if cached is None or cached[0] is not ctx or ctx._flat is not cached[1]:
+            scene._dtof_uploaded = (ctx, ctx.upload(scene))   # flatten + BVH build + H2D once per scene
+        flat = scene._dtof_uploaded[1]
         p = self.params(scene.sensor.sampler, seed, spp)
         return ctx.render(flat, p, develop=develop)
 

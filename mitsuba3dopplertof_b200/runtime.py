@@ -1,0 +1,151 @@
+"""Loader + thin object wrapper for libdtof_b200.so (the C ABI in include/dtof.h).
+
+The product path is the CUDA library only: if the shared object is missing, fails to load, or no CUDA
+device is present, every entry point raises -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import _abi
+from .integrator import DTOFError
+
+__all__ = ["load_library", "build_library", "Context", "get_context", "library_path"]
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB: Optional[C.CDLL] = None
+_CTX: Dict[int, "Context"] = {}
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, "libdtof_b200.so")
+
+
+def build_library(verbose: bool = False) -> str:
+    """Compile csrc/ for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    r = subprocess.run(["make", "-C", os.path.join(_HERE, "csrc")], capture_output=True, text=True)
+    if verbose or r.returncode:
+        print(r.stdout[-4000:], r.stderr[-4000:])
+    if r.returncode:
+        raise DTOFError("building libdtof_b200.so failed")
+    return library_path()
+
+
+def load_library() -> C.CDLL:
+    global _LIB
+    if _LIB is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise DTOFError(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "(there is no CPU fallback)")
+        lib = C.CDLL(path)
+        _abi.bind(lib)   # AttributeError if a symbol of include/dtof.h is not exported
+        if lib.dtof_abi_version() != _abi.ABI_VERSION:
+            raise DTOFError("libdtof_b200.so ABI version mismatch")
+        _LIB = lib
+    return _LIB
+
+
+class Context:
+    """One dtof_ctx (one GPU). Thread-compatible, like the C ABI."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        self.device = int(device)
+        h = C.c_void_p()
+        rc = self.lib.dtof_create(C.byref(h), self.device)
+        if rc != _abi.OK:
+            raise DTOFError(f"dtof_create(device={device}) failed with status {rc}: no usable CUDA device "
+                            "(the product path has no CPU fallback)")
+        self.h = h
+        self._flat = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.dtof_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:   # noqa: BLE001
+            pass
+
+    def _check(self, rc: int):
+        if rc != _abi.OK:
+            msg = self.lib.dtof_last_error(self.h).decode("utf-8", "replace")
+            if rc == _abi.ERR_INVALID:
+                raise ValueError(msg)
+            raise DTOFError(f"[status {rc}] {msg}")
+
+    # ---- scene ---------------------------------------------------------------------------------
+    def upload(self, scene_or_flat):
+        flat = scene_or_flat.flatten() if hasattr(scene_or_flat, "flatten") else scene_or_flat
+        self._check(self.lib.dtof_upload_scene(self.h, C.byref(flat.desc)))
+        self._flat = flat
+        return flat
+
+    def update_instances(self, first: int, instances) -> None:
+        arr = (_abi.Instance * len(instances))(*instances)
+        self._check(self.lib.dtof_update_instances(self.h, first, len(instances), arr))
+
+    def pass_info(self, params: _abi.Params) -> _abi.PassInfo:
+        pi = _abi.PassInfo()
+        self._check(self.lib.dtof_pass_info_for(self.h, C.byref(params), C.byref(pi)))
+        return pi
+
+    # ---- rendering -------------------------------------------------------------------------------
+    def render(self, flat, params: _abi.Params, develop: bool = True, both: bool = False):
+        """Host buffers in/out (copies inside the call): the end-to-end path a plugin uses."""
+        h, w = flat.height, flat.width
+        rgbw = np.empty((h, w, 4), np.float32) if (both or not develop) else None
+        img = np.empty((h, w, 3), np.float32) if (both or develop) else None
+        self._check(self.lib.dtof_render(self.h, C.byref(params), _abi.as_fp(rgbw) if rgbw is not None else None,
+                                         _abi.as_fp(img) if img is not None else None))
+        if both:
+            return img, rgbw
+        return img if develop else rgbw
+
+    def render_device(self, params: _abi.Params, d_rgbw_ptr: int, stream_ptr: int = 0) -> None:
+        """Accumulate into a caller-owned device tensor (e.g. torch.Tensor.data_ptr()), asynchronously."""
+        self._check(self.lib.dtof_render_device(self.h, C.byref(params), C.c_void_p(d_rgbw_ptr), C.c_void_p(stream_ptr)))
+
+    def develop_device(self, d_rgbw_ptr: int, d_img_ptr: int, stream_ptr: int = 0) -> None:
+        self._check(self.lib.dtof_develop_device(self.h, C.c_void_p(d_rgbw_ptr), C.c_void_p(d_img_ptr), C.c_void_p(stream_ptr)))
+
+    def trace_samples(self, params: _abi.Params, lanes) -> np.ndarray:
+        lanes = np.ascontiguousarray(lanes, np.uint64)
+        out = np.zeros(lanes.size, _abi.SAMPLE_RECORD_DTYPE)
+        self._check(self.lib.dtof_trace_samples(self.h, C.byref(params), lanes.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                                lanes.size, out.ctypes.data_as(C.POINTER(_abi.SampleRecord))))
+        return out
+
+    # ---- instrumentation -----------------------------------------------------------------------
+    def set_stats(self, enabled: bool) -> None:
+        self._check(self.lib.dtof_set_stats(self.h, int(enabled)))
+
+    def stats(self) -> _abi.Stats:
+        st = _abi.Stats()
+        self._check(self.lib.dtof_get_stats(self.h, C.byref(st)))
+        return st
+
+    def launch_count(self) -> int:
+        return int(self.lib.dtof_launch_count(self.h))
+
+    def last_kernel_ms(self) -> float:
+        ms = C.c_float()
+        self._check(self.lib.dtof_last_kernel_ms(self.h, C.byref(ms)))
+        return float(ms.value)
+
+
+def get_context(device: Optional[int] = None) -> Context:
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    if device not in _CTX:
+        _CTX[device] = Context(device)
+    return _CTX[device]

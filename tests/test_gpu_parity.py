@@ -1,0 +1,129 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path through the C ABI against
+(1) the reference's own per-lane radiance (tests/golden/lanes_*.json), (2) the CPU oracle on the same inputs,
+(3) size-independent properties at the BASELINE configuration sizes."""
+import os
+
+import numpy as np
+import pytest
+
+import golden_util as gu
+import mitsuba3dopplertof_b200 as dt
+
+pytestmark = pytest.mark.gpu
+
+LOWPASS = [n for n in gu.case_names() if "_full" not in n]
+FULL = [n for n in gu.case_names() if "_full" in n]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from mitsuba3dopplertof_b200 import runtime
+    c = runtime.Context(0)   # raises if the .so or the GPU is missing: no CPU fallback
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("name", LOWPASS)
+def test_cuda_lanes_match_reference_and_oracle(ctx, name):
+    import oracle_lib
+    scene, params, ref = gu.load_case(name)
+    flat = ctx.upload(scene)
+    rec = ctx.trace_samples(params, ref["lanes"])
+    frac, worst, bad = gu.compare(rec, ref)
+    assert frac >= 0.99, f"{name}: {len(bad)} lanes differ from the reference run: {ref['lanes'][bad][:8]}"
+    assert worst <= gu.REL_TOL
+    # against the oracle: same arithmetic, so far tighter than the reference tolerance
+    orc = oracle_lib.OracleScene(flat, 0).trace(params, ref["lanes"])
+    d = np.abs(rec["rgb"].astype(np.float64) - orc["rgb"])
+    tol = 1e-5 * np.maximum(np.abs(orc["rgb"]), gu.ABS_FLOOR)
+    ok = (d <= tol).all(axis=1)
+    assert ok.mean() >= 0.99, f"{name}: CUDA vs oracle mismatch on lanes {ref['lanes'][~ok][:8]}"
+    assert np.array_equal(rec["depth"][ok], orc["depth"][ok])
+    assert np.array_equal(rec["rng_draws"][ok], orc["rng_draws"][ok])   # identical stream consumption
+    np.testing.assert_array_equal(rec["time"], orc["time"])               # sampler + camera are bit-exact
+    np.testing.assert_array_equal(rec["sample_pos"], orc["sample_pos"])
+    np.testing.assert_array_equal(rec["ray_d"], orc["ray_d"])
+
+
+@pytest.mark.parametrize("name", FULL)
+def test_cuda_full_waveform_mode_matches_oracle(ctx, name):
+    import oracle_lib
+    scene, params, ref = gu.load_case(name)
+    flat = ctx.upload(scene)
+    rec = ctx.trace_samples(params, ref["lanes"])
+    orc = oracle_lib.OracleScene(flat, 0).trace(params, ref["lanes"])
+    d = np.abs(rec["rgb"].astype(np.float64) - orc["rgb"]).max(axis=1) / np.maximum(np.abs(orc["rgb"]).max(axis=1), 1e-2)
+    assert (d <= 1e-5).mean() >= 0.98
+
+
+@pytest.mark.parametrize("scene_name,kw", [
+    ("c1_example", dict(resx=48, resy=40, spp=64)),
+    ("c2_arealight", dict(resx=40, resy=40, spp=32)),
+    ("c4_domino", dict(resx=64, resy=32, spp=32, wave="trapezoidal", tsm="antithetic_mirror", shift=0.0, w_g=150)),
+    ("c5_slabroom", dict(resx=32, resy=32, spp=36, tcn=3, pcn=6, tsm="antithetic")),   # spp not a multiple of 32
+])
+def test_cuda_film_matches_oracle(ctx, scene_name, kw):
+    import oracle_lib
+    scene = dt.load_file(os.path.join(gu.SCENES, scene_name + ".xml"), **kw)
+    params = scene.integrator.params(scene.sensor.sampler, seed=5)
+    flat = ctx.upload(scene)
+    img, rgbw = ctx.render(flat, params, both=True)
+    ref = oracle_lib.OracleScene(flat).render(params, develop=False)
+    scale = np.abs(ref[..., :3]).max()
+    assert np.abs(rgbw[..., 3] - ref[..., 3]).max() <= 1e-4 * ref[..., 3].max()
+    assert np.abs(rgbw[..., :3] - ref[..., :3]).max() <= 2e-4 * scale
+    w = np.where(rgbw[..., 3:] == 0, 1, rgbw[..., 3:])
+    np.testing.assert_allclose(img, rgbw[..., :3] / w, rtol=1e-6, atol=1e-9)   # develop = RGB / W
+
+
+@pytest.mark.parametrize("rfilter", ["box", "gaussian", "tent"])
+def test_cuda_film_filters(ctx, rfilter):
+    import oracle_lib
+    scene = dt.load_file(os.path.join(gu.SCENES, "c1_example.xml"), resx=24, resy=24, spp=32)
+    scene.sensor.film.rfilter = rfilter
+    params = scene.integrator.params(scene.sensor.sampler)
+    flat = ctx.upload(scene)
+    rgbw = ctx.render(flat, params, develop=False)
+    ref = oracle_lib.OracleScene(flat).render(params, develop=False)
+    assert np.abs(rgbw - ref).max() <= 2e-4 * np.abs(ref).max()
+    if rfilter == "box":
+        assert np.array_equal(rgbw[..., 3], np.full((24, 24), 32.0, np.float32))   # exact sample counts
+
+
+def test_full_size_properties_c1(ctx):
+    """BASELINE config 1 at full size (256x256 @ 1024 spp): properties that need no CPU reference."""
+    scene = dt.load_file(os.path.join(gu.SCENES, "c1_example.xml"))
+    params = scene.integrator.params(scene.sensor.sampler)
+    flat = ctx.upload(scene)
+    n = 256 * 256 * 1024
+    full = ctx.render(flat, params, develop=False)
+    # (a) linearity over lane shards: two halves (split on a correlate-group boundary) sum to the whole
+    pa = scene.integrator.params(scene.sensor.sampler, lane_begin=0, lane_end=n // 2)
+    pb = scene.integrator.params(scene.sensor.sampler, lane_begin=n // 2, lane_end=n)
+    halves = ctx.render(flat, pa, develop=False) + ctx.render(flat, pb, develop=False)
+    assert np.abs(halves - full).max() <= 1e-4 * np.abs(full[..., :3]).max() + 1e-3   # W ~ 1e3 -> 1e-3 abs
+    # (b) film weight: tent of radius 1 is a partition of unity -> interior pixels collect spp of weight
+    inner = full[2:-2, 2:-2, 3]
+    assert abs(inner.mean() - 1024.0) < 0.5
+    # (c) the reference's committed render of this very scene (cuda_rgb, fp16 EXR): same sample streams
+    gold = np.load(os.path.join(gu.GOLDEN, "scene_exr.npy")).astype(np.float32)
+    img = full[..., :3] / full[..., 3:]
+    num = ((img - gold) ** 2).mean()
+    den = (gold ** 2).mean()
+    assert num / den < 5e-3, f"relative MSE vs configs_example/scene.exr = {num / den:.3e}"
+
+
+def test_c_abi_error_behaviour(ctx):
+    scene = dt.load_file(os.path.join(gu.SCENES, "c1_example.xml"), resx=16, resy=16, spp=16)
+    flat = ctx.upload(scene)
+    p = scene.integrator.params(scene.sensor.sampler)
+    p.wave_function_type = 9
+    with pytest.raises(ValueError):
+        ctx.render(flat, p)
+    p = scene.integrator.params(scene.sensor.sampler)
+    p.lane_end = 10 ** 12
+    with pytest.raises(ValueError):
+        ctx.render(flat, p)
+    p = scene.integrator.params(scene.sensor.sampler)
+    with pytest.raises(ValueError):
+        ctx.trace_samples(p, [16 * 16 * 16])   # one past the wavefront

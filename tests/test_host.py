@@ -1,0 +1,128 @@
+"""CPU tests of the host-side mirror (scene XML subset, property parsing, flattening) and of the C ABI
+library's symbol table (no compute calls without a GPU)."""
+import ctypes as C
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+import golden_util as gu
+import mitsuba3dopplertof_b200 as dt
+from mitsuba3dopplertof_b200 import _abi, runtime
+from mitsuba3dopplertof_b200.transform import perspective_projection
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "dtof.h")).read()
+    declared = set(re.findall(r"\b(dtof_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(_abi.DTOF_SYMBOLS), declared ^ set(_abi.DTOF_SYMBOLS)
+    if not os.path.exists(runtime.library_path()):
+        runtime.build_library()
+    lib = runtime.load_library()   # binds (and therefore resolves) every symbol
+    assert lib.dtof_abi_version() == _abi.ABI_VERSION
+
+
+def test_abi_struct_sizes_match_header():
+    # sizes computed from include/dtof.h by the C compiler
+    import subprocess, tempfile
+    src = '#include "dtof.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",' \
+          'sizeof(dtof_mesh),sizeof(dtof_instance),sizeof(dtof_bsdf),sizeof(dtof_emitter),sizeof(dtof_camera),' \
+          'sizeof(dtof_film),sizeof(dtof_scene_desc),sizeof(dtof_params),sizeof(dtof_sample_record),sizeof(dtof_stats),' \
+          'sizeof(dtof_pass_info));return 0;}\n'
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "s.c"), "w").write(src)
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "s.c"), "-o", os.path.join(d, "s")], check=True)
+        sizes = list(map(int, subprocess.run([os.path.join(d, "s")], capture_output=True, text=True).stdout.split()))
+    mine = [C.sizeof(t) for t in (_abi.Mesh, _abi.Instance, _abi.Bsdf, _abi.Emitter, _abi.Camera, _abi.Film,
+                                  _abi.SceneDesc, _abi.Params, _abi.SampleRecord, _abi.Stats, _abi.PassInfo)]
+    assert sizes == mine
+
+
+def test_no_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(dt.DTOFError):
+        runtime.Context(0)
+    scene = dt.load_file(os.path.join(gu.SCENES, "c1_example.xml"), resx=8, resy=8, spp=4)
+    with pytest.raises(dt.DTOFError):
+        scene.integrator.render(scene)
+
+
+def test_example_scene_loads_unchanged():
+    ref_xml = "/root/reference/configs_example/scene.xml"
+    path = ref_xml if os.path.exists(ref_xml) else os.path.join(gu.SCENES, "c1_example.xml")
+    sc = dt.load_file(path)
+    integ = sc.integrator
+    assert (integ.max_depth, integ.rr_depth, integ.path_correlation_depth) == (4, 5, 4)
+    assert integ.time_sampling_method == "antithetic" and float(integ.antithetic_shift) == 0.5
+    assert float(integ.hetero_frequency) == 1.0 and float(integ.sensor_phase_offset) == 0.0
+    assert float(integ.w_s) == pytest.approx(30.0 + 1.0 / 0.0015 * 1e-6, rel=1e-6)
+    assert sc.sensor.sampler.sample_count == 1024 and sc.sensor.sampler.time_correlate_number == 2
+    flat = sc.flatten()
+    assert (flat.n_triangles, flat.desc.n_instances, flat.desc.n_emitters) == (34, 3, 1)
+    inst = flat.instances[1]
+    assert inst.animated == 1 and inst.t0 == 0.0 and inst.t1 == np.float32(0.0015)
+    assert inst.m1[11] - inst.m0[11] == pytest.approx(0.015, rel=1e-5)   # <translate z="0.015"/> on keyframe 1
+
+
+def test_property_surface_and_errors():
+    i = dt.DopplerToFPathIntegrator()
+    assert (float(i.time), float(i.w_g), float(i.g_1), float(i.g_0), float(i.w_s)) == (np.float32(0.0015), 30.0, 0.5, 0.5, 30.0)
+    assert i.time_sampling_method == "antithetic" and float(i.antithetic_shift) == 0.5
+    assert i.use_stratified_sampling_for_each_interval and i.low_frequency_component_only
+    assert (i.max_depth, i.rr_depth, i.path_correlation_depth) == (-1, 5, 0)
+    assert float(dt.DopplerToFPathIntegrator(time_sampling_method="stratified").antithetic_shift) == 0.0
+    j = dt.DopplerToFPathIntegrator(w_g=30.0, w_s=30.001)   # hetero_frequency derived from w_s - w_g
+    assert float(j.hetero_frequency) == pytest.approx((np.float32(30.001) - np.float32(30.0)) * 1e6 * 0.0015, rel=1e-5)
+    k = dt.DopplerToFPathIntegrator(hetero_offset=0.25)
+    assert float(k.sensor_phase_offset) == pytest.approx(np.pi / 2, rel=1e-6)
+    for bad in (dict(wave_function_type="sawtooth"), dict(time_sampling_method="periodic"), dict(rr_depth=0),
+                dict(max_depth=-2), dict(not_a_property=1)):
+        with pytest.raises(ValueError):
+            dt.DopplerToFPathIntegrator(**bad)
+    with pytest.raises(ValueError):   # README says sampler, the code says integrator (SURVEY.md finding 7)
+        dt.load_string('<scene version="3.0.0"><integrator type="dopplertofpath"/><sensor type="perspective">'
+                       '<sampler type="correlated"><boolean name="use_stratified_sampling_for_each_interval" value="true"/>'
+                       '</sampler></sensor></scene>')
+    s = dt.CorrelatedSampler(sample_count=8, time_correlate_number=4)
+    assert s.path_correlate_number == 4
+    with pytest.raises(ValueError):
+        dt.DopplerToFPathIntegrator(time_sampling_method="antithetic_mirror").params(s)
+
+
+def test_perspective_projection_matches_reference_headers():
+    hv = json.load(open(os.path.join(gu.GOLDEN, "header_vectors.json")))
+    for c in hv["perspective"]:
+        c2s = perspective_projection(c["film"], c["crop"], c["offset"], c["fov"], c["near"], c["far"])
+        s2c = c2s.inverse().matrix.astype(np.float32).reshape(16)
+        ref = np.array(c["sample_to_camera"], np.float32)
+        np.testing.assert_allclose(s2c, ref, rtol=3e-7, atol=1e-9)
+
+
+def test_rectangle_winding_matches_frame_normal():
+    from mitsuba3dopplertof_b200.scene import _flatten_shape, Shape
+    for m in (np.diag([1.0, 1, 1, 1]), np.diag([1.0, -1, 1, 1]), np.diag([2.0, 3, -1, 1])):
+        t = dt.Transform4.from_matrix(m)
+        fm = _flatten_shape(Shape("rectangle"), t)
+        p = fm.positions
+        n_geo = np.cross(p[fm.faces[0][1]] - p[fm.faces[0][0]], p[fm.faces[0][2]] - p[fm.faces[0][0]])
+        n_ref = t.astype(np.float32).transform_normal((0, 0, 1))
+        assert np.dot(n_geo, n_ref) > 0
+
+
+def test_mesh_loaders(tmp_path):
+    from mitsuba3dopplertof_b200.meshio import load_mesh
+    pos, faces, nrm, uv = load_mesh(os.path.join(gu.SCENES, "gem.ply"), face_normals=True)
+    assert pos.shape == (6, 3) and faces.shape == (8, 3) and nrm is None and uv is None
+    pos, faces, nrm, uv = load_mesh(os.path.join(gu.SCENES, "gem.ply"))
+    assert nrm.shape == (6, 3) and np.allclose(np.linalg.norm(nrm, axis=1), 1, atol=1e-6)
+    obj = tmp_path / "q.obj"
+    obj.write_text("v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvt 1 1\nvt 0 1\nvn 0 0 1\n"
+                   "f 1/1/1 2/2/1 3/3/1 4/4/1\n")
+    pos, faces, nrm, uv = load_mesh(str(obj))
+    assert faces.tolist() == [[0, 1, 2], [0, 2, 3]] and uv.shape == (4, 2) and nrm.shape == (4, 3)
