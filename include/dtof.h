@@ -183,6 +183,12 @@ typedef struct dtof_params {
      * lane_end == 0 means "all lanes". Lanes are idx = pixel * spp_per_pass + slot as in
      * src/render/integrator.cpp:273-290. */
     uint64_t lane_begin, lane_end;
+    /* Interleaved sharding inside [lane_begin, lane_end): the range is cut into blocks of `shard_block` lanes and
+     * this call renders the blocks b with b % shard_count == shard_index. shard_block == 0 disables it.
+     *   sample-slot (spp) sharding over G GPUs : shard_block = spp_per_pass / G  (a multiple of lcm(tcn, pcn))
+     *   interleaved tile sharding              : shard_block = spp_per_pass * pixels_per_tile */
+    uint64_t shard_block;
+    uint32_t shard_count, shard_index;
 } dtof_params;
 
 /* Per-lane record returned by dtof_trace_samples (and by the CPU oracle): everything the

@@ -87,6 +87,7 @@ class Params(C.Structure):
         ("time_correlate_number", C.c_uint32), ("path_correlate_number", C.c_uint32),
         ("seed", C.c_uint32),
         ("lane_begin", C.c_uint64), ("lane_end", C.c_uint64),
+        ("shard_block", C.c_uint64), ("shard_count", C.c_uint32), ("shard_index", C.c_uint32),
     ]
 
 

@@ -35,6 +35,9 @@ struct RenderArgs {
     Modulation mod;
     uint32_t spp_per_pass, n_passes;
     unsigned long long lane_begin, lane_end;     // lanes of every pass handled by this launch
+    unsigned long long n_local;                  // number of lanes this launch renders (after interleaved sharding)
+    unsigned long long shard_block;
+    uint32_t shard_count, shard_index;
     unsigned long long *work_counter;            // chunk dispenser
     Counters *stats;
     // record mode
@@ -63,7 +66,7 @@ __global__ void __launch_bounds__(kBlock, 2) render_kernel(const __grid_constant
     }
     const int lane = threadIdx.x & 31;
     Counters st = {};
-    const unsigned long long n_lanes = RECORD ? (unsigned long long) A.n_rec : (A.lane_end - A.lane_begin);
+    const unsigned long long n_lanes = RECORD ? (unsigned long long) A.n_rec : A.n_local;
     const unsigned long long n_chunks = (n_lanes + kBlock - 1) / kBlock;
 
     for (;;) {
@@ -77,8 +80,16 @@ __global__ void __launch_bounds__(kBlock, 2) render_kernel(const __grid_constant
         const unsigned long long li = chunk * kBlock + threadIdx.x;
         const bool lane_on = li < n_lanes;
         unsigned long long idx64 = 0;
-        if (lane_on)
-            idx64 = RECORD ? A.rec_lanes[li] : (A.lane_begin + li);
+        if (lane_on) {
+            if (RECORD) {
+                idx64 = A.rec_lanes[li];
+            } else if (A.shard_block) {   // local lane -> (block of this shard, offset) -> global lane
+                unsigned long long j = li / A.shard_block, within = li - j * A.shard_block;
+                idx64 = A.lane_begin + (j * A.shard_count + A.shard_index) * A.shard_block + within;
+            } else {
+                idx64 = A.lane_begin + li;
+            }
+        }
         const uint32_t idx = (uint32_t) idx64;
         const uint32_t pixel = idx / A.spp_per_pass;
         const uint32_t py = pixel / A.film.width, px = pixel - py * A.film.width;
@@ -344,6 +355,19 @@ dtof_status launch_render(dtof_ctx *ctx, const dtof_params *p, float *d_rgbw, cu
     if (A.lane_end > pi.wavefront_size || A.lane_begin > A.lane_end)
         return fail(ctx, DTOF_ERR_INVALID, "lane range [%llu, %llu) outside the wavefront of %llu lanes", A.lane_begin,
                     A.lane_end, (unsigned long long) pi.wavefront_size);
+    A.n_local = A.lane_end - A.lane_begin;
+    A.shard_block = 0;
+    if (p->shard_block) {
+        if (p->shard_count == 0 || p->shard_index >= p->shard_count)
+            return fail(ctx, DTOF_ERR_INVALID, "shard_index %u outside shard_count %u", p->shard_index, p->shard_count);
+        unsigned long long total = A.lane_end - A.lane_begin, B = p->shard_block, R = p->shard_count, r = p->shard_index;
+        unsigned long long full_blocks = total / B, tail = total % B;
+        unsigned long long mine = full_blocks / R + (r < full_blocks % R ? 1 : 0);
+        A.n_local = mine * B + ((tail && full_blocks % R == r) ? tail : 0);
+        A.shard_block = B;
+        A.shard_count = p->shard_count;
+        A.shard_index = p->shard_index;
+    }
     FilmParams &F = A.film;
     F.rgbw = d_rgbw;
     F.width = ctx->film.width, F.height = ctx->film.height;
@@ -365,7 +389,7 @@ dtof_status launch_render(dtof_ctx *ctx, const dtof_params *p, float *d_rgbw, cu
     const bool record = d_rec != nullptr;
     const size_t trav_bytes = ctx->nodes_bytes + ctx->tris_bytes + ctx->insts_bytes;
     const bool use_smem = trav_bytes <= kSmemSceneLimit && trav_bytes + 1024 <= ctx->smem_optin && !getenv("DTOF_NO_SMEM");
-    unsigned long long n_lanes = record ? n_rec : (A.lane_end - A.lane_begin);
+    unsigned long long n_lanes = record ? n_rec : A.n_local;
     unsigned long long n_chunks = (n_lanes + kBlock - 1) / kBlock;
     int grid = (int) std::min<unsigned long long>(std::max<unsigned long long>(n_chunks, 1), (unsigned long long) ctx->sm_count * 2);
     CU(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), stream));
@@ -758,6 +782,7 @@ dtof_status dtof_trace_samples(dtof_ctx *ctx, const dtof_params *params, const u
     dtof_params p = *params;
     p.lane_begin = 0;
     p.lane_end = 0;
+    p.shard_block = 0;
     s = launch_render(ctx, &p, ctx->d_rgbw, 0, d_lanes, d_rec, n);
     if (s == DTOF_OK) {
         e = cudaMemcpy(out, d_rec, n * sizeof(dtof_sample_record), cudaMemcpyDeviceToHost);

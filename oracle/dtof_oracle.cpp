@@ -1371,6 +1371,8 @@ int dtof_oracle_render(const dtof_oracle_scene *s, const dtof_params *p, int n_t
     uint64_t lane_begin = p->lane_begin, lane_end = p->lane_end ? p->lane_end : pi.wavefront_size;
     if (lane_end > pi.wavefront_size || lane_begin > lane_end)
         return 2;
+    if (p->shard_block && (p->shard_count == 0 || p->shard_index >= p->shard_count))
+        return 2;
     Modulation mod(*p);
     FilmSplat splat(s->film);
     std::vector<double> accum(npx * 4, 0.0);
@@ -1394,6 +1396,8 @@ int dtof_oracle_render(const dtof_oracle_scene *s, const dtof_params *p, int n_t
                 for (uint32_t slot = 0; slot < pi.spp_per_pass; ++slot) {
                     uint64_t idx = pixel * pi.spp_per_pass + slot;
                     if (idx < lane_begin || idx >= lane_end)
+                        continue;
+                    if (p->shard_block && ((idx - lane_begin) / p->shard_block) % p->shard_count != p->shard_index)
                         continue;
                     LaneSampler smp;
                     smp.seed(*p, idx, pi.spp_per_pass);

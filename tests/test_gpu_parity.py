@@ -127,3 +127,17 @@ def test_c_abi_error_behaviour(ctx):
     p = scene.integrator.params(scene.sensor.sampler)
     with pytest.raises(ValueError):
         ctx.trace_samples(p, [16 * 16 * 16])   # one past the wavefront
+
+
+@pytest.mark.parametrize("mode,world", [("slots", 4), ("tiles", 3)])
+def test_interleaved_shards_sum_to_whole(ctx, mode, world):
+    """The shards the multi-GPU path hands to each rank (distributed.shard_params) partition the wavefront."""
+    from mitsuba3dopplertof_b200.distributed import shard_params
+    scene = dt.load_file(os.path.join(gu.SCENES, "c3_rotor.xml"), resx=40, resy=24, spp=64, pcn=4)
+    params = scene.integrator.params(scene.sensor.sampler, seed=2)
+    flat = ctx.upload(scene)
+    pi = ctx.pass_info(params)
+    whole = ctx.render(flat, params, develop=False)
+    parts = sum(ctx.render(flat, shard_params(params, pi, world, r, mode, tile_pixels=7), develop=False) for r in range(world))
+    assert np.abs(parts - whole).max() <= 1e-5 * np.abs(whole).max()
+    assert np.abs(parts[..., 3] - whole[..., 3]).max() <= 1e-4
