@@ -1,10 +1,11 @@
 // libdtof_b200.so -- C ABI (include/dtof.h) + render kernels for sm_100a.
 //
-// Kernel design: a persistent, register-resident "fused wavefront": one thread per
-// wavefront lane, CTAs of 256 lanes pull 256-lane chunks (= part of ONE pixel when spp_per_pass >= 256)
-// from an atomic work counter. Scenes whose traversal data (nodes + triangles + instances) fit in shared
-// memory are staged there once per CTA with 128-bit copies; larger scenes are read through L1/L2 with
-// 128-bit loads. Film accumulation is warp-aggregated (36 atomics per warp instead of 36 per lane).
+// Kernel design: a persistent, register-resident "fused wavefront": one thread per wavefront
+// lane; every WARP pulls work units of kUnit consecutive lanes (part of ONE pixel when spp_per_pass >= 32) from an
+// atomic counter -- no block-wide barrier after start-up. Traversal data that fits in shared memory is staged
+// there once per CTA with 128-bit copies; tiny scenes are walked flat and warp-coherently, larger ones through the
+// BVH, huge ones through L1/L2 with 128-bit loads. Film accumulation is warp-aggregated (36 atomics per warp
+// instead of 36 per lane).
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -19,16 +20,21 @@
 #include "dtof_bvh.h"
 #include "dtof_device.cuh"
 #include "dtof_layout.h"
+#include "dtof_path.cuh"
 
 using namespace dtof;
 
 namespace {
 
 constexpr int kBlock = 256;
+constexpr unsigned long long kUnit = 256;       // lanes per work unit fetched by one warp (8 warp iterations)
 constexpr size_t kSmemSceneLimit = 96 * 1024;   // traversal data up to this size is staged in shared memory
+constexpr uint32_t kFlatMaxTris = 64;           // scenes up to this many triangles use the flat coherent walk
 
 struct RenderArgs {
     DeviceScene scene;
+    const float4 *tris_flat;                     // triangles in scene order (flat mode)
+    const float4 *inst_box;                      // instance world boxes
     dtof_camera cam;
     FilmParams film;
     dtof_params p;
@@ -38,77 +44,74 @@ struct RenderArgs {
     unsigned long long n_local;                  // number of lanes this launch renders (after interleaved sharding)
     unsigned long long shard_block;
     uint32_t shard_count, shard_index;
-    unsigned long long *work_counter;            // chunk dispenser
+    unsigned long long *work_counter;            // work-unit dispenser
     Counters *stats;
     // record mode
     const unsigned long long *rec_lanes;
     dtof_sample_record *rec_out;
     uint32_t n_rec;
-    uint32_t smem_nodes_bytes, smem_tris_bytes, smem_insts_bytes;
+    uint32_t nodes_bytes, tris_bytes, insts_bytes, boxes_bytes;
 };
 
-template <bool STATS, bool SMEM, bool RECORD>
+template <int MODE, bool STATS, bool RECORD>
 __global__ void __launch_bounds__(kBlock, 2) render_kernel(const __grid_constant__ RenderArgs A) {
     extern __shared__ float4 smem[];
-    __shared__ unsigned long long s_chunk;
-    const float4 *N = A.scene.nodes, *T = A.scene.tris, *I = A.scene.insts;
-    if (SMEM) {
-        // stage nodes | tris | instances into shared memory (128-bit copies)
-        uint32_t nn = A.smem_nodes_bytes / 16, nt = A.smem_tris_bytes / 16, ni = A.smem_insts_bytes / 16;
-        float4 *sN = smem, *sT = smem + nn, *sI = smem + nn + nt;
+    TravPtrs TP;
+    TP.N = A.scene.nodes, TP.T = A.scene.tris, TP.TF = A.tris_flat, TP.I = A.scene.insts, TP.B = A.inst_box;
+    if (MODE != MODE_BVH_GLOBAL) {
+        // stage the traversal data into shared memory (128-bit copies): [nodes | tris] or [flat tris], insts, boxes
+        const uint32_t nn = MODE == MODE_BVH_SMEM ? A.nodes_bytes / 16 : 0, nt = A.tris_bytes / 16,
+                       ni = A.insts_bytes / 16, nb = A.boxes_bytes / 16;
+        float4 *sN = smem, *sT = sN + nn, *sI = sT + nt, *sB = sI + ni;
+        const float4 *gT = MODE == MODE_BVH_SMEM ? A.scene.tris : A.tris_flat;
         for (uint32_t i = threadIdx.x; i < nn; i += kBlock) sN[i] = A.scene.nodes[i];
-        for (uint32_t i = threadIdx.x; i < nt; i += kBlock) sT[i] = A.scene.tris[i];
+        for (uint32_t i = threadIdx.x; i < nt; i += kBlock) sT[i] = gT[i];
         for (uint32_t i = threadIdx.x; i < ni; i += kBlock) sI[i] = A.scene.insts[i];
+        for (uint32_t i = threadIdx.x; i < nb; i += kBlock) sB[i] = A.inst_box[i];
         __syncthreads();
-        N = sN;
-        T = sT;
-        I = sI;
+        TP.N = sN, TP.T = sT, TP.TF = sT, TP.I = sI, TP.B = sB;
     }
     const int lane = threadIdx.x & 31;
     Counters st = {};
     const unsigned long long n_lanes = RECORD ? (unsigned long long) A.n_rec : A.n_local;
-    const unsigned long long n_chunks = (n_lanes + kBlock - 1) / kBlock;
+    const unsigned long long n_units = (n_lanes + kUnit - 1) / kUnit;
 
     for (;;) {
-        if (threadIdx.x == 0)
-            s_chunk = atomicAdd(A.work_counter, 1ull);
-        __syncthreads();
-        const unsigned long long chunk = s_chunk;
-        __syncthreads();
-        if (chunk >= n_chunks)
+        unsigned long long unit = 0;
+        if (lane == 0)
+            unit = atomicAdd(A.work_counter, 1ull);
+        unit = __shfl_sync(kFullMask, unit, 0);
+        if (unit >= n_units)
             break;
-        const unsigned long long li = chunk * kBlock + threadIdx.x;
-        const bool lane_on = li < n_lanes;
-        unsigned long long idx64 = 0;
-        if (lane_on) {
-            if (RECORD) {
-                idx64 = A.rec_lanes[li];
-            } else if (A.shard_block) {   // local lane -> (block of this shard, offset) -> global lane
-                unsigned long long j = li / A.shard_block, within = li - j * A.shard_block;
-                idx64 = A.lane_begin + (j * A.shard_count + A.shard_index) * A.shard_block + within;
-            } else {
-                idx64 = A.lane_begin + li;
+        for (unsigned long long li = unit * kUnit + lane; li < (unit + 1) * kUnit; li += 32) {
+            if (li - lane >= n_lanes)   // warp-uniform: the whole iteration is past the end
+                break;
+            const bool lane_on = li < n_lanes;
+            unsigned long long idx64 = 0;
+            if (lane_on) {
+                if (RECORD) {
+                    idx64 = A.rec_lanes[li];
+                } else if (A.shard_block) {   // local lane -> (block of this shard, offset) -> global lane
+                    unsigned long long j = li / A.shard_block, within = li - j * A.shard_block;
+                    idx64 = A.lane_begin + (j * A.shard_count + A.shard_index) * A.shard_block + within;
+                } else {
+                    idx64 = A.lane_begin + li;
+                }
             }
-        }
-        const uint32_t idx = (uint32_t) idx64;
-        const uint32_t pixel = idx / A.spp_per_pass;
-        const uint32_t py = pixel / A.film.width, px = pixel - py * A.film.width;
-        LaneSampler smp;
-        if (lane_on)
+            const uint32_t idx = (uint32_t) idx64;
+            const uint32_t pixel = idx / A.spp_per_pass;
+            const uint32_t py = pixel / A.film.width, px = pixel - py * A.film.width;
+            LaneSampler smp;
             smp.seed(A.p, idx, A.spp_per_pass);
 
-        for (uint32_t pass = 0; pass < (RECORD ? 1u : A.n_passes); ++pass) {
-            V3 rgb = v3(0, 0, 0);
-            float spx = 0.f, spy = 0.f;
-            if (lane_on) {
+            for (uint32_t pass = 0; pass < (RECORD ? 1u : A.n_passes); ++pass) {
                 // render_sample(), Doppler branch (src/render/integrator.cpp:476-542)
                 const bool correlate_pixel = A.p.path_correlation_depth > 0;
                 const float scale_x = 1.f / (float) A.film.width, scale_y = 1.f / (float) A.film.height;
                 const float off_x = -(float) A.film.crop_x * scale_x, off_y = -(float) A.film.crop_y * scale_y;
                 const float posx = (float) (px + A.film.crop_x), posy = (float) (py + A.film.crop_y);
                 float jx = smp.next_1d(correlate_pixel), jy = smp.next_1d(correlate_pixel);
-                spx = posx + jx;
-                spy = posy + jy;
+                float spx = posx + jx, spy = posy + jy;
                 float ax = fmaf(spx, scale_x, off_x), ay = fmaf(spy, scale_y, off_y);
                 float time = A.cam.shutter_open;
                 if (A.cam.shutter_open_time > 0.f)
@@ -116,32 +119,30 @@ __global__ void __launch_bounds__(kBlock, 2) render_kernel(const __grid_constant
                 V3 o, d;
                 float maxt;
                 camera_ray(A.cam, ax, ay, o, d, maxt);
-                PathOut r = trace_path<STATS>(A.scene, N, T, I, A.p, A.mod, smp, o, d, maxt, time, st);
-                rgb = r.rgb;
+                PathOut r = trace_path<MODE, STATS>(A.scene, TP, A.p, A.mod, smp, lane_on, o, d, maxt, time, st);
+                V3 rgb = r.rgb;
                 if (A.film.rfilter == DTOF_RFILTER_BOX) {
                     spx = posx;
                     spy = posy;
                 }
-                if (STATS) st.samples++;
+                if (STATS && lane_on) st.samples++;
                 if (RECORD) {
-                    dtof_sample_record &rec = A.rec_out[li];
-                    rec.sample_pos[0] = spx, rec.sample_pos[1] = spy;
-                    rec.time = time;
-                    rec.ray_o[0] = o.x, rec.ray_o[1] = o.y, rec.ray_o[2] = o.z;
-                    rec.ray_d[0] = d.x, rec.ray_d[1] = d.y, rec.ray_d[2] = d.z;
-                    rec.ray_maxt = maxt;
-                    rec.rgb[0] = rgb.x, rec.rgb[1] = rgb.y, rec.rgb[2] = rgb.z;
-                    rec.path_length = r.path_length;
-                    rec.depth = r.depth;
-                    rec.rng_draws = smp.draws;
-                }
-                smp.advance();
-            }
-            if (!RECORD) {
-                // ---- film: warp-aggregated when the whole warp splats the same 3x3 footprint
-                const int ix = (int) floorf(spx), iy = (int) floorf(spy);
-                const unsigned on_mask = __ballot_sync(kFullMask, lane_on);
-                if (on_mask) {
+                    if (lane_on) {
+                        dtof_sample_record &rec = A.rec_out[li];
+                        rec.sample_pos[0] = spx, rec.sample_pos[1] = spy;
+                        rec.time = time;
+                        rec.ray_o[0] = o.x, rec.ray_o[1] = o.y, rec.ray_o[2] = o.z;
+                        rec.ray_d[0] = d.x, rec.ray_d[1] = d.y, rec.ray_d[2] = d.z;
+                        rec.ray_maxt = maxt;
+                        rec.rgb[0] = rgb.x, rec.rgb[1] = rgb.y, rec.rgb[2] = rgb.z;
+                        rec.path_length = r.path_length;
+                        rec.depth = r.depth;
+                        rec.rng_draws = smp.draws;
+                    }
+                } else {
+                    // ---- film: warp-aggregated when the whole warp splats the same 3x3 footprint
+                    const int ix = (int) floorf(spx), iy = (int) floorf(spy);
+                    const unsigned on_mask = __ballot_sync(kFullMask, lane_on);
                     const int leader = __ffs(on_mask) - 1;
                     const int lx = __shfl_sync(kFullMask, ix, leader), ly = __shfl_sync(kFullMask, iy, leader);
                     const bool uniform = __all_sync(kFullMask, !lane_on || (ix == lx && iy == ly));
@@ -150,6 +151,7 @@ __global__ void __launch_bounds__(kBlock, 2) render_kernel(const __grid_constant
                     else if (lane_on)
                         splat_generic(A.film, spx, spy, rgb);
                 }
+                smp.advance();
             }
         }
     }
@@ -186,6 +188,11 @@ struct dtof_ctx {
     dtof_camera cam{};
     dtof_film film{};
     DeviceScene ds{};
+    void *d_tris_flat = nullptr, *d_boxes = nullptr;
+    size_t flat_bytes = 0, boxes_bytes = 0;
+    uint32_t n_tris_total = 0;
+    int forced_mode = -1;       // DTOF_MODE env / stats runs: -1 = automatic
+    int last_mode = -1;
     void *d_nodes = nullptr, *d_tris = nullptr, *d_shade = nullptr, *d_insts = nullptr, *d_meshes = nullptr,
          *d_bsdfs = nullptr, *d_emitters = nullptr, *d_cdf = nullptr, *d_pmf = nullptr;
     std::vector<InstRec> h_insts;
@@ -227,7 +234,7 @@ dtof_status fail(dtof_ctx *c, dtof_status s, const char *fmt, ...) {
     } while (0)
 
 void free_scene(dtof_ctx *c) {
-    void **ptrs[] = { &c->d_nodes, &c->d_tris, &c->d_shade, &c->d_insts, &c->d_meshes, &c->d_bsdfs,
+    void **ptrs[] = { &c->d_tris_flat, &c->d_boxes, &c->d_nodes, &c->d_tris, &c->d_shade, &c->d_insts, &c->d_meshes, &c->d_bsdfs,
                       &c->d_emitters, &c->d_cdf, &c->d_pmf };
     for (void **p : ptrs) {
         if (*p)
@@ -321,19 +328,28 @@ Modulation make_modulation(const dtof_params &p) {
     return m;
 }
 
-template <bool STATS, bool RECORD>
-dtof_status launch_variant(dtof_ctx *ctx, RenderArgs &A, bool use_smem, int grid, cudaStream_t stream) {
-    size_t smem = use_smem ? (size_t) A.smem_nodes_bytes + A.smem_tris_bytes + A.smem_insts_bytes : 0;
-    if (use_smem) {
-        auto k = render_kernel<STATS, true, RECORD>;
+template <int MODE, bool STATS, bool RECORD>
+dtof_status launch_variant(dtof_ctx *ctx, RenderArgs &A, int grid, cudaStream_t stream) {
+    size_t smem = 0;
+    if (MODE == MODE_BVH_SMEM)
+        smem = (size_t) A.nodes_bytes + A.tris_bytes + A.insts_bytes + A.boxes_bytes;
+    else if (MODE == MODE_FLAT_SMEM)
+        smem = (size_t) A.tris_bytes + A.insts_bytes + A.boxes_bytes;
+    auto k = render_kernel<MODE, STATS, RECORD>;
+    if (smem)
         CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        k<<<grid, kBlock, smem, stream>>>(A);
-    } else {
-        render_kernel<STATS, false, RECORD><<<grid, kBlock, 0, stream>>>(A);
-    }
+    k<<<grid, kBlock, smem, stream>>>(A);
     ctx->launches++;
     CU(cudaGetLastError());
     return DTOF_OK;
+}
+
+template <int MODE>
+dtof_status launch_mode(dtof_ctx *ctx, RenderArgs &A, bool record, int grid, cudaStream_t stream) {
+    if (record)
+        return launch_variant<MODE, false, true>(ctx, A, grid, stream);
+    return ctx->stats_enabled ? launch_variant<MODE, true, false>(ctx, A, grid, stream)
+                              : launch_variant<MODE, false, false>(ctx, A, grid, stream);
 }
 
 dtof_status launch_render(dtof_ctx *ctx, const dtof_params *p, float *d_rgbw, cudaStream_t stream,
@@ -383,28 +399,45 @@ dtof_status launch_render(dtof_ctx *ctx, const dtof_params *p, float *d_rgbw, cu
     A.rec_lanes = d_lanes;
     A.rec_out = d_rec;
     A.n_rec = n_rec;
-    A.smem_nodes_bytes = (uint32_t) ctx->nodes_bytes;
-    A.smem_tris_bytes = (uint32_t) ctx->tris_bytes;
-    A.smem_insts_bytes = (uint32_t) ctx->insts_bytes;
+    A.tris_flat = (const float4 *) ctx->d_tris_flat;
+    A.inst_box = (const float4 *) ctx->d_boxes;
     const bool record = d_rec != nullptr;
-    const size_t trav_bytes = ctx->nodes_bytes + ctx->tris_bytes + ctx->insts_bytes;
-    const bool use_smem = trav_bytes <= kSmemSceneLimit && trav_bytes + 1024 <= ctx->smem_optin && !getenv("DTOF_NO_SMEM");
+    // ---- traversal mode: flat coherent walk for tiny scenes, BVH in shared memory while it fits, else BVH from HBM
+    const size_t bvh_bytes = ctx->nodes_bytes + ctx->tris_bytes + ctx->insts_bytes + ctx->boxes_bytes;
+    const size_t flat_bytes = ctx->flat_bytes + ctx->insts_bytes + ctx->boxes_bytes;
+    int mode = MODE_BVH_GLOBAL;
+    if (bvh_bytes <= kSmemSceneLimit && bvh_bytes + 1024 <= ctx->smem_optin)
+        mode = MODE_BVH_SMEM;
+    if (ctx->n_tris_total <= kFlatMaxTris && flat_bytes + 1024 <= ctx->smem_optin)
+        mode = MODE_FLAT_SMEM;
+    int want = ctx->forced_mode;
+    if (const char *e = getenv("DTOF_MODE"))
+        want = atoi(e);
+    if (want == MODE_BVH_GLOBAL || (want == MODE_BVH_SMEM && bvh_bytes + 1024 <= ctx->smem_optin) ||
+        (want == MODE_FLAT_SMEM && flat_bytes + 1024 <= ctx->smem_optin))
+        mode = want;
+    A.nodes_bytes = (uint32_t) ctx->nodes_bytes;
+    A.tris_bytes = (uint32_t) (mode == MODE_FLAT_SMEM ? ctx->flat_bytes : ctx->tris_bytes);
+    A.insts_bytes = (uint32_t) ctx->insts_bytes;
+    A.boxes_bytes = (uint32_t) ctx->boxes_bytes;
     unsigned long long n_lanes = record ? n_rec : A.n_local;
-    unsigned long long n_chunks = (n_lanes + kBlock - 1) / kBlock;
-    int grid = (int) std::min<unsigned long long>(std::max<unsigned long long>(n_chunks, 1), (unsigned long long) ctx->sm_count * 2);
+    unsigned long long n_units = (n_lanes + kUnit - 1) / kUnit;
+    unsigned long long want_ctas = (n_units + (kBlock / 32) - 1) / (kBlock / 32);
+    int grid = (int) std::min<unsigned long long>(std::max<unsigned long long>(want_ctas, 1), (unsigned long long) ctx->sm_count * 2);
     CU(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), stream));
     if (ctx->stats_enabled)
         CU(cudaMemsetAsync(ctx->d_stats, 0, sizeof(Counters), stream));
     CU(cudaEventRecord(ctx->ev0, stream));
     dtof_status s;
-    if (record)
-        s = ctx->stats_enabled ? launch_variant<true, true>(ctx, A, use_smem, grid, stream)
-                               : launch_variant<false, true>(ctx, A, use_smem, grid, stream);
+    if (mode == MODE_FLAT_SMEM)
+        s = launch_mode<MODE_FLAT_SMEM>(ctx, A, record, grid, stream);
+    else if (mode == MODE_BVH_SMEM)
+        s = launch_mode<MODE_BVH_SMEM>(ctx, A, record, grid, stream);
     else
-        s = ctx->stats_enabled ? launch_variant<true, false>(ctx, A, use_smem, grid, stream)
-                               : launch_variant<false, false>(ctx, A, use_smem, grid, stream);
+        s = launch_mode<MODE_BVH_GLOBAL>(ctx, A, record, grid, stream);
     if (s != DTOF_OK)
         return s;
+    ctx->last_mode = mode;
     CU(cudaEventRecord(ctx->ev1, stream));
     ctx->last_stream = stream;
     ctx->have_timing = true;
@@ -611,6 +644,7 @@ dtof_status dtof_upload_scene(dtof_ctx *ctx, const dtof_scene_desc *sc) {
     if (built.max_depth + built.tlas_depth + 4 > kStackSize)
         return fail(ctx, DTOF_ERR_UNSUPPORTED, "BVH too deep for the traversal stack (%d + %d)", built.max_depth, built.tlas_depth);
     std::vector<InstRec> insts(sc->n_instances);
+    std::vector<TriIsect> tris_flat;   // scene (gid) order, for the flat traversal of tiny scenes
     for (uint32_t g = 0; g < sc->n_instances; ++g) {
         const dtof_instance &in = sc->instances[g];
         InstRec &r = insts[g];
@@ -619,6 +653,10 @@ dtof_status dtof_upload_scene(dtof_ctx *ctx, const dtof_scene_desc *sc) {
         r.t0 = in.t0, r.t1 = in.t1;
         r.root = built.inst_root[g];
         r.animated = in.animated ? 1u : 0u;
+        r.first_tri = (uint32_t) tris_flat.size();
+        r.n_tris = (uint32_t) groups[g].tris.size();
+        r.pad0 = r.pad1 = 0;
+        tris_flat.insert(tris_flat.end(), groups[g].tris.begin(), groups[g].tris.end());
     }
 
     // ---- upload
@@ -628,6 +666,13 @@ dtof_status dtof_upload_scene(dtof_ctx *ctx, const dtof_scene_desc *sc) {
     if ((s = upload_vec(ctx, built.tris, &ctx->d_tris)) != DTOF_OK) return s;
     if ((s = upload_vec(ctx, shade, &ctx->d_shade)) != DTOF_OK) return s;
     if ((s = upload_vec(ctx, insts, &ctx->d_insts)) != DTOF_OK) return s;
+    if (tris_flat.size() > 4096)
+        tris_flat.resize(0);           // only tiny scenes ever use it
+    if ((s = upload_vec(ctx, tris_flat, &ctx->d_tris_flat)) != DTOF_OK) return s;
+    if ((s = upload_vec(ctx, built.inst_box, &ctx->d_boxes)) != DTOF_OK) return s;
+    ctx->flat_bytes = tris_flat.size() * sizeof(TriIsect);
+    ctx->boxes_bytes = built.inst_box.size() * sizeof(InstBox);
+    ctx->n_tris_total = gid;
     if ((s = upload_vec(ctx, meshes, &ctx->d_meshes)) != DTOF_OK) return s;
     if ((s = upload_vec(ctx, bsdfs, &ctx->d_bsdfs)) != DTOF_OK) return s;
     if ((s = upload_vec(ctx, emitters, &ctx->d_emitters)) != DTOF_OK) return s;

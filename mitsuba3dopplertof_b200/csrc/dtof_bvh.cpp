@@ -248,7 +248,11 @@ void build_scene_bvh(const std::vector<GroupInput> &groups, BuiltScene &out) {
         out.root = ~(int32_t) 0x7fffffff;   // never dereferenced: has_geometry = false
         out.has_geometry = false;
     } else {
-        auto make_ileaf = [&](uint32_t lo, uint32_t) -> int32_t { return ~(int32_t) irefs[lo].id; };
+        // animated instance -> instance leaf; static group -> its BLAS root is spliced in (single-level traversal)
+        auto make_ileaf = [&](uint32_t lo, uint32_t) -> int32_t {
+            uint32_t g = irefs[lo].id;
+            return groups[g].animated ? ~(int32_t) (g << 4) : out.inst_root[g];
+        };
         Box bb;
         out.root = build_range(irefs, 0, (uint32_t) irefs.size(), out.nodes, 1, 1, make_ileaf, bb, tdepth);
         out.has_geometry = true;
@@ -258,6 +262,15 @@ void build_scene_bvh(const std::vector<GroupInput> &groups, BuiltScene &out) {
         }
     }
     out.tlas_depth = tdepth;
+    out.inst_box.assign(groups.size(), InstBox{});
+    for (size_t g = 0; g < groups.size(); ++g) {
+        Box b = inst_boxes[g];
+        if (b.valid())
+            pad_box(b);
+        else
+            b.lo[0] = b.lo[1] = b.lo[2] = 1.f, b.hi[0] = b.hi[1] = b.hi[2] = -1.f;   // never hit
+        out.inst_box[g] = InstBox{ b.lo[0], b.lo[1], b.lo[2], 0.f, b.hi[0], b.hi[1], b.hi[2], 0.f };
+    }
 }
 
 } // namespace dtof

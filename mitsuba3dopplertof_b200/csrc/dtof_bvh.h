@@ -17,6 +17,7 @@ struct BuiltScene {
     std::vector<BvhNode> nodes;   // all BLAS nodes followed by the TLAS nodes; child indices are absolute
     std::vector<TriIsect> tris;   // leaf order
     std::vector<int32_t> inst_root;
+    std::vector<InstBox> inst_box;   // padded world bounds per instance
     int32_t root = 0;             // child reference of the TLAS root
     int max_depth = 0, tlas_depth = 0;
     bool has_geometry = false;

@@ -6,11 +6,11 @@
 // Stages (all __device__ functions below, fused by the render kernel in dtof_api.cu):
 //   sampler      LaneSampler            <- src/samplers/correlated.cpp:38-167, src/render/sampler.cpp:85-134
 //   camera       camera_ray()           <- src/sensors/perspective.cpp:238-279
-//   traversal    trace<ANY>()           <- Scene::ray_intersect / ray_test (src/render/scene.cpp:125-154),
+//   traversal    trace_bvh/trace_flat   <- Scene::ray_intersect / ray_test (src/render/scene.cpp:125-154),
 //                                          Embree motion instances (ext/embree/kernels/common/scene_instance.h:133-206)
 //   interaction  compute_si()           <- src/render/mesh.cpp:633-789, src/shapes/instance.cpp:155-250,
 //                                          include/mitsuba/render/interaction.h:258-268,493-516
-//   shading      trace_path()           <- src/integrators/dopplertofpath.cpp:79-283
+//   shading      trace_path() (dtof_path.cuh) <- src/integrators/dopplertofpath.cpp:79-283
 //   modulation   Modulation::eval()     <- dopplertofpath.cpp:60-77, include/mitsuba/render/waveform_utils.h:24-62
 //   film         splat_*()              <- src/render/imageblock.cpp:206-232,418-477
 //
@@ -371,6 +371,37 @@ struct Hit {
     int32_t inst;
 };
 
+// Moeller-Trumbore (include/mitsuba/render/mesh.h:342-365) against one stored triangle (p0 | e1 | e2), split into a
+// conservative pre-test and the exact reference arithmetic. The pre-test works on the un-normalised numerators
+// (U = tvec.pvec, V = d.qvec, D = det), never rejects a triangle the exact test accepts (margins >> the 2 ulp that
+// u = U * (1/D) can move), and lets most tests finish without the IEEE reciprocal. Accepted hits are bit-identical to
+// the plain formula.
+DTOF_DEV bool tri_test(const float4 a, const float4 b, const float4 c, V3 ro, V3 rd, float best, float &t_out,
+                       float &u_out, float &v_out) {
+    V3 e1 = v3(b.x, b.y, b.z), e2 = v3(c.x, c.y, c.z);
+    V3 pvec = cross3(rd, e2);
+    float det = dot3(e1, pvec);
+    V3 tvec = ro - v3(a.x, a.y, a.z);
+    float U = dot3(tvec, pvec);
+    float Da = fabsf(det);
+    float Us = mulsign(U, det);
+    if (!(Us >= -1e-20f * Da && Us <= Da * 1.000001f))
+        return false;
+    V3 qvec = cross3(tvec, e1);
+    float V = dot3(rd, qvec);
+    float Vs = mulsign(V, det);
+    if (!(Vs >= -1e-20f * Da && Us + Vs <= Da * 1.000002f))
+        return false;
+    float inv_det = 1.f / det;
+    float u = U * inv_det;
+    float v = V * inv_det;
+    float t = dot3(e2, qvec) * inv_det;
+    t_out = t;
+    u_out = u;
+    v_out = v;
+    return u >= 0.f && u <= 1.f && v >= 0.f && u + v <= 1.f && t >= 0.f && t <= best;
+}
+
 DTOF_DEV void load_inst_matrix(const float4 *ip, float time, bool clamp, M34 &M) {
     // AnimatedTransform::eval (clamped, transform.h:451-456) or Embree's unclamped fraction (default.h:225-231)
     float4 q6 = ip[6];
@@ -388,26 +419,54 @@ DTOF_DEV void load_inst_matrix(const float4 *ip, float time, bool clamp, M34 &M)
     }
 }
 
-// Closest-hit (ANY=false) or any-hit (ANY=true) traversal of the two-level BVH with per-ray time.
+// Enter an animated instance (Embree: world->local = rcp(lerp(M0, M1, f)) with the UNCLAMPED fraction f,
+// ext/embree/kernels/common/scene_instance.h:133-138,186-206, default.h:225-231)
+DTOF_DEV void enter_instance(const float4 *ip, V3 o, V3 d, float time, V3 &ro, V3 &rd) {
+    M34 M;
+    load_inst_matrix(ip, time, false, M);
+    M34 inv = inverse_m34(M);
+    ro = xf_point(inv, o);
+    rd = xf_vector(inv, d);
+}
+
+constexpr int kDone = 0x7fffffff;
+
+// Closest-hit (ANY=false) or any-hit (ANY=true) traversal of the BVH with per-ray time.
+// Static geometry is single-level (the static group's BLAS is spliced into the TLAS); an animated instance is an
+// "instance leaf": the ray is moved into the instance's space, a sentinel marks the way back.
+// Loop shape after Aila & Laine: a lane stays in the inner-node loop (popping included) until it holds a leaf.
 // `N`, `T`, `I` are the node / triangle / instance arrays (global memory, or their shared-memory copies).
 template <bool ANY, bool STATS>
-DTOF_DEV bool trace(const float4 *__restrict__ N, const float4 *__restrict__ T, const float4 *__restrict__ I,
-                    int32_t root, V3 o, V3 d, float tmax, float time, Hit &hit, Counters &st) {
+DTOF_DEV bool trace_bvh(const float4 *__restrict__ N, const float4 *__restrict__ T, const float4 *__restrict__ I,
+                        int32_t root, V3 o, V3 d, float tmax, float time, Hit &hit, Counters &st) {
     int stack[kStackSize];
     int sp = 0;
     int node = root;
-    bool in_blas = false;
     int cur_inst = -1;
-    V3 ro = o, rd = d;                                       // ray in the current (world / object) space
-    V3 id = v3(1.f / d.x, 1.f / d.y, 1.f / d.z);
+    V3 ro = o, rd = d;                                       // ray in the current (world / instance) space
+    const V3 wid = v3(1.f / d.x, 1.f / d.y, 1.f / d.z);
+    V3 id = wid;
     float best = tmax;
     bool found = false;
     if (STATS) {
         if (ANY) st.rays_shadow++; else st.rays_closest++;
     }
-    for (;;) {
-        // ---- descend through inner nodes
-        while (node >= 0) {
+#define DTOF_POP()                                                                                         \
+    do {                                                                                                   \
+        if (sp == 0) {                                                                                     \
+            node = kDone;                                                                                  \
+        } else {                                                                                           \
+            node = stack[--sp];                                                                            \
+            if (node == kSentinel) { /* leave the instance: back to the world-space ray */                 \
+                ro = o, rd = d, id = wid, cur_inst = -1;                                                   \
+                node = sp ? stack[--sp] : kDone;                                                           \
+            }                                                                                              \
+        }                                                                                                  \
+    } while (0)
+
+    while (node != kDone) {
+        // ---- inner nodes (node in [0, kDone))
+        while ((unsigned) node < (unsigned) kDone) {
             const float4 *np = N + 4 * (size_t) node;
             float4 n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3];
             if (STATS) st.nodes++;
@@ -426,82 +485,117 @@ DTOF_DEV bool trace(const float4 *__restrict__ N, const float4 *__restrict__ T, 
             int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
             if (h0 && h1) {
                 bool swap = t1n < t0n;
-                int nearc = swap ? c1 : c0, farc = swap ? c0 : c1;
-                stack[sp++] = farc;
-                node = nearc;
-            } else if (h0) {
-                node = c0;
-            } else if (h1) {
-                node = c1;
+                stack[sp++] = swap ? c0 : c1;
+                node = swap ? c1 : c0;
+            } else if (h0 || h1) {
+                node = h0 ? c0 : c1;
             } else {
-                goto pop;
+                DTOF_POP();
             }
         }
+        if (node == kDone)
+            break;
         // ---- leaf
-        if (!in_blas) {
-            // TLAS leaf: enter the instance (Embree: world->local = rcp(lerp(M0, M1, f)), unclamped f)
-            cur_inst = ~node;
-            const float4 *ip = I + 7 * (size_t) cur_inst;
-            float4 q6 = ip[6];
-            if (__float_as_uint(q6.w) != 0u) {
-                if (STATS) st.inst++;
-                M34 M;
-                load_inst_matrix(ip, time, false, M);
-                M34 inv = inverse_m34(M);
-                ro = xf_point(inv, o);
-                rd = xf_vector(inv, d);
-                id = v3(1.f / rd.x, 1.f / rd.y, 1.f / rd.z);
-            }
+        uint32_t code = (uint32_t) ~node;
+        uint32_t count = code & 15u;
+        if (count == 0) {
+            cur_inst = (int) (code >> 4);
+            const float4 *ip = I + 8 * (size_t) cur_inst;
+            if (STATS) st.inst++;
+            enter_instance(ip, o, d, time, ro, rd);
+            id = v3(1.f / rd.x, 1.f / rd.y, 1.f / rd.z);
             stack[sp++] = kSentinel;
-            in_blas = true;
-            node = __float_as_int(q6.z);
+            node = __float_as_int(ip[6].z);
             continue;
-        } else {
-            uint32_t code = (uint32_t) ~node;
-            uint32_t first = code >> 4, count = code & 15u;
-            for (uint32_t i = 0; i < count; ++i) {
-                const float4 *tp = T + 3 * (size_t) (first + i);
-                float4 a = tp[0], b = tp[1], c = tp[2];
-                if (STATS) st.tris++;
-                // moeller_trumbore, include/mitsuba/render/mesh.h:342-365
-                V3 e1 = v3(b.x, b.y, b.z), e2 = v3(c.x, c.y, c.z);
-                V3 pvec = cross3(rd, e2);
-                float inv_det = 1.f / dot3(e1, pvec);
-                V3 tvec = ro - v3(a.x, a.y, a.z);
-                float u = dot3(tvec, pvec) * inv_det;
-                V3 qvec = cross3(tvec, e1);
-                float v = dot3(rd, qvec) * inv_det;
-                float t = dot3(e2, qvec) * inv_det;
-                bool ok = u >= 0.f && u <= 1.f && v >= 0.f && u + v <= 1.f && t >= 0.f && t <= best;
-                if (ok) {
-                    if (ANY)
-                        return true;
-                    uint32_t gid = __float_as_uint(a.w);
-                    if (t < best || !found || gid < hit.gid) {
-                        best = t;
-                        hit.t = t;
-                        hit.u = u;
-                        hit.v = v;
-                        hit.gid = gid;
-                        hit.inst = cur_inst;
-                        found = true;
-                    }
+        }
+        uint32_t first = code >> 4;
+        for (uint32_t i = 0; i < count; ++i) {
+            const float4 *tp = T + 3 * (size_t) (first + i);
+            float4 a = tp[0], b = tp[1], c = tp[2];
+            if (STATS) st.tris++;
+            float t, u, v;
+            if (tri_test(a, b, c, ro, rd, best, t, u, v)) {
+                if (ANY)
+                    return true;
+                uint32_t gid = __float_as_uint(a.w);
+                if (t < best || !found || gid < hit.gid) {
+                    best = t;
+                    hit.t = t;
+                    hit.u = u;
+                    hit.v = v;
+                    hit.gid = gid;
+                    hit.inst = cur_inst;
+                    found = true;
                 }
             }
         }
-    pop:
-        if (sp == 0)
-            break;
-        node = stack[--sp];
-        if (node == kSentinel) {   // leave the instance: back to the world-space ray
-            in_blas = false;
-            ro = o;
-            rd = d;
-            id = v3(1.f / d.x, 1.f / d.y, 1.f / d.z);
-            if (sp == 0)
-                break;
-            node = stack[--sp];
+        DTOF_POP();
+    }
+#undef DTOF_POP
+    return found;
+}
+
+// Flat, warp-coherent traversal for tiny scenes: every lane walks ALL triangles of every instance in scene order
+// (uniform control flow, shared-memory reads are broadcasts, no stack). An animated instance is skipped when no lane
+// of the warp touches its padded world bounds. With a few dozen triangles this beats the per-lane BVH walk, whose
+// SIMD efficiency on incoherent bounce rays is ~1/3 (profiles/r01_render_c2_v1_ncu_summary.json).
+// `TF` = triangles in scene (gid) order, `B` = instance world boxes. Must be called by all 32 lanes of the warp;
+// `lane_active` masks lanes without a ray.
+template <bool ANY, bool STATS>
+DTOF_DEV bool trace_flat(const float4 *__restrict__ TF, const float4 *__restrict__ I, const float4 *__restrict__ B,
+                         uint32_t n_insts, V3 o, V3 d, float tmax, float time, bool lane_active, Hit &hit, Counters &st) {
+    float best = tmax;
+    bool found = false;
+    const V3 wid = v3(1.f / d.x, 1.f / d.y, 1.f / d.z);
+    if (STATS && lane_active) {
+        if (ANY) st.rays_shadow++; else st.rays_closest++;
+    }
+    for (uint32_t g = 0; g < n_insts; ++g) {
+        const float4 *ip = I + 8 * (size_t) g;
+        const float4 q6 = ip[6], q7 = ip[7];
+        const uint32_t first = __float_as_uint(q7.x), n = __float_as_uint(q7.y);
+        const bool animated = __float_as_uint(q6.w) != 0u;
+        V3 ro = o, rd = d;
+        bool want = lane_active && !(ANY && found);
+        if (animated) {
+            // world-bounds cull (slab test as in the BVH walk), decided per warp
+            float4 lo = B[2 * g], hi = B[2 * g + 1];
+            float lx = (lo.x - o.x) * wid.x, hx = (hi.x - o.x) * wid.x;
+            float ly = (lo.y - o.y) * wid.y, hy = (hi.y - o.y) * wid.y;
+            float lz = (lo.z - o.z) * wid.z, hz = (hi.z - o.z) * wid.z;
+            float tn = fmaxf(fmaxf(fminf(lx, hx), fminf(ly, hy)), fmaxf(fminf(lz, hz), 0.f));
+            float tf = fminf(fminf(fmaxf(lx, hx), fmaxf(ly, hy)), fmaxf(lz, hz)) * 1.0000005f;
+            want = want && tn <= fminf(tf, best);
+            if (!__any_sync(kFullMask, want))
+                continue;
+            if (STATS && want) st.inst++;
+            enter_instance(ip, o, d, time, ro, rd);
+        } else if (!__any_sync(kFullMask, want)) {
+            continue;
         }
+        const float4 *tp = TF + 3 * (size_t) first;
+#pragma unroll 2
+        for (uint32_t i = 0; i < n; ++i, tp += 3) {
+            float4 a = tp[0], b = tp[1], c = tp[2];
+            if (STATS && want) st.tris++;
+            float t, u, v;
+            if (want && tri_test(a, b, c, ro, rd, best, t, u, v)) {
+                if (ANY) {
+                    found = true;
+                    want = false;
+                } else if (t < best || !found) {   // scene order == ascending gid: ties keep the first
+                    best = t;
+                    hit.t = t;
+                    hit.u = u;
+                    hit.v = v;
+                    hit.gid = __float_as_uint(a.w);
+                    hit.inst = animated ? (int) g : -1;
+                    found = true;
+                }
+            }
+        }
+        if (ANY && __all_sync(kFullMask, found || !lane_active))
+            break;
     }
     return found;
 }
@@ -551,8 +645,8 @@ DTOF_DEV void compute_si(const DeviceScene &S, const float4 *__restrict__ I, con
         si.n = -si.n;
         si.sh_n = -si.sh_n;
     }
-    const float4 *ip = I + 7 * (size_t) h.inst;
-    if (__float_as_uint(ip[6].w) != 0u) {
+    if (h.inst >= 0) {   // only animated instances are recorded on a hit
+        const float4 *ip = I + 8 * (size_t) h.inst;
         M34 to_world;
         load_inst_matrix(ip, ray_time, true, to_world);
         M34 to_object = inverse_m34(to_world);
@@ -637,196 +731,6 @@ struct PathOut {
     float path_length;
     uint32_t depth;
 };
-
-// DopplerToFPathIntegrator::sample (JIT semantics), see the oracle for the line-by-line citations
-template <bool STATS>
-DTOF_DEV PathOut trace_path(const DeviceScene &S, const float4 *__restrict__ N, const float4 *__restrict__ T,
-                            const float4 *__restrict__ I, const dtof_params &P, const Modulation &mod,
-                            LaneSampler &smp, V3 ray_o, V3 ray_d, float ray_maxt, float time_in, Counters &st) {
-    PathOut out{ v3(0, 0, 0), 0.f, 0 };
-    if (P.max_depth == 0)
-        return out;
-    const uint32_t max_depth = (uint32_t) P.max_depth, rr_depth = (uint32_t) P.rr_depth;
-    const float ray_time = time_in < P.time ? time_in : time_in - P.time;
-    V3 throughput = v3(1, 1, 1), result = v3(0, 0, 0);
-    float path_length = 0.f, eta = 1.f;
-    uint32_t depth = 0;
-    bool valid_ray = false;
-    V3 prev_p = v3(0, 0, 0);
-    float prev_bsdf_pdf = 1.f;
-    bool prev_bsdf_delta = true;
-    bool active = true;
-    const uint32_t n_em = S.n_emitters;
-    const float emitter_pmf = n_em ? 1.f / (float) n_em : 0.f;
-
-    while (active) {
-        const bool correlate = (depth + 1) < P.path_correlation_depth;
-        Hit h;
-        h.gid = 0;
-        bool valid = S.has_geometry && trace<false, STATS>(N, T, I, S.root, ray_o, ray_d, ray_maxt, ray_time, h, st);
-        SI si;
-        uint32_t bsdf_flags = 0;
-        V3 refl = v3(0, 0, 0);
-        int32_t mesh_emitter = -1;
-        if (valid) {
-            compute_si(S, I, h, ray_d, ray_time, si);
-            const MeshRec &mr = S.meshes[si.mesh];
-            mesh_emitter = mr.emitter;
-            const BsdfRec br = S.bsdfs[mr.bsdf];
-            bsdf_flags = br.flags;
-            refl = v3(br.r, br.g, br.b);
-            path_length += h.t * eta;
-        }
-        // ---- direct emission
-        if (valid && mesh_emitter >= 0) {
-            const MeshRec &em_mesh = S.meshes[si.mesh];
-            const EmitterRec em = S.emitters[mesh_emitter];
-            V3 rel = si.p - prev_p;
-            float dist = sqrtf(dot3(rel, rel));
-            V3 dsd = rel / dist;
-            float em_pdf = 0.f;
-            if (!prev_bsdf_delta) {
-                float dp = dot3(dsd, si.sh_n);
-                float pdf = em_mesh.inv_area, adp = fabsf(dp);
-                pdf *= adp != 0.f ? (dist * dist) / adp : 0.f;
-                em_pdf = (dp < 0.f ? pdf : 0.f) * emitter_pmf;
-            }
-            float mis_bsdf = mis_weight(prev_bsdf_pdf, em_pdf);
-            float lw = mod.eval(ray_time, path_length);
-            V3 Le = (si.wi.z > 0.f && prev_bsdf_pdf > 0.f) ? v3(em.vr, em.vg, em.vb) : v3(0, 0, 0);
-            V3 c = Le * mis_bsdf * lw;
-            result = v3(fmaf(throughput.x, c.x, result.x), fmaf(throughput.y, c.y, result.y),
-                        fmaf(throughput.z, c.z, result.z));
-        }
-        const bool active_next = (depth + 1 < max_depth) && valid;
-        const bool smooth = (bsdf_flags & 2u) != 0;
-        const bool twosided = (bsdf_flags & 1u) != 0;
-
-        // ---- emitter sampling: the 2D sample is always consumed
-        uint64_t e1a = smp.rng_path.step(), e1b = smp.rng.step();
-        uint64_t e2a = smp.rng_path.step(), e2b = smp.rng.step();
-        smp.draws += 2;
-        bool active_em = active_next && smooth && n_em > 0;
-        V3 ds_d = v3(0, 0, 0), em_weight = v3(0, 0, 0), wo = v3(0, 0, 0);
-        float ds_dist = 0.f, ds_pdf = 0.f;
-        bool ds_delta = false;
-        if (active_em) {
-            uint32_t index = 0;
-            float sx = 0.f, sy = 0.f;
-            V3 ds_p, ds_n, spec;
-            EmitterRec em = S.emitters[0];
-            if (n_em > 1 || em.kind != DTOF_EMITTER_POINT) {
-                sx = u32_to_float(pcg_output(correlate ? e1a : e1b));
-                sy = u32_to_float(pcg_output(correlate ? e2a : e2b));
-            }
-            if (n_em > 1) {
-                float scaled = sx * (float) n_em;
-                index = min((uint32_t) scaled, n_em - 1u);
-                sx = scaled - (float) index;
-                em = S.emitters[index];
-            }
-            if (em.kind == DTOF_EMITTER_POINT) {
-                ds_p = v3(em.px, em.py, em.pz);
-                ds_pdf = 1.f;
-                ds_delta = true;
-                ds_d = ds_p - si.p;
-                float dist2 = dot3(ds_d, ds_d), inv_dist = rsqrt_ieee(dist2);
-                ds_dist = sqrtf(dist2);
-                ds_d = ds_d * inv_dist;
-                float f = inv_dist * inv_dist;
-                spec = v3(em.vr * f, em.vg * f, em.vb * f);
-            } else {
-                sample_position(S, S.meshes[em.mesh], sx, sy, ds_p, ds_n, ds_pdf);
-                ds_d = ds_p - si.p;
-                float dist2 = dot3(ds_d, ds_d);
-                ds_dist = sqrtf(dist2);
-                ds_d = ds_d / ds_dist;
-                float dp = fabsf(dot3(ds_d, ds_n));
-                float x = dist2 / dp;
-                ds_pdf *= isfinite(x) ? x : 0.f;
-                bool em_active = dot3(ds_d, ds_n) < 0.f && ds_pdf != 0.f;
-                spec = em_active ? v3(em.vr / ds_pdf, em.vg / ds_pdf, em.vb / ds_pdf) : v3(0, 0, 0);
-            }
-            if (n_em > 1) {
-                ds_pdf *= emitter_pmf;
-                spec = spec * (float) n_em;
-            }
-            if (ds_pdf != 0.f) {
-                V3 so = offset_p(si.p, si.n, ds_p - si.p);
-                V3 sd = ds_p - so;
-                float dist = sqrtf(dot3(sd, sd));
-                sd = sd / dist;
-                Hit dummy;
-                if (trace<true, STATS>(N, T, I, S.root, so, sd, dist * (1.f - kShadowEps), ray_time, dummy, st)) {
-                    spec = v3(0, 0, 0);
-                    ds_pdf = 0.f;
-                }
-            }
-            em_weight = spec;
-            active_em = ds_pdf != 0.f;
-            wo = v3(dot3(ds_d, si.sh_s), dot3(ds_d, si.sh_t), dot3(ds_d, si.sh_n));
-        }
-
-        // ---- BSDF eval + sample; sample_1 is drawn but unused by the diffuse lobe
-        smp.skip_1d();
-        float s2x = smp.next_1d(correlate), s2y = smp.next_1d(correlate);
-        V3 bsdf_val = v3(0, 0, 0), bsdf_weight = v3(0, 0, 0), bs_wo = v3(0, 0, 0);
-        float bsdf_pdf = 0.f, bs_pdf = 0.f, bs_eta = 0.f;
-        if (valid && smooth) {
-            float wi_z = si.wi.z, wo_z = wo.z;
-            if (twosided) {
-                wo_z = mulsign(wo_z, wi_z);
-                wi_z = fabsf(wi_z);
-            }
-            if (wi_z > 0.f && wo_z > 0.f) {
-                bsdf_val = refl * kInvPi * wo_z;
-                bsdf_pdf = kInvPi * wo_z;
-            }
-            if (wi_z > 0.f) {
-                bs_wo = square_to_cosine_hemisphere(s2x, s2y);
-                bs_pdf = kInvPi * bs_wo.z;
-                bs_eta = 1.f;
-                if (bs_pdf > 0.f)
-                    bsdf_weight = refl;
-                if (twosided)
-                    bs_wo.z = mulsign(bs_wo.z, si.wi.z);
-            }
-        }
-        if (active_em) {
-            float mis_em = ds_delta ? 1.f : mis_weight(ds_pdf, bsdf_pdf);
-            float lw = mod.eval(ray_time, path_length + ds_dist);
-            V3 c = bsdf_val * em_weight * mis_em * lw;
-            result = v3(fmaf(throughput.x, c.x, result.x), fmaf(throughput.y, c.y, result.y),
-                        fmaf(throughput.z, c.z, result.z));
-        }
-        if (valid) {
-            V3 wd = fma3(si.sh_n, bs_wo.z, fma3(si.sh_t, bs_wo.y, si.sh_s * bs_wo.x));
-            ray_o = offset_p(si.p, si.n, wd);
-            ray_d = wd;
-            ray_maxt = 3.402823466e+38f;
-            prev_p = si.p;
-        }
-        throughput = throughput * bsdf_weight;
-        eta *= bs_eta;
-        valid_ray = valid_ray || valid;
-        prev_bsdf_pdf = bs_pdf;
-        prev_bsdf_delta = false;
-        if (valid)
-            depth += 1;
-        float tmax = max3(throughput);
-        float rr_prob = fminf(tmax * (eta * eta), 0.95f);
-        bool rr_active = depth >= rr_depth;
-        float q = smp.next_1d(correlate);
-        bool rr_continue = q < rr_prob;
-        if (rr_active)
-            throughput = throughput * (1.f / rr_prob);
-        active = active_next && (!rr_active || rr_continue) && tmax != 0.f;
-    }
-    out.rgb = valid_ray ? result : v3(0, 0, 0);
-    out.path_length = path_length;
-    out.depth = depth;
-    return out;
-}
 
 DTOF_DEV void camera_ray(const dtof_camera &c, float u, float v, V3 &o, V3 &d, float &maxt) {
     const float *m = c.sample_to_camera;

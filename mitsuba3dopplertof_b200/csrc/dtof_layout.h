@@ -3,7 +3,7 @@
 // Everything a ray touches during traversal is a 16-byte-aligned record fetched with 128-bit loads:
 //   BvhNode   64 B  binary BVH node holding BOTH children's boxes (so one fetch decides both sides)
 //   TriIsect  48 B  p0 + the two edges + the triangle's global id (Moeller-Trumbore inputs, mesh.h:342-365)
-//   InstRec  112 B  per-instance motion: two 3x4 keyframes, key times, BLAS root
+//   InstRec  128 B  per-instance motion: two 3x4 keyframes, key times, BLAS root, triangle range
 // and, once per hit,
 //   TriShade  96 B  p1, p2, vertex normals, uvs, mesh id/flags (Mesh::compute_surface_interaction inputs)
 // These sizes are the per-unit figures of the traversal roofline.
@@ -12,8 +12,10 @@
 
 namespace dtof {
 
-// Child reference encoding: ref >= 0 -> inner node index; ref < 0 -> leaf.
-//   TLAS leaf: ~ref = instance index.   BLAS leaf: ~ref = (first_tri << 4) | count, count in [1, 15].
+// Child reference encoding: ref >= 0 -> inner node index; ref < 0 -> leaf with code = ~ref:
+//   triangle leaf : code = (first_tri << 4) | count, count in [1, 15]
+//   instance leaf : code = (instance  << 4) | 0      (animated instances only; the static group's BLAS is linked
+//                                                     into the TLAS directly, so static geometry is single-level)
 struct alignas(16) BvhNode {
     float c0_lox, c0_hix, c0_loy, c0_hiy;   // child 0 box x/y
     float c1_lox, c1_hix, c1_loy, c1_hiy;   // child 1 box x/y
@@ -51,8 +53,16 @@ struct alignas(16) InstRec {
     float t0, t1;
     int32_t root;          // child reference of the BLAS root
     uint32_t animated;
+    uint32_t first_tri;    // range in the scene-order triangle array (flat traversal of tiny scenes)
+    uint32_t n_tris;
+    uint32_t pad0, pad1;
 };
-static_assert(sizeof(InstRec) == 112, "InstRec must be 112 bytes");
+static_assert(sizeof(InstRec) == 128, "InstRec must be 128 bytes");
+
+struct alignas(16) InstBox {   // padded world bounds over both keyframes (instance culling in the flat traversal)
+    float lox, loy, loz, pad0;
+    float hix, hiy, hiz, pad1;
+};
 
 struct MeshRec {
     uint32_t bsdf;
