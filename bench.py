@@ -4,7 +4,7 @@
 Metric: Msamples/s = camera samples (pixels x spp, each a full path of <= max_depth bounces incl. NEE) per second
 of render(), scene resident on the GPU.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3|c4] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3|c4|c5] [--impl reference]
 
 * step         one render() of the workload (film zeroed, all passes, film all-reduce when N > 1, develop)
 * value        whole-job samples / device time (CUDA events per step on the render stream, max over ranks);
@@ -46,6 +46,10 @@ WORKLOADS = {
     "c4": ("c4_domino.xml", {"resx": 1024, "resy": 1024, "spp": 4096, "wave": "trapezoidal", "tsm": "antithetic_mirror",
                               "shift": 0.0, "w_g": 150},
            "C4 domino (32 animated boxes), trapezoidal, antithetic_mirror, 1024x1024 @ 4096 spp (2 passes x 2048)"),
+    # C5: one of the 16 renders (seed = rank) the reference needs for 2048^2 @ 16k spp: 1024 spp = 2 passes x 512
+    "c5": ("c5_slabroom.xml", {"resx": 2048, "resy": 2048, "spp": 1024},
+           "C5 slab room + 4.2 M-triangle displaced sphere as one animated instance, 2048x2048 @ 1024 spp per render "
+           "(2 passes x 512; 16 renders with seed 0..15 make the 16k-spp image)"),
 }
 
 
@@ -89,10 +93,17 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons)}
 
 
-def load_workload(name):
+def load_workload(name, spp=0):
     import mitsuba3dopplertof_b200 as dt
     fn, params, desc = WORKLOADS[name]
+    params = dict(params)
+    if spp:
+        params["spp"] = spp
+        desc += f" [REDUCED to {spp} spp: profiling run, not a bench value]"
     scene = dt.load_file(os.path.join(ROOT, "tests", "scenes", fn), **params)
+    if name == "c5":
+        from mitsuba3dopplertof_b200 import procedural
+        scene = procedural.large_scene(scene, n=592, seed=1234)
     return scene, desc
 
 
@@ -162,7 +173,7 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    scene, desc = load_workload(args.workload)
+    scene, desc = load_workload(args.workload, args.spp)
     cores = os.cpu_count() or 1
     fn, params, _ = WORKLOADS[args.workload]
     p = dict({"resx": 256, "resy": 256, "spp": 1024}, **params)
@@ -205,6 +216,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--spp", type=int, default=0, help="override the workload's spp (profiling under ncu only)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -222,7 +234,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    scene, desc = load_workload(args.workload)
+    scene, desc = load_workload(args.workload, args.spp)
     ctx = runtime.Context(local)
     t0 = time.perf_counter()
     flat = ctx.upload(scene)
@@ -267,6 +279,7 @@ def main():
         s1.synchronize()
         kernel_ms.append(ctx.last_kernel_ms())
     torch.cuda.synchronize()
+    prod_mode = ctx.last_traversal_mode()
     if world > 1:
         dist.barrier()
     launches = ctx.launch_count() - launches0 + args.steps   # ours + one film memset per step
@@ -307,8 +320,11 @@ def main():
 
     # ---- roofline of the dominant kernel (render_kernel): algorithmic traversal bytes / kernel time
     ctx.set_stats(True)
-    lanes = min(pi.wavefront_size, 1 << 24)        # the counters are per-sample averages: a 16M-lane slice is plenty
-    ps = scene.integrator.params(sampler, seed=seed, lane_begin=0, lane_end=lanes)
+    # the counters are per-sample averages: every K-th pixel (all its sample slots) is plenty, ~16 M lanes
+    K = max(1, int(pi.wavefront_size // (1 << 24))) | 1
+    ps = scene.integrator.params(sampler, seed=seed)
+    if K > 1:
+        ps.shard_block, ps.shard_count, ps.shard_index = pi.spp_per_pass, K, 0
     film.zero_()
     ctx.render_device(ps, film.data_ptr(), stream.cuda_stream)
     torch.cuda.synchronize()
@@ -319,6 +335,7 @@ def main():
     instr_per_sample = (40 * st.nodes_visited + 45 * st.tris_tested + 110 * st.inst_visits) / n + \
         420 * (st.rays_closest / n) + 60
     kms = float(np.mean(kernel_ms))
+    mode_name = {0: "bvh_global", 1: "bvh_smem", 2: "flat_smem"}.get(prod_mode, str(prod_mode))
     peaks, peak_src = measured_peaks()
     achieved = bytes_per_sample * samples_per_step / (kms * 1e-3) / 1e9
     clk = clocks.summary()
@@ -329,7 +346,10 @@ def main():
         "kernel_ms": kms, "bytes_per_sample": bytes_per_sample,
         "per_sample": {"rays_closest": st.rays_closest / n, "rays_shadow": st.rays_shadow / n, "nodes": st.nodes_visited / n,
                        "tris": st.tris_tested / n, "inst": st.inst_visits / n},
-        "note": "traversal data of this workload is staged in shared memory, so the byte rate is served by SMEM/L1, not HBM",
+        "traversal_mode": mode_name,
+        "note": ("counts are those of the BVH walk (closest + shadow rays); " + (
+            "the traversal data of this workload is staged in shared memory, so the byte rate is served by SMEM, not HBM"
+            if mode_name != "bvh_global" else "nodes/triangles are read through L1/L2 from HBM")),
         "issue": {"instr_per_sample_model": instr_per_sample,
                   "achieved_lane_instr_per_s": instr_per_sample * samples_per_step / (kms * 1e-3),
                   "peak_lane_instr_per_s": issue_peak,

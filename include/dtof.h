@@ -203,7 +203,8 @@ typedef struct dtof_sample_record {
     uint32_t rng_draws;    /* draws consumed from the independent stream */
 } dtof_sample_record;
 
-/* Traversal work counters of the last render (filled when DTOF_STATS=1 or dtof_set_stats(ctx,1)). */
+/* Traversal work counters of the last render (filled after dtof_set_stats(ctx, 1)). They count the BVH walk:
+ * a scene that normally runs the flat shared-memory walk is rendered through its BVH while stats are on. */
 typedef struct dtof_stats {
     uint64_t samples;        /* camera samples traced */
     uint64_t rays_closest, rays_shadow;
@@ -219,6 +220,14 @@ typedef struct dtof_pass_info {
     uint64_t wavefront_size; /* lanes per pass */
 } dtof_pass_info;
 
+/* Result of the host half of dtof_upload_scene (validation + flattening + BVH build), no GPU needed. */
+typedef struct dtof_scene_info {
+    uint32_t n_triangles, n_nodes, n_instances, bvh_depth;
+    uint64_t traversal_bytes;   /* nodes + leaf-order triangles + instance records */
+    uint64_t shading_bytes;     /* per-hit triangle records */
+    float build_ms;
+} dtof_scene_info;
+
 /* ---- entry points ------------------------------------------------------------------------ */
 
 uint32_t dtof_abi_version(void);
@@ -230,6 +239,11 @@ const char *dtof_last_error(const dtof_ctx *ctx);
 
 /* Flatten, build the two-level BVH and upload everything to HBM. May be called again to replace the scene. */
 dtof_status dtof_upload_scene(dtof_ctx *ctx, const dtof_scene_desc *scene);
+
+/* Validate a scene description and build its BVH on the host WITHOUT touching the GPU (what the Scene constructor's
+ * checks do in the reference, src/render/scene.cpp:22-100, src/render/shapegroup.cpp:27-30). `err` (may be NULL)
+ * receives the message on failure. */
+dtof_status dtof_scene_info_for(const dtof_scene_desc *scene, dtof_scene_info *out, char *err, uint32_t err_len);
 
 /* Replace the keyframes of instances [first, first+n) without rebuilding bottom-level BVHs
  * (animation loops, doppler_tutorials/src/main_animation.py:61-157). */
@@ -258,6 +272,10 @@ dtof_status dtof_trace_samples(dtof_ctx *ctx, const dtof_params *params, const u
 /* Enable/disable traversal counters (slower kernel variant) and read them back after a render. */
 dtof_status dtof_set_stats(dtof_ctx *ctx, int enabled);
 dtof_status dtof_get_stats(dtof_ctx *ctx, dtof_stats *out);
+
+/* Traversal variant the last render kernel ran with: 0 = BVH read from HBM through L1/L2, 1 = BVH staged in shared
+ * memory, 2 = flat warp-coherent walk over all triangles in shared memory (tiny scenes); -1 = nothing rendered yet. */
+int dtof_last_traversal_mode(const dtof_ctx *ctx);
 
 /* Number of kernels this library launched on this context since creation (bench.py's gpu_launches). */
 uint64_t dtof_launch_count(const dtof_ctx *ctx);

@@ -120,6 +120,11 @@ class PassInfo(C.Structure):
     _fields_ = [("spp_per_pass", C.c_uint32), ("n_passes", C.c_uint32), ("wavefront_size", C.c_uint64)]
 
 
+class SceneInfo(C.Structure):
+    _fields_ = [("n_triangles", C.c_uint32), ("n_nodes", C.c_uint32), ("n_instances", C.c_uint32), ("bvh_depth", C.c_uint32),
+                ("traversal_bytes", C.c_uint64), ("shading_bytes", C.c_uint64), ("build_ms", C.c_float)]
+
+
 # every symbol include/dtof.h declares: name -> (restype, argtypes)
 _ctx = C.c_void_p
 DTOF_SYMBOLS = {
@@ -128,6 +133,7 @@ DTOF_SYMBOLS = {
     "dtof_destroy": (None, [_ctx]),
     "dtof_last_error": (C.c_char_p, [_ctx]),
     "dtof_upload_scene": (C.c_int, [_ctx, C.POINTER(SceneDesc)]),
+    "dtof_scene_info_for": (C.c_int, [C.POINTER(SceneDesc), C.POINTER(SceneInfo), C.c_char_p, C.c_uint32]),
     "dtof_update_instances": (C.c_int, [_ctx, C.c_uint32, C.c_uint32, C.POINTER(Instance)]),
     "dtof_pass_info_for": (C.c_int, [_ctx, C.POINTER(Params), C.POINTER(PassInfo)]),
     "dtof_render": (C.c_int, [_ctx, C.POINTER(Params), _fp, _fp]),
@@ -137,6 +143,7 @@ DTOF_SYMBOLS = {
                                      C.POINTER(SampleRecord)]),
     "dtof_set_stats": (C.c_int, [_ctx, C.c_int]),
     "dtof_get_stats": (C.c_int, [_ctx, C.POINTER(Stats)]),
+    "dtof_last_traversal_mode": (C.c_int, [_ctx]),
     "dtof_launch_count": (C.c_uint64, [_ctx]),
     "dtof_last_kernel_ms": (C.c_int, [_ctx, C.POINTER(C.c_float)]),
 }

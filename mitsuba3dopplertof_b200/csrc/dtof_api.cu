@@ -8,6 +8,7 @@
 // instead of 36 per lane).
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -27,6 +28,9 @@ using namespace dtof;
 namespace {
 
 constexpr int kBlock = 256;
+#ifndef DTOF_MIN_CTAS
+#define DTOF_MIN_CTAS 2
+#endif
 constexpr unsigned long long kUnit = 256;       // lanes per work unit fetched by one warp (8 warp iterations)
 constexpr size_t kSmemSceneLimit = 96 * 1024;   // traversal data up to this size is staged in shared memory
 constexpr uint32_t kFlatMaxTris = 64;           // scenes up to this many triangles use the flat coherent walk
@@ -54,7 +58,7 @@ struct RenderArgs {
 };
 
 template <int MODE, bool STATS, bool RECORD>
-__global__ void __launch_bounds__(kBlock, 2) render_kernel(const __grid_constant__ RenderArgs A) {
+__global__ void __launch_bounds__(kBlock, DTOF_MIN_CTAS) render_kernel(const __grid_constant__ RenderArgs A) {
     extern __shared__ float4 smem[];
     TravPtrs TP;
     TP.N = A.scene.nodes, TP.T = A.scene.tris, TP.TF = A.tris_flat, TP.I = A.scene.insts, TP.B = A.inst_box;
@@ -416,6 +420,10 @@ dtof_status launch_render(dtof_ctx *ctx, const dtof_params *p, float *d_rgbw, cu
     if (want == MODE_BVH_GLOBAL || (want == MODE_BVH_SMEM && bvh_bytes + 1024 <= ctx->smem_optin) ||
         (want == MODE_FLAT_SMEM && flat_bytes + 1024 <= ctx->smem_optin))
         mode = want;
+    // the traversal counters are defined on the BVH walk (algorithmic work of the scene), whatever
+    // mode the production launch of this scene picks
+    if (ctx->stats_enabled && !record && mode == MODE_FLAT_SMEM)
+        mode = bvh_bytes + 1024 <= ctx->smem_optin ? MODE_BVH_SMEM : MODE_BVH_GLOBAL;
     A.nodes_bytes = (uint32_t) ctx->nodes_bytes;
     A.tris_bytes = (uint32_t) (mode == MODE_FLAT_SMEM ? ctx->flat_bytes : ctx->tris_bytes);
     A.insts_bytes = (uint32_t) ctx->insts_bytes;
@@ -423,7 +431,7 @@ dtof_status launch_render(dtof_ctx *ctx, const dtof_params *p, float *d_rgbw, cu
     unsigned long long n_lanes = record ? n_rec : A.n_local;
     unsigned long long n_units = (n_lanes + kUnit - 1) / kUnit;
     unsigned long long want_ctas = (n_units + (kBlock / 32) - 1) / (kBlock / 32);
-    int grid = (int) std::min<unsigned long long>(std::max<unsigned long long>(want_ctas, 1), (unsigned long long) ctx->sm_count * 2);
+    int grid = (int) std::min<unsigned long long>(std::max<unsigned long long>(want_ctas, 1), (unsigned long long) ctx->sm_count * DTOF_MIN_CTAS);
     CU(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), stream));
     if (ctx->stats_enabled)
         CU(cudaMemsetAsync(ctx->d_stats, 0, sizeof(Counters), stream));
@@ -446,53 +454,22 @@ dtof_status launch_render(dtof_ctx *ctx, const dtof_params *p, float *d_rgbw, cu
 
 } // namespace
 
-// ==================================================================================================
-extern "C" {
+namespace {
 
-uint32_t dtof_abi_version(void) { return DTOF_ABI_VERSION; }
+// Host half of dtof_upload_scene: validate, flatten, build the two-level BVH. No CUDA call in here.
+struct HostScene {
+    std::vector<MeshRec> meshes;
+    std::vector<BsdfRec> bsdfs;
+    std::vector<EmitterRec> emitters;
+    std::vector<TriShade> shade;
+    std::vector<float> cdf, pmf;
+    std::vector<InstRec> insts;
+    std::vector<TriIsect> tris_flat;
+    BuiltScene built;
+    uint32_t n_tris = 0;
+};
 
-dtof_status dtof_create(dtof_ctx **out, int device) {
-    if (!out)
-        return DTOF_ERR_INVALID;
-    *out = nullptr;
-    int n = 0;
-    cudaError_t e = cudaGetDeviceCount(&n);
-    if (e != cudaSuccess || device < 0 || device >= n)
-        return e != cudaSuccess ? DTOF_ERR_CUDA : DTOF_ERR_INVALID;
-    dtof_ctx *ctx = new dtof_ctx();
-    ctx->device = device;
-    cudaDeviceProp prop;
-    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess ||
-        cudaMalloc(&ctx->d_counter, sizeof(unsigned long long)) != cudaSuccess ||
-        cudaMalloc(&ctx->d_stats, sizeof(Counters)) != cudaSuccess || cudaEventCreate(&ctx->ev0) != cudaSuccess ||
-        cudaEventCreate(&ctx->ev1) != cudaSuccess) {
-        delete ctx;
-        return DTOF_ERR_CUDA;
-    }
-    ctx->sm_count = prop.multiProcessorCount;
-    ctx->smem_optin = prop.sharedMemPerBlockOptin;
-    *out = ctx;
-    return DTOF_OK;
-}
-
-void dtof_destroy(dtof_ctx *ctx) {
-    if (!ctx)
-        return;
-    cudaSetDevice(ctx->device);
-    free_scene(ctx);
-    if (ctx->d_counter) cudaFree(ctx->d_counter);
-    if (ctx->d_stats) cudaFree(ctx->d_stats);
-    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
-    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-    delete ctx;
-}
-
-const char *dtof_last_error(const dtof_ctx *ctx) { return ctx ? ctx->error.c_str() : "null context"; }
-
-dtof_status dtof_upload_scene(dtof_ctx *ctx, const dtof_scene_desc *sc) {
-    if (!ctx || !sc)
-        return DTOF_ERR_INVALID;
-    CU(cudaSetDevice(ctx->device));
+dtof_status prepare_scene(dtof_ctx *ctx, const dtof_scene_desc *sc, HostScene &H) {
     if (sc->film.width == 0 || sc->film.height == 0)
         return fail(ctx, DTOF_ERR_INVALID, "empty film");
     if (sc->film.rfilter > DTOF_RFILTER_GAUSSIAN)
@@ -500,11 +477,14 @@ dtof_status dtof_upload_scene(dtof_ctx *ctx, const dtof_scene_desc *sc) {
     if (sc->film.rfilter != DTOF_RFILTER_BOX && !(sc->film.rfilter_radius > 0.f && sc->film.rfilter_radius <= 7.5f))
         return fail(ctx, DTOF_ERR_INVALID, "rfilter radius out of range");
     // ---- validate + flatten
-    std::vector<MeshRec> meshes(sc->n_meshes);
-    std::vector<BsdfRec> bsdfs(sc->n_bsdfs);
-    std::vector<EmitterRec> emitters(sc->n_emitters);
-    std::vector<TriShade> shade;
-    std::vector<float> cdf, pmf;
+    std::vector<MeshRec> &meshes = H.meshes;
+    std::vector<BsdfRec> &bsdfs = H.bsdfs;
+    std::vector<EmitterRec> &emitters = H.emitters;
+    std::vector<TriShade> &shade = H.shade;
+    std::vector<float> &cdf = H.cdf, &pmf = H.pmf;
+    meshes.assign(sc->n_meshes, MeshRec{});
+    bsdfs.assign(sc->n_bsdfs, BsdfRec{});
+    emitters.assign(sc->n_emitters, EmitterRec{});
     std::vector<GroupInput> groups(sc->n_instances);
     std::vector<uint32_t> mesh_first_gid(sc->n_meshes, 0xffffffffu);
     for (uint32_t i = 0; i < sc->n_bsdfs; ++i) {
@@ -639,12 +619,13 @@ dtof_status dtof_upload_scene(dtof_ctx *ctx, const dtof_scene_desc *sc) {
     (void) all_point;
 
     // ---- BVH
-    BuiltScene built;
+    BuiltScene &built = H.built;
     build_scene_bvh(groups, built);
     if (built.max_depth + built.tlas_depth + 4 > kStackSize)
         return fail(ctx, DTOF_ERR_UNSUPPORTED, "BVH too deep for the traversal stack (%d + %d)", built.max_depth, built.tlas_depth);
-    std::vector<InstRec> insts(sc->n_instances);
-    std::vector<TriIsect> tris_flat;   // scene (gid) order, for the flat traversal of tiny scenes
+    std::vector<InstRec> &insts = H.insts;
+    insts.assign(sc->n_instances, InstRec{});
+    std::vector<TriIsect> &tris_flat = H.tris_flat;   // scene (gid) order, for the flat traversal of tiny scenes
     for (uint32_t g = 0; g < sc->n_instances; ++g) {
         const dtof_instance &in = sc->instances[g];
         InstRec &r = insts[g];
@@ -656,18 +637,82 @@ dtof_status dtof_upload_scene(dtof_ctx *ctx, const dtof_scene_desc *sc) {
         r.first_tri = (uint32_t) tris_flat.size();
         r.n_tris = (uint32_t) groups[g].tris.size();
         r.pad0 = r.pad1 = 0;
-        tris_flat.insert(tris_flat.end(), groups[g].tris.begin(), groups[g].tris.end());
+        if (gid <= 4096)               // only tiny scenes ever use the flat walk
+            tris_flat.insert(tris_flat.end(), groups[g].tris.begin(), groups[g].tris.end());
     }
 
+    H.n_tris = gid;
+    return DTOF_OK;
+}
+
+} // namespace
+
+// ==================================================================================================
+extern "C" {
+
+uint32_t dtof_abi_version(void) { return DTOF_ABI_VERSION; }
+
+dtof_status dtof_create(dtof_ctx **out, int device) {
+    if (!out)
+        return DTOF_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || device < 0 || device >= n)
+        return e != cudaSuccess ? DTOF_ERR_CUDA : DTOF_ERR_INVALID;
+    dtof_ctx *ctx = new dtof_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess ||
+        cudaMalloc(&ctx->d_counter, sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMalloc(&ctx->d_stats, sizeof(Counters)) != cudaSuccess || cudaEventCreate(&ctx->ev0) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+        delete ctx;
+        return DTOF_ERR_CUDA;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    *out = ctx;
+    return DTOF_OK;
+}
+
+void dtof_destroy(dtof_ctx *ctx) {
+    if (!ctx)
+        return;
+    cudaSetDevice(ctx->device);
+    free_scene(ctx);
+    if (ctx->d_counter) cudaFree(ctx->d_counter);
+    if (ctx->d_stats) cudaFree(ctx->d_stats);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    delete ctx;
+}
+
+const char *dtof_last_error(const dtof_ctx *ctx) { return ctx ? ctx->error.c_str() : "null context"; }
+
+dtof_status dtof_upload_scene(dtof_ctx *ctx, const dtof_scene_desc *sc) {
+    if (!ctx || !sc)
+        return DTOF_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    HostScene H;
+    dtof_status s = prepare_scene(ctx, sc, H);
+    if (s != DTOF_OK)
+        return s;
+    std::vector<MeshRec> &meshes = H.meshes;
+    std::vector<BsdfRec> &bsdfs = H.bsdfs;
+    std::vector<EmitterRec> &emitters = H.emitters;
+    std::vector<TriShade> &shade = H.shade;
+    std::vector<float> &cdf = H.cdf, &pmf = H.pmf;
+    std::vector<InstRec> &insts = H.insts;
+    std::vector<TriIsect> &tris_flat = H.tris_flat;
+    BuiltScene &built = H.built;
+    const uint32_t gid = H.n_tris;
     // ---- upload
     free_scene(ctx);
-    dtof_status s;
     if ((s = upload_vec(ctx, built.nodes, &ctx->d_nodes)) != DTOF_OK) return s;
     if ((s = upload_vec(ctx, built.tris, &ctx->d_tris)) != DTOF_OK) return s;
     if ((s = upload_vec(ctx, shade, &ctx->d_shade)) != DTOF_OK) return s;
     if ((s = upload_vec(ctx, insts, &ctx->d_insts)) != DTOF_OK) return s;
-    if (tris_flat.size() > 4096)
-        tris_flat.resize(0);           // only tiny scenes ever use it
     if ((s = upload_vec(ctx, tris_flat, &ctx->d_tris_flat)) != DTOF_OK) return s;
     if ((s = upload_vec(ctx, built.inst_box, &ctx->d_boxes)) != DTOF_OK) return s;
     ctx->flat_bytes = tris_flat.size() * sizeof(TriIsect);
@@ -705,6 +750,30 @@ dtof_status dtof_upload_scene(dtof_ctx *ctx, const dtof_scene_desc *sc) {
     CU(cudaMalloc(&ctx->d_rgbw, ctx->film_px * 4 * sizeof(float)));
     CU(cudaMalloc(&ctx->d_img, ctx->film_px * 3 * sizeof(float)));
     ctx->has_scene = true;
+    return DTOF_OK;
+}
+
+dtof_status dtof_scene_info_for(const dtof_scene_desc *sc, dtof_scene_info *out, char *err, uint32_t err_len) {
+    if (!sc || !out)
+        return DTOF_ERR_INVALID;
+    dtof_ctx tmp;   // host-only: carries the error string, never touches CUDA
+    HostScene H;
+    auto t0 = std::chrono::steady_clock::now();
+    dtof_status s = prepare_scene(&tmp, sc, H);
+    double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (s != DTOF_OK) {
+        if (err && err_len)
+            snprintf(err, err_len, "%s", tmp.error.c_str());
+        return s;
+    }
+    out->n_triangles = H.n_tris;
+    out->n_nodes = (uint32_t) H.built.nodes.size();
+    out->n_instances = sc->n_instances;
+    out->bvh_depth = (uint32_t) (H.built.max_depth + H.built.tlas_depth);
+    out->traversal_bytes = (uint64_t) H.built.nodes.size() * sizeof(BvhNode) + (uint64_t) H.built.tris.size() * sizeof(TriIsect) +
+                           (uint64_t) H.insts.size() * sizeof(InstRec);
+    out->shading_bytes = (uint64_t) H.shade.size() * sizeof(TriShade);
+    out->build_ms = (float) ms;
     return DTOF_OK;
 }
 
@@ -860,6 +929,8 @@ dtof_status dtof_get_stats(dtof_ctx *ctx, dtof_stats *out) {
     out->inst_visits = c.inst;
     return DTOF_OK;
 }
+
+int dtof_last_traversal_mode(const dtof_ctx *ctx) { return ctx ? ctx->last_mode : -1; }
 
 uint64_t dtof_launch_count(const dtof_ctx *ctx) { return ctx ? ctx->launches : 0; }
 

@@ -5,6 +5,7 @@
 #include "dtof_bvh.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cfloat>
 #include <cmath>
 #include <cstring>
@@ -165,6 +166,114 @@ inline void xf_point(const float *m, const float *p, float *o) {
         o[r] = m[4 * r + 0] * p[0] + m[4 * r + 1] * p[1] + m[4 * r + 2] * p[2] + m[4 * r + 3];
 }
 
+// Large groups (multi-million-triangle meshes): the top of the tree is built serially down to subtrees of
+// <= n / kTaskSplit references; the subtrees are independent jobs built by a thread pool into private node /
+// triangle arrays (local indices), then appended to the output with their indices rebased.
+constexpr uint32_t kParallelMin = 1u << 16;
+constexpr uint32_t kTaskSplit = 256;
+
+struct SubtreeJob {
+    uint32_t lo, hi;
+    int depth;
+    std::vector<BvhNode> nodes;
+    std::vector<TriIsect> tris;
+    int32_t root = 0;
+    int max_depth = 0;
+};
+
+int32_t build_group_parallel(const GroupInput &G, std::vector<Ref> &refs, BuiltScene &out, int &max_depth) {
+    const uint32_t n = (uint32_t) refs.size();
+    const uint32_t job_size = std::max<uint32_t>(n / kTaskSplit, 4096);
+    std::vector<SubtreeJob> jobs;
+    // top of the tree: a "leaf" of the top builder is a job; its reference is a placeholder patched below
+    std::vector<BvhNode> top;
+    auto make_job = [&](uint32_t lo, uint32_t hi) -> int32_t {
+        SubtreeJob j;
+        j.lo = lo, j.hi = hi, j.depth = 0;
+        jobs.push_back(std::move(j));
+        return ~(int32_t) (((uint32_t) (jobs.size() - 1) << 4) | 0u);   // count 0 marks a job placeholder here
+    };
+    Box bb;
+    int top_depth = 0;
+    std::vector<int> job_depth;
+    // build_range does not pass the depth to make_leaf: recover each job's depth from the top tree afterwards
+    int32_t top_root = build_range(refs, 0, n, top, 1, job_size, make_job, bb, top_depth);
+    job_depth.assign(jobs.size(), 1);
+    {   // depth of every placeholder in the top tree
+        struct E { int32_t ref; int depth; };
+        std::vector<E> st{ { top_root, 1 } };
+        while (!st.empty()) {
+            E e = st.back();
+            st.pop_back();
+            if (e.ref >= 0) {
+                st.push_back({ top[e.ref].child0, e.depth + 1 });
+                st.push_back({ top[e.ref].child1, e.depth + 1 });
+            } else {
+                job_depth[(uint32_t) ~e.ref >> 4] = e.depth;
+            }
+        }
+    }
+    unsigned n_threads = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+    std::atomic<size_t> next{ 0 };
+    auto worker = [&]() {
+        for (;;) {
+            size_t k = next.fetch_add(1);
+            if (k >= jobs.size())
+                break;
+            SubtreeJob &j = jobs[k];
+            auto make_leaf = [&](uint32_t lo, uint32_t hi) -> int32_t {
+                uint32_t first = (uint32_t) j.tris.size();
+                for (uint32_t i = lo; i < hi; ++i)
+                    j.tris.push_back(G.tris[refs[i].id]);
+                return ~(int32_t) ((first << 4) | (hi - lo));
+            };
+            Box b;
+            j.root = build_range(refs, j.lo, j.hi, j.nodes, job_depth[k], kMaxLeaf, make_leaf, b, j.max_depth);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < n_threads; ++t)
+        pool.emplace_back(worker);
+    worker();
+    for (auto &t : pool)
+        t.join();
+    // append: top nodes first, then every job's nodes / triangles with rebased indices
+    const int32_t top_base = (int32_t) out.nodes.size();
+    out.nodes.insert(out.nodes.end(), top.begin(), top.end());
+    std::vector<int32_t> job_ref(jobs.size());
+    for (size_t k = 0; k < jobs.size(); ++k) {
+        SubtreeJob &j = jobs[k];
+        const int32_t node_base = (int32_t) out.nodes.size();
+        const uint32_t tri_base = (uint32_t) out.tris.size();
+        auto rebase = [&](int32_t ref) -> int32_t {
+            if (ref >= 0)
+                return ref + node_base;
+            uint32_t code = (uint32_t) ~ref;
+            return ~(int32_t) ((((code >> 4) + tri_base) << 4) | (code & 15u));
+        };
+        for (BvhNode nd : j.nodes) {
+            nd.child0 = rebase(nd.child0);
+            nd.child1 = rebase(nd.child1);
+            out.nodes.push_back(nd);
+        }
+        out.tris.insert(out.tris.end(), j.tris.begin(), j.tris.end());
+        job_ref[k] = rebase(j.root);
+        max_depth = std::max(max_depth, j.max_depth);
+        std::vector<BvhNode>().swap(j.nodes);
+        std::vector<TriIsect>().swap(j.tris);
+    }
+    auto patch = [&](int32_t ref) -> int32_t {
+        return ref >= 0 ? ref + top_base : job_ref[(uint32_t) ~ref >> 4];
+    };
+    for (size_t i = 0; i < top.size(); ++i) {
+        BvhNode &nd = out.nodes[top_base + i];
+        nd.child0 = patch(nd.child0);
+        nd.child1 = patch(nd.child1);
+    }
+    max_depth = std::max(max_depth, top_depth);
+    return patch(top_root);
+}
+
 } // namespace
 
 void build_scene_bvh(const std::vector<GroupInput> &groups, BuiltScene &out) {
@@ -193,22 +302,22 @@ void build_scene_bvh(const std::vector<GroupInput> &groups, BuiltScene &out) {
             refs[i].id = i;
             gb.grow(refs[i].box);
         }
-        uint32_t tri_base = (uint32_t) out.tris.size();
-        auto make_leaf = [&](uint32_t lo, uint32_t hi) -> int32_t {
-            uint32_t first = (uint32_t) out.tris.size();
-            for (uint32_t i = lo; i < hi; ++i)
-                out.tris.push_back(G.tris[refs[i].id]);
-            return ~(int32_t) ((first << 4) | (hi - lo));
-        };
-        (void) tri_base;
-        Box bb;
         int depth = 0;
         int32_t root;
         if (n == 0) {
             // empty group: a leaf with zero triangles is not encodable -> point at an empty range via count 0
             root = ~(int32_t) (((uint32_t) out.tris.size()) << 4);
-        } else {
+        } else if (n < kParallelMin) {
+            auto make_leaf = [&](uint32_t lo, uint32_t hi) -> int32_t {
+                uint32_t first = (uint32_t) out.tris.size();
+                for (uint32_t i = lo; i < hi; ++i)
+                    out.tris.push_back(G.tris[refs[i].id]);
+                return ~(int32_t) ((first << 4) | (hi - lo));
+            };
+            Box bb;
             root = build_range(refs, 0, n, out.nodes, 1, kMaxLeaf, make_leaf, bb, depth);
+        } else {
+            root = build_group_parallel(G, refs, out, depth);
         }
         out.inst_root[g] = root;
         out.max_depth = std::max(out.max_depth, depth);

@@ -15,7 +15,7 @@ import numpy as np
 from . import _abi
 from .integrator import DTOFError
 
-__all__ = ["load_library", "build_library", "Context", "get_context", "library_path"]
+__all__ = ["load_library", "build_library", "scene_info", "Context", "get_context", "library_path"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB: Optional[C.CDLL] = None
@@ -23,7 +23,8 @@ _CTX: Dict[int, "Context"] = {}
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "libdtof_b200.so")
+    # DTOF_LIB selects another build of the same library (kernel experiments); there is still no non-CUDA path
+    return os.environ.get("DTOF_LIB") or os.path.join(_HERE, "libdtof_b200.so")
 
 
 def build_library(verbose: bool = False) -> str:
@@ -49,6 +50,20 @@ def load_library() -> C.CDLL:
             raise DTOFError("libdtof_b200.so ABI version mismatch")
         _LIB = lib
     return _LIB
+
+
+def scene_info(scene_or_flat) -> _abi.SceneInfo:
+    """Host half of the upload (validation, flattening, BVH build) -- needs the library but no GPU."""
+    lib = load_library()
+    flat = scene_or_flat.flatten() if hasattr(scene_or_flat, "flatten") else scene_or_flat
+    info, err = _abi.SceneInfo(), C.create_string_buffer(512)
+    rc = lib.dtof_scene_info_for(C.byref(flat.desc), C.byref(info), err, 512)
+    if rc != _abi.OK:
+        msg = err.value.decode("utf-8", "replace")
+        if rc == _abi.ERR_INVALID:
+            raise ValueError(msg)
+        raise DTOFError(f"[status {rc}] {msg}")
+    return info
 
 
 class Context:
@@ -133,6 +148,9 @@ class Context:
         st = _abi.Stats()
         self._check(self.lib.dtof_get_stats(self.h, C.byref(st)))
         return st
+
+    def last_traversal_mode(self) -> int:
+        return int(self.lib.dtof_last_traversal_mode(self.h))
 
     def launch_count(self) -> int:
         return int(self.lib.dtof_launch_count(self.h))
