@@ -1,0 +1,309 @@
+// Mitsuba-side binding of libdtof_b200.so: the plugin a maintainer of juhyeonkim95/Mitsuba3DopplerToF adds as
+// src/integrators/dopplertofpath_b200.cpp (plugin name "dopplertofpath_b200", or installed over "dopplertofpath").
+// It keeps the reference's property surface, walks the loaded mitsuba::Scene, hands plain arrays to the C ABI
+// (include/dtof.h) and puts the returned RGBW tensor into the film, i.e. it replaces
+//   SamplingIntegrator::render            src/render/integrator.cpp:104-347
+// for this integrator. Built for scalar_rgb (Float = float, host memory), with the reference's exact compile flags
+// (INTEGRATION.md). NOT compiled in this repository's image: the reference needs its CMake build (generated
+// config.h, Embree, Dr.Jit), which this round treats as unbuildable; `host/dtof_render` is the compiled and tested
+// twin of this file (same flattening code path in host/dtof_scene.cpp).
+//
+// Two accessors must be added to the reference because the data is private there (8 lines):
+//   Shape::animated_to_world()                  -> Instance::m_transform   (src/shapes/instance.cpp:340)
+//   Sampler::time/path_correlate_number()       -> CorrelatedSampler members (src/samplers/correlated.cpp:18-19)
+#include <mitsuba/core/properties.h>
+#include <mitsuba/core/transform.h>
+#include <mitsuba/render/bsdf.h>
+#include <mitsuba/render/emitter.h>
+#include <mitsuba/render/film.h>
+#include <mitsuba/render/imageblock.h>
+#include <mitsuba/render/integrator.h>
+#include <mitsuba/render/mesh.h>
+#include <mitsuba/render/sampler.h>
+#include <mitsuba/render/scene.h>
+#include <mitsuba/render/sensor.h>
+
+#include "dtof.h"
+
+NAMESPACE_BEGIN(mitsuba)
+
+namespace {
+// Collects the children / parameters an object exposes through traverse() (the only public window onto
+// Rectangle::m_to_world, ShapeGroup::m_shapes, TwoSidedBRDF::m_brdf, PointLight::m_position ...).
+struct Collector : TraversalCallback {
+    std::vector<std::pair<std::string, Object *>> objects;
+    std::vector<std::pair<std::string, void *>> params;
+    void put_parameter_impl(const std::string &name, void *ptr, uint32_t, const std::type_info &) override {
+        params.emplace_back(name, ptr);
+    }
+    void put_object(const std::string &name, Object *obj, uint32_t) override { objects.emplace_back(name, obj); }
+    template <typename T> T *param(const char *name) {
+        for (auto &p : params)
+            if (p.first == name)
+                return (T *) p.second;
+        return nullptr;
+    }
+};
+} // namespace
+
+template <typename Float, typename Spectrum>
+class DopplerToFPathB200 final : public MonteCarloIntegrator<Float, Spectrum> {
+public:
+    MI_IMPORT_BASE(MonteCarloIntegrator, m_max_depth, m_rr_depth, m_hide_emitters, m_time_sampling_method, m_antithetic_shift,
+                   m_use_stratified_sampling_for_each_interval, m_path_correlation_depth, m_is_doppler_integrator, m_stop,
+                   m_render_timer, should_stop)
+    MI_IMPORT_TYPES(Scene, Sensor, Film, ImageBlock, Sampler, Shape, Mesh, BSDF, Emitter, Medium)
+
+    DopplerToFPathB200(const Properties &props) : Base(props) {
+        if constexpr (dr::is_jit_v<Float> || !is_rgb_v<Spectrum>)
+            Throw("dopplertofpath_b200 is a scalar_rgb host plugin: the GPU work happens behind the C ABI");
+        m_is_doppler_integrator = true;
+        // same reads, defaults and syntactic sugar as DopplerToFPathIntegrator (src/integrators/dopplertofpath.cpp:19-57)
+        m_p = dtof_params{};
+        m_p.time = props.get<ScalarFloat>("time", 0.0015f);
+        m_p.w_g = props.get<ScalarFloat>("w_g", 30.f);
+        m_p.g_1 = props.get<ScalarFloat>("g_1", 0.5f);
+        m_p.g_0 = props.get<ScalarFloat>("g_0", 0.5f);
+        ScalarFloat w_s = props.get<ScalarFloat>("w_s", 30.f);
+        m_p.sensor_phase_offset = props.get<ScalarFloat>("sensor_phase_offset", 0.f);
+        if (props.has_property("hetero_offset"))
+            m_p.sensor_phase_offset = props.get<ScalarFloat>("hetero_offset", 0.0) * 2 * M_PI;
+        if (props.has_property("hetero_frequency"))
+            m_p.hetero_frequency = props.get<ScalarFloat>("hetero_frequency", 1.0);
+        else
+            m_p.hetero_frequency = (w_s - m_p.w_g) * 1e6 * m_p.time;
+        std::string wave = props.get<std::string>("wave_function_type", "sinusoidal");
+        if (wave == "sinusoidal") m_p.wave_function_type = DTOF_WAVE_SINUSOIDAL;
+        else if (wave == "rectangular") m_p.wave_function_type = DTOF_WAVE_RECTANGULAR;
+        else if (wave == "triangular") m_p.wave_function_type = DTOF_WAVE_TRIANGULAR;
+        else if (wave == "trapezoidal") m_p.wave_function_type = DTOF_WAVE_TRAPEZOIDAL;
+        else Throw("unknown wave_function_type \"%s\"", wave);
+        m_p.low_frequency_component_only = props.get<bool>("low_frequency_component_only", true);
+        m_device = props.get<int>("device", 0);
+        if (dtof_create(&m_ctx, m_device) != DTOF_OK)
+            Throw("dtof_create(device=%i) failed: no usable CUDA device (there is no CPU fallback)", m_device);
+    }
+    ~DopplerToFPathB200() { dtof_destroy(m_ctx); }
+
+    TensorXf render(Scene *scene, Sensor *sensor, uint32_t seed, uint32_t spp, bool develop, bool /*evaluate*/) override {
+        m_stop = false;
+        m_render_timer.reset();
+        Film *film = sensor->film();
+        if (m_uploaded != scene) {          // flatten + BVH build + H2D once per scene
+            upload(scene, sensor);
+            m_uploaded = scene;
+        }
+        dtof_params p = m_p;
+        p.max_depth = (int32_t) m_max_depth, p.rr_depth = (int32_t) m_rr_depth, p.hide_emitters = m_hide_emitters;
+        p.time_sampling_method = (uint32_t) m_time_sampling_method;      // ETimeSampling order == dtof_time_sampling
+        p.antithetic_shift = m_antithetic_shift;
+        p.use_stratified_sampling_for_each_interval = m_use_stratified_sampling_for_each_interval;
+        p.path_correlation_depth = m_path_correlation_depth;
+        const Sampler *sampler = sensor->sampler();
+        p.sample_count = spp ? spp : sampler->sample_count();            // integrator.cpp:121-124
+        p.base_seed = sampler->seed();
+        p.time_correlate_number = sampler->time_correlate_number();      // accessor added by the reference-side patch
+        p.path_correlate_number = sampler->path_correlate_number();
+        p.seed = seed;
+
+        ScalarVector2u size = film->crop_size();
+        film->prepare({});                                               // channels R,G,B,W (hdrfilm.cpp:235-279)
+        size_t n = (size_t) size.x() * size.y() * 4;
+        std::unique_ptr<float[]> rgbw(new float[n]);
+        if (dtof_render(m_ctx, &p, rgbw.get(), nullptr) != DTOF_OK)      // H2D params, kernels, D2H film inside
+            Throw("dtof_render: %s", dtof_last_error(m_ctx));
+        // hand the accumulation tensor to the film exactly as the JIT branch does (integrator.cpp:266,310-323)
+        size_t shape[3] = { size.y(), size.x(), 4 };
+        TensorXf tensor(dr::load<DynamicBuffer<Float>>(rgbw.get(), n), 3, shape);
+        ref<ImageBlock> block = new ImageBlock(tensor, film->crop_offset(), film->rfilter(), /*border*/ false);
+        film->put_block(block);
+        Log(Info, "Rendering finished. (took %s)", util::time_string((float) m_render_timer.value(), true));
+        return develop ? film->develop() : TensorXf();
+    }
+
+    // The scalar entry point stays available for callers that sample single rays (integrator.h:200-205):
+    // it is the reference's own CPU code and is not on the accelerated path.
+    std::pair<Spectrum, Mask> sample(const Scene *, Sampler *, const RayDifferential3f &, const Medium *, Float *,
+                                     Mask) const override {
+        Throw("dopplertofpath_b200 renders whole images through render(); use 'dopplertofpath' for per-ray sample()");
+    }
+
+    MI_DECLARE_CLASS()
+
+private:
+    static void m34(const ScalarTransform4f &t, float *out) {
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 4; ++c)
+                out[4 * r + c] = t.matrix(r, c);
+    }
+    struct MeshBuf {
+        std::vector<float> pos, nrm, uv;
+        std::vector<uint32_t> idx;
+    };
+    uint32_t bsdf_index(const BSDF *bsdf, std::vector<dtof_bsdf> &out) {
+        dtof_bsdf b{};
+        b.kind = DTOF_BSDF_DIFFUSE;
+        const BSDF *inner = bsdf;
+        if (bsdf->class_()->name() == "TwoSidedBRDF") {
+            Collector c;
+            const_cast<BSDF *>(bsdf)->traverse(&c);
+            if (c.objects.size() != 2 || c.objects[0].second != c.objects[1].second)
+                Throw("twosided with two different BRDFs is outside the accelerated path");
+            inner = (const BSDF *) c.objects[0].second;
+            b.twosided = 1;
+        }
+        if (inner->class_()->name() != "SmoothDiffuse")
+            Throw("BSDF \"%s\" is outside the accelerated path (diffuse | twosided(diffuse))", inner->class_()->name());
+        SurfaceInteraction3f si = dr::zeros<SurfaceInteraction3f>();
+        Spectrum r = inner->eval_diffuse_reflectance(si);                // constant RGB reflectance
+        b.reflectance[0] = r[0], b.reflectance[1] = r[1], b.reflectance[2] = r[2];
+        for (size_t i = 0; i < out.size(); ++i)
+            if (!memcmp(&out[i], &b, sizeof(b)))
+                return (uint32_t) i;
+        out.push_back(b);
+        return (uint32_t) out.size() - 1;
+    }
+    void add_shape(const Shape *shape, std::vector<dtof_mesh> &meshes, std::vector<MeshBuf> &bufs, std::vector<dtof_bsdf> &bsdfs) {
+        dtof_mesh m{};
+        MeshBuf buf;
+        m.emitter = -1;
+        m.bsdf = bsdf_index(shape->bsdf(), bsdfs);
+        if (shape->is_mesh()) {                                          // Mesh, Cube, PLY, OBJ: world / group space buffers
+            const Mesh *mesh = (const Mesh *) shape;
+            buf.pos.assign(mesh->vertex_positions_buffer().data(), mesh->vertex_positions_buffer().data() + 3 * mesh->vertex_count());
+            buf.idx.assign(mesh->faces_buffer().data(), mesh->faces_buffer().data() + 3 * mesh->face_count());
+            if (mesh->has_vertex_normals())
+                buf.nrm.assign(mesh->vertex_normals_buffer().data(), mesh->vertex_normals_buffer().data() + 3 * mesh->vertex_count());
+            if (mesh->has_vertex_texcoords())
+                buf.uv.assign(mesh->vertex_texcoords_buffer().data(), mesh->vertex_texcoords_buffer().data() + 2 * mesh->vertex_count());
+            m.kind = DTOF_SHAPE_MESH;
+            m.flip_normals = mesh->has_flipped_normals();
+        } else if (shape->class_()->name() == "Rectangle") {             // analytic quad -> 2 triangles + parametrisation
+            Collector c;
+            const_cast<Shape *>(shape)->traverse(&c);
+            const ScalarTransform4f &tw = *c.param<ScalarTransform4f>("to_world");
+            const float corners[4][2] = { { -1, -1 }, { 1, -1 }, { 1, 1 }, { -1, 1 } };
+            for (auto &cn : corners) {
+                ScalarPoint3f p = tw.transform_affine(ScalarPoint3f(cn[0], cn[1], 0.f));
+                buf.pos.insert(buf.pos.end(), { p.x(), p.y(), p.z() });
+            }
+            buf.uv = { 0, 0, 1, 0, 1, 1, 0, 1 };
+            bool ccw = dr::det(ScalarMatrix3f(tw.matrix)) > 0;
+            buf.idx = ccw ? std::vector<uint32_t>{ 0, 1, 2, 0, 2, 3 } : std::vector<uint32_t>{ 0, 2, 1, 0, 3, 2 };
+            m.kind = DTOF_SHAPE_RECTANGLE;
+            m34(tw, m.rect_to_world);
+        } else {
+            Throw("shape \"%s\" is outside the accelerated path (meshes and rectangles)", shape->class_()->name());
+        }
+        meshes.push_back(m);
+        bufs.push_back(std::move(buf));
+    }
+    void upload(const Scene *scene, const Sensor *sensor) {
+        std::vector<dtof_mesh> meshes;
+        std::vector<MeshBuf> bufs;
+        std::vector<dtof_bsdf> bsdfs;
+        std::vector<dtof_instance> instances;
+        std::vector<dtof_emitter> emitters;
+        std::vector<std::pair<const Shape *, uint32_t>> mesh_of;
+        // static group first, then one instance per animated shape (the XML rewrite already produced
+        // shapegroup + instance pairs, src/core/xml.cpp:1166-1192)
+        for (auto &s : scene->shapes())
+            if (!s->is_instance()) {
+                mesh_of.emplace_back(s.get(), (uint32_t) meshes.size());
+                add_shape(s.get(), meshes, bufs, bsdfs);
+            }
+        dtof_instance st{};
+        st.n_meshes = (uint32_t) meshes.size();
+        const float ident[12] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0 };
+        memcpy(st.m0, ident, sizeof(ident));
+        memcpy(st.m1, ident, sizeof(ident));
+        if (st.n_meshes)
+            instances.push_back(st);
+        for (auto &s : scene->shapes())
+            if (s->is_instance()) {
+                const AnimatedTransform *at = s->animated_to_world();    // accessor added by the reference-side patch
+                dtof_instance in{};
+                in.first_mesh = (uint32_t) meshes.size();
+                in.animated = 1;
+                in.t0 = at->get_min_time(), in.t1 = at->get_max_time();
+                m34(at->eval(in.t0), in.m0);                             // Instance::embree_geometry, instance.cpp:295-310
+                m34(at->eval(in.t1), in.m1);
+                Collector c;                                             // ShapeGroup::traverse lists the members
+                ((Shape *) s->get_shapegroup())->traverse(&c);
+                for (auto &o : c.objects)
+                    add_shape((const Shape *) o.second, meshes, bufs, bsdfs);
+                in.n_meshes = (uint32_t) meshes.size() - in.first_mesh;
+                instances.push_back(in);
+            }
+        for (auto &e : scene->emitters()) {                              // order = Scene::m_emitters (scene.cpp:40-64)
+            dtof_emitter d{};
+            SurfaceInteraction3f si = dr::zeros<SurfaceInteraction3f>();
+            si.wi = ScalarVector3f(0, 0, 1);
+            Collector c;
+            e->traverse(&c);
+            if (e->class_()->name() == "PointLight") {
+                d.kind = DTOF_EMITTER_POINT;
+                const ScalarPoint3f &p = *c.param<ScalarPoint3f>("position");
+                d.position[0] = p.x(), d.position[1] = p.y(), d.position[2] = p.z();
+                Spectrum I = ((const Texture<Float, Spectrum> *) c.objects[0].second)->eval(si);
+                d.value[0] = I[0], d.value[1] = I[1], d.value[2] = I[2];
+            } else if (e->class_()->name() == "AreaLight") {
+                d.kind = DTOF_EMITTER_AREA;
+                for (auto &mo : mesh_of)
+                    if (mo.first->emitter() == e.get()) {
+                        d.mesh = mo.second;
+                        meshes[mo.second].emitter = (int32_t) emitters.size();
+                    }
+                Spectrum L = e->eval(si);
+                d.value[0] = L[0], d.value[1] = L[1], d.value[2] = L[2];
+            } else {
+                Throw("emitter \"%s\" is outside the accelerated path (point | area)", e->class_()->name());
+            }
+            emitters.push_back(d);
+        }
+        for (size_t i = 0; i < meshes.size(); ++i) {
+            meshes[i].n_vertices = (uint32_t) bufs[i].pos.size() / 3;
+            meshes[i].n_faces = (uint32_t) bufs[i].idx.size() / 3;
+            meshes[i].positions = bufs[i].pos.data();
+            meshes[i].normals = bufs[i].nrm.empty() ? nullptr : bufs[i].nrm.data();
+            meshes[i].texcoords = bufs[i].uv.empty() ? nullptr : bufs[i].uv.data();
+            meshes[i].faces = bufs[i].idx.data();
+        }
+        dtof_scene_desc d{};
+        d.n_meshes = (uint32_t) meshes.size(), d.meshes = meshes.data();
+        d.n_instances = (uint32_t) instances.size(), d.instances = instances.data();
+        d.n_bsdfs = (uint32_t) bsdfs.size(), d.bsdfs = bsdfs.data();
+        d.n_emitters = (uint32_t) emitters.size(), d.emitters = emitters.data();
+        // camera: PerspectiveCamera (perspective.cpp:172-198); sample_to_camera is exposed through traverse()
+        Collector c;
+        const_cast<Sensor *>(sensor)->traverse(&c);
+        m34(*c.param<ScalarTransform4f>("to_world"), d.camera.to_world);
+        const Film *film = sensor->film();
+        ScalarFloat x_fov = *c.param<ScalarFloat>("x_fov"), nearc = *c.param<ScalarFloat>("near_clip"), farc = *c.param<ScalarFloat>("far_clip");
+        ScalarTransform4f s2c = perspective_projection(film->size(), film->crop_size(), film->crop_offset(), x_fov, nearc, farc).inverse();
+        for (int r = 0; r < 4; ++r)
+            for (int k = 0; k < 4; ++k)
+                d.camera.sample_to_camera[4 * r + k] = s2c.matrix(r, k);
+        d.camera.near_clip = nearc, d.camera.far_clip = farc;
+        d.camera.shutter_open = sensor->shutter_open(), d.camera.shutter_open_time = sensor->shutter_open_time();
+        d.film.width = film->crop_size().x(), d.film.height = film->crop_size().y();
+        d.film.crop_offset_x = film->crop_offset().x(), d.film.crop_offset_y = film->crop_offset().y();
+        const std::string rf = film->rfilter()->class_()->name();
+        d.film.rfilter = rf == "BoxFilter" ? DTOF_RFILTER_BOX : rf == "TentFilter" ? DTOF_RFILTER_TENT : DTOF_RFILTER_GAUSSIAN;
+        if (rf != "BoxFilter" && rf != "TentFilter" && rf != "GaussianFilter")
+            Throw("reconstruction filter \"%s\" is outside the accelerated path (box | tent | gaussian)", rf);
+        d.film.rfilter_radius = film->rfilter()->radius();
+        d.film.gaussian_stddev = d.film.rfilter_radius / 4.f;            // gaussian.cpp:50-53: radius = 4 * stddev
+        if (dtof_upload_scene(m_ctx, &d) != DTOF_OK)
+            Throw("dtof_upload_scene: %s", dtof_last_error(m_ctx));
+    }
+
+    dtof_params m_p;
+    dtof_ctx *m_ctx = nullptr;
+    const Scene *m_uploaded = nullptr;
+    int m_device = 0;
+};
+
+MI_IMPLEMENT_CLASS_VARIANT(DopplerToFPathB200, MonteCarloIntegrator)
+MI_EXPORT_PLUGIN(DopplerToFPathB200, "Doppler ToF path tracer (B200 CUDA library behind the dtof C ABI)")
+NAMESPACE_END(mitsuba)

@@ -29,7 +29,7 @@ namespace {
 
 constexpr int kBlock = 256;
 #ifndef DTOF_MIN_CTAS
-#define DTOF_MIN_CTAS 2
+#define DTOF_MIN_CTAS 3
 #endif
 constexpr unsigned long long kUnit = 256;       // lanes per work unit fetched by one warp (8 warp iterations)
 constexpr size_t kSmemSceneLimit = 96 * 1024;   // traversal data up to this size is staged in shared memory

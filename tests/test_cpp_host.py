@@ -1,0 +1,120 @@
+"""The C++ host (host/: XML reader, property surfaces, flattening; what a Mitsuba-side plugin / the dtof_render CLI
+uses) and the Python mirror must hand IDENTICAL scene descriptions to the C ABI. CPU only: `dtof_render --dump-desc`
+stops after flattening. The GPU test at the bottom renders through the CLI and compares with the Python path."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import golden_util as gu
+import mitsuba3dopplertof_b200 as dt
+from mitsuba3dopplertof_b200 import _abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "host", "dtof_render")
+
+
+@pytest.fixture(scope="module")
+def cli():
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "host")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return CLI
+
+
+def _serialize_python(flat) -> bytes:
+    out = [b"DTOFDESC1\n", np.uint32(flat.desc.n_meshes).tobytes()]
+    for i in range(flat.desc.n_meshes):
+        m = flat.meshes[i]
+        nv, nf = m.n_vertices, m.n_faces
+        out.append(np.array([nv, nf, bool(m.normals), bool(m.texcoords), m.bsdf, m.emitter & 0xFFFFFFFF, m.flip_normals, m.kind],
+                            np.uint32).tobytes())
+        out.append(np.array(list(m.rect_to_world), np.float32).tobytes())
+        out.append(np.ctypeslib.as_array(m.positions, (nv * 3,)).tobytes())
+        if m.normals:
+            out.append(np.ctypeslib.as_array(m.normals, (nv * 3,)).tobytes())
+        if m.texcoords:
+            out.append(np.ctypeslib.as_array(m.texcoords, (nv * 2,)).tobytes())
+        out.append(np.ctypeslib.as_array(m.faces, (nf * 3,)).tobytes())
+    for n, arr, typ in ((flat.desc.n_instances, flat.instances, _abi.Instance), (flat.desc.n_bsdfs, flat.bsdfs, _abi.Bsdf),
+                        (flat.desc.n_emitters, flat.emitters, _abi.Emitter)):
+        out.append(np.uint32(n).tobytes())
+        out.append(C.string_at(C.addressof(arr), n * C.sizeof(typ)))
+    out.append(bytes(flat.desc.camera))
+    out.append(bytes(flat.desc.film))
+    return b"".join(out)
+
+
+CASES = [
+    ("c1_example.xml", {}),
+    ("c1_example.xml", {"resx": 128, "resy": 96, "spp": 64, "tsm": "stratified", "wave": "triangular"}),
+    ("c2_arealight.xml", {"resx": 512, "resy": 512}),
+    ("c2b_two_emitters.xml", {}),
+    ("c3_rotor.xml", {"pcn": 4}),
+    ("c4_domino.xml", {"w_g": 150}),
+    ("c5_slabroom.xml", {"tcn": 3, "pcn": 6}),
+]
+
+
+@pytest.mark.parametrize("scene,params", CASES)
+def test_cpp_host_flattens_like_python_host(cli, tmp_path, scene, params):
+    path = os.path.join(gu.SCENES, scene)
+    dump = str(tmp_path / "desc.bin")
+    args = [cli, "--dump-desc", dump] + [f"-D{k}={v}" for k, v in params.items()] + [path]
+    r = subprocess.run(args, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = open(dump, "rb").read()
+    want = _serialize_python(dt.load_file(path, **params).flatten())
+    assert len(got) == len(want)
+    if got != want:   # tolerate last-ulp differences of double-precision library routines, nothing else
+        a, b = np.frombuffer(got[10:], np.uint8), np.frombuffer(want[10:], np.uint8)
+        n = (len(a) // 4) * 4
+        a, b = a[:n].view(np.uint32), b[:n].view(np.uint32)
+        diff = np.nonzero(a != b)[0]
+        fa, fb = a.view(np.float32)[diff], b.view(np.float32)[diff]
+        assert np.all(np.abs(fa - fb) <= 2e-7 * np.maximum(np.abs(fb), 1e-30)), f"{len(diff)} words differ"
+        assert len(diff) <= 8, f"{len(diff)} words differ between the C++ and the Python host"
+
+
+def test_cpp_host_integrator_property_surface(cli, tmp_path):
+    """Same names / defaults / errors as the reference constructors (dopplertofpath.cpp:19-57, integrator.cpp:54-100)."""
+    base = open(os.path.join(gu.SCENES, "c1_example.xml")).read()
+
+    def run(xml, *extra):
+        p = tmp_path / "s.xml"
+        p.write_text(xml)
+        return subprocess.run([cli, "--dump-desc", str(tmp_path / "d.bin"), *extra, str(p)], capture_output=True, text=True)
+    assert run(base).returncode == 0
+    bad = base.replace('<float name="w_g" value="$w_g" />', '<float name="w_g" value="$w_g" /><float name="bogus" value="1" />')
+    r = run(bad)
+    assert r.returncode == 1 and "unreferenced property" in r.stderr
+    r = run(base, "-Dwave=sawtooth")
+    assert r.returncode == 1 and "wave_function_type" in r.stderr
+    r = run(base, "-Dtsm=periodic")
+    assert r.returncode == 1 and "time_sampling_method" in r.stderr
+    r = run(base, "-Dnot_a_param=1")
+    assert r.returncode == 1 and "Unused parameter" in r.stderr
+    # use_stratified_sampling_for_each_interval belongs to the integrator, not the sampler (SURVEY.md finding 7)
+    bad = base.replace('<integer name="time_correlate_number"', '<boolean name="use_stratified_sampling_for_each_interval" value="true" />'
+                       '<integer name="time_correlate_number"')
+    r = run(bad)
+    assert r.returncode == 1 and "unreferenced property" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cli_render_matches_python_path(cli, tmp_path):
+    from mitsuba3dopplertof_b200 import runtime
+    path = os.path.join(gu.SCENES, "c2_arealight.xml")
+    out = str(tmp_path / "out.npy")
+    r = subprocess.run([cli, "-Dresx=64", "-Dresy=48", "-Dspp=64", "-s", "3", "--raw", "-o", out, path], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "Rendering finished." in r.stdout
+    got = np.load(out)
+    scene = dt.load_file(path, resx=64, resy=48, spp=64)
+    ctx = runtime.Context(0)
+    flat = ctx.upload(scene)
+    want = ctx.render(flat, scene.integrator.params(scene.sensor.sampler, seed=3), develop=False)
+    assert got.shape == want.shape == (48, 64, 4)
+    # same inputs, same kernel: only the order of the float atomics differs
+    assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
