@@ -29,11 +29,11 @@ namespace {
 
 constexpr int kBlock = 256;
 #ifndef DTOF_MIN_CTAS
-#define DTOF_MIN_CTAS 3
+#define DTOF_MIN_CTAS 4
 #endif
 constexpr unsigned long long kUnit = 256;       // lanes per work unit fetched by one warp (8 warp iterations)
 constexpr size_t kSmemSceneLimit = 96 * 1024;   // traversal data up to this size is staged in shared memory
-constexpr uint32_t kFlatMaxTris = 64;           // scenes up to this many triangles use the flat coherent walk
+constexpr uint32_t kFlatMaxTris = 0;            // flat coherent walk: never automatic (DTOF_MODE=2 only), see r01_tuning.md
 
 struct RenderArgs {
     DeviceScene scene;
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(kBlock, DTOF_MIN_CTAS) render_kernel(const __g
             const uint32_t pixel = idx / A.spp_per_pass;
             const uint32_t py = pixel / A.film.width, px = pixel - py * A.film.width;
             LaneSampler smp;
-            smp.seed(A.p, idx, A.spp_per_pass);
+            smp.seed(A.p, idx);
 
             for (uint32_t pass = 0; pass < (RECORD ? 1u : A.n_passes); ++pass) {
                 // render_sample(), Doppler branch (src/render/integrator.cpp:476-542)
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(kBlock, DTOF_MIN_CTAS) render_kernel(const __g
                 float ax = fmaf(spx, scale_x, off_x), ay = fmaf(spy, scale_y, off_y);
                 float time = A.cam.shutter_open;
                 if (A.cam.shutter_open_time > 0.f)
-                    time += smp.next_time(A.p, A.spp_per_pass) * A.cam.shutter_open_time;
+                    time += smp.next_time(A.p, idx, A.spp_per_pass, pass) * A.cam.shutter_open_time;
                 V3 o, d;
                 float maxt;
                 camera_ray(A.cam, ax, ay, o, d, maxt);
@@ -155,7 +155,6 @@ __global__ void __launch_bounds__(kBlock, DTOF_MIN_CTAS) render_kernel(const __g
                     else if (lane_on)
                         splat_generic(A.film, spx, spy, rgb);
                 }
-                smp.advance();
             }
         }
     }
@@ -412,7 +411,7 @@ dtof_status launch_render(dtof_ctx *ctx, const dtof_params *p, float *d_rgbw, cu
     int mode = MODE_BVH_GLOBAL;
     if (bvh_bytes <= kSmemSceneLimit && bvh_bytes + 1024 <= ctx->smem_optin)
         mode = MODE_BVH_SMEM;
-    if (ctx->n_tris_total <= kFlatMaxTris && flat_bytes + 1024 <= ctx->smem_optin)
+    if (ctx->n_tris_total <= kFlatMaxTris && ctx->n_tris_total > 0 && flat_bytes + 1024 <= ctx->smem_optin)
         mode = MODE_FLAT_SMEM;
     int want = ctx->forced_mode;
     if (const char *e = getenv("DTOF_MODE"))

@@ -8,6 +8,7 @@
 #include <atomic>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 
@@ -66,7 +67,7 @@ inline void set_child(BvhNode &n, int which, const Box &b, int32_t ref) {
 }
 
 constexpr int kBins = 16;
-constexpr uint32_t kMaxLeaf = 4;
+static uint32_t kMaxLeaf = 4;   // set per scene in build_scene_bvh; DTOF_MAX_LEAF overrides (tuning experiments)
 constexpr int kSahDepthLimit = 40;   // beyond this depth fall back to median splits (bounds the traversal stack)
 
 // Generic top-down builder over `refs[lo,hi)`. `make_leaf(lo, hi)` returns the leaf reference.
@@ -277,6 +278,15 @@ int32_t build_group_parallel(const GroupInput &G, std::vector<Ref> &refs, BuiltS
 } // namespace
 
 void build_scene_bvh(const std::vector<GroupInput> &groups, BuiltScene &out) {
+    // Leaf size, measured on B200 (profiles/r01_tuning.md): scenes whose traversal data sits in shared memory are
+    // instruction bound and want few triangle tests per leaf (2); multi-million-triangle scenes are L2/HBM bound and
+    // want fewer, fatter nodes (4).
+    size_t total_tris = 0;
+    for (auto &g : groups)
+        total_tris += g.tris.size();
+    kMaxLeaf = total_tris <= 4096 ? 2 : 4;
+    if (const char *e = getenv("DTOF_MAX_LEAF"))
+        kMaxLeaf = (uint32_t) std::min(15, std::max(1, atoi(e)));
     out.nodes.clear();
     out.tris.clear();
     out.inst_root.assign(groups.size(), 0);

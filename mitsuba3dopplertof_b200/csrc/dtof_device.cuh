@@ -168,31 +168,19 @@ DTOF_DEV uint32_t permute_kensler(uint32_t index, uint32_t sample_count, uint32_
     return (index + seed) % sample_count;
 }
 
-// CorrelatedSampler (JIT branch). The time stream is consumed once per pass, so only its state is kept.
+// CorrelatedSampler (JIT branch). Only the two streams the bounce loop draws from live in registers; the time
+// stream (one draw per pass) and the per-pixel permutation seed are re-derived from (idx, pass) when a pass starts.
 struct LaneSampler {
-    Pcg rng, rng_path, rng_time;
-    uint32_t perm_seed, dim, pass, idx_mod_spp;
+    Pcg rng, rng_path;
     uint32_t draws;
 
-    DTOF_DEV void seed(const dtof_params &p, uint32_t idx, uint32_t spp_pp) {
+    DTOF_DEV void seed(const dtof_params &p, uint32_t idx) {
         uint32_t S = p.base_seed + p.seed, a, b;
         tea32(S, idx, a, b);
         rng.seed(a, b);
-        tea32(S + 1, idx / p.time_correlate_number, a, b);
-        rng_time.seed(a, b);
         tea32(S + 2, idx / p.path_correlate_number, a, b);
         rng_path.seed(a, b);
-        uint32_t sequence_idx = spp_pp * (idx / spp_pp);
-        tea32(p.base_seed, sequence_idx + p.seed, a, b);
-        perm_seed = a;
-        dim = 0;
-        pass = 0;
-        idx_mod_spp = spp_pp > 1 ? idx % spp_pp : 0;
         draws = 0;
-    }
-    DTOF_DEV void advance() {
-        dim = 0;
-        pass++;
     }
     // next_1d_correlate: both streams step, one output is formed
     DTOF_DEV float next_1d(bool correlate) {
@@ -206,27 +194,36 @@ struct LaneSampler {
         rng.step();
         draws++;
     }
-    DTOF_DEV float next_time(const dtof_params &p, uint32_t spp_pp) {
+    // next_1d_time of pass `pass` (src/samplers/correlated.cpp:92-153); dimension_index restarts at 0 every pass
+    DTOF_DEV float next_time(const dtof_params &p, uint32_t idx, uint32_t spp_pp, uint32_t pass) {
         uint32_t strategy = p.time_sampling_method, tcn = p.time_correlate_number;
         if (strategy == DTOF_TIME_UNIFORM) {
             draws++;
             return rng.next_f32();
         }
-        uint32_t si = pass * spp_pp + idx_mod_spp;
+        uint32_t si = pass * spp_pp + (spp_pp > 1 ? idx % spp_pp : 0);
         float r;
         if (strategy == DTOF_TIME_STRATIFIED) {
             r = rng.next_f32();
             draws++;
-        } else {
+        } else {   // the time stream advances exactly once per pass in the antithetic modes
+            uint32_t a, b;
+            tea32(p.base_seed + p.seed + 1, idx / tcn, a, b);
+            Pcg rng_time;
+            rng_time.seed(a, b);
+#pragma unroll 1
+            for (uint32_t k = 0; k < pass; ++k)
+                rng_time.step();
             r = rng_time.next_f32();
         }
         if (p.use_stratified_sampling_for_each_interval) {
             uint32_t n_stratum = p.sample_count / tcn;
             uint32_t pp;
             if (strategy == DTOF_TIME_STRATIFIED) {
-                uint32_t p1 = permute_kensler(si / tcn, n_stratum, perm_seed + dim);
-                uint32_t p2 = permute_kensler(si / tcn, n_stratum, perm_seed + dim + 1);
-                dim += 2;
+                uint32_t perm_seed, unused;
+                tea32(p.base_seed, spp_pp * (idx / spp_pp) + p.seed, perm_seed, unused);
+                uint32_t p1 = permute_kensler(si / tcn, n_stratum, perm_seed);
+                uint32_t p2 = permute_kensler(si / tcn, n_stratum, perm_seed + 1);
                 pp = (si % tcn != 0) ? p1 : p2;
             } else {
                 pp = si / tcn;
@@ -305,7 +302,7 @@ DTOF_DEV float waveform_full(float t_, uint32_t type) {
 struct Modulation {
     float w_g, w_d, k_phi, phase, half_g1, g1, g0, w_gd;
     uint32_t type, lowpass;
-    DTOF_DEV float eval(float ray_time, float path_length) const {
+    __device__ __noinline__ float eval(float ray_time, float path_length) const {
         float phi = k_phi * path_length;
         if (lowpass) {
             float t = w_d * ray_time + phase + phi;
@@ -436,9 +433,9 @@ constexpr int kDone = 0x7fffffff;
 // "instance leaf": the ray is moved into the instance's space, a sentinel marks the way back.
 // Loop shape after Aila & Laine: a lane stays in the inner-node loop (popping included) until it holds a leaf.
 // `N`, `T`, `I` are the node / triangle / instance arrays (global memory, or their shared-memory copies).
-template <bool ANY, bool STATS>
+template <bool STATS>
 DTOF_DEV bool trace_bvh(const float4 *__restrict__ N, const float4 *__restrict__ T, const float4 *__restrict__ I,
-                        int32_t root, V3 o, V3 d, float tmax, float time, Hit &hit, Counters &st) {
+                        int32_t root, const bool ANY, V3 o, V3 d, float tmax, float time, Hit &hit, Counters &st) {
     int stack[kStackSize];
     int sp = 0;
     int node = root;
@@ -535,15 +532,17 @@ DTOF_DEV bool trace_bvh(const float4 *__restrict__ N, const float4 *__restrict__
     return found;
 }
 
-// Flat, warp-coherent traversal for tiny scenes: every lane walks ALL triangles of every instance in scene order
-// (uniform control flow, shared-memory reads are broadcasts, no stack). An animated instance is skipped when no lane
-// of the warp touches its padded world bounds. With a few dozen triangles this beats the per-lane BVH walk, whose
-// SIMD efficiency on incoherent bounce rays is ~1/3 (profiles/r01_render_c2_v1_ncu_summary.json).
+// Flat, warp-coherent traversal: every lane walks ALL triangles of every instance in scene order (uniform control
+// flow, shared-memory reads are broadcasts, no stack). An animated instance is skipped when no lane of the warp
+// touches its padded world bounds. Kept as a measured alternative (DTOF_MODE=2): since the kernel runs at 4 CTAs/SM
+// with leaves of <= 2 triangles the per-lane BVH walk is faster even for 22-36 triangle scenes
+// (profiles/r01_tuning.md), so it is never selected automatically.
 // `TF` = triangles in scene (gid) order, `B` = instance world boxes. Must be called by all 32 lanes of the warp;
 // `lane_active` masks lanes without a ray.
-template <bool ANY, bool STATS>
+template <bool STATS>
 DTOF_DEV bool trace_flat(const float4 *__restrict__ TF, const float4 *__restrict__ I, const float4 *__restrict__ B,
-                         uint32_t n_insts, V3 o, V3 d, float tmax, float time, bool lane_active, Hit &hit, Counters &st) {
+                         uint32_t n_insts, const bool ANY, V3 o, V3 d, float tmax, float time, bool lane_active, Hit &hit,
+                         Counters &st) {
     float best = tmax;
     bool found = false;
     const V3 wid = v3(1.f / d.x, 1.f / d.y, 1.f / d.z);
