@@ -129,6 +129,7 @@ def cpu_oracle_throughput(scene, seed, target_seconds=12.0):
     t0 = time.perf_counter()
     osc.render(p, cores)
     dt1 = time.perf_counter() - t0
+    cpu_oracle_throughput.last_seconds = dt1
     return px * spp2 / dt1 / 1e6, cores, f"{flat.width}x{flat.height} @ {spp2} spp of the same scene ({dt1:.1f} s)"
 
 
@@ -178,7 +179,7 @@ def run_reference_arm(args):
     fn, params, _ = WORKLOADS[args.workload]
     p = dict({"resx": 256, "resy": 256, "spp": 1024}, **params)
     px = int(p["resx"]) * int(p["resy"])
-    kind, vals = "reference", []
+    kind, vals, secs = "reference", [], []
     spp = 8
     try:
         probe = reference_binary_throughput(args.workload, 4, cores)
@@ -196,13 +197,17 @@ def run_reference_arm(args):
             v, cores, sample = cpu_oracle_throughput(scene, 0, target_seconds=10.0)
             if i >= min(args.warmup, 1):
                 vals.append(v)
+                secs.append(cpu_oracle_throughput.last_seconds)
     value = float(np.mean(vals))
-    ms = px * spp / (value * 1e6) * 1e3 if kind == "reference" else None
+    ms = px * spp / (value * 1e6) * 1e3 if kind == "reference" else float(np.mean(secs)) * 1e3
+    note = ("reference binary (scalar_rgb + Embree; llvm_rgb cannot load libLLVM in this image)" if kind == "reference" else
+            "oracle port: multithreaded C++ restatement of the reference algorithm (JIT stream semantics, own BVH); the "
+            "reference itself only builds through its CMake tree, which is not available on the bench box (DESIGN.md 2)")
     print(json.dumps({
         "impl": "reference", "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "note": "CPU arm: llvm_rgb cannot run (no libLLVM in the image); scalar_rgb timed"},
+        "config": {"workload": desc, "note": note, "step": "one bounded sample of the workload (see cpu_baseline.sample)"},
         "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))

@@ -133,8 +133,10 @@ struct DopplerToFPathIntegrator {
     int32_t max_depth = -1, rr_depth = 5;
     bool hide_emitters = false;
     double timeout = -1.0;
+    uint32_t kind = DTOF_INTEGRATOR_DOPPLERTOFPATH;   // or DTOF_INTEGRATOR_VELOCITY (src/integrators/velocity.cpp)
     // props: name -> textual value (already $-substituted); throws on unknown names / bad enum strings
-    explicit DopplerToFPathIntegrator(const std::map<std::string, std::string> &props = {});
+    explicit DopplerToFPathIntegrator(const std::map<std::string, std::string> &props = {},
+                                      uint32_t kind = DTOF_INTEGRATOR_DOPPLERTOFPATH);
     dtof_params params(const CorrelatedSampler &s, uint32_t seed = 0, uint32_t spp = 0) const;
 };
 

@@ -391,7 +391,14 @@ dtof_camera PerspectiveSensor::abi() const {
 }
 
 // ================================================================================================ integrator
-DopplerToFPathIntegrator::DopplerToFPathIntegrator(const std::map<std::string, std::string> &props) {
+DopplerToFPathIntegrator::DopplerToFPathIntegrator(const std::map<std::string, std::string> &props, uint32_t kind_) : kind(kind_) {
+    static const std::set<std::string> velocity_known = {
+        "time", "max_depth", "rr_depth", "hide_emitters", "timeout", "block_size", "samples_per_pass", "time_sampling_method",
+        "antithetic_shift", "use_stratified_sampling_for_each_interval", "path_correlation_depth", "is_doppler_integrator" };
+    if (kind == DTOF_INTEGRATOR_VELOCITY)
+        for (auto &kv : props)
+            if (!velocity_known.count(kv.first))
+                throw Error("velocity: unreferenced property \"" + kv.first + "\"");
     static const std::set<std::string> known = {
         "time", "w_g", "g_1", "g_0", "w_s", "sensor_phase_offset", "hetero_offset", "hetero_frequency", "wave_function_type",
         "low_frequency_component_only", "max_depth", "rr_depth", "hide_emitters", "timeout", "is_doppler_integrator",
@@ -467,6 +474,7 @@ dtof_params DopplerToFPathIntegrator::params(const CorrelatedSampler &s, uint32_
     p.time_correlate_number = s.time_correlate_number;
     p.path_correlate_number = s.path_correlate_number;
     p.seed = seed;
+    p.integrator = kind;
     if (time_sampling_method == DTOF_TIME_ANTITHETIC_MIRROR && s.time_correlate_number != 2)
         throw Error("antithetic_mirror requires time_correlate_number == 2");   // correlated.cpp:141-142
     if (s.time_correlate_number < 1 || s.path_correlate_number < 1)
@@ -1019,12 +1027,12 @@ struct Loader {
                     defaults[k] = sub(*node->attr("value"));
             } else if (node->tag == "integrator") {
                 std::string typ = attr(*node, "type");
-                if (typ != "dopplertofpath")
-                    throw Error("integrator '" + typ + "' is outside the hot-path scope (dopplertofpath)");
+                if (typ != "dopplertofpath" && typ != "velocity")
+                    throw Error("integrator '" + typ + "' is outside the hot-path scope (dopplertofpath|velocity)");
                 std::map<std::string, std::string> ip;
                 for (auto &kv : props(*node))
                     ip[kv.first] = kv.second.value;
-                sc.integrator = DopplerToFPathIntegrator(ip);
+                sc.integrator = DopplerToFPathIntegrator(ip, typ == "velocity" ? DTOF_INTEGRATOR_VELOCITY : DTOF_INTEGRATOR_DOPPLERTOFPATH);
                 have_integrator = true;
             } else if (node->tag == "sensor") {
                 sc.sensor = sensor(*node);

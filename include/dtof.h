@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define DTOF_ABI_VERSION 1
+#define DTOF_ABI_VERSION 2
 
 typedef struct dtof_ctx dtof_ctx;
 
@@ -67,6 +67,12 @@ typedef enum dtof_waveform {
     DTOF_WAVE_TRIANGULAR = 2,
     DTOF_WAVE_TRAPEZOIDAL = 3
 } dtof_waveform;
+
+/* Which SamplingIntegrator::sample() the lanes run. VELOCITY = the reference's ground-truth radial-velocity
+ * integrator (src/integrators/velocity.cpp:113-127): two closest-hit queries of the camera ray at t = 0 and t = `time`,
+ * value (t2 - t1) / time in all three channels; it is NOT a Doppler integrator, so render_sample takes the stock
+ * branch (src/render/integrator.cpp:409-472): jitter and time come from the sampler's independent stream only. */
+typedef enum dtof_integrator_kind { DTOF_INTEGRATOR_DOPPLERTOFPATH = 0, DTOF_INTEGRATOR_VELOCITY = 1 } dtof_integrator_kind;
 
 typedef enum dtof_rfilter { DTOF_RFILTER_BOX = 0, DTOF_RFILTER_TENT = 1, DTOF_RFILTER_GAUSSIAN = 2 } dtof_rfilter;
 typedef enum dtof_shape_kind { DTOF_SHAPE_MESH = 0, DTOF_SHAPE_RECTANGLE = 1 } dtof_shape_kind;
@@ -189,6 +195,8 @@ typedef struct dtof_params {
      *   interleaved tile sharding              : shard_block = spp_per_pass * pixels_per_tile */
     uint64_t shard_block;
     uint32_t shard_count, shard_index;
+    uint32_t integrator;              /* dtof_integrator_kind; 0 = dopplertofpath */
+    uint32_t reserved;                /* must be 0 */
 } dtof_params;
 
 /* Per-lane record returned by dtof_trace_samples (and by the CPU oracle): everything the

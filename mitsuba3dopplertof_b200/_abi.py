@@ -8,7 +8,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # enums (include/dtof.h)
 TIME_UNIFORM, TIME_STRATIFIED, TIME_ANTITHETIC, TIME_ANTITHETIC_MIRROR = range(4)
@@ -17,6 +17,7 @@ RFILTER_BOX, RFILTER_TENT, RFILTER_GAUSSIAN = range(3)
 SHAPE_MESH, SHAPE_RECTANGLE = range(2)
 BSDF_DIFFUSE, BSDF_NULL_BLACK = range(2)
 EMITTER_POINT, EMITTER_AREA = range(2)
+INTEGRATOR_DOPPLERTOFPATH, INTEGRATOR_VELOCITY = range(2)
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED, ERR_STATE = range(6)
 
@@ -88,6 +89,7 @@ class Params(C.Structure):
         ("seed", C.c_uint32),
         ("lane_begin", C.c_uint64), ("lane_end", C.c_uint64),
         ("shard_block", C.c_uint64), ("shard_count", C.c_uint32), ("shard_index", C.c_uint32),
+        ("integrator", C.c_uint32), ("reserved", C.c_uint32),
     ]
 
 

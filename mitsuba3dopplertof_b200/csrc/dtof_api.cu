@@ -57,7 +57,7 @@ struct RenderArgs {
     uint32_t nodes_bytes, tris_bytes, insts_bytes, boxes_bytes;
 };
 
-template <int MODE, bool STATS, bool RECORD>
+template <int MODE, bool STATS, bool RECORD, bool VELOCITY>
 __global__ void __launch_bounds__(kBlock, DTOF_MIN_CTAS) render_kernel(const __grid_constant__ RenderArgs A) {
     extern __shared__ float4 smem[];
     TravPtrs TP;
@@ -109,21 +109,35 @@ __global__ void __launch_bounds__(kBlock, DTOF_MIN_CTAS) render_kernel(const __g
             smp.seed(A.p, idx);
 
             for (uint32_t pass = 0; pass < (RECORD ? 1u : A.n_passes); ++pass) {
-                // render_sample(), Doppler branch (src/render/integrator.cpp:476-542)
+                // render_sample(): Doppler branch (src/render/integrator.cpp:476-542), or the stock branch (:409-472)
+                // for the velocity integrator -- jitter and time from the independent stream only
                 const bool correlate_pixel = A.p.path_correlation_depth > 0;
                 const float scale_x = 1.f / (float) A.film.width, scale_y = 1.f / (float) A.film.height;
                 const float off_x = -(float) A.film.crop_x * scale_x, off_y = -(float) A.film.crop_y * scale_y;
                 const float posx = (float) (px + A.film.crop_x), posy = (float) (py + A.film.crop_y);
-                float jx = smp.next_1d(correlate_pixel), jy = smp.next_1d(correlate_pixel);
+                float jx, jy;
+                if (VELOCITY) {
+                    jx = smp.rng.next_f32(), jy = smp.rng.next_f32();
+                    smp.draws += 2;
+                } else {
+                    jx = smp.next_1d(correlate_pixel), jy = smp.next_1d(correlate_pixel);
+                }
                 float spx = posx + jx, spy = posy + jy;
                 float ax = fmaf(spx, scale_x, off_x), ay = fmaf(spy, scale_y, off_y);
                 float time = A.cam.shutter_open;
-                if (A.cam.shutter_open_time > 0.f)
-                    time += smp.next_time(A.p, idx, A.spp_per_pass, pass) * A.cam.shutter_open_time;
+                if (A.cam.shutter_open_time > 0.f) {
+                    if (VELOCITY) {
+                        time += smp.rng.next_f32() * A.cam.shutter_open_time;
+                        smp.draws++;
+                    } else {
+                        time += smp.next_time(A.p, idx, A.spp_per_pass, pass) * A.cam.shutter_open_time;
+                    }
+                }
                 V3 o, d;
                 float maxt;
                 camera_ray(A.cam, ax, ay, o, d, maxt);
-                PathOut r = trace_path<MODE, STATS>(A.scene, TP, A.p, A.mod, smp, lane_on, o, d, maxt, time, st);
+                PathOut r = VELOCITY ? trace_velocity<MODE, STATS>(A.scene, TP, A.p, lane_on, o, d, maxt, st)
+                                     : trace_path<MODE, STATS>(A.scene, TP, A.p, A.mod, smp, lane_on, o, d, maxt, time, st);
                 V3 rgb = r.rgb;
                 if (A.film.rfilter == DTOF_RFILTER_BOX) {
                     spx = posx;
@@ -312,6 +326,8 @@ dtof_status check_params(dtof_ctx *ctx, const dtof_params *p) {
         return fail(ctx, DTOF_ERR_INVALID, "sample_count < time_correlate_number");
     if (!(p->time > 0.f))
         return fail(ctx, DTOF_ERR_INVALID, "time must be > 0");
+    if (p->integrator > DTOF_INTEGRATOR_VELOCITY || p->reserved != 0)
+        return fail(ctx, DTOF_ERR_INVALID, "unknown integrator kind %u", p->integrator);
     return DTOF_OK;
 }
 
@@ -331,14 +347,14 @@ Modulation make_modulation(const dtof_params &p) {
     return m;
 }
 
-template <int MODE, bool STATS, bool RECORD>
+template <int MODE, bool STATS, bool RECORD, bool VELOCITY>
 dtof_status launch_variant(dtof_ctx *ctx, RenderArgs &A, int grid, cudaStream_t stream) {
     size_t smem = 0;
     if (MODE == MODE_BVH_SMEM)
         smem = (size_t) A.nodes_bytes + A.tris_bytes + A.insts_bytes + A.boxes_bytes;
     else if (MODE == MODE_FLAT_SMEM)
         smem = (size_t) A.tris_bytes + A.insts_bytes + A.boxes_bytes;
-    auto k = render_kernel<MODE, STATS, RECORD>;
+    auto k = render_kernel<MODE, STATS, RECORD, VELOCITY>;
     if (smem)
         CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     k<<<grid, kBlock, smem, stream>>>(A);
@@ -349,10 +365,13 @@ dtof_status launch_variant(dtof_ctx *ctx, RenderArgs &A, int grid, cudaStream_t 
 
 template <int MODE>
 dtof_status launch_mode(dtof_ctx *ctx, RenderArgs &A, bool record, int grid, cudaStream_t stream) {
+    if (A.p.integrator == DTOF_INTEGRATOR_VELOCITY)   // counters are not instrumented for the velocity variant
+        return record ? launch_variant<MODE, false, true, true>(ctx, A, grid, stream)
+                      : launch_variant<MODE, false, false, true>(ctx, A, grid, stream);
     if (record)
-        return launch_variant<MODE, false, true>(ctx, A, grid, stream);
-    return ctx->stats_enabled ? launch_variant<MODE, true, false>(ctx, A, grid, stream)
-                              : launch_variant<MODE, false, false>(ctx, A, grid, stream);
+        return launch_variant<MODE, false, true, false>(ctx, A, grid, stream);
+    return ctx->stats_enabled ? launch_variant<MODE, true, false, false>(ctx, A, grid, stream)
+                              : launch_variant<MODE, false, false, false>(ctx, A, grid, stream);
 }
 
 dtof_status launch_render(dtof_ctx *ctx, const dtof_params *p, float *d_rgbw, cudaStream_t stream,

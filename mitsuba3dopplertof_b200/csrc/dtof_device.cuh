@@ -41,13 +41,53 @@ DTOF_DEV V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); 
 DTOF_DEV V3 operator-(V3 a) { return v3(-a.x, -a.y, -a.z); }
 DTOF_DEV V3 operator*(V3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
 DTOF_DEV V3 operator*(V3 a, V3 b) { return v3(a.x * b.x, a.y * b.y, a.z * b.z); }
+// ---- shading arithmetic precision ---------------------------------------------------------------------------------
+// Sampler, camera ray and the accepted-hit arithmetic of the triangle test are IEEE (they decide WHICH pixel / time /
+// triangle a sample sees and are compared bit for bit with the oracle). Everything after the hit -- surface frame,
+// emitter / BSDF sampling, MIS, modulation argument reduction, Russian roulette -- uses the SFU approximations below
+// (<= 2 ulp per operation), exactly the operations the reference's own CUDA variants emit (div/rcp/sqrt/rsqrt
+// `.approx.ftz`, ext/drjit/ext/drjit-core/src/cuda_eval.cpp:433-655). They are ~1e-7 relative per operation against
+// the 1e-4 per-sample tolerance, and shrink the kernel by a fifth (an IEEE division is ~10 SASS instructions plus a
+// slow-path call, an approximate one 1-4), which matters because the kernel is instruction-cache / issue bound
+// (profiles/r01_tuning.md: +37 %). -DDTOF_EXACT_MATH restores IEEE everywhere.
+#ifdef DTOF_EXACT_MATH
+DTOF_DEV float fdiv(float a, float b) { return a / b; }
+DTOF_DEV float frcp(float a) { return 1.f / a; }
+DTOF_DEV float fsqrt(float a) { return sqrtf(a); }
+DTOF_DEV float frsqrt(float a) { return 1.f / sqrtf(a); }
 DTOF_DEV V3 operator/(V3 a, float s) { return v3(a.x / s, a.y / s, a.z / s); }
+#else
+DTOF_DEV float fdiv(float a, float b) {
+    float r;
+    asm("div.full.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+DTOF_DEV float frcp(float a) {
+    float r;
+    asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(a));
+    return r;
+}
+DTOF_DEV float fsqrt(float a) {
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(a));
+    return r;
+}
+DTOF_DEV float frsqrt(float a) {
+    float r;
+    asm("rsqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(a));
+    return r;
+}
+DTOF_DEV V3 operator/(V3 a, float s) {
+    float r = frcp(s);
+    return v3(a.x * r, a.y * r, a.z * r);
+}
+#endif
 DTOF_DEV V3 fma3(V3 a, float s, V3 b) { return v3(fmaf(a.x, s, b.x), fmaf(a.y, s, b.y), fmaf(a.z, s, b.z)); }
 DTOF_DEV float dot3(V3 a, V3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
 DTOF_DEV V3 cross3(V3 a, V3 b) {
     return v3(fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x)));
 }
-DTOF_DEV float rsqrt_ieee(float x) { return 1.f / sqrtf(x); }
+DTOF_DEV float rsqrt_ieee(float x) { return frsqrt(x); }   // IEEE only with DTOF_EXACT_MATH
 DTOF_DEV V3 normalize3(V3 a) { return a * rsqrt_ieee(dot3(a, a)); }
 DTOF_DEV float mulsign(float v, float s) {
     return __uint_as_float(__float_as_uint(v) ^ (__float_as_uint(s) & 0x80000000u));
@@ -77,7 +117,7 @@ DTOF_DEV M34 inverse_m34(const M34 &M) {
     float c00 = fmaf(a[5], a[10], -(a[6] * a[9])), c01 = fmaf(a[6], a[8], -(a[4] * a[10])),
           c02 = fmaf(a[4], a[9], -(a[5] * a[8]));
     float det = fmaf(a[0], c00, fmaf(a[1], c01, a[2] * c02));
-    float id = 1.f / det;
+    float id = frcp(det);
     M34 r;
     r.m[0] = c00 * id;
     r.m[1] = fmaf(a[2], a[9], -(a[1] * a[10])) * id;
@@ -271,7 +311,7 @@ DTOF_DEV float dr_cos(float x) {
     dr_sincos(x, s, c);
     return c;
 }
-DTOF_DEV float dr_fmod(float x, float y) { return fmaf(-truncf(x / y), y, x); }
+DTOF_DEV float dr_fmod(float x, float y) { return fmaf(-truncf(fdiv(x, y)), y, x); }
 
 constexpr float kPi = 3.14159265358979323846f;
 constexpr float kTwoPi = 6.28318530717958647692f;
@@ -281,11 +321,11 @@ DTOF_DEV float waveform_lowpass(float t_, uint32_t type) {
     float t = dr_fmod(t_, kTwoPi);
     if (type == DTOF_WAVE_SINUSOIDAL)
         return dr_cos(t);
-    float a = t / kPi, b = 2.f - a, c = a < b ? a : b;
+    float a = t * kInvPi, b = 2.f - a, c = a < b ? a : b;
     if (type == DTOF_WAVE_RECTANGULAR)
         return 2.f - 4.f * c;
     if (type == DTOF_WAVE_TRIANGULAR)
-        return (4.f * c * c * c - 6.f * c * c + 1.f) * 2.f / 3.f;
+        return fdiv((4.f * c * c * c - 6.f * c * c + 1.f) * 2.f, 3.f);
     float r = 2.f - 4.f * c;
     return fminf(fmaxf(2.f * r, -2.f), 2.f);
 }
@@ -294,7 +334,7 @@ DTOF_DEV float waveform_full(float t_, uint32_t type) {
     if (type == DTOF_WAVE_RECTANGULAR)
         return fabsf(t - kPi) > 0.5f * kPi ? 1.f : -1.f;
     if (type == DTOF_WAVE_TRIANGULAR)
-        return t < kPi ? 1.f - 2.f * t / kPi : -3.f + 2.f * t / kPi;
+        return t < kPi ? 1.f - fdiv(2.f * t, kPi) : -3.f + fdiv(2.f * t, kPi);
     return dr_cos(t);   // sinusoidal, and trapezoidal falls through (waveform_utils.h:27-32)
 }
 
@@ -320,7 +360,7 @@ DTOF_DEV V3 square_to_cosine_hemisphere(float sx, float sy) {
     float x = fmaf(2.f, sx, -1.f), y = fmaf(2.f, sy, -1.f);
     bool is_zero = x == 0.f && y == 0.f, q13 = fabsf(x) < fabsf(y);
     float r = q13 ? y : x, rp = q13 ? x : y;
-    float phi = 0.25f * kPi * rp / r;
+    float phi = fdiv(0.25f * kPi * rp, r);
     if (q13)
         phi = 0.5f * kPi - phi;
     if (is_zero)
@@ -328,17 +368,17 @@ DTOF_DEV V3 square_to_cosine_hemisphere(float sx, float sy) {
     float s, c;
     dr_sincos(phi, s, c);
     float px = r * c, py = r * s;
-    float z = sqrtf(fmaxf(1.f - fmaf(py, py, px * px), 0.f));
+    float z = fsqrt(fmaxf(1.f - fmaf(py, py, px * px), 0.f));
     return v3(px, py, z);
 }
 DTOF_DEV void coordinate_system(V3 n, V3 &s, V3 &t) {
     float sign = copysignf(1.f, n.z);
-    float a = -1.f / (sign + n.z), b = n.x * n.y * a;
+    float a = -frcp(sign + n.z), b = n.x * n.y * a;
     s = v3(mulsign(n.x * n.x * a, n.z) + 1.f, mulsign(b, n.z), mulsign(-n.x, n.z));
     t = v3(b, fmaf(n.y, n.y * a, sign), -n.y);
 }
 DTOF_DEV void square_to_uniform_triangle(float sx, float sy, float &bx, float &by) {
-    float t = sqrtf(fmaxf(1.f - sx, 0.f));
+    float t = fsqrt(fmaxf(1.f - sx, 0.f));
     bx = 1.f - t;
     by = t * sy;
 }
@@ -402,7 +442,7 @@ DTOF_DEV bool tri_test(const float4 a, const float4 b, const float4 c, V3 ro, V3
 DTOF_DEV void load_inst_matrix(const float4 *ip, float time, bool clamp, M34 &M) {
     // AnimatedTransform::eval (clamped, transform.h:451-456) or Embree's unclamped fraction (default.h:225-231)
     float4 q6 = ip[6];
-    float f = (time - q6.x) / (q6.y - q6.x);
+    float f = fdiv(time - q6.x, q6.y - q6.x);
     if (clamp)
         f = fminf(fmaxf(f, 0.f), 1.f);
     float s = 1.f - f;
@@ -441,7 +481,7 @@ DTOF_DEV bool trace_bvh(const float4 *__restrict__ N, const float4 *__restrict__
     int node = root;
     int cur_inst = -1;
     V3 ro = o, rd = d;                                       // ray in the current (world / instance) space
-    const V3 wid = v3(1.f / d.x, 1.f / d.y, 1.f / d.z);
+    const V3 wid = v3(frcp(d.x), frcp(d.y), frcp(d.z));   // boxes are padded by 1e-5 relative: 1 ulp is immaterial
     V3 id = wid;
     float best = tmax;
     bool found = false;
@@ -500,7 +540,7 @@ DTOF_DEV bool trace_bvh(const float4 *__restrict__ N, const float4 *__restrict__
             const float4 *ip = I + 8 * (size_t) cur_inst;
             if (STATS) st.inst++;
             enter_instance(ip, o, d, time, ro, rd);
-            id = v3(1.f / rd.x, 1.f / rd.y, 1.f / rd.z);
+            id = v3(frcp(rd.x), frcp(rd.y), frcp(rd.z));
             stack[sp++] = kSentinel;
             node = __float_as_int(ip[6].z);
             continue;
@@ -545,7 +585,7 @@ DTOF_DEV bool trace_flat(const float4 *__restrict__ TF, const float4 *__restrict
                          Counters &st) {
     float best = tmax;
     bool found = false;
-    const V3 wid = v3(1.f / d.x, 1.f / d.y, 1.f / d.z);
+    const V3 wid = v3(frcp(d.x), frcp(d.y), frcp(d.z));   // boxes are padded by 1e-5 relative: 1 ulp is immaterial
     if (STATS && lane_active) {
         if (ANY) st.rays_shadow++; else st.rays_closest++;
     }
@@ -627,7 +667,7 @@ DTOF_DEV void compute_si(const DeviceScene &S, const float4 *__restrict__ I, con
         float d0x = u1x - u0x, d0y = u1y - u0y, d1x = u2x - u0x, d1y = u2y - u0y;
         float det = fmaf(d0x, d1y, -(d0y * d1x));
         if (det != 0.f) {
-            float inv_det = 1.f / det;
+            float inv_det = frcp(det);
             dp_du = v3(fmaf(d1y, dp0.x, -(d0y * dp1.x)), fmaf(d1y, dp0.y, -(d0y * dp1.y)),
                        fmaf(d1y, dp0.z, -(d0y * dp1.z))) *
                     inv_det;
@@ -675,7 +715,7 @@ DTOF_DEV V3 offset_p(V3 p, V3 n, V3 d) {
 DTOF_DEV float mis_weight(float a, float b) {
     a *= a;
     b *= b;
-    float w = a / (a + b);
+    float w = fdiv(a, a + b);
     return isfinite(w) ? w : 0.f;
 }
 
@@ -703,7 +743,7 @@ DTOF_DEV void sample_position(const DeviceScene &S, const MeshRec &m, float sx, 
     uint32_t face = lo;
     float pmf_n = pmf[face] * m.inv_area;
     float cdf_n = face > 0 ? cdf[face - 1] * m.inv_area : 0.f;
-    sy = (sy - cdf_n) / pmf_n;
+    sy = fdiv(sy - cdf_n, pmf_n);
     const float4 *sp = S.shade + 7 * (size_t) (m.first_gid + face);
     float4 s0 = __ldg(sp + 0), s1 = __ldg(sp + 1), s2 = __ldg(sp + 2);
     V3 p0 = v3(s0.x, s0.y, s0.z), p1 = v3(s1.x, s1.y, s1.z), p2 = v3(s2.x, s2.y, s2.z);
@@ -738,7 +778,7 @@ DTOF_DEV void camera_ray(const dtof_camera &c, float u, float v, V3 &o, V3 &d, f
     for (int i = 0; i < 4; ++i)
         r[i] = fmaf(m[4 * i + 2], 0.f, fmaf(m[4 * i + 1], v, fmaf(m[4 * i + 0], u, m[4 * i + 3])));
     V3 near_p = v3(r[0] / r[3], r[1] / r[3], r[2] / r[3]);
-    V3 dl = normalize3(near_p);
+    V3 dl = near_p * (1.f / sqrtf(dot3(near_p, near_p)));   // IEEE: the camera ray is compared bit for bit
     M34 tw;
 #pragma unroll
     for (int i = 0; i < 12; ++i)

@@ -37,6 +37,32 @@ DTOF_DEV bool trace_any_mode(const DeviceScene &S, const TravPtrs &P, bool any, 
     return trace_bvh<STATS>(P.N, P.T, P.I, S.root, any, o, d, tmax, time, hit, st);
 }
 
+// VelocityIntegrator::sample (src/integrators/velocity.cpp:113-127): the camera ray is intersected at t = 0 and at
+// t = `time`; the sample is (t2 - t1) / time where both hits exist, else 0. Must be called by all lanes of a warp.
+template <int MODE, bool STATS>
+DTOF_DEV PathOut trace_velocity(const DeviceScene &S, const TravPtrs &TP, const dtof_params &P, bool lane_on, V3 ray_o,
+                                V3 ray_d, float ray_maxt, Counters &st) {
+    PathOut out{ v3(0, 0, 0), 0.f, 0 };
+    const bool active = lane_on && P.max_depth != 0;
+    float t[2];
+    bool ok[2];
+#pragma unroll 1
+    for (int k = 0; k < 2; ++k) {
+        Hit h;
+        h.gid = 0;
+        h.inst = -1;
+        h.t = 0.f;
+        ok[k] = trace_any_mode<MODE, STATS>(S, TP, false, ray_o, ray_d, ray_maxt, k ? P.time : 0.f, active, h, st);
+        t[k] = ok[k] ? h.t : 0.f;
+    }
+    if (active && ok[0] && ok[1]) {
+        float v = (t[1] - t[0]) / P.time;
+        out.rgb = v3(v, v, v);
+        out.depth = 1;
+    }
+    return out;
+}
+
 // Must be called by all 32 lanes of a warp; `lane_on` masks lanes without a sample.
 //
 // The loop body is a two-phase state machine around ONE inlined traversal (a single copy of the traversal code keeps
@@ -68,7 +94,7 @@ DTOF_DEV PathOut trace_path(const DeviceScene &S, const TravPtrs &TP, const dtof
     bool prev_bsdf_delta = true;
     bool active = lane_on && P.max_depth != 0;
     const uint32_t n_em = S.n_emitters;
-    const float emitter_pmf = n_em ? 1.f / (float) n_em : 0.f;
+    const float emitter_pmf = n_em ? 1.f / (float) n_em : 0.f;   // once per sample: IEEE
 
     // state handed from phase 0 to phase 1
     bool phase_shadow = false, want_shadow = false;
@@ -114,13 +140,13 @@ DTOF_DEV PathOut trace_path(const DeviceScene &S, const TravPtrs &TP, const dtof
             const MeshRec &em_mesh = S.meshes[si.mesh];
             const EmitterRec em = S.emitters[mesh_emitter];
             V3 rel = si.p - prev_p;                                         // DirectionSample(scene, si, prev_si)
-            float dist = sqrtf(dot3(rel, rel));
+            float dist = fsqrt(dot3(rel, rel));
             V3 dsd = rel / dist;
             float em_pdf = 0.f;
             if (!prev_bsdf_delta) {                                         // AreaLight::pdf_direction, area.cpp:148-166
                 float dp = dot3(dsd, si.sh_n);
                 float pdf = em_mesh.inv_area, adp = fabsf(dp);
-                pdf *= adp != 0.f ? (dist * dist) / adp : 0.f;
+                pdf *= adp != 0.f ? fdiv(dist * dist, adp) : 0.f;
                 em_pdf = (dp < 0.f ? pdf : 0.f) * emitter_pmf;
             }
             float mis_bsdf = mis_weight(prev_bsdf_pdf, em_pdf);
@@ -161,7 +187,7 @@ DTOF_DEV PathOut trace_path(const DeviceScene &S, const TravPtrs &TP, const dtof
                 ds_delta = true;
                 ds_d = ds_p - si.p;
                 float dist2 = dot3(ds_d, ds_d), inv_dist = rsqrt_ieee(dist2);
-                ds_dist = sqrtf(dist2);
+                ds_dist = fsqrt(dist2);
                 ds_d = ds_d * inv_dist;
                 float f = inv_dist * inv_dist;
                 spec = v3(em.vr * f, em.vg * f, em.vb * f);
@@ -169,13 +195,13 @@ DTOF_DEV PathOut trace_path(const DeviceScene &S, const TravPtrs &TP, const dtof
                 sample_position(S, S.meshes[em.mesh], sx, sy, ds_p, ds_n, ds_pdf);
                 ds_d = ds_p - si.p;
                 float dist2 = dot3(ds_d, ds_d);
-                ds_dist = sqrtf(dist2);
+                ds_dist = fsqrt(dist2);
                 ds_d = ds_d / ds_dist;
                 float dp = fabsf(dot3(ds_d, ds_n));
-                float x = dist2 / dp;
+                float x = fdiv(dist2, dp);
                 ds_pdf *= isfinite(x) ? x : 0.f;
                 bool em_active = dot3(ds_d, ds_n) < 0.f && ds_pdf != 0.f;
-                spec = em_active ? v3(em.vr / ds_pdf, em.vg / ds_pdf, em.vb / ds_pdf) : v3(0, 0, 0);
+                spec = em_active ? v3(em.vr, em.vg, em.vb) / ds_pdf : v3(0, 0, 0);
             }
             if (n_em > 1) {
                 ds_pdf *= emitter_pmf;
@@ -185,7 +211,7 @@ DTOF_DEV PathOut trace_path(const DeviceScene &S, const TravPtrs &TP, const dtof
             if (ds_pdf != 0.f) {                                            // spawn_ray_to, interaction.h:141-148
                 so = offset_p(si.p, si.n, ds_p - si.p);
                 sd = ds_p - so;
-                float dist = sqrtf(dot3(sd, sd));
+                float dist = fsqrt(dot3(sd, sd));
                 sd = sd / dist;
                 s_maxt = dist * (1.f - kShadowEps);
                 want_shadow = true;
@@ -245,7 +271,7 @@ DTOF_DEV PathOut trace_path(const DeviceScene &S, const TravPtrs &TP, const dtof
         float q = smp.next_1d(correlate);                                   // always drawn
         bool rr_continue = q < rr_prob;
         if (rr_active)
-            throughput = throughput * (1.f / rr_prob);
+            throughput = throughput * frcp(rr_prob);
         active = active_next && (!rr_active || rr_continue) && tmax != 0.f;
     }
     out.rgb = valid_ray ? result : v3(0, 0, 0);

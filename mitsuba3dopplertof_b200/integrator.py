@@ -24,7 +24,7 @@ import numpy as np
 
 from . import _abi
 
-__all__ = ["DopplerToFPathIntegrator", "DTOFError"]
+__all__ = ["DopplerToFPathIntegrator", "VelocityIntegrator", "DTOFError"]
 
 f32 = np.float32
 
@@ -46,6 +46,8 @@ class DTOFError(RuntimeError):
 
 
 class DopplerToFPathIntegrator:
+    KIND = _abi.INTEGRATOR_DOPPLERTOFPATH
+
     def __init__(self, **props):
         unknown = set(props) - _KNOWN
         if unknown:
@@ -118,6 +120,7 @@ class DopplerToFPathIntegrator:
         p.path_correlate_number = int(sampler.path_correlate_number)
         p.seed = int(seed) & 0xFFFFFFFF
         p.lane_begin, p.lane_end = int(lane_begin), int(lane_end)
+        p.integrator = self.KIND
         if self.time_sampling_method == "antithetic_mirror" and p.time_correlate_number != 2:
             raise ValueError("antithetic_mirror requires time_correlate_number == 2")  # correlated.cpp:141-142
         if p.time_correlate_number < 1 or p.path_correlate_number < 1:
@@ -146,4 +149,29 @@ class DopplerToFPathIntegrator:
 
     def __repr__(self):
         return (f"DopplerToFPathIntegrator[\n  max_depth = {self.max_depth & 0xFFFFFFFF},\n"
+                f"  rr_depth = {self.rr_depth}\n]")
+
+
+class VelocityIntegrator(DopplerToFPathIntegrator):
+    """`velocity`: the reference's ground-truth radial-velocity integrator (src/integrators/velocity.cpp:87-127;
+    used by doppler_tutorials/src/program_runner.py:33-54). Properties: `time` (0.0015) plus the SamplingIntegrator /
+    MonteCarloIntegrator ones; it is not a Doppler integrator, so pixel jitter and time come from the sampler's
+    independent stream (render_sample stock branch, src/render/integrator.cpp:409-472). Every channel of the image is
+    (t(time) - t(0)) / time along the camera ray, 0 where either query misses."""
+    KIND = _abi.INTEGRATOR_VELOCITY
+    _VELOCITY_PROPS = {"time", "max_depth", "rr_depth", "hide_emitters", "timeout", "block_size", "samples_per_pass",
+                       "time_sampling_method", "antithetic_shift", "use_stratified_sampling_for_each_interval",
+                       "path_correlation_depth", "is_doppler_integrator"}
+
+    def __init__(self, **props):
+        unknown = set(props) - self._VELOCITY_PROPS
+        if unknown:
+            raise ValueError(f"velocity: unreferenced propert{'ies' if len(unknown) > 1 else 'y'} {sorted(unknown)}")
+        super().__init__(**props)
+        self.is_doppler_integrator = bool(props.get("is_doppler_integrator", False))
+        if self.is_doppler_integrator:
+            raise ValueError("velocity with is_doppler_integrator=true is outside the hot-path scope")
+
+    def __repr__(self):
+        return (f"VelocityIntegrator[\n  max_depth = {self.max_depth & 0xFFFFFFFF},\n"
                 f"  rr_depth = {self.rr_depth}\n]")

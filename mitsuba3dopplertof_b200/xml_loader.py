@@ -16,7 +16,7 @@ from typing import Dict, Optional
 
 import numpy as np
 
-from .integrator import DopplerToFPathIntegrator
+from .integrator import DopplerToFPathIntegrator, VelocityIntegrator
 from .scene import (Bsdf, CorrelatedSampler, Film, PerspectiveSensor, PointLight, Scene, Shape)
 from .transform import AnimatedTransform, Transform4
 
@@ -225,9 +225,12 @@ class _Loader:
                     self.defaults[k] = self.sub(node.get("value"))
             elif node.tag == "integrator":
                 typ = self.attr(node, "type")
-                if typ != "dopplertofpath":
-                    raise ValueError(f"integrator '{typ}' is outside the hot-path scope (dopplertofpath)")
-                sc.integrator = DopplerToFPathIntegrator(**self.props(node))
+                if typ == "dopplertofpath":
+                    sc.integrator = DopplerToFPathIntegrator(**self.props(node))
+                elif typ == "velocity":
+                    sc.integrator = VelocityIntegrator(**self.props(node))
+                else:
+                    raise ValueError(f"integrator '{typ}' is outside the hot-path scope (dopplertofpath|velocity)")
             elif node.tag == "sensor":
                 sc.sensor = self.sensor(node)
             elif node.tag == "bsdf":

@@ -1165,18 +1165,51 @@ inline void lane_sample(const dtof_oracle_scene &sc, const dtof_params &P, const
     float scale_x = 1.f / (float) f.width, scale_y = 1.f / (float) f.height;
     float off_x = -(float) f.crop_offset_x * scale_x, off_y = -(float) f.crop_offset_y * scale_y;
     float posx = (float) (px + f.crop_offset_x), posy = (float) (py + f.crop_offset_y);
-    float jx = smp.next_1d(correlate_pixel), jy = smp.next_1d(correlate_pixel);
+    const bool velocity = P.integrator == DTOF_INTEGRATOR_VELOCITY;
+    // a non-Doppler integrator takes the stock branch of render_sample (src/render/integrator.cpp:409-472):
+    // Sampler::next_2d / next_1d = the independent stream only (src/samplers/correlated.cpp:78-90)
+    float jx, jy;
+    if (velocity) {
+        jx = smp.rng.next_f32(), jy = smp.rng.next_f32();
+        smp.draws += 2;
+    } else {
+        jx = smp.next_1d(correlate_pixel), jy = smp.next_1d(correlate_pixel);
+    }
     float spx = posx + jx, spy = posy + jy;
     float ax = fmaf(spx, scale_x, off_x), ay = fmaf(spy, scale_y, off_y);
     float time = sc.cam.shutter_open;
-    if (sc.cam.shutter_open_time > 0.f)
-        time += smp.next_time(P.time_sampling_method, P.antithetic_shift,
-                              P.use_stratified_sampling_for_each_interval != 0) *
-                sc.cam.shutter_open_time;
+    if (sc.cam.shutter_open_time > 0.f) {
+        if (velocity) {
+            time += smp.rng.next_f32() * sc.cam.shutter_open_time;
+            smp.draws++;
+        } else {
+            time += smp.next_time(P.time_sampling_method, P.antithetic_shift,
+                                  P.use_stratified_sampling_for_each_interval != 0) *
+                    sc.cam.shutter_open_time;
+        }
+    }
     V3 o, d;
     float maxt;
     camera_ray(sc.cam, ax, ay, o, d, maxt);
-    PathResult r = trace_path(sc, P, mod, smp, o, d, maxt, time, st);
+    PathResult r;
+    if (velocity) {
+        // VelocityIntegrator::sample, src/integrators/velocity.cpp:113-127: closest hits at ray.time = 0 and = m_time
+        r.rgb = v3(0, 0, 0);
+        r.path_length = 0.f;
+        r.depth = 0;
+        if (P.max_depth != 0) {
+            Hit h1, h2;
+            bool v1 = intersect_closest(sc, o, d, maxt, 0.f, h1, st);
+            bool v2 = intersect_closest(sc, o, d, maxt, P.time, h2, st);
+            if (v1 && v2) {
+                float vel = ((v2 ? h2.t : 0.f) - (v1 ? h1.t : 0.f)) / P.time;
+                r.rgb = v3(vel, vel, vel);
+                r.depth = 1;
+            }
+        }
+    } else {
+        r = trace_path(sc, P, mod, smp, o, d, maxt, time, st);
+    }
     bool box = f.rfilter == DTOF_RFILTER_BOX;
     rec.sample_pos[0] = box ? posx : spx;
     rec.sample_pos[1] = box ? posy : spy;

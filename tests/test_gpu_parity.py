@@ -32,12 +32,18 @@ def test_cuda_lanes_match_reference_and_oracle(ctx, name):
     frac, worst, bad = gu.compare(rec, ref)
     assert frac >= 0.99, f"{name}: {len(bad)} lanes differ from the reference run: {ref['lanes'][bad][:8]}"
     assert worst <= gu.REL_TOL
-    # against the oracle: same arithmetic, so far tighter than the reference tolerance
+    # against the oracle: identical streams and hit arithmetic; the shading arithmetic after the hit uses the SFU
+    # approximations the reference's CUDA variants use (<= 2 ulp per op, csrc/dtof_device.cuh), so the comparison is
+    # statistical: the same 1e-4 bound as against the reference on >= 99 % of lanes, a median at rounding level and
+    # p90 <= 1e-5 (measured: p50 ~1e-7, p90 ~1e-6, p99 1e-5 .. 8e-5 for the 150 MHz cases -- one ulp of a 10 m path
+    # length is 3e-6 rad of phase there)
     orc = oracle_lib.OracleScene(flat, 0).trace(params, ref["lanes"])
     d = np.abs(rec["rgb"].astype(np.float64) - orc["rgb"])
-    tol = 1e-5 * np.maximum(np.abs(orc["rgb"]), gu.ABS_FLOOR)
-    ok = (d <= tol).all(axis=1)
+    scale = np.maximum(np.abs(orc["rgb"]), gu.ABS_FLOOR)
+    ok = (d <= gu.REL_TOL * scale).all(axis=1)
     assert ok.mean() >= 0.99, f"{name}: CUDA vs oracle mismatch on lanes {ref['lanes'][~ok][:8]}"
+    rel = (d / scale).max(axis=1)
+    assert np.median(rel) <= 1e-6 and np.quantile(rel, 0.9) <= 1e-5, (np.median(rel), np.quantile(rel, 0.9))
     assert np.array_equal(rec["depth"][ok], orc["depth"][ok])
     assert np.array_equal(rec["rng_draws"][ok], orc["rng_draws"][ok])   # identical stream consumption
     np.testing.assert_array_equal(rec["time"], orc["time"])               # sampler + camera are bit-exact
