@@ -345,9 +345,18 @@ def main():
     achieved = bytes_per_sample * samples_per_step / (kms * 1e-3) / 1e9
     clk = clocks.summary()
     issue_peak = 148 * 4 * 32 * (clk["sm_mhz"] or peaks.get("sm_max_mhz", 1965.0)) * 1e6
+    traffic, ncu_issue = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(args.workload)
+        if tj:
+            traffic = tj["bytes_per_sample"] * samples_per_step
+            ncu_issue = tj.get("issue_active_pct")
+    except Exception:   # noqa: BLE001
+        pass
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-        "traffic": None, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})", "kernel": "render_kernel",
+        "traffic": traffic, "traffic_source": "profiles/r01_traffic.json (ncu dram bytes per sample x samples per launch)" if traffic else None,
+        "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})", "kernel": "render_kernel",
         "kernel_ms": kms, "bytes_per_sample": bytes_per_sample,
         "per_sample": {"rays_closest": st.rays_closest / n, "rays_shadow": st.rays_shadow / n, "nodes": st.nodes_visited / n,
                        "tris": st.tris_tested / n, "inst": st.inst_visits / n},
@@ -358,7 +367,8 @@ def main():
         "issue": {"instr_per_sample_model": instr_per_sample,
                   "achieved_lane_instr_per_s": instr_per_sample * samples_per_step / (kms * 1e-3),
                   "peak_lane_instr_per_s": issue_peak,
-                  "frac": instr_per_sample * samples_per_step / (kms * 1e-3) / issue_peak},
+                  "frac": instr_per_sample * samples_per_step / (kms * 1e-3) / issue_peak,
+                  "ncu_issue_active_pct": ncu_issue},
     }
 
     cpu = None

@@ -265,6 +265,12 @@ dtof_status dtof_pass_info_for(const dtof_ctx *ctx, const dtof_params *params, d
  * image_out: height*width*3 floats (developed RGB = RGB/W); either may be NULL. Copies are inside. */
 dtof_status dtof_render(dtof_ctx *ctx, const dtof_params *params, float *rgbw_out, float *image_out);
 
+/* The tutorials' multi-pass driver (render_image_multi_pass, doppler_tutorials/src/program_runner.py:11-31):
+ * n_renders renders with seed = params->seed + i (i = 0 .. n_renders-1), each developed (RGB / W), averaged ON THE
+ * DEVICE; the scene stays resident and only the final H*W*3 image crosses to the host. This is also how a 16k-spp
+ * image is produced (16 renders of 1024 spp; a single 16k-spp render() throws in the reference). */
+dtof_status dtof_render_multi_pass(dtof_ctx *ctx, const dtof_params *params, uint32_t n_renders, float *image_out);
+
 /* Render, ACCUMULATING into a caller-provided DEVICE tensor d_rgbw (height*width*4 floats, on the context's
  * device) on CUDA stream `stream` (a cudaStream_t, NULL = default stream). Asynchronous. The caller zeroes the
  * tensor, reduces it across GPUs (ncclAllReduce sum) and calls dtof_develop_device. */

@@ -139,6 +139,7 @@ DTOF_SYMBOLS = {
     "dtof_update_instances": (C.c_int, [_ctx, C.c_uint32, C.c_uint32, C.POINTER(Instance)]),
     "dtof_pass_info_for": (C.c_int, [_ctx, C.POINTER(Params), C.POINTER(PassInfo)]),
     "dtof_render": (C.c_int, [_ctx, C.POINTER(Params), _fp, _fp]),
+    "dtof_render_multi_pass": (C.c_int, [_ctx, C.POINTER(Params), C.c_uint32, _fp]),
     "dtof_render_device": (C.c_int, [_ctx, C.POINTER(Params), C.c_void_p, C.c_void_p]),
     "dtof_develop_device": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dtof_trace_samples": (C.c_int, [_ctx, C.POINTER(Params), C.POINTER(C.c_uint64), C.c_uint32,

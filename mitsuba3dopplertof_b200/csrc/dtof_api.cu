@@ -194,6 +194,24 @@ __global__ void develop_kernel(const float4 *__restrict__ rgbw, float *__restric
     img[3 * i + 2] = v.z / w;
 }
 
+// image (+)= RGB / W * scale: one developed render folded into the running multi-pass mean
+__global__ void develop_accumulate_kernel(const float4 *__restrict__ rgbw, float *__restrict__ img, size_t n, float scale, int first) {
+    size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    float4 v = rgbw[i];
+    float w = v.w == 0.f ? 1.f : v.w;
+    float r = v.x / w * scale, g = v.y / w * scale, b = v.z / w * scale;
+    if (!first) {
+        r += img[3 * i + 0];
+        g += img[3 * i + 1];
+        b += img[3 * i + 2];
+    }
+    img[3 * i + 0] = r;
+    img[3 * i + 1] = g;
+    img[3 * i + 2] = b;
+}
+
 } // namespace
 
 // ==================================================================================================
@@ -878,6 +896,36 @@ dtof_status dtof_render(dtof_ctx *ctx, const dtof_params *params, float *rgbw_ou
         CU(cudaMemcpyAsync(rgbw_out, ctx->d_rgbw, ctx->film_px * 4 * sizeof(float), cudaMemcpyDeviceToHost, 0));
     if (image_out)
         CU(cudaMemcpyAsync(image_out, ctx->d_img, ctx->film_px * 3 * sizeof(float), cudaMemcpyDeviceToHost, 0));
+    CU(cudaStreamSynchronize(0));
+    return DTOF_OK;
+}
+
+dtof_status dtof_render_multi_pass(dtof_ctx *ctx, const dtof_params *params, uint32_t n_renders, float *image_out) {
+    if (!ctx)
+        return DTOF_ERR_INVALID;
+    if (!ctx->has_scene)
+        return fail(ctx, DTOF_ERR_STATE, "no scene uploaded");
+    if (!image_out || n_renders == 0)
+        return fail(ctx, DTOF_ERR_INVALID, "image_out is NULL or n_renders is 0");
+    dtof_status s = check_params(ctx, params);
+    if (s != DTOF_OK)
+        return s;
+    CU(cudaSetDevice(ctx->device));
+    const size_t n = ctx->film_px;
+    const float scale = 1.f / (float) n_renders;
+    float ms_total = 0.f;
+    for (uint32_t i = 0; i < n_renders; ++i) {
+        dtof_params p = *params;
+        p.seed = params->seed + i;
+        CU(cudaMemsetAsync(ctx->d_rgbw, 0, n * 4 * sizeof(float), 0));
+        if ((s = launch_render(ctx, &p, ctx->d_rgbw, 0, nullptr, nullptr, 0)) != DTOF_OK)
+            return s;
+        develop_accumulate_kernel<<<(unsigned) ((n + 255) / 256), 256>>>((const float4 *) ctx->d_rgbw, ctx->d_img, n, scale, i == 0);
+        ctx->launches++;
+        CU(cudaGetLastError());
+        (void) ms_total;
+    }
+    CU(cudaMemcpyAsync(image_out, ctx->d_img, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, 0));
     CU(cudaStreamSynchronize(0));
     return DTOF_OK;
 }

@@ -147,6 +147,18 @@ class DopplerToFPathIntegrator:
         p = self.params(scene.sensor.sampler, seed, spp)
         return ctx.render(flat, p, develop=develop)
 
+    def render_multi_pass(self, scene, spp_per_pass: int, passes: int, seed: int = 0, device: Optional[int] = None) -> np.ndarray:
+        """`render_image_multi_pass(scene, integrator, spp, passes)` of the tutorials
+        (doppler_tutorials/src/program_runner.py:11-31): mean over `passes` renders with seed, seed+1, ...;
+        the scene stays on the GPU and the mean is formed there."""
+        from .runtime import get_context
+        ctx = get_context(device)
+        cached = getattr(scene, "_dtof_uploaded", None)
+        if cached is None or cached[0] is not ctx or ctx._flat is not cached[1]:
+            scene._dtof_uploaded = (ctx, ctx.upload(scene))
+        flat = scene._dtof_uploaded[1]
+        return ctx.render_multi_pass(flat, self.params(scene.sensor.sampler, seed, spp_per_pass), passes)
+
     def __repr__(self):
         return (f"DopplerToFPathIntegrator[\n  max_depth = {self.max_depth & 0xFFFFFFFF},\n"
                 f"  rr_depth = {self.rr_depth}\n]")

@@ -126,6 +126,12 @@ class Context:
             return img, rgbw
         return img if develop else rgbw
 
+    def render_multi_pass(self, flat, params: _abi.Params, n_renders: int) -> np.ndarray:
+        """Mean of `n_renders` developed renders with seed, seed+1, ... (averaged on the device)."""
+        img = np.empty((flat.height, flat.width, 3), np.float32)
+        self._check(self.lib.dtof_render_multi_pass(self.h, C.byref(params), int(n_renders), _abi.as_fp(img)))
+        return img
+
     def render_device(self, params: _abi.Params, d_rgbw_ptr: int, stream_ptr: int = 0) -> None:
         """Accumulate into a caller-owned device tensor (e.g. torch.Tensor.data_ptr()), asynchronously."""
         self._check(self.lib.dtof_render_device(self.h, C.byref(params), C.c_void_p(d_rgbw_ptr), C.c_void_p(stream_ptr)))

@@ -147,3 +147,15 @@ def test_interleaved_shards_sum_to_whole(ctx, mode, world):
     parts = sum(ctx.render(flat, shard_params(params, pi, world, r, mode, tile_pixels=7), develop=False) for r in range(world))
     assert np.abs(parts - whole).max() <= 1e-5 * np.abs(whole).max()
     assert np.abs(parts[..., 3] - whole[..., 3]).max() <= 1e-4
+
+
+def test_multi_pass_driver_equals_mean_of_renders(ctx):
+    """dtof_render_multi_pass == render_image_multi_pass of the tutorials: mean of developed renders, seed = 0, 1, 2."""
+    scene = dt.load_file(os.path.join(gu.SCENES, "c2_arealight.xml"), resx=48, resy=32, spp=64)
+    flat = ctx.upload(scene)
+    base = scene.integrator.params(scene.sensor.sampler, seed=10, spp=32)
+    got = ctx.render_multi_pass(flat, base, 3)
+    want = np.mean([ctx.render(flat, scene.integrator.params(scene.sensor.sampler, seed=10 + i, spp=32)) for i in range(3)], axis=0)
+    assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
+    with pytest.raises(ValueError):
+        ctx.render_multi_pass(flat, base, 0)
