@@ -109,6 +109,7 @@ struct Film {
 
 struct CorrelatedSampler {
     uint32_t sample_count = 4, seed = 0, time_correlate_number = 2, path_correlate_number = 2;
+    bool correlated = true;   // false: `independent` (PCG32Sampler only), usable by the non-Doppler integrators
 };
 
 struct PerspectiveSensor {
@@ -133,7 +134,7 @@ struct DopplerToFPathIntegrator {
     int32_t max_depth = -1, rr_depth = 5;
     bool hide_emitters = false;
     double timeout = -1.0;
-    uint32_t kind = DTOF_INTEGRATOR_DOPPLERTOFPATH;   // or DTOF_INTEGRATOR_VELOCITY (src/integrators/velocity.cpp)
+    uint32_t kind = DTOF_INTEGRATOR_DOPPLERTOFPATH;   // or _VELOCITY (src/integrators/velocity.cpp), _PATH (src/integrators/path.cpp)
     // props: name -> textual value (already $-substituted); throws on unknown names / bad enum strings
     explicit DopplerToFPathIntegrator(const std::map<std::string, std::string> &props = {},
                                       uint32_t kind = DTOF_INTEGRATOR_DOPPLERTOFPATH);

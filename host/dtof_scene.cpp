@@ -399,6 +399,10 @@ DopplerToFPathIntegrator::DopplerToFPathIntegrator(const std::map<std::string, s
         for (auto &kv : props)
             if (!velocity_known.count(kv.first))
                 throw Error("velocity: unreferenced property \"" + kv.first + "\"");
+    if (kind == DTOF_INTEGRATOR_PATH)   // PathIntegrator (src/integrators/path.cpp:93) reads nothing of its own
+        for (auto &kv : props)
+            if (kv.first == "time" || !velocity_known.count(kv.first))
+                throw Error("path: unreferenced property \"" + kv.first + "\"");
     static const std::set<std::string> known = {
         "time", "w_g", "g_1", "g_0", "w_s", "sensor_phase_offset", "hetero_offset", "hetero_frequency", "wave_function_type",
         "low_frequency_component_only", "max_depth", "rr_depth", "hide_emitters", "timeout", "is_doppler_integrator",
@@ -475,6 +479,8 @@ dtof_params DopplerToFPathIntegrator::params(const CorrelatedSampler &s, uint32_
     p.path_correlate_number = s.path_correlate_number;
     p.seed = seed;
     p.integrator = kind;
+    if (kind == DTOF_INTEGRATOR_DOPPLERTOFPATH && !s.correlated)
+        throw Error("dopplertofpath is driven by the 'correlated' sampler (README.md:61)");
     if (time_sampling_method == DTOF_TIME_ANTITHETIC_MIRROR && s.time_correlate_number != 2)
         throw Error("antithetic_mirror requires time_correlate_number == 2");   // correlated.cpp:141-142
     if (s.time_correlate_number < 1 || s.path_correlate_number < 1)
@@ -966,12 +972,18 @@ struct Loader {
             if (ch->tag == "transform" && nm && *nm == "to_world") {
                 s.to_world = transform(*ch);
             } else if (ch->tag == "sampler") {
-                if (attr(*ch, "type") != "correlated")
-                    throw Error("dopplertofpath is driven by the 'correlated' sampler (README.md:61)");
+                const std::string skind = attr(*ch, "type");
+                if (skind != "correlated" && skind != "independent")
+                    throw Error("sampler '" + skind + "' is outside the hot-path scope (correlated; independent for path/velocity)");
                 auto sp = props(*ch);
+                CorrelatedSampler cs;
+                if (skind == "independent") {   // PCG32Sampler only: the stream `path` / `velocity` draw from (sampler.cpp:115-134)
+                    reject_unknown(sp, { "sample_count", "seed" }, "independent sampler");
+                    cs.correlated = false;
+                    cs.time_correlate_number = 1;
+                }
                 // use_stratified_sampling_for_each_interval is an INTEGRATOR property (SURVEY.md finding 7)
                 reject_unknown(sp, { "sample_count", "seed", "time_correlate_number", "path_correlate_number" }, "correlated sampler");
-                CorrelatedSampler cs;
                 if (sp.count("sample_count")) cs.sample_count = (uint32_t) parse_int(sp["sample_count"].value);
                 if (sp.count("seed")) cs.seed = (uint32_t) parse_int(sp["seed"].value);
                 if (sp.count("time_correlate_number")) cs.time_correlate_number = (uint32_t) parse_int(sp["time_correlate_number"].value);
@@ -1027,12 +1039,13 @@ struct Loader {
                     defaults[k] = sub(*node->attr("value"));
             } else if (node->tag == "integrator") {
                 std::string typ = attr(*node, "type");
-                if (typ != "dopplertofpath" && typ != "velocity")
-                    throw Error("integrator '" + typ + "' is outside the hot-path scope (dopplertofpath|velocity)");
+                if (typ != "dopplertofpath" && typ != "velocity" && typ != "path")
+                    throw Error("integrator '" + typ + "' is outside the hot-path scope (dopplertofpath|velocity|path)");
                 std::map<std::string, std::string> ip;
                 for (auto &kv : props(*node))
                     ip[kv.first] = kv.second.value;
-                sc.integrator = DopplerToFPathIntegrator(ip, typ == "velocity" ? DTOF_INTEGRATOR_VELOCITY : DTOF_INTEGRATOR_DOPPLERTOFPATH);
+                sc.integrator = DopplerToFPathIntegrator(ip, typ == "velocity" ? DTOF_INTEGRATOR_VELOCITY
+                                                             : typ == "path" ? DTOF_INTEGRATOR_PATH : DTOF_INTEGRATOR_DOPPLERTOFPATH);
                 have_integrator = true;
             } else if (node->tag == "sensor") {
                 sc.sensor = sensor(*node);
@@ -1076,6 +1089,8 @@ struct Loader {
                 throw Error("Unused parameter \"" + k + "\"!");   // xml.cpp:1069
         if (!have_integrator)
             throw Error("scene has no integrator");
+        if (sc.integrator.kind == DTOF_INTEGRATOR_DOPPLERTOFPATH && !sc.sensor.sampler.correlated)
+            throw Error("dopplertofpath is driven by the 'correlated' sampler (README.md:61)");
         return sc;
     }
 };

@@ -4,13 +4,16 @@
 // (include/dtof.h) and puts the returned RGBW tensor into the film, i.e. it replaces
 //   SamplingIntegrator::render            src/render/integrator.cpp:104-347
 // for this integrator. Built for scalar_rgb (Float = float, host memory), with the reference's exact compile flags
-// (INTEGRATION.md). NOT compiled in this repository's image: the reference needs its CMake build (generated
-// config.h, Embree, Dr.Jit), which this round treats as unbuildable; `host/dtof_render` is the compiled and tested
-// twin of this file (same flattening code path in host/dtof_scene.cpp).
+// (INTEGRATION.md). It compiles against the UNMODIFIED reference headers and loads into the unmodified reference
+// runtime (`mitsuba -m scalar_rgb scene.xml`): oracle/ref_harness/Makefile builds it next to a reference runtime in
+// oracle/_ref/plugins/, tests/test_mitsuba_plugin.py renders through it on the GPU box.
 //
-// Two accessors must be added to the reference because the data is private there (8 lines):
-//   Shape::animated_to_world()                  -> Instance::m_transform   (src/shapes/instance.cpp:340)
-//   Sampler::time/path_correlate_number()       -> CorrelatedSampler members (src/samplers/correlated.cpp:18-19)
+// Two pieces of state are private in the reference (declared inside .cpp files, no accessor, not exposed through
+// traverse()): Instance::m_transform (src/shapes/instance.cpp:338-340) and CorrelatedSampler's correlate numbers
+// (src/samplers/correlated.cpp:179-183). They are read through layout mirrors of those two classes (below), checked
+// against the class name; upstream would rather add the accessors listed in INTEGRATION.md section 2.
+#include <cmath>
+
 #include <mitsuba/core/properties.h>
 #include <mitsuba/core/transform.h>
 #include <mitsuba/render/bsdf.h>
@@ -46,6 +49,34 @@ struct Collector : TraversalCallback {
 };
 } // namespace
 
+// Layout mirrors (same base class, same member types in the same order => same offsets under the Itanium ABI).
+// Never instantiated; only used to read two members of objects the reference's own plugins constructed.
+template <typename Float, typename Spectrum>
+struct InstanceLayout : public Shape<Float, Spectrum> {                  // src/shapes/instance.cpp:52-341
+    ref<Object> m_shapegroup;
+    ref<AnimatedTransform> m_transform;
+};
+template <typename Float, typename Spectrum>
+struct CorrelatedSamplerLayout : public PCG32Sampler<Float, Spectrum> {  // src/samplers/correlated.cpp:13-187
+    using PCG32 = mitsuba::PCG32<dr::uint32_array_t<Float>>;
+    PCG32 m_rng_time;
+    int m_time_correlate_number;
+    PCG32 m_rng_path;
+    int m_path_correlate_number;
+    dr::uint32_array_t<Float> m_permutation_seed;
+};
+
+// Protected members declared in the reference's headers, read through a pointer to member named from a derived class
+// (Sampler::m_base_seed include/mitsuba/render/sampler.h:184, Mesh::m_flip_normals include/mitsuba/render/mesh.h:456).
+template <typename Float, typename Spectrum>
+struct SamplerPeek : public Sampler<Float, Spectrum> {
+    static uint32_t base_seed(const Sampler<Float, Spectrum> *s) { return s->*(&SamplerPeek::m_base_seed); }
+};
+template <typename Float, typename Spectrum>
+struct MeshPeek : public Mesh<Float, Spectrum> {
+    static bool flip_normals(const Mesh<Float, Spectrum> *m) { return m->*(&MeshPeek::m_flip_normals); }
+};
+
 template <typename Float, typename Spectrum>
 class DopplerToFPathB200 final : public MonteCarloIntegrator<Float, Spectrum> {
 public:
@@ -67,7 +98,7 @@ public:
         ScalarFloat w_s = props.get<ScalarFloat>("w_s", 30.f);
         m_p.sensor_phase_offset = props.get<ScalarFloat>("sensor_phase_offset", 0.f);
         if (props.has_property("hetero_offset"))
-            m_p.sensor_phase_offset = props.get<ScalarFloat>("hetero_offset", 0.0) * 2 * M_PI;
+            m_p.sensor_phase_offset = props.get<ScalarFloat>("hetero_offset", 0.0) * 2 * 3.14159265358979323846;
         if (props.has_property("hetero_frequency"))
             m_p.hetero_frequency = props.get<ScalarFloat>("hetero_frequency", 1.0);
         else
@@ -101,9 +132,15 @@ public:
         p.path_correlation_depth = m_path_correlation_depth;
         const Sampler *sampler = sensor->sampler();
         p.sample_count = spp ? spp : sampler->sample_count();            // integrator.cpp:121-124
-        p.base_seed = sampler->seed();
-        p.time_correlate_number = sampler->time_correlate_number();      // accessor added by the reference-side patch
-        p.path_correlate_number = sampler->path_correlate_number();
+        p.base_seed = SamplerPeek<Float, Spectrum>::base_seed(sampler);   // sampler.cpp:13-14
+        if (sampler->class_()->name() != "CorrelatedSampler")
+            Throw("dopplertofpath_b200 needs the 'correlated' sampler (got %s)", sampler->class_()->name());
+        auto *cs = reinterpret_cast<const CorrelatedSamplerLayout<Float, Spectrum> *>(sampler);
+        p.time_correlate_number = (uint32_t) cs->m_time_correlate_number;   // correlated.cpp:18-19
+        p.path_correlate_number = (uint32_t) cs->m_path_correlate_number;
+        if (p.time_correlate_number - 1u > 4095u || p.path_correlate_number - 1u > 4095u)
+            Throw("implausible correlate numbers (%u, %u): the CorrelatedSampler layout differs from the mirrored one",
+                  p.time_correlate_number, p.path_correlate_number);
         p.seed = seed;
 
         ScalarVector2u size = film->crop_size();
@@ -177,7 +214,7 @@ private:
             if (mesh->has_vertex_texcoords())
                 buf.uv.assign(mesh->vertex_texcoords_buffer().data(), mesh->vertex_texcoords_buffer().data() + 2 * mesh->vertex_count());
             m.kind = DTOF_SHAPE_MESH;
-            m.flip_normals = mesh->has_flipped_normals();
+            m.flip_normals = MeshPeek<Float, Spectrum>::flip_normals(mesh);
         } else if (shape->class_()->name() == "Rectangle") {             // analytic quad -> 2 triangles + parametrisation
             Collector c;
             const_cast<Shape *>(shape)->traverse(&c);
@@ -221,7 +258,10 @@ private:
             instances.push_back(st);
         for (auto &s : scene->shapes())
             if (s->is_instance()) {
-                const AnimatedTransform *at = s->animated_to_world();    // accessor added by the reference-side patch
+                const AnimatedTransform *at =                            // Instance::m_transform, instance.cpp:63
+                    reinterpret_cast<const InstanceLayout<Float, Spectrum> *>(s.get())->m_transform.get();
+                if (!at || at->size() == 0)
+                    Throw("instance without keyframes: the Instance layout differs from the mirrored one");
                 dtof_instance in{};
                 in.first_mesh = (uint32_t) meshes.size();
                 in.animated = 1;
@@ -229,7 +269,7 @@ private:
                 m34(at->eval(in.t0), in.m0);                             // Instance::embree_geometry, instance.cpp:295-310
                 m34(at->eval(in.t1), in.m1);
                 Collector c;                                             // ShapeGroup::traverse lists the members
-                ((Shape *) s->get_shapegroup())->traverse(&c);
+                ((Shape *) const_cast<Shape *>(s.get())->get_shapegroup())->traverse(&c);
                 for (auto &o : c.objects)
                     add_shape((const Shape *) o.second, meshes, bufs, bsdfs);
                 in.n_meshes = (uint32_t) meshes.size() - in.first_mesh;
@@ -240,7 +280,7 @@ private:
             SurfaceInteraction3f si = dr::zeros<SurfaceInteraction3f>();
             si.wi = ScalarVector3f(0, 0, 1);
             Collector c;
-            e->traverse(&c);
+            const_cast<Emitter *>(e.get())->traverse(&c);
             if (e->class_()->name() == "PointLight") {
                 d.kind = DTOF_EMITTER_POINT;
                 const ScalarPoint3f &p = *c.param<ScalarPoint3f>("position");

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define DTOF_ABI_VERSION 2
+#define DTOF_ABI_VERSION 3
 
 typedef struct dtof_ctx dtof_ctx;
 
@@ -71,8 +71,16 @@ typedef enum dtof_waveform {
 /* Which SamplingIntegrator::sample() the lanes run. VELOCITY = the reference's ground-truth radial-velocity
  * integrator (src/integrators/velocity.cpp:113-127): two closest-hit queries of the camera ray at t = 0 and t = `time`,
  * value (t2 - t1) / time in all three channels; it is NOT a Doppler integrator, so render_sample takes the stock
- * branch (src/render/integrator.cpp:409-472): jitter and time come from the sampler's independent stream only. */
-typedef enum dtof_integrator_kind { DTOF_INTEGRATOR_DOPPLERTOFPATH = 0, DTOF_INTEGRATOR_VELOCITY = 1 } dtof_integrator_kind;
+ * branch (src/render/integrator.cpp:409-472): jitter and time come from the sampler's independent stream only.
+ * PATH = the stock path tracer (src/integrators/path.cpp:103-283) the tutorials use for the radiance pass
+ * (doppler_tutorials/src/program_runner.py:57-80): the same bounce loop as dopplertofpath without the modulation
+ * weight and without the time wrap, every draw from Sampler::next_1d/next_2d = the independent stream
+ * (src/samplers/correlated.cpp:78-90), stock render_sample branch. */
+typedef enum dtof_integrator_kind {
+    DTOF_INTEGRATOR_DOPPLERTOFPATH = 0,
+    DTOF_INTEGRATOR_VELOCITY = 1,
+    DTOF_INTEGRATOR_PATH = 2
+} dtof_integrator_kind;
 
 typedef enum dtof_rfilter { DTOF_RFILTER_BOX = 0, DTOF_RFILTER_TENT = 1, DTOF_RFILTER_GAUSSIAN = 2 } dtof_rfilter;
 typedef enum dtof_shape_kind { DTOF_SHAPE_MESH = 0, DTOF_SHAPE_RECTANGLE = 1 } dtof_shape_kind;

@@ -5,13 +5,13 @@ Host-side mirror of the reference's plugin surface (scene XML subset, integrator
 `render(scene, seed, spp)`) over the C ABI of `libdtof_b200.so` (include/dtof.h). Importing the package
 needs neither the CUDA library nor a GPU; rendering does, and fails loudly without them.
 """
-from .integrator import DopplerToFPathIntegrator, DTOFError, VelocityIntegrator
+from .integrator import DopplerToFPathIntegrator, DTOFError, PathIntegrator, VelocityIntegrator
 from .scene import (Bsdf, CorrelatedSampler, Film, PerspectiveSensor, PointLight, Scene, Shape, cube, mesh,
                     rectangle)
 from .transform import AnimatedTransform, Transform4
 from .xml_loader import load_file, load_string
 
 __all__ = [
-    "DopplerToFPathIntegrator", "VelocityIntegrator", "DTOFError", "Bsdf", "CorrelatedSampler", "Film", "PerspectiveSensor", "PointLight",
+    "DopplerToFPathIntegrator", "VelocityIntegrator", "PathIntegrator", "DTOFError", "Bsdf", "CorrelatedSampler", "Film", "PerspectiveSensor", "PointLight",
     "Scene", "Shape", "cube", "mesh", "rectangle", "AnimatedTransform", "Transform4", "load_file", "load_string",
 ]

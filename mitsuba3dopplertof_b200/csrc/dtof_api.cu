@@ -57,7 +57,7 @@ struct RenderArgs {
     uint32_t nodes_bytes, tris_bytes, insts_bytes, boxes_bytes;
 };
 
-template <int MODE, bool STATS, bool RECORD, bool VELOCITY>
+template <int MODE, bool STATS, bool RECORD, int KIND>
 __global__ void __launch_bounds__(kBlock, DTOF_MIN_CTAS) render_kernel(const __grid_constant__ RenderArgs A) {
     extern __shared__ float4 smem[];
     TravPtrs TP;
@@ -75,6 +75,8 @@ __global__ void __launch_bounds__(kBlock, DTOF_MIN_CTAS) render_kernel(const __g
         __syncthreads();
         TP.N = sN, TP.T = sT, TP.TF = sT, TP.I = sI, TP.B = sB;
     }
+    constexpr bool VELOCITY = KIND == DTOF_INTEGRATOR_VELOCITY;
+    constexpr bool STOCK_SAMPLE = KIND != DTOF_INTEGRATOR_DOPPLERTOFPATH;   // stock render_sample branch (integrator.cpp:409-472)
     const int lane = threadIdx.x & 31;
     Counters st = {};
     const unsigned long long n_lanes = RECORD ? (unsigned long long) A.n_rec : A.n_local;
@@ -110,13 +112,13 @@ __global__ void __launch_bounds__(kBlock, DTOF_MIN_CTAS) render_kernel(const __g
 
             for (uint32_t pass = 0; pass < (RECORD ? 1u : A.n_passes); ++pass) {
                 // render_sample(): Doppler branch (src/render/integrator.cpp:476-542), or the stock branch (:409-472)
-                // for the velocity integrator -- jitter and time from the independent stream only
+                // for the velocity and path integrators -- jitter and time from the independent stream only
                 const bool correlate_pixel = A.p.path_correlation_depth > 0;
                 const float scale_x = 1.f / (float) A.film.width, scale_y = 1.f / (float) A.film.height;
                 const float off_x = -(float) A.film.crop_x * scale_x, off_y = -(float) A.film.crop_y * scale_y;
                 const float posx = (float) (px + A.film.crop_x), posy = (float) (py + A.film.crop_y);
                 float jx, jy;
-                if (VELOCITY) {
+                if (STOCK_SAMPLE) {
                     jx = smp.rng.next_f32(), jy = smp.rng.next_f32();
                     smp.draws += 2;
                 } else {
@@ -126,7 +128,7 @@ __global__ void __launch_bounds__(kBlock, DTOF_MIN_CTAS) render_kernel(const __g
                 float ax = fmaf(spx, scale_x, off_x), ay = fmaf(spy, scale_y, off_y);
                 float time = A.cam.shutter_open;
                 if (A.cam.shutter_open_time > 0.f) {
-                    if (VELOCITY) {
+                    if (STOCK_SAMPLE) {
                         time += smp.rng.next_f32() * A.cam.shutter_open_time;
                         smp.draws++;
                     } else {
@@ -137,7 +139,8 @@ __global__ void __launch_bounds__(kBlock, DTOF_MIN_CTAS) render_kernel(const __g
                 float maxt;
                 camera_ray(A.cam, ax, ay, o, d, maxt);
                 PathOut r = VELOCITY ? trace_velocity<MODE, STATS>(A.scene, TP, A.p, lane_on, o, d, maxt, st)
-                                     : trace_path<MODE, STATS>(A.scene, TP, A.p, A.mod, smp, lane_on, o, d, maxt, time, st);
+                                     : trace_path<MODE, STATS, KIND == DTOF_INTEGRATOR_DOPPLERTOFPATH>(A.scene, TP, A.p, A.mod, smp,
+                                                                                                       lane_on, o, d, maxt, time, st);
                 V3 rgb = r.rgb;
                 if (A.film.rfilter == DTOF_RFILTER_BOX) {
                     spx = posx;
@@ -342,9 +345,9 @@ dtof_status check_params(dtof_ctx *ctx, const dtof_params *p) {
     if (p->use_stratified_sampling_for_each_interval && p->time_sampling_method != DTOF_TIME_UNIFORM &&
         p->sample_count / p->time_correlate_number == 0)
         return fail(ctx, DTOF_ERR_INVALID, "sample_count < time_correlate_number");
-    if (!(p->time > 0.f))
+    if (!(p->time > 0.f) && p->integrator != DTOF_INTEGRATOR_PATH)   // `path` has no time property
         return fail(ctx, DTOF_ERR_INVALID, "time must be > 0");
-    if (p->integrator > DTOF_INTEGRATOR_VELOCITY || p->reserved != 0)
+    if (p->integrator > DTOF_INTEGRATOR_PATH || p->reserved != 0)
         return fail(ctx, DTOF_ERR_INVALID, "unknown integrator kind %u", p->integrator);
     return DTOF_OK;
 }
@@ -365,14 +368,14 @@ Modulation make_modulation(const dtof_params &p) {
     return m;
 }
 
-template <int MODE, bool STATS, bool RECORD, bool VELOCITY>
+template <int MODE, bool STATS, bool RECORD, int KIND>
 dtof_status launch_variant(dtof_ctx *ctx, RenderArgs &A, int grid, cudaStream_t stream) {
     size_t smem = 0;
     if (MODE == MODE_BVH_SMEM)
         smem = (size_t) A.nodes_bytes + A.tris_bytes + A.insts_bytes + A.boxes_bytes;
     else if (MODE == MODE_FLAT_SMEM)
         smem = (size_t) A.tris_bytes + A.insts_bytes + A.boxes_bytes;
-    auto k = render_kernel<MODE, STATS, RECORD, VELOCITY>;
+    auto k = render_kernel<MODE, STATS, RECORD, KIND>;
     if (smem)
         CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     k<<<grid, kBlock, smem, stream>>>(A);
@@ -383,13 +386,16 @@ dtof_status launch_variant(dtof_ctx *ctx, RenderArgs &A, int grid, cudaStream_t 
 
 template <int MODE>
 dtof_status launch_mode(dtof_ctx *ctx, RenderArgs &A, bool record, int grid, cudaStream_t stream) {
-    if (A.p.integrator == DTOF_INTEGRATOR_VELOCITY)   // counters are not instrumented for the velocity variant
-        return record ? launch_variant<MODE, false, true, true>(ctx, A, grid, stream)
-                      : launch_variant<MODE, false, false, true>(ctx, A, grid, stream);
+    if (A.p.integrator == DTOF_INTEGRATOR_VELOCITY)   // counters are not instrumented for the velocity / path variants
+        return record ? launch_variant<MODE, false, true, DTOF_INTEGRATOR_VELOCITY>(ctx, A, grid, stream)
+                      : launch_variant<MODE, false, false, DTOF_INTEGRATOR_VELOCITY>(ctx, A, grid, stream);
+    if (A.p.integrator == DTOF_INTEGRATOR_PATH)
+        return record ? launch_variant<MODE, false, true, DTOF_INTEGRATOR_PATH>(ctx, A, grid, stream)
+                      : launch_variant<MODE, false, false, DTOF_INTEGRATOR_PATH>(ctx, A, grid, stream);
     if (record)
-        return launch_variant<MODE, false, true, false>(ctx, A, grid, stream);
-    return ctx->stats_enabled ? launch_variant<MODE, true, false, false>(ctx, A, grid, stream)
-                              : launch_variant<MODE, false, false, false>(ctx, A, grid, stream);
+        return launch_variant<MODE, false, true, DTOF_INTEGRATOR_DOPPLERTOFPATH>(ctx, A, grid, stream);
+    return ctx->stats_enabled ? launch_variant<MODE, true, false, DTOF_INTEGRATOR_DOPPLERTOFPATH>(ctx, A, grid, stream)
+                              : launch_variant<MODE, false, false, DTOF_INTEGRATOR_DOPPLERTOFPATH>(ctx, A, grid, stream);
 }
 
 dtof_status launch_render(dtof_ctx *ctx, const dtof_params *p, float *d_rgbw, cudaStream_t stream,

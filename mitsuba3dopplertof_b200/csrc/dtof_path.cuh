@@ -34,7 +34,7 @@ DTOF_DEV bool trace_any_mode(const DeviceScene &S, const TravPtrs &P, bool any, 
         return trace_flat<STATS>(P.TF, P.I, P.B, S.n_insts, any, o, d, tmax, time, lane_active, hit, st);
     if (!lane_active || !S.has_geometry)
         return false;
-    return trace_bvh<STATS>(P.N, P.T, P.I, S.root, any, o, d, tmax, time, hit, st);
+    return trace_bvh<STATS, MODE == MODE_BVH_GLOBAL>(P.N, P.T, P.I, S.root, any, o, d, tmax, time, hit, st);
 }
 
 // VelocityIntegrator::sample (src/integrators/velocity.cpp:113-127): the camera ray is intersected at t = 0 and at
@@ -76,13 +76,15 @@ DTOF_DEV PathOut trace_velocity(const DeviceScene &S, const TravPtrs &TP, const 
 //            and operands of :214-226.
 // Only ~a dozen values live across the shadow traversal (instead of the whole surface interaction), which is what
 // lets the kernel run at 4+ CTAs per SM. All lanes of a warp are always in the same phase.
-template <int MODE, bool STATS>
+// DOPPLER = false is the stock path tracer (src/integrators/path.cpp:103-283): no time wrap, modulation weight 1,
+// every draw is Sampler::next_1d / next_2d, i.e. the independent stream only (the path stream does not move).
+template <int MODE, bool STATS, bool DOPPLER>
 DTOF_DEV PathOut trace_path(const DeviceScene &S, const TravPtrs &TP, const dtof_params &P, const Modulation &mod,
                             LaneSampler &smp, bool lane_on, V3 ray_o, V3 ray_d, float ray_maxt, float time_in,
                             Counters &st) {
     PathOut out{ v3(0, 0, 0), 0.f, 0 };
     const uint32_t max_depth = (uint32_t) P.max_depth, rr_depth = (uint32_t) P.rr_depth;   // -1 -> 0xffffffff
-    const float ray_time = time_in < P.time ? time_in : time_in - P.time;                  // dopplertofpath.cpp:93
+    const float ray_time = (!DOPPLER || time_in < P.time) ? time_in : time_in - P.time;    // dopplertofpath.cpp:93
     V3 throughput = v3(1, 1, 1), result = v3(0, 0, 0);
     // eta: every BSDF in scope has eta = 1 on a live path (bs.eta is 0 only where the throughput is 0 too and the
     // lane stops), so `path_length += t * eta`, `eta *= bs.eta` and `rr_prob = tmax * eta^2` reduce to eta == 1.
@@ -121,7 +123,7 @@ DTOF_DEV PathOut trace_path(const DeviceScene &S, const TravPtrs &TP, const dtof
         if (!active)
             continue;
         const bool valid = hit;
-        const bool correlate = (depth + 1) < P.path_correlation_depth;   // :122
+        const bool correlate = DOPPLER && (depth + 1) < P.path_correlation_depth;   // :122
         SI si;
         uint32_t bsdf_flags = 0;
         V3 refl = v3(0, 0, 0);
@@ -150,7 +152,7 @@ DTOF_DEV PathOut trace_path(const DeviceScene &S, const TravPtrs &TP, const dtof
                 em_pdf = (dp < 0.f ? pdf : 0.f) * emitter_pmf;
             }
             float mis_bsdf = mis_weight(prev_bsdf_pdf, em_pdf);
-            float lw = mod.eval(ray_time, path_length);
+            float lw = DOPPLER ? mod.eval(ray_time, path_length) : 1.f;
             V3 Le = (si.wi.z > 0.f && prev_bsdf_pdf > 0.f) ? v3(em.vr, em.vg, em.vb) : v3(0, 0, 0);
             V3 c = Le * mis_bsdf * lw;
             result = v3(fmaf(throughput.x, c.x, result.x), fmaf(throughput.y, c.y, result.y),
@@ -160,8 +162,8 @@ DTOF_DEV PathOut trace_path(const DeviceScene &S, const TravPtrs &TP, const dtof
         const bool smooth = (bsdf_flags & 2u) != 0, twosided = (bsdf_flags & 1u) != 0;
 
         // ---- emitter sampling (:187-202): the 2D sample is always consumed, its value only when needed
-        uint64_t e1a = smp.rng_path.step(), e1b = smp.rng.step();
-        uint64_t e2a = smp.rng_path.step(), e2b = smp.rng.step();
+        uint64_t e1a = DOPPLER ? smp.rng_path.step() : 0ull, e1b = smp.rng.step();
+        uint64_t e2a = DOPPLER ? smp.rng_path.step() : 0ull, e2b = smp.rng.step();
         smp.draws += 2;
         bool active_em = active_next && smooth && n_em > 0, ds_delta = false;
         V3 em_weight = v3(0, 0, 0), wo = v3(0, 0, 0);
@@ -220,8 +222,8 @@ DTOF_DEV PathOut trace_path(const DeviceScene &S, const TravPtrs &TP, const dtof
         }
         // an occluded or zero-pdf emitter sample clears active_em (:190): the term is pending iff want_shadow
         // ---- BSDF eval + sample (:206-210); sample_1 is drawn but unused by the diffuse lobe
-        smp.skip_1d();
-        float s2x = smp.next_1d(correlate), s2y = smp.next_1d(correlate);
+        smp.template skip_1d<DOPPLER>();
+        float s2x = smp.template next_1d<DOPPLER>(correlate), s2y = smp.template next_1d<DOPPLER>(correlate);
         V3 bsdf_val = v3(0, 0, 0), bsdf_weight = v3(0, 0, 0), bs_wo = v3(0, 0, 0);
         float bsdf_pdf = 0.f, bs_pdf = 0.f;                                 // zero-initialised BSDFSample3f
         if (valid && smooth) {
@@ -246,7 +248,7 @@ DTOF_DEV PathOut trace_path(const DeviceScene &S, const TravPtrs &TP, const dtof
         // ---- emitter sampling contribution (:214-226), added in phase 1 if the shadow ray is unoccluded
         if (want_shadow) {
             float mis_em = ds_delta ? 1.f : mis_weight(ds_pdf, bsdf_pdf);
-            float lw = mod.eval(ray_time, path_length + ds_dist);
+            float lw = DOPPLER ? mod.eval(ray_time, path_length + ds_dist) : 1.f;
             c_nee = bsdf_val * em_weight * mis_em * lw;
             thr_nee = throughput;
         }
@@ -268,7 +270,7 @@ DTOF_DEV PathOut trace_path(const DeviceScene &S, const TravPtrs &TP, const dtof
         float tmax = max3(throughput);
         float rr_prob = fminf(tmax, 0.95f);                                 // eta == 1
         bool rr_active = depth >= rr_depth;
-        float q = smp.next_1d(correlate);                                   // always drawn
+        float q = smp.template next_1d<DOPPLER>(correlate);                 // always drawn
         bool rr_continue = q < rr_prob;
         if (rr_active)
             throughput = throughput * frcp(rr_prob);

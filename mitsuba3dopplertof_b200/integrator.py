@@ -24,7 +24,7 @@ import numpy as np
 
 from . import _abi
 
-__all__ = ["DopplerToFPathIntegrator", "VelocityIntegrator", "DTOFError"]
+__all__ = ["DopplerToFPathIntegrator", "VelocityIntegrator", "PathIntegrator", "DTOFError"]
 
 f32 = np.float32
 
@@ -121,6 +121,8 @@ class DopplerToFPathIntegrator:
         p.seed = int(seed) & 0xFFFFFFFF
         p.lane_begin, p.lane_end = int(lane_begin), int(lane_end)
         p.integrator = self.KIND
+        if self.KIND == _abi.INTEGRATOR_DOPPLERTOFPATH and getattr(sampler, "kind", "correlated") != "correlated":
+            raise ValueError("dopplertofpath is driven by the 'correlated' sampler (README.md:61)")
         if self.time_sampling_method == "antithetic_mirror" and p.time_correlate_number != 2:
             raise ValueError("antithetic_mirror requires time_correlate_number == 2")  # correlated.cpp:141-142
         if p.time_correlate_number < 1 or p.path_correlate_number < 1:
@@ -186,4 +188,30 @@ class VelocityIntegrator(DopplerToFPathIntegrator):
 
     def __repr__(self):
         return (f"VelocityIntegrator[\n  max_depth = {self.max_depth & 0xFFFFFFFF},\n"
+                f"  rr_depth = {self.rr_depth}\n]")
+
+
+class PathIntegrator(DopplerToFPathIntegrator):
+    """`path`: the stock path tracer (src/integrators/path.cpp:103-283) the tutorials render the radiance pass with
+    (doppler_tutorials/src/program_runner.py:57-80). The bounce loop is the one `dopplertofpath` was derived from: no
+    modulation weight, no time wrap, every draw is Sampler::next_1d / next_2d, i.e. the sampler's independent stream
+    (identical for `independent` and `correlated`, src/samplers/correlated.cpp:78-90), and render_sample takes the
+    stock branch (src/render/integrator.cpp:409-472). Properties: those of MonteCarloIntegrator / SamplingIntegrator;
+    `time`, `w_g`, ... are not read by the plugin and therefore rejected like the XML loader does."""
+    KIND = _abi.INTEGRATOR_PATH
+    _PATH_PROPS = {"max_depth", "rr_depth", "hide_emitters", "timeout", "block_size", "samples_per_pass",
+                   "time_sampling_method", "antithetic_shift", "use_stratified_sampling_for_each_interval",
+                   "path_correlation_depth", "is_doppler_integrator"}
+
+    def __init__(self, **props):
+        unknown = set(props) - self._PATH_PROPS
+        if unknown:
+            raise ValueError(f"path: unreferenced propert{'ies' if len(unknown) > 1 else 'y'} {sorted(unknown)}")
+        super().__init__(**props)
+        self.is_doppler_integrator = bool(props.get("is_doppler_integrator", False))
+        if self.is_doppler_integrator:
+            raise ValueError("path with is_doppler_integrator=true is outside the hot-path scope")
+
+    def __repr__(self):
+        return (f"PathIntegrator[\n  max_depth = {self.max_depth & 0xFFFFFFFF},\n"
                 f"  rr_depth = {self.rr_depth}\n]")

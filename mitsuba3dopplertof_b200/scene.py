@@ -113,6 +113,7 @@ class CorrelatedSampler:
     seed: int = 0
     time_correlate_number: int = 2
     path_correlate_number: Optional[int] = None
+    kind: str = "correlated"   # "independent": PCG32Sampler only, usable by the non-Doppler integrators (path, velocity)
 
     def __post_init__(self):
         if self.path_correlate_number is None:

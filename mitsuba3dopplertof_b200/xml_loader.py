@@ -16,7 +16,7 @@ from typing import Dict, Optional
 
 import numpy as np
 
-from .integrator import DopplerToFPathIntegrator, VelocityIntegrator
+from .integrator import DopplerToFPathIntegrator, PathIntegrator, VelocityIntegrator
 from .scene import (Bsdf, CorrelatedSampler, Film, PerspectiveSensor, PointLight, Scene, Shape)
 from .transform import AnimatedTransform, Transform4
 
@@ -179,13 +179,17 @@ class _Loader:
             if ch.tag == "transform" and ch.get("name") == "to_world":
                 s.to_world = self.transform(ch)
             elif ch.tag == "sampler":
-                if self.attr(ch, "type") != "correlated":
-                    raise ValueError("dopplertofpath is driven by the 'correlated' sampler (README.md:61)")
+                kind = self.attr(ch, "type")
+                if kind not in ("correlated", "independent"):
+                    raise ValueError(f"sampler '{kind}' is outside the hot-path scope (correlated; independent for path/velocity)")
                 sp = self.props(ch)
-                s.sampler = CorrelatedSampler(int(sp.pop("sample_count", 4)), int(sp.pop("seed", 0)),
-                                              int(sp.pop("time_correlate_number", 2)), sp.pop("path_correlate_number", None))
+                if kind == "independent":   # PCG32Sampler only: the stream `path` / `velocity` draw from (sampler.cpp:115-134)
+                    s.sampler = CorrelatedSampler(int(sp.pop("sample_count", 4)), int(sp.pop("seed", 0)), 1, 1, kind="independent")
+                else:
+                    s.sampler = CorrelatedSampler(int(sp.pop("sample_count", 4)), int(sp.pop("seed", 0)),
+                                                  int(sp.pop("time_correlate_number", 2)), sp.pop("path_correlate_number", None))
                 if sp:   # e.g. use_stratified_sampling_for_each_interval is an INTEGRATOR property
-                    raise ValueError(f"correlated sampler: unreferenced property {sorted(sp)}")
+                    raise ValueError(f"{kind} sampler: unreferenced property {sorted(sp)}")
             elif ch.tag == "film":
                 fp = self.props(ch)
                 f = Film(int(fp.pop("width", 768)), int(fp.pop("height", 576)))
@@ -229,8 +233,10 @@ class _Loader:
                     sc.integrator = DopplerToFPathIntegrator(**self.props(node))
                 elif typ == "velocity":
                     sc.integrator = VelocityIntegrator(**self.props(node))
+                elif typ == "path":
+                    sc.integrator = PathIntegrator(**self.props(node))
                 else:
-                    raise ValueError(f"integrator '{typ}' is outside the hot-path scope (dopplertofpath|velocity)")
+                    raise ValueError(f"integrator '{typ}' is outside the hot-path scope (dopplertofpath|velocity|path)")
             elif node.tag == "sensor":
                 sc.sensor = self.sensor(node)
             elif node.tag == "bsdf":
@@ -261,6 +267,8 @@ class _Loader:
         sc.scene_order = order
         if sc.integrator is None:
             raise ValueError("scene has no integrator")
+        if type(sc.integrator) is DopplerToFPathIntegrator and sc.sensor is not None and sc.sensor.sampler.kind != "correlated":
+            raise ValueError("dopplertofpath is driven by the 'correlated' sampler (README.md:61)")
         return sc
 
 

@@ -239,8 +239,14 @@ struct LaneSampler {
     }
     uint32_t sample_index() const { return pass * spp_pp + idx_mod_spp; } // sampler.cpp:94-103
 
-    // next_1d_correlate, correlated.cpp:156-161: BOTH streams always advance
+    bool stock = false; // true: the integrator calls Sampler::next_1d / next_2d (path, velocity), not *_correlate
+    // next_1d_correlate, correlated.cpp:156-161: BOTH streams always advance;
+    // Sampler::next_1d, correlated.cpp:78-83: the independent stream only
     float next_1d(bool correlate) {
+        if (stock) {
+            draws++;
+            return rng.next_f32();
+        }
         float r1 = rng_path.next_f32();
         float r2 = rng.next_f32();
         draws++;
@@ -858,7 +864,10 @@ PathResult trace_path(const dtof_oracle_scene &sc, const dtof_params &P, const M
         return out;
     uint32_t max_depth = (uint32_t) P.max_depth; // -1 -> 0xffffffff, integrator.cpp:573-577
     uint32_t rr_depth = (uint32_t) P.rr_depth;
-    float ray_time = ray_time_in < P.time ? ray_time_in : ray_time_in - P.time; // :93
+    // PathIntegrator::sample (src/integrators/path.cpp:103-283) is the same loop without the time wrap, without the
+    // modulation weight and with Sampler::next_1d / next_2d draws (LaneSampler::stock)
+    const bool doppler = P.integrator != DTOF_INTEGRATOR_PATH;
+    float ray_time = (!doppler || ray_time_in < P.time) ? ray_time_in : ray_time_in - P.time; // :93
 
     V3 throughput = v3(1, 1, 1), result = v3(0, 0, 0);
     float path_length = 0.f, eta = 1.f;
@@ -873,7 +882,7 @@ PathResult trace_path(const dtof_oracle_scene &sc, const dtof_params &P, const M
 
     // loop.set_max_iterations(m_max_depth) is only a hint; the loop runs while(active)
     while (active) {
-        bool correlate = (depth + 1) < P.path_correlation_depth; // :122
+        bool correlate = doppler && (depth + 1) < P.path_correlation_depth; // :122
 
         Hit h;
         bool valid = intersect_closest(sc, ray_o, ray_d, ray_maxt, ray_time, h, st); // :136
@@ -901,7 +910,7 @@ PathResult trace_path(const dtof_oracle_scene &sc, const dtof_params &P, const M
                 em_pdf = (dp < 0.f ? pdf : 0.f) * emitter_pmf;
             }
             float mis_bsdf = mis_weight(prev_bsdf_pdf, em_pdf);
-            float lw = mod.eval(ray_time, path_length);
+            float lw = doppler ? mod.eval(ray_time, path_length) : 1.f;
             // AreaLight::eval: radiance & (cos_theta(si.wi) > 0), area.cpp:82-89
             V3 Le = (si.wi.z > 0.f && prev_bsdf_pdf > 0.f) ? v3(em.value[0], em.value[1], em.value[2]) : v3(0, 0, 0);
             V3 c = Le * mis_bsdf * lw;
@@ -1016,7 +1025,7 @@ PathResult trace_path(const dtof_oracle_scene &sc, const dtof_params &P, const M
         if (active_em) {
             float mis_em = ds.delta ? 1.f : mis_weight(ds.pdf, bsdf_pdf);
             float em_path_length = path_length + ds.dist;
-            float lw = mod.eval(ray_time, em_path_length);
+            float lw = doppler ? mod.eval(ray_time, em_path_length) : 1.f;
             V3 c = bsdf_val * em_weight * mis_em * lw;
             result = v3(fmaf(throughput.x, c.x, result.x), fmaf(throughput.y, c.y, result.y),
                         fmaf(throughput.z, c.z, result.z));
@@ -1166,10 +1175,12 @@ inline void lane_sample(const dtof_oracle_scene &sc, const dtof_params &P, const
     float off_x = -(float) f.crop_offset_x * scale_x, off_y = -(float) f.crop_offset_y * scale_y;
     float posx = (float) (px + f.crop_offset_x), posy = (float) (py + f.crop_offset_y);
     const bool velocity = P.integrator == DTOF_INTEGRATOR_VELOCITY;
+    const bool stock = P.integrator != DTOF_INTEGRATOR_DOPPLERTOFPATH;
+    smp.stock = stock;
     // a non-Doppler integrator takes the stock branch of render_sample (src/render/integrator.cpp:409-472):
     // Sampler::next_2d / next_1d = the independent stream only (src/samplers/correlated.cpp:78-90)
     float jx, jy;
-    if (velocity) {
+    if (stock) {
         jx = smp.rng.next_f32(), jy = smp.rng.next_f32();
         smp.draws += 2;
     } else {
@@ -1179,7 +1190,7 @@ inline void lane_sample(const dtof_oracle_scene &sc, const dtof_params &P, const
     float ax = fmaf(spx, scale_x, off_x), ay = fmaf(spy, scale_y, off_y);
     float time = sc.cam.shutter_open;
     if (sc.cam.shutter_open_time > 0.f) {
-        if (velocity) {
+        if (stock) {
             time += smp.rng.next_f32() * sc.cam.shutter_open_time;
             smp.draws++;
         } else {

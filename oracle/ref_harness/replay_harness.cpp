@@ -256,12 +256,16 @@ int main(int argc, char **argv) {
             Vector2f pos((float) (px + crop_offset.x()), (float) (py + crop_offset.y()));
             for (uint32_t pass = 0; pass < n_passes; ++pass) {
                 // render_sample() Doppler branch, integrator.cpp:476-509
-                Vector2f sample_pos = pos + Vector2f(sampler->next_2d_correlate(true, correlate_pixel)),
+                // ... or the stock branch (:409-472) for integrators that are not Doppler integrators (path, velocity)
+                const bool doppler = integ->m_is_doppler_integrator;
+                Vector2f sample_pos = pos + (doppler ? Vector2f(sampler->next_2d_correlate(true, correlate_pixel))
+                                                     : Vector2f(sampler->next_2d(true))),
                          adjusted = dr::fmadd(sample_pos, scale, offset);
                 float time = sensor->shutter_open();
                 if (sensor->shutter_open_time() > 0.f)
-                    time += sampler->next_1d_time(true, integ->m_time_sampling_method, integ->m_antithetic_shift,
-                                                  integ->m_use_stratified_sampling_for_each_interval) *
+                    time += (doppler ? sampler->next_1d_time(true, integ->m_time_sampling_method, integ->m_antithetic_shift,
+                                                             integ->m_use_stratified_sampling_for_each_interval)
+                                     : sampler->next_1d(true)) *
                             sensor->shutter_open_time();
                 auto [ray, ray_weight] = sensor->sample_ray_differential(time, 0.f, Point2f(adjusted), Point2f(.5f));
                 if (getenv("DTOF_DEBUG")) {

@@ -53,6 +53,24 @@ CASES = {
     "c5_slabroom_full_sin": ("c5_slabroom", {"lowpass": "false", "wave": "sinusoidal", "hetero_frequency": 0.0}, 2, False),
     "c5_slabroom_lowpass": ("c5_slabroom", {}, 0, True),
 }
+# the stock path tracer (src/integrators/path.cpp) on the same scenes: the integrator element is swapped (golden_util.swap_integrator)
+PATH_CASES = {
+    "path_c1": ("c1_example", {}, 0, True),
+    "path_c2_arealight": ("c2_arealight", {"resx": 512, "resy": 512}, 0, True),
+    "path_c2b_rr": ("c2b_two_emitters", {"max_depth": 16, "rr_depth": 2}, 5, True),
+    "path_c3_rotor": ("c3_rotor", {"resx": 512, "resy": 512, "spp": 64}, 2, True),
+    "path_c5_slabroom": ("c5_slabroom", {}, 1, True),
+}
+# the ground-truth radial velocity integrator (src/integrators/velocity.cpp). Its value (t2 - t1) / time scales by exactly
+# 2^20 under the time scaling; golden_util.load_case undoes it.
+VELOCITY_CASES = {
+    "velocity_c1": ("c1_example", {}, 0, True),
+    "velocity_c3_rotor": ("c3_rotor", {"resx": 512, "resy": 512, "spp": 64}, 1, True),
+    "velocity_c4_domino": ("c4_domino", {"resx": 512, "resy": 512, "spp": 64}, 2, True),
+}
+CASES.update(PATH_CASES)
+CASES.update(VELOCITY_CASES)
+SWAPPED = dict({k: "path" for k in PATH_CASES}, **{k: "velocity" for k in VELOCITY_CASES})
 DEFAULTS = {"spp": 1024, "resx": 256, "resy": 256, "max_depth": 4, "tcn": 2, "pcn": 2}
 N_PIXELS = 48
 
@@ -84,17 +102,28 @@ def run_case(name):
         f.write("\n".join(map(str, lanes)) + "\n")
     p = dict(DEFAULTS, **params)
     tval = T * SCALE if scaled else T
-    cmd = [os.path.join(REF_RT, "replay_harness"), os.path.join(SCENES, scene + ".xml"), "--seed", str(seed),
+    scene_file = os.path.join(SCENES, scene + ".xml")
+    if name in SWAPPED:
+        sys.path[:0] = [os.path.dirname(HERE), ROOT]
+        import golden_util
+        scene_file = os.path.join(SCENES, f"_tmp_{name}.xml")   # next to the .ply files it references
+        with open(scene_file, "w") as f:
+            f.write(golden_util.swap_integrator(open(os.path.join(SCENES, scene + ".xml")).read(), SWAPPED[name]))
+    cmd = [os.path.join(REF_RT, "replay_harness"), scene_file, "--seed", str(seed),
            "--tcn", str(p["tcn"]), "--pcn", str(p["pcn"]), "--lanes", lanes_file, f"-DT={tval:.9g}"]
+    if name in VELOCITY_CASES:   # the integrator's own `time`: 0.75 T (golden_util.swap_integrator), scaled like T
+        cmd.append(f"-DTvel={np.float32(0.001125) * (SCALE if scaled else np.float32(1)):.9g}")
     for k, v in params.items():
         cmd.append(f"-D{k}={v}")
     env = dict(os.environ, LD_LIBRARY_PATH=REF_RT, DTOF_REF_DIR=REF_RT)
     out = subprocess.run(cmd, check=True, capture_output=True, text=True, env=env).stdout.splitlines()
+    if name in SWAPPED:
+        os.remove(scene_file)
     rows = [l.split() for l in out if l and l[0].isdigit()]
     rows = [r for r in rows if int(r[1]) == 0]    # pass 0 only (later passes are not JIT-faithful in scalar mode)
     assert len(rows) == len(lanes), (len(rows), len(lanes))
     rec = {
-        "scene": scene + ".xml", "xml_params": params, "seed": seed, "time_scale": float(SCALE) if scaled else 1.0,
+        "scene": scene + ".xml", "integrator": SWAPPED.get(name, "dopplertofpath"), "xml_params": params, "seed": seed, "time_scale": float(SCALE) if scaled else 1.0,
         "header": [l for l in out if l.startswith("#")][0],
         "columns": "idx px py sample_pos.x sample_pos.y time ray_o(3) ray_d(3) ray_maxt R G B",
         "lanes": [int(r[0]) for r in rows],

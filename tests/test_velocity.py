@@ -1,7 +1,8 @@
 """`velocity` integrator (reference: src/integrators/velocity.cpp:87-127).
 
-The reference has no test or artefact for it and the fixture harness needs the reference runtime, so parity is pinned
-by (a) an analytic property of the example scene (its two cubes translate by -/+0.015 along z in 1.5 ms while the
+The reference has no test or artefact for it, so parity is pinned by (0) per-lane values of the reference's own
+VelocityIntegrator::sample driven by the JIT-variant sample streams (tests/golden/lanes_velocity_*.json,
+tests/golden/make_golden.py), (a) an analytic property of the example scene (its two cubes translate by -/+0.015 along z in 1.5 ms while the
 camera looks down -z, so the radial velocity of every visible box face is +/-10 up to the cosine of the pixel's
 viewing angle; static walls give exactly 0) and (b) CUDA == oracle on identical sample streams."""
 import os
@@ -78,3 +79,37 @@ def test_velocity_cuda_matches_oracle():
     ref = oracle_lib.OracleScene(flat).render(params, develop=False)
     assert np.abs(rgbw[..., 3] - ref[..., 3]).max() <= 1e-4 * ref[..., 3].max()
     assert np.abs(rgbw[..., :3] - ref[..., :3]).max() <= 2e-3 * np.abs(ref[..., :3]).max()
+
+
+# ---- reference-generated fixtures -----------------------------------------------------------------------------------
+# (t2 - t1) / time amplifies a 1-ulp difference of a hit distance (t ~ 5-7 -> ulp 4.8e-7) to 3e-4; Embree's
+# watertight triangle test and the Moeller-Trumbore of the path agree to ~2 ulp of t, so |dv| <= 1.5e-3 (v ~ 10).
+VEL_TOL = 1.5e-3
+
+
+def _check_velocity(rec, ref):
+    np.testing.assert_allclose(rec["sample_pos"], ref["sample_pos"], rtol=0, atol=1e-4)
+    np.testing.assert_allclose(rec["time"], ref["time"], rtol=2e-6, atol=1e-12)
+    np.testing.assert_allclose(rec["ray_d"], ref["ray_d"], rtol=0, atol=2e-6)
+    d = np.abs(rec["rgb"].astype(np.float64) - ref["rgb"]).max(axis=1)
+    # silhouette samples (a hit at one time, a miss at the other) are edge decisions: allow 1 %
+    assert (d <= VEL_TOL).mean() >= 0.99, np.sort(d)[-5:]
+
+
+@pytest.mark.parametrize("name", gu.case_names("velocity"))
+def test_velocity_oracle_matches_reference_lanes(name):
+    scene, params, ref = gu.load_case(name)
+    assert params.integrator == 1
+    rec = oracle_lib.OracleScene(scene.flatten(), 0).trace(params, ref["lanes"])
+    _check_velocity(rec, ref)
+    assert (np.abs(ref["rgb"]) > 0.05).any()           # the fixture does see moving geometry
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", gu.case_names("velocity"))
+def test_velocity_cuda_matches_reference_lanes(name):
+    from mitsuba3dopplertof_b200 import runtime
+    scene, params, ref = gu.load_case(name)
+    ctx = runtime.Context(0)
+    ctx.upload(scene)
+    _check_velocity(ctx.trace_samples(params, ref["lanes"]), ref)
