@@ -11,7 +11,9 @@
 set -euo pipefail
 REF=${REF:-/root/reference}
 BUILD=${BUILD:-/tmp/refbuild}
-OUT="$(cd "$(dirname "$0")/../_ref" 2>/dev/null && pwd || (mkdir -p "$(dirname "$0")/../_ref" && cd "$(dirname "$0")/../_ref" && pwd))"
+HERE="$(cd "$(dirname "$0")" && pwd)"
+mkdir -p "$HERE/../_ref"
+OUT="$(cd "$HERE/../_ref" && pwd)"
 mkdir -p "$BUILD" && cd "$BUILD"
 cat > noipo.cmake <<'EOC'
 set(CMAKE_C_COMPILE_OPTIONS_IPO "")
@@ -24,5 +26,5 @@ cmake -G Ninja "$REF" -DCMAKE_BUILD_TYPE=Release -DMI_ENABLE_PYTHON=OFF -DMI_DEF
       -DCMAKE_PROJECT_INCLUDE="$BUILD/noipo.cmake"
 ninja -j"${JOBS:-6}"
 cp -a mitsuba lib*.so plugins include "$OUT"/
-make -C "$(dirname "$0")"        # replay_harness, header_vectors, plugins/dopplertofpath_b200.so
+make -C "$HERE"        # replay_harness, header_vectors, plugins/dopplertofpath_b200.so
 echo "reference runtime + harness + plugin in $OUT"
