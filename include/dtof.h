@@ -299,6 +299,12 @@ dtof_status dtof_get_stats(dtof_ctx *ctx, dtof_stats *out);
  * memory, 2 = flat warp-coherent walk over all triangles in shared memory (tiny scenes); -1 = nothing rendered yet. */
 int dtof_last_traversal_mode(const dtof_ctx *ctx);
 
+/* Pipeline the last render ran through: 0 = fused kernel (one lane owns one path in registers), 1 = wavefront
+ * pipeline (generate / trace with dynamic ray fetch / shade / shadow / splat kernels exchanging compacted queues
+ * through HBM; chosen when the BVH is walked from HBM). The environment variable DTOF_WAVEFRONT=0|1 overrides the
+ * choice; per-lane results are identical in both. -1 = nothing rendered yet. */
+int dtof_last_pipeline(const dtof_ctx *ctx);
+
 /* Number of kernels this library launched on this context since creation (bench.py's gpu_launches). */
 uint64_t dtof_launch_count(const dtof_ctx *ctx);
 

@@ -147,6 +147,7 @@ DTOF_SYMBOLS = {
     "dtof_set_stats": (C.c_int, [_ctx, C.c_int]),
     "dtof_get_stats": (C.c_int, [_ctx, C.POINTER(Stats)]),
     "dtof_last_traversal_mode": (C.c_int, [_ctx]),
+    "dtof_last_pipeline": (C.c_int, [_ctx]),
     "dtof_launch_count": (C.c_uint64, [_ctx]),
     "dtof_last_kernel_ms": (C.c_int, [_ctx, C.POINTER(C.c_float)]),
 }

@@ -22,6 +22,7 @@
 #include "dtof_device.cuh"
 #include "dtof_layout.h"
 #include "dtof_path.cuh"
+#include "dtof_wavefront.cuh"
 
 using namespace dtof;
 
@@ -249,6 +250,12 @@ struct dtof_ctx {
     bool have_timing = false;
     int sm_count = 148;
     size_t smem_optin = 0;
+    // wavefront pipeline (dtof_wavefront.cuh): queues and per-lane path state for one batch of lanes
+    WfBuffers wf{};
+    void *wf_block = nullptr;
+    size_t wf_cap = 0;
+    uint32_t *wf_host_count = nullptr;   // pinned
+    int last_pipeline = 0;               // 0 = fused kernel, 1 = wavefront
 };
 
 namespace {
@@ -398,6 +405,143 @@ dtof_status launch_mode(dtof_ctx *ctx, RenderArgs &A, bool record, int grid, cud
                               : launch_variant<MODE, false, false, DTOF_INTEGRATOR_DOPPLERTOFPATH>(ctx, A, grid, stream);
 }
 
+// ---- wavefront pipeline (dtof_wavefront.cuh) ------------------------------------------------------------------
+constexpr size_t kWfDefaultBatch = 1u << 23;   // lanes per batch: 8 Mi lanes x ~260 B of queues and state = 2.1 GiB
+
+void free_wavefront(dtof_ctx *c) {
+    if (c->wf_block)
+        cudaFree(c->wf_block);
+    c->wf_block = nullptr;
+    c->wf_cap = 0;
+    c->wf = WfBuffers{};
+}
+
+// One allocation, carved into the SoA arrays of WfBuffers (every array 256-byte aligned).
+dtof_status ensure_wavefront(dtof_ctx *ctx, size_t cap) {
+    if (ctx->wf_cap >= cap)
+        return DTOF_OK;
+    free_wavefront(ctx);
+    size_t off = 0;
+    auto carve = [&](size_t elem) {
+        size_t at = off;
+        off += (cap * elem + 255) / 256 * 256;
+        return at;
+    };
+    const size_t o_rng = carve(16), o_rngp = carve(16), o_thr = carve(16), o_res = carve(16), o_prev = carve(16),
+                 o_film = carve(8), o_qo0 = carve(16), o_qo1 = carve(16), o_qd0 = carve(16), o_qd1 = carve(16),
+                 o_ql0 = carve(4), o_ql1 = carve(4), o_hit = carve(16), o_hi = carve(4), o_so = carve(16), o_sd = carve(16),
+                 o_st = carve(16), o_sc = carve(16), o_sl = carve(4);
+    const size_t o_ring = off;
+    off += 256;
+    if (cudaMalloc(&ctx->wf_block, off) != cudaSuccess) {
+        ctx->wf_block = nullptr;
+        return fail(ctx, DTOF_ERR_NOMEM, "cudaMalloc of %zu bytes of wavefront queues failed", off);
+    }
+    if (!ctx->wf_host_count && cudaMallocHost(&ctx->wf_host_count, 64) != cudaSuccess)
+        return fail(ctx, DTOF_ERR_NOMEM, "cudaMallocHost failed");
+    char *b = (char *) ctx->wf_block;
+    WfBuffers &W = ctx->wf;
+    W.rng = (ulonglong2 *) (b + o_rng), W.rng_path = (ulonglong2 *) (b + o_rngp);
+    W.thr_len = (float4 *) (b + o_thr), W.res_pdf = (float4 *) (b + o_res), W.prev_meta = (float4 *) (b + o_prev);
+    W.film_pos = (float2 *) (b + o_film);
+    W.q_o[0] = (float4 *) (b + o_qo0), W.q_o[1] = (float4 *) (b + o_qo1);
+    W.q_d[0] = (float4 *) (b + o_qd0), W.q_d[1] = (float4 *) (b + o_qd1);
+    W.q_lane[0] = (uint32_t *) (b + o_ql0), W.q_lane[1] = (uint32_t *) (b + o_ql1);
+    W.hit = (float4 *) (b + o_hit), W.hit_inst = (int32_t *) (b + o_hi);
+    W.s_o = (float4 *) (b + o_so), W.s_d = (float4 *) (b + o_sd), W.s_thr = (float4 *) (b + o_st), W.s_c = (float4 *) (b + o_sc);
+    W.s_lane = (uint32_t *) (b + o_sl);
+    W.ring = (uint32_t *) (b + o_ring);
+    ctx->wf_cap = cap;
+    return DTOF_OK;
+}
+
+template <int MODE, bool ANY> dtof_status launch_wf_trace(dtof_ctx *ctx, const WfArgs &W, int grid, size_t smem, cudaStream_t stream) {
+    auto k = wf_trace_kernel<MODE, ANY>;
+    if (smem)
+        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    k<<<grid, kWfBlock, smem, stream>>>(W);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return DTOF_OK;
+}
+
+// Renders the lanes of `A` (all passes) through the wavefront pipeline. `mode` is MODE_BVH_GLOBAL or MODE_BVH_SMEM.
+dtof_status launch_wavefront(dtof_ctx *ctx, const RenderArgs &A, int mode, cudaStream_t stream) {
+    size_t batch = kWfDefaultBatch;
+    if (const char *e = getenv("DTOF_WF_BATCH"))
+        batch = std::max<size_t>(1024, (size_t) atoll(e));
+    uint32_t threshold = 24;
+    if (const char *e = getenv("DTOF_WF_THRESHOLD"))
+        threshold = (uint32_t) atoi(e);
+    const size_t cap = (size_t) std::min<unsigned long long>(A.n_local, batch);
+    if (cap == 0)
+        return DTOF_OK;
+    dtof_status s = ensure_wavefront(ctx, cap);
+    if (s != DTOF_OK)
+        return s;
+    WfArgs W{};
+    W.scene = A.scene, W.cam = A.cam, W.film = A.film, W.p = A.p, W.mod = A.mod, W.buf = ctx->wf;
+    W.spp_per_pass = A.spp_per_pass;
+    W.lane_begin = A.lane_begin, W.shard_block = A.shard_block, W.shard_count = A.shard_count, W.shard_index = A.shard_index;
+    W.fetch_threshold = threshold;
+    W.inner_threshold = 16;
+    if (const char *e = getenv("DTOF_WF_INNER"))
+        W.inner_threshold = (uint32_t) atoi(e);
+    W.nodes_bytes = A.nodes_bytes, W.tris_bytes = A.tris_bytes, W.insts_bytes = A.insts_bytes;
+    const bool doppler = A.p.integrator == DTOF_INTEGRATOR_DOPPLERTOFPATH;
+    const size_t smem = mode == MODE_BVH_SMEM ? (size_t) A.nodes_bytes + A.tris_bytes + A.insts_bytes : 0;
+    const int trace_grid = ctx->sm_count * DTOF_WF_TRACE_CTAS, shade_grid = ctx->sm_count * DTOF_WF_SHADE_CTAS,
+              stream_grid = ctx->sm_count * 8;
+    const bool bounded = A.p.max_depth >= 0;
+    for (unsigned long long begin = 0; begin < A.n_local; begin += cap) {
+        W.batch_begin = begin;
+        W.n_slots = (uint32_t) std::min<unsigned long long>(cap, A.n_local - begin);
+        for (uint32_t pass = 0; pass < A.n_passes; ++pass) {
+            W.pass = pass;
+            W.bounce = 0;
+            CU(cudaMemsetAsync(ctx->wf.ring, 0, kWfRing * 4 * sizeof(uint32_t), stream));
+            if (doppler)
+                wf_generate_kernel<DTOF_INTEGRATOR_DOPPLERTOFPATH><<<stream_grid, kWfBlock, 0, stream>>>(W);
+            else
+                wf_generate_kernel<DTOF_INTEGRATOR_PATH><<<stream_grid, kWfBlock, 0, stream>>>(W);
+            ctx->launches++;
+            CU(cudaGetLastError());
+            for (uint32_t b = 0; !bounded || b < (uint32_t) A.p.max_depth; ++b) {
+                W.bounce = b;
+                if (b + 1 >= (uint32_t) kWfRing)   // recycle the ring slot the next bounce will count into
+                    CU(cudaMemsetAsync(ctx->wf.ring + 4 * ((b + 1) % kWfRing), 0, 4 * sizeof(uint32_t), stream));
+                s = mode == MODE_BVH_SMEM ? launch_wf_trace<MODE_BVH_SMEM, false>(ctx, W, trace_grid, smem, stream)
+                                          : launch_wf_trace<MODE_BVH_GLOBAL, false>(ctx, W, trace_grid, 0, stream);
+                if (s != DTOF_OK)
+                    return s;
+                if (doppler)
+                    wf_shade_kernel<true><<<shade_grid, kWfBlock, 0, stream>>>(W);
+                else
+                    wf_shade_kernel<false><<<shade_grid, kWfBlock, 0, stream>>>(W);
+                ctx->launches++;
+                CU(cudaGetLastError());
+                s = mode == MODE_BVH_SMEM ? launch_wf_trace<MODE_BVH_SMEM, true>(ctx, W, trace_grid, smem, stream)
+                                          : launch_wf_trace<MODE_BVH_GLOBAL, true>(ctx, W, trace_grid, 0, stream);
+                if (s != DTOF_OK)
+                    return s;
+                // bounded depth: every bounce is enqueued blind (an empty queue costs one idle launch). Unbounded or
+                // deep paths (Russian roulette ends them): from the 8th bounce on, look at the next queue's length.
+                if (b >= 7 && (!bounded || (uint32_t) A.p.max_depth > 8)) {
+                    CU(cudaMemcpyAsync(ctx->wf_host_count, ctx->wf.ring + 4 * ((b + 1) % kWfRing), sizeof(uint32_t),
+                                       cudaMemcpyDeviceToHost, stream));
+                    CU(cudaStreamSynchronize(stream));
+                    if (*ctx->wf_host_count == 0)
+                        break;
+                }
+            }
+            wf_splat_kernel<<<stream_grid, kWfBlock, 0, stream>>>(W);
+            ctx->launches++;
+            CU(cudaGetLastError());
+        }
+    }
+    return DTOF_OK;
+}
+
 dtof_status launch_render(dtof_ctx *ctx, const dtof_params *p, float *d_rgbw, cudaStream_t stream,
                           const unsigned long long *d_lanes, dtof_sample_record *d_rec, uint32_t n_rec) {
     dtof_pass_info pi;
@@ -479,6 +623,25 @@ dtof_status launch_render(dtof_ctx *ctx, const dtof_params *p, float *d_rgbw, cu
         CU(cudaMemsetAsync(ctx->d_stats, 0, sizeof(Counters), stream));
     CU(cudaEventRecord(ctx->ev0, stream));
     dtof_status s;
+    // ---- pipeline: the wavefront pipeline with dynamic ray fetch where the BVH is walked from HBM (divergent
+    // traversal lengths), the fused kernel for shared-memory scenes, record / stats runs and the velocity integrator.
+    // DTOF_WAVEFRONT=0 / 1 forces the choice (1 also for shared-memory scenes).
+    int wavefront = mode == MODE_BVH_GLOBAL ? 1 : 0;
+    if (const char *e = getenv("DTOF_WAVEFRONT"))
+        wavefront = atoi(e);
+    if (record || ctx->stats_enabled || p->integrator == DTOF_INTEGRATOR_VELOCITY || mode == MODE_FLAT_SMEM ||
+        !ctx->ds.has_geometry)
+        wavefront = 0;
+    ctx->last_pipeline = wavefront;
+    if (wavefront) {
+        if ((s = launch_wavefront(ctx, A, mode, stream)) != DTOF_OK)
+            return s;
+        ctx->last_mode = mode;
+        CU(cudaEventRecord(ctx->ev1, stream));
+        ctx->last_stream = stream;
+        ctx->have_timing = true;
+        return DTOF_OK;
+    }
     if (mode == MODE_FLAT_SMEM)
         s = launch_mode<MODE_FLAT_SMEM>(ctx, A, record, grid, stream);
     else if (mode == MODE_BVH_SMEM)
@@ -723,6 +886,8 @@ void dtof_destroy(dtof_ctx *ctx) {
         return;
     cudaSetDevice(ctx->device);
     free_scene(ctx);
+    free_wavefront(ctx);
+    if (ctx->wf_host_count) cudaFreeHost(ctx->wf_host_count);
     if (ctx->d_counter) cudaFree(ctx->d_counter);
     if (ctx->d_stats) cudaFree(ctx->d_stats);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -1003,6 +1168,8 @@ dtof_status dtof_get_stats(dtof_ctx *ctx, dtof_stats *out) {
 }
 
 int dtof_last_traversal_mode(const dtof_ctx *ctx) { return ctx ? ctx->last_mode : -1; }
+
+int dtof_last_pipeline(const dtof_ctx *ctx) { return ctx && ctx->have_timing ? ctx->last_pipeline : -1; }
 
 uint64_t dtof_launch_count(const dtof_ctx *ctx) { return ctx ? ctx->launches : 0; }
 

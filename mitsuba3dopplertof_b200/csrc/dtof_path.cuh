@@ -63,222 +63,256 @@ DTOF_DEV PathOut trace_velocity(const DeviceScene &S, const TravPtrs &TP, const 
     return out;
 }
 
+// Per-lane state of one path between bounces: the loop-carried variables of DopplerToFPathIntegrator::sample
+// (dopplertofpath.cpp:95-121). The fused kernel keeps it in registers for the whole path; the wavefront pipeline
+// (dtof_wavefront.cuh) stores it in HBM between the stages of a bounce.
+struct PathState {
+    V3 throughput, result, prev_p;
+    float path_length, prev_bsdf_pdf;
+    uint32_t depth;
+    bool valid_ray, prev_bsdf_delta, active;
+    // eta: every BSDF in scope has eta = 1 on a live path (bs.eta is 0 only where the throughput is 0 too and the
+    // lane stops), so `path_length += t * eta`, `eta *= bs.eta` and `rr_prob = tmax * eta^2` reduce to eta == 1.
+    DTOF_DEV void init(bool on) {
+        throughput = v3(1, 1, 1), result = v3(0, 0, 0), prev_p = v3(0, 0, 0);
+        path_length = 0.f, prev_bsdf_pdf = 1.f;
+        depth = 0;
+        valid_ray = false;                        // no environment emitter in scope (:102)
+        prev_bsdf_delta = true;
+        active = on;
+    }
+};
+
+// The emitter-sampling term of a bounce, pending until its shadow ray has been traced (:214-226)
+struct PendingNee {
+    bool want;
+    V3 thr, c, o, d;
+    float maxt;
+};
+
+// One iteration of the reference's loop body (:136-276) for a lane whose path ray has been traced: interaction,
+// emission, emitter sampling, BSDF eval + sample, next ray, throughput, Russian roulette. Nothing in it depends on
+// the shadow ray except whether the emitter-sampling term is added, and the shadow ray draws no random numbers, so
+// that term is returned as a pending contribution. `ray_o/ray_d/ray_maxt` hold the traced ray on entry and the next
+// path ray on exit.
+// DOPPLER = false is the stock path tracer (src/integrators/path.cpp:103-283): no time wrap, modulation weight 1,
+// every draw is Sampler::next_1d / next_2d, i.e. the independent stream only (the path stream does not move).
+template <bool DOPPLER>
+DTOF_DEV void shade_bounce(const DeviceScene &S, const float4 *__restrict__ I, const dtof_params &P, const Modulation &mod,
+                           LaneSampler &smp, PathState &ps, const bool hit, const Hit &h, V3 &ray_o, V3 &ray_d,
+                           float &ray_maxt, const float ray_time, const float emitter_pmf, PendingNee &nee) {
+    const uint32_t max_depth = (uint32_t) P.max_depth, rr_depth = (uint32_t) P.rr_depth;   // -1 -> 0xffffffff
+    const uint32_t n_em = S.n_emitters;
+    V3 &throughput = ps.throughput, &result = ps.result;
+    float &path_length = ps.path_length;
+    uint32_t &depth = ps.depth;
+    nee.want = false;
+    const bool valid = hit;
+    const bool correlate = DOPPLER && (depth + 1) < P.path_correlation_depth;   // :122
+    SI si;
+    uint32_t bsdf_flags = 0;
+    V3 refl = v3(0, 0, 0);
+    int32_t mesh_emitter = -1;
+    if (valid) {
+        compute_si(S, I, h, ray_d, ray_time, si);
+        const MeshRec &mr = S.meshes[si.mesh];
+        mesh_emitter = mr.emitter;
+        const BsdfRec br = S.bsdfs[mr.bsdf];
+        bsdf_flags = br.flags;
+        refl = v3(br.r, br.g, br.b);
+        path_length += h.t;                                             // :141 (eta == 1)
+    }
+    // ---- direct emission (:150-168)
+    if (valid && mesh_emitter >= 0) {
+        const MeshRec &em_mesh = S.meshes[si.mesh];
+        const EmitterRec em = S.emitters[mesh_emitter];
+        V3 rel = si.p - ps.prev_p;                                      // DirectionSample(scene, si, prev_si)
+        float dist = fsqrt(dot3(rel, rel));
+        V3 dsd = rel / dist;
+        float em_pdf = 0.f;
+        if (!ps.prev_bsdf_delta) {                                      // AreaLight::pdf_direction, area.cpp:148-166
+            float dp = dot3(dsd, si.sh_n);
+            float pdf = em_mesh.inv_area, adp = fabsf(dp);
+            pdf *= adp != 0.f ? fdiv(dist * dist, adp) : 0.f;
+            em_pdf = (dp < 0.f ? pdf : 0.f) * emitter_pmf;
+        }
+        float mis_bsdf = mis_weight(ps.prev_bsdf_pdf, em_pdf);
+        float lw = DOPPLER ? mod.eval(ray_time, path_length) : 1.f;
+        V3 Le = (si.wi.z > 0.f && ps.prev_bsdf_pdf > 0.f) ? v3(em.vr, em.vg, em.vb) : v3(0, 0, 0);
+        V3 c = Le * mis_bsdf * lw;
+        result = v3(fmaf(throughput.x, c.x, result.x), fmaf(throughput.y, c.y, result.y),
+                    fmaf(throughput.z, c.z, result.z));
+    }
+    const bool active_next = (depth + 1 < max_depth) && valid;         // :171
+    const bool smooth = (bsdf_flags & 2u) != 0, twosided = (bsdf_flags & 1u) != 0;
+
+    // ---- emitter sampling (:187-202): the 2D sample is always consumed, its value only when needed
+    uint64_t e1a = DOPPLER ? smp.rng_path.step() : 0ull, e1b = smp.rng.step();
+    uint64_t e2a = DOPPLER ? smp.rng_path.step() : 0ull, e2b = smp.rng.step();
+    smp.draws += 2;
+    bool active_em = active_next && smooth && n_em > 0, ds_delta = false;
+    V3 em_weight = v3(0, 0, 0), wo = v3(0, 0, 0);
+    float ds_dist = 0.f, ds_pdf = 0.f;
+    if (active_em) {
+        uint32_t index = 0;
+        float sx = 0.f, sy = 0.f;
+        V3 ds_p, ds_n, spec, ds_d;
+        EmitterRec em = S.emitters[0];
+        if (n_em > 1 || em.kind != DTOF_EMITTER_POINT) {
+            sx = u32_to_float(pcg_output(correlate ? e1a : e1b));
+            sy = u32_to_float(pcg_output(correlate ? e2a : e2b));
+        }
+        if (n_em > 1) {                                                 // Scene::sample_emitter, scene.cpp:171-189
+            float scaled = sx * (float) n_em;
+            index = min((uint32_t) scaled, n_em - 1u);
+            sx = scaled - (float) index;
+            em = S.emitters[index];
+        }
+        if (em.kind == DTOF_EMITTER_POINT) {                            // PointLight::sample_direction, point.cpp:118-147
+            ds_p = v3(em.px, em.py, em.pz);
+            ds_pdf = 1.f;
+            ds_delta = true;
+            ds_d = ds_p - si.p;
+            float dist2 = dot3(ds_d, ds_d), inv_dist = rsqrt_ieee(dist2);
+            ds_dist = fsqrt(dist2);
+            ds_d = ds_d * inv_dist;
+            float f = inv_dist * inv_dist;
+            spec = v3(em.vr * f, em.vg * f, em.vb * f);
+        } else {                                                        // AreaLight / Shape::sample_direction
+            sample_position(S, S.meshes[em.mesh], sx, sy, ds_p, ds_n, ds_pdf);
+            ds_d = ds_p - si.p;
+            float dist2 = dot3(ds_d, ds_d);
+            ds_dist = fsqrt(dist2);
+            ds_d = ds_d / ds_dist;
+            float dp = fabsf(dot3(ds_d, ds_n));
+            float x = fdiv(dist2, dp);
+            ds_pdf *= isfinite(x) ? x : 0.f;
+            bool em_active = dot3(ds_d, ds_n) < 0.f && ds_pdf != 0.f;
+            spec = em_active ? v3(em.vr, em.vg, em.vb) / ds_pdf : v3(0, 0, 0);
+        }
+        if (n_em > 1) {
+            ds_pdf *= emitter_pmf;
+            spec = spec * (float) n_em;
+        }
+        em_weight = spec;
+        if (ds_pdf != 0.f) {                                            // spawn_ray_to, interaction.h:141-148
+            nee.o = offset_p(si.p, si.n, ds_p - si.p);
+            nee.d = ds_p - nee.o;
+            float dist = fsqrt(dot3(nee.d, nee.d));
+            nee.d = nee.d / dist;
+            nee.maxt = dist * (1.f - kShadowEps);
+            nee.want = true;
+        }
+        wo = v3(dot3(ds_d, si.sh_s), dot3(ds_d, si.sh_t), dot3(ds_d, si.sh_n));
+    }
+    // an occluded or zero-pdf emitter sample clears active_em (:190): the term is pending iff nee.want
+    // ---- BSDF eval + sample (:206-210); sample_1 is drawn but unused by the diffuse lobe
+    smp.template skip_1d<DOPPLER>();
+    float s2x = smp.template next_1d<DOPPLER>(correlate), s2y = smp.template next_1d<DOPPLER>(correlate);
+    V3 bsdf_val = v3(0, 0, 0), bsdf_weight = v3(0, 0, 0), bs_wo = v3(0, 0, 0);
+    float bsdf_pdf = 0.f, bs_pdf = 0.f;                                 // zero-initialised BSDFSample3f
+    if (valid && smooth) {
+        float wi_z = si.wi.z, wo_z = wo.z;
+        if (twosided) {                                                 // TwoSidedBRDF, twosided.cpp:111-125,219-235
+            wo_z = mulsign(wo_z, wi_z);
+            wi_z = fabsf(wi_z);
+        }
+        if (wi_z > 0.f && wo_z > 0.f) {                                 // SmoothDiffuse::eval_pdf, diffuse.cpp:160-176
+            bsdf_val = refl * kInvPi * wo_z;
+            bsdf_pdf = kInvPi * wo_z;
+        }
+        if (wi_z > 0.f) {                                               // SmoothDiffuse::sample, diffuse.cpp:101-125
+            bs_wo = square_to_cosine_hemisphere(s2x, s2y);
+            bs_pdf = kInvPi * bs_wo.z;
+            if (bs_pdf > 0.f)
+                bsdf_weight = refl;
+            if (twosided)
+                bs_wo.z = mulsign(bs_wo.z, si.wi.z);
+        }
+    }
+    // ---- emitter sampling contribution (:214-226), added once the shadow ray is known to be unoccluded
+    if (nee.want) {
+        float mis_em = ds_delta ? 1.f : mis_weight(ds_pdf, bsdf_pdf);
+        float lw = DOPPLER ? mod.eval(ray_time, path_length + ds_dist) : 1.f;
+        nee.c = bsdf_val * em_weight * mis_em * lw;
+        nee.thr = throughput;
+    }
+    // ---- BSDF sampling (:230-251)
+    if (valid) {
+        V3 wd = fma3(si.sh_n, bs_wo.z, fma3(si.sh_t, bs_wo.y, si.sh_s * bs_wo.x));
+        ray_o = offset_p(si.p, si.n, wd);
+        ray_d = wd;
+        ray_maxt = 3.402823466e+38f;
+        ps.prev_p = si.p;
+    }
+    throughput = throughput * bsdf_weight;
+    ps.valid_ray = ps.valid_ray || valid;                               // :253-254
+    ps.prev_bsdf_pdf = bs_pdf;
+    ps.prev_bsdf_delta = false;
+    // ---- stopping criterion (:262-276)
+    if (valid)
+        depth += 1;
+    float tmax = max3(throughput);
+    float rr_prob = fminf(tmax, 0.95f);                                 // eta == 1
+    bool rr_active = depth >= rr_depth;
+    float q = smp.template next_1d<DOPPLER>(correlate);                 // always drawn
+    bool rr_continue = q < rr_prob;
+    if (rr_active)
+        throughput = throughput * frcp(rr_prob);
+    ps.active = active_next && (!rr_active || rr_continue) && tmax != 0.f;
+}
+
 // Must be called by all 32 lanes of a warp; `lane_on` masks lanes without a sample.
 //
 // The loop body is a two-phase state machine around ONE inlined traversal (a single copy of the traversal code keeps
 // the kernel's instruction footprint down):
-//   phase 0  trace the path ray (closest hit), then run the reference's WHOLE loop body (:136-276): interaction,
-//            emission, emitter sampling, BSDF eval + sample, next ray, throughput, Russian roulette. Nothing in it
-//            depends on the shadow ray except whether the emitter-sampling term is added, and the shadow ray draws
-//            no random numbers, so that term is kept as a pending contribution (thr_nee, c_nee).
+//   phase 0  trace the path ray (closest hit), then run the reference's WHOLE loop body (shade_bounce).
 //   phase 1  trace the shadow ray (any hit; Scene::ray_test inside sample_emitter_direction, scene.cpp:262-268) and
 //            add the pending term when it is unoccluded: result = fma(thr_nee, c_nee, result), the very operation
 //            and operands of :214-226.
 // Only ~a dozen values live across the shadow traversal (instead of the whole surface interaction), which is what
 // lets the kernel run at 4+ CTAs per SM. All lanes of a warp are always in the same phase.
-// DOPPLER = false is the stock path tracer (src/integrators/path.cpp:103-283): no time wrap, modulation weight 1,
-// every draw is Sampler::next_1d / next_2d, i.e. the independent stream only (the path stream does not move).
 template <int MODE, bool STATS, bool DOPPLER>
 DTOF_DEV PathOut trace_path(const DeviceScene &S, const TravPtrs &TP, const dtof_params &P, const Modulation &mod,
                             LaneSampler &smp, bool lane_on, V3 ray_o, V3 ray_d, float ray_maxt, float time_in,
                             Counters &st) {
     PathOut out{ v3(0, 0, 0), 0.f, 0 };
-    const uint32_t max_depth = (uint32_t) P.max_depth, rr_depth = (uint32_t) P.rr_depth;   // -1 -> 0xffffffff
     const float ray_time = (!DOPPLER || time_in < P.time) ? time_in : time_in - P.time;    // dopplertofpath.cpp:93
-    V3 throughput = v3(1, 1, 1), result = v3(0, 0, 0);
-    // eta: every BSDF in scope has eta = 1 on a live path (bs.eta is 0 only where the throughput is 0 too and the
-    // lane stops), so `path_length += t * eta`, `eta *= bs.eta` and `rr_prob = tmax * eta^2` reduce to eta == 1.
-    float path_length = 0.f;
-    uint32_t depth = 0;
-    bool valid_ray = false;                       // no environment emitter in scope (:102)
-    V3 prev_p = v3(0, 0, 0);
-    float prev_bsdf_pdf = 1.f;
-    bool prev_bsdf_delta = true;
-    bool active = lane_on && P.max_depth != 0;
-    const uint32_t n_em = S.n_emitters;
-    const float emitter_pmf = n_em ? 1.f / (float) n_em : 0.f;   // once per sample: IEEE
+    PathState ps;
+    ps.init(lane_on && P.max_depth != 0);
+    const float emitter_pmf = S.n_emitters ? 1.f / (float) S.n_emitters : 0.f;   // once per sample: IEEE
 
     // state handed from phase 0 to phase 1
-    bool phase_shadow = false, want_shadow = false;
-    V3 thr_nee = v3(0, 0, 0), c_nee = v3(0, 0, 0), so = v3(0, 0, 0), sd = v3(0, 0, 1);
-    float s_maxt = 0.f;
+    bool phase_shadow = false;
+    PendingNee nee;
+    nee.want = false;
+    nee.thr = v3(0, 0, 0), nee.c = v3(0, 0, 0), nee.o = v3(0, 0, 0), nee.d = v3(0, 0, 1);
+    nee.maxt = 0.f;
 
-    while (phase_shadow || __any_sync(kFullMask, active)) {
+    while (phase_shadow || __any_sync(kFullMask, ps.active)) {
         Hit h;
         h.gid = 0;
         h.inst = -1;
-        const bool hit = trace_any_mode<MODE, STATS>(S, TP, phase_shadow, phase_shadow ? so : ray_o, phase_shadow ? sd : ray_d,
-                                                     phase_shadow ? s_maxt : ray_maxt, ray_time,
-                                                     phase_shadow ? want_shadow : active, h, st);
+        const bool hit = trace_any_mode<MODE, STATS>(S, TP, phase_shadow, phase_shadow ? nee.o : ray_o, phase_shadow ? nee.d : ray_d,
+                                                     phase_shadow ? nee.maxt : ray_maxt, ray_time,
+                                                     phase_shadow ? nee.want : ps.active, h, st);
         if (phase_shadow) {   // ---- phase 1: the pending emitter-sampling term (:214-226)
             phase_shadow = false;
-            if (want_shadow && !hit)
-                result = v3(fmaf(thr_nee.x, c_nee.x, result.x), fmaf(thr_nee.y, c_nee.y, result.y),
-                            fmaf(thr_nee.z, c_nee.z, result.z));
+            if (nee.want && !hit)
+                ps.result = v3(fmaf(nee.thr.x, nee.c.x, ps.result.x), fmaf(nee.thr.y, nee.c.y, ps.result.y),
+                               fmaf(nee.thr.z, nee.c.z, ps.result.z));
             continue;
         }
         // ---- phase 0
         phase_shadow = true;
-        want_shadow = false;
-        if (!active)
+        nee.want = false;
+        if (!ps.active)
             continue;
-        const bool valid = hit;
-        const bool correlate = DOPPLER && (depth + 1) < P.path_correlation_depth;   // :122
-        SI si;
-        uint32_t bsdf_flags = 0;
-        V3 refl = v3(0, 0, 0);
-        int32_t mesh_emitter = -1;
-        if (valid) {
-            compute_si(S, TP.I, h, ray_d, ray_time, si);
-            const MeshRec &mr = S.meshes[si.mesh];
-            mesh_emitter = mr.emitter;
-            const BsdfRec br = S.bsdfs[mr.bsdf];
-            bsdf_flags = br.flags;
-            refl = v3(br.r, br.g, br.b);
-            path_length += h.t;                                             // :141 (eta == 1)
-        }
-        // ---- direct emission (:150-168)
-        if (valid && mesh_emitter >= 0) {
-            const MeshRec &em_mesh = S.meshes[si.mesh];
-            const EmitterRec em = S.emitters[mesh_emitter];
-            V3 rel = si.p - prev_p;                                         // DirectionSample(scene, si, prev_si)
-            float dist = fsqrt(dot3(rel, rel));
-            V3 dsd = rel / dist;
-            float em_pdf = 0.f;
-            if (!prev_bsdf_delta) {                                         // AreaLight::pdf_direction, area.cpp:148-166
-                float dp = dot3(dsd, si.sh_n);
-                float pdf = em_mesh.inv_area, adp = fabsf(dp);
-                pdf *= adp != 0.f ? fdiv(dist * dist, adp) : 0.f;
-                em_pdf = (dp < 0.f ? pdf : 0.f) * emitter_pmf;
-            }
-            float mis_bsdf = mis_weight(prev_bsdf_pdf, em_pdf);
-            float lw = DOPPLER ? mod.eval(ray_time, path_length) : 1.f;
-            V3 Le = (si.wi.z > 0.f && prev_bsdf_pdf > 0.f) ? v3(em.vr, em.vg, em.vb) : v3(0, 0, 0);
-            V3 c = Le * mis_bsdf * lw;
-            result = v3(fmaf(throughput.x, c.x, result.x), fmaf(throughput.y, c.y, result.y),
-                        fmaf(throughput.z, c.z, result.z));
-        }
-        const bool active_next = (depth + 1 < max_depth) && valid;         // :171
-        const bool smooth = (bsdf_flags & 2u) != 0, twosided = (bsdf_flags & 1u) != 0;
-
-        // ---- emitter sampling (:187-202): the 2D sample is always consumed, its value only when needed
-        uint64_t e1a = DOPPLER ? smp.rng_path.step() : 0ull, e1b = smp.rng.step();
-        uint64_t e2a = DOPPLER ? smp.rng_path.step() : 0ull, e2b = smp.rng.step();
-        smp.draws += 2;
-        bool active_em = active_next && smooth && n_em > 0, ds_delta = false;
-        V3 em_weight = v3(0, 0, 0), wo = v3(0, 0, 0);
-        float ds_dist = 0.f, ds_pdf = 0.f;
-        if (active_em) {
-            uint32_t index = 0;
-            float sx = 0.f, sy = 0.f;
-            V3 ds_p, ds_n, spec, ds_d;
-            EmitterRec em = S.emitters[0];
-            if (n_em > 1 || em.kind != DTOF_EMITTER_POINT) {
-                sx = u32_to_float(pcg_output(correlate ? e1a : e1b));
-                sy = u32_to_float(pcg_output(correlate ? e2a : e2b));
-            }
-            if (n_em > 1) {                                                 // Scene::sample_emitter, scene.cpp:171-189
-                float scaled = sx * (float) n_em;
-                index = min((uint32_t) scaled, n_em - 1u);
-                sx = scaled - (float) index;
-                em = S.emitters[index];
-            }
-            if (em.kind == DTOF_EMITTER_POINT) {                            // PointLight::sample_direction, point.cpp:118-147
-                ds_p = v3(em.px, em.py, em.pz);
-                ds_pdf = 1.f;
-                ds_delta = true;
-                ds_d = ds_p - si.p;
-                float dist2 = dot3(ds_d, ds_d), inv_dist = rsqrt_ieee(dist2);
-                ds_dist = fsqrt(dist2);
-                ds_d = ds_d * inv_dist;
-                float f = inv_dist * inv_dist;
-                spec = v3(em.vr * f, em.vg * f, em.vb * f);
-            } else {                                                        // AreaLight / Shape::sample_direction
-                sample_position(S, S.meshes[em.mesh], sx, sy, ds_p, ds_n, ds_pdf);
-                ds_d = ds_p - si.p;
-                float dist2 = dot3(ds_d, ds_d);
-                ds_dist = fsqrt(dist2);
-                ds_d = ds_d / ds_dist;
-                float dp = fabsf(dot3(ds_d, ds_n));
-                float x = fdiv(dist2, dp);
-                ds_pdf *= isfinite(x) ? x : 0.f;
-                bool em_active = dot3(ds_d, ds_n) < 0.f && ds_pdf != 0.f;
-                spec = em_active ? v3(em.vr, em.vg, em.vb) / ds_pdf : v3(0, 0, 0);
-            }
-            if (n_em > 1) {
-                ds_pdf *= emitter_pmf;
-                spec = spec * (float) n_em;
-            }
-            em_weight = spec;
-            if (ds_pdf != 0.f) {                                            // spawn_ray_to, interaction.h:141-148
-                so = offset_p(si.p, si.n, ds_p - si.p);
-                sd = ds_p - so;
-                float dist = fsqrt(dot3(sd, sd));
-                sd = sd / dist;
-                s_maxt = dist * (1.f - kShadowEps);
-                want_shadow = true;
-            }
-            wo = v3(dot3(ds_d, si.sh_s), dot3(ds_d, si.sh_t), dot3(ds_d, si.sh_n));
-        }
-        // an occluded or zero-pdf emitter sample clears active_em (:190): the term is pending iff want_shadow
-        // ---- BSDF eval + sample (:206-210); sample_1 is drawn but unused by the diffuse lobe
-        smp.template skip_1d<DOPPLER>();
-        float s2x = smp.template next_1d<DOPPLER>(correlate), s2y = smp.template next_1d<DOPPLER>(correlate);
-        V3 bsdf_val = v3(0, 0, 0), bsdf_weight = v3(0, 0, 0), bs_wo = v3(0, 0, 0);
-        float bsdf_pdf = 0.f, bs_pdf = 0.f;                                 // zero-initialised BSDFSample3f
-        if (valid && smooth) {
-            float wi_z = si.wi.z, wo_z = wo.z;
-            if (twosided) {                                                 // TwoSidedBRDF, twosided.cpp:111-125,219-235
-                wo_z = mulsign(wo_z, wi_z);
-                wi_z = fabsf(wi_z);
-            }
-            if (wi_z > 0.f && wo_z > 0.f) {                                 // SmoothDiffuse::eval_pdf, diffuse.cpp:160-176
-                bsdf_val = refl * kInvPi * wo_z;
-                bsdf_pdf = kInvPi * wo_z;
-            }
-            if (wi_z > 0.f) {                                               // SmoothDiffuse::sample, diffuse.cpp:101-125
-                bs_wo = square_to_cosine_hemisphere(s2x, s2y);
-                bs_pdf = kInvPi * bs_wo.z;
-                if (bs_pdf > 0.f)
-                    bsdf_weight = refl;
-                if (twosided)
-                    bs_wo.z = mulsign(bs_wo.z, si.wi.z);
-            }
-        }
-        // ---- emitter sampling contribution (:214-226), added in phase 1 if the shadow ray is unoccluded
-        if (want_shadow) {
-            float mis_em = ds_delta ? 1.f : mis_weight(ds_pdf, bsdf_pdf);
-            float lw = DOPPLER ? mod.eval(ray_time, path_length + ds_dist) : 1.f;
-            c_nee = bsdf_val * em_weight * mis_em * lw;
-            thr_nee = throughput;
-        }
-        // ---- BSDF sampling (:230-251)
-        if (valid) {
-            V3 wd = fma3(si.sh_n, bs_wo.z, fma3(si.sh_t, bs_wo.y, si.sh_s * bs_wo.x));
-            ray_o = offset_p(si.p, si.n, wd);
-            ray_d = wd;
-            ray_maxt = 3.402823466e+38f;
-            prev_p = si.p;
-        }
-        throughput = throughput * bsdf_weight;
-        valid_ray = valid_ray || valid;                                     // :253-254
-        prev_bsdf_pdf = bs_pdf;
-        prev_bsdf_delta = false;
-        // ---- stopping criterion (:262-276)
-        if (valid)
-            depth += 1;
-        float tmax = max3(throughput);
-        float rr_prob = fminf(tmax, 0.95f);                                 // eta == 1
-        bool rr_active = depth >= rr_depth;
-        float q = smp.template next_1d<DOPPLER>(correlate);                 // always drawn
-        bool rr_continue = q < rr_prob;
-        if (rr_active)
-            throughput = throughput * frcp(rr_prob);
-        active = active_next && (!rr_active || rr_continue) && tmax != 0.f;
+        shade_bounce<DOPPLER>(S, TP.I, P, mod, smp, ps, hit, h, ray_o, ray_d, ray_maxt, ray_time, emitter_pmf, nee);
     }
-    out.rgb = valid_ray ? result : v3(0, 0, 0);
-    out.path_length = path_length;
-    out.depth = depth;
+    out.rgb = ps.valid_ray ? ps.result : v3(0, 0, 0);
+    out.path_length = ps.path_length;
+    out.depth = ps.depth;
     return out;
 }
 

@@ -1,0 +1,470 @@
+// Wavefront pipeline of the B200 Doppler-ToF path tracer (sm_100a): the same per-lane algorithm as the fused kernel
+// (dtof_api.cu: render_kernel), cut into stages that exchange compacted ray / hit queues through HBM.
+//
+// Why it exists: in a scene whose BVH lives in HBM (millions of triangles) the rays of a warp need wildly different
+// numbers of traversal steps, and the fused kernel -- one lane owns one path, the warp waits for its slowest ray --
+// runs the walk at ~8 of 32 lanes (profiles/r01_render_c5_v5_ncu_summary.json). Here traversal is a kernel of its own
+// with DYNAMIC FETCH (after Aila & Laine 2009): a persistent warp keeps 32 rays in flight and a lane that finishes
+// its ray pulls the next one from the queue, so lane utilisation no longer depends on the slowest ray of a fixed
+// group. Shading runs over compacted queues at full warps.
+//
+// Stages per batch of lanes and pass (all on one stream, no host round trip while max_depth is bounded):
+//   wf_generate   sampler seeding / time / camera ray (render_sample, src/render/integrator.cpp:476-542)     -> queue 0
+//   per bounce b: wf_trace<closest>  queue b -> hits                      (Scene::ray_intersect, scene.cpp:125-137)
+//                 wf_shade           hits -> path state, queue b+1, shadow queue   (dopplertofpath.cpp:136-276)
+//                 wf_trace<any>      shadow queue -> result += thr * c when unoccluded       (:214-226, scene.cpp:262-268)
+//   wf_splat      ImageBlock::put of every lane of the batch, warp-aggregated             (imageblock.cpp:418-531)
+// Queues are compacted with one atomicAdd per warp (ballot + popc). Per-lane results are bit-identical to the fused
+// kernel: both run shade_bounce() / tri_test() / the same slab test; only the order of the film atomics differs.
+#pragma once
+#include "dtof_path.cuh"
+
+namespace dtof {
+
+constexpr int kWfBlock = 256;
+constexpr int kWfRing = 16;            // bounce slots in the counter ring
+constexpr uint32_t kWfMiss = 0xffffffffu;
+#ifndef DTOF_WF_TRACE_CTAS
+#define DTOF_WF_TRACE_CTAS 5
+#endif
+#ifndef DTOF_WF_SHADE_CTAS
+#define DTOF_WF_SHADE_CTAS 3
+#endif
+
+// counters of bounce b live at ring + 4 * (b % kWfRing)
+enum : int { WF_N_RAY = 0, WF_N_SHADOW = 1, WF_FETCH_CLOSEST = 2, WF_FETCH_SHADOW = 3 };
+
+struct WfBuffers {
+    // per-lane path state, indexed by the lane's slot in the batch
+    ulonglong2 *rng, *rng_path;     // PCG32 (state, inc) of the independent / path-correlated streams
+    float4 *thr_len;                // throughput.xyz, path_length
+    float4 *res_pdf;                // result.xyz, prev_bsdf_pdf
+    float4 *prev_meta;              // prev_p.xyz, bits: depth | valid_ray << 30 | prev_bsdf_delta << 31
+    float2 *film_pos;               // position handed to ImageBlock::put
+    // path-ray queues (ping-pong), compacted: {o.xyz, maxt}, {d.xyz, time}, lane slot
+    float4 *q_o[2], *q_d[2];
+    uint32_t *q_lane[2];
+    // closest-hit records by queue entry: {t, u, v, gid} (gid = kWfMiss: no hit), instance
+    float4 *hit;
+    int32_t *hit_inst;
+    // shadow-ray queue with the pending emitter-sampling term
+    float4 *s_o, *s_d, *s_thr, *s_c;
+    uint32_t *s_lane;
+    uint32_t *ring;                 // kWfRing x 4 counters
+};
+
+struct WfArgs {
+    DeviceScene scene;
+    dtof_camera cam;
+    FilmParams film;
+    dtof_params p;
+    Modulation mod;
+    WfBuffers buf;
+    uint32_t spp_per_pass, pass;
+    unsigned long long lane_begin, shard_block;
+    uint32_t shard_count, shard_index;
+    unsigned long long batch_begin;   // local lane index of slot 0
+    uint32_t n_slots;                 // lanes of this batch
+    uint32_t bounce;
+    uint32_t fetch_threshold;         // dynamic fetch: refill when fewer lanes than this still hold a ray
+    uint32_t inner_threshold;         // phase scheduling: inner-node steps run while this many lanes want one
+    uint32_t nodes_bytes, tris_bytes, insts_bytes;
+};
+
+DTOF_DEV uint32_t *wf_slot(const WfArgs &A, uint32_t bounce) { return A.buf.ring + 4 * (bounce % kWfRing); }
+
+// ------------------------------------------------------------------------------------------------
+// Stage 1: render_sample() up to the camera ray (Doppler branch src/render/integrator.cpp:476-542, stock branch
+// :409-472 for the `path` integrator).
+template <int KIND>
+__global__ void __launch_bounds__(kWfBlock) wf_generate_kernel(const __grid_constant__ WfArgs A) {
+    constexpr bool STOCK_SAMPLE = KIND != DTOF_INTEGRATOR_DOPPLERTOFPATH;
+    constexpr bool DOPPLER = !STOCK_SAMPLE;
+    const WfBuffers &B = A.buf;
+    const bool any_depth = A.p.max_depth != 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        wf_slot(A, 0)[WF_N_RAY] = any_depth ? A.n_slots : 0u;
+    for (uint32_t s = blockIdx.x * kWfBlock + threadIdx.x; s < A.n_slots; s += gridDim.x * kWfBlock) {
+        const unsigned long long li = A.batch_begin + s;
+        unsigned long long idx64;
+        if (A.shard_block) {   // local lane -> (block of this shard, offset) -> global lane
+            unsigned long long j = li / A.shard_block, within = li - j * A.shard_block;
+            idx64 = A.lane_begin + (j * A.shard_count + A.shard_index) * A.shard_block + within;
+        } else {
+            idx64 = A.lane_begin + li;
+        }
+        const uint32_t idx = (uint32_t) idx64;
+        const uint32_t pixel = idx / A.spp_per_pass;
+        const uint32_t py = pixel / A.film.width, px = pixel - py * A.film.width;
+        LaneSampler smp;
+        if (A.pass == 0) {
+            smp.seed(A.p, idx);
+        } else {   // the streams continue across passes (integrator.cpp:299-308)
+            ulonglong2 r = B.rng[s];
+            smp.rng.state = r.x, smp.rng.inc = r.y;
+            if (DOPPLER) {
+                ulonglong2 q = B.rng_path[s];
+                smp.rng_path.state = q.x, smp.rng_path.inc = q.y;
+            }
+            smp.draws = 0;
+        }
+        const bool correlate_pixel = A.p.path_correlation_depth > 0;
+        const float scale_x = 1.f / (float) A.film.width, scale_y = 1.f / (float) A.film.height;
+        const float off_x = -(float) A.film.crop_x * scale_x, off_y = -(float) A.film.crop_y * scale_y;
+        const float posx = (float) (px + A.film.crop_x), posy = (float) (py + A.film.crop_y);
+        float jx, jy;
+        if (STOCK_SAMPLE) {
+            jx = smp.rng.next_f32(), jy = smp.rng.next_f32();
+        } else {
+            jx = smp.next_1d(correlate_pixel), jy = smp.next_1d(correlate_pixel);
+        }
+        float spx = posx + jx, spy = posy + jy;
+        float ax = fmaf(spx, scale_x, off_x), ay = fmaf(spy, scale_y, off_y);
+        float time = A.cam.shutter_open;
+        if (A.cam.shutter_open_time > 0.f) {
+            if (STOCK_SAMPLE)
+                time += smp.rng.next_f32() * A.cam.shutter_open_time;
+            else
+                time += smp.next_time(A.p, idx, A.spp_per_pass, A.pass) * A.cam.shutter_open_time;
+        }
+        V3 o, d;
+        float maxt;
+        camera_ray(A.cam, ax, ay, o, d, maxt);
+        const float ray_time = (!DOPPLER || time < A.p.time) ? time : time - A.p.time;   // dopplertofpath.cpp:93
+        if (A.film.rfilter == DTOF_RFILTER_BOX) {
+            spx = posx;
+            spy = posy;
+        }
+        B.rng[s] = make_ulonglong2(smp.rng.state, smp.rng.inc);
+        if (DOPPLER)
+            B.rng_path[s] = make_ulonglong2(smp.rng_path.state, smp.rng_path.inc);
+        B.thr_len[s] = make_float4(1.f, 1.f, 1.f, 0.f);
+        B.res_pdf[s] = make_float4(0.f, 0.f, 0.f, 1.f);
+        B.prev_meta[s] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0x80000000u));   // depth 0, prev_bsdf_delta
+        B.film_pos[s] = make_float2(spx, spy);
+        if (any_depth) {
+            B.q_o[0][s] = make_float4(o.x, o.y, o.z, maxt);
+            B.q_d[0][s] = make_float4(d.x, d.y, d.z, ray_time);
+            B.q_lane[0][s] = s;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage 2 / 4: closest-hit (ANY = false) or any-hit (ANY = true) traversal.
+//
+// Two things keep the lanes of a warp busy although their rays need very different work:
+//  * DYNAMIC FETCH: a persistent warp keeps up to 32 rays in flight; when `32 - fetch_threshold` lanes have finished
+//    their rays they pull new ones from the queue (one atomicAdd per refill).
+//  * PHASE SCHEDULING instead of the while-while loop: every iteration the warp votes and runs ONE of two uniform
+//    phases -- a box-test step for the lanes that hold an inner node, or leaf processing (triangle tests / instance
+//    entry) for the lanes that hold a leaf. Inner steps run while at least `inner_threshold` lanes want one; lanes
+//    holding a leaf wait until enough of them have gathered. In a while-while loop the inner loop runs until the LAST
+//    lane reaches a leaf: with ~5 inner nodes between leaves on incoherent rays that is ~20 iterations of which a
+//    lane uses 5 (measured: 10.8 of 32 lanes active, profiles/r01_tuning.md).
+// The walk itself (slab test, child order, triangle test, tie-break, instance entry) is the one of trace_bvh
+// (dtof_device.cuh), so hits are identical. The world-space ray is not kept live while a lane is inside an instance;
+// it is re-read from the queue when the lane leaves it.
+template <int MODE, bool ANY>
+__global__ void __launch_bounds__(kWfBlock, DTOF_WF_TRACE_CTAS) wf_trace_kernel(const __grid_constant__ WfArgs A) {
+    constexpr bool SLAB_FMA = MODE == MODE_BVH_GLOBAL;
+    extern __shared__ float4 wf_smem[];
+    const float4 *__restrict__ N = A.scene.nodes, *__restrict__ T = A.scene.tris, *__restrict__ I = A.scene.insts;
+    if (MODE == MODE_BVH_SMEM) {
+        const uint32_t nn = A.nodes_bytes / 16, nt = A.tris_bytes / 16, ni = A.insts_bytes / 16;
+        float4 *sN = wf_smem, *sT = sN + nn, *sI = sT + nt;
+        for (uint32_t i = threadIdx.x; i < nn; i += kWfBlock) sN[i] = A.scene.nodes[i];
+        for (uint32_t i = threadIdx.x; i < nt; i += kWfBlock) sT[i] = A.scene.tris[i];
+        for (uint32_t i = threadIdx.x; i < ni; i += kWfBlock) sI[i] = A.scene.insts[i];
+        __syncthreads();
+        N = sN, T = sT, I = sI;
+    }
+    const WfBuffers &B = A.buf;
+    uint32_t *slot = wf_slot(A, A.bounce);
+    const uint32_t n = slot[ANY ? WF_N_SHADOW : WF_N_RAY];
+    uint32_t *fetch = slot + (ANY ? WF_FETCH_SHADOW : WF_FETCH_CLOSEST);
+    const int q = A.bounce & 1;
+    const float4 *__restrict__ qo = ANY ? B.s_o : B.q_o[q], *__restrict__ qd = ANY ? B.s_d : B.q_d[q];
+    const int lane = threadIdx.x & 31;
+    const uint32_t refill_at = 32u - min(A.fetch_threshold, 31u);   // idle lanes that trigger a refill (>= 1)
+    const uint32_t inner_min = max(A.inner_threshold, 1u);
+
+    int stack[kStackSize];
+    int sp = 0, node = kDone, cur_inst = -1;
+    uint32_t k = kWfMiss;
+    V3 ro = v3(0, 0, 0), rd = v3(0, 0, 1), id = v3(0, 0, 0), nd = v3(0, 0, 0);
+    float best = 0.f;
+    Hit hit;
+    hit.t = 0.f, hit.u = 0.f, hit.v = 0.f, hit.gid = 0, hit.inst = -1;
+    bool found = false, exhausted = false;
+
+#define DTOF_WF_POP()                                                                                      \
+    do {                                                                                                   \
+        if (sp == 0) {                                                                                     \
+            node = kDone;                                                                                  \
+        } else {                                                                                           \
+            node = stack[--sp];                                                                            \
+            if (node == kSentinel) { /* leave the instance: back to the world-space ray */                 \
+                const float4 a_ = qo[k], b_ = qd[k];                                                       \
+                ro = v3(a_.x, a_.y, a_.z), rd = v3(b_.x, b_.y, b_.z);                                      \
+                id = v3(frcp(rd.x), frcp(rd.y), frcp(rd.z));                                               \
+                nd = v3(-(ro.x * id.x), -(ro.y * id.y), -(ro.z * id.z));                                   \
+                cur_inst = -1;                                                                             \
+                node = sp ? stack[--sp] : kDone;                                                           \
+            }                                                                                              \
+        }                                                                                                  \
+    } while (0)
+
+    for (;;) {
+        // ---- a finished ray hands over its result
+        if (node == kDone && k != kWfMiss) {
+            if (ANY) {
+                if (!found) {   // unoccluded: result = fma(thr_nee, c_nee, result), dopplertofpath.cpp:214-226
+                    const uint32_t s = B.s_lane[k];
+                    const float4 thr = B.s_thr[k], c = B.s_c[k];
+                    float4 r = B.res_pdf[s];
+                    r.x = fmaf(thr.x, c.x, r.x), r.y = fmaf(thr.y, c.y, r.y), r.z = fmaf(thr.z, c.z, r.z);
+                    B.res_pdf[s] = r;
+                }
+            } else {
+                B.hit[k] = make_float4(hit.t, hit.u, hit.v, __uint_as_float(found ? hit.gid : kWfMiss));
+                B.hit_inst[k] = hit.inst;
+            }
+            k = kWfMiss;
+        }
+        // ---- dynamic fetch: refill the lanes that hold no ray
+        const bool need = node == kDone;
+        const unsigned m = __ballot_sync(kFullMask, need);
+        if (!exhausted && (uint32_t) __popc(m) >= refill_at) {
+            const int leader = __ffs(m) - 1;
+            const uint32_t cnt = __popc(m);
+            uint32_t base = 0;
+            if (lane == leader)
+                base = atomicAdd(fetch, cnt);
+            base = __shfl_sync(kFullMask, base, leader);
+            exhausted = base + cnt >= n;
+            const uint32_t kk = base + __popc(m & ((1u << lane) - 1u));
+            if (need && kk < n) {
+                k = kk;
+                const float4 a = qo[k], b = qd[k];
+                ro = v3(a.x, a.y, a.z), rd = v3(b.x, b.y, b.z);
+                best = a.w;
+                id = v3(frcp(rd.x), frcp(rd.y), frcp(rd.z));
+                nd = v3(-(ro.x * id.x), -(ro.y * id.y), -(ro.z * id.z));
+                sp = 0, cur_inst = -1, found = false;
+                hit.gid = 0, hit.inst = -1;
+                node = A.scene.root;
+            }
+        }
+        // ---- vote for the phase of this iteration
+        const bool is_inner = (unsigned) node < (unsigned) kDone, is_leaf = node < 0;
+        const unsigned m_inner = __ballot_sync(kFullMask, is_inner), m_leaf = __ballot_sync(kFullMask, is_leaf);
+        if (!(m_inner | m_leaf)) {
+            if (exhausted)
+                break;
+            continue;
+        }
+        if ((uint32_t) __popc(m_inner) >= inner_min || !m_leaf) {
+            // ---- phase A: one inner-node step
+            if (is_inner) {
+                const float4 *np = N + 4 * (size_t) node;
+                float4 n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3];
+                float c0lx, c0hx, c0ly, c0hy, c0lz, c0hz, c1lx, c1hx, c1ly, c1hy, c1lz, c1hz, widen;
+                if (SLAB_FMA) {
+                    c0lx = fmaf(n0.x, id.x, nd.x), c0hx = fmaf(n0.y, id.x, nd.x);
+                    c0ly = fmaf(n0.z, id.y, nd.y), c0hy = fmaf(n0.w, id.y, nd.y);
+                    c0lz = fmaf(n2.x, id.z, nd.z), c0hz = fmaf(n2.y, id.z, nd.z);
+                    c1lx = fmaf(n1.x, id.x, nd.x), c1hx = fmaf(n1.y, id.x, nd.x);
+                    c1ly = fmaf(n1.z, id.y, nd.y), c1hy = fmaf(n1.w, id.y, nd.y);
+                    c1lz = fmaf(n2.z, id.z, nd.z), c1hz = fmaf(n2.w, id.z, nd.z);
+                    widen = 1.000003f;
+                } else {
+                    c0lx = (n0.x - ro.x) * id.x, c0hx = (n0.y - ro.x) * id.x;
+                    c0ly = (n0.z - ro.y) * id.y, c0hy = (n0.w - ro.y) * id.y;
+                    c0lz = (n2.x - ro.z) * id.z, c0hz = (n2.y - ro.z) * id.z;
+                    c1lx = (n1.x - ro.x) * id.x, c1hx = (n1.y - ro.x) * id.x;
+                    c1ly = (n1.z - ro.y) * id.y, c1hy = (n1.w - ro.y) * id.y;
+                    c1lz = (n2.z - ro.z) * id.z, c1hz = (n2.w - ro.z) * id.z;
+                    widen = 1.0000005f;
+                }
+                float t0n = fmaxf(fmaxf(fminf(c0lx, c0hx), fminf(c0ly, c0hy)), fmaxf(fminf(c0lz, c0hz), 0.f));
+                float t0f = fminf(fminf(fmaxf(c0lx, c0hx), fmaxf(c0ly, c0hy)), fmaxf(c0lz, c0hz)) * widen;
+                float t1n = fmaxf(fmaxf(fminf(c1lx, c1hx), fminf(c1ly, c1hy)), fmaxf(fminf(c1lz, c1hz), 0.f));
+                float t1f = fminf(fminf(fmaxf(c1lx, c1hx), fmaxf(c1ly, c1hy)), fmaxf(c1lz, c1hz)) * widen;
+                bool h0 = t0n <= fminf(t0f, best), h1 = t1n <= fminf(t1f, best);
+                int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+                if (h0 && h1) {
+                    bool swap = t1n < t0n;
+                    stack[sp++] = swap ? c0 : c1;
+                    node = swap ? c1 : c0;
+                } else if (h0 || h1) {
+                    node = h0 ? c0 : c1;
+                } else {
+                    DTOF_WF_POP();
+                }
+            }
+        } else if (is_leaf) {
+            // ---- phase B: the lanes that hold a leaf process it
+            const uint32_t code = (uint32_t) ~node;
+            const uint32_t count = code & 15u;
+            if (count == 0) {   // animated instance: move the ray into its space (Embree semantics, enter_instance)
+                cur_inst = (int) (code >> 4);
+                const float4 *ip = I + 8 * (size_t) cur_inst;
+                const float4 a = qo[k], b = qd[k];
+                enter_instance(ip, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), b.w, ro, rd);
+                id = v3(frcp(rd.x), frcp(rd.y), frcp(rd.z));
+                nd = v3(-(ro.x * id.x), -(ro.y * id.y), -(ro.z * id.z));
+                stack[sp++] = kSentinel;
+                node = __float_as_int(ip[6].z);
+            } else {
+                const uint32_t first = code >> 4;
+                bool terminate = false;
+                for (uint32_t i = 0; i < count; ++i) {
+                    const float4 *tp = T + 3 * (size_t) (first + i);
+                    float4 a = tp[0], b = tp[1], c = tp[2];
+                    float t, u, v;
+                    if (tri_test(a, b, c, ro, rd, best, t, u, v)) {
+                        if (ANY) {
+                            found = true;
+                            terminate = true;
+                            break;
+                        }
+                        uint32_t gid = __float_as_uint(a.w);
+                        if (t < best || !found || gid < hit.gid) {
+                            best = t;
+                            hit.t = t, hit.u = u, hit.v = v;
+                            hit.gid = gid;
+                            hit.inst = cur_inst;
+                            found = true;
+                        }
+                    }
+                }
+                if (terminate)
+                    node = kDone;
+                else
+                    DTOF_WF_POP();
+            }
+        }
+    }
+#undef DTOF_WF_POP
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage 3: one iteration of the bounce loop for every entry of the path-ray queue (full warps).
+template <bool DOPPLER>
+__global__ void __launch_bounds__(kWfBlock, DTOF_WF_SHADE_CTAS) wf_shade_kernel(const __grid_constant__ WfArgs A) {
+    const WfBuffers &B = A.buf;
+    uint32_t *slot = wf_slot(A, A.bounce), *next = wf_slot(A, A.bounce + 1);
+    const uint32_t n = slot[WF_N_RAY];
+    const int q = A.bounce & 1, qn = q ^ 1;
+    const int lane = threadIdx.x & 31;
+    const float emitter_pmf = A.scene.n_emitters ? 1.f / (float) A.scene.n_emitters : 0.f;
+    const uint32_t stride = gridDim.x * kWfBlock;
+    for (uint32_t base = blockIdx.x * kWfBlock + (threadIdx.x & ~31u); base < n; base += stride) {
+        const uint32_t k = base + lane;
+        const bool on = k < n;
+        PathState ps;
+        PendingNee nee;
+        nee.want = false;
+        ps.active = false;
+        V3 ray_o = v3(0, 0, 0), ray_d = v3(0, 0, 1);
+        float ray_maxt = 0.f, ray_time = 0.f;
+        uint32_t s = 0;
+        if (on) {
+            s = B.q_lane[q][k];
+            const float4 d4 = B.q_d[q][k], h4 = B.hit[k];
+            ray_d = v3(d4.x, d4.y, d4.z);
+            ray_time = d4.w;
+            Hit h;
+            h.t = h4.x, h.u = h4.y, h.v = h4.z;
+            h.gid = __float_as_uint(h4.w);
+            h.inst = B.hit_inst[k];
+            const bool hit = h.gid != kWfMiss;
+            const float4 a = B.thr_len[s], r = B.res_pdf[s], c = B.prev_meta[s];
+            const uint32_t meta = __float_as_uint(c.w);
+            ps.throughput = v3(a.x, a.y, a.z), ps.path_length = a.w;
+            ps.result = v3(r.x, r.y, r.z), ps.prev_bsdf_pdf = r.w;
+            ps.prev_p = v3(c.x, c.y, c.z);
+            ps.depth = meta & 0x3fffffffu;
+            ps.valid_ray = (meta & 0x40000000u) != 0;
+            ps.prev_bsdf_delta = (meta & 0x80000000u) != 0;
+            ps.active = true;
+            LaneSampler smp;
+            const ulonglong2 g = B.rng[s];
+            smp.rng.state = g.x, smp.rng.inc = g.y;
+            if (DOPPLER) {
+                const ulonglong2 gp = B.rng_path[s];
+                smp.rng_path.state = gp.x, smp.rng_path.inc = gp.y;
+            }
+            smp.draws = 0;
+            shade_bounce<DOPPLER>(A.scene, A.scene.insts, A.p, A.mod, smp, ps, hit, h, ray_o, ray_d, ray_maxt, ray_time,
+                                  emitter_pmf, nee);
+            B.rng[s] = make_ulonglong2(smp.rng.state, smp.rng.inc);
+            if (DOPPLER)
+                B.rng_path[s] = make_ulonglong2(smp.rng_path.state, smp.rng_path.inc);
+            B.thr_len[s] = make_float4(ps.throughput.x, ps.throughput.y, ps.throughput.z, ps.path_length);
+            B.res_pdf[s] = make_float4(ps.result.x, ps.result.y, ps.result.z, ps.prev_bsdf_pdf);
+            B.prev_meta[s] = make_float4(ps.prev_p.x, ps.prev_p.y, ps.prev_p.z,
+                                         __uint_as_float(ps.depth | (ps.valid_ray ? 0x40000000u : 0u) |
+                                                         (ps.prev_bsdf_delta ? 0x80000000u : 0u)));
+        }
+        // ---- compaction: one atomicAdd per warp and queue
+        const unsigned m_next = __ballot_sync(kFullMask, on && ps.active);
+        const unsigned m_shadow = __ballot_sync(kFullMask, on && nee.want);
+        uint32_t b_next = 0, b_shadow = 0;
+        if (lane == 0) {
+            if (m_next) b_next = atomicAdd(next + WF_N_RAY, (uint32_t) __popc(m_next));
+            if (m_shadow) b_shadow = atomicAdd(slot + WF_N_SHADOW, (uint32_t) __popc(m_shadow));
+        }
+        b_next = __shfl_sync(kFullMask, b_next, 0);
+        b_shadow = __shfl_sync(kFullMask, b_shadow, 0);
+        const unsigned lt = (1u << lane) - 1u;
+        if (on && ps.active) {
+            const uint32_t j = b_next + __popc(m_next & lt);
+            B.q_o[qn][j] = make_float4(ray_o.x, ray_o.y, ray_o.z, ray_maxt);
+            B.q_d[qn][j] = make_float4(ray_d.x, ray_d.y, ray_d.z, ray_time);
+            B.q_lane[qn][j] = s;
+        }
+        if (on && nee.want) {
+            const uint32_t j = b_shadow + __popc(m_shadow & lt);
+            B.s_o[j] = make_float4(nee.o.x, nee.o.y, nee.o.z, nee.maxt);
+            B.s_d[j] = make_float4(nee.d.x, nee.d.y, nee.d.z, ray_time);
+            B.s_thr[j] = make_float4(nee.thr.x, nee.thr.y, nee.thr.z, 0.f);
+            B.s_c[j] = make_float4(nee.c.x, nee.c.y, nee.c.z, 0.f);
+            B.s_lane[j] = s;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage 5: film. Slots are in lane order (pixel-major), so a warp usually splats one 3x3 footprint.
+__global__ void __launch_bounds__(kWfBlock) wf_splat_kernel(const __grid_constant__ WfArgs A) {
+    const WfBuffers &B = A.buf;
+    const int lane = threadIdx.x & 31;
+    const uint32_t stride = gridDim.x * kWfBlock;
+    for (uint32_t base = blockIdx.x * kWfBlock + (threadIdx.x & ~31u); base < A.n_slots; base += stride) {
+        const uint32_t s = base + lane;
+        const bool lane_on = s < A.n_slots;
+        V3 rgb = v3(0, 0, 0);
+        float spx = 0.f, spy = 0.f;
+        if (lane_on) {
+            const float4 r = B.res_pdf[s];
+            const uint32_t meta = __float_as_uint(B.prev_meta[s].w);
+            const float2 fp = B.film_pos[s];
+            if (meta & 0x40000000u)   // valid_ray (dopplertofpath.cpp:279)
+                rgb = v3(r.x, r.y, r.z);
+            spx = fp.x, spy = fp.y;
+        }
+        const int ix = (int) floorf(spx), iy = (int) floorf(spy);
+        const unsigned on_mask = __ballot_sync(kFullMask, lane_on);
+        const int leader = __ffs(on_mask) - 1;
+        const int lx = __shfl_sync(kFullMask, ix, leader), ly = __shfl_sync(kFullMask, iy, leader);
+        const bool uniform = __all_sync(kFullMask, !lane_on || (ix == lx && iy == ly));
+        if (uniform && A.film.rfilter == DTOF_RFILTER_TENT && A.film.n == 1)
+            splat_tent3_warp(A.film, lx, ly, spx, spy, rgb, lane_on, lane);
+        else if (lane_on)
+            splat_generic(A.film, spx, spy, rgb);
+    }
+}
+
+} // namespace dtof

@@ -158,6 +158,10 @@ class Context:
     def last_traversal_mode(self) -> int:
         return int(self.lib.dtof_last_traversal_mode(self.h))
 
+    def last_pipeline(self) -> int:
+        """0 = fused kernel, 1 = wavefront pipeline (include/dtof.h: dtof_last_pipeline)"""
+        return int(self.lib.dtof_last_pipeline(self.h))
+
     def launch_count(self) -> int:
         return int(self.lib.dtof_launch_count(self.h))
 
