@@ -251,10 +251,15 @@ struct dtof_ctx {
     int sm_count = 148;
     size_t smem_optin = 0;
     // wavefront pipeline (dtof_wavefront.cuh): queues and per-lane path state for one batch of lanes
-    WfBuffers wf{};
-    void *wf_block = nullptr;
+    // Two sets, so that two batches are in flight on two streams: the memory-bound shading of one overlaps the
+    // issue-bound traversal of the other.
+    WfBuffers wf[kWfMaxSets]{};
+    void *wf_block[kWfMaxSets] = {};
     size_t wf_cap = 0;
-    uint32_t *wf_host_count = nullptr;   // pinned
+    int wf_sets = 0;
+    cudaStream_t wf_stream[kWfMaxSets] = {};
+    cudaEvent_t wf_ev_start = nullptr, wf_ev_done[kWfMaxSets] = {};
+    uint32_t *wf_host_count = nullptr;   // pinned, one word per set
     int last_pipeline = 0;               // 0 = fused kernel, 1 = wavefront
 };
 
@@ -406,19 +411,30 @@ dtof_status launch_mode(dtof_ctx *ctx, RenderArgs &A, bool record, int grid, cud
 }
 
 // ---- wavefront pipeline (dtof_wavefront.cuh) ------------------------------------------------------------------
-constexpr size_t kWfDefaultBatch = 1u << 23;   // lanes per batch: 8 Mi lanes x ~260 B of queues and state = 2.1 GiB
+constexpr size_t kWfDefaultBatch = 1u << 24;   // lanes per batch: 16 Mi lanes x ~260 B of queues and state = 4.2 GiB per set
 
 void free_wavefront(dtof_ctx *c) {
-    if (c->wf_block)
-        cudaFree(c->wf_block);
-    c->wf_block = nullptr;
+    for (int i = 0; i < kWfMaxSets; ++i) {
+        if (c->wf_block[i])
+            cudaFree(c->wf_block[i]);
+        c->wf_block[i] = nullptr;
+        c->wf[i] = WfBuffers{};
+    }
     c->wf_cap = 0;
-    c->wf = WfBuffers{};
+    c->wf_sets = 0;
 }
 
-// One allocation, carved into the SoA arrays of WfBuffers (every array 256-byte aligned).
-dtof_status ensure_wavefront(dtof_ctx *ctx, size_t cap) {
-    if (ctx->wf_cap >= cap)
+// One allocation per set, carved into the SoA arrays of WfBuffers (every array 256-byte aligned).
+dtof_status ensure_wavefront(dtof_ctx *ctx, size_t cap, int sets) {
+    if (!ctx->wf_stream[0]) {
+        for (int i = 0; i < kWfMaxSets; ++i) {
+            CU(cudaStreamCreateWithFlags(&ctx->wf_stream[i], cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&ctx->wf_ev_done[i], cudaEventDisableTiming));
+        }
+        CU(cudaEventCreateWithFlags(&ctx->wf_ev_start, cudaEventDisableTiming));
+        CU(cudaMallocHost(&ctx->wf_host_count, 64));
+    }
+    if (ctx->wf_cap >= cap && ctx->wf_sets >= sets)
         return DTOF_OK;
     free_wavefront(ctx);
     size_t off = 0;
@@ -433,25 +449,27 @@ dtof_status ensure_wavefront(dtof_ctx *ctx, size_t cap) {
                  o_st = carve(16), o_sc = carve(16), o_sl = carve(4);
     const size_t o_ring = off;
     off += 256;
-    if (cudaMalloc(&ctx->wf_block, off) != cudaSuccess) {
-        ctx->wf_block = nullptr;
-        return fail(ctx, DTOF_ERR_NOMEM, "cudaMalloc of %zu bytes of wavefront queues failed", off);
+    for (int i = 0; i < sets; ++i) {
+        if (cudaMalloc(&ctx->wf_block[i], off) != cudaSuccess) {
+            ctx->wf_block[i] = nullptr;
+            free_wavefront(ctx);
+            return fail(ctx, DTOF_ERR_NOMEM, "cudaMalloc of %zu bytes of wavefront queues failed", off);
+        }
+        char *b = (char *) ctx->wf_block[i];
+        WfBuffers &W = ctx->wf[i];
+        W.rng = (ulonglong2 *) (b + o_rng), W.rng_path = (ulonglong2 *) (b + o_rngp);
+        W.thr_len = (float4 *) (b + o_thr), W.res_pdf = (float4 *) (b + o_res), W.prev_meta = (float4 *) (b + o_prev);
+        W.film_pos = (float2 *) (b + o_film);
+        W.q_o[0] = (float4 *) (b + o_qo0), W.q_o[1] = (float4 *) (b + o_qo1);
+        W.q_d[0] = (float4 *) (b + o_qd0), W.q_d[1] = (float4 *) (b + o_qd1);
+        W.q_lane[0] = (uint32_t *) (b + o_ql0), W.q_lane[1] = (uint32_t *) (b + o_ql1);
+        W.hit = (float4 *) (b + o_hit), W.hit_inst = (int32_t *) (b + o_hi);
+        W.s_o = (float4 *) (b + o_so), W.s_d = (float4 *) (b + o_sd), W.s_thr = (float4 *) (b + o_st), W.s_c = (float4 *) (b + o_sc);
+        W.s_lane = (uint32_t *) (b + o_sl);
+        W.ring = (uint32_t *) (b + o_ring);
     }
-    if (!ctx->wf_host_count && cudaMallocHost(&ctx->wf_host_count, 64) != cudaSuccess)
-        return fail(ctx, DTOF_ERR_NOMEM, "cudaMallocHost failed");
-    char *b = (char *) ctx->wf_block;
-    WfBuffers &W = ctx->wf;
-    W.rng = (ulonglong2 *) (b + o_rng), W.rng_path = (ulonglong2 *) (b + o_rngp);
-    W.thr_len = (float4 *) (b + o_thr), W.res_pdf = (float4 *) (b + o_res), W.prev_meta = (float4 *) (b + o_prev);
-    W.film_pos = (float2 *) (b + o_film);
-    W.q_o[0] = (float4 *) (b + o_qo0), W.q_o[1] = (float4 *) (b + o_qo1);
-    W.q_d[0] = (float4 *) (b + o_qd0), W.q_d[1] = (float4 *) (b + o_qd1);
-    W.q_lane[0] = (uint32_t *) (b + o_ql0), W.q_lane[1] = (uint32_t *) (b + o_ql1);
-    W.hit = (float4 *) (b + o_hit), W.hit_inst = (int32_t *) (b + o_hi);
-    W.s_o = (float4 *) (b + o_so), W.s_d = (float4 *) (b + o_sd), W.s_thr = (float4 *) (b + o_st), W.s_c = (float4 *) (b + o_sc);
-    W.s_lane = (uint32_t *) (b + o_sl);
-    W.ring = (uint32_t *) (b + o_ring);
     ctx->wf_cap = cap;
+    ctx->wf_sets = sets;
     return DTOF_OK;
 }
 
@@ -466,6 +484,7 @@ template <int MODE, bool ANY> dtof_status launch_wf_trace(dtof_ctx *ctx, const W
 }
 
 // Renders the lanes of `A` (all passes) through the wavefront pipeline. `mode` is MODE_BVH_GLOBAL or MODE_BVH_SMEM.
+// Batches alternate between two internal streams (fork from / join into `stream` with events).
 dtof_status launch_wavefront(dtof_ctx *ctx, const RenderArgs &A, int mode, cudaStream_t stream) {
     size_t batch = kWfDefaultBatch;
     if (const char *e = getenv("DTOF_WF_BATCH"))
@@ -473,14 +492,18 @@ dtof_status launch_wavefront(dtof_ctx *ctx, const RenderArgs &A, int mode, cudaS
     uint32_t threshold = 24;
     if (const char *e = getenv("DTOF_WF_THRESHOLD"))
         threshold = (uint32_t) atoi(e);
+    int n_streams = kWfMaxSets;
+    if (const char *e = getenv("DTOF_WF_STREAMS"))
+        n_streams = std::min(std::max(atoi(e), 1), kWfMaxSets);
     const size_t cap = (size_t) std::min<unsigned long long>(A.n_local, batch);
     if (cap == 0)
         return DTOF_OK;
-    dtof_status s = ensure_wavefront(ctx, cap);
+    n_streams = (int) std::min<unsigned long long>((unsigned long long) n_streams, (A.n_local + cap - 1) / cap);
+    dtof_status s = ensure_wavefront(ctx, cap, n_streams);
     if (s != DTOF_OK)
         return s;
     WfArgs W{};
-    W.scene = A.scene, W.cam = A.cam, W.film = A.film, W.p = A.p, W.mod = A.mod, W.buf = ctx->wf;
+    W.scene = A.scene, W.cam = A.cam, W.film = A.film, W.p = A.p, W.mod = A.mod;
     W.spp_per_pass = A.spp_per_pass;
     W.lane_begin = A.lane_begin, W.shard_block = A.shard_block, W.shard_count = A.shard_count, W.shard_index = A.shard_index;
     W.fetch_threshold = threshold;
@@ -490,54 +513,70 @@ dtof_status launch_wavefront(dtof_ctx *ctx, const RenderArgs &A, int mode, cudaS
     W.nodes_bytes = A.nodes_bytes, W.tris_bytes = A.tris_bytes, W.insts_bytes = A.insts_bytes;
     const bool doppler = A.p.integrator == DTOF_INTEGRATOR_DOPPLERTOFPATH;
     const size_t smem = mode == MODE_BVH_SMEM ? (size_t) A.nodes_bytes + A.tris_bytes + A.insts_bytes : 0;
-    const int trace_grid = ctx->sm_count * DTOF_WF_TRACE_CTAS, shade_grid = ctx->sm_count * DTOF_WF_SHADE_CTAS,
+    // with two batches in flight a traversal kernel leaves room for the other batch's CTAs
+    // (measured on the 4.2 M-triangle scene, profiles/r01_tuning.md: 4 batches in flight x 2 CTAs/SM per traversal kernel)
+    int trace_ctas = n_streams >= 3 ? 2 : n_streams == 2 ? DTOF_WF_TRACE_CTAS - 1 : DTOF_WF_TRACE_CTAS;
+    if (const char *e = getenv("DTOF_WF_TRACE_GRID"))
+        trace_ctas = std::max(1, atoi(e));
+    const int trace_grid = ctx->sm_count * trace_ctas, shade_grid = ctx->sm_count * DTOF_WF_SHADE_CTAS * (kWfBlock / kWfShadeBlock),
               stream_grid = ctx->sm_count * 8;
     const bool bounded = A.p.max_depth >= 0;
-    for (unsigned long long begin = 0; begin < A.n_local; begin += cap) {
+    CU(cudaEventRecord(ctx->wf_ev_start, stream));
+    for (int i = 0; i < n_streams; ++i)
+        CU(cudaStreamWaitEvent(ctx->wf_stream[i], ctx->wf_ev_start, 0));
+    unsigned batch_index = 0;
+    for (unsigned long long begin = 0; begin < A.n_local; begin += cap, ++batch_index) {
+        const int set = (int) (batch_index % (unsigned) n_streams);
+        cudaStream_t st = ctx->wf_stream[set];
+        W.buf = ctx->wf[set];
         W.batch_begin = begin;
         W.n_slots = (uint32_t) std::min<unsigned long long>(cap, A.n_local - begin);
         for (uint32_t pass = 0; pass < A.n_passes; ++pass) {
             W.pass = pass;
             W.bounce = 0;
-            CU(cudaMemsetAsync(ctx->wf.ring, 0, kWfRing * 4 * sizeof(uint32_t), stream));
+            CU(cudaMemsetAsync(W.buf.ring, 0, kWfRing * 4 * sizeof(uint32_t), st));
             if (doppler)
-                wf_generate_kernel<DTOF_INTEGRATOR_DOPPLERTOFPATH><<<stream_grid, kWfBlock, 0, stream>>>(W);
+                wf_generate_kernel<DTOF_INTEGRATOR_DOPPLERTOFPATH><<<stream_grid, kWfBlock, 0, st>>>(W);
             else
-                wf_generate_kernel<DTOF_INTEGRATOR_PATH><<<stream_grid, kWfBlock, 0, stream>>>(W);
+                wf_generate_kernel<DTOF_INTEGRATOR_PATH><<<stream_grid, kWfBlock, 0, st>>>(W);
             ctx->launches++;
             CU(cudaGetLastError());
             for (uint32_t b = 0; !bounded || b < (uint32_t) A.p.max_depth; ++b) {
                 W.bounce = b;
                 if (b + 1 >= (uint32_t) kWfRing)   // recycle the ring slot the next bounce will count into
-                    CU(cudaMemsetAsync(ctx->wf.ring + 4 * ((b + 1) % kWfRing), 0, 4 * sizeof(uint32_t), stream));
-                s = mode == MODE_BVH_SMEM ? launch_wf_trace<MODE_BVH_SMEM, false>(ctx, W, trace_grid, smem, stream)
-                                          : launch_wf_trace<MODE_BVH_GLOBAL, false>(ctx, W, trace_grid, 0, stream);
+                    CU(cudaMemsetAsync(W.buf.ring + 4 * ((b + 1) % kWfRing), 0, 4 * sizeof(uint32_t), st));
+                s = mode == MODE_BVH_SMEM ? launch_wf_trace<MODE_BVH_SMEM, false>(ctx, W, trace_grid, smem, st)
+                                          : launch_wf_trace<MODE_BVH_GLOBAL, false>(ctx, W, trace_grid, 0, st);
                 if (s != DTOF_OK)
                     return s;
                 if (doppler)
-                    wf_shade_kernel<true><<<shade_grid, kWfBlock, 0, stream>>>(W);
+                    wf_shade_kernel<true><<<shade_grid, kWfShadeBlock, 0, st>>>(W);
                 else
-                    wf_shade_kernel<false><<<shade_grid, kWfBlock, 0, stream>>>(W);
+                    wf_shade_kernel<false><<<shade_grid, kWfShadeBlock, 0, st>>>(W);
                 ctx->launches++;
                 CU(cudaGetLastError());
-                s = mode == MODE_BVH_SMEM ? launch_wf_trace<MODE_BVH_SMEM, true>(ctx, W, trace_grid, smem, stream)
-                                          : launch_wf_trace<MODE_BVH_GLOBAL, true>(ctx, W, trace_grid, 0, stream);
+                s = mode == MODE_BVH_SMEM ? launch_wf_trace<MODE_BVH_SMEM, true>(ctx, W, trace_grid, smem, st)
+                                          : launch_wf_trace<MODE_BVH_GLOBAL, true>(ctx, W, trace_grid, 0, st);
                 if (s != DTOF_OK)
                     return s;
                 // bounded depth: every bounce is enqueued blind (an empty queue costs one idle launch). Unbounded or
                 // deep paths (Russian roulette ends them): from the 8th bounce on, look at the next queue's length.
                 if (b >= 7 && (!bounded || (uint32_t) A.p.max_depth > 8)) {
-                    CU(cudaMemcpyAsync(ctx->wf_host_count, ctx->wf.ring + 4 * ((b + 1) % kWfRing), sizeof(uint32_t),
-                                       cudaMemcpyDeviceToHost, stream));
-                    CU(cudaStreamSynchronize(stream));
-                    if (*ctx->wf_host_count == 0)
+                    uint32_t *h = ctx->wf_host_count + set;
+                    CU(cudaMemcpyAsync(h, W.buf.ring + 4 * ((b + 1) % kWfRing), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+                    CU(cudaStreamSynchronize(st));
+                    if (*h == 0)
                         break;
                 }
             }
-            wf_splat_kernel<<<stream_grid, kWfBlock, 0, stream>>>(W);
+            wf_splat_kernel<<<stream_grid, kWfBlock, 0, st>>>(W);
             ctx->launches++;
             CU(cudaGetLastError());
         }
+    }
+    for (int i = 0; i < n_streams; ++i) {
+        CU(cudaEventRecord(ctx->wf_ev_done[i], ctx->wf_stream[i]));
+        CU(cudaStreamWaitEvent(stream, ctx->wf_ev_done[i], 0));
     }
     return DTOF_OK;
 }
@@ -888,6 +927,11 @@ void dtof_destroy(dtof_ctx *ctx) {
     free_scene(ctx);
     free_wavefront(ctx);
     if (ctx->wf_host_count) cudaFreeHost(ctx->wf_host_count);
+    for (int i = 0; i < kWfMaxSets; ++i) {
+        if (ctx->wf_stream[i]) cudaStreamDestroy(ctx->wf_stream[i]);
+        if (ctx->wf_ev_done[i]) cudaEventDestroy(ctx->wf_ev_done[i]);
+    }
+    if (ctx->wf_ev_start) cudaEventDestroy(ctx->wf_ev_start);
     if (ctx->d_counter) cudaFree(ctx->d_counter);
     if (ctx->d_stats) cudaFree(ctx->d_stats);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);

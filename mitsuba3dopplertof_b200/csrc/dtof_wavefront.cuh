@@ -22,14 +22,17 @@
 namespace dtof {
 
 constexpr int kWfBlock = 256;
+constexpr int kWfMaxSets = 4;         // batches in flight (one stream and one set of queues each)
 constexpr int kWfRing = 16;            // bounce slots in the counter ring
 constexpr uint32_t kWfMiss = 0xffffffffu;
+constexpr uint32_t kWfChunk = 256;    // rays a warp reserves from a queue per atomicAdd
 #ifndef DTOF_WF_TRACE_CTAS
 #define DTOF_WF_TRACE_CTAS 5
 #endif
 #ifndef DTOF_WF_SHADE_CTAS
-#define DTOF_WF_SHADE_CTAS 3
-#endif
+#define DTOF_WF_SHADE_CTAS 3           // per 256 threads; the shading kernel runs 128-thread blocks so that its CTAs fit
+#endif                                 // into the register file next to the other batch's traversal CTAs
+constexpr int kWfShadeBlock = 128;
 
 // counters of bounce b live at ring + 4 * (b % kWfRing)
 enum : int { WF_N_RAY = 0, WF_N_SHADOW = 1, WF_FETCH_CLOSEST = 2, WF_FETCH_SHADOW = 3 };
@@ -198,71 +201,66 @@ __global__ void __launch_bounds__(kWfBlock, DTOF_WF_TRACE_CTAS) wf_trace_kernel(
     hit.t = 0.f, hit.u = 0.f, hit.v = 0.f, hit.gid = 0, hit.inst = -1;
     bool found = false, exhausted = false;
 
-#define DTOF_WF_POP()                                                                                      \
-    do {                                                                                                   \
-        if (sp == 0) {                                                                                     \
-            node = kDone;                                                                                  \
-        } else {                                                                                           \
-            node = stack[--sp];                                                                            \
-            if (node == kSentinel) { /* leave the instance: back to the world-space ray */                 \
-                const float4 a_ = qo[k], b_ = qd[k];                                                       \
-                ro = v3(a_.x, a_.y, a_.z), rd = v3(b_.x, b_.y, b_.z);                                      \
-                id = v3(frcp(rd.x), frcp(rd.y), frcp(rd.z));                                               \
-                nd = v3(-(ro.x * id.x), -(ro.y * id.y), -(ro.z * id.z));                                   \
-                cur_inst = -1;                                                                             \
-                node = sp ? stack[--sp] : kDone;                                                           \
-            }                                                                                              \
-        }                                                                                                  \
-    } while (0)
+    // the sentinel that marks the way out of an instance is popped like a leaf and handled in the leaf phase
+#define DTOF_WF_POP() node = sp ? stack[--sp] : kDone
 
+    uint32_t w_next = 0, w_end = 0;   // rays this warp has reserved from the queue (warp-uniform)
     for (;;) {
-        // ---- a finished ray hands over its result
-        if (node == kDone && k != kWfMiss) {
-            if (ANY) {
-                if (!found) {   // unoccluded: result = fma(thr_nee, c_nee, result), dopplertofpath.cpp:214-226
-                    const uint32_t s = B.s_lane[k];
-                    const float4 thr = B.s_thr[k], c = B.s_c[k];
-                    float4 r = B.res_pdf[s];
-                    r.x = fmaf(thr.x, c.x, r.x), r.y = fmaf(thr.y, c.y, r.y), r.z = fmaf(thr.z, c.z, r.z);
-                    B.res_pdf[s] = r;
-                }
-            } else {
-                B.hit[k] = make_float4(hit.t, hit.u, hit.v, __uint_as_float(found ? hit.gid : kWfMiss));
-                B.hit_inst[k] = hit.inst;
-            }
-            k = kWfMiss;
-        }
-        // ---- dynamic fetch: refill the lanes that hold no ray
-        const bool need = node == kDone;
-        const unsigned m = __ballot_sync(kFullMask, need);
-        if (!exhausted && (uint32_t) __popc(m) >= refill_at) {
-            const int leader = __ffs(m) - 1;
-            const uint32_t cnt = __popc(m);
-            uint32_t base = 0;
-            if (lane == leader)
-                base = atomicAdd(fetch, cnt);
-            base = __shfl_sync(kFullMask, base, leader);
-            exhausted = base + cnt >= n;
-            const uint32_t kk = base + __popc(m & ((1u << lane) - 1u));
-            if (need && kk < n) {
-                k = kk;
-                const float4 a = qo[k], b = qd[k];
-                ro = v3(a.x, a.y, a.z), rd = v3(b.x, b.y, b.z);
-                best = a.w;
-                id = v3(frcp(rd.x), frcp(rd.y), frcp(rd.z));
-                nd = v3(-(ro.x * id.x), -(ro.y * id.y), -(ro.z * id.z));
-                sp = 0, cur_inst = -1, found = false;
-                hit.gid = 0, hit.inst = -1;
-                node = A.scene.root;
-            }
-        }
-        // ---- vote for the phase of this iteration
+        // ---- vote: what does every lane hold?
         const bool is_inner = (unsigned) node < (unsigned) kDone, is_leaf = node < 0;
         const unsigned m_inner = __ballot_sync(kFullMask, is_inner), m_leaf = __ballot_sync(kFullMask, is_leaf);
-        if (!(m_inner | m_leaf)) {
-            if (exhausted)
-                break;
-            continue;
+        const unsigned m_idle = ~(m_inner | m_leaf);
+        if ((uint32_t) __popc(m_idle) >= refill_at) {
+            const bool idle = !is_inner && !is_leaf;
+            // ---- finished rays hand over their results
+            if (idle && k != kWfMiss) {
+                if (ANY) {
+                    if (!found) {   // unoccluded: result = fma(thr_nee, c_nee, result), dopplertofpath.cpp:214-226
+                        const uint32_t s = B.s_lane[k];
+                        const float4 thr = B.s_thr[k], c = B.s_c[k];
+                        float4 r = B.res_pdf[s];
+                        r.x = fmaf(thr.x, c.x, r.x), r.y = fmaf(thr.y, c.y, r.y), r.z = fmaf(thr.z, c.z, r.z);
+                        B.res_pdf[s] = r;
+                    }
+                } else {
+                    B.hit[k] = make_float4(hit.t, hit.u, hit.v, __uint_as_float(found ? hit.gid : kWfMiss));
+                    B.hit_inst[k] = hit.inst;
+                }
+                k = kWfMiss;
+            }
+            // ---- dynamic fetch: the idle lanes take rays from the chunk the warp has reserved (one atomicAdd per
+            // kWfChunk rays); lanes the chunk cannot serve wait for the next refill
+            if (!exhausted) {
+                if (w_next == w_end) {
+                    uint32_t base = 0;
+                    if (lane == 0)
+                        base = atomicAdd(fetch, kWfChunk);
+                    base = __shfl_sync(kFullMask, base, 0);
+                    w_next = min(base, n), w_end = min(base + kWfChunk, n);
+                    exhausted = w_next == w_end;
+                }
+                const uint32_t give = min((uint32_t) __popc(m_idle), w_end - w_next);
+                const uint32_t rank = __popc(m_idle & ((1u << lane) - 1u));
+                if (idle && rank < give) {
+                    k = w_next + rank;
+                    const float4 a = qo[k], b = qd[k];
+                    ro = v3(a.x, a.y, a.z), rd = v3(b.x, b.y, b.z);
+                    best = a.w;
+                    id = v3(frcp(rd.x), frcp(rd.y), frcp(rd.z));
+                    nd = v3(-(ro.x * id.x), -(ro.y * id.y), -(ro.z * id.z));
+                    sp = 0, cur_inst = -1, found = false;
+                    hit.gid = 0, hit.inst = -1;
+                    node = A.scene.root;
+                }
+                w_next += give;
+                if (give)
+                    continue;   // vote again with the new rays
+            }
+            if (m_idle == kFullMask) {
+                if (exhausted)
+                    break;
+                continue;
+            }
         }
         if ((uint32_t) __popc(m_inner) >= inner_min || !m_leaf) {
             // ---- phase A: one inner-node step
@@ -307,7 +305,14 @@ __global__ void __launch_bounds__(kWfBlock, DTOF_WF_TRACE_CTAS) wf_trace_kernel(
             // ---- phase B: the lanes that hold a leaf process it
             const uint32_t code = (uint32_t) ~node;
             const uint32_t count = code & 15u;
-            if (count == 0) {   // animated instance: move the ray into its space (Embree semantics, enter_instance)
+            if (node == kSentinel) {   // leave the instance: back to the world-space ray
+                const float4 a = qo[k], b = qd[k];
+                ro = v3(a.x, a.y, a.z), rd = v3(b.x, b.y, b.z);
+                id = v3(frcp(rd.x), frcp(rd.y), frcp(rd.z));
+                nd = v3(-(ro.x * id.x), -(ro.y * id.y), -(ro.z * id.z));
+                cur_inst = -1;
+                DTOF_WF_POP();
+            } else if (count == 0) {   // animated instance: move the ray into its space (Embree semantics, enter_instance)
                 cur_inst = (int) (code >> 4);
                 const float4 *ip = I + 8 * (size_t) cur_inst;
                 const float4 a = qo[k], b = qd[k];
@@ -352,15 +357,16 @@ __global__ void __launch_bounds__(kWfBlock, DTOF_WF_TRACE_CTAS) wf_trace_kernel(
 // ------------------------------------------------------------------------------------------------
 // Stage 3: one iteration of the bounce loop for every entry of the path-ray queue (full warps).
 template <bool DOPPLER>
-__global__ void __launch_bounds__(kWfBlock, DTOF_WF_SHADE_CTAS) wf_shade_kernel(const __grid_constant__ WfArgs A) {
+__global__ void __launch_bounds__(kWfShadeBlock, DTOF_WF_SHADE_CTAS * (kWfBlock / kWfShadeBlock))
+wf_shade_kernel(const __grid_constant__ WfArgs A) {
     const WfBuffers &B = A.buf;
     uint32_t *slot = wf_slot(A, A.bounce), *next = wf_slot(A, A.bounce + 1);
     const uint32_t n = slot[WF_N_RAY];
     const int q = A.bounce & 1, qn = q ^ 1;
     const int lane = threadIdx.x & 31;
     const float emitter_pmf = A.scene.n_emitters ? 1.f / (float) A.scene.n_emitters : 0.f;
-    const uint32_t stride = gridDim.x * kWfBlock;
-    for (uint32_t base = blockIdx.x * kWfBlock + (threadIdx.x & ~31u); base < n; base += stride) {
+    const uint32_t stride = gridDim.x * kWfShadeBlock;
+    for (uint32_t base = blockIdx.x * kWfShadeBlock + (threadIdx.x & ~31u); base < n; base += stride) {
         const uint32_t k = base + lane;
         const bool on = k < n;
         PathState ps;
