@@ -12,7 +12,8 @@ of render(), scene resident on the GPU.
 * e2e          same metric through the host-buffer C ABI call (`dtof_update_instances` + `dtof_render`):
                H2D of the animated-instance keyframes + parameters, D2H of the RGBW film and the developed image
 * roofline     traversal bytes: (64 B x nodes + 48 B x triangles + 112 B x instance entries) per sample, counted by a
-               separate stats launch of the same kernel, + 16 B film; / measured HBM copy bandwidth
+               separate stats launch of the fused kernel (same walk), + 16 B film; / measured HBM copy bandwidth.
+               Scenes whose BVH is walked from HBM (c5) render through the wavefront pipeline (csrc/dtof_wavefront.cuh)
 * cpu_baseline the CPU oracle (oracle/, a port of the reference algorithm) on all host threads, bounded sample
 * N > 1        weak scaling: rank r renders the workload with seed r (the tutorials' multi-seed averaging,
                doppler_tutorials/src/program_runner.py:11-31), films are summed with one NCCL all-reduce per step
@@ -285,6 +286,7 @@ def main():
         kernel_ms.append(ctx.last_kernel_ms())
     torch.cuda.synchronize()
     prod_mode = ctx.last_traversal_mode()
+    prod_pipeline = ctx.last_pipeline()      # 0 = fused kernel, 1 = wavefront pipeline (HBM-resident scenes)
     if world > 1:
         dist.barrier()
     launches = ctx.launch_count() - launches0 + args.steps   # ours + one film memset per step
@@ -347,7 +349,8 @@ def main():
     issue_peak = 148 * 4 * 32 * (clk["sm_mhz"] or peaks.get("sm_max_mhz", 1965.0)) * 1e6
     traffic, ncu_issue = None, None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(args.workload)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(
+            args.workload + ("_wavefront" if prod_pipeline == 1 else ""))
         if tj:
             traffic = tj["bytes_per_sample"] * samples_per_step
             ncu_issue = tj.get("issue_active_pct")
@@ -356,14 +359,20 @@ def main():
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
         "traffic": traffic, "traffic_source": "profiles/r01_traffic.json (ncu dram bytes per sample x samples per launch)" if traffic else None,
-        "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})", "kernel": "render_kernel",
+        "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})",
+        "kernel": ("wavefront pipeline: wf_generate + per bounce wf_trace<closest> / wf_shade / wf_trace<any> + wf_splat, "
+                   "several batches in flight (kernel_ms spans the whole pipeline of one render)") if prod_pipeline == 1
+        else "render_kernel",
+        "pipeline": "wavefront" if prod_pipeline == 1 else "fused",
         "kernel_ms": kms, "bytes_per_sample": bytes_per_sample,
         "per_sample": {"rays_closest": st.rays_closest / n, "rays_shadow": st.rays_shadow / n, "nodes": st.nodes_visited / n,
                        "tris": st.tris_tested / n, "inst": st.inst_visits / n},
         "traversal_mode": mode_name,
         "note": ("counts are those of the BVH walk (closest + shadow rays); " + (
             "the traversal data of this workload is staged in shared memory, so the byte rate is served by SMEM, not HBM"
-            if mode_name != "bvh_global" else "nodes/triangles are read through L1/L2 from HBM")),
+            if mode_name != "bvh_global" else "nodes/triangles are read through L1/L2 from HBM") + (
+            "; the wavefront pipeline additionally moves its ray / hit queues and per-lane path state through HBM, "
+            "which is part of `traffic`, not of the algorithmic bytes" if prod_pipeline == 1 else "")),
         "issue": {"instr_per_sample_model": instr_per_sample,
                   "achieved_lane_instr_per_s": instr_per_sample * samples_per_step / (kms * 1e-3),
                   "peak_lane_instr_per_s": issue_peak,

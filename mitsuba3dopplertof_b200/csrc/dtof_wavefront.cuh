@@ -14,7 +14,7 @@
 //                 wf_shade           hits -> path state, queue b+1, shadow queue   (dopplertofpath.cpp:136-276)
 //                 wf_trace<any>      shadow queue -> result += thr * c when unoccluded       (:214-226, scene.cpp:262-268)
 //   wf_splat      ImageBlock::put of every lane of the batch, warp-aggregated             (imageblock.cpp:418-531)
-// Queues are compacted with one atomicAdd per warp (ballot + popc). Per-lane results are bit-identical to the fused
+// Queues are compacted with one atomicAdd per CTA (ballot + popc per warp, counts combined in shared memory). Per-lane results are bit-identical to the fused
 // kernel: both run shade_bounce() / tri_test() / the same slab test; only the order of the film atomics differs.
 #pragma once
 #include "dtof_path.cuh"
@@ -27,12 +27,12 @@ constexpr int kWfRing = 16;            // bounce slots in the counter ring
 constexpr uint32_t kWfMiss = 0xffffffffu;
 constexpr uint32_t kWfChunk = 256;    // rays a warp reserves from a queue per atomicAdd
 #ifndef DTOF_WF_TRACE_CTAS
-#define DTOF_WF_TRACE_CTAS 5
+#define DTOF_WF_TRACE_CTAS 6
 #endif
 #ifndef DTOF_WF_SHADE_CTAS
-#define DTOF_WF_SHADE_CTAS 3           // per 256 threads; the shading kernel runs 128-thread blocks so that its CTAs fit
-#endif                                 // into the register file next to the other batch's traversal CTAs
-constexpr int kWfShadeBlock = 128;
+#define DTOF_WF_SHADE_CTAS 3
+#endif
+constexpr int kWfShadeBlock = 256;
 
 // counters of bounce b live at ring + 4 * (b % kWfRing)
 enum : int { WF_N_RAY = 0, WF_N_SHADOW = 1, WF_FETCH_CLOSEST = 2, WF_FETCH_SHADOW = 3 };
@@ -366,8 +366,10 @@ wf_shade_kernel(const __grid_constant__ WfArgs A) {
     const int lane = threadIdx.x & 31;
     const float emitter_pmf = A.scene.n_emitters ? 1.f / (float) A.scene.n_emitters : 0.f;
     const uint32_t stride = gridDim.x * kWfShadeBlock;
-    for (uint32_t base = blockIdx.x * kWfShadeBlock + (threadIdx.x & ~31u); base < n; base += stride) {
-        const uint32_t k = base + lane;
+    __shared__ uint32_t sh_count[2][kWfShadeBlock / 32], sh_base[2];
+    const int warp = threadIdx.x >> 5;
+    for (uint32_t bbase = blockIdx.x * kWfShadeBlock; bbase < n; bbase += stride) {   // block-uniform trip count
+        const uint32_t k = bbase + threadIdx.x;
         const bool on = k < n;
         PathState ps;
         PendingNee nee;
@@ -414,16 +416,30 @@ wf_shade_kernel(const __grid_constant__ WfArgs A) {
                                          __uint_as_float(ps.depth | (ps.valid_ray ? 0x40000000u : 0u) |
                                                          (ps.prev_bsdf_delta ? 0x80000000u : 0u)));
         }
-        // ---- compaction: one atomicAdd per warp and queue
+        // ---- compaction: one atomicAdd per CTA and queue. All warps of the machine count into the same two words, and
+        // same-address atomics serialise in L2: with one atomicAdd per warp the kernel spent 46 % of its stall samples
+        // waiting for them (profiles/r01_tuning.md).
         const unsigned m_next = __ballot_sync(kFullMask, on && ps.active);
         const unsigned m_shadow = __ballot_sync(kFullMask, on && nee.want);
-        uint32_t b_next = 0, b_shadow = 0;
         if (lane == 0) {
-            if (m_next) b_next = atomicAdd(next + WF_N_RAY, (uint32_t) __popc(m_next));
-            if (m_shadow) b_shadow = atomicAdd(slot + WF_N_SHADOW, (uint32_t) __popc(m_shadow));
+            sh_count[0][warp] = __popc(m_next);
+            sh_count[1][warp] = __popc(m_shadow);
         }
-        b_next = __shfl_sync(kFullMask, b_next, 0);
-        b_shadow = __shfl_sync(kFullMask, b_shadow, 0);
+        __syncthreads();
+        if (threadIdx.x < 2) {
+            uint32_t total = 0;
+#pragma unroll
+            for (int w = 0; w < kWfShadeBlock / 32; ++w)
+                total += sh_count[threadIdx.x][w];
+            sh_base[threadIdx.x] = total ? atomicAdd(threadIdx.x == 0 ? next + WF_N_RAY : slot + WF_N_SHADOW, total) : 0u;
+        }
+        __syncthreads();
+        uint32_t b_next = sh_base[0], b_shadow = sh_base[1];
+        for (int w = 0; w < warp; ++w) {
+            b_next += sh_count[0][w];
+            b_shadow += sh_count[1][w];
+        }
+        __syncthreads();   // sh_count / sh_base are rewritten by the next iteration
         const unsigned lt = (1u << lane) - 1u;
         if (on && ps.active) {
             const uint32_t j = b_next + __popc(m_next & lt);
