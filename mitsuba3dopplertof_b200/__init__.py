@@ -10,8 +10,9 @@ from .scene import (Bsdf, CorrelatedSampler, Film, PerspectiveSensor, PointLight
                     rectangle)
 from .transform import AnimatedTransform, Transform4
 from .xml_loader import load_file, load_string
+from . import tof  # noqa: E402  (tutorial post-processing and drivers; needs the renderer only when called)
 
 __all__ = [
     "DopplerToFPathIntegrator", "VelocityIntegrator", "PathIntegrator", "DTOFError", "Bsdf", "CorrelatedSampler", "Film", "PerspectiveSensor", "PointLight",
-    "Scene", "Shape", "cube", "mesh", "rectangle", "AnimatedTransform", "Transform4", "load_file", "load_string",
+    "Scene", "Shape", "cube", "mesh", "rectangle", "AnimatedTransform", "Transform4", "load_file", "load_string", "tof",
 ]

@@ -150,17 +150,17 @@ def test_large_mesh_defaults_to_the_wavefront(ctx, env):
 
 
 def test_two_pass_render_keeps_the_streams_across_passes(ctx, env):
-    """2048 x 2048 @ 2048 spp is 2 passes x 1024 spp (wavefront > 2^32 lanes, integrator.cpp:231-238); a lane range keeps
+    """2048 x 2048 @ 1024 spp is 2 passes x 512 spp (wavefront of 2^32 lanes > 0xffffffff, integrator.cpp:231-238); a lane range keeps
     the test small. The random streams continue from pass 0 into pass 1 (integrator.cpp:299-308): the wavefront pipeline
     carries them in its per-lane state, the fused kernel in registers."""
-    scene = dt.load_file(os.path.join(gu.SCENES, "c2_arealight.xml"), resx=2048, resy=2048, spp=2048)
+    scene = dt.load_file(os.path.join(gu.SCENES, "c2_arealight.xml"), resx=2048, resy=2048, spp=1024)
     flat = ctx.upload(scene)
-    first = (1000 * 2048 + 1000) * 1024          # pixel (1000, 1000), spp_per_pass = 1024
-    params = scene.integrator.params(scene.sensor.sampler, seed=11, lane_begin=first, lane_end=first + 3 * 1024 + 100)
+    first = (1000 * 2048 + 1000) * 512           # pixel (1000, 1000), spp_per_pass = 512
+    params = scene.integrator.params(scene.sensor.sampler, seed=11, lane_begin=first, lane_end=first + 3 * 512 + 100)
     pi = ctx.pass_info(params)
-    assert (pi.n_passes, pi.spp_per_pass) == (2, 1024)
+    assert (pi.n_passes, pi.spp_per_pass) == (2, 512)
     fused = _render(ctx, flat, params, env, 0)
-    wave = _render(ctx, flat, params, env, 1, DTOF_WF_BATCH=1500)   # batch borders inside a pixel, 3 batches x 2 passes
+    wave = _render(ctx, flat, params, env, 1, DTOF_WF_BATCH=1024)   # 2 batches x 2 passes, ragged
     assert fused[..., 3].sum() > 0
     assert np.abs(wave[..., 3] - fused[..., 3]).max() <= 2e-6 * fused[..., 3].max()
     assert np.abs(wave[..., :3] - fused[..., :3]).max() <= 2e-5 * np.abs(fused[..., :3]).max()
