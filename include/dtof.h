@@ -262,7 +262,9 @@ dtof_status dtof_upload_scene(dtof_ctx *ctx, const dtof_scene_desc *scene);
 dtof_status dtof_scene_info_for(const dtof_scene_desc *scene, dtof_scene_info *out, char *err, uint32_t err_len);
 
 /* Replace the keyframes of instances [first, first+n) without rebuilding bottom-level BVHs
- * (animation loops, doppler_tutorials/src/main_animation.py:61-157). */
+ * (animation loops, doppler_tutorials/src/main_animation.py:61-157). The top-level BVH is rebuilt on the host from
+ * the groups' object-space bounds and replaces the old one in place, so the new motion may leave the bounds the scene
+ * was uploaded with; geometry, materials and the `animated` flag of an instance cannot change. */
 dtof_status dtof_update_instances(dtof_ctx *ctx, uint32_t first, uint32_t n, const dtof_instance *instances);
 
 /* Pass split of a render with these parameters; DTOF_ERR_INVALID where the reference throws

@@ -235,6 +235,9 @@ struct dtof_ctx {
     void *d_nodes = nullptr, *d_tris = nullptr, *d_shade = nullptr, *d_insts = nullptr, *d_meshes = nullptr,
          *d_bsdfs = nullptr, *d_emitters = nullptr, *d_cdf = nullptr, *d_pmf = nullptr;
     std::vector<InstRec> h_insts;
+    std::vector<TlasEntry> h_tlas;   // per instance: motion, object-space bounds, BLAS root (TLAS rebuild on keyframe updates)
+    uint32_t tlas_begin = 0, n_tlas_nodes = 0;
+    int blas_depth = 0;
     size_t nodes_bytes = 0, tris_bytes = 0, insts_bytes = 0;
     int bvh_depth = 0;
     // render state
@@ -979,6 +982,18 @@ dtof_status dtof_upload_scene(dtof_ctx *ctx, const dtof_scene_desc *sc) {
     ctx->tris_bytes = built.tris.size() * sizeof(TriIsect);
     ctx->insts_bytes = insts.size() * sizeof(InstRec);
     ctx->bvh_depth = built.max_depth + built.tlas_depth;
+    ctx->blas_depth = built.max_depth;
+    ctx->tlas_begin = built.tlas_begin;
+    ctx->n_tlas_nodes = (uint32_t) built.nodes.size() - built.tlas_begin;
+    ctx->h_tlas.assign(sc->n_instances, TlasEntry{});
+    for (uint32_t g = 0; g < sc->n_instances; ++g) {
+        TlasEntry &E = ctx->h_tlas[g];
+        E.animated = sc->instances[g].animated != 0;
+        memcpy(E.m0, sc->instances[g].m0, sizeof(E.m0));
+        memcpy(E.m1, sc->instances[g].m1, sizeof(E.m1));
+        E.object_box = built.group_box[g];
+        E.blas_root = built.inst_root[g];
+    }
     DeviceScene &D = ctx->ds;
     D.nodes = (const float4 *) ctx->d_nodes;
     D.tris = (const float4 *) ctx->d_tris;
@@ -1036,18 +1051,41 @@ dtof_status dtof_update_instances(dtof_ctx *ctx, uint32_t first, uint32_t n, con
     if ((uint64_t) first + n > ctx->h_insts.size())
         return fail(ctx, DTOF_ERR_INVALID, "instance range out of bounds");
     CU(cudaSetDevice(ctx->device));
-    // Only the keyframes move; the TLAS bounds are kept, so the new motion must stay inside the bounds
-    // the scene was uploaded with (re-upload otherwise).
+    // The keyframes move, the BLASes stay: the TLAS (k - 1 nodes over k instances) is rebuilt on the host from the
+    // groups' object-space bounds and overwrites the old TLAS nodes in place -- an animation loop never re-uploads
+    // geometry (doppler_tutorials/src/main_animation.py:61-157 reloads the whole scene per frame).
     for (uint32_t i = 0; i < n; ++i) {
-        InstRec &r = ctx->h_insts[first + i];
+        const InstRec &r = ctx->h_insts[first + i];
         if ((r.animated != 0) != (instances[i].animated != 0))
             return fail(ctx, DTOF_ERR_INVALID, "cannot change the animated flag of instance %u", first + i);
+        if (instances[i].animated && !(instances[i].t1 > instances[i].t0))
+            return fail(ctx, DTOF_ERR_INVALID, "instance %u: keyframe times must be increasing", first + i);
+    }
+    for (uint32_t i = 0; i < n; ++i) {
+        InstRec &r = ctx->h_insts[first + i];
         memcpy(r.m0, instances[i].m0, sizeof(r.m0));
         memcpy(r.m1, instances[i].m1, sizeof(r.m1));
         r.t0 = instances[i].t0, r.t1 = instances[i].t1;
+        TlasEntry &E = ctx->h_tlas[first + i];
+        memcpy(E.m0, instances[i].m0, sizeof(E.m0));
+        memcpy(E.m1, instances[i].m1, sizeof(E.m1));
     }
+    BuiltScene tl;
+    std::vector<BvhNode> tlas;
+    build_tlas(ctx->h_tlas, (int32_t) ctx->tlas_begin, tlas, tl);
+    if (tlas.size() != ctx->n_tlas_nodes)
+        return fail(ctx, DTOF_ERR_STATE, "TLAS rebuild produced %zu nodes, expected %u", tlas.size(), ctx->n_tlas_nodes);
+    if (ctx->blas_depth + tl.tlas_depth + 4 > kStackSize)
+        return fail(ctx, DTOF_ERR_UNSUPPORTED, "BVH too deep for the traversal stack (%d + %d)", ctx->blas_depth, tl.tlas_depth);
     CU(cudaMemcpy((char *) ctx->d_insts + first * sizeof(InstRec), ctx->h_insts.data() + first, n * sizeof(InstRec),
                   cudaMemcpyHostToDevice));
+    if (!tlas.empty())
+        CU(cudaMemcpy((char *) ctx->d_nodes + (size_t) ctx->tlas_begin * sizeof(BvhNode), tlas.data(), tlas.size() * sizeof(BvhNode),
+                      cudaMemcpyHostToDevice));
+    if (!tl.inst_box.empty())
+        CU(cudaMemcpy(ctx->d_boxes, tl.inst_box.data(), tl.inst_box.size() * sizeof(InstBox), cudaMemcpyHostToDevice));
+    ctx->ds.root = tl.root;
+    ctx->bvh_depth = ctx->blas_depth + tl.tlas_depth;
     return DTOF_OK;
 }
 

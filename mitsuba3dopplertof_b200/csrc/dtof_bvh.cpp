@@ -291,7 +291,7 @@ void build_scene_bvh(const std::vector<GroupInput> &groups, BuiltScene &out) {
     out.tris.clear();
     out.inst_root.assign(groups.size(), 0);
     out.max_depth = 0;
-    std::vector<Box> inst_boxes(groups.size());
+    std::vector<Box> group_boxes(groups.size());
 
     // ---- BLAS per group
     for (size_t g = 0; g < groups.size(); ++g) {
@@ -331,28 +331,59 @@ void build_scene_bvh(const std::vector<GroupInput> &groups, BuiltScene &out) {
         }
         out.inst_root[g] = root;
         out.max_depth = std::max(out.max_depth, depth);
-        // world bounds of the instance: union of the group's box corners under both keyframes
+        group_boxes[g] = gb;   // empty (invalid) when the group has no triangles
+    }
+
+    // ---- TLAS over instances (one instance per leaf), appended after the BLAS nodes
+    out.group_box.assign(groups.size(), InstBox{});
+    std::vector<TlasEntry> entries(groups.size());
+    for (size_t g = 0; g < groups.size(); ++g) {
+        // object-space bounds of the group: dtof_update_instances rebuilds the TLAS from them for new keyframes
+        const Box &b = group_boxes[g];
+        InstBox ob{ 1.f, 1.f, 1.f, 0.f, -1.f, -1.f, -1.f, 0.f };   // lo > hi: empty group
+        if (b.valid())
+            ob = InstBox{ b.lo[0], b.lo[1], b.lo[2], 0.f, b.hi[0], b.hi[1], b.hi[2], 0.f };
+        out.group_box[g] = ob;
+        entries[g].animated = groups[g].animated;
+        memcpy(entries[g].m0, groups[g].m0, sizeof(entries[g].m0));
+        memcpy(entries[g].m1, groups[g].m1, sizeof(entries[g].m1));
+        entries[g].object_box = ob;
+        entries[g].blas_root = out.inst_root[g];
+    }
+    out.tlas_begin = (uint32_t) out.nodes.size();
+    std::vector<BvhNode> tlas;
+    build_tlas(entries, (int32_t) out.tlas_begin, tlas, out);
+    out.nodes.insert(out.nodes.end(), tlas.begin(), tlas.end());
+}
+
+void build_tlas(const std::vector<TlasEntry> &entries, int32_t base, std::vector<BvhNode> &tlas, BuiltScene &out) {
+    const size_t n = entries.size();
+    std::vector<Box> inst_boxes(n);
+    for (size_t g = 0; g < n; ++g) {
+        const TlasEntry &E = entries[g];
+        const InstBox &ob = E.object_box;
         Box wb;
-        if (n) {
-            if (!G.animated) {
-                wb = gb;
+        if (ob.lox <= ob.hix) {
+            // world bounds of the instance: union of the group's box corners under both keyframes
+            if (!E.animated) {
+                float lo[3] = { ob.lox, ob.loy, ob.loz }, hi[3] = { ob.hix, ob.hiy, ob.hiz };
+                wb.grow(lo);
+                wb.grow(hi);
             } else {
                 for (int c = 0; c < 8; ++c) {
-                    float p[3] = { (c & 1) ? gb.hi[0] : gb.lo[0], (c & 2) ? gb.hi[1] : gb.lo[1], (c & 4) ? gb.hi[2] : gb.lo[2] };
+                    float p[3] = { (c & 1) ? ob.hix : ob.lox, (c & 2) ? ob.hiy : ob.loy, (c & 4) ? ob.hiz : ob.loz };
                     float q[3];
-                    xf_point(G.m0, p, q);
+                    xf_point(E.m0, p, q);
                     wb.grow(q);
-                    xf_point(G.m1, p, q);
+                    xf_point(E.m1, p, q);
                     wb.grow(q);
                 }
             }
         }
         inst_boxes[g] = wb;
     }
-
-    // ---- TLAS over instances (one instance per leaf)
     std::vector<Ref> irefs;
-    for (size_t g = 0; g < groups.size(); ++g) {
+    for (size_t g = 0; g < n; ++g) {
         if (!inst_boxes[g].valid())
             continue;
         Ref r;
@@ -363,17 +394,28 @@ void build_scene_bvh(const std::vector<GroupInput> &groups, BuiltScene &out) {
         irefs.push_back(r);
     }
     int tdepth = 0;
+    tlas.clear();
     if (irefs.empty()) {
         out.root = ~(int32_t) 0x7fffffff;   // never dereferenced: has_geometry = false
         out.has_geometry = false;
     } else {
-        // animated instance -> instance leaf; static group -> its BLAS root is spliced in (single-level traversal)
-        auto make_ileaf = [&](uint32_t lo, uint32_t) -> int32_t {
-            uint32_t g = irefs[lo].id;
-            return groups[g].animated ? ~(int32_t) (g << 4) : out.inst_root[g];
-        };
+        // every leaf is first a placeholder ~(g << 4): local node indices (>= 0) can then be rebased to absolute ones
+        // without touching the leaves. Afterwards: animated instance -> instance leaf (the placeholder itself);
+        // static group -> its BLAS root is spliced in (single-level traversal)
+        auto make_ileaf = [&](uint32_t lo, uint32_t) -> int32_t { return ~(int32_t) (irefs[lo].id << 4); };
         Box bb;
-        out.root = build_range(irefs, 0, (uint32_t) irefs.size(), out.nodes, 1, 1, make_ileaf, bb, tdepth);
+        int32_t root = build_range(irefs, 0, (uint32_t) irefs.size(), tlas, 1, 1, make_ileaf, bb, tdepth);
+        auto patch = [&](int32_t ref) -> int32_t {
+            if (ref >= 0)
+                return ref + base;
+            const uint32_t g = (uint32_t) ~ref >> 4;
+            return entries[g].animated ? ref : entries[g].blas_root;
+        };
+        for (BvhNode &nd : tlas) {
+            nd.child0 = patch(nd.child0);
+            nd.child1 = patch(nd.child1);
+        }
+        out.root = patch(root);
         out.has_geometry = true;
         for (int a = 0; a < 3; ++a) {
             out.scene_lo[a] = bb.lo[a];
@@ -381,8 +423,8 @@ void build_scene_bvh(const std::vector<GroupInput> &groups, BuiltScene &out) {
         }
     }
     out.tlas_depth = tdepth;
-    out.inst_box.assign(groups.size(), InstBox{});
-    for (size_t g = 0; g < groups.size(); ++g) {
+    out.inst_box.assign(n, InstBox{});
+    for (size_t g = 0; g < n; ++g) {
         Box b = inst_boxes[g];
         if (b.valid())
             pad_box(b);

@@ -18,7 +18,7 @@ from .integrator import DopplerToFPathIntegrator, PathIntegrator, VelocityIntegr
 
 __all__ = ["rgb2luminance", "to_tof_image", "to_tof_image_0_5", "calc_velocity_from_homo_hetero",
            "calc_velocity_from_homo_heteros", "render_image_multi_pass", "run_scene_velocity", "run_scene_radiance",
-           "run_scene_doppler_tof", "doppler_velocity_map"]
+           "run_scene_doppler_tof", "doppler_velocity_map", "update_motion"]
 
 SPEED_OF_LIGHT = 3e8   # the tutorials' constant (image_utils.py:160), not 299 792 458
 
@@ -69,6 +69,33 @@ def calc_velocity_from_homo_heteros(homodynes: Sequence, heterodynes: Sequence, 
         ratio_sum = ratio_sum + ratio * weight
         weight_sum = weight_sum + weight
     return _velocity_from_ratio(ratio_sum / weight_sum, kwargs.get("exposure_time", 0.0015), kwargs.get("w_g", 30))
+
+
+# ---- animation (main_animation.py) -------------------------------------------------------------------------------
+
+def update_motion(ctx: runtime.Context, scene, flat, motions) -> None:
+    """Next frame of an animation without re-uploading geometry: `motions` maps an index into `scene.shapes` (an
+    animated shape) to its new `AnimatedTransform`. The shape's `to_world` is replaced, the keyframes are sent with
+    `dtof_update_instances` (which rebuilds the top-level BVH for the new bounds); BLASes, materials and the film stay
+    resident. The reference's animation loop loads a new scene file per frame (main_animation.py:61-64)."""
+    from . import _abi
+    import ctypes as C
+    from .transform import Transform4
+    moving = [i for i, sh in enumerate(scene.shapes) if sh.animated]
+    first_moving = 1 if len(moving) < len(scene.shapes) else 0        # instance 0 is the static group, if any
+    for shape_index, at in motions.items():
+        if shape_index not in moving:
+            raise ValueError(f"shape {shape_index} is not animated: only the keyframes of animated shapes can change")
+        scene.shapes[shape_index].to_world = at
+        inst_index = first_moving + moving.index(shape_index)
+        t0, t1 = at.get_min_time(), at.get_max_time()                  # Instance::embree_geometry, instance.cpp:295-310
+        eye = np.eye(4, dtype=np.float32)
+        m0, m1 = Transform4(at.eval(t0), eye).m34(), Transform4(at.eval(t1), eye).m34()
+        old = flat.instances[inst_index]
+        inst = _abi.Instance(old.first_mesh, old.n_meshes, 1, float(np.float32(t0)), float(np.float32(t1)),
+                             (C.c_float * 12)(*m0.tolist()), (C.c_float * 12)(*m1.tolist()))
+        flat.instances[inst_index] = inst
+        ctx.update_instances(inst_index, [inst])
 
 
 # ---- drivers (program_runner.py) ---------------------------------------------------------------------------------

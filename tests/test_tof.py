@@ -74,3 +74,46 @@ def test_doppler_pipeline_recovers_the_ground_truth_velocity():
     assert np.median(err) < 2.5                     # m/s, of 10
     static = (np.abs(gt) < 1e-3) & (np.abs(homos[0]) > np.median(np.abs(homos[0])))
     assert np.median(np.abs(v[static])) < 1.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("big_scene", [False, True])
+def test_animation_frames_reuse_the_uploaded_scene(big_scene):
+    """update_motion (dtof_update_instances + TLAS rebuild) against a fresh upload of the same frame: the moved cube
+    leaves the bounds it was uploaded with, so a stale TLAS would cull it."""
+    import copy
+    from mitsuba3dopplertof_b200 import procedural, runtime
+    from mitsuba3dopplertof_b200.transform import AnimatedTransform, Transform4
+
+    def load():
+        sc = dt.load_file(os.path.join(gu.SCENES, "c5_slabroom.xml" if big_scene else "c1_example.xml"), resx=48, resy=48, spp=32)
+        return procedural.large_scene(sc, n=80, seed=1234) if big_scene else sc   # 76 800 triangles: BVH walked from HBM
+
+    scene = load()
+    moving = [i for i, sh in enumerate(scene.shapes) if sh.animated]
+    assert moving
+    target = moving[-1]
+    old = scene.shapes[target].to_world
+    shift = np.eye(4, dtype=np.float32)
+    shift[0, 3], shift[1, 3] = 0.35, 0.2                         # well outside the uploaded bounds
+    at = AnimatedTransform()
+    for t, tr in zip(old.times, old.transforms):
+        m = (shift @ tr.matrix).astype(np.float32)
+        at.append(t, Transform4.from_matrix(m, np.float32))
+
+    ctx = runtime.Context(0)
+    try:
+        flat = ctx.upload(scene)
+        params = scene.integrator.params(scene.sensor.sampler, seed=2)
+        frame0 = ctx.render(flat, params, develop=False)
+        tof.update_motion(ctx, scene, flat, {target: at})
+        frame1 = ctx.render(flat, params, develop=False)
+        fresh_scene = load()
+        fresh_scene.shapes[target].to_world = copy.deepcopy(at)
+        fresh = ctx.render(ctx.upload(fresh_scene), params, develop=False)
+    finally:
+        ctx.close()
+    scale = np.abs(fresh[..., :3]).max()
+    assert np.abs(frame1[..., :3] - frame0[..., :3]).max() > 1e-2 * scale      # the frame did change
+    assert np.abs(frame1[..., :3] - fresh[..., :3]).max() <= 2e-5 * scale      # and equals the fresh upload
+    assert np.abs(frame1[..., 3] - fresh[..., 3]).max() <= 2e-6 * fresh[..., 3].max()
