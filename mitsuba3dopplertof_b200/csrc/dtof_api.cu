@@ -69,7 +69,8 @@ __global__ void __launch_bounds__(kBlock, DTOF_MIN_CTAS) render_kernel(const __g
                        ni = A.insts_bytes / 16, nb = A.boxes_bytes / 16;
         float4 *sN = smem, *sT = sN + nn, *sI = sT + nt, *sB = sI + ni;
         const float4 *gT = MODE == MODE_BVH_SMEM ? A.scene.tris : A.tris_flat;
-        for (uint32_t i = threadIdx.x; i < nn; i += kBlock) sN[i] = A.scene.nodes[i];
+        if constexpr (MODE == MODE_BVH_SMEM)
+            for (uint32_t i = threadIdx.x; i < nn; i += kBlock) sN[i] = A.scene.nodes[i];
         for (uint32_t i = threadIdx.x; i < nt; i += kBlock) sT[i] = gT[i];
         for (uint32_t i = threadIdx.x; i < ni; i += kBlock) sI[i] = A.scene.insts[i];
         for (uint32_t i = threadIdx.x; i < nb; i += kBlock) sB[i] = A.inst_box[i];
@@ -1166,7 +1167,6 @@ dtof_status dtof_render_multi_pass(dtof_ctx *ctx, const dtof_params *params, uin
     CU(cudaSetDevice(ctx->device));
     const size_t n = ctx->film_px;
     const float scale = 1.f / (float) n_renders;
-    float ms_total = 0.f;
     for (uint32_t i = 0; i < n_renders; ++i) {
         dtof_params p = *params;
         p.seed = params->seed + i;
@@ -1176,7 +1176,6 @@ dtof_status dtof_render_multi_pass(dtof_ctx *ctx, const dtof_params *params, uin
         develop_accumulate_kernel<<<(unsigned) ((n + 255) / 256), 256>>>((const float4 *) ctx->d_rgbw, ctx->d_img, n, scale, i == 0);
         ctx->launches++;
         CU(cudaGetLastError());
-        (void) ms_total;
     }
     CU(cudaMemcpyAsync(image_out, ctx->d_img, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, 0));
     CU(cudaStreamSynchronize(0));
