@@ -105,7 +105,11 @@ def load_workload(name, spp=0):
     scene = dt.load_file(os.path.join(ROOT, "tests", "scenes", fn), **params)
     if name == "c5":
         from mitsuba3dopplertof_b200 import procedural
-        scene = procedural.large_scene(scene, n=592, seed=1234)
+        # 12 n^2 triangles: n = 592 -> 4.2 M (the workload); --mesh-n scales it for the mid-size experiments of the tuning log
+        n = int(os.environ.get("DTOF_BENCH_MESH_N", "592"))
+        if n != 592:
+            desc += f" [mesh n = {n}: {12 * n * n} triangles, experiment, not a bench value]"
+        scene = procedural.large_scene(scene, n=n, seed=1234)
     return scene, desc
 
 

@@ -514,6 +514,9 @@ dtof_status launch_wavefront(dtof_ctx *ctx, const RenderArgs &A, int mode, cudaS
     W.inner_threshold = 16;
     if (const char *e = getenv("DTOF_WF_INNER"))
         W.inner_threshold = (uint32_t) atoi(e);
+    W.double_step = 20;
+    if (const char *e = getenv("DTOF_WF_DOUBLE"))
+        W.double_step = (uint32_t) atoi(e);
     W.nodes_bytes = A.nodes_bytes, W.tris_bytes = A.tris_bytes, W.insts_bytes = A.insts_bytes;
     const bool doppler = A.p.integrator == DTOF_INTEGRATOR_DOPPLERTOFPATH;
     const size_t smem = mode == MODE_BVH_SMEM ? (size_t) A.nodes_bytes + A.tris_bytes + A.insts_bytes : 0;

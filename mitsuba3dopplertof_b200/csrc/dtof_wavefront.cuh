@@ -71,6 +71,7 @@ struct WfArgs {
     uint32_t bounce;
     uint32_t fetch_threshold;         // dynamic fetch: refill when fewer lanes than this still hold a ray
     uint32_t inner_threshold;         // phase scheduling: inner-node steps run while this many lanes want one
+    uint32_t double_step;             // ... and two steps per vote while this many want one (33 = never)
     uint32_t nodes_bytes, tris_bytes, insts_bytes;
 };
 
@@ -263,8 +264,11 @@ __global__ void __launch_bounds__(kWfBlock, DTOF_WF_TRACE_CTAS) wf_trace_kernel(
             }
         }
         if ((uint32_t) __popc(m_inner) >= inner_min || !m_leaf) {
-            // ---- phase A: one inner-node step
-            if (is_inner) {
+            // ---- phase A: one inner-node step, two when most of the warp wants one (halves the vote overhead)
+            const int steps = (uint32_t) __popc(m_inner) >= A.double_step ? 2 : 1;
+#pragma unroll 1
+            for (int step = 0; step < steps; ++step)
+            if ((unsigned) node < (unsigned) kDone) {
                 const float4 *np = N + 4 * (size_t) node;
                 float4 n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3];
                 float c0lx, c0hx, c0ly, c0hy, c0lz, c0hz, c1lx, c1hx, c1ly, c1hy, c1lz, c1hz, widen;
