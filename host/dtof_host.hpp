@@ -174,6 +174,8 @@ Scene load_string(const std::string &xml, const std::string &base_dir, const std
 // mesh files
 void load_mesh_file(const std::string &path, bool face_normals, std::vector<float> &pos, std::vector<uint32_t> &faces,
                     std::vector<float> &normals, std::vector<float> &uvs);
+void load_serialized_file(const std::string &path, int shape_index, bool face_normals, std::vector<float> &pos,
+                          std::vector<uint32_t> &faces, std::vector<float> &normals, std::vector<float> &uvs);
 
 // ---------------------------------------------------------------------------------------------- renderer
 // RAII wrapper of one dtof_ctx; errors become exceptions carrying dtof_last_error(). No CPU fallback.

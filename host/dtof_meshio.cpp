@@ -7,6 +7,8 @@
 #include <sstream>
 #include <tuple>
 
+#include <zlib.h>
+
 #include "dtof_host.hpp"
 
 namespace dtof_host {
@@ -306,6 +308,118 @@ void vertex_normals(const std::vector<float> &pos, const std::vector<uint32_t> &
 }
 
 } // namespace
+
+// One sub-mesh of a Mitsuba `.serialized` file (src/shapes/serialized.cpp:229-392): header 0x041C, version 3 / 4, one
+// zlib stream per sub-mesh, end-of-file offset dictionary; float or double payload narrowed to float, optional
+// normals / texture coordinates, vertex colours skipped, uint32 indices. Error texts are the reference's.
+void load_serialized_file(const std::string &path, int shape_index, bool face_normals, std::vector<float> &pos,
+                          std::vector<uint32_t> &faces, std::vector<float> &normals, std::vector<float> &uvs) {
+    auto fail = [&](const std::string &descr) -> void {
+        throw Error("Error while loading serialized file \"" + path + "\": " + descr + "!");
+    };
+    if (shape_index < 0)
+        fail("shape index must be nonnegative");
+    std::ifstream f(path, std::ios::binary);
+    if (!f)
+        fail("file not found");
+    std::vector<unsigned char> data((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    auto rd16 = [&](size_t o) { return (uint32_t) data[o] | ((uint32_t) data[o + 1] << 8); };
+    auto rd32 = [&](size_t o) { return rd16(o) | (rd16(o + 2) << 16); };
+    auto rd64 = [&](size_t o) { return (uint64_t) rd32(o) | ((uint64_t) rd32(o + 4) << 32); };
+    if (data.size() < 4 || rd16(0) != 0x041Cu)
+        fail("encountered an invalid file format");
+    const uint32_t version = rd16(2);
+    if (version != 3 && version != 4)
+        fail("encountered an incompatible file version");
+    size_t offset = 0;
+    if (shape_index != 0) {
+        if (data.size() < 8)
+            fail("encountered an invalid file format");
+        const uint32_t count = rd32(data.size() - 4);
+        if ((uint32_t) shape_index >= count)
+            fail("Unable to unserialize mesh, shape index is out of range! (requested " + std::to_string(shape_index) +
+                 " out of 0.." + std::to_string((long long) count - 1) + ")");
+        offset = version == 4 ? (size_t) rd64(data.size() - 8 * (size_t) (count - shape_index) - 4)
+                              : (size_t) rd32(data.size() - 4 * (size_t) (count - shape_index + 1));
+        if (offset + 4 > data.size())
+            fail("encountered an invalid file format");
+    }
+    // inflate the sub-mesh's stream (it ends where the next header starts; zlib stops at the stream end by itself)
+    std::vector<unsigned char> raw;
+    {
+        z_stream zs;
+        memset(&zs, 0, sizeof(zs));
+        if (inflateInit(&zs) != Z_OK)
+            fail("zlib initialisation failed");
+        zs.next_in = data.data() + offset + 4;
+        zs.avail_in = (uInt) (data.size() - offset - 4);
+        unsigned char buf[1 << 16];
+        int rc = Z_OK;
+        while (rc != Z_STREAM_END) {
+            zs.next_out = buf;
+            zs.avail_out = sizeof(buf);
+            rc = inflate(&zs, Z_NO_FLUSH);
+            if (rc != Z_OK && rc != Z_STREAM_END) {
+                inflateEnd(&zs);
+                fail("the compressed stream is corrupt");
+            }
+            raw.insert(raw.end(), buf, buf + (sizeof(buf) - zs.avail_out));
+            if (rc == Z_OK && zs.avail_in == 0 && zs.avail_out != 0)
+                break;
+        }
+        inflateEnd(&zs);
+    }
+    size_t at = 0;
+    auto take = [&](size_t n) -> const unsigned char * {
+        if (at + n > raw.size())
+            fail("unexpected end of the compressed stream");
+        const unsigned char *p = raw.data() + at;
+        at += n;
+        return p;
+    };
+    uint32_t flags;
+    memcpy(&flags, take(4), 4);
+    if (version == 4) {
+        while (*take(1) != 0) {
+        }
+    }
+    uint64_t nv, nf;
+    memcpy(&nv, take(8), 8);
+    memcpy(&nf, take(8), 8);
+    const bool dp = (flags & 0x2000u) != 0;
+    auto array = [&](size_t dim, std::vector<float> *dst) {
+        const size_t n = (size_t) nv * dim;
+        const unsigned char *p = take(n * (dp ? 8 : 4));
+        if (!dst)
+            return;
+        dst->resize(n);
+        if (dp) {
+            for (size_t i = 0; i < n; ++i) {
+                double v;
+                memcpy(&v, p + 8 * i, 8);
+                (*dst)[i] = (float) v;
+            }
+        } else {
+            memcpy(dst->data(), p, 4 * n);
+        }
+    };
+    normals.clear();
+    uvs.clear();
+    array(3, &pos);
+    if (flags & 0x1u)
+        array(3, face_normals ? nullptr : &normals);
+    if (flags & 0x2u)
+        array(2, &uvs);
+    if (flags & 0x8u)
+        array(3, nullptr);
+    faces.resize((size_t) nf * 3);
+    memcpy(faces.data(), take((size_t) nf * 12), (size_t) nf * 12);
+    for (uint32_t i : faces)
+        if ((size_t) i >= pos.size() / 3)
+            throw Error(path + ": face references a vertex out of range");
+    if (normals.empty() && !face_normals)
+        vertex_normals(pos, faces, normals);
+}
 
 void load_mesh_file(const std::string &path, bool face_normals, std::vector<float> &pos, std::vector<uint32_t> &faces,
                     std::vector<float> &normals, std::vector<float> &uvs) {

@@ -913,8 +913,8 @@ struct Loader {
         Shape sh;
         if (typ == "rectangle") sh.kind = Shape::Rectangle;
         else if (typ == "cube") sh.kind = Shape::Cube;
-        else if (typ == "obj" || typ == "ply") sh.kind = Shape::Mesh;
-        else throw Error("shape type '" + typ + "' is outside the hot-path scope (rectangle|cube|obj|ply)");
+        else if (typ == "obj" || typ == "ply" || typ == "serialized") sh.kind = Shape::Mesh;
+        else throw Error("shape type '" + typ + "' is outside the hot-path scope (rectangle|cube|obj|ply|serialized)");
         sh.id = attr(node, "id", "");
         if (p.count("flip_normals")) {
             sh.flip_normals = parse_bool(p["flip_normals"].value);
@@ -943,7 +943,7 @@ struct Loader {
                         sh.radiance[i] = (float) ep["radiance"].vec[i];
             }
         }
-        if (typ == "obj" || typ == "ply") {
+        if (typ == "obj" || typ == "ply" || typ == "serialized") {
             if (!p.count("filename"))
                 throw Error("shape '" + typ + "': missing 'filename'");
             std::string fn = p["filename"].value;
@@ -954,7 +954,16 @@ struct Loader {
                 p.erase("face_normals");
             }
             std::string path = (!fn.empty() && fn[0] == '/') ? fn : base_dir + "/" + fn;
-            load_mesh_file(path, face_normals, sh.positions, sh.faces, sh.normals, sh.texcoords);
+            if (typ == "serialized") {
+                int shape_index = 0;
+                if (p.count("shape_index")) {
+                    shape_index = (int) parse_int(p["shape_index"].value);
+                    p.erase("shape_index");
+                }
+                load_serialized_file(path, shape_index, face_normals, sh.positions, sh.faces, sh.normals, sh.texcoords);
+            } else {
+                load_mesh_file(path, face_normals, sh.positions, sh.faces, sh.normals, sh.texcoords);
+            }
             if (face_normals)
                 sh.normals.clear();
         }

@@ -499,11 +499,19 @@ dtof_status launch_wavefront(dtof_ctx *ctx, const RenderArgs &A, int mode, cudaS
     int n_streams = kWfMaxSets;
     if (const char *e = getenv("DTOF_WF_STREAMS"))
         n_streams = std::min(std::max(atoi(e), 1), kWfMaxSets);
-    const size_t cap = (size_t) std::min<unsigned long long>(A.n_local, batch);
+    size_t cap = (size_t) std::min<unsigned long long>(A.n_local, batch);
     if (cap == 0)
         return DTOF_OK;
-    n_streams = (int) std::min<unsigned long long>((unsigned long long) n_streams, (A.n_local + cap - 1) / cap);
-    dtof_status s = ensure_wavefront(ctx, cap, n_streams);
+    const int want_streams = n_streams;
+    dtof_status s;
+    for (;;) {   // a GPU that cannot hold 4 x 4.2 GiB of queues next to the scene gets smaller batches
+        n_streams = (int) std::min<unsigned long long>((unsigned long long) want_streams, (A.n_local + cap - 1) / cap);
+        s = ensure_wavefront(ctx, cap, n_streams);
+        if (s != DTOF_ERR_NOMEM || cap <= (1u << 16))
+            break;
+        cudaGetLastError();   // clear the allocation error
+        cap /= 2;
+    }
     if (s != DTOF_OK)
         return s;
     WfArgs W{};

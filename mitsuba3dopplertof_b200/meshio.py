@@ -1,4 +1,4 @@
-"""PLY / OBJ readers for the host-side scene ingest.
+"""PLY / OBJ / serialized readers for the host-side scene ingest.
 
 Behaviour follows the reference loaders for the parts the hot path observes:
   * src/shapes/ply.cpp: vertex x/y/z, optional nx/ny/nz, optional u/v (or s/t), faces as lists, polygons fan-
@@ -6,15 +6,19 @@ Behaviour follows the reference loaders for the parts the hot path observes:
     vertex normals (Mesh::recompute_vertex_normals, src/render/mesh.cpp:283-345) -- done here with the
     same angle weighting.
   * src/shapes/obj.cpp: v / vt / vn / f with index triplets, vertices de-duplicated per (v,vt,vn) key.
+  * src/shapes/serialized.cpp:229-392: the `.serialized` container (header 0x041C, version 3 or 4, one zlib stream per
+    sub-mesh, end-of-file offset dictionary selected by `shape_index`); single or double precision payload narrowed to
+    float32, optional normals / texture coordinates, vertex colours skipped, uint32 indices.
 """
 from __future__ import annotations
 
 import struct
-from typing import Optional, Tuple
+import zlib
+from typing import Optional, Sequence, Tuple
 
 import numpy as np
 
-__all__ = ["load_mesh", "load_ply", "load_obj", "vertex_normals"]
+__all__ = ["load_mesh", "load_ply", "load_obj", "load_serialized", "write_serialized", "vertex_normals"]
 
 _PLY_TYPES = {
     "char": "b", "int8": "b", "uchar": "B", "uint8": "B", "short": "h", "int16": "h", "ushort": "H", "uint16": "H",
@@ -142,8 +146,107 @@ def load_obj(path: str):
     return pos, np.asarray(faces, np.uint32).reshape(-1, 3), nrm, uv
 
 
-def load_mesh(path: str, face_normals: bool = False) -> Tuple[np.ndarray, np.ndarray, Optional[np.ndarray], Optional[np.ndarray]]:
-    pos, faces, nrm, uv = load_ply(path) if path.lower().endswith(".ply") else load_obj(path)
+_SER_HEADER, _SER_V3, _SER_V4 = 0x041C, 0x0003, 0x0004
+_SER_NORMALS, _SER_TEXCOORDS, _SER_COLORS, _SER_FACE_NORMALS, _SER_SINGLE, _SER_DOUBLE = 0x1, 0x2, 0x8, 0x10, 0x1000, 0x2000
+
+
+def load_serialized(path: str, shape_index: int = 0):
+    """One sub-mesh of a Mitsuba `.serialized` file (src/shapes/serialized.cpp:229-392). Errors carry the reference's
+    messages. Returns (positions, faces, normals | None, texcoords | None) as float32 / uint32."""
+    def fail(descr):
+        raise ValueError(f'Error while loading serialized file "{path}": {descr}!')
+
+    if shape_index < 0:
+        fail("shape index must be nonnegative")
+    try:
+        data = open(path, "rb").read()
+    except OSError:
+        fail("file not found")
+    if len(data) < 4:
+        fail("encountered an invalid file format")
+    fmt, version = struct.unpack_from("<HH", data, 0)
+    if fmt != _SER_HEADER:
+        fail("encountered an invalid file format")
+    if version not in (_SER_V3, _SER_V4):
+        fail("encountered an incompatible file version")
+    offset = 0
+    if shape_index != 0:
+        count = struct.unpack_from("<I", data, len(data) - 4)[0]
+        if shape_index >= count:
+            fail(f"Unable to unserialize mesh, shape index is out of range! (requested {shape_index} out of 0..{count - 1})")
+        if version == _SER_V4:
+            offset = struct.unpack_from("<Q", data, len(data) - 8 * (count - shape_index) - 4)[0]
+        else:
+            offset = struct.unpack_from("<I", data, len(data) - 4 * (count - shape_index + 1))[0]
+    z = zlib.decompressobj()
+    raw = z.decompress(data[offset + 4:])       # the sub-mesh's own header (4 bytes) precedes its zlib stream
+    pos_in = [0]
+
+    def take(n):
+        if pos_in[0] + n > len(raw):
+            fail("unexpected end of the compressed stream")
+        out = raw[pos_in[0]:pos_in[0] + n]
+        pos_in[0] += n
+        return out
+
+    flags = struct.unpack("<I", take(4))[0]
+    if version == _SER_V4:
+        end = raw.index(b"\0", pos_in[0])      # null-terminated shape name
+        pos_in[0] = end + 1
+    n_vertices, n_faces = struct.unpack("<QQ", take(16))
+    dtype = np.dtype("<f8") if flags & _SER_DOUBLE else np.dtype("<f4")
+
+    def array(dim):
+        a = np.frombuffer(take(n_vertices * dim * dtype.itemsize), dtype=dtype).reshape(n_vertices, dim)
+        return a.astype(np.float32)              # read_helper: (float) values[i]
+
+    pos = array(3)
+    nrm = array(3) if flags & _SER_NORMALS else None
+    uv = array(2) if flags & _SER_TEXCOORDS else None
+    if flags & _SER_COLORS:
+        array(3)                                  # advance_helper: vertex colours are skipped
+    faces = np.frombuffer(take(n_faces * 12), dtype="<u4").reshape(n_faces, 3).astype(np.uint32)
+    return pos, faces, nrm, uv
+
+
+def write_serialized(path: str, meshes: Sequence[dict], version: int = 4, double_precision: bool = False) -> None:
+    """Writes sub-meshes {positions, faces, normals?, texcoords?, colors?, name?} as a `.serialized` file (format of
+    src/shapes/serialized.cpp:98-176) -- used to produce test assets the reference's own loader reads."""
+    assert version in (_SER_V3, _SER_V4)
+    ft = "<f8" if double_precision else "<f4"
+    blob, offsets = b"", []
+    for m in meshes:
+        offsets.append(len(blob))
+        flags = _SER_DOUBLE if double_precision else _SER_SINGLE
+        body = b""
+        if version == _SER_V4:
+            body += m.get("name", "mesh").encode("utf-8") + b"\0"
+        pos = np.asarray(m["positions"], np.float64)
+        faces = np.asarray(m["faces"], np.uint32)
+        body += struct.pack("<QQ", len(pos), len(faces)) + pos.astype(ft).tobytes()
+        for key, flag in (("normals", _SER_NORMALS), ("texcoords", _SER_TEXCOORDS), ("colors", _SER_COLORS)):
+            if m.get(key) is not None:
+                flags |= flag
+                body += np.asarray(m[key], np.float64).astype(ft).tobytes()
+        body += faces.astype("<u4").tobytes()
+        blob += struct.pack("<HH", _SER_HEADER, version) + zlib.compress(struct.pack("<I", flags) + body)
+    if version == _SER_V4:
+        blob += b"".join(struct.pack("<Q", o) for o in offsets)
+    else:
+        blob += b"".join(struct.pack("<I", o) for o in offsets)
+    blob += struct.pack("<I", len(meshes))
+    with open(path, "wb") as f:
+        f.write(blob)
+
+
+def load_mesh(path: str, face_normals: bool = False, shape_index: int = 0) -> Tuple[np.ndarray, np.ndarray, Optional[np.ndarray], Optional[np.ndarray]]:
+    low = path.lower()
+    if low.endswith(".serialized"):
+        pos, faces, nrm, uv = load_serialized(path, shape_index)
+        if face_normals:
+            nrm = None                            # serialized.cpp:341-346: normals in the file are skipped
+    else:
+        pos, faces, nrm, uv = load_ply(path) if low.endswith(".ply") else load_obj(path)
     if nrm is None and not face_normals:
         nrm = vertex_normals(pos, faces)
     return pos, faces, nrm, uv

@@ -142,7 +142,7 @@ class _Loader:
     def shape(self, node) -> Shape:
         typ = self.attr(node, "type")
         p = self.props(node)
-        sh = Shape({"rectangle": "rectangle", "cube": "cube", "obj": "mesh", "ply": "mesh"}.get(typ, typ),
+        sh = Shape({"rectangle": "rectangle", "cube": "cube", "obj": "mesh", "ply": "mesh", "serialized": "mesh"}.get(typ, typ),
                    id=node.get("id", ""))
         sh.flip_normals = bool(p.pop("flip_normals", False))
         for ch in node:
@@ -156,16 +156,22 @@ class _Loader:
                 if self.attr(ch, "type") != "area":
                     raise ValueError("only 'area' emitters can be attached to shapes")
                 sh.radiance = self.props(ch).get("radiance", (1.0, 1.0, 1.0))
-        if typ in ("obj", "ply"):
-            from .meshio import load_mesh
+        if typ in ("obj", "ply", "serialized"):
+            from .meshio import load_mesh, load_serialized
             fn = p.pop("filename")
             face_normals = bool(p.pop("face_normals", False))
-            pos, faces, nrm, uv = load_mesh(os.path.join(self.base_dir, fn), face_normals=face_normals)
+            if typ == "serialized":   # the plugin, not the file extension, selects the loader (serialized.cpp:229-248)
+                pos, faces, nrm, uv = load_serialized(os.path.join(self.base_dir, fn), int(p.pop("shape_index", 0)))
+                if nrm is None and not face_normals:
+                    from .meshio import vertex_normals
+                    nrm = vertex_normals(pos, faces)
+            else:
+                pos, faces, nrm, uv = load_mesh(os.path.join(self.base_dir, fn), face_normals=face_normals)
             if face_normals:
                 nrm = None
             sh.positions, sh.faces, sh.normals, sh.texcoords = pos, faces, nrm, uv
         elif typ not in ("rectangle", "cube"):
-            raise ValueError(f"shape type '{typ}' is outside the hot-path scope (rectangle|cube|obj|ply)")
+            raise ValueError(f"shape type '{typ}' is outside the hot-path scope (rectangle|cube|obj|ply|serialized)")
         if p:
             raise ValueError(f"shape '{typ}': unreferenced property {sorted(p)}")
         return sh

@@ -52,6 +52,8 @@ CASES = {
     "c5_slabroom_full": ("c5_slabroom", {"lowpass": "false", "wave": "rectangular"}, 0, False),
     "c5_slabroom_full_sin": ("c5_slabroom", {"lowpass": "false", "wave": "sinusoidal", "hetero_frequency": 0.0}, 2, False),
     "c5_slabroom_lowpass": ("c5_slabroom", {}, 0, True),
+    # the gem as sub-mesh 1 of a double-precision v4 `.serialized` file: the reference's SerializedMesh loader
+    "c6_serialized": ("c6_serialized", {}, 4, True),
 }
 # the stock path tracer (src/integrators/path.cpp) on the same scenes: the integrator element is swapped (golden_util.swap_integrator)
 PATH_CASES = {

@@ -113,3 +113,23 @@ with open('gem.ply', 'w') as fh:
         fh.write('%g %g %g\n' % p)
     for t in f:
         fh.write('3 %d %d %d\n' % t)
+
+# gem.serialized + c6_serialized.xml: the gem of c5_slabroom.xml as sub-mesh 1 of a version-4, double-precision
+# `.serialized` file (sub-mesh 0 is a decoy triangle; normals, uvs and colours are present so that the loader has to
+# skip / narrow them). tests/golden/lanes_c6_serialized.json is the reference's own SerializedMesh loader on this file.
+import os
+import sys
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', '..'))
+from mitsuba3dopplertof_b200 import meshio   # noqa: E402
+_pos, _faces, _, _ = meshio.load_ply('gem.ply')
+_rng = np.random.default_rng(5)
+meshio.write_serialized('gem.serialized', [
+    {"name": "decoy", "positions": [[0, 0, 0], [1, 0, 0], [0, 1, 0]], "faces": [[0, 1, 2]]},
+    {"name": "gem", "positions": _pos, "faces": _faces, "normals": _pos / np.linalg.norm(_pos, axis=1, keepdims=True),
+     "texcoords": _rng.random((len(_pos), 2)), "colors": _rng.random((len(_pos), 3))}], version=4, double_precision=True)
+with open('c5_slabroom.xml') as fh:
+    _xml = fh.read().replace('<shape type="ply" id="Gem">\n\t\t<string name="filename" value="gem.ply" />',
+                             '<shape type="serialized" id="Gem">\n\t\t<string name="filename" value="gem.serialized" />\n'
+                             '\t\t<integer name="shape_index" value="1" />')
+with open('c6_serialized.xml', 'w') as fh:
+    fh.write(_xml)

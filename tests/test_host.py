@@ -126,3 +126,72 @@ def test_mesh_loaders(tmp_path):
                    "f 1/1/1 2/2/1 3/3/1 4/4/1\n")
     pos, faces, nrm, uv = load_mesh(str(obj))
     assert faces.tolist() == [[0, 1, 2], [0, 2, 3]] and uv.shape == (4, 2) and nrm.shape == (4, 3)
+
+
+# ---- `.serialized` meshes (src/shapes/serialized.cpp) -----------------------------------------------------------------
+
+def _ser_meshes():
+    rng = np.random.default_rng(3)
+    a = {"name": "a", "positions": rng.standard_normal((5, 3)), "faces": [[0, 1, 2], [2, 3, 4]],
+         "normals": rng.standard_normal((5, 3)), "texcoords": rng.random((5, 2)), "colors": rng.random((5, 3))}
+    b = {"name": "second mesh", "positions": rng.standard_normal((4, 3)), "faces": [[0, 1, 2], [0, 2, 3]]}
+    return a, b
+
+
+@pytest.mark.parametrize("version", [3, 4])
+@pytest.mark.parametrize("double_precision", [False, True])
+def test_serialized_round_trip(tmp_path, version, double_precision):
+    from mitsuba3dopplertof_b200 import meshio
+    a, b = _ser_meshes()
+    path = str(tmp_path / "m.serialized")
+    meshio.write_serialized(path, [a, b], version=version, double_precision=double_precision)
+    for index, m in enumerate((a, b)):
+        pos, faces, nrm, uv = meshio.load_serialized(path, index)
+        assert pos.dtype == np.float32 and faces.dtype == np.uint32
+        np.testing.assert_array_equal(pos, np.asarray(m["positions"]).astype(np.float32))   # narrowed like read_helper
+        np.testing.assert_array_equal(faces, np.asarray(m["faces"], np.uint32))
+        if "normals" in m:
+            np.testing.assert_array_equal(nrm, np.asarray(m["normals"]).astype(np.float32))
+            np.testing.assert_array_equal(uv, np.asarray(m["texcoords"]).astype(np.float32))
+        else:
+            assert nrm is None and uv is None
+    # load_mesh: face_normals drops the file's normals, otherwise missing normals are computed (serialized.cpp:341-346,386-391)
+    assert meshio.load_mesh(path, face_normals=True)[2] is None
+    assert meshio.load_mesh(path, shape_index=1)[2].shape == (4, 3)
+
+
+def test_serialized_errors_follow_the_reference(tmp_path):
+    from mitsuba3dopplertof_b200 import meshio
+    a, b = _ser_meshes()
+    path = str(tmp_path / "m.serialized")
+    meshio.write_serialized(path, [a, b])
+    with pytest.raises(ValueError, match="shape index is out of range"):
+        meshio.load_serialized(path, 2)
+    with pytest.raises(ValueError, match="shape index must be nonnegative"):
+        meshio.load_serialized(path, -1)
+    with pytest.raises(ValueError, match="file not found"):
+        meshio.load_serialized(str(tmp_path / "missing.serialized"))
+    bad = tmp_path / "bad.serialized"
+    bad.write_bytes(b"\x00\x00\x04\x00" + open(path, "rb").read()[4:])
+    with pytest.raises(ValueError, match="invalid file format"):
+        meshio.load_serialized(str(bad))
+    bad.write_bytes(b"\x1c\x04\x07\x00" + open(path, "rb").read()[4:])
+    with pytest.raises(ValueError, match="incompatible file version"):
+        meshio.load_serialized(str(bad))
+
+
+def test_serialized_scene_equals_the_ply_scene():
+    """tests/scenes/c6_serialized.xml holds the gem of c5_slabroom.xml as sub-mesh 1 of a double-precision v4 file."""
+    import golden_util as gu
+    a = dt.load_file(os.path.join(gu.SCENES, "c6_serialized.xml")).flatten()
+    b = dt.load_file(os.path.join(gu.SCENES, "c5_slabroom.xml")).flatten()
+    assert a.n_triangles == b.n_triangles
+    assert a.desc.n_meshes == b.desc.n_meshes
+    for i in range(a.desc.n_meshes):
+        ma, mb = a.desc.meshes[i], b.desc.meshes[i]
+        assert (ma.n_vertices, ma.n_faces) == (mb.n_vertices, mb.n_faces)
+        np.testing.assert_array_equal(np.ctypeslib.as_array(ma.positions, shape=(ma.n_vertices * 3,)),
+                                      np.ctypeslib.as_array(mb.positions, shape=(mb.n_vertices * 3,)))
+        np.testing.assert_array_equal(np.ctypeslib.as_array(ma.faces, shape=(ma.n_faces * 3,)),
+                                      np.ctypeslib.as_array(mb.faces, shape=(mb.n_faces * 3,)))
+        assert bool(ma.normals) == bool(mb.normals)
