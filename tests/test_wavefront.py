@@ -164,3 +164,21 @@ def test_two_pass_render_keeps_the_streams_across_passes(ctx, env):
     assert fused[..., 3].sum() > 0
     assert np.abs(wave[..., 3] - fused[..., 3]).max() <= 2e-6 * fused[..., 3].max()
     assert np.abs(wave[..., :3] - fused[..., :3]).max() <= 2e-5 * np.abs(fused[..., :3]).max()
+
+
+def test_full_size_c2_both_pipelines_agree(ctx, env):
+    """BASELINE config 2 at full size (512x512 @ 1024 spp, 268 M lanes, 16 batches of 16 Mi lanes on four streams):
+    the two pipelines accumulate the same per-lane values, so the films agree to float32 summation order."""
+    scene = dt.load_file(os.path.join(gu.SCENES, "c2_arealight.xml"), resx=512, resy=512)
+    params = scene.integrator.params(scene.sensor.sampler)
+    flat = ctx.upload(scene)
+    fused = _render(ctx, flat, params, env, 0)
+    wave = _render(ctx, flat, params, env, 1)
+    scale = np.abs(fused[..., :3]).max()
+    assert np.abs(wave[..., :3] - fused[..., :3]).max() <= 1e-4 * scale
+    assert np.abs(wave[..., 3] - fused[..., 3]).max() <= 1e-4 * fused[..., 3].max()
+    # tent of radius 1 is a partition of unity: interior pixels collect spp of weight
+    assert abs(wave[2:-2, 2:-2, 3].mean() - 1024.0) < 0.5
+    # heterodyne + antithetic pairs: the image is a small difference of large per-sample values
+    img = wave[..., :3] / wave[..., 3:]
+    assert np.isfinite(img).all() and np.abs(img).max() < 1.0
