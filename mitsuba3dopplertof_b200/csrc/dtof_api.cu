@@ -973,7 +973,8 @@ dtof_status dtof_upload_scene(dtof_ctx *ctx, const dtof_scene_desc *sc) {
     std::vector<TriIsect> &tris_flat = H.tris_flat;
     BuiltScene &built = H.built;
     const uint32_t gid = H.n_tris;
-    // ---- upload
+    // ---- upload (asynchronous renders of the previous scene must have finished, see dtof_update_instances)
+    CU(cudaDeviceSynchronize());
     free_scene(ctx);
     if ((s = upload_vec(ctx, built.nodes, &ctx->d_nodes)) != DTOF_OK) return s;
     if ((s = upload_vec(ctx, built.tris, &ctx->d_tris)) != DTOF_OK) return s;
@@ -1082,6 +1083,9 @@ dtof_status dtof_update_instances(dtof_ctx *ctx, uint32_t first, uint32_t n, con
         memcpy(E.m0, instances[i].m0, sizeof(E.m0));
         memcpy(E.m1, instances[i].m1, sizeof(E.m1));
     }
+    // renders launched with dtof_render_device are asynchronous and the wavefront pipeline runs on internal
+    // non-blocking streams, which a plain cudaMemcpy does not wait for: finish them before the scene changes
+    CU(cudaDeviceSynchronize());
     BuiltScene tl;
     std::vector<BvhNode> tlas;
     build_tlas(ctx->h_tlas, (int32_t) ctx->tlas_begin, tlas, tl);
