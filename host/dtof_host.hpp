@@ -92,9 +92,12 @@ struct Shape {
     bool animated() const { return has_anim && anim.size() > 1; }
 };
 
+// `point` (src/emitters/point.cpp), or with constant_env the constant environment emitter (src/emitters/constant.cpp),
+// whose radiance is kept in `intensity`
 struct PointLight {
     float position[3] = { 0, 0, 0 };
     float intensity[3] = { 1, 1, 1 };
+    bool constant_env = false;
 };
 
 struct Film {

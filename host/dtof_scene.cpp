@@ -720,7 +720,11 @@ std::unique_ptr<FlatScene> Scene::flatten() const {
         } else {
             const PointLight &pl = emitters[o.second];
             dtof_emitter e{};
-            e.kind = DTOF_EMITTER_POINT;
+            e.kind = pl.constant_env ? DTOF_EMITTER_CONSTANT : DTOF_EMITTER_POINT;
+            if (pl.constant_env)
+                for (const dtof_emitter &prev : fs->emitters)
+                    if (prev.kind == DTOF_EMITTER_CONSTANT)
+                        throw Error("Only one environment emitter can be specified per scene.");   // scene.cpp:53-55
             memcpy(e.position, pl.position, sizeof(e.position));
             memcpy(e.value, pl.intensity, sizeof(e.value));
             fs->emitters.push_back(e);
@@ -1067,10 +1071,22 @@ struct Loader {
                 sc.shapes.push_back(shape(*node));
             } else if (node->tag == "emitter") {
                 std::string typ = attr(*node, "type");
-                if (typ != "point")
-                    throw Error("emitter '" + typ + "' is outside the hot-path scope (point|area)");
+                if (typ != "point" && typ != "constant")
+                    throw Error("emitter '" + typ + "' is outside the hot-path scope (point|area|constant)");
                 auto p = props(*node);
                 PointLight pl;
+                if (typ == "constant") {
+                    pl.constant_env = true;
+                    for (auto &kv : p)
+                        if (kv.first != "radiance")
+                            throw Error("emitter 'constant': unreferenced property \"" + kv.first + "\"");
+                    if (p.count("radiance"))
+                        for (int i = 0; i < 3; ++i)
+                            pl.intensity[i] = (float) p["radiance"].vec[i];
+                    sc.order.emplace_back('e', (uint32_t) sc.emitters.size());
+                    sc.emitters.push_back(pl);
+                    continue;
+                }
                 bool have_pos = p.count("position") != 0;
                 if (have_pos)
                     for (int i = 0; i < 3; ++i)

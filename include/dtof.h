@@ -85,7 +85,7 @@ typedef enum dtof_integrator_kind {
 typedef enum dtof_rfilter { DTOF_RFILTER_BOX = 0, DTOF_RFILTER_TENT = 1, DTOF_RFILTER_GAUSSIAN = 2 } dtof_rfilter;
 typedef enum dtof_shape_kind { DTOF_SHAPE_MESH = 0, DTOF_SHAPE_RECTANGLE = 1 } dtof_shape_kind;
 typedef enum dtof_bsdf_kind { DTOF_BSDF_DIFFUSE = 0, DTOF_BSDF_NULL_BLACK = 1 } dtof_bsdf_kind;
-typedef enum dtof_emitter_kind { DTOF_EMITTER_POINT = 0, DTOF_EMITTER_AREA = 1 } dtof_emitter_kind;
+typedef enum dtof_emitter_kind { DTOF_EMITTER_POINT = 0, DTOF_EMITTER_AREA = 1, DTOF_EMITTER_CONSTANT = 2 } dtof_emitter_kind;
 
 /* ---- scene description ------------------------------------------------------------------ */
 
@@ -127,12 +127,15 @@ typedef struct dtof_bsdf {
     float reflectance[3];
 } dtof_bsdf;
 
-/* PointLight (src/emitters/point.cpp) or AreaLight (src/emitters/area.cpp) on mesh `mesh`. */
+/* PointLight (src/emitters/point.cpp), AreaLight (src/emitters/area.cpp) on mesh `mesh`, or the constant environment
+ * emitter (src/emitters/constant.cpp; at most one per scene, scene.cpp:52-56). The library derives the environment's
+ * bounding sphere from the uploaded geometry as ConstantBackgroundEmitter::set_scene does (constant.cpp:73-82). The
+ * emitters' order is the order of Scene::m_emitters (scene.cpp:34-50): it decides which one a sample selects. */
 typedef struct dtof_emitter {
     uint32_t kind;            /* dtof_emitter_kind */
     uint32_t mesh;            /* AREA: index of the emitting mesh (must be in the static group) */
     float position[3];        /* POINT */
-    float value[3];           /* POINT: intensity; AREA: radiance */
+    float value[3];           /* POINT: intensity; AREA, CONSTANT: radiance */
 } dtof_emitter;
 
 /* PerspectiveCamera, src/sensors/perspective.cpp:172-279. sample_to_camera is

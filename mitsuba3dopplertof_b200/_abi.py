@@ -16,7 +16,7 @@ WAVE_SINUSOIDAL, WAVE_RECTANGULAR, WAVE_TRIANGULAR, WAVE_TRAPEZOIDAL = range(4)
 RFILTER_BOX, RFILTER_TENT, RFILTER_GAUSSIAN = range(3)
 SHAPE_MESH, SHAPE_RECTANGLE = range(2)
 BSDF_DIFFUSE, BSDF_NULL_BLACK = range(2)
-EMITTER_POINT, EMITTER_AREA = range(2)
+EMITTER_POINT, EMITTER_AREA, EMITTER_CONSTANT = range(3)
 INTEGRATOR_DOPPLERTOFPATH, INTEGRATOR_VELOCITY, INTEGRATOR_PATH = range(3)
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED, ERR_STATE = range(6)

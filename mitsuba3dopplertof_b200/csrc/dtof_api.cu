@@ -58,7 +58,7 @@ struct RenderArgs {
     uint32_t nodes_bytes, tris_bytes, insts_bytes, boxes_bytes;
 };
 
-template <int MODE, bool STATS, bool RECORD, int KIND>
+template <int MODE, bool STATS, bool RECORD, int KIND, bool ENV>
 __global__ void __launch_bounds__(kBlock, DTOF_MIN_CTAS) render_kernel(const __grid_constant__ RenderArgs A) {
     extern __shared__ float4 smem[];
     TravPtrs TP;
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(kBlock, DTOF_MIN_CTAS) render_kernel(const __g
                 float maxt;
                 camera_ray(A.cam, ax, ay, o, d, maxt);
                 PathOut r = VELOCITY ? trace_velocity<MODE, STATS>(A.scene, TP, A.p, lane_on, o, d, maxt, st)
-                                     : trace_path<MODE, STATS, KIND == DTOF_INTEGRATOR_DOPPLERTOFPATH>(A.scene, TP, A.p, A.mod, smp,
+                                     : trace_path<MODE, STATS, KIND == DTOF_INTEGRATOR_DOPPLERTOFPATH, ENV>(A.scene, TP, A.p, A.mod, smp,
                                                                                                        lane_on, o, d, maxt, time, st);
                 V3 rgb = r.rgb;
                 if (A.film.rfilter == DTOF_RFILTER_BOX) {
@@ -384,14 +384,14 @@ Modulation make_modulation(const dtof_params &p) {
     return m;
 }
 
-template <int MODE, bool STATS, bool RECORD, int KIND>
+template <int MODE, bool STATS, bool RECORD, int KIND, bool ENV>
 dtof_status launch_variant(dtof_ctx *ctx, RenderArgs &A, int grid, cudaStream_t stream) {
     size_t smem = 0;
     if (MODE == MODE_BVH_SMEM)
         smem = (size_t) A.nodes_bytes + A.tris_bytes + A.insts_bytes + A.boxes_bytes;
     else if (MODE == MODE_FLAT_SMEM)
         smem = (size_t) A.tris_bytes + A.insts_bytes + A.boxes_bytes;
-    auto k = render_kernel<MODE, STATS, RECORD, KIND>;
+    auto k = render_kernel<MODE, STATS, RECORD, KIND, ENV>;
     if (smem)
         CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     k<<<grid, kBlock, smem, stream>>>(A);
@@ -400,18 +400,20 @@ dtof_status launch_variant(dtof_ctx *ctx, RenderArgs &A, int grid, cudaStream_t 
     return DTOF_OK;
 }
 
-template <int MODE>
+// ENV = the scene has a constant environment emitter (compiled in only for the BVH modes; launch_render never picks
+// the flat walk for such a scene). The velocity integrator does not shade, so it has no ENV instantiation.
+template <int MODE, bool ENV>
 dtof_status launch_mode(dtof_ctx *ctx, RenderArgs &A, bool record, int grid, cudaStream_t stream) {
     if (A.p.integrator == DTOF_INTEGRATOR_VELOCITY)   // counters are not instrumented for the velocity / path variants
-        return record ? launch_variant<MODE, false, true, DTOF_INTEGRATOR_VELOCITY>(ctx, A, grid, stream)
-                      : launch_variant<MODE, false, false, DTOF_INTEGRATOR_VELOCITY>(ctx, A, grid, stream);
+        return record ? launch_variant<MODE, false, true, DTOF_INTEGRATOR_VELOCITY, false>(ctx, A, grid, stream)
+                      : launch_variant<MODE, false, false, DTOF_INTEGRATOR_VELOCITY, false>(ctx, A, grid, stream);
     if (A.p.integrator == DTOF_INTEGRATOR_PATH)
-        return record ? launch_variant<MODE, false, true, DTOF_INTEGRATOR_PATH>(ctx, A, grid, stream)
-                      : launch_variant<MODE, false, false, DTOF_INTEGRATOR_PATH>(ctx, A, grid, stream);
+        return record ? launch_variant<MODE, false, true, DTOF_INTEGRATOR_PATH, ENV>(ctx, A, grid, stream)
+                      : launch_variant<MODE, false, false, DTOF_INTEGRATOR_PATH, ENV>(ctx, A, grid, stream);
     if (record)
-        return launch_variant<MODE, false, true, DTOF_INTEGRATOR_DOPPLERTOFPATH>(ctx, A, grid, stream);
-    return ctx->stats_enabled ? launch_variant<MODE, true, false, DTOF_INTEGRATOR_DOPPLERTOFPATH>(ctx, A, grid, stream)
-                              : launch_variant<MODE, false, false, DTOF_INTEGRATOR_DOPPLERTOFPATH>(ctx, A, grid, stream);
+        return launch_variant<MODE, false, true, DTOF_INTEGRATOR_DOPPLERTOFPATH, ENV>(ctx, A, grid, stream);
+    return ctx->stats_enabled ? launch_variant<MODE, true, false, DTOF_INTEGRATOR_DOPPLERTOFPATH, ENV>(ctx, A, grid, stream)
+                              : launch_variant<MODE, false, false, DTOF_INTEGRATOR_DOPPLERTOFPATH, ENV>(ctx, A, grid, stream);
 }
 
 // ---- wavefront pipeline (dtof_wavefront.cuh) ------------------------------------------------------------------
@@ -660,6 +662,9 @@ dtof_status launch_render(dtof_ctx *ctx, const dtof_params *p, float *d_rgbw, cu
     if (want == MODE_BVH_GLOBAL || (want == MODE_BVH_SMEM && bvh_bytes + 1024 <= ctx->smem_optin) ||
         (want == MODE_FLAT_SMEM && flat_bytes + 1024 <= ctx->smem_optin))
         mode = want;
+    const bool env = ctx->ds.env_emitter >= 0;
+    if (env && mode == MODE_FLAT_SMEM)   // the flat walk has no environment-emitter instantiation
+        mode = bvh_bytes + 1024 <= ctx->smem_optin ? MODE_BVH_SMEM : MODE_BVH_GLOBAL;
     // the traversal counters are defined on the BVH walk (algorithmic work of the scene), whatever
     // mode the production launch of this scene picks
     if (ctx->stats_enabled && !record && mode == MODE_FLAT_SMEM)
@@ -697,11 +702,13 @@ dtof_status launch_render(dtof_ctx *ctx, const dtof_params *p, float *d_rgbw, cu
         return DTOF_OK;
     }
     if (mode == MODE_FLAT_SMEM)
-        s = launch_mode<MODE_FLAT_SMEM>(ctx, A, record, grid, stream);
+        s = launch_mode<MODE_FLAT_SMEM, false>(ctx, A, record, grid, stream);
     else if (mode == MODE_BVH_SMEM)
-        s = launch_mode<MODE_BVH_SMEM>(ctx, A, record, grid, stream);
+        s = env ? launch_mode<MODE_BVH_SMEM, true>(ctx, A, record, grid, stream)
+                : launch_mode<MODE_BVH_SMEM, false>(ctx, A, record, grid, stream);
     else
-        s = launch_mode<MODE_BVH_GLOBAL>(ctx, A, record, grid, stream);
+        s = env ? launch_mode<MODE_BVH_GLOBAL, true>(ctx, A, record, grid, stream)
+                : launch_mode<MODE_BVH_GLOBAL, false>(ctx, A, record, grid, stream);
     if (s != DTOF_OK)
         return s;
     ctx->last_mode = mode;
@@ -726,6 +733,9 @@ struct HostScene {
     std::vector<TriIsect> tris_flat;
     BuiltScene built;
     uint32_t n_tris = 0;
+    // constant environment emitter: index (-1: none) and the scene's bounding sphere (constant.cpp:73-82)
+    int32_t env_emitter = -1;
+    float env_center[3] = { 0.f, 0.f, 0.f }, env_radius = 1.f;
 };
 
 dtof_status prepare_scene(dtof_ctx *ctx, const dtof_scene_desc *sc, HostScene &H) {
@@ -868,8 +878,13 @@ dtof_status prepare_scene(dtof_ctx *ctx, const dtof_scene_desc *sc, HostScene &H
     bool all_point = true;
     for (uint32_t i = 0; i < sc->n_emitters; ++i) {
         const dtof_emitter &e = sc->emitters[i];
-        if (e.kind > DTOF_EMITTER_AREA)
+        if (e.kind > DTOF_EMITTER_CONSTANT)
             return fail(ctx, DTOF_ERR_UNSUPPORTED, "emitter kind %u is outside the hot-path scope", e.kind);
+        if (e.kind == DTOF_EMITTER_CONSTANT) {
+            if (H.env_emitter >= 0)
+                return fail(ctx, DTOF_ERR_INVALID, "Only one environment emitter can be specified per scene.");   // scene.cpp:53-55
+            H.env_emitter = (int32_t) i;
+        }
         if (e.kind == DTOF_EMITTER_AREA && (e.mesh >= sc->n_meshes || sc->meshes[e.mesh].emitter != (int32_t) i))
             return fail(ctx, DTOF_ERR_INVALID, "area emitter %u and its mesh do not reference each other", i);
         all_point = all_point && e.kind == DTOF_EMITTER_POINT;
@@ -882,6 +897,45 @@ dtof_status prepare_scene(dtof_ctx *ctx, const dtof_scene_desc *sc, HostScene &H
     build_scene_bvh(groups, built);
     if (built.max_depth + built.tlas_depth + 4 > kStackSize)
         return fail(ctx, DTOF_ERR_UNSUPPORTED, "BVH too deep for the traversal stack (%d + %d)", built.max_depth, built.tlas_depth);
+    if (H.env_emitter >= 0) {
+        // Scene::bbox (scene.cpp:36): union of the shapes' boxes -- static shapes: their vertices; an instance: the 8
+        // corners of its group's box under both keyframes (instance.cpp:101-114). Then ConstantBackgroundEmitter::
+        // set_scene: bounding sphere, radius * (1 + RayEpsilon), at least RayEpsilon; an empty scene gives (0, 1).
+        float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
+        auto grow = [&](const float *q) {
+            for (int a = 0; a < 3; ++a)
+                lo[a] = std::min(lo[a], q[a]), hi[a] = std::max(hi[a], q[a]);
+        };
+        for (uint32_t g = 0; g < sc->n_instances; ++g) {
+            const InstBox &ob = built.group_box[g];
+            if (!(ob.lox <= ob.hix))
+                continue;
+            for (int c = 0; c < 8; ++c) {
+                const float p[3] = { (c & 1) ? ob.hix : ob.lox, (c & 2) ? ob.hiy : ob.loy, (c & 4) ? ob.hiz : ob.loz };
+                if (!sc->instances[g].animated) {
+                    grow(p);
+                    continue;
+                }
+                for (const float *M : { sc->instances[g].m0, sc->instances[g].m1 }) {   // Transform * Point, column by column
+                    float q[3];
+                    for (int r = 0; r < 3; ++r)
+                        q[r] = std::fmaf(M[4 * r + 3], 1.f, std::fmaf(M[4 * r + 2], p[2], std::fmaf(M[4 * r + 1], p[1], M[4 * r] * p[0])));
+                    grow(q);
+                }
+            }
+        }
+        if (lo[0] <= hi[0]) {
+            float c[3], d2 = 0.f;
+            for (int a = 0; a < 3; ++a) {
+                c[a] = (lo[a] + hi[a]) * .5f;
+                H.env_center[a] = c[a];
+            }
+            HV3 dv{ c[0] - hi[0], c[1] - hi[1], c[2] - hi[2] };
+            d2 = hdot(dv, dv);
+            const float eps = 1500.f * 5.9604644775390625e-08f;   // math::RayEpsilon<float>
+            H.env_radius = std::max(eps, std::sqrt(d2) * (1.f + eps));
+        }
+    }
     std::vector<InstRec> &insts = H.insts;
     insts.assign(sc->n_instances, InstRec{});
     std::vector<TriIsect> &tris_flat = H.tris_flat;   // scene (gid) order, for the flat traversal of tiny scenes
@@ -1023,6 +1077,13 @@ dtof_status dtof_upload_scene(dtof_ctx *ctx, const dtof_scene_desc *sc) {
     D.n_nodes = (uint32_t) built.nodes.size();
     D.n_tris = (uint32_t) built.tris.size();
     D.has_geometry = built.has_geometry ? 1u : 0u;
+    D.env_emitter = H.env_emitter;
+    if (H.env_emitter >= 0) {
+        const dtof_emitter &e = sc->emitters[H.env_emitter];
+        D.env_r = e.value[0], D.env_g = e.value[1], D.env_b = e.value[2];
+        D.env_cx = H.env_center[0], D.env_cy = H.env_center[1], D.env_cz = H.env_center[2];
+        D.env_radius = H.env_radius;
+    }
     ctx->cam = sc->camera;
     ctx->film = sc->film;
     ctx->film_px = (size_t) sc->film.width * sc->film.height;

@@ -373,6 +373,15 @@ DTOF_DEV V3 square_to_cosine_hemisphere(float sx, float sy) {
     float z = fsqrt(fmaxf(1.f - fmaf(py, py, px * px), 0.f));
     return v3(px, py, z);
 }
+// warp::square_to_uniform_sphere (include/mitsuba/core/warp.h:250-255)
+DTOF_DEV V3 square_to_uniform_sphere(float sx, float sy) {
+    float z = fmaf(-2.f, sy, 1.f);
+    float r = fsqrt(fmaxf(fmaf(-z, z, 1.f), 0.f));   // circ(z) = safe_sqrt(fnmadd(z, z, 1))
+    float s, c;
+    dr_sincos(2.f * kPi * sx, s, c);
+    return v3(r * c, r * s, z);
+}
+constexpr float kInvFourPi = 0.07957747154594766788f;
 DTOF_DEV void coordinate_system(V3 n, V3 &s, V3 &t) {
     float sign = copysignf(1.f, n.z);
     float a = -frcp(sign + n.z), b = n.x * n.y * a;
@@ -398,6 +407,10 @@ struct DeviceScene {
     const float *area_cdf, *area_pmf;
     int32_t root;
     uint32_t n_emitters, n_insts, n_nodes, n_tris, has_geometry;
+    // constant environment emitter (src/emitters/constant.cpp): index into `emitters` or -1; radiance; bounding sphere
+    int32_t env_emitter;
+    float env_r, env_g, env_b;
+    float env_cx, env_cy, env_cz, env_radius;
 };
 
 struct Counters {

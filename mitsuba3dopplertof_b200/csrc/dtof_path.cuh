@@ -73,11 +73,11 @@ struct PathState {
     bool valid_ray, prev_bsdf_delta, active;
     // eta: every BSDF in scope has eta = 1 on a live path (bs.eta is 0 only where the throughput is 0 too and the
     // lane stops), so `path_length += t * eta`, `eta *= bs.eta` and `rr_prob = tmax * eta^2` reduce to eta == 1.
-    DTOF_DEV void init(bool on) {
+    DTOF_DEV void init(bool on, bool env_visible) {
         throughput = v3(1, 1, 1), result = v3(0, 0, 0), prev_p = v3(0, 0, 0);
         path_length = 0.f, prev_bsdf_pdf = 1.f;
         depth = 0;
-        valid_ray = false;                        // no environment emitter in scope (:102)
+        valid_ray = env_visible;                  // !hide_emitters && the scene has an environment emitter (:102)
         prev_bsdf_delta = true;
         active = on;
     }
@@ -97,7 +97,10 @@ struct PendingNee {
 // path ray on exit.
 // DOPPLER = false is the stock path tracer (src/integrators/path.cpp:103-283): no time wrap, modulation weight 1,
 // every draw is Sampler::next_1d / next_2d, i.e. the independent stream only (the path stream does not move).
-template <bool DOPPLER>
+// ENV compiles the constant environment emitter in (src/emitters/constant.cpp). It is a template parameter because the
+// fused kernel runs at 64 registers: the extra live values cost it 4 % even when no scene uses them
+// (profiles/r01_tuning.md), so scenes without an environment emitter run the ENV = false instantiation.
+template <bool DOPPLER, bool ENV>
 DTOF_DEV void shade_bounce(const DeviceScene &S, const float4 *__restrict__ I, const dtof_params &P, const Modulation &mod,
                            LaneSampler &smp, PathState &ps, const bool hit, const Hit &h, V3 &ray_o, V3 &ray_d,
                            float &ray_maxt, const float ray_time, const float emitter_pmf, PendingNee &nee) {
@@ -143,6 +146,17 @@ DTOF_DEV void shade_bounce(const DeviceScene &S, const float4 *__restrict__ I, c
         result = v3(fmaf(throughput.x, c.x, result.x), fmaf(throughput.y, c.y, result.y),
                     fmaf(throughput.z, c.z, result.z));
     }
+    // ---- the ray left the scene: the environment emitter is "hit" (si.emitter(scene), scene.h:583-594). The path
+    // length is not advanced (:141); DirectionSample(scene, si, prev_si).d = -si.wi = ray_d (records.h:173-180)
+    if (ENV && !valid && S.env_emitter >= 0) {
+        float em_pdf = ps.prev_bsdf_delta ? 0.f : kInvFourPi * emitter_pmf;     // constant.cpp:141-146, scene.cpp:293-299
+        float mis_bsdf = mis_weight(ps.prev_bsdf_pdf, em_pdf);
+        float lw = DOPPLER ? mod.eval(ray_time, path_length) : 1.f;
+        V3 Le = ps.prev_bsdf_pdf > 0.f ? v3(S.env_r, S.env_g, S.env_b) : v3(0, 0, 0);
+        V3 c = Le * mis_bsdf * lw;
+        result = v3(fmaf(throughput.x, c.x, result.x), fmaf(throughput.y, c.y, result.y),
+                    fmaf(throughput.z, c.z, result.z));
+    }
     const bool active_next = (depth + 1 < max_depth) && valid;         // :171
     const bool smooth = (bsdf_flags & 2u) != 0, twosided = (bsdf_flags & 1u) != 0;
 
@@ -178,6 +192,14 @@ DTOF_DEV void shade_bounce(const DeviceScene &S, const float4 *__restrict__ I, c
             ds_d = ds_d * inv_dist;
             float f = inv_dist * inv_dist;
             spec = v3(em.vr * f, em.vg * f, em.vb * f);
+        } else if (ENV && em.kind == DTOF_EMITTER_CONSTANT) {                  // ConstantBackgroundEmitter::sample_direction, constant.cpp:112-139
+            ds_d = square_to_uniform_sphere(sx, sy);
+            V3 rel = si.p - v3(S.env_cx, S.env_cy, S.env_cz);
+            float radius = fmaxf(S.env_radius, fsqrt(dot3(rel, rel)));   // the sphere grows to contain the reference point
+            ds_dist = 2.f * radius;
+            ds_p = fma3(ds_d, ds_dist, si.p);
+            ds_pdf = kInvFourPi;
+            spec = v3(em.vr, em.vg, em.vb) / ds_pdf;
         } else {                                                        // AreaLight / Shape::sample_direction
             sample_position(S, S.meshes[em.mesh], sx, sy, ds_p, ds_n, ds_pdf);
             ds_d = ds_p - si.p;
@@ -272,14 +294,14 @@ DTOF_DEV void shade_bounce(const DeviceScene &S, const float4 *__restrict__ I, c
 //            and operands of :214-226.
 // Only ~a dozen values live across the shadow traversal (instead of the whole surface interaction), which is what
 // lets the kernel run at 4+ CTAs per SM. All lanes of a warp are always in the same phase.
-template <int MODE, bool STATS, bool DOPPLER>
+template <int MODE, bool STATS, bool DOPPLER, bool ENV>
 DTOF_DEV PathOut trace_path(const DeviceScene &S, const TravPtrs &TP, const dtof_params &P, const Modulation &mod,
                             LaneSampler &smp, bool lane_on, V3 ray_o, V3 ray_d, float ray_maxt, float time_in,
                             Counters &st) {
     PathOut out{ v3(0, 0, 0), 0.f, 0 };
     const float ray_time = (!DOPPLER || time_in < P.time) ? time_in : time_in - P.time;    // dopplertofpath.cpp:93
     PathState ps;
-    ps.init(lane_on && P.max_depth != 0);
+    ps.init(lane_on && P.max_depth != 0, ENV && S.env_emitter >= 0 && !P.hide_emitters);
     const float emitter_pmf = S.n_emitters ? 1.f / (float) S.n_emitters : 0.f;   // once per sample: IEEE
 
     // state handed from phase 0 to phase 1
@@ -308,7 +330,7 @@ DTOF_DEV PathOut trace_path(const DeviceScene &S, const TravPtrs &TP, const dtof
         nee.want = false;
         if (!ps.active)
             continue;
-        shade_bounce<DOPPLER>(S, TP.I, P, mod, smp, ps, hit, h, ray_o, ray_d, ray_maxt, ray_time, emitter_pmf, nee);
+        shade_bounce<DOPPLER, ENV>(S, TP.I, P, mod, smp, ps, hit, h, ray_o, ray_d, ray_maxt, ray_time, emitter_pmf, nee);
     }
     out.rgb = ps.valid_ray ? ps.result : v3(0, 0, 0);
     out.path_length = ps.path_length;

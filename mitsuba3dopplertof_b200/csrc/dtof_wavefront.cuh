@@ -144,7 +144,9 @@ __global__ void __launch_bounds__(kWfBlock) wf_generate_kernel(const __grid_cons
             B.rng_path[s] = make_ulonglong2(smp.rng_path.state, smp.rng_path.inc);
         B.thr_len[s] = make_float4(1.f, 1.f, 1.f, 0.f);
         B.res_pdf[s] = make_float4(0.f, 0.f, 0.f, 1.f);
-        B.prev_meta[s] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0x80000000u));   // depth 0, prev_bsdf_delta
+        // depth 0, prev_bsdf_delta, valid_ray = environment emitter visible (dopplertofpath.cpp:102)
+        B.prev_meta[s] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0x80000000u |
+                                     ((A.scene.env_emitter >= 0 && !A.p.hide_emitters) ? 0x40000000u : 0u)));
         B.film_pos[s] = make_float2(spx, spy);
         if (any_depth) {
             B.q_o[0][s] = make_float4(o.x, o.y, o.z, maxt);
@@ -409,7 +411,7 @@ wf_shade_kernel(const __grid_constant__ WfArgs A) {
                 smp.rng_path.state = gp.x, smp.rng_path.inc = gp.y;
             }
             smp.draws = 0;
-            shade_bounce<DOPPLER>(A.scene, A.scene.insts, A.p, A.mod, smp, ps, hit, h, ray_o, ray_d, ray_maxt, ray_time,
+            shade_bounce<DOPPLER, true>(A.scene, A.scene.insts, A.p, A.mod, smp, ps, hit, h, ray_o, ray_d, ray_maxt, ray_time,
                                   emitter_pmf, nee);
             B.rng[s] = make_ulonglong2(smp.rng.state, smp.rng.inc);
             if (DOPPLER)

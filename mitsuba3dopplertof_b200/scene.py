@@ -23,7 +23,7 @@ from . import _abi
 from .transform import AnimatedTransform, Transform4, perspective_projection
 
 __all__ = [
-    "Bsdf", "Shape", "PointLight", "Film", "CorrelatedSampler", "PerspectiveSensor", "Scene", "FlatScene",
+    "Bsdf", "Shape", "PointLight", "ConstantEmitter", "Film", "CorrelatedSampler", "PerspectiveSensor", "Scene", "FlatScene",
     "rectangle", "cube", "mesh",
 ]
 
@@ -78,6 +78,13 @@ class PointLight:
     """src/emitters/point.cpp:65-85: position = ``position`` or translation of ``to_world``."""
     position: Sequence[float] = (0.0, 0.0, 0.0)
     intensity: Sequence[float] = (1.0, 1.0, 1.0)
+
+
+@dataclass
+class ConstantEmitter:
+    """src/emitters/constant.cpp: constant environment emitter (`radiance`, RGB); at most one per scene. Its bounding
+    sphere comes from the scene's geometry (set_scene, :73-82) and is derived by the library at upload."""
+    radiance: Sequence[float] = (1.0, 1.0, 1.0)
 
 
 @dataclass
@@ -350,6 +357,11 @@ class Scene:
                     emitters.append(_abi.Emitter(_abi.EMITTER_AREA, mi_, (C.c_float * 3)(0, 0, 0), rgb3(s.radiance)))
             else:
                 e = self.emitters[i]
-                emitters.append(_abi.Emitter(_abi.EMITTER_POINT, 0, (C.c_float * 3)(*[float(f32(x)) for x in e.position]),
-                                             rgb3(e.intensity)))
+                if isinstance(e, ConstantEmitter):
+                    if any(em.kind == _abi.EMITTER_CONSTANT for em in emitters):
+                        raise ValueError("Only one environment emitter can be specified per scene.")   # scene.cpp:53-55
+                    emitters.append(_abi.Emitter(_abi.EMITTER_CONSTANT, 0, (C.c_float * 3)(0, 0, 0), rgb3(e.radiance)))
+                else:
+                    emitters.append(_abi.Emitter(_abi.EMITTER_POINT, 0, (C.c_float * 3)(*[float(f32(x)) for x in e.position]),
+                                                 rgb3(e.intensity)))
         return FlatScene(meshes, instances, bsdfs, emitters, self.sensor.abi(), self.sensor.film.abi())

@@ -17,7 +17,7 @@ from typing import Dict, Optional
 import numpy as np
 
 from .integrator import DopplerToFPathIntegrator, PathIntegrator, VelocityIntegrator
-from .scene import (Bsdf, CorrelatedSampler, Film, PerspectiveSensor, PointLight, Scene, Shape)
+from .scene import (Bsdf, ConstantEmitter, CorrelatedSampler, Film, PerspectiveSensor, PointLight, Scene, Shape)
 from .transform import AnimatedTransform, Transform4
 
 __all__ = ["load_file", "load_string"]
@@ -254,9 +254,16 @@ class _Loader:
                 sc.shapes.append(self.shape(node))
             elif node.tag == "emitter":
                 typ = self.attr(node, "type")
-                if typ != "point":
-                    raise ValueError(f"emitter '{typ}' is outside the hot-path scope (point|area)")
+                if typ not in ("point", "constant"):
+                    raise ValueError(f"emitter '{typ}' is outside the hot-path scope (point|area|constant)")
                 p = self.props(node)
+                if typ == "constant":
+                    unknown = set(p) - {"radiance"}
+                    if unknown:
+                        raise ValueError(f"emitter 'constant': unreferenced property {sorted(unknown)}")
+                    order.append(("emitter", len(sc.emitters)))
+                    sc.emitters.append(ConstantEmitter(p.get("radiance", (1.0,) * 3)))
+                    continue
                 pos = p.get("position")
                 for ch in node:
                     if ch.tag == "transform" and ch.get("name") == "to_world":

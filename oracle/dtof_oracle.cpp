@@ -412,6 +412,16 @@ struct Modulation {
 // ------------------------------------------------------------------------------------------
 // Warps / frames
 // ------------------------------------------------------------------------------------------
+// warp::square_to_uniform_sphere, include/mitsuba/core/warp.h:250-255
+constexpr float kInvFourPi = 0.07957747154594766788f;
+inline V3 square_to_uniform_sphere(float sx, float sy) {
+    float z = fmaf(-2.f, sy, 1.f);                       // fnmadd(2, y, 1)
+    float r = sqrtf(std::max(fmaf(-z, z, 1.f), 0.f));    // circ(z) = safe_sqrt(fnmadd(z, z, 1))
+    float s, c;
+    dr_sincos(2.f * 3.14159265358979323846f * sx, s, c);
+    return v3(r * c, r * s, z);
+}
+
 // square_to_uniform_disk_concentric + square_to_cosine_hemisphere, include/mitsuba/core/warp.h:54-89,320-330
 inline V3 square_to_cosine_hemisphere(float sx, float sy) {
     float x = fmaf(2.f, sx, -1.f), y = fmaf(2.f, sy, -1.f);
@@ -498,6 +508,11 @@ struct dtof_oracle_scene {
     dtof_camera cam;
     dtof_film film;
     mutable Counters stats;
+    // constant environment emitter (src/emitters/constant.cpp): index into `emitters` (-1: none) and its bounding
+    // sphere (ConstantBackgroundEmitter::set_scene, :73-82)
+    int env_emitter = -1;
+    V3 env_center = v3(0, 0, 0);
+    float env_radius = 1.f;
 };
 
 namespace {
@@ -872,7 +887,7 @@ PathResult trace_path(const dtof_oracle_scene &sc, const dtof_params &P, const M
     V3 throughput = v3(1, 1, 1), result = v3(0, 0, 0);
     float path_length = 0.f, eta = 1.f;
     uint32_t depth = 0;
-    bool valid_ray = false; // no environment emitter in scope (:102)
+    bool valid_ray = !P.hide_emitters && sc.env_emitter >= 0; // :102
     V3 prev_p = v3(0, 0, 0);
     float prev_bsdf_pdf = 1.f;
     bool prev_bsdf_delta = true;
@@ -918,6 +933,20 @@ PathResult trace_path(const dtof_oracle_scene &sc, const dtof_params &P, const M
                         fmaf(throughput.z, c.z, result.z));
         }
 
+        // the ray left the scene: si.emitter(scene) is the environment emitter (scene.h:583-594). The path length is
+        // not advanced (:141); DirectionSample(scene, si, prev_si).d = -si.wi = ray_d (records.h:173-180)
+        if (!valid && sc.env_emitter >= 0) {
+            const dtof_emitter &em = sc.emitters[sc.env_emitter];
+            // Scene::pdf_emitter_direction (scene.cpp:293-299) x ConstantBackgroundEmitter::pdf_direction (:141-146)
+            float em_pdf = prev_bsdf_delta ? 0.f : kInvFourPi * emitter_pmf;
+            float mis_bsdf = mis_weight(prev_bsdf_pdf, em_pdf);
+            float lw = doppler ? mod.eval(ray_time, path_length) : 1.f;
+            V3 Le = prev_bsdf_pdf > 0.f ? v3(em.value[0], em.value[1], em.value[2]) : v3(0, 0, 0); // eval(si, active)
+            V3 c = Le * mis_bsdf * lw;
+            result = v3(fmaf(throughput.x, c.x, result.x), fmaf(throughput.y, c.y, result.y),
+                        fmaf(throughput.z, c.z, result.z));
+        }
+
         bool active_next = (depth + 1 < max_depth) && valid; // :171
 
         // ---- emitter sampling (:187-202); the 2D sample is ALWAYS drawn (Appendix A.6e)
@@ -953,6 +982,16 @@ PathResult trace_path(const dtof_oracle_scene &sc, const dtof_params &P, const M
                 ds.d = ds.d * inv_dist;
                 float f = inv_dist * inv_dist;
                 spec = v3(em.value[0] * f, em.value[1] * f, em.value[2] * f);
+            } else if (em.kind == DTOF_EMITTER_CONSTANT) { // ConstantBackgroundEmitter::sample_direction, constant.cpp:112-139
+                ds.d = square_to_uniform_sphere(sx, sy);
+                V3 rel = si.p - sc.env_center;
+                float radius = std::max(sc.env_radius, sqrtf(dot3(rel, rel))); // grows to contain the reference point
+                ds.dist = 2.f * radius;
+                ds.p = fma3(ds.d, ds.dist, si.p);
+                ds.n = v3(-ds.d.x, -ds.d.y, -ds.d.z);
+                ds.pdf = kInvFourPi;
+                ds.delta = false;
+                spec = v3(em.value[0] / ds.pdf, em.value[1] / ds.pdf, em.value[2] / ds.pdf);
             } else { // AreaLight::sample_direction (area.cpp:117-146) -> Shape::sample_direction (shape.cpp:370-387)
                 const OMesh &em_mesh = sc.meshes[em.mesh];
                 sample_position(em_mesh, sx, sy, ds.p, ds.n, ds.pdf);
@@ -1378,6 +1417,46 @@ dtof_oracle_scene *dtof_oracle_scene_create(const dtof_scene_desc *d, int use_bv
         bool bvh = use_bvh > 0 || (use_bvh < 0 && g.n_tris > 64);
         if (bvh && g.n_tris > 0)
             build_bvh(s->tris, g);
+    }
+    for (uint32_t i = 0; i < d->n_emitters; ++i)
+        if (d->emitters[i].kind == DTOF_EMITTER_CONSTANT)
+            s->env_emitter = (int) i;
+    if (s->env_emitter >= 0) {
+        // Scene::bbox (scene.cpp:36) = union of the shapes' boxes: static shapes by their vertices, an instance by the
+        // 8 corners of its group's box under both keyframes (instance.cpp:101-114); then the bounding sphere with
+        // radius * (1 + RayEpsilon), at least RayEpsilon (constant.cpp:73-82); an empty scene gives ((0,0,0), 1)
+        V3 lo = v3(INFINITY, INFINITY, INFINITY), hi = v3(-INFINITY, -INFINITY, -INFINITY);
+        auto grow = [&](V3 q) {
+            lo = v3(std::min(lo.x, q.x), std::min(lo.y, q.y), std::min(lo.z, q.z));
+            hi = v3(std::max(hi.x, q.x), std::max(hi.y, q.y), std::max(hi.z, q.z));
+        };
+        for (uint32_t i = 0; i < d->n_instances; ++i) {
+            const dtof_instance &in = d->instances[i];
+            V3 glo = v3(INFINITY, INFINITY, INFINITY), ghi = v3(-INFINITY, -INFINITY, -INFINITY);
+            bool any = false;
+            for (uint32_t mi = in.first_mesh; mi < in.first_mesh + in.n_meshes; ++mi)
+                for (const V3 &q : s->meshes[mi].pos) {
+                    glo = v3(std::min(glo.x, q.x), std::min(glo.y, q.y), std::min(glo.z, q.z));
+                    ghi = v3(std::max(ghi.x, q.x), std::max(ghi.y, q.y), std::max(ghi.z, q.z));
+                    any = true;
+                }
+            if (!any)
+                continue;
+            for (int c = 0; c < 8; ++c) {
+                V3 q = v3((c & 1) ? ghi.x : glo.x, (c & 2) ? ghi.y : glo.y, (c & 4) ? ghi.z : glo.z);
+                if (!in.animated) {
+                    grow(q);
+                } else {
+                    grow(xf_point(s->groups[i].m0, q));
+                    grow(xf_point(s->groups[i].m1, q));
+                }
+            }
+        }
+        if (lo.x <= hi.x) {
+            s->env_center = (lo + hi) * .5f;
+            V3 dv = s->env_center - hi;
+            s->env_radius = std::max(kRayEps, sqrtf(dot3(dv, dv)) * (1.f + kRayEps));
+        }
     }
     return s;
 }

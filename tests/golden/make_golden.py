@@ -54,6 +54,9 @@ CASES = {
     "c5_slabroom_lowpass": ("c5_slabroom", {}, 0, True),
     # the gem as sub-mesh 1 of a double-precision v4 `.serialized` file: the reference's SerializedMesh loader
     "c6_serialized": ("c6_serialized", {}, 4, True),
+    # open scene (floor + the two moving boxes) under a constant environment emitter + the point light (2 emitters)
+    "c7_constant": ("c7_constant", {"max_depth": 5, "pcd": 5}, 0, True),
+    "c7_constant_homodyne": ("c7_constant", {"hetero_frequency": 0.0, "tsm": "uniform", "shift": 0.0, "rr_depth": 2, "max_depth": 8}, 6, True),
 }
 # the stock path tracer (src/integrators/path.cpp) on the same scenes: the integrator element is swapped (golden_util.swap_integrator)
 PATH_CASES = {
@@ -62,6 +65,7 @@ PATH_CASES = {
     "path_c2b_rr": ("c2b_two_emitters", {"max_depth": 16, "rr_depth": 2}, 5, True),
     "path_c3_rotor": ("c3_rotor", {"resx": 512, "resy": 512, "spp": 64}, 2, True),
     "path_c5_slabroom": ("c5_slabroom", {}, 1, True),
+    "path_c7_constant": ("c7_constant", {}, 3, True),
 }
 # the ground-truth radial velocity integrator (src/integrators/velocity.cpp). Its value (t2 - t1) / time scales by exactly
 # 2^20 under the time scaling; golden_util.load_case undoes it.

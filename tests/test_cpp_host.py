@@ -54,7 +54,8 @@ CASES = [
     ("c3_rotor.xml", {"pcn": 4}),
     ("c4_domino.xml", {"w_g": 150}),
     ("c5_slabroom.xml", {"tcn": 3, "pcn": 6}),
-    ("c6_serialized.xml", {}),                      # `serialized` shape: zlib container, sub-mesh 1, double precision
+    ("c6_serialized.xml", {}),
+    ("c7_constant.xml", {"max_depth": 5}),          # constant environment emitter + point light                      # `serialized` shape: zlib container, sub-mesh 1, double precision
 ]
 
 

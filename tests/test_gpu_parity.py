@@ -67,6 +67,7 @@ def test_cuda_full_waveform_mode_matches_oracle(ctx, name):
     ("c2_arealight", dict(resx=40, resy=40, spp=32)),
     ("c4_domino", dict(resx=64, resy=32, spp=32, wave="trapezoidal", tsm="antithetic_mirror", shift=0.0, w_g=150)),
     ("c5_slabroom", dict(resx=32, resy=32, spp=36, tcn=3, pcn=6, tsm="antithetic")),   # spp not a multiple of 32
+    ("c7_constant", dict(resx=40, resy=32, spp=32, hetero_frequency=0.0, max_depth=6)),  # constant environment emitter
 ])
 def test_cuda_film_matches_oracle(ctx, scene_name, kw):
     import oracle_lib
@@ -159,3 +160,28 @@ def test_multi_pass_driver_equals_mean_of_renders(ctx):
     assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
     with pytest.raises(ValueError):
         ctx.render_multi_pass(flat, base, 0)
+
+
+@pytest.mark.parametrize("hide", [False, True])
+def test_environment_emitter_and_hide_emitters(ctx, hide):
+    """`constant` environment emitter (src/emitters/constant.cpp): escaping paths collect its radiance; with
+    hide_emitters the camera does not see it directly (valid_ray starts false, dopplertofpath.cpp:102,279)."""
+    import oracle_lib
+    scene = dt.load_file(os.path.join(gu.SCENES, "c7_constant.xml"), resx=32, resy=32, spp=32, hetero_frequency=0.0)
+    scene.integrator.hide_emitters = hide
+    params = scene.integrator.params(scene.sensor.sampler, seed=1)
+    assert params.hide_emitters == int(hide)
+    flat = ctx.upload(scene)
+    rgbw = ctx.render(flat, params, develop=False)
+    ref = oracle_lib.OracleScene(flat).render(params, develop=False)
+    assert np.abs(rgbw[..., :3] - ref[..., :3]).max() <= 2e-4 * np.abs(ref[..., :3]).max()
+    sky = rgbw[0, 0, :3] / rgbw[0, 0, 3]            # top-left pixel looks past the geometry
+    if hide:
+        assert np.all(sky == 0)
+    else:
+        assert np.all(np.abs(sky) > 0)
+    # two environment emitters are rejected like Scene's constructor does (scene.cpp:53-55)
+    scene.emitters.append(dt.ConstantEmitter((1, 1, 1)))
+    scene.scene_order = None
+    with pytest.raises(ValueError):
+        scene.flatten()
