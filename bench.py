@@ -158,7 +158,7 @@ def reference_binary_throughput(workload, spp, threads):
         path = os.path.join(d, "scene_moment.xml")
         open(path, "w").write(xml)
         for f in os.listdir(os.path.join(ROOT, "tests", "scenes")):
-            if f.endswith(".ply"):
+            if f.endswith((".ply", ".serialized")):
                 os.symlink(os.path.join(ROOT, "tests", "scenes", f), os.path.join(d, f))
         cmd = [exe, "-m", "scalar_rgb", "-t", str(threads), "-o", os.path.join(d, "out.exr"), f"-Dspp={spp}"]
         for k, v in params.items():

@@ -296,8 +296,12 @@ private:
                     }
                 Spectrum L = e->eval(si);
                 d.value[0] = L[0], d.value[1] = L[1], d.value[2] = L[2];
+            } else if (e->class_()->name() == "ConstantBackgroundEmitter") {
+                d.kind = DTOF_EMITTER_CONSTANT;                          // the library derives the bounding sphere itself
+                Spectrum L = e->eval(si);
+                d.value[0] = L[0], d.value[1] = L[1], d.value[2] = L[2];
             } else {
-                Throw("emitter \"%s\" is outside the accelerated path (point | area)", e->class_()->name());
+                Throw("emitter \"%s\" is outside the accelerated path (point | area | constant)", e->class_()->name());
             }
             emitters.push_back(d);
         }

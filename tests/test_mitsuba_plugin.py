@@ -62,7 +62,7 @@ def _plugin_scene(tmp_path, name, integrator="dopplertofpath_b200"):
     path = os.path.join(str(tmp_path), name)
     open(path, "w").write(xml)
     for f in os.listdir(SCENES):
-        if f.endswith(".ply") and not os.path.exists(os.path.join(str(tmp_path), f)):
+        if f.endswith((".ply", ".serialized")) and not os.path.exists(os.path.join(str(tmp_path), f)):
             os.symlink(os.path.join(SCENES, f), os.path.join(str(tmp_path), f))
     return path
 
@@ -97,6 +97,8 @@ def test_plugin_fails_loudly_without_a_gpu(tmp_path):
     ("c2_arealight.xml", {"resx": 96, "resy": 64, "spp": 64}),
     ("c4_domino.xml", {"resx": 128, "resy": 96, "spp": 64, "wave": "trapezoidal", "tsm": "antithetic_mirror", "shift": 0.0, "w_g": 150}),
     ("c5_slabroom.xml", {"resx": 64, "resy": 64, "spp": 32}),
+    ("c6_serialized.xml", {"resx": 64, "resy": 64, "spp": 32}),                          # reference's SerializedMesh loader
+    ("c7_constant.xml", {"resx": 64, "resy": 48, "spp": 32, "hetero_frequency": 0.0}),   # constant environment emitter
 ])
 def test_reference_cli_renders_through_the_plugin(tmp_path, name, defs):
     """`mitsuba -m scalar_rgb scene.xml` with integrator dopplertofpath_b200 == the Python host's render of the same
