@@ -70,10 +70,12 @@ struct AnimatedTransform {
 };
 
 // ---------------------------------------------------------------------------------------------- scene objects
+// `diffuse`, or `conductor` (reflectance = specular_reflectance, eta + i k = complex index of refraction)
 struct Bsdf {
     float reflectance[3] = { 0.5f, 0.5f, 0.5f };
     bool twosided = false;
     uint32_t kind = DTOF_BSDF_DIFFUSE;
+    float eta[3] = { 0.f, 0.f, 0.f }, k[3] = { 1.f, 1.f, 1.f };
 };
 
 struct Shape {

@@ -638,14 +638,20 @@ std::unique_ptr<FlatScene> Scene::flatten() const {
         Bsdf b = s.has_bsdf ? s.bsdf : Bsdf();   // Shape default BSDF: diffuse (src/render/shape.cpp:60-65)
         for (size_t i = 0; i < fs->bsdfs.size(); ++i) {
             const dtof_bsdf &o = fs->bsdfs[i];
+            const bool c = b.kind == DTOF_BSDF_CONDUCTOR;   // eta / k only distinguish conductors
             if (o.kind == b.kind && (o.twosided != 0) == b.twosided && o.reflectance[0] == b.reflectance[0] &&
-                o.reflectance[1] == b.reflectance[1] && o.reflectance[2] == b.reflectance[2])
+                o.reflectance[1] == b.reflectance[1] && o.reflectance[2] == b.reflectance[2] &&
+                (!c || (!memcmp(o.eta, b.eta, sizeof(o.eta)) && !memcmp(o.k, b.k, sizeof(o.k)))))
                 return (uint32_t) i;
         }
         dtof_bsdf nb{};
         nb.kind = b.kind;
         nb.twosided = b.twosided ? 1u : 0u;
         memcpy(nb.reflectance, b.reflectance, sizeof(nb.reflectance));
+        if (b.kind == DTOF_BSDF_CONDUCTOR) {
+            memcpy(nb.eta, b.eta, sizeof(nb.eta));
+            memcpy(nb.k, b.k, sizeof(nb.k));
+        }
         fs->bsdfs.push_back(nb);
         return (uint32_t) fs->bsdfs.size() - 1;
     };
@@ -899,7 +905,25 @@ struct Loader {
                     b.reflectance[i] = (float) p["reflectance"].vec[i];
             return b;
         }
-        throw Error("bsdf type '" + typ + "' is outside the hot-path scope (diffuse|twosided)");
+        if (typ == "conductor") {   // SmoothConductor ctor, src/bsdfs/conductor.cpp:213-230
+            auto p = props(node);
+            reject_unknown(p, { "specular_reflectance", "material", "eta", "k" }, "conductor");
+            const std::string material = p.count("material") ? p["material"].value : "none";
+            if (material != "none") {
+                if (p.count("eta"))
+                    throw Error("Should specify either (eta, k) or material, not both.");
+                throw Error("conductor material '" + material + "' (measured spectra) is outside the hot-path scope: give eta / k");
+            }
+            Bsdf b;
+            b.kind = DTOF_BSDF_CONDUCTOR;
+            for (int i = 0; i < 3; ++i) {
+                b.reflectance[i] = p.count("specular_reflectance") ? (float) p["specular_reflectance"].vec[i] : 1.f;
+                b.eta[i] = p.count("eta") ? (float) p["eta"].vec[i] : 0.f;
+                b.k[i] = p.count("k") ? (float) p["k"].vec[i] : 1.f;
+            }
+            return b;
+        }
+        throw Error("bsdf type '" + typ + "' is outside the hot-path scope (diffuse|conductor|twosided)");
     }
     Bsdf bsdf_or_ref(const XmlNode &node) {
         if (node.tag == "ref") {

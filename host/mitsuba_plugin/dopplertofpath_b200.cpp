@@ -189,11 +189,26 @@ private:
             inner = (const BSDF *) c.objects[0].second;
             b.twosided = 1;
         }
-        if (inner->class_()->name() != "SmoothDiffuse")
-            Throw("BSDF \"%s\" is outside the accelerated path (diffuse | twosided(diffuse))", inner->class_()->name());
         SurfaceInteraction3f si = dr::zeros<SurfaceInteraction3f>();
-        Spectrum r = inner->eval_diffuse_reflectance(si);                // constant RGB reflectance
-        b.reflectance[0] = r[0], b.reflectance[1] = r[1], b.reflectance[2] = r[2];
+        if (inner->class_()->name() == "SmoothConductor") {               // eta, k, specular_reflectance (conductor.cpp:232-236)
+            b.kind = DTOF_BSDF_CONDUCTOR;
+            Collector c;
+            const_cast<BSDF *>(inner)->traverse(&c);
+            auto tex = [&](const char *name) -> Spectrum {
+                for (auto &o : c.objects)
+                    if (o.first == name)
+                        return ((const Texture<Float, Spectrum> *) o.second)->eval(si);
+                Throw("conductor without '%s'", name);
+            };
+            Spectrum e = tex("eta"), k = tex("k"), r = tex("specular_reflectance");
+            for (int i = 0; i < 3; ++i)
+                b.eta[i] = e[i], b.k[i] = k[i], b.reflectance[i] = r[i];
+        } else {
+            if (inner->class_()->name() != "SmoothDiffuse")
+                Throw("BSDF \"%s\" is outside the accelerated path (diffuse | conductor | twosided(...))", inner->class_()->name());
+            Spectrum r = inner->eval_diffuse_reflectance(si);            // constant RGB reflectance
+            b.reflectance[0] = r[0], b.reflectance[1] = r[1], b.reflectance[2] = r[2];
+        }
         for (size_t i = 0; i < out.size(); ++i)
             if (!memcmp(&out[i], &b, sizeof(b)))
                 return (uint32_t) i;

@@ -8,14 +8,14 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # enums (include/dtof.h)
 TIME_UNIFORM, TIME_STRATIFIED, TIME_ANTITHETIC, TIME_ANTITHETIC_MIRROR = range(4)
 WAVE_SINUSOIDAL, WAVE_RECTANGULAR, WAVE_TRIANGULAR, WAVE_TRAPEZOIDAL = range(4)
 RFILTER_BOX, RFILTER_TENT, RFILTER_GAUSSIAN = range(3)
 SHAPE_MESH, SHAPE_RECTANGLE = range(2)
-BSDF_DIFFUSE, BSDF_NULL_BLACK = range(2)
+BSDF_DIFFUSE, BSDF_NULL_BLACK, BSDF_CONDUCTOR = range(3)
 EMITTER_POINT, EMITTER_AREA, EMITTER_CONSTANT = range(3)
 INTEGRATOR_DOPPLERTOFPATH, INTEGRATOR_VELOCITY, INTEGRATOR_PATH = range(3)
 
@@ -43,7 +43,8 @@ class Instance(C.Structure):
 
 
 class Bsdf(C.Structure):
-    _fields_ = [("kind", C.c_uint32), ("twosided", C.c_uint32), ("reflectance", C.c_float * 3)]
+    _fields_ = [("kind", C.c_uint32), ("twosided", C.c_uint32), ("reflectance", C.c_float * 3),
+                ("eta", C.c_float * 3), ("k", C.c_float * 3)]
 
 
 class Emitter(C.Structure):

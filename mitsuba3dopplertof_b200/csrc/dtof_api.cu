@@ -662,8 +662,8 @@ dtof_status launch_render(dtof_ctx *ctx, const dtof_params *p, float *d_rgbw, cu
     if (want == MODE_BVH_GLOBAL || (want == MODE_BVH_SMEM && bvh_bytes + 1024 <= ctx->smem_optin) ||
         (want == MODE_FLAT_SMEM && flat_bytes + 1024 <= ctx->smem_optin))
         mode = want;
-    const bool env = ctx->ds.env_emitter >= 0;
-    if (env && mode == MODE_FLAT_SMEM)   // the flat walk has no environment-emitter instantiation
+    const bool env = ctx->ds.extended != 0;   // environment emitter or conductor: the ENV = true instantiations
+    if (env && mode == MODE_FLAT_SMEM)   // the flat walk has no such instantiation
         mode = bvh_bytes + 1024 <= ctx->smem_optin ? MODE_BVH_SMEM : MODE_BVH_GLOBAL;
     // the traversal counters are defined on the BVH walk (algorithmic work of the scene), whatever
     // mode the production launch of this scene picks
@@ -736,6 +736,7 @@ struct HostScene {
     // constant environment emitter: index (-1: none) and the scene's bounding sphere (constant.cpp:73-82)
     int32_t env_emitter = -1;
     float env_center[3] = { 0.f, 0.f, 0.f }, env_radius = 1.f;
+    bool extended = false;   // the scene needs the ENV = true kernel instantiations (environment emitter or conductor)
 };
 
 dtof_status prepare_scene(dtof_ctx *ctx, const dtof_scene_desc *sc, HostScene &H) {
@@ -758,10 +759,13 @@ dtof_status prepare_scene(dtof_ctx *ctx, const dtof_scene_desc *sc, HostScene &H
     std::vector<uint32_t> mesh_first_gid(sc->n_meshes, 0xffffffffu);
     for (uint32_t i = 0; i < sc->n_bsdfs; ++i) {
         const dtof_bsdf &b = sc->bsdfs[i];
-        if (b.kind > DTOF_BSDF_NULL_BLACK)
+        if (b.kind > DTOF_BSDF_CONDUCTOR)
             return fail(ctx, DTOF_ERR_UNSUPPORTED, "bsdf kind %u is outside the hot-path scope", b.kind);
         bsdfs[i] = BsdfRec{ b.reflectance[0], b.reflectance[1], b.reflectance[2],
-                            (b.twosided ? 1u : 0u) | (b.kind == DTOF_BSDF_DIFFUSE ? 2u : 0u) };
+                            (b.twosided ? 1u : 0u) | (b.kind == DTOF_BSDF_DIFFUSE ? 2u : 0u) |
+                                (b.kind == DTOF_BSDF_CONDUCTOR ? 4u : 0u),
+                            b.eta[0], b.eta[1], b.eta[2], 0.f, b.k[0], b.k[1], b.k[2], 0.f };
+        H.extended = H.extended || b.kind == DTOF_BSDF_CONDUCTOR;
     }
     uint32_t gid = 0;
     for (uint32_t g = 0; g < sc->n_instances; ++g) {
@@ -884,6 +888,7 @@ dtof_status prepare_scene(dtof_ctx *ctx, const dtof_scene_desc *sc, HostScene &H
             if (H.env_emitter >= 0)
                 return fail(ctx, DTOF_ERR_INVALID, "Only one environment emitter can be specified per scene.");   // scene.cpp:53-55
             H.env_emitter = (int32_t) i;
+            H.extended = true;
         }
         if (e.kind == DTOF_EMITTER_AREA && (e.mesh >= sc->n_meshes || sc->meshes[e.mesh].emitter != (int32_t) i))
             return fail(ctx, DTOF_ERR_INVALID, "area emitter %u and its mesh do not reference each other", i);
@@ -1077,6 +1082,7 @@ dtof_status dtof_upload_scene(dtof_ctx *ctx, const dtof_scene_desc *sc) {
     D.n_nodes = (uint32_t) built.nodes.size();
     D.n_tris = (uint32_t) built.tris.size();
     D.has_geometry = built.has_geometry ? 1u : 0u;
+    D.extended = H.extended ? 1u : 0u;
     D.env_emitter = H.env_emitter;
     if (H.env_emitter >= 0) {
         const dtof_emitter &e = sc->emitters[H.env_emitter];

@@ -373,6 +373,19 @@ DTOF_DEV V3 square_to_cosine_hemisphere(float sx, float sy) {
     float z = fsqrt(fmaxf(1.f - fmaf(py, py, px * px), 0.f));
     return v3(px, py, z);
 }
+// fresnel_conductor (include/mitsuba/render/fresnel.h:93-117), one colour channel
+DTOF_DEV float fresnel_conductor(float cos_theta_i, float eta_r, float eta_i) {
+    float cos2 = cos_theta_i * cos_theta_i, sin2 = 1.f - cos2, sin4 = sin2 * sin2;
+    float temp_1 = eta_r * eta_r - eta_i * eta_i - sin2;
+    float a_2_pb_2 = fsqrt(fmaxf(temp_1 * temp_1 + 4.f * eta_i * eta_i * eta_r * eta_r, 0.f));
+    float a = fsqrt(fmaxf(.5f * (a_2_pb_2 + temp_1), 0.f));
+    float term_1 = a_2_pb_2 + cos2, term_2 = 2.f * cos_theta_i * a;
+    float r_s = fdiv(term_1 - term_2, term_1 + term_2);
+    float term_3 = a_2_pb_2 * cos2 + sin4, term_4 = term_2 * sin2;
+    float r_p = r_s * fdiv(term_3 - term_4, term_3 + term_4);
+    return .5f * (r_s + r_p);
+}
+
 // warp::square_to_uniform_sphere (include/mitsuba/core/warp.h:250-255)
 DTOF_DEV V3 square_to_uniform_sphere(float sx, float sy) {
     float z = fmaf(-2.f, sy, 1.f);
@@ -408,6 +421,7 @@ struct DeviceScene {
     int32_t root;
     uint32_t n_emitters, n_insts, n_nodes, n_tris, has_geometry;
     // constant environment emitter (src/emitters/constant.cpp): index into `emitters` or -1; radiance; bounding sphere
+    uint32_t extended;     // the scene uses an environment emitter or a conductor (kernel template parameter ENV)
     int32_t env_emitter;
     float env_r, env_g, env_b;
     float env_cx, env_cy, env_cz, env_radius;

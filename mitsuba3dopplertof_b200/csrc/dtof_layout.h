@@ -80,9 +80,11 @@ struct MeshRec {
     uint32_t pad[3];
 };
 
-struct BsdfRec {
-    float r, g, b;
-    uint32_t flags;        // bit0: twosided, bit1: smooth diffuse lobe present
+struct alignas(16) BsdfRec {
+    float r, g, b;         // diffuse reflectance / conductor specular_reflectance
+    uint32_t flags;        // bit0: twosided, bit1: smooth diffuse lobe present, bit2: smooth conductor (delta reflection)
+    float eta_r, eta_g, eta_b, pad0;   // conductor: complex index of refraction eta + i k
+    float k_r, k_g, k_b, pad1;
 };
 
 struct EmitterRec {

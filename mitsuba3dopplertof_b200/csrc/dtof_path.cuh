@@ -113,16 +113,17 @@ DTOF_DEV void shade_bounce(const DeviceScene &S, const float4 *__restrict__ I, c
     const bool valid = hit;
     const bool correlate = DOPPLER && (depth + 1) < P.path_correlation_depth;   // :122
     SI si;
-    uint32_t bsdf_flags = 0;
+    uint32_t bsdf_flags = 0, bsdf_id = 0;
     V3 refl = v3(0, 0, 0);
     int32_t mesh_emitter = -1;
     if (valid) {
         compute_si(S, I, h, ray_d, ray_time, si);
         const MeshRec &mr = S.meshes[si.mesh];
         mesh_emitter = mr.emitter;
-        const BsdfRec br = S.bsdfs[mr.bsdf];
-        bsdf_flags = br.flags;
-        refl = v3(br.r, br.g, br.b);
+        bsdf_id = mr.bsdf;
+        const float4 b0 = *reinterpret_cast<const float4 *>(&S.bsdfs[mr.bsdf]);   // {r, g, b, flags}
+        bsdf_flags = __float_as_uint(b0.w);
+        refl = v3(b0.x, b0.y, b0.z);
         path_length += h.t;                                             // :141 (eta == 1)
     }
     // ---- direct emission (:150-168)
@@ -252,6 +253,18 @@ DTOF_DEV void shade_bounce(const DeviceScene &S, const float4 *__restrict__ I, c
                 bs_wo.z = mulsign(bs_wo.z, si.wi.z);
         }
     }
+    bool sampled_delta = false;
+    if (ENV && valid && (bsdf_flags & 4u)) {                             // SmoothConductor::sample, conductor.cpp:247-300
+        float wi_z = twosided ? fabsf(si.wi.z) : si.wi.z;                // TwoSidedBRDF: |wi.z| in, sign restored on wo.z
+        if (wi_z > 0.f) {
+            const BsdfRec &br = S.bsdfs[bsdf_id];
+            bs_wo = v3(-si.wi.x, -si.wi.y, si.wi.z);                     // reflect(wi); twosided: mulsign(|wi.z|, wi.z) = wi.z
+            bs_pdf = 1.f;
+            bsdf_weight = v3(refl.x * fresnel_conductor(wi_z, br.eta_r, br.k_r), refl.y * fresnel_conductor(wi_z, br.eta_g, br.k_g),
+                             refl.z * fresnel_conductor(wi_z, br.eta_b, br.k_b));
+            sampled_delta = true;                                        // bs.sampled_type = DeltaReflection
+        }
+    }
     // ---- emitter sampling contribution (:214-226), added once the shadow ray is known to be unoccluded
     if (nee.want) {
         float mis_em = ds_delta ? 1.f : mis_weight(ds_pdf, bsdf_pdf);
@@ -270,7 +283,7 @@ DTOF_DEV void shade_bounce(const DeviceScene &S, const float4 *__restrict__ I, c
     throughput = throughput * bsdf_weight;
     ps.valid_ray = ps.valid_ray || valid;                               // :253-254
     ps.prev_bsdf_pdf = bs_pdf;
-    ps.prev_bsdf_delta = false;
+    ps.prev_bsdf_delta = sampled_delta;                                 // has_flag(bsdf_sample.sampled_type, Delta), :250
     // ---- stopping criterion (:262-276)
     if (valid)
         depth += 1;

@@ -33,10 +33,14 @@ f32 = np.float32
 # ------------------------------------------------------------------------------------------------
 @dataclass
 class Bsdf:
-    """``diffuse`` (src/bsdfs/diffuse.cpp), optionally wrapped in ``twosided`` (src/bsdfs/twosided.cpp)."""
+    """``diffuse`` (src/bsdfs/diffuse.cpp) or ``conductor`` (src/bsdfs/conductor.cpp: `reflectance` is its
+    specular_reflectance, `eta` / `k` the complex index of refraction, material "none" = (0, 1)), optionally wrapped in
+    ``twosided`` (src/bsdfs/twosided.cpp)."""
     reflectance: Sequence[float] = (0.5, 0.5, 0.5)   # SmoothDiffuse default reflectance 0.5
     twosided: bool = False
     kind: int = _abi.BSDF_DIFFUSE
+    eta: Sequence[float] = (0.0, 0.0, 0.0)
+    k: Sequence[float] = (1.0, 1.0, 1.0)
 
 
 @dataclass
@@ -300,10 +304,16 @@ class Scene:
 
         def bsdf_id(b: Optional[Bsdf]) -> int:
             b = b if b is not None else Bsdf()   # Shape default BSDF: diffuse (src/render/shape.cpp:60-65)
-            key = (b.kind, bool(b.twosided), tuple(float(f32(x)) for x in b.reflectance))
+            def rgb(v):
+                v = np.atleast_1d(np.asarray(v, f32))
+                return tuple(float(x) for x in ((v.tolist() * 3)[:3] if v.size == 1 else v.tolist()))
+            conductor = b.kind == _abi.BSDF_CONDUCTOR
+            key = (b.kind, bool(b.twosided), tuple(float(f32(x)) for x in b.reflectance),
+                   rgb(b.eta) if conductor else (0.0,) * 3, rgb(b.k) if conductor else (0.0,) * 3)
             if key not in bsdf_index:
                 bsdf_index[key] = len(bsdfs)
-                bsdfs.append(_abi.Bsdf(b.kind, int(b.twosided), (C.c_float * 3)(*key[2])))
+                bsdfs.append(_abi.Bsdf(b.kind, int(b.twosided), (C.c_float * 3)(*key[2]), (C.c_float * 3)(*key[3]),
+                                       (C.c_float * 3)(*key[4])))
             return bsdf_index[key]
 
         meshes: List[_FlatMesh] = []

@@ -122,14 +122,27 @@ class _Loader:
             if len(inner) != 1:
                 raise ValueError("twosided with two different BRDFs is outside the hot-path scope")
             b = self.bsdf_or_ref(inner[0])
-            return Bsdf(b.reflectance, True, b.kind)
+            return Bsdf(b.reflectance, True, b.kind, b.eta, b.k)
         if typ == "diffuse":
             p = self.props(node)
             unknown = set(p) - {"reflectance"}
             if unknown:
                 raise ValueError(f"diffuse: unreferenced property {sorted(unknown)}")
             return Bsdf(p.get("reflectance", (0.5, 0.5, 0.5)), False)
-        raise ValueError(f"bsdf type '{typ}' is outside the hot-path scope (diffuse|twosided)")
+        if typ == "conductor":   # SmoothConductor ctor, src/bsdfs/conductor.cpp:213-230
+            from . import _abi
+            p = self.props(node)
+            unknown = set(p) - {"specular_reflectance", "material", "eta", "k"}
+            if unknown:
+                raise ValueError(f"conductor: unreferenced property {sorted(unknown)}")
+            material = p.get("material", "none")
+            if material != "none":
+                if "eta" in p:
+                    raise ValueError("Should specify either (eta, k) or material, not both.")
+                raise ValueError(f"conductor material '{material}' (measured spectra) is outside the hot-path scope: give eta / k")
+            return Bsdf(p.get("specular_reflectance", (1.0, 1.0, 1.0)), False, _abi.BSDF_CONDUCTOR,
+                        p.get("eta", (0.0, 0.0, 0.0)), p.get("k", (1.0, 1.0, 1.0)))
+        raise ValueError(f"bsdf type '{typ}' is outside the hot-path scope (diffuse|conductor|twosided)")
 
     def bsdf_or_ref(self, node) -> Bsdf:
         if node.tag == "ref":

@@ -412,6 +412,19 @@ struct Modulation {
 // ------------------------------------------------------------------------------------------
 // Warps / frames
 // ------------------------------------------------------------------------------------------
+// fresnel_conductor, include/mitsuba/render/fresnel.h:93-117 (one colour channel)
+inline float fresnel_conductor(float cos_theta_i, float eta_r, float eta_i) {
+    float cos2 = cos_theta_i * cos_theta_i, sin2 = 1.f - cos2, sin4 = sin2 * sin2;
+    float temp_1 = eta_r * eta_r - eta_i * eta_i - sin2;
+    float a_2_pb_2 = sqrtf(std::max(temp_1 * temp_1 + 4.f * eta_i * eta_i * eta_r * eta_r, 0.f));
+    float a = sqrtf(std::max(.5f * (a_2_pb_2 + temp_1), 0.f));
+    float term_1 = a_2_pb_2 + cos2, term_2 = 2.f * cos_theta_i * a;
+    float r_s = (term_1 - term_2) / (term_1 + term_2);
+    float term_3 = a_2_pb_2 * cos2 + sin4, term_4 = term_2 * sin2;
+    float r_p = r_s * (term_3 - term_4) / (term_3 + term_4);
+    return .5f * (r_s + r_p);
+}
+
 // warp::square_to_uniform_sphere, include/mitsuba/core/warp.h:250-255
 constexpr float kInvFourPi = 0.07957747154594766788f;
 inline V3 square_to_uniform_sphere(float sx, float sy) {
@@ -1060,6 +1073,21 @@ PathResult trace_path(const dtof_oracle_scene &sc, const dtof_params &P, const M
             }
         }
 
+        bool sampled_delta = false;
+        if (valid && bsdf->kind == DTOF_BSDF_CONDUCTOR) { // SmoothConductor::sample, conductor.cpp:247-300
+            // TwoSidedBRDF (twosided.cpp:124-127): |wi.z| goes in, the sign of wi.z is restored on wo.z
+            float wi_z = bsdf->twosided ? fabsf(si.wi.z) : si.wi.z;
+            if (wi_z > 0.f) {
+                bs_wo = v3(-si.wi.x, -si.wi.y, si.wi.z); // reflect(wi)
+                bs_pdf = 1.f;
+                bs_eta = 1.f;
+                bsdf_weight = v3(bsdf->reflectance[0] * fresnel_conductor(wi_z, bsdf->eta[0], bsdf->k[0]),
+                                 bsdf->reflectance[1] * fresnel_conductor(wi_z, bsdf->eta[1], bsdf->k[1]),
+                                 bsdf->reflectance[2] * fresnel_conductor(wi_z, bsdf->eta[2], bsdf->k[2]));
+                sampled_delta = true; // bs.sampled_type = DeltaReflection
+            }
+        }
+
         // ---- emitter sampling contribution (:214-226)
         if (active_em) {
             float mis_em = ds.delta ? 1.f : mis_weight(ds.pdf, bsdf_pdf);
@@ -1083,7 +1111,7 @@ PathResult trace_path(const dtof_oracle_scene &sc, const dtof_params &P, const M
         eta *= bs_eta;
         valid_ray = valid_ray || valid; // :253-254
         prev_bsdf_pdf = bs_pdf;
-        prev_bsdf_delta = false;
+        prev_bsdf_delta = sampled_delta; // has_flag(bsdf_sample.sampled_type, BSDFFlags::Delta), :250
 
         // ---- stopping criterion (:262-276)
         if (valid)

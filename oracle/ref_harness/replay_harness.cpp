@@ -95,18 +95,52 @@ public:
     mi::ref<Base> clone() override { return this; }
     void seed(uint32_t, uint32_t) override {}
 
-    float next_1d(bool = true) override { return m_rng.next_float32(); }
-    Point2f next_2d(bool active = true) override {
-        float a = next_1d(active), b = next_1d(active);
-        return Point2f(a, b);
-    }
-    float next_1d_correlate(bool = true, bool correlate = false) override {
+    // ---- JIT-faithful draw consumption inside sample() ------------------------------------------------------------
+    // Every iteration of the path loop draws, in the JIT variants, [emitter 2D, bsdf 1D, bsdf 2D, roulette 1D]
+    // (dopplertofpath.cpp:187-210,262-270; path.cpp likewise). The SCALAR build evaluates `dr::any_or<true>(active_em)`
+    // on the lane's real mask and skips the emitter 2D draw on a surface without a smooth lobe (a mirror), which the
+    // JIT variants never do. begin_path() arms a small state machine that notices the missing 2D draw (a 1D request
+    // arrives where the emitter 2D was expected) and burns the two values the JIT variants would have consumed.
+    enum Expect { EM_2D, BSDF_1D, BSDF_2D, RR_1D, FREE };
+    void begin_path() { m_expect = EM_2D; }
+    void end_path() { m_expect = FREE; }
+    float raw_1d() { return m_rng.next_float32(); }
+    float raw_1d_correlate(bool correlate) {
         float r1 = m_rng_path.next_float32();
         float r2 = m_rng.next_float32();
         return correlate ? r1 : r2;
     }
-    Point2f next_2d_correlate(bool active = true, bool correlate = false) override {
-        float a = next_1d_correlate(active, correlate), b = next_1d_correlate(active, correlate);
+    template <bool TWO> void track(bool correlated) {
+        if (m_expect == FREE)
+            return;
+        if (!TWO && m_expect == EM_2D) {   // the scalar branch skipped the emitter sample: realign with the JIT streams
+            for (int i = 0; i < 2; ++i) {
+                if (correlated)
+                    raw_1d_correlate(false);
+                else
+                    raw_1d();
+            }
+            m_expect = BSDF_1D;
+        }
+        m_expect = m_expect == EM_2D ? BSDF_1D : m_expect == BSDF_1D ? BSDF_2D : m_expect == BSDF_2D ? RR_1D : EM_2D;
+    }
+
+    float next_1d(bool = true) override {
+        track<false>(false);
+        return raw_1d();
+    }
+    Point2f next_2d(bool = true) override {
+        track<true>(false);
+        float a = raw_1d(), b = raw_1d();
+        return Point2f(a, b);
+    }
+    float next_1d_correlate(bool = true, bool correlate = false) override {
+        track<false>(true);
+        return raw_1d_correlate(correlate);
+    }
+    Point2f next_2d_correlate(bool = true, bool correlate = false) override {
+        track<true>(true);
+        float a = raw_1d_correlate(correlate), b = raw_1d_correlate(correlate);
         return Point2f(a, b);
     }
     // correlated.cpp:92-153 (scalar restatement, same statement order)
@@ -159,6 +193,7 @@ public:
 private:
     PCG m_rng, m_rng_time, m_rng_path;
     uint32_t m_tcn, m_pcn, m_perm_seed = 0, m_spp_pp = 1, m_idx = 0, m_pass = 0, m_dim = 0;
+    Expect m_expect = FREE;
 };
 mi::Class *ReplaySampler::s_class = new mi::Class("ReplaySampler", "Sampler", "scalar_rgb", nullptr, nullptr);
 
@@ -281,7 +316,9 @@ int main(int argc, char **argv) {
                     fprintf(stderr, "  ds.p=(%.9g %.9g %.9g) d=(%.9g %.9g %.9g) dist=%.9g pdf=%.9g w=(%.9g %.9g %.9g)\n", ds.p.x(),
                             ds.p.y(), ds.p.z(), ds.d.x(), ds.d.y(), ds.d.z(), ds.dist, ds.pdf, w.x(), w.y(), w.z());
                 }
+                sampler->begin_path();
                 auto [spec, valid] = integ->sample(scene, sampler.get(), ray, nullptr, aovs, true);
+                sampler->end_path();
                 S rgb = ray_weight * spec;
                 printf("%u %u %u %u %.9g %.9g %.9g %.9g %.9g %.9g %.9g %.9g %.9g %.9g %.9g %.9g %.9g\n", idx, pass, px, py,
                        sample_pos.x(), sample_pos.y(), time, ray.o.x(), ray.o.y(), ray.o.z(), ray.d.x(), ray.d.y(),

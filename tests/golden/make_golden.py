@@ -56,6 +56,9 @@ CASES = {
     "c6_serialized": ("c6_serialized", {}, 4, True),
     # open scene (floor + the two moving boxes) under a constant environment emitter + the point light (2 emitters)
     "c7_constant": ("c7_constant", {"max_depth": 5, "pcd": 5}, 0, True),
+    # smooth conductors: the tall box (explicit eta / k, one-sided) and the back wall (two-sided perfect mirror)
+    "c8_conductor": ("c8_conductor", {"max_depth": 6, "pcd": 6}, 0, True),
+    "c8_conductor_homodyne": ("c8_conductor", {"hetero_frequency": 0.0, "max_depth": 8, "rr_depth": 3, "tsm": "stratified", "shift": 0.0}, 2, True),
     "c7_constant_homodyne": ("c7_constant", {"hetero_frequency": 0.0, "tsm": "uniform", "shift": 0.0, "rr_depth": 2, "max_depth": 8}, 6, True),
 }
 # the stock path tracer (src/integrators/path.cpp) on the same scenes: the integrator element is swapped (golden_util.swap_integrator)
@@ -66,6 +69,7 @@ PATH_CASES = {
     "path_c3_rotor": ("c3_rotor", {"resx": 512, "resy": 512, "spp": 64}, 2, True),
     "path_c5_slabroom": ("c5_slabroom", {}, 1, True),
     "path_c7_constant": ("c7_constant", {}, 3, True),
+    "path_c8_conductor": ("c8_conductor", {"max_depth": 6}, 1, True),
 }
 # the ground-truth radial velocity integrator (src/integrators/velocity.cpp). Its value (t2 - t1) / time scales by exactly
 # 2^20 under the time scaling; golden_util.load_case undoes it.

@@ -55,7 +55,8 @@ CASES = [
     ("c4_domino.xml", {"w_g": 150}),
     ("c5_slabroom.xml", {"tcn": 3, "pcn": 6}),
     ("c6_serialized.xml", {}),
-    ("c7_constant.xml", {"max_depth": 5}),          # constant environment emitter + point light                      # `serialized` shape: zlib container, sub-mesh 1, double precision
+    ("c7_constant.xml", {"max_depth": 5}),          # constant environment emitter + point light
+    ("c8_conductor.xml", {"max_depth": 6}),         # smooth conductors (explicit eta / k, and the two-sided mirror)                      # `serialized` shape: zlib container, sub-mesh 1, double precision
 ]
 
 

@@ -68,6 +68,7 @@ def test_cuda_full_waveform_mode_matches_oracle(ctx, name):
     ("c4_domino", dict(resx=64, resy=32, spp=32, wave="trapezoidal", tsm="antithetic_mirror", shift=0.0, w_g=150)),
     ("c5_slabroom", dict(resx=32, resy=32, spp=36, tcn=3, pcn=6, tsm="antithetic")),   # spp not a multiple of 32
     ("c7_constant", dict(resx=40, resy=32, spp=32, hetero_frequency=0.0, max_depth=6)),  # constant environment emitter
+    ("c8_conductor", dict(resx=40, resy=40, spp=32, hetero_frequency=0.0, max_depth=8)),  # mirrors: delta BSDF samples
 ])
 def test_cuda_film_matches_oracle(ctx, scene_name, kw):
     import oracle_lib
