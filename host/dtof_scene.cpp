@@ -638,7 +638,7 @@ std::unique_ptr<FlatScene> Scene::flatten() const {
         Bsdf b = s.has_bsdf ? s.bsdf : Bsdf();   // Shape default BSDF: diffuse (src/render/shape.cpp:60-65)
         for (size_t i = 0; i < fs->bsdfs.size(); ++i) {
             const dtof_bsdf &o = fs->bsdfs[i];
-            const bool c = b.kind == DTOF_BSDF_CONDUCTOR;   // eta / k only distinguish conductors
+            const bool c = b.kind == DTOF_BSDF_CONDUCTOR || b.kind == DTOF_BSDF_DIELECTRIC;   // the kinds that use eta / k
             if (o.kind == b.kind && (o.twosided != 0) == b.twosided && o.reflectance[0] == b.reflectance[0] &&
                 o.reflectance[1] == b.reflectance[1] && o.reflectance[2] == b.reflectance[2] &&
                 (!c || (!memcmp(o.eta, b.eta, sizeof(o.eta)) && !memcmp(o.k, b.k, sizeof(o.k)))))
@@ -648,7 +648,7 @@ std::unique_ptr<FlatScene> Scene::flatten() const {
         nb.kind = b.kind;
         nb.twosided = b.twosided ? 1u : 0u;
         memcpy(nb.reflectance, b.reflectance, sizeof(nb.reflectance));
-        if (b.kind == DTOF_BSDF_CONDUCTOR) {
+        if (b.kind == DTOF_BSDF_CONDUCTOR || b.kind == DTOF_BSDF_DIELECTRIC) {
             memcpy(nb.eta, b.eta, sizeof(nb.eta));
             memcpy(nb.k, b.k, sizeof(nb.k));
         }
@@ -880,6 +880,27 @@ struct Loader {
             if (!known.count(kv.first))
                 throw Error(who + ": unreferenced property \"" + kv.first + "\"");
     }
+    // lookup_ior (include/mitsuba/render/ior.h:23-98): a number, or a material of the table
+    static float lookup_ior(const std::string &value) {
+        static const std::pair<const char *, float> table[] = {
+            { "vacuum", 1.0f }, { "helium", 1.000036f }, { "hydrogen", 1.000132f }, { "air", 1.000277f },
+            { "carbon dioxide", 1.00045f }, { "water", 1.3330f }, { "acetone", 1.36f }, { "ethanol", 1.361f },
+            { "carbon tetrachloride", 1.461f }, { "glycerol", 1.4729f }, { "benzene", 1.501f }, { "silicone oil", 1.52045f },
+            { "bromine", 1.661f }, { "water ice", 1.31f }, { "fused quartz", 1.458f }, { "pyrex", 1.470f },
+            { "acrylic glass", 1.49f }, { "polypropylene", 1.49f }, { "bk7", 1.5046f }, { "sodium chloride", 1.544f },
+            { "amber", 1.55f }, { "pet", 1.5750f }, { "diamond", 2.419f } };
+        std::string name;
+        for (char c : value)
+            name += (char) std::tolower((unsigned char) c);
+        char *end = nullptr;
+        float v = std::strtof(name.c_str(), &end);
+        if (end != name.c_str() && *end == 0)
+            return v;
+        for (auto &e : table)
+            if (name == e.first)
+                return e.second;
+        throw Error("Unable to find an IOR value for \"" + name + "\"!");
+    }
     Bsdf bsdf(const XmlNode &node) {
         std::string typ = attr(node, "type");
         if (typ == "twosided") {
@@ -893,6 +914,8 @@ struct Loader {
             if (n != 1)
                 throw Error("twosided with two different BRDFs is outside the hot-path scope");
             Bsdf b = bsdf_or_ref(*inner);
+            if (b.kind == DTOF_BSDF_DIELECTRIC)   // twosided.cpp:102-103
+                throw Error("Only materials without a transmission component can be nested!");
             b.twosided = true;
             return b;
         }
@@ -923,7 +946,23 @@ struct Loader {
             }
             return b;
         }
-        throw Error("bsdf type '" + typ + "' is outside the hot-path scope (diffuse|conductor|twosided)");
+        if (typ == "dielectric") {   // SmoothDielectric ctor, src/bsdfs/dielectric.cpp:199-228
+            auto p = props(node);
+            reject_unknown(p, { "int_ior", "ext_ior", "specular_reflectance", "specular_transmittance" }, "dielectric");
+            const float int_ior = lookup_ior(p.count("int_ior") ? p["int_ior"].value : "bk7");
+            const float ext_ior = lookup_ior(p.count("ext_ior") ? p["ext_ior"].value : "air");
+            if (int_ior < 0.f || ext_ior < 0.f)
+                throw Error("The interior and exterior indices of refraction must be positive!");
+            Bsdf b;
+            b.kind = DTOF_BSDF_DIELECTRIC;
+            b.eta[0] = int_ior / ext_ior, b.eta[1] = b.eta[2] = 0.f;
+            for (int i = 0; i < 3; ++i) {
+                b.reflectance[i] = p.count("specular_reflectance") ? (float) p["specular_reflectance"].vec[i] : 1.f;
+                b.k[i] = p.count("specular_transmittance") ? (float) p["specular_transmittance"].vec[i] : 1.f;
+            }
+            return b;
+        }
+        throw Error("bsdf type '" + typ + "' is outside the hot-path scope (diffuse|conductor|dielectric|twosided)");
     }
     Bsdf bsdf_or_ref(const XmlNode &node) {
         if (node.tag == "ref") {

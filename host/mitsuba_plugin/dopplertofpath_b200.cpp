@@ -203,9 +203,22 @@ private:
             Spectrum e = tex("eta"), k = tex("k"), r = tex("specular_reflectance");
             for (int i = 0; i < 3; ++i)
                 b.eta[i] = e[i], b.k[i] = k[i], b.reflectance[i] = r[i];
+        } else if (inner->class_()->name() == "SmoothDielectric") {        // eta + optional tints (dielectric.cpp:230-237)
+            b.kind = DTOF_BSDF_DIELECTRIC;
+            Collector c;
+            const_cast<BSDF *>(inner)->traverse(&c);
+            b.eta[0] = (float) *c.param<ScalarFloat>("eta");
+            for (int i = 0; i < 3; ++i)
+                b.reflectance[i] = b.k[i] = 1.f;
+            for (auto &o : c.objects) {
+                Spectrum v = ((const Texture<Float, Spectrum> *) o.second)->eval(si);
+                float *dst = o.first == "specular_reflectance" ? b.reflectance : o.first == "specular_transmittance" ? b.k : nullptr;
+                if (dst)
+                    dst[0] = v[0], dst[1] = v[1], dst[2] = v[2];
+            }
         } else {
             if (inner->class_()->name() != "SmoothDiffuse")
-                Throw("BSDF \"%s\" is outside the accelerated path (diffuse | conductor | twosided(...))", inner->class_()->name());
+                Throw("BSDF \"%s\" is outside the accelerated path (diffuse | conductor | dielectric | twosided(...))", inner->class_()->name());
             Spectrum r = inner->eval_diffuse_reflectance(si);            // constant RGB reflectance
             b.reflectance[0] = r[0], b.reflectance[1] = r[1], b.reflectance[2] = r[2];
         }

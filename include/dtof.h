@@ -84,7 +84,9 @@ typedef enum dtof_integrator_kind {
 
 typedef enum dtof_rfilter { DTOF_RFILTER_BOX = 0, DTOF_RFILTER_TENT = 1, DTOF_RFILTER_GAUSSIAN = 2 } dtof_rfilter;
 typedef enum dtof_shape_kind { DTOF_SHAPE_MESH = 0, DTOF_SHAPE_RECTANGLE = 1 } dtof_shape_kind;
-typedef enum dtof_bsdf_kind { DTOF_BSDF_DIFFUSE = 0, DTOF_BSDF_NULL_BLACK = 1, DTOF_BSDF_CONDUCTOR = 2 } dtof_bsdf_kind;
+typedef enum dtof_bsdf_kind {
+    DTOF_BSDF_DIFFUSE = 0, DTOF_BSDF_NULL_BLACK = 1, DTOF_BSDF_CONDUCTOR = 2, DTOF_BSDF_DIELECTRIC = 3
+} dtof_bsdf_kind;
 typedef enum dtof_emitter_kind { DTOF_EMITTER_POINT = 0, DTOF_EMITTER_AREA = 1, DTOF_EMITTER_CONSTANT = 2 } dtof_emitter_kind;
 
 /* ---- scene description ------------------------------------------------------------------ */
@@ -120,15 +122,17 @@ typedef struct dtof_instance {
     float m1[12];             /* to_world at t1 */
 } dtof_instance;
 
-/* SmoothDiffuse (src/bsdfs/diffuse.cpp) or SmoothConductor (src/bsdfs/conductor.cpp: perfect specular reflection
+/* SmoothDiffuse (src/bsdfs/diffuse.cpp), SmoothConductor (src/bsdfs/conductor.cpp: perfect specular reflection
  * weighted by specular_reflectance * fresnel_conductor(cos_theta_i, eta + i k), include/mitsuba/render/fresnel.h:93-117;
- * material "none" is eta = 0, k = 1), optionally wrapped by TwoSidedBRDF (src/bsdfs/twosided.cpp). */
+ * material "none" is eta = 0, k = 1) or SmoothDielectric (src/bsdfs/dielectric.cpp: Fresnel-weighted choice between
+ * specular reflection and refraction, never two-sided); the first two optionally wrapped by TwoSidedBRDF
+ * (src/bsdfs/twosided.cpp). */
 typedef struct dtof_bsdf {
     uint32_t kind;            /* dtof_bsdf_kind */
     uint32_t twosided;
-    float reflectance[3];     /* DIFFUSE: reflectance; CONDUCTOR: specular_reflectance */
-    float eta[3];             /* CONDUCTOR: real part of the index of refraction (RGB) */
-    float k[3];               /* CONDUCTOR: extinction coefficient (RGB) */
+    float reflectance[3];     /* DIFFUSE: reflectance; CONDUCTOR, DIELECTRIC: specular_reflectance */
+    float eta[3];             /* CONDUCTOR: real part of the index of refraction (RGB); DIELECTRIC: eta[0] = int_ior / ext_ior */
+    float k[3];               /* CONDUCTOR: extinction coefficient (RGB); DIELECTRIC: specular_transmittance */
 } dtof_bsdf;
 
 /* PointLight (src/emitters/point.cpp), AreaLight (src/emitters/area.cpp) on mesh `mesh`, or the constant environment

@@ -452,7 +452,7 @@ dtof_status ensure_wavefront(dtof_ctx *ctx, size_t cap, int sets) {
     const size_t o_rng = carve(16), o_rngp = carve(16), o_thr = carve(16), o_res = carve(16), o_prev = carve(16),
                  o_film = carve(8), o_qo0 = carve(16), o_qo1 = carve(16), o_qd0 = carve(16), o_qd1 = carve(16),
                  o_ql0 = carve(4), o_ql1 = carve(4), o_hit = carve(16), o_hi = carve(4), o_so = carve(16), o_sd = carve(16),
-                 o_st = carve(16), o_sc = carve(16), o_sl = carve(4);
+                 o_st = carve(16), o_sc = carve(16), o_sl = carve(4), o_eta = carve(4);
     const size_t o_ring = off;
     off += 256;
     for (int i = 0; i < sets; ++i) {
@@ -466,6 +466,7 @@ dtof_status ensure_wavefront(dtof_ctx *ctx, size_t cap, int sets) {
         W.rng = (ulonglong2 *) (b + o_rng), W.rng_path = (ulonglong2 *) (b + o_rngp);
         W.thr_len = (float4 *) (b + o_thr), W.res_pdf = (float4 *) (b + o_res), W.prev_meta = (float4 *) (b + o_prev);
         W.film_pos = (float2 *) (b + o_film);
+        W.eta = (float *) (b + o_eta);
         W.q_o[0] = (float4 *) (b + o_qo0), W.q_o[1] = (float4 *) (b + o_qo1);
         W.q_d[0] = (float4 *) (b + o_qd0), W.q_d[1] = (float4 *) (b + o_qd1);
         W.q_lane[0] = (uint32_t *) (b + o_ql0), W.q_lane[1] = (uint32_t *) (b + o_ql1);
@@ -759,13 +760,17 @@ dtof_status prepare_scene(dtof_ctx *ctx, const dtof_scene_desc *sc, HostScene &H
     std::vector<uint32_t> mesh_first_gid(sc->n_meshes, 0xffffffffu);
     for (uint32_t i = 0; i < sc->n_bsdfs; ++i) {
         const dtof_bsdf &b = sc->bsdfs[i];
-        if (b.kind > DTOF_BSDF_CONDUCTOR)
+        if (b.kind > DTOF_BSDF_DIELECTRIC)
             return fail(ctx, DTOF_ERR_UNSUPPORTED, "bsdf kind %u is outside the hot-path scope", b.kind);
+        if (b.kind == DTOF_BSDF_DIELECTRIC && b.twosided)
+            return fail(ctx, DTOF_ERR_INVALID, "Only materials without a transmission component can be nested!");   // twosided.cpp:102-103
+        if (b.kind == DTOF_BSDF_DIELECTRIC && !(b.eta[0] > 0.f))
+            return fail(ctx, DTOF_ERR_INVALID, "The interior and exterior indices of refraction must be positive!");
         bsdfs[i] = BsdfRec{ b.reflectance[0], b.reflectance[1], b.reflectance[2],
                             (b.twosided ? 1u : 0u) | (b.kind == DTOF_BSDF_DIFFUSE ? 2u : 0u) |
-                                (b.kind == DTOF_BSDF_CONDUCTOR ? 4u : 0u),
+                                (b.kind == DTOF_BSDF_CONDUCTOR ? 4u : 0u) | (b.kind == DTOF_BSDF_DIELECTRIC ? 8u : 0u),
                             b.eta[0], b.eta[1], b.eta[2], 0.f, b.k[0], b.k[1], b.k[2], 0.f };
-        H.extended = H.extended || b.kind == DTOF_BSDF_CONDUCTOR;
+        H.extended = H.extended || b.kind == DTOF_BSDF_CONDUCTOR || b.kind == DTOF_BSDF_DIELECTRIC;
     }
     uint32_t gid = 0;
     for (uint32_t g = 0; g < sc->n_instances; ++g) {

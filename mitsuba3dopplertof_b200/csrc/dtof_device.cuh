@@ -373,6 +373,24 @@ DTOF_DEV V3 square_to_cosine_hemisphere(float sx, float sy) {
     float z = fsqrt(fmaxf(1.f - fmaf(py, py, px * px), 0.f));
     return v3(px, py, z);
 }
+// fresnel(cos_theta_i, eta) of a dielectric interface (include/mitsuba/render/fresnel.h:35-71)
+DTOF_DEV void fresnel_dielectric(float cos_theta_i, float eta, float &r, float &cos_theta_t, float &eta_it, float &eta_ti) {
+    const bool outside = cos_theta_i >= 0.f;
+    const float rcp_eta = frcp(eta);
+    eta_it = outside ? eta : rcp_eta;
+    eta_ti = outside ? rcp_eta : eta;
+    float cos_theta_t_sqr = fmaf(-fmaf(-cos_theta_i, cos_theta_i, 1.f), eta_ti * eta_ti, 1.f);
+    float ci = fabsf(cos_theta_i), ct = fsqrt(fmaxf(cos_theta_t_sqr, 0.f));
+    float a_s = fdiv(fmaf(-eta_it, ct, ci), fmaf(eta_it, ct, ci));
+    float a_p = fdiv(fmaf(-eta_it, ci, ct), fmaf(eta_it, ci, ct));
+    r = 0.5f * (a_s * a_s + a_p * a_p);
+    if (eta == 1.f)
+        r = 0.f;
+    else if (ci == 0.f)
+        r = 1.f;
+    cos_theta_t = outside ? -ct : ct;   // mulsign_neg(cos_theta_t_abs, cos_theta_i)
+}
+
 // fresnel_conductor (include/mitsuba/render/fresnel.h:93-117), one colour channel
 DTOF_DEV float fresnel_conductor(float cos_theta_i, float eta_r, float eta_i) {
     float cos2 = cos_theta_i * cos_theta_i, sin2 = 1.f - cos2, sin4 = sin2 * sin2;

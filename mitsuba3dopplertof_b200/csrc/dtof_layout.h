@@ -82,9 +82,10 @@ struct MeshRec {
 
 struct alignas(16) BsdfRec {
     float r, g, b;         // diffuse reflectance / conductor specular_reflectance
-    uint32_t flags;        // bit0: twosided, bit1: smooth diffuse lobe present, bit2: smooth conductor (delta reflection)
-    float eta_r, eta_g, eta_b, pad0;   // conductor: complex index of refraction eta + i k
-    float k_r, k_g, k_b, pad1;
+    uint32_t flags;        // bit0: twosided, bit1: smooth diffuse lobe present, bit2: smooth conductor (delta reflection),
+                           // bit3: smooth dielectric (delta reflection + refraction)
+    float eta_r, eta_g, eta_b, pad0;   // conductor: complex index of refraction eta + i k; dielectric: eta_r = int_ior / ext_ior
+    float k_r, k_g, k_b, pad1;         // dielectric: specular_transmittance
 };
 
 struct EmitterRec {

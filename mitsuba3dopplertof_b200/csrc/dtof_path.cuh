@@ -69,13 +69,14 @@ DTOF_DEV PathOut trace_velocity(const DeviceScene &S, const TravPtrs &TP, const 
 struct PathState {
     V3 throughput, result, prev_p;
     float path_length, prev_bsdf_pdf;
+    float eta;   // product of the sampled lobes' relative indices of refraction (:251); only dielectrics change it
     uint32_t depth;
     bool valid_ray, prev_bsdf_delta, active;
     // eta: every BSDF in scope has eta = 1 on a live path (bs.eta is 0 only where the throughput is 0 too and the
     // lane stops), so `path_length += t * eta`, `eta *= bs.eta` and `rr_prob = tmax * eta^2` reduce to eta == 1.
     DTOF_DEV void init(bool on, bool env_visible) {
         throughput = v3(1, 1, 1), result = v3(0, 0, 0), prev_p = v3(0, 0, 0);
-        path_length = 0.f, prev_bsdf_pdf = 1.f;
+        path_length = 0.f, prev_bsdf_pdf = 1.f, eta = 1.f;
         depth = 0;
         valid_ray = env_visible;                  // !hide_emitters && the scene has an environment emitter (:102)
         prev_bsdf_delta = true;
@@ -124,7 +125,7 @@ DTOF_DEV void shade_bounce(const DeviceScene &S, const float4 *__restrict__ I, c
         const float4 b0 = *reinterpret_cast<const float4 *>(&S.bsdfs[mr.bsdf]);   // {r, g, b, flags}
         bsdf_flags = __float_as_uint(b0.w);
         refl = v3(b0.x, b0.y, b0.z);
-        path_length += h.t;                                             // :141 (eta == 1)
+        path_length += ENV ? h.t * ps.eta : h.t;                        // :141 (eta == 1 without dielectrics)
     }
     // ---- direct emission (:150-168)
     if (valid && mesh_emitter >= 0) {
@@ -230,7 +231,11 @@ DTOF_DEV void shade_bounce(const DeviceScene &S, const float4 *__restrict__ I, c
     }
     // an occluded or zero-pdf emitter sample clears active_em (:190): the term is pending iff nee.want
     // ---- BSDF eval + sample (:206-210); sample_1 is drawn but unused by the diffuse lobe
-    smp.template skip_1d<DOPPLER>();
+    float s1 = 0.f;                                                     // lobe selection of the dielectric
+    if (ENV)
+        s1 = smp.template next_1d<DOPPLER>(correlate);
+    else
+        smp.template skip_1d<DOPPLER>();
     float s2x = smp.template next_1d<DOPPLER>(correlate), s2y = smp.template next_1d<DOPPLER>(correlate);
     V3 bsdf_val = v3(0, 0, 0), bsdf_weight = v3(0, 0, 0), bs_wo = v3(0, 0, 0);
     float bsdf_pdf = 0.f, bs_pdf = 0.f;                                 // zero-initialised BSDFSample3f
@@ -265,6 +270,24 @@ DTOF_DEV void shade_bounce(const DeviceScene &S, const float4 *__restrict__ I, c
             sampled_delta = true;                                        // bs.sampled_type = DeltaReflection
         }
     }
+    float bs_eta = 1.f;
+    if (ENV && valid && (bsdf_flags & 8u)) {                             // SmoothDielectric::sample, dielectric.cpp:250-366
+        const BsdfRec &br = S.bsdfs[bsdf_id];
+        float r_i, cos_theta_t, eta_it, eta_ti;
+        fresnel_dielectric(si.wi.z, br.eta_r, r_i, cos_theta_t, eta_it, eta_ti);
+        const bool selected_r = s1 <= r_i;
+        bs_pdf = selected_r ? r_i : 1.f - r_i;
+        if (selected_r) {
+            bs_wo = v3(-si.wi.x, -si.wi.y, si.wi.z);                     // reflect(wi)
+            bsdf_weight = refl;
+        } else {
+            bs_wo = v3(-eta_ti * si.wi.x, -eta_ti * si.wi.y, cos_theta_t);   // refract(wi, cos_theta_t, eta_ti)
+            bs_eta = eta_it;
+            const float f2 = eta_ti * eta_ti;                            // radiance is scaled by the solid-angle compression
+            bsdf_weight = v3(br.k_r * f2, br.k_g * f2, br.k_b * f2);
+        }
+        sampled_delta = true;
+    }
     // ---- emitter sampling contribution (:214-226), added once the shadow ray is known to be unoccluded
     if (nee.want) {
         float mis_em = ds_delta ? 1.f : mis_weight(ds_pdf, bsdf_pdf);
@@ -288,7 +311,9 @@ DTOF_DEV void shade_bounce(const DeviceScene &S, const float4 *__restrict__ I, c
     if (valid)
         depth += 1;
     float tmax = max3(throughput);
-    float rr_prob = fminf(tmax, 0.95f);                                 // eta == 1
+    if (ENV)
+        ps.eta *= bs_eta;                                               // :251
+    float rr_prob = fminf(ENV ? tmax * (ps.eta * ps.eta) : tmax, 0.95f);   // :264
     bool rr_active = depth >= rr_depth;
     float q = smp.template next_1d<DOPPLER>(correlate);                 // always drawn
     bool rr_continue = q < rr_prob;

@@ -44,6 +44,7 @@ struct WfBuffers {
     float4 *res_pdf;                // result.xyz, prev_bsdf_pdf
     float4 *prev_meta;              // prev_p.xyz, bits: depth | valid_ray << 30 | prev_bsdf_delta << 31
     float2 *film_pos;               // position handed to ImageBlock::put
+    float *eta;                     // accumulated relative index of refraction; touched only in scenes with dielectrics
     // path-ray queues (ping-pong), compacted: {o.xyz, maxt}, {d.xyz, time}, lane slot
     float4 *q_o[2], *q_d[2];
     uint32_t *q_lane[2];
@@ -148,6 +149,8 @@ __global__ void __launch_bounds__(kWfBlock) wf_generate_kernel(const __grid_cons
         B.prev_meta[s] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0x80000000u |
                                      ((A.scene.env_emitter >= 0 && !A.p.hide_emitters) ? 0x40000000u : 0u)));
         B.film_pos[s] = make_float2(spx, spy);
+        if (A.scene.extended)
+            B.eta[s] = 1.f;
         if (any_depth) {
             B.q_o[0][s] = make_float4(o.x, o.y, o.z, maxt);
             B.q_d[0][s] = make_float4(d.x, d.y, d.z, ray_time);
@@ -402,6 +405,7 @@ wf_shade_kernel(const __grid_constant__ WfArgs A) {
             ps.depth = meta & 0x3fffffffu;
             ps.valid_ray = (meta & 0x40000000u) != 0;
             ps.prev_bsdf_delta = (meta & 0x80000000u) != 0;
+            ps.eta = A.scene.extended ? B.eta[s] : 1.f;
             ps.active = true;
             LaneSampler smp;
             const ulonglong2 g = B.rng[s];
@@ -416,6 +420,8 @@ wf_shade_kernel(const __grid_constant__ WfArgs A) {
             B.rng[s] = make_ulonglong2(smp.rng.state, smp.rng.inc);
             if (DOPPLER)
                 B.rng_path[s] = make_ulonglong2(smp.rng_path.state, smp.rng_path.inc);
+            if (A.scene.extended)
+                B.eta[s] = ps.eta;
             B.thr_len[s] = make_float4(ps.throughput.x, ps.throughput.y, ps.throughput.z, ps.path_length);
             B.res_pdf[s] = make_float4(ps.result.x, ps.result.y, ps.result.z, ps.prev_bsdf_pdf);
             B.prev_meta[s] = make_float4(ps.prev_p.x, ps.prev_p.y, ps.prev_p.z,

@@ -35,7 +35,8 @@ f32 = np.float32
 class Bsdf:
     """``diffuse`` (src/bsdfs/diffuse.cpp) or ``conductor`` (src/bsdfs/conductor.cpp: `reflectance` is its
     specular_reflectance, `eta` / `k` the complex index of refraction, material "none" = (0, 1)), optionally wrapped in
-    ``twosided`` (src/bsdfs/twosided.cpp)."""
+    ``twosided`` (src/bsdfs/twosided.cpp); or ``dielectric`` (src/bsdfs/dielectric.cpp: `eta[0]` = int_ior / ext_ior,
+    `reflectance` / `k` = specular_reflectance / specular_transmittance; never two-sided)."""
     reflectance: Sequence[float] = (0.5, 0.5, 0.5)   # SmoothDiffuse default reflectance 0.5
     twosided: bool = False
     kind: int = _abi.BSDF_DIFFUSE
@@ -307,7 +308,7 @@ class Scene:
             def rgb(v):
                 v = np.atleast_1d(np.asarray(v, f32))
                 return tuple(float(x) for x in ((v.tolist() * 3)[:3] if v.size == 1 else v.tolist()))
-            conductor = b.kind == _abi.BSDF_CONDUCTOR
+            conductor = b.kind in (_abi.BSDF_CONDUCTOR, _abi.BSDF_DIELECTRIC)   # the kinds that use eta / k
             key = (b.kind, bool(b.twosided), tuple(float(f32(x)) for x in b.reflectance),
                    rgb(b.eta) if conductor else (0.0,) * 3, rgb(b.k) if conductor else (0.0,) * 3)
             if key not in bsdf_index:

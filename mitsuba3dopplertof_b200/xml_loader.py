@@ -122,6 +122,9 @@ class _Loader:
             if len(inner) != 1:
                 raise ValueError("twosided with two different BRDFs is outside the hot-path scope")
             b = self.bsdf_or_ref(inner[0])
+            from . import _abi
+            if b.kind == _abi.BSDF_DIELECTRIC:   # twosided.cpp:102-103
+                raise ValueError("Only materials without a transmission component can be nested!")
             return Bsdf(b.reflectance, True, b.kind, b.eta, b.k)
         if typ == "diffuse":
             p = self.props(node)
@@ -142,7 +145,19 @@ class _Loader:
                 raise ValueError(f"conductor material '{material}' (measured spectra) is outside the hot-path scope: give eta / k")
             return Bsdf(p.get("specular_reflectance", (1.0, 1.0, 1.0)), False, _abi.BSDF_CONDUCTOR,
                         p.get("eta", (0.0, 0.0, 0.0)), p.get("k", (1.0, 1.0, 1.0)))
-        raise ValueError(f"bsdf type '{typ}' is outside the hot-path scope (diffuse|conductor|twosided)")
+        if typ == "dielectric":   # SmoothDielectric ctor, src/bsdfs/dielectric.cpp:199-228
+            from . import _abi
+            p = self.props(node)
+            unknown = set(p) - {"int_ior", "ext_ior", "specular_reflectance", "specular_transmittance"}
+            if unknown:
+                raise ValueError(f"dielectric: unreferenced property {sorted(unknown)}")
+            int_ior, ext_ior = lookup_ior(p.get("int_ior", "bk7")), lookup_ior(p.get("ext_ior", "air"))
+            if int_ior < 0 or ext_ior < 0:
+                raise ValueError("The interior and exterior indices of refraction must be positive!")
+            eta = float(np.float32(int_ior) / np.float32(ext_ior))
+            return Bsdf(p.get("specular_reflectance", (1.0, 1.0, 1.0)), False, _abi.BSDF_DIELECTRIC, (eta, 0.0, 0.0),
+                        p.get("specular_transmittance", (1.0, 1.0, 1.0)))
+        raise ValueError(f"bsdf type '{typ}' is outside the hot-path scope (diffuse|conductor|dielectric|twosided)")
 
     def bsdf_or_ref(self, node) -> Bsdf:
         if node.tag == "ref":
@@ -302,6 +317,28 @@ def load_file(path: str, **params) -> Scene:
     """`mi.load_file(path, **params)`: params override `<default>` values like `-Dkey=value`."""
     tree = ET.parse(path)
     return _Loader({k: str(v) for k, v in params.items()}, os.path.dirname(os.path.abspath(path))).load(tree.getroot())
+
+
+# include/mitsuba/render/ior.h:23-49
+_IOR = {"vacuum": 1.0, "helium": 1.000036, "hydrogen": 1.000132, "air": 1.000277, "carbon dioxide": 1.00045,
+        "water": 1.3330, "acetone": 1.36, "ethanol": 1.361, "carbon tetrachloride": 1.461, "glycerol": 1.4729,
+        "benzene": 1.501, "silicone oil": 1.52045, "bromine": 1.661, "water ice": 1.31, "fused quartz": 1.458,
+        "pyrex": 1.470, "acrylic glass": 1.49, "polypropylene": 1.49, "bk7": 1.5046, "sodium chloride": 1.544,
+        "amber": 1.55, "pet": 1.5750, "diamond": 2.419}
+
+
+def lookup_ior(value) -> float:
+    """`lookup_ior` (include/mitsuba/render/ior.h:52-98): a number, or the name of a material of the table."""
+    if isinstance(value, (int, float)):
+        return float(value)
+    name = str(value).strip().lower()
+    try:
+        return float(name)
+    except ValueError:
+        pass
+    if name not in _IOR:
+        raise ValueError(f'Unable to find an IOR value for "{name}"! Valid choices are: ' + ", ".join(_IOR))
+    return _IOR[name]
 
 
 def load_string(xml: str, base_dir: str = ".", **params) -> Scene:

@@ -412,6 +412,23 @@ struct Modulation {
 // ------------------------------------------------------------------------------------------
 // Warps / frames
 // ------------------------------------------------------------------------------------------
+// fresnel(cos_theta_i, eta) of a dielectric interface, include/mitsuba/render/fresnel.h:35-71
+inline void fresnel_dielectric(float cos_theta_i, float eta, float &r, float &cos_theta_t, float &eta_it, float &eta_ti) {
+    bool outside = cos_theta_i >= 0.f;
+    float rcp_eta = 1.f / eta;
+    eta_it = outside ? eta : rcp_eta;
+    eta_ti = outside ? rcp_eta : eta;
+    float cos_theta_t_sqr = fmaf(-fmaf(-cos_theta_i, cos_theta_i, 1.f), eta_ti * eta_ti, 1.f);
+    float ci = fabsf(cos_theta_i), ct = sqrtf(std::max(cos_theta_t_sqr, 0.f));
+    bool index_matched = eta == 1.f, special = index_matched || ci == 0.f;
+    float a_s = fmaf(-eta_it, ct, ci) / fmaf(eta_it, ct, ci);
+    float a_p = fmaf(-eta_it, ci, ct) / fmaf(eta_it, ci, ct);
+    r = 0.5f * (a_s * a_s + a_p * a_p);
+    if (special)
+        r = index_matched ? 0.f : 1.f;
+    cos_theta_t = cos_theta_i >= 0.f ? -ct : ct; // mulsign_neg = select(v2 >= 0, -v1, v1), array_router.h:389-396
+}
+
 // fresnel_conductor, include/mitsuba/render/fresnel.h:93-117 (one colour channel)
 inline float fresnel_conductor(float cos_theta_i, float eta_r, float eta_i) {
     float cos2 = cos_theta_i * cos_theta_i, sin2 = 1.f - cos2, sin4 = sin2 * sin2;
@@ -1044,7 +1061,6 @@ PathResult trace_path(const dtof_oracle_scene &sc, const dtof_params &P, const M
 
         // ---- BSDF eval + sample (:206-210); draws ALWAYS consumed
         float s1 = smp.next_1d(correlate);
-        (void) s1;
         float s2x = smp.next_1d(correlate), s2y = smp.next_1d(correlate);
 
         V3 bsdf_val = v3(0, 0, 0), bsdf_weight = v3(0, 0, 0), bs_wo = v3(0, 0, 0);
@@ -1086,6 +1102,25 @@ PathResult trace_path(const dtof_oracle_scene &sc, const dtof_params &P, const M
                                  bsdf->reflectance[2] * fresnel_conductor(wi_z, bsdf->eta[2], bsdf->k[2]));
                 sampled_delta = true; // bs.sampled_type = DeltaReflection
             }
+        }
+
+        if (valid && bsdf->kind == DTOF_BSDF_DIELECTRIC) { // SmoothDielectric::sample, dielectric.cpp:250-366
+            float r_i, cos_theta_t, eta_it, eta_ti;
+            fresnel_dielectric(si.wi.z, bsdf->eta[0], r_i, cos_theta_t, eta_it, eta_ti);
+            float t_i = 1.f - r_i;
+            bool selected_r = s1 <= r_i;
+            bs_pdf = selected_r ? r_i : t_i;
+            if (selected_r) {
+                bs_wo = v3(-si.wi.x, -si.wi.y, si.wi.z); // reflect(wi)
+                bs_eta = 1.f;
+                bsdf_weight = v3(bsdf->reflectance[0], bsdf->reflectance[1], bsdf->reflectance[2]);
+            } else {
+                bs_wo = v3(-eta_ti * si.wi.x, -eta_ti * si.wi.y, cos_theta_t); // refract(wi, cos_theta_t, eta_ti), fresnel.h
+                bs_eta = eta_it;
+                float f2 = eta_ti * eta_ti; // TransportMode::Radiance: solid-angle compression
+                bsdf_weight = v3(bsdf->k[0] * f2, bsdf->k[1] * f2, bsdf->k[2] * f2);
+            }
+            sampled_delta = true;
         }
 
         // ---- emitter sampling contribution (:214-226)

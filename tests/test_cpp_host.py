@@ -56,7 +56,8 @@ CASES = [
     ("c5_slabroom.xml", {"tcn": 3, "pcn": 6}),
     ("c6_serialized.xml", {}),
     ("c7_constant.xml", {"max_depth": 5}),          # constant environment emitter + point light
-    ("c8_conductor.xml", {"max_depth": 6}),         # smooth conductors (explicit eta / k, and the two-sided mirror)                      # `serialized` shape: zlib container, sub-mesh 1, double precision
+    ("c8_conductor.xml", {"max_depth": 6}),         # smooth conductors (explicit eta / k, and the two-sided mirror)
+    ("c9_dielectric.xml", {"max_depth": 8}),        # smooth dielectrics (named and numeric indices of refraction, tints)                      # `serialized` shape: zlib container, sub-mesh 1, double precision
 ]
 
 
