@@ -638,7 +638,8 @@ std::unique_ptr<FlatScene> Scene::flatten() const {
         Bsdf b = s.has_bsdf ? s.bsdf : Bsdf();   // Shape default BSDF: diffuse (src/render/shape.cpp:60-65)
         for (size_t i = 0; i < fs->bsdfs.size(); ++i) {
             const dtof_bsdf &o = fs->bsdfs[i];
-            const bool c = b.kind == DTOF_BSDF_CONDUCTOR || b.kind == DTOF_BSDF_DIELECTRIC;   // the kinds that use eta / k
+            const bool c = b.kind == DTOF_BSDF_CONDUCTOR || b.kind == DTOF_BSDF_DIELECTRIC ||
+                           b.kind == DTOF_BSDF_THINDIELECTRIC;   // the kinds that use eta / k
             if (o.kind == b.kind && (o.twosided != 0) == b.twosided && o.reflectance[0] == b.reflectance[0] &&
                 o.reflectance[1] == b.reflectance[1] && o.reflectance[2] == b.reflectance[2] &&
                 (!c || (!memcmp(o.eta, b.eta, sizeof(o.eta)) && !memcmp(o.k, b.k, sizeof(o.k)))))
@@ -648,7 +649,7 @@ std::unique_ptr<FlatScene> Scene::flatten() const {
         nb.kind = b.kind;
         nb.twosided = b.twosided ? 1u : 0u;
         memcpy(nb.reflectance, b.reflectance, sizeof(nb.reflectance));
-        if (b.kind == DTOF_BSDF_CONDUCTOR || b.kind == DTOF_BSDF_DIELECTRIC) {
+        if (b.kind == DTOF_BSDF_CONDUCTOR || b.kind == DTOF_BSDF_DIELECTRIC || b.kind == DTOF_BSDF_THINDIELECTRIC) {
             memcpy(nb.eta, b.eta, sizeof(nb.eta));
             memcpy(nb.k, b.k, sizeof(nb.k));
         }
@@ -914,7 +915,7 @@ struct Loader {
             if (n != 1)
                 throw Error("twosided with two different BRDFs is outside the hot-path scope");
             Bsdf b = bsdf_or_ref(*inner);
-            if (b.kind == DTOF_BSDF_DIELECTRIC)   // twosided.cpp:102-103
+            if (b.kind == DTOF_BSDF_DIELECTRIC || b.kind == DTOF_BSDF_THINDIELECTRIC)   // twosided.cpp:102-103
                 throw Error("Only materials without a transmission component can be nested!");
             b.twosided = true;
             return b;
@@ -946,15 +947,15 @@ struct Loader {
             }
             return b;
         }
-        if (typ == "dielectric") {   // SmoothDielectric ctor, src/bsdfs/dielectric.cpp:199-228
+        if (typ == "dielectric" || typ == "thindielectric") {   // dielectric.cpp:199-228, thindielectric.cpp:104-126
             auto p = props(node);
-            reject_unknown(p, { "int_ior", "ext_ior", "specular_reflectance", "specular_transmittance" }, "dielectric");
+            reject_unknown(p, { "int_ior", "ext_ior", "specular_reflectance", "specular_transmittance" }, typ.c_str());
             const float int_ior = lookup_ior(p.count("int_ior") ? p["int_ior"].value : "bk7");
             const float ext_ior = lookup_ior(p.count("ext_ior") ? p["ext_ior"].value : "air");
             if (int_ior < 0.f || ext_ior < 0.f)
                 throw Error("The interior and exterior indices of refraction must be positive!");
             Bsdf b;
-            b.kind = DTOF_BSDF_DIELECTRIC;
+            b.kind = typ == "dielectric" ? DTOF_BSDF_DIELECTRIC : DTOF_BSDF_THINDIELECTRIC;
             b.eta[0] = int_ior / ext_ior, b.eta[1] = b.eta[2] = 0.f;
             for (int i = 0; i < 3; ++i) {
                 b.reflectance[i] = p.count("specular_reflectance") ? (float) p["specular_reflectance"].vec[i] : 1.f;
@@ -962,7 +963,7 @@ struct Loader {
             }
             return b;
         }
-        throw Error("bsdf type '" + typ + "' is outside the hot-path scope (diffuse|conductor|dielectric|twosided)");
+        throw Error("bsdf type '" + typ + "' is outside the hot-path scope (diffuse|conductor|dielectric|thindielectric|twosided)");
     }
     Bsdf bsdf_or_ref(const XmlNode &node) {
         if (node.tag == "ref") {

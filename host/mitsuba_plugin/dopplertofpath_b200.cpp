@@ -203,8 +203,9 @@ private:
             Spectrum e = tex("eta"), k = tex("k"), r = tex("specular_reflectance");
             for (int i = 0; i < 3; ++i)
                 b.eta[i] = e[i], b.k[i] = k[i], b.reflectance[i] = r[i];
-        } else if (inner->class_()->name() == "SmoothDielectric") {        // eta + optional tints (dielectric.cpp:230-237)
-            b.kind = DTOF_BSDF_DIELECTRIC;
+        } else if (inner->class_()->name() == "SmoothDielectric" || inner->class_()->name() == "ThinDielectric") {
+            // eta + optional tints (dielectric.cpp:230-237, thindielectric.cpp:128-138)
+            b.kind = inner->class_()->name() == "SmoothDielectric" ? DTOF_BSDF_DIELECTRIC : DTOF_BSDF_THINDIELECTRIC;
             Collector c;
             const_cast<BSDF *>(inner)->traverse(&c);
             b.eta[0] = (float) *c.param<ScalarFloat>("eta");

@@ -85,7 +85,8 @@ typedef enum dtof_integrator_kind {
 typedef enum dtof_rfilter { DTOF_RFILTER_BOX = 0, DTOF_RFILTER_TENT = 1, DTOF_RFILTER_GAUSSIAN = 2 } dtof_rfilter;
 typedef enum dtof_shape_kind { DTOF_SHAPE_MESH = 0, DTOF_SHAPE_RECTANGLE = 1 } dtof_shape_kind;
 typedef enum dtof_bsdf_kind {
-    DTOF_BSDF_DIFFUSE = 0, DTOF_BSDF_NULL_BLACK = 1, DTOF_BSDF_CONDUCTOR = 2, DTOF_BSDF_DIELECTRIC = 3
+    DTOF_BSDF_DIFFUSE = 0, DTOF_BSDF_NULL_BLACK = 1, DTOF_BSDF_CONDUCTOR = 2, DTOF_BSDF_DIELECTRIC = 3,
+    DTOF_BSDF_THINDIELECTRIC = 4
 } dtof_bsdf_kind;
 typedef enum dtof_emitter_kind { DTOF_EMITTER_POINT = 0, DTOF_EMITTER_AREA = 1, DTOF_EMITTER_CONSTANT = 2 } dtof_emitter_kind;
 
@@ -125,8 +126,9 @@ typedef struct dtof_instance {
 /* SmoothDiffuse (src/bsdfs/diffuse.cpp), SmoothConductor (src/bsdfs/conductor.cpp: perfect specular reflection
  * weighted by specular_reflectance * fresnel_conductor(cos_theta_i, eta + i k), include/mitsuba/render/fresnel.h:93-117;
  * material "none" is eta = 0, k = 1) or SmoothDielectric (src/bsdfs/dielectric.cpp: Fresnel-weighted choice between
- * specular reflection and refraction, never two-sided); the first two optionally wrapped by TwoSidedBRDF
- * (src/bsdfs/twosided.cpp). */
+ * specular reflection and refraction, never two-sided) or ThinDielectric (src/bsdfs/thindielectric.cpp: a thin slab,
+ * r' = 2r / (1 + r), the transmitted ray goes straight on as a Null interaction; same fields as DIELECTRIC); the first
+ * two optionally wrapped by TwoSidedBRDF (src/bsdfs/twosided.cpp). */
 typedef struct dtof_bsdf {
     uint32_t kind;            /* dtof_bsdf_kind */
     uint32_t twosided;

@@ -760,17 +760,19 @@ dtof_status prepare_scene(dtof_ctx *ctx, const dtof_scene_desc *sc, HostScene &H
     std::vector<uint32_t> mesh_first_gid(sc->n_meshes, 0xffffffffu);
     for (uint32_t i = 0; i < sc->n_bsdfs; ++i) {
         const dtof_bsdf &b = sc->bsdfs[i];
-        if (b.kind > DTOF_BSDF_DIELECTRIC)
+        if (b.kind > DTOF_BSDF_THINDIELECTRIC)
             return fail(ctx, DTOF_ERR_UNSUPPORTED, "bsdf kind %u is outside the hot-path scope", b.kind);
-        if (b.kind == DTOF_BSDF_DIELECTRIC && b.twosided)
+        const bool dielectric = b.kind == DTOF_BSDF_DIELECTRIC || b.kind == DTOF_BSDF_THINDIELECTRIC;
+        if (dielectric && b.twosided)
             return fail(ctx, DTOF_ERR_INVALID, "Only materials without a transmission component can be nested!");   // twosided.cpp:102-103
-        if (b.kind == DTOF_BSDF_DIELECTRIC && !(b.eta[0] > 0.f))
+        if (dielectric && !(b.eta[0] > 0.f))
             return fail(ctx, DTOF_ERR_INVALID, "The interior and exterior indices of refraction must be positive!");
         bsdfs[i] = BsdfRec{ b.reflectance[0], b.reflectance[1], b.reflectance[2],
                             (b.twosided ? 1u : 0u) | (b.kind == DTOF_BSDF_DIFFUSE ? 2u : 0u) |
-                                (b.kind == DTOF_BSDF_CONDUCTOR ? 4u : 0u) | (b.kind == DTOF_BSDF_DIELECTRIC ? 8u : 0u),
+                                (b.kind == DTOF_BSDF_CONDUCTOR ? 4u : 0u) | (dielectric ? 8u : 0u) |
+                                (b.kind == DTOF_BSDF_THINDIELECTRIC ? 16u : 0u),
                             b.eta[0], b.eta[1], b.eta[2], 0.f, b.k[0], b.k[1], b.k[2], 0.f };
-        H.extended = H.extended || b.kind == DTOF_BSDF_CONDUCTOR || b.kind == DTOF_BSDF_DIELECTRIC;
+        H.extended = H.extended || b.kind == DTOF_BSDF_CONDUCTOR || dielectric;
     }
     uint32_t gid = 0;
     for (uint32_t g = 0; g < sc->n_instances; ++g) {

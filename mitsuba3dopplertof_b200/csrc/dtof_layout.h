@@ -83,7 +83,7 @@ struct MeshRec {
 struct alignas(16) BsdfRec {
     float r, g, b;         // diffuse reflectance / conductor specular_reflectance
     uint32_t flags;        // bit0: twosided, bit1: smooth diffuse lobe present, bit2: smooth conductor (delta reflection),
-                           // bit3: smooth dielectric (delta reflection + refraction)
+                           // bit3: smooth dielectric (delta reflection + refraction), bit4: thin dielectric (+ bit3)
     float eta_r, eta_g, eta_b, pad0;   // conductor: complex index of refraction eta + i k; dielectric: eta_r = int_ior / ext_ior
     float k_r, k_g, k_b, pad1;         // dielectric: specular_transmittance
 };

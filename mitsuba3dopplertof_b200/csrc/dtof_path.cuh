@@ -271,15 +271,23 @@ DTOF_DEV void shade_bounce(const DeviceScene &S, const float4 *__restrict__ I, c
         }
     }
     float bs_eta = 1.f;
-    if (ENV && valid && (bsdf_flags & 8u)) {                             // SmoothDielectric::sample, dielectric.cpp:250-366
+    bool sampled_null = false;
+    if (ENV && valid && (bsdf_flags & 8u)) {     // SmoothDielectric::sample (dielectric.cpp:250-366), ThinDielectric (thindielectric.cpp:140-189)
         const BsdfRec &br = S.bsdfs[bsdf_id];
+        const bool thin = (bsdf_flags & 16u) != 0;
         float r_i, cos_theta_t, eta_it, eta_ti;
-        fresnel_dielectric(si.wi.z, br.eta_r, r_i, cos_theta_t, eta_it, eta_ti);
+        fresnel_dielectric(thin ? fabsf(si.wi.z) : si.wi.z, br.eta_r, r_i, cos_theta_t, eta_it, eta_ti);
+        if (thin)
+            r_i *= fdiv(2.f, 1.f + r_i);                                 // internal reflections: r' = r + trt + tr^3t + ..
         const bool selected_r = s1 <= r_i;
         bs_pdf = selected_r ? r_i : 1.f - r_i;
         if (selected_r) {
             bs_wo = v3(-si.wi.x, -si.wi.y, si.wi.z);                     // reflect(wi)
             bsdf_weight = refl;
+        } else if (thin) {
+            bs_wo = v3(-si.wi.x, -si.wi.y, -si.wi.z);                    // straight on: a Null interaction
+            bsdf_weight = v3(br.k_r, br.k_g, br.k_b);
+            sampled_null = true;
         } else {
             bs_wo = v3(-eta_ti * si.wi.x, -eta_ti * si.wi.y, cos_theta_t);   // refract(wi, cos_theta_t, eta_ti)
             bs_eta = eta_it;
@@ -304,7 +312,7 @@ DTOF_DEV void shade_bounce(const DeviceScene &S, const float4 *__restrict__ I, c
         ps.prev_p = si.p;
     }
     throughput = throughput * bsdf_weight;
-    ps.valid_ray = ps.valid_ray || valid;                               // :253-254
+    ps.valid_ray = ps.valid_ray || (valid && !(ENV && sampled_null));   // :253-254: not for a Null interaction
     ps.prev_bsdf_pdf = bs_pdf;
     ps.prev_bsdf_delta = sampled_delta;                                 // has_flag(bsdf_sample.sampled_type, Delta), :250
     // ---- stopping criterion (:262-276)

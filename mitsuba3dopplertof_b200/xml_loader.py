@@ -123,7 +123,7 @@ class _Loader:
                 raise ValueError("twosided with two different BRDFs is outside the hot-path scope")
             b = self.bsdf_or_ref(inner[0])
             from . import _abi
-            if b.kind == _abi.BSDF_DIELECTRIC:   # twosided.cpp:102-103
+            if b.kind in (_abi.BSDF_DIELECTRIC, _abi.BSDF_THINDIELECTRIC):   # twosided.cpp:102-103
                 raise ValueError("Only materials without a transmission component can be nested!")
             return Bsdf(b.reflectance, True, b.kind, b.eta, b.k)
         if typ == "diffuse":
@@ -145,19 +145,20 @@ class _Loader:
                 raise ValueError(f"conductor material '{material}' (measured spectra) is outside the hot-path scope: give eta / k")
             return Bsdf(p.get("specular_reflectance", (1.0, 1.0, 1.0)), False, _abi.BSDF_CONDUCTOR,
                         p.get("eta", (0.0, 0.0, 0.0)), p.get("k", (1.0, 1.0, 1.0)))
-        if typ == "dielectric":   # SmoothDielectric ctor, src/bsdfs/dielectric.cpp:199-228
+        if typ in ("dielectric", "thindielectric"):   # dielectric.cpp:199-228, thindielectric.cpp:104-126
             from . import _abi
             p = self.props(node)
             unknown = set(p) - {"int_ior", "ext_ior", "specular_reflectance", "specular_transmittance"}
             if unknown:
-                raise ValueError(f"dielectric: unreferenced property {sorted(unknown)}")
+                raise ValueError(f"{typ}: unreferenced property {sorted(unknown)}")
             int_ior, ext_ior = lookup_ior(p.get("int_ior", "bk7")), lookup_ior(p.get("ext_ior", "air"))
             if int_ior < 0 or ext_ior < 0:
                 raise ValueError("The interior and exterior indices of refraction must be positive!")
             eta = float(np.float32(int_ior) / np.float32(ext_ior))
-            return Bsdf(p.get("specular_reflectance", (1.0, 1.0, 1.0)), False, _abi.BSDF_DIELECTRIC, (eta, 0.0, 0.0),
+            return Bsdf(p.get("specular_reflectance", (1.0, 1.0, 1.0)), False,
+                        _abi.BSDF_DIELECTRIC if typ == "dielectric" else _abi.BSDF_THINDIELECTRIC, (eta, 0.0, 0.0),
                         p.get("specular_transmittance", (1.0, 1.0, 1.0)))
-        raise ValueError(f"bsdf type '{typ}' is outside the hot-path scope (diffuse|conductor|dielectric|twosided)")
+        raise ValueError(f"bsdf type '{typ}' is outside the hot-path scope (diffuse|conductor|dielectric|thindielectric|twosided)")
 
     def bsdf_or_ref(self, node) -> Bsdf:
         if node.tag == "ref":

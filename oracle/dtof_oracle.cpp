@@ -1104,9 +1104,14 @@ PathResult trace_path(const dtof_oracle_scene &sc, const dtof_params &P, const M
             }
         }
 
-        if (valid && bsdf->kind == DTOF_BSDF_DIELECTRIC) { // SmoothDielectric::sample, dielectric.cpp:250-366
+        bool sampled_null = false;
+        if (valid && (bsdf->kind == DTOF_BSDF_DIELECTRIC || bsdf->kind == DTOF_BSDF_THINDIELECTRIC)) {
+            // SmoothDielectric::sample (dielectric.cpp:250-366) / ThinDielectric::sample (thindielectric.cpp:140-189)
+            const bool thin = bsdf->kind == DTOF_BSDF_THINDIELECTRIC;
             float r_i, cos_theta_t, eta_it, eta_ti;
-            fresnel_dielectric(si.wi.z, bsdf->eta[0], r_i, cos_theta_t, eta_it, eta_ti);
+            fresnel_dielectric(thin ? fabsf(si.wi.z) : si.wi.z, bsdf->eta[0], r_i, cos_theta_t, eta_it, eta_ti);
+            if (thin)
+                r_i *= 2.f / (1.f + r_i); // internal reflections: r' = r + trt + tr^3t + ..
             float t_i = 1.f - r_i;
             bool selected_r = s1 <= r_i;
             bs_pdf = selected_r ? r_i : t_i;
@@ -1114,6 +1119,11 @@ PathResult trace_path(const dtof_oracle_scene &sc, const dtof_params &P, const M
                 bs_wo = v3(-si.wi.x, -si.wi.y, si.wi.z); // reflect(wi)
                 bs_eta = 1.f;
                 bsdf_weight = v3(bsdf->reflectance[0], bsdf->reflectance[1], bsdf->reflectance[2]);
+            } else if (thin) {
+                bs_wo = v3(-si.wi.x, -si.wi.y, -si.wi.z); // straight on: BSDFFlags::Null
+                bs_eta = 1.f;
+                bsdf_weight = v3(bsdf->k[0], bsdf->k[1], bsdf->k[2]);
+                sampled_null = true;
             } else {
                 bs_wo = v3(-eta_ti * si.wi.x, -eta_ti * si.wi.y, cos_theta_t); // refract(wi, cos_theta_t, eta_ti), fresnel.h
                 bs_eta = eta_it;
@@ -1144,7 +1154,7 @@ PathResult trace_path(const dtof_oracle_scene &sc, const dtof_params &P, const M
         }
         throughput = throughput * bsdf_weight;
         eta *= bs_eta;
-        valid_ray = valid_ray || valid; // :253-254
+        valid_ray = valid_ray || (valid && !sampled_null); // :253-254: a Null interaction does not make the ray valid
         prev_bsdf_pdf = bs_pdf;
         prev_bsdf_delta = sampled_delta; // has_flag(bsdf_sample.sampled_type, BSDFFlags::Delta), :250
 

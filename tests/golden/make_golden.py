@@ -62,6 +62,8 @@ CASES = {
     # smooth dielectrics: the short box is bk7 glass in air, the tall box water with tinted lobes (eta tracking)
     "c9_dielectric": ("c9_dielectric", {"max_depth": 8, "pcd": 8}, 0, True),
     "c9_dielectric_homodyne": ("c9_dielectric", {"hetero_frequency": 0.0, "max_depth": 12, "rr_depth": 3, "pcd": 2}, 5, True),
+    # c9 + a tinted thin glass pane (thindielectric: Null transmission, valid_ray semantics)
+    "c10_thinglass": ("c10_thinglass", {"max_depth": 8, "pcd": 8, "hetero_frequency": 0.0}, 1, True),
     "c7_constant_homodyne": ("c7_constant", {"hetero_frequency": 0.0, "tsm": "uniform", "shift": 0.0, "rr_depth": 2, "max_depth": 8}, 6, True),
 }
 # the stock path tracer (src/integrators/path.cpp) on the same scenes: the integrator element is swapped (golden_util.swap_integrator)
@@ -74,6 +76,7 @@ PATH_CASES = {
     "path_c7_constant": ("c7_constant", {}, 3, True),
     "path_c8_conductor": ("c8_conductor", {"max_depth": 6}, 1, True),
     "path_c9_dielectric": ("c9_dielectric", {"max_depth": 8}, 2, True),
+    "path_c10_thinglass": ("c10_thinglass", {"max_depth": 6}, 0, True),
 }
 # the ground-truth radial velocity integrator (src/integrators/velocity.cpp). Its value (t2 - t1) / time scales by exactly
 # 2^20 under the time scaling; golden_util.load_case undoes it.
