@@ -638,8 +638,7 @@ std::unique_ptr<FlatScene> Scene::flatten() const {
         Bsdf b = s.has_bsdf ? s.bsdf : Bsdf();   // Shape default BSDF: diffuse (src/render/shape.cpp:60-65)
         for (size_t i = 0; i < fs->bsdfs.size(); ++i) {
             const dtof_bsdf &o = fs->bsdfs[i];
-            const bool c = b.kind == DTOF_BSDF_CONDUCTOR || b.kind == DTOF_BSDF_DIELECTRIC ||
-                           b.kind == DTOF_BSDF_THINDIELECTRIC;   // the kinds that use eta / k
+            const bool c = b.kind != DTOF_BSDF_DIFFUSE;   // every other kind uses eta / k
             if (o.kind == b.kind && (o.twosided != 0) == b.twosided && o.reflectance[0] == b.reflectance[0] &&
                 o.reflectance[1] == b.reflectance[1] && o.reflectance[2] == b.reflectance[2] &&
                 (!c || (!memcmp(o.eta, b.eta, sizeof(o.eta)) && !memcmp(o.k, b.k, sizeof(o.k)))))
@@ -649,7 +648,7 @@ std::unique_ptr<FlatScene> Scene::flatten() const {
         nb.kind = b.kind;
         nb.twosided = b.twosided ? 1u : 0u;
         memcpy(nb.reflectance, b.reflectance, sizeof(nb.reflectance));
-        if (b.kind == DTOF_BSDF_CONDUCTOR || b.kind == DTOF_BSDF_DIELECTRIC || b.kind == DTOF_BSDF_THINDIELECTRIC) {
+        if (b.kind != DTOF_BSDF_DIFFUSE) {
             memcpy(nb.eta, b.eta, sizeof(nb.eta));
             memcpy(nb.k, b.k, sizeof(nb.k));
         }
@@ -947,6 +946,24 @@ struct Loader {
             }
             return b;
         }
+        if (typ == "plastic") {   // SmoothPlastic ctor, src/bsdfs/plastic.cpp:157-183
+            auto p = props(node);
+            reject_unknown(p, { "int_ior", "ext_ior", "diffuse_reflectance", "specular_reflectance", "nonlinear" }, "plastic");
+            const float int_ior = lookup_ior(p.count("int_ior") ? p["int_ior"].value : "polypropylene");
+            const float ext_ior = lookup_ior(p.count("ext_ior") ? p["ext_ior"].value : "air");
+            if (int_ior < 0.f || ext_ior < 0.f)
+                throw Error("The interior and exterior indices of refraction must be positive!");
+            Bsdf b;
+            b.kind = DTOF_BSDF_PLASTIC;
+            b.eta[0] = int_ior / ext_ior;
+            b.eta[1] = p.count("nonlinear") && parse_bool(p["nonlinear"].value) ? 1.f : 0.f;
+            b.eta[2] = 0.f;
+            for (int i = 0; i < 3; ++i) {
+                b.reflectance[i] = p.count("diffuse_reflectance") ? (float) p["diffuse_reflectance"].vec[i] : 0.5f;
+                b.k[i] = p.count("specular_reflectance") ? (float) p["specular_reflectance"].vec[i] : 1.f;
+            }
+            return b;
+        }
         if (typ == "dielectric" || typ == "thindielectric") {   // dielectric.cpp:199-228, thindielectric.cpp:104-126
             auto p = props(node);
             reject_unknown(p, { "int_ior", "ext_ior", "specular_reflectance", "specular_transmittance" }, typ.c_str());
@@ -963,7 +980,7 @@ struct Loader {
             }
             return b;
         }
-        throw Error("bsdf type '" + typ + "' is outside the hot-path scope (diffuse|conductor|dielectric|thindielectric|twosided)");
+        throw Error("bsdf type '" + typ + "' is outside the hot-path scope (diffuse|conductor|dielectric|thindielectric|plastic|twosided)");
     }
     Bsdf bsdf_or_ref(const XmlNode &node) {
         if (node.tag == "ref") {

@@ -217,9 +217,24 @@ private:
                 if (dst)
                     dst[0] = v[0], dst[1] = v[1], dst[2] = v[2];
             }
+        } else if (inner->class_()->name() == "SmoothPlastic") {          // plastic.cpp:157-208
+            b.kind = DTOF_BSDF_PLASTIC;
+            Collector c;
+            const_cast<BSDF *>(inner)->traverse(&c);
+            b.eta[0] = (float) *c.param<ScalarFloat>("eta");
+            // `nonlinear` is not a traversed parameter; the plugin prints it (to_string, plastic.cpp:368-382)
+            b.eta[1] = inner->to_string().find("nonlinear = 1") != std::string::npos ? 1.f : 0.f;
+            for (int i = 0; i < 3; ++i)
+                b.reflectance[i] = 0.5f, b.k[i] = 1.f;
+            for (auto &o : c.objects) {
+                Spectrum v = ((const Texture<Float, Spectrum> *) o.second)->eval(si);
+                float *dst = o.first == "diffuse_reflectance" ? b.reflectance : o.first == "specular_reflectance" ? b.k : nullptr;
+                if (dst)
+                    dst[0] = v[0], dst[1] = v[1], dst[2] = v[2];
+            }
         } else {
             if (inner->class_()->name() != "SmoothDiffuse")
-                Throw("BSDF \"%s\" is outside the accelerated path (diffuse | conductor | dielectric | twosided(...))", inner->class_()->name());
+                Throw("BSDF \"%s\" is outside the accelerated path (diffuse | conductor | dielectric | thindielectric | plastic | twosided(...))", inner->class_()->name());
             Spectrum r = inner->eval_diffuse_reflectance(si);            // constant RGB reflectance
             b.reflectance[0] = r[0], b.reflectance[1] = r[1], b.reflectance[2] = r[2];
         }

@@ -567,10 +567,18 @@ dtof_status launch_wavefront(dtof_ctx *ctx, const RenderArgs &A, int mode, cudaS
                                           : launch_wf_trace<MODE_BVH_GLOBAL, false>(ctx, W, trace_grid, 0, st);
                 if (s != DTOF_OK)
                     return s;
-                if (doppler)
-                    wf_shade_kernel<true><<<shade_grid, kWfShadeBlock, 0, st>>>(W);
-                else
-                    wf_shade_kernel<false><<<shade_grid, kWfShadeBlock, 0, st>>>(W);
+                // ENV: environment emitter / non-diffuse BSDFs compiled in only for the scenes that use them
+                if (A.scene.extended) {
+                    if (doppler)
+                        wf_shade_kernel<true, true><<<shade_grid, kWfShadeBlock, 0, st>>>(W);
+                    else
+                        wf_shade_kernel<false, true><<<shade_grid, kWfShadeBlock, 0, st>>>(W);
+                } else {
+                    if (doppler)
+                        wf_shade_kernel<true, false><<<shade_grid, kWfShadeBlock, 0, st>>>(W);
+                    else
+                        wf_shade_kernel<false, false><<<shade_grid, kWfShadeBlock, 0, st>>>(W);
+                }
                 ctx->launches++;
                 CU(cudaGetLastError());
                 s = mode == MODE_BVH_SMEM ? launch_wf_trace<MODE_BVH_SMEM, true>(ctx, W, trace_grid, smem, st)
@@ -760,7 +768,7 @@ dtof_status prepare_scene(dtof_ctx *ctx, const dtof_scene_desc *sc, HostScene &H
     std::vector<uint32_t> mesh_first_gid(sc->n_meshes, 0xffffffffu);
     for (uint32_t i = 0; i < sc->n_bsdfs; ++i) {
         const dtof_bsdf &b = sc->bsdfs[i];
-        if (b.kind > DTOF_BSDF_THINDIELECTRIC)
+        if (b.kind > DTOF_BSDF_PLASTIC)
             return fail(ctx, DTOF_ERR_UNSUPPORTED, "bsdf kind %u is outside the hot-path scope", b.kind);
         const bool dielectric = b.kind == DTOF_BSDF_DIELECTRIC || b.kind == DTOF_BSDF_THINDIELECTRIC;
         if (dielectric && b.twosided)
@@ -772,7 +780,28 @@ dtof_status prepare_scene(dtof_ctx *ctx, const dtof_scene_desc *sc, HostScene &H
                                 (b.kind == DTOF_BSDF_CONDUCTOR ? 4u : 0u) | (dielectric ? 8u : 0u) |
                                 (b.kind == DTOF_BSDF_THINDIELECTRIC ? 16u : 0u),
                             b.eta[0], b.eta[1], b.eta[2], 0.f, b.k[0], b.k[1], b.k[2], 0.f };
-        H.extended = H.extended || b.kind == DTOF_BSDF_CONDUCTOR || dielectric;
+        H.extended = H.extended || b.kind == DTOF_BSDF_CONDUCTOR || dielectric || b.kind == DTOF_BSDF_PLASTIC;
+        if (b.kind == DTOF_BSDF_PLASTIC) {   // SmoothPlastic::parameters_changed, plastic.cpp:193-208
+            if (!(b.eta[0] > 0.f))
+                return fail(ctx, DTOF_ERR_INVALID, "The interior and exterior indices of refraction must be positive!");
+            const float eta = b.eta[0], inv_eta = 1.f / (1.f / eta);   // fresnel_diffuse_reflectance(1 / eta): its inv_eta
+            const float e = 1.f / eta;                                  // the argument
+            float fdr;
+            if (e < 1.f) {
+                fdr = std::fmaf(0.0636f, inv_eta, std::fmaf(e, std::fmaf(e, -1.4399f, 0.7099f), 0.6681f));
+            } else {
+                const float c[6] = { 0.919317f, -3.4793f, 6.75335f, -7.80989f, 4.98554f, -1.36881f };
+                fdr = c[5];
+                for (int j = 4; j >= 0; --j)
+                    fdr = std::fmaf(inv_eta, fdr, c[j]);
+            }
+            const float d_mean = (b.reflectance[0] + b.reflectance[1] + b.reflectance[2]) * (1.f / 3.f);
+            const float s_mean = (b.k[0] + b.k[1] + b.k[2]) * (1.f / 3.f);
+            BsdfRec &r = bsdfs[i];
+            r.flags |= 2u | 32u;
+            r.eta_r = eta, r.eta_g = fdr, r.eta_b = 1.f / (eta * eta), r.pad0 = s_mean / (d_mean + s_mean);
+            r.pad1 = b.eta[1] != 0.f ? 1.f : 0.f;
+        }
     }
     uint32_t gid = 0;
     for (uint32_t g = 0; g < sc->n_instances; ++g) {

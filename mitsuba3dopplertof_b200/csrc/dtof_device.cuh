@@ -391,6 +391,12 @@ DTOF_DEV void fresnel_dielectric(float cos_theta_i, float eta, float &r, float &
     cos_theta_t = outside ? -ct : ct;   // mulsign_neg(cos_theta_t_abs, cos_theta_i)
 }
 
+DTOF_DEV float fresnel_r(float cos_theta_i, float eta) {
+    float r, ct, eit, eti;
+    fresnel_dielectric(cos_theta_i, eta, r, ct, eit, eti);
+    return r;
+}
+
 // fresnel_conductor (include/mitsuba/render/fresnel.h:93-117), one colour channel
 DTOF_DEV float fresnel_conductor(float cos_theta_i, float eta_r, float eta_i) {
     float cos2 = cos_theta_i * cos_theta_i, sin2 = 1.f - cos2, sin4 = sin2 * sin2;

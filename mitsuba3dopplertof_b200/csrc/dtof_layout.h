@@ -83,9 +83,11 @@ struct MeshRec {
 struct alignas(16) BsdfRec {
     float r, g, b;         // diffuse reflectance / conductor specular_reflectance
     uint32_t flags;        // bit0: twosided, bit1: smooth diffuse lobe present, bit2: smooth conductor (delta reflection),
-                           // bit3: smooth dielectric (delta reflection + refraction), bit4: thin dielectric (+ bit3)
-    float eta_r, eta_g, eta_b, pad0;   // conductor: complex index of refraction eta + i k; dielectric: eta_r = int_ior / ext_ior
-    float k_r, k_g, k_b, pad1;         // dielectric: specular_transmittance
+                           // bit3: smooth dielectric (delta reflection + refraction), bit4: thin dielectric (+ bit3),
+                           // bit5: smooth plastic (+ bit1: its diffuse base is a smooth lobe)
+    float eta_r, eta_g, eta_b, pad0;   // conductor: complex index of refraction eta + i k; dielectric: eta_r = int_ior / ext_ior;
+                                       // plastic: eta, fdr_int, 1 / eta^2, specular sampling weight (plastic.cpp:193-208)
+    float k_r, k_g, k_b, pad1;         // dielectric: specular_transmittance; plastic: specular_reflectance, nonlinear (0 / 1)
 };
 
 struct EmitterRec {

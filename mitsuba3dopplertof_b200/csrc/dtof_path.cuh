@@ -239,7 +239,44 @@ DTOF_DEV void shade_bounce(const DeviceScene &S, const float4 *__restrict__ I, c
     float s2x = smp.template next_1d<DOPPLER>(correlate), s2y = smp.template next_1d<DOPPLER>(correlate);
     V3 bsdf_val = v3(0, 0, 0), bsdf_weight = v3(0, 0, 0), bs_wo = v3(0, 0, 0);
     float bsdf_pdf = 0.f, bs_pdf = 0.f;                                 // zero-initialised BSDFSample3f
-    if (valid && smooth) {
+    bool sampled_delta = false;
+    if (ENV && valid && (bsdf_flags & 32u)) {                            // SmoothPlastic::eval / pdf / sample, plastic.cpp:210-345
+        const BsdfRec &br = S.bsdfs[bsdf_id];
+        const float eta = br.eta_r, fdr_int = br.eta_g, inv_eta_2 = br.eta_b, ssw = br.pad0;
+        float wi_z = si.wi.z, wo_z = wo.z;
+        if (twosided) {
+            wo_z = mulsign(wo_z, wi_z);
+            wi_z = fabsf(wi_z);
+        }
+        // diffuse_reflectance / (1 - fdr_int [* diffuse_reflectance])
+        const bool nonlinear = br.pad1 != 0.f;
+        const V3 diff = v3(fdiv(refl.x, 1.f - (nonlinear ? refl.x * fdr_int : fdr_int)), fdiv(refl.y, 1.f - (nonlinear ? refl.y * fdr_int : fdr_int)),
+                           fdiv(refl.z, 1.f - (nonlinear ? refl.z * fdr_int : fdr_int)));
+        const float f_i = fresnel_r(wi_z, eta);
+        const float prob_s0 = f_i * ssw, prob_d0 = (1.f - f_i) * (1.f - ssw);
+        if (wi_z > 0.f && wo_z > 0.f) {
+            const float f_o = fresnel_r(wo_z, eta);
+            bsdf_val = diff * (kInvPi * wo_z * inv_eta_2 * (1.f - f_i) * (1.f - f_o));
+            bsdf_pdf = kInvPi * wo_z * fdiv(prob_d0, prob_s0 + prob_d0);
+        }
+        if (wi_z > 0.f) {
+            const float prob_specular = fdiv(prob_s0, prob_s0 + prob_d0), prob_diffuse = 1.f - prob_specular;
+            if (s1 < prob_specular) {
+                bs_wo = v3(-si.wi.x, -si.wi.y, wi_z);                    // reflect(wi) of the (flipped) incident direction
+                bs_pdf = prob_specular;
+                const float value = fdiv(f_i, bs_pdf);
+                bsdf_weight = v3(value * br.k_r, value * br.k_g, value * br.k_b);
+                sampled_delta = true;
+            } else {
+                bs_wo = square_to_cosine_hemisphere(s2x, s2y);
+                bs_pdf = prob_diffuse * (kInvPi * bs_wo.z);
+                const float f_o = fresnel_r(bs_wo.z, eta);
+                bsdf_weight = diff * fdiv(inv_eta_2 * (1.f - f_i) * (1.f - f_o), prob_diffuse);
+            }
+            if (twosided)
+                bs_wo.z = mulsign(bs_wo.z, si.wi.z);
+        }
+    } else if (valid && smooth) {
         float wi_z = si.wi.z, wo_z = wo.z;
         if (twosided) {                                                 // TwoSidedBRDF, twosided.cpp:111-125,219-235
             wo_z = mulsign(wo_z, wi_z);
@@ -258,7 +295,6 @@ DTOF_DEV void shade_bounce(const DeviceScene &S, const float4 *__restrict__ I, c
                 bs_wo.z = mulsign(bs_wo.z, si.wi.z);
         }
     }
-    bool sampled_delta = false;
     if (ENV && valid && (bsdf_flags & 4u)) {                             // SmoothConductor::sample, conductor.cpp:247-300
         float wi_z = twosided ? fabsf(si.wi.z) : si.wi.z;                // TwoSidedBRDF: |wi.z| in, sign restored on wo.z
         if (wi_z > 0.f) {

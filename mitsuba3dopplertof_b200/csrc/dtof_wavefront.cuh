@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(kWfBlock, DTOF_WF_TRACE_CTAS) wf_trace_kernel(
 
 // ------------------------------------------------------------------------------------------------
 // Stage 3: one iteration of the bounce loop for every entry of the path-ray queue (full warps).
-template <bool DOPPLER>
+template <bool DOPPLER, bool ENV>
 __global__ void __launch_bounds__(kWfShadeBlock, DTOF_WF_SHADE_CTAS * (kWfBlock / kWfShadeBlock))
 wf_shade_kernel(const __grid_constant__ WfArgs A) {
     const WfBuffers &B = A.buf;
@@ -405,7 +405,7 @@ wf_shade_kernel(const __grid_constant__ WfArgs A) {
             ps.depth = meta & 0x3fffffffu;
             ps.valid_ray = (meta & 0x40000000u) != 0;
             ps.prev_bsdf_delta = (meta & 0x80000000u) != 0;
-            ps.eta = A.scene.extended ? B.eta[s] : 1.f;
+            ps.eta = ENV ? B.eta[s] : 1.f;
             ps.active = true;
             LaneSampler smp;
             const ulonglong2 g = B.rng[s];
@@ -415,12 +415,12 @@ wf_shade_kernel(const __grid_constant__ WfArgs A) {
                 smp.rng_path.state = gp.x, smp.rng_path.inc = gp.y;
             }
             smp.draws = 0;
-            shade_bounce<DOPPLER, true>(A.scene, A.scene.insts, A.p, A.mod, smp, ps, hit, h, ray_o, ray_d, ray_maxt, ray_time,
+            shade_bounce<DOPPLER, ENV>(A.scene, A.scene.insts, A.p, A.mod, smp, ps, hit, h, ray_o, ray_d, ray_maxt, ray_time,
                                   emitter_pmf, nee);
             B.rng[s] = make_ulonglong2(smp.rng.state, smp.rng.inc);
             if (DOPPLER)
                 B.rng_path[s] = make_ulonglong2(smp.rng_path.state, smp.rng_path.inc);
-            if (A.scene.extended)
+            if (ENV)
                 B.eta[s] = ps.eta;
             B.thr_len[s] = make_float4(ps.throughput.x, ps.throughput.y, ps.throughput.z, ps.path_length);
             B.res_pdf[s] = make_float4(ps.result.x, ps.result.y, ps.result.z, ps.prev_bsdf_pdf);

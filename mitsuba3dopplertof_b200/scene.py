@@ -308,7 +308,7 @@ class Scene:
             def rgb(v):
                 v = np.atleast_1d(np.asarray(v, f32))
                 return tuple(float(x) for x in ((v.tolist() * 3)[:3] if v.size == 1 else v.tolist()))
-            conductor = b.kind in (_abi.BSDF_CONDUCTOR, _abi.BSDF_DIELECTRIC, _abi.BSDF_THINDIELECTRIC)   # kinds using eta / k
+            conductor = b.kind != _abi.BSDF_DIFFUSE   # every other kind uses eta / k
             key = (b.kind, bool(b.twosided), tuple(float(f32(x)) for x in b.reflectance),
                    rgb(b.eta) if conductor else (0.0,) * 3, rgb(b.k) if conductor else (0.0,) * 3)
             if key not in bsdf_index:

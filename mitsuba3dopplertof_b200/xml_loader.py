@@ -145,6 +145,18 @@ class _Loader:
                 raise ValueError(f"conductor material '{material}' (measured spectra) is outside the hot-path scope: give eta / k")
             return Bsdf(p.get("specular_reflectance", (1.0, 1.0, 1.0)), False, _abi.BSDF_CONDUCTOR,
                         p.get("eta", (0.0, 0.0, 0.0)), p.get("k", (1.0, 1.0, 1.0)))
+        if typ == "plastic":   # SmoothPlastic ctor, src/bsdfs/plastic.cpp:157-183
+            from . import _abi
+            p = self.props(node)
+            unknown = set(p) - {"int_ior", "ext_ior", "diffuse_reflectance", "specular_reflectance", "nonlinear"}
+            if unknown:
+                raise ValueError(f"plastic: unreferenced property {sorted(unknown)}")
+            int_ior, ext_ior = lookup_ior(p.get("int_ior", "polypropylene")), lookup_ior(p.get("ext_ior", "air"))
+            if int_ior < 0 or ext_ior < 0:
+                raise ValueError("The interior and exterior indices of refraction must be positive!")
+            eta = float(np.float32(int_ior) / np.float32(ext_ior))
+            return Bsdf(p.get("diffuse_reflectance", (0.5, 0.5, 0.5)), False, _abi.BSDF_PLASTIC,
+                        (eta, 1.0 if p.get("nonlinear", False) else 0.0, 0.0), p.get("specular_reflectance", (1.0, 1.0, 1.0)))
         if typ in ("dielectric", "thindielectric"):   # dielectric.cpp:199-228, thindielectric.cpp:104-126
             from . import _abi
             p = self.props(node)
@@ -158,7 +170,7 @@ class _Loader:
             return Bsdf(p.get("specular_reflectance", (1.0, 1.0, 1.0)), False,
                         _abi.BSDF_DIELECTRIC if typ == "dielectric" else _abi.BSDF_THINDIELECTRIC, (eta, 0.0, 0.0),
                         p.get("specular_transmittance", (1.0, 1.0, 1.0)))
-        raise ValueError(f"bsdf type '{typ}' is outside the hot-path scope (diffuse|conductor|dielectric|thindielectric|twosided)")
+        raise ValueError(f"bsdf type '{typ}' is outside the hot-path scope (diffuse|conductor|dielectric|thindielectric|plastic|twosided)")
 
     def bsdf_or_ref(self, node) -> Bsdf:
         if node.tag == "ref":

@@ -429,6 +429,41 @@ inline void fresnel_dielectric(float cos_theta_i, float eta, float &r, float &co
     cos_theta_t = cos_theta_i >= 0.f ? -ct : ct; // mulsign_neg = select(v2 >= 0, -v1, v1), array_router.h:389-396
 }
 
+// fresnel_diffuse_reflectance, include/mitsuba/render/fresnel.h:328-355
+inline float fresnel_diffuse_reflectance(float eta) {
+    float inv_eta = 1.f / eta;
+    float approx_1 = fmaf(0.0636f, inv_eta, fmaf(eta, fmaf(eta, -1.4399f, 0.7099f), 0.6681f));
+    const float c[6] = { 0.919317f, -3.4793f, 6.75335f, -7.80989f, 4.98554f, -1.36881f };
+    float approx_2 = c[5];
+    for (int i = 4; i >= 0; --i)
+        approx_2 = fmaf(inv_eta, approx_2, c[i]); // dr::horner
+    return eta < 1.f ? approx_1 : approx_2;
+}
+inline float fresnel_r(float cos_theta_i, float eta) {
+    float r, ct, eit, eti;
+    fresnel_dielectric(cos_theta_i, eta, r, ct, eit, eti);
+    return r;
+}
+// constants of SmoothPlastic::parameters_changed (plastic.cpp:193-208)
+struct PlasticParams {
+    float eta, inv_eta_2, fdr_int, ssw;
+    bool nonlinear;
+    explicit PlasticParams(const dtof_bsdf &b) {
+        eta = b.eta[0];
+        nonlinear = b.eta[1] != 0.f;
+        inv_eta_2 = 1.f / (eta * eta);
+        fdr_int = fresnel_diffuse_reflectance(1.f / eta);
+        float d_mean = (b.reflectance[0] + b.reflectance[1] + b.reflectance[2]) * (1.f / 3.f);
+        float s_mean = (b.k[0] + b.k[1] + b.k[2]) * (1.f / 3.f);
+        ssw = s_mean / (d_mean + s_mean);
+    }
+    V3 diff(const dtof_bsdf &b) const { // diffuse_reflectance / (1 - fdr_int [* diffuse_reflectance])
+        V3 d = v3(b.reflectance[0], b.reflectance[1], b.reflectance[2]);
+        return nonlinear ? v3(d.x / (1.f - d.x * fdr_int), d.y / (1.f - d.y * fdr_int), d.z / (1.f - d.z * fdr_int))
+                         : v3(d.x / (1.f - fdr_int), d.y / (1.f - fdr_int), d.z / (1.f - fdr_int));
+    }
+};
+
 // fresnel_conductor, include/mitsuba/render/fresnel.h:93-117 (one colour channel)
 inline float fresnel_conductor(float cos_theta_i, float eta_r, float eta_i) {
     float cos2 = cos_theta_i * cos_theta_i, sin2 = 1.f - cos2, sin4 = sin2 * sin2;
@@ -982,7 +1017,7 @@ PathResult trace_path(const dtof_oracle_scene &sc, const dtof_params &P, const M
         // ---- emitter sampling (:187-202); the 2D sample is ALWAYS drawn (Appendix A.6e)
         float e1 = smp.next_1d(correlate), e2 = smp.next_1d(correlate);
         const dtof_bsdf *bsdf = valid ? &sc.bsdfs[sc.meshes[si.mesh].bsdf] : nullptr;
-        bool smooth = bsdf && bsdf->kind == DTOF_BSDF_DIFFUSE;
+        bool smooth = bsdf && (bsdf->kind == DTOF_BSDF_DIFFUSE || bsdf->kind == DTOF_BSDF_PLASTIC); // BSDFFlags::Smooth
         bool active_em = active_next && smooth;
         DirSample ds{};
         V3 em_weight = v3(0, 0, 0), wo = v3(0, 0, 0);
@@ -1065,7 +1100,42 @@ PathResult trace_path(const dtof_oracle_scene &sc, const dtof_params &P, const M
 
         V3 bsdf_val = v3(0, 0, 0), bsdf_weight = v3(0, 0, 0), bs_wo = v3(0, 0, 0);
         float bsdf_pdf = 0.f, bs_pdf = 0.f, bs_eta = 0.f; // zero-initialised BSDFSample3f when nothing is sampled
-        if (valid && smooth) {
+        bool sampled_delta = false;
+        if (valid && bsdf->kind == DTOF_BSDF_PLASTIC) { // SmoothPlastic::eval / pdf / sample, plastic.cpp:210-345
+            const PlasticParams pp(*bsdf);
+            float wi_z = si.wi.z, wo_z = wo.z;
+            if (bsdf->twosided) {
+                wo_z = mulsign(wo_z, wi_z);
+                wi_z = fabsf(wi_z);
+            }
+            const float f_i = fresnel_r(wi_z, pp.eta);
+            const float prob_s0 = f_i * pp.ssw, prob_d0 = (1.f - f_i) * (1.f - pp.ssw);
+            if (wi_z > 0.f && wo_z > 0.f) {
+                float f_o = fresnel_r(wo_z, pp.eta);
+                float scale = kInvPi * wo_z * pp.inv_eta_2 * (1.f - f_i) * (1.f - f_o);
+                bsdf_val = pp.diff(*bsdf) * scale;
+                bsdf_pdf = kInvPi * wo_z * (prob_d0 / (prob_s0 + prob_d0));
+            }
+            if (wi_z > 0.f) {
+                float prob_specular = prob_s0 / (prob_s0 + prob_d0), prob_diffuse = 1.f - prob_specular;
+                bs_eta = 1.f;
+                if (s1 < prob_specular) {
+                    bs_wo = v3(-si.wi.x, -si.wi.y, wi_z); // reflect(wi) of the (flipped) incident direction
+                    bs_pdf = prob_specular;
+                    float value = f_i / bs_pdf;
+                    bsdf_weight = v3(value * bsdf->k[0], value * bsdf->k[1], value * bsdf->k[2]);
+                    sampled_delta = true;
+                } else {
+                    bs_wo = square_to_cosine_hemisphere(s2x, s2y);
+                    bs_pdf = prob_diffuse * (kInvPi * bs_wo.z);
+                    float f_o = fresnel_r(bs_wo.z, pp.eta);
+                    float scale = pp.inv_eta_2 * (1.f - f_i) * (1.f - f_o) / prob_diffuse;
+                    bsdf_weight = pp.diff(*bsdf) * scale;
+                }
+                if (bsdf->twosided)
+                    bs_wo.z = mulsign(bs_wo.z, si.wi.z);
+            }
+        } else if (valid && smooth) {
             V3 refl = v3(bsdf->reflectance[0], bsdf->reflectance[1], bsdf->reflectance[2]);
             float wi_z = si.wi.z, wo_z = wo.z;
             if (bsdf->twosided) { // TwoSidedBRDF, twosided.cpp:111-125,219-235 (brdf[0]==brdf[1])
@@ -1089,7 +1159,6 @@ PathResult trace_path(const dtof_oracle_scene &sc, const dtof_params &P, const M
             }
         }
 
-        bool sampled_delta = false;
         if (valid && bsdf->kind == DTOF_BSDF_CONDUCTOR) { // SmoothConductor::sample, conductor.cpp:247-300
             // TwoSidedBRDF (twosided.cpp:124-127): |wi.z| goes in, the sign of wi.z is restored on wo.z
             float wi_z = bsdf->twosided ? fabsf(si.wi.z) : si.wi.z;

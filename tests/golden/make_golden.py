@@ -64,6 +64,9 @@ CASES = {
     "c9_dielectric_homodyne": ("c9_dielectric", {"hetero_frequency": 0.0, "max_depth": 12, "rr_depth": 3, "pcd": 2}, 5, True),
     # c9 + a tinted thin glass pane (thindielectric: Null transmission, valid_ray semantics)
     "c10_thinglass": ("c10_thinglass", {"max_depth": 8, "pcd": 8, "hetero_frequency": 0.0}, 1, True),
+    # smooth plastic: the floor (nonlinear, tinted coat, one-sided) and the short box (two-sided, int_ior 1.9)
+    "c11_plastic": ("c11_plastic", {"max_depth": 6, "pcd": 6}, 0, True),
+    "c11_plastic_homodyne": ("c11_plastic", {"hetero_frequency": 0.0, "max_depth": 8, "rr_depth": 3}, 3, True),
     "c7_constant_homodyne": ("c7_constant", {"hetero_frequency": 0.0, "tsm": "uniform", "shift": 0.0, "rr_depth": 2, "max_depth": 8}, 6, True),
 }
 # the stock path tracer (src/integrators/path.cpp) on the same scenes: the integrator element is swapped (golden_util.swap_integrator)
@@ -77,6 +80,7 @@ PATH_CASES = {
     "path_c8_conductor": ("c8_conductor", {"max_depth": 6}, 1, True),
     "path_c9_dielectric": ("c9_dielectric", {"max_depth": 8}, 2, True),
     "path_c10_thinglass": ("c10_thinglass", {"max_depth": 6}, 0, True),
+    "path_c11_plastic": ("c11_plastic", {"max_depth": 6}, 4, True),
 }
 # the ground-truth radial velocity integrator (src/integrators/velocity.cpp). Its value (t2 - t1) / time scales by exactly
 # 2^20 under the time scaling; golden_util.load_case undoes it.

@@ -71,6 +71,7 @@ def test_cuda_full_waveform_mode_matches_oracle(ctx, name):
     ("c8_conductor", dict(resx=40, resy=40, spp=32, hetero_frequency=0.0, max_depth=8)),  # mirrors: delta BSDF samples
     ("c9_dielectric", dict(resx=40, resy=40, spp=32, hetero_frequency=0.0, max_depth=10, rr_depth=4)),  # glass: eta tracking
     ("c10_thinglass", dict(resx=40, resy=40, spp=32, hetero_frequency=0.0, max_depth=8)),  # thin pane: Null transmission
+    ("c11_plastic", dict(resx=40, resy=40, spp=32, hetero_frequency=0.0, max_depth=6)),  # plastic: smooth + delta lobe
 ])
 def test_cuda_film_matches_oracle(ctx, scene_name, kw):
     import oracle_lib
