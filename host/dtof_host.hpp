@@ -76,6 +76,8 @@ struct Bsdf {
     bool twosided = false;
     uint32_t kind = DTOF_BSDF_DIFFUSE;
     float eta[3] = { 0.f, 0.f, 0.f }, k[3] = { 1.f, 1.f, 1.f };
+    float alpha[2] = { 0.f, 0.f };   // roughconductor: alpha_u, alpha_v
+    uint32_t distribution = 0;       // roughconductor: 0 beckmann, 1 ggx
 };
 
 struct Shape {

@@ -641,13 +641,15 @@ std::unique_ptr<FlatScene> Scene::flatten() const {
             const bool c = b.kind != DTOF_BSDF_DIFFUSE;   // every other kind uses eta / k
             if (o.kind == b.kind && (o.twosided != 0) == b.twosided && o.reflectance[0] == b.reflectance[0] &&
                 o.reflectance[1] == b.reflectance[1] && o.reflectance[2] == b.reflectance[2] &&
-                (!c || (!memcmp(o.eta, b.eta, sizeof(o.eta)) && !memcmp(o.k, b.k, sizeof(o.k)))))
+                (!c || (!memcmp(o.eta, b.eta, sizeof(o.eta)) && !memcmp(o.k, b.k, sizeof(o.k)))) &&
+                o.alpha[0] == b.alpha[0] && o.alpha[1] == b.alpha[1] && o.distribution == b.distribution)
                 return (uint32_t) i;
         }
         dtof_bsdf nb{};
         nb.kind = b.kind;
         nb.twosided = b.twosided ? 1u : 0u;
         memcpy(nb.reflectance, b.reflectance, sizeof(nb.reflectance));
+        nb.alpha[0] = b.alpha[0], nb.alpha[1] = b.alpha[1], nb.distribution = b.distribution;
         if (b.kind != DTOF_BSDF_DIFFUSE) {
             memcpy(nb.eta, b.eta, sizeof(nb.eta));
             memcpy(nb.k, b.k, sizeof(nb.k));
@@ -946,6 +948,40 @@ struct Loader {
             }
             return b;
         }
+        if (typ == "roughconductor") {   // RoughConductor ctor, src/bsdfs/roughconductor.cpp:160-211
+            auto p = props(node);
+            reject_unknown(p, { "specular_reflectance", "material", "eta", "k", "distribution", "alpha", "alpha_u", "alpha_v", "sample_visible" },
+                           "roughconductor");
+            const std::string material = p.count("material") ? p["material"].value : "none";
+            if (material != "none") {
+                if (p.count("eta"))
+                    throw Error("Should specify either (eta, k) or material, not both.");
+                throw Error("conductor material '" + material + "' (measured spectra) is outside the hot-path scope: give eta / k");
+            }
+            const std::string distr = p.count("distribution") ? p["distribution"].value : "beckmann";
+            if (distr != "beckmann" && distr != "ggx")
+                throw Error("Specified an invalid distribution \"" + distr + "\", must be \"beckmann\" or \"ggx\"!");
+            if (p.count("sample_visible") && !parse_bool(p["sample_visible"].value))
+                throw Error("roughconductor with sample_visible=false is outside the hot-path scope");
+            Bsdf b;
+            b.kind = DTOF_BSDF_ROUGHCONDUCTOR;
+            b.distribution = distr == "ggx" ? 1u : 0u;
+            if (p.count("alpha_u") || p.count("alpha_v")) {
+                if (!p.count("alpha_u") || !p.count("alpha_v"))
+                    throw Error("Microfacet model: both 'alpha_u' and 'alpha_v' must be specified.");
+                if (p.count("alpha"))
+                    throw Error("Microfacet model: please specifyeither 'alpha' or 'alpha_u'/'alpha_v'.");
+                b.alpha[0] = (float) parse_float(p["alpha_u"].value), b.alpha[1] = (float) parse_float(p["alpha_v"].value);
+            } else {
+                b.alpha[0] = b.alpha[1] = p.count("alpha") ? (float) parse_float(p["alpha"].value) : 0.1f;
+            }
+            for (int i = 0; i < 3; ++i) {
+                b.reflectance[i] = p.count("specular_reflectance") ? (float) p["specular_reflectance"].vec[i] : 1.f;
+                b.eta[i] = p.count("eta") ? (float) p["eta"].vec[i] : 0.f;
+                b.k[i] = p.count("k") ? (float) p["k"].vec[i] : 1.f;
+            }
+            return b;
+        }
         if (typ == "plastic") {   // SmoothPlastic ctor, src/bsdfs/plastic.cpp:157-183
             auto p = props(node);
             reject_unknown(p, { "int_ior", "ext_ior", "diffuse_reflectance", "specular_reflectance", "nonlinear" }, "plastic");
@@ -980,7 +1016,7 @@ struct Loader {
             }
             return b;
         }
-        throw Error("bsdf type '" + typ + "' is outside the hot-path scope (diffuse|conductor|dielectric|thindielectric|plastic|twosided)");
+        throw Error("bsdf type '" + typ + "' is outside the hot-path scope (diffuse|conductor|roughconductor|dielectric|thindielectric|plastic|twosided)");
     }
     Bsdf bsdf_or_ref(const XmlNode &node) {
         if (node.tag == "ref") {

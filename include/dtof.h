@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define DTOF_ABI_VERSION 4
+#define DTOF_ABI_VERSION 5
 
 typedef struct dtof_ctx dtof_ctx;
 
@@ -86,7 +86,7 @@ typedef enum dtof_rfilter { DTOF_RFILTER_BOX = 0, DTOF_RFILTER_TENT = 1, DTOF_RF
 typedef enum dtof_shape_kind { DTOF_SHAPE_MESH = 0, DTOF_SHAPE_RECTANGLE = 1 } dtof_shape_kind;
 typedef enum dtof_bsdf_kind {
     DTOF_BSDF_DIFFUSE = 0, DTOF_BSDF_NULL_BLACK = 1, DTOF_BSDF_CONDUCTOR = 2, DTOF_BSDF_DIELECTRIC = 3,
-    DTOF_BSDF_THINDIELECTRIC = 4, DTOF_BSDF_PLASTIC = 5
+    DTOF_BSDF_THINDIELECTRIC = 4, DTOF_BSDF_PLASTIC = 5, DTOF_BSDF_ROUGHCONDUCTOR = 6
 } dtof_bsdf_kind;
 typedef enum dtof_emitter_kind { DTOF_EMITTER_POINT = 0, DTOF_EMITTER_AREA = 1, DTOF_EMITTER_CONSTANT = 2 } dtof_emitter_kind;
 
@@ -128,8 +128,10 @@ typedef struct dtof_instance {
  * material "none" is eta = 0, k = 1) or SmoothDielectric (src/bsdfs/dielectric.cpp: Fresnel-weighted choice between
  * specular reflection and refraction, never two-sided) or ThinDielectric (src/bsdfs/thindielectric.cpp: a thin slab,
  * r' = 2r / (1 + r), the transmitted ray goes straight on as a Null interaction; same fields as DIELECTRIC) or
- * SmoothPlastic (src/bsdfs/plastic.cpp: a diffuse base under a smooth dielectric coat); diffuse, conductor and plastic
- * optionally wrapped by TwoSidedBRDF (src/bsdfs/twosided.cpp). */
+ * SmoothPlastic (src/bsdfs/plastic.cpp: a diffuse base under a smooth dielectric coat) or RoughConductor
+ * (src/bsdfs/roughconductor.cpp: Beckmann or GGX microfacets with visible-normal sampling,
+ * include/mitsuba/render/microfacet.h); diffuse, conductor, plastic and roughconductor optionally wrapped by
+ * TwoSidedBRDF (src/bsdfs/twosided.cpp). */
 typedef struct dtof_bsdf {
     uint32_t kind;            /* dtof_bsdf_kind */
     uint32_t twosided;
@@ -138,6 +140,9 @@ typedef struct dtof_bsdf {
                                * int_ior / ext_ior; PLASTIC: eta[1] != 0 = `nonlinear` */
     float k[3];               /* CONDUCTOR: extinction coefficient (RGB); DIELECTRIC: specular_transmittance;
                                * PLASTIC: specular_reflectance */
+    float alpha[2];           /* ROUGHCONDUCTOR: alpha_u, alpha_v (reflectance / eta / k as for CONDUCTOR) */
+    uint32_t distribution;    /* ROUGHCONDUCTOR: 0 = beckmann, 1 = ggx (MicrofacetType) */
+    uint32_t reserved;        /* 0 */
 } dtof_bsdf;
 
 /* PointLight (src/emitters/point.cpp), AreaLight (src/emitters/area.cpp) on mesh `mesh`, or the constant environment

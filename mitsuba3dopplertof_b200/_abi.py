@@ -8,14 +8,15 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # enums (include/dtof.h)
 TIME_UNIFORM, TIME_STRATIFIED, TIME_ANTITHETIC, TIME_ANTITHETIC_MIRROR = range(4)
 WAVE_SINUSOIDAL, WAVE_RECTANGULAR, WAVE_TRIANGULAR, WAVE_TRAPEZOIDAL = range(4)
 RFILTER_BOX, RFILTER_TENT, RFILTER_GAUSSIAN = range(3)
 SHAPE_MESH, SHAPE_RECTANGLE = range(2)
-BSDF_DIFFUSE, BSDF_NULL_BLACK, BSDF_CONDUCTOR, BSDF_DIELECTRIC, BSDF_THINDIELECTRIC, BSDF_PLASTIC = range(6)
+BSDF_DIFFUSE, BSDF_NULL_BLACK, BSDF_CONDUCTOR, BSDF_DIELECTRIC, BSDF_THINDIELECTRIC, BSDF_PLASTIC, \
+    BSDF_ROUGHCONDUCTOR = range(7)
 EMITTER_POINT, EMITTER_AREA, EMITTER_CONSTANT = range(3)
 INTEGRATOR_DOPPLERTOFPATH, INTEGRATOR_VELOCITY, INTEGRATOR_PATH = range(3)
 
@@ -44,7 +45,8 @@ class Instance(C.Structure):
 
 class Bsdf(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("twosided", C.c_uint32), ("reflectance", C.c_float * 3),
-                ("eta", C.c_float * 3), ("k", C.c_float * 3)]
+                ("eta", C.c_float * 3), ("k", C.c_float * 3), ("alpha", C.c_float * 2), ("distribution", C.c_uint32),
+                ("reserved", C.c_uint32)]
 
 
 class Emitter(C.Structure):

@@ -391,6 +391,108 @@ DTOF_DEV void fresnel_dielectric(float cos_theta_i, float eta, float &r, float &
     cos_theta_t = outside ? -ct : ct;   // mulsign_neg(cos_theta_t_abs, cos_theta_i)
 }
 
+// ---- MicrofacetDistribution with visible-normal sampling (include/mitsuba/render/microfacet.h:185-428) -------------
+// dr::erfinv (ext/drjit/include/drjit/math.h:1527-1550, after M. Giles)
+DTOF_DEV float dr_erfinv(float x) {
+    float w = -logf((1.f - x) * (1.f + x));
+    float w1 = w - 2.5f, w2 = fsqrt(w) - 3.f;
+    float p1 = 2.81022636e-08f, p2 = -0.000200214257f;
+    p1 = fmaf(p1, w1, 3.43273939e-07f), p2 = fmaf(p2, w2, 0.000100950558f);
+    p1 = fmaf(p1, w1, -3.5233877e-06f), p2 = fmaf(p2, w2, 0.00134934322f);
+    p1 = fmaf(p1, w1, -4.39150654e-06f), p2 = fmaf(p2, w2, -0.00367342844f);
+    p1 = fmaf(p1, w1, 0.00021858087f), p2 = fmaf(p2, w2, 0.00573950773f);
+    p1 = fmaf(p1, w1, -0.00125372503f), p2 = fmaf(p2, w2, -0.0076224613f);
+    p1 = fmaf(p1, w1, -0.00417768164f), p2 = fmaf(p2, w2, 0.00943887047f);
+    p1 = fmaf(p1, w1, 0.246640727f), p2 = fmaf(p2, w2, 1.00167406f);
+    p1 = fmaf(p1, w1, 1.50140941f), p2 = fmaf(p2, w2, 2.83297682f);
+    return (w < 5.f ? p1 : p2) * x;
+}
+struct Microfacet {
+    bool ggx;
+    float au, av;
+    DTOF_DEV float eval(V3 m) const {   // :185-210
+        float alpha_uv = au * av, cos_theta = m.z, cos_theta_2 = cos_theta * cos_theta, result;
+        float ex = fdiv(m.x, au), ey = fdiv(m.y, av);
+        if (!ggx) {
+            result = fdiv(expf(-fdiv(ex * ex + ey * ey, cos_theta_2)), kPi * alpha_uv * (cos_theta_2 * cos_theta_2));
+        } else {
+            float q = ex * ex + ey * ey + m.z * m.z;
+            result = frcp(kPi * alpha_uv * (q * q));
+        }
+        return result * cos_theta > 1e-20f ? result : 0.f;
+    }
+    DTOF_DEV float smith_g1(V3 v, V3 m) const {   // :341-365
+        float ax = au * v.x, ay = av * v.y;
+        float xy_alpha_2 = ax * ax + ay * ay, tan_theta_alpha_2 = fdiv(xy_alpha_2, v.z * v.z), result;
+        if (!ggx) {
+            float a = frsqrt(tan_theta_alpha_2), a_sqr = a * a;
+            result = a >= 1.6f ? 1.f : fdiv(3.535f * a + 2.181f * a_sqr, 1.f + 2.276f * a + 2.577f * a_sqr);
+        } else {
+            result = fdiv(2.f, 1.f + fsqrt(1.f + tan_theta_alpha_2));
+        }
+        if (xy_alpha_2 == 0.f)
+            result = 1.f;
+        if (dot3(v, m) * v.z <= 0.f)
+            result = 0.f;
+        return result;
+    }
+    DTOF_DEV void sample_visible_11(float cos_theta_i, float sx, float sy, float &slope_x, float &slope_y) const {   // :368-418
+        if (!ggx) {
+            const float inv_sqrt_pi = 0.56418958354775628695f;
+            float tan_theta_i = fdiv(fsqrt(fmaxf(fmaf(-cos_theta_i, cos_theta_i, 1.f), 0.f)), cos_theta_i);
+            float cot_theta_i = frcp(tan_theta_i);
+            float maxval = erff(cot_theta_i);
+            sx = fmaxf(fminf(sx, 1.f - 1e-6f), 1e-6f);
+            sy = fmaxf(fminf(sy, 1.f - 1e-6f), 1e-6f);
+            float x = maxval - (maxval + 1.f) * erff(fsqrt(-logf(sx)));
+            sx *= 1.f + maxval + inv_sqrt_pi * tan_theta_i * expf(-(cot_theta_i * cot_theta_i));
+#pragma unroll 1
+            for (int i = 0; i < 3; ++i) {   // three Newton iterations
+                float slope = dr_erfinv(x);
+                float value = 1.f + x + inv_sqrt_pi * tan_theta_i * expf(-(slope * slope)) - sx;
+                float derivative = 1.f - slope * tan_theta_i;
+                x -= fdiv(value, derivative);
+            }
+            slope_x = dr_erfinv(x);
+            slope_y = dr_erfinv(fmaf(2.f, sy, -1.f));
+        } else {
+            // warp::square_to_uniform_disk_concentric (warp.h:54-89), as in square_to_cosine_hemisphere below
+            float x0 = fmaf(2.f, sx, -1.f), y0 = fmaf(2.f, sy, -1.f);
+            bool is_zero = x0 == 0.f && y0 == 0.f, q13 = fabsf(x0) < fabsf(y0);
+            float r = q13 ? y0 : x0, rp = q13 ? x0 : y0;
+            float phi = fdiv(0.25f * kPi * rp, r);
+            if (q13)
+                phi = 0.5f * kPi - phi;
+            if (is_zero)
+                phi = 0.f;
+            float s, c;
+            dr_sincos(phi, s, c);
+            float px = r * c, py = r * s;
+            float t = 0.5f * (1.f + cos_theta_i);
+            float a = fsqrt(fmaxf(1.f - px * px, 0.f));
+            py = fmaf(py, t, fmaf(-a, t, a));   // dr::lerp(a, py, t)
+            float z = fsqrt(fmaxf(1.f - (px * px + py * py), 0.f));
+            float sin_theta_i = fsqrt(fmaxf(1.f - cos_theta_i * cos_theta_i, 0.f));
+            float norm = frcp(fmaf(sin_theta_i, py, cos_theta_i * z));
+            slope_x = fmaf(cos_theta_i, py, -(sin_theta_i * z)) * norm;
+            slope_y = px * norm;
+        }
+    }
+    DTOF_DEV V3 sample(V3 wi, float sx, float sy, float &pdf) const {   // :296-326
+        V3 wi_p = normalize3(v3(au * wi.x, av * wi.y, wi.z));
+        float sin_theta_2 = fmaf(wi_p.x, wi_p.x, wi_p.y * wi_p.y), inv = frsqrt(sin_theta_2);
+        float sin_phi = fminf(fmaxf(wi_p.y * inv, -1.f), 1.f), cos_phi = fminf(fmaxf(wi_p.x * inv, -1.f), 1.f);
+        if (fabsf(sin_theta_2) <= 4.f * 5.9604644775390625e-08f)
+            sin_phi = 0.f, cos_phi = 1.f;
+        float slx, sly;
+        sample_visible_11(wi_p.z, sx, sy, slx, sly);
+        float rx = fmaf(cos_phi, slx, -(sin_phi * sly)) * au, ry = fmaf(sin_phi, slx, cos_phi * sly) * av;
+        V3 m = normalize3(v3(-rx, -ry, 1.f));
+        pdf = fdiv(eval(m) * smith_g1(wi, m) * fabsf(dot3(wi, m)), wi.z);
+        return m;
+    }
+};
+
 DTOF_DEV float fresnel_r(float cos_theta_i, float eta) {
     float r, ct, eit, eti;
     fresnel_dielectric(cos_theta_i, eta, r, ct, eit, eti);

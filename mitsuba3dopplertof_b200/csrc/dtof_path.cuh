@@ -240,7 +240,41 @@ DTOF_DEV void shade_bounce(const DeviceScene &S, const float4 *__restrict__ I, c
     V3 bsdf_val = v3(0, 0, 0), bsdf_weight = v3(0, 0, 0), bs_wo = v3(0, 0, 0);
     float bsdf_pdf = 0.f, bs_pdf = 0.f;                                 // zero-initialised BSDFSample3f
     bool sampled_delta = false;
-    if (ENV && valid && (bsdf_flags & 32u)) {                            // SmoothPlastic::eval / pdf / sample, plastic.cpp:210-345
+    if (ENV && valid && (bsdf_flags & 64u)) {                            // RoughConductor::eval / pdf / sample, roughconductor.cpp:226-390
+        const BsdfRec &br = S.bsdfs[bsdf_id];
+        Microfacet distr;
+        distr.ggx = (bsdf_flags & 128u) != 0, distr.au = br.pad0, distr.av = br.pad1;
+        V3 wi = si.wi, wo_l = wo;
+        if (twosided) {
+            wo_l.z = mulsign(wo_l.z, wi.z);
+            wi.z = fabsf(wi.z);
+        }
+        if (wi.z > 0.f && wo_l.z > 0.f) {
+            const V3 H = normalize3(wo_l + wi);
+            const float D = distr.eval(H), g1_i = distr.smith_g1(wi, H), c = dot3(wi, H);
+            if (D != 0.f) {
+                const float result = fdiv(D * g1_i * distr.smith_g1(wo_l, H), 4.f * wi.z);
+                bsdf_val = v3(fresnel_conductor(c, br.eta_r, br.k_r) * (result * refl.x), fresnel_conductor(c, br.eta_g, br.k_g) * (result * refl.y),
+                              fresnel_conductor(c, br.eta_b, br.k_b) * (result * refl.z));
+            }
+            if (c > 0.f && dot3(wo_l, H) > 0.f)
+                bsdf_pdf = fdiv(D * g1_i, 4.f * wi.z);
+        }
+        if (wi.z > 0.f) {
+            float pdf_m;
+            const V3 m = distr.sample(wi, s2x, s2y, pdf_m);
+            const float dwm = dot3(wi, m);
+            bs_wo = v3(fmaf(2.f * dwm, m.x, -wi.x), fmaf(2.f * dwm, m.y, -wi.y), fmaf(2.f * dwm, m.z, -wi.z));   // reflect(wi, m)
+            const bool ok = pdf_m != 0.f && bs_wo.z > 0.f;
+            const float weight = distr.smith_g1(bs_wo, m);
+            bs_pdf = fdiv(pdf_m, 4.f * dot3(bs_wo, m));
+            if (ok)
+                bsdf_weight = v3(fresnel_conductor(dwm, br.eta_r, br.k_r) * (weight * refl.x), fresnel_conductor(dwm, br.eta_g, br.k_g) * (weight * refl.y),
+                                 fresnel_conductor(dwm, br.eta_b, br.k_b) * (weight * refl.z));
+            if (twosided)
+                bs_wo.z = mulsign(bs_wo.z, si.wi.z);
+        }
+    } else if (ENV && valid && (bsdf_flags & 32u)) {                            // SmoothPlastic::eval / pdf / sample, plastic.cpp:210-345
         const BsdfRec &br = S.bsdfs[bsdf_id];
         const float eta = br.eta_r, fdr_int = br.eta_g, inv_eta_2 = br.eta_b, ssw = br.pad0;
         float wi_z = si.wi.z, wo_z = wo.z;

@@ -42,6 +42,8 @@ class Bsdf:
     kind: int = _abi.BSDF_DIFFUSE
     eta: Sequence[float] = (0.0, 0.0, 0.0)
     k: Sequence[float] = (1.0, 1.0, 1.0)
+    alpha: Sequence[float] = (0.0, 0.0)          # roughconductor: alpha_u, alpha_v
+    distribution: int = 0                        # roughconductor: 0 beckmann, 1 ggx
 
 
 @dataclass
@@ -310,11 +312,12 @@ class Scene:
                 return tuple(float(x) for x in ((v.tolist() * 3)[:3] if v.size == 1 else v.tolist()))
             conductor = b.kind != _abi.BSDF_DIFFUSE   # every other kind uses eta / k
             key = (b.kind, bool(b.twosided), tuple(float(f32(x)) for x in b.reflectance),
-                   rgb(b.eta) if conductor else (0.0,) * 3, rgb(b.k) if conductor else (0.0,) * 3)
+                   rgb(b.eta) if conductor else (0.0,) * 3, rgb(b.k) if conductor else (0.0,) * 3,
+                   (float(f32(b.alpha[0])), float(f32(b.alpha[1]))), int(b.distribution))
             if key not in bsdf_index:
                 bsdf_index[key] = len(bsdfs)
                 bsdfs.append(_abi.Bsdf(b.kind, int(b.twosided), (C.c_float * 3)(*key[2]), (C.c_float * 3)(*key[3]),
-                                       (C.c_float * 3)(*key[4])))
+                                       (C.c_float * 3)(*key[4]), (C.c_float * 2)(*key[5]), key[6], 0))
             return bsdf_index[key]
 
         meshes: List[_FlatMesh] = []

@@ -125,7 +125,7 @@ class _Loader:
             from . import _abi
             if b.kind in (_abi.BSDF_DIELECTRIC, _abi.BSDF_THINDIELECTRIC):   # twosided.cpp:102-103
                 raise ValueError("Only materials without a transmission component can be nested!")
-            return Bsdf(b.reflectance, True, b.kind, b.eta, b.k)
+            return Bsdf(b.reflectance, True, b.kind, b.eta, b.k, b.alpha, b.distribution)
         if typ == "diffuse":
             p = self.props(node)
             unknown = set(p) - {"reflectance"}
@@ -145,6 +145,33 @@ class _Loader:
                 raise ValueError(f"conductor material '{material}' (measured spectra) is outside the hot-path scope: give eta / k")
             return Bsdf(p.get("specular_reflectance", (1.0, 1.0, 1.0)), False, _abi.BSDF_CONDUCTOR,
                         p.get("eta", (0.0, 0.0, 0.0)), p.get("k", (1.0, 1.0, 1.0)))
+        if typ == "roughconductor":   # RoughConductor ctor, src/bsdfs/roughconductor.cpp:160-211
+            from . import _abi
+            p = self.props(node)
+            unknown = set(p) - {"specular_reflectance", "material", "eta", "k", "distribution", "alpha", "alpha_u", "alpha_v",
+                                "sample_visible"}
+            if unknown:
+                raise ValueError(f"roughconductor: unreferenced property {sorted(unknown)}")
+            material = p.get("material", "none")
+            if material != "none":
+                if "eta" in p:
+                    raise ValueError("Should specify either (eta, k) or material, not both.")
+                raise ValueError(f"conductor material '{material}' (measured spectra) is outside the hot-path scope: give eta / k")
+            distr = p.get("distribution", "beckmann")
+            if distr not in ("beckmann", "ggx"):
+                raise ValueError(f'Specified an invalid distribution "{distr}", must be "beckmann" or "ggx"!')
+            if not p.get("sample_visible", True):
+                raise ValueError("roughconductor with sample_visible=false is outside the hot-path scope")
+            if "alpha_u" in p or "alpha_v" in p:
+                if "alpha_u" not in p or "alpha_v" not in p:
+                    raise ValueError("Microfacet model: both 'alpha_u' and 'alpha_v' must be specified.")
+                if "alpha" in p:
+                    raise ValueError("Microfacet model: please specifyeither 'alpha' or 'alpha_u'/'alpha_v'.")
+                alpha = (float(p["alpha_u"]), float(p["alpha_v"]))
+            else:
+                alpha = (float(p.get("alpha", 0.1)),) * 2
+            return Bsdf(p.get("specular_reflectance", (1.0, 1.0, 1.0)), False, _abi.BSDF_ROUGHCONDUCTOR,
+                        p.get("eta", (0.0, 0.0, 0.0)), p.get("k", (1.0, 1.0, 1.0)), alpha, 1 if distr == "ggx" else 0)
         if typ == "plastic":   # SmoothPlastic ctor, src/bsdfs/plastic.cpp:157-183
             from . import _abi
             p = self.props(node)
@@ -170,7 +197,7 @@ class _Loader:
             return Bsdf(p.get("specular_reflectance", (1.0, 1.0, 1.0)), False,
                         _abi.BSDF_DIELECTRIC if typ == "dielectric" else _abi.BSDF_THINDIELECTRIC, (eta, 0.0, 0.0),
                         p.get("specular_transmittance", (1.0, 1.0, 1.0)))
-        raise ValueError(f"bsdf type '{typ}' is outside the hot-path scope (diffuse|conductor|dielectric|thindielectric|plastic|twosided)")
+        raise ValueError(f"bsdf type '{typ}' is outside the hot-path scope (diffuse|conductor|roughconductor|dielectric|thindielectric|plastic|twosided)")
 
     def bsdf_or_ref(self, node) -> Bsdf:
         if node.tag == "ref":

@@ -429,6 +429,111 @@ inline void fresnel_dielectric(float cos_theta_i, float eta, float &r, float &co
     cos_theta_t = cos_theta_i >= 0.f ? -ct : ct; // mulsign_neg = select(v2 >= 0, -v1, v1), array_router.h:389-396
 }
 
+// ---- MicrofacetDistribution with visible-normal sampling, include/mitsuba/render/microfacet.h:185-428 -------------
+// dr::erfinv (ext/drjit/include/drjit/math.h:1527-1550, after M. Giles)
+inline float dr_erfinv(float x) {
+    float w = -logf((1.f - x) * (1.f + x));
+    float w1 = w - 2.5f, w2 = sqrtf(w) - 3.f;
+    const float a[9] = { 1.50140941f, 0.246640727f, -0.00417768164f, -0.00125372503f, 0.00021858087f, -4.39150654e-06f,
+                         -3.5233877e-06f, 3.43273939e-07f, 2.81022636e-08f };
+    const float b[9] = { 2.83297682f, 1.00167406f, 0.00943887047f, -0.0076224613f, 0.00573950773f, -0.00367342844f,
+                         0.00134934322f, 0.000100950558f, -0.000200214257f };
+    float p1 = a[8], p2 = b[8];
+    for (int i = 7; i >= 0; --i) {
+        p1 = fmaf(p1, w1, a[i]);
+        p2 = fmaf(p2, w2, b[i]);
+    }
+    return (w < 5.f ? p1 : p2) * x;
+}
+struct Microfacet {
+    bool ggx;
+    float au, av;
+    Microfacet(bool ggx_, float au_, float av_) : ggx(ggx_), au(std::max(au_, 1e-4f)), av(std::max(av_, 1e-4f)) {}
+    static float sqr(float x) { return x * x; }
+    float eval(V3 m) const { // :185-210
+        float alpha_uv = au * av, cos_theta = m.z, cos_theta_2 = cos_theta * cos_theta, result;
+        const float pi = 3.14159265358979323846f;
+        if (!ggx)
+            result = expf(-(sqr(m.x / au) + sqr(m.y / av)) / cos_theta_2) / (pi * alpha_uv * sqr(cos_theta_2));
+        else
+            result = 1.f / (pi * alpha_uv * sqr(sqr(m.x / au) + sqr(m.y / av) + sqr(m.z)));
+        return result * cos_theta > 1e-20f ? result : 0.f;
+    }
+    float smith_g1(V3 v, V3 m) const { // :341-365
+        float xy_alpha_2 = sqr(au * v.x) + sqr(av * v.y), tan_theta_alpha_2 = xy_alpha_2 / sqr(v.z), result;
+        if (!ggx) {
+            float a = 1.f / sqrtf(tan_theta_alpha_2), a_sqr = a * a;
+            result = a >= 1.6f ? 1.f : (3.535f * a + 2.181f * a_sqr) / (1.f + 2.276f * a + 2.577f * a_sqr);
+        } else {
+            result = 2.f / (1.f + sqrtf(1.f + tan_theta_alpha_2));
+        }
+        if (xy_alpha_2 == 0.f)
+            result = 1.f;
+        if (dot3(v, m) * v.z <= 0.f)
+            result = 0.f;
+        return result;
+    }
+    void sample_visible_11(float cos_theta_i, float sx, float sy, float &slope_x, float &slope_y) const { // :368-418
+        if (!ggx) {
+            const float inv_sqrt_pi = 0.56418958354775628695f;
+            float tan_theta_i = sqrtf(std::max(fmaf(-cos_theta_i, cos_theta_i, 1.f), 0.f)) / cos_theta_i;
+            float cot_theta_i = 1.f / tan_theta_i;
+            float maxval = erff(cot_theta_i);
+            sx = std::max(std::min(sx, 1.f - 1e-6f), 1e-6f);
+            sy = std::max(std::min(sy, 1.f - 1e-6f), 1e-6f);
+            float x = maxval - (maxval + 1.f) * erff(sqrtf(-logf(sx)));
+            sx *= 1.f + maxval + inv_sqrt_pi * tan_theta_i * expf(-sqr(cot_theta_i));
+            for (int i = 0; i < 3; ++i) {
+                float slope = dr_erfinv(x);
+                float value = 1.f + x + inv_sqrt_pi * tan_theta_i * expf(-sqr(slope)) - sx;
+                float derivative = 1.f - slope * tan_theta_i;
+                x -= value / derivative;
+            }
+            slope_x = dr_erfinv(x);
+            slope_y = dr_erfinv(fmaf(2.f, sy, -1.f));
+        } else {
+            // warp::square_to_uniform_disk_concentric (warp.h:54-89)
+            float px, py;
+            {
+                float x = fmaf(2.f, sx, -1.f), y = fmaf(2.f, sy, -1.f);
+                bool is_zero = x == 0.f && y == 0.f, quadrant_1_or_3 = fabsf(x) < fabsf(y);
+                float r = quadrant_1_or_3 ? y : x, rp = quadrant_1_or_3 ? x : y;
+                float phi = 0.25f * 3.14159265358979323846f * rp / r;
+                if (quadrant_1_or_3)
+                    phi = 0.5f * 3.14159265358979323846f - phi;
+                if (is_zero)
+                    phi = 0.f;
+                float s, c;
+                dr_sincos(phi, s, c);
+                px = r * c, py = r * s;
+            }
+            float s = 0.5f * (1.f + cos_theta_i);
+            float a = sqrtf(std::max(1.f - px * px, 0.f));
+            py = fmaf(py, s, fmaf(-a, s, a)); // dr::lerp(a, b, t) = fmadd(b, t, fnmadd(a, t, a))
+            float x = px, y = py, z = sqrtf(std::max(1.f - (px * px + py * py), 0.f));
+            float sin_theta_i = sqrtf(std::max(1.f - cos_theta_i * cos_theta_i, 0.f));
+            float norm = 1.f / fmaf(sin_theta_i, y, cos_theta_i * z);
+            slope_x = fmaf(cos_theta_i, y, -(sin_theta_i * z)) * norm;
+            slope_y = x * norm;
+        }
+    }
+    // visible normal sampling, :296-326; returns m and its density
+    V3 sample(V3 wi, float sx, float sy, float &pdf) const {
+        V3 wi_p = normalize3(v3(au * wi.x, av * wi.y, wi.z));
+        // Frame3f::sincos_phi (frame.h): sin_theta_2 = x^2 + y^2, inv = rsqrt, result = (y, x) * inv, (0, 1) when tiny
+        float sin_theta_2 = fmaf(wi_p.x, wi_p.x, wi_p.y * wi_p.y), inv = 1.f / sqrtf(sin_theta_2);
+        float sin_phi = wi_p.y * inv, cos_phi = wi_p.x * inv;
+        if (fabsf(sin_theta_2) <= 4.f * 1.1920929e-07f)
+            sin_phi = 0.f, cos_phi = 1.f;
+        float slx, sly;
+        sample_visible_11(wi_p.z, sx, sy, slx, sly);
+        float rx = fmaf(cos_phi, slx, -(sin_phi * sly)) * au, ry = fmaf(sin_phi, slx, cos_phi * sly) * av;
+        V3 m = normalize3(v3(-rx, -ry, 1.f));
+        pdf = eval(m) * smith_g1(wi, m) * fabsf(dot3(wi, m)) / wi.z;
+        return m;
+    }
+};
+
 // fresnel_diffuse_reflectance, include/mitsuba/render/fresnel.h:328-355
 inline float fresnel_diffuse_reflectance(float eta) {
     float inv_eta = 1.f / eta;
@@ -1017,7 +1122,8 @@ PathResult trace_path(const dtof_oracle_scene &sc, const dtof_params &P, const M
         // ---- emitter sampling (:187-202); the 2D sample is ALWAYS drawn (Appendix A.6e)
         float e1 = smp.next_1d(correlate), e2 = smp.next_1d(correlate);
         const dtof_bsdf *bsdf = valid ? &sc.bsdfs[sc.meshes[si.mesh].bsdf] : nullptr;
-        bool smooth = bsdf && (bsdf->kind == DTOF_BSDF_DIFFUSE || bsdf->kind == DTOF_BSDF_PLASTIC); // BSDFFlags::Smooth
+        bool smooth = bsdf && (bsdf->kind == DTOF_BSDF_DIFFUSE || bsdf->kind == DTOF_BSDF_PLASTIC ||
+                               bsdf->kind == DTOF_BSDF_ROUGHCONDUCTOR); // BSDFFlags::Smooth (diffuse or glossy lobe)
         bool active_em = active_next && smooth;
         DirSample ds{};
         V3 em_weight = v3(0, 0, 0), wo = v3(0, 0, 0);
@@ -1101,7 +1207,46 @@ PathResult trace_path(const dtof_oracle_scene &sc, const dtof_params &P, const M
         V3 bsdf_val = v3(0, 0, 0), bsdf_weight = v3(0, 0, 0), bs_wo = v3(0, 0, 0);
         float bsdf_pdf = 0.f, bs_pdf = 0.f, bs_eta = 0.f; // zero-initialised BSDFSample3f when nothing is sampled
         bool sampled_delta = false;
-        if (valid && bsdf->kind == DTOF_BSDF_PLASTIC) { // SmoothPlastic::eval / pdf / sample, plastic.cpp:210-345
+        if (valid && bsdf->kind == DTOF_BSDF_ROUGHCONDUCTOR) { // RoughConductor::eval / pdf / sample, roughconductor.cpp:226-390
+            const Microfacet distr(bsdf->distribution == 1, bsdf->alpha[0], bsdf->alpha[1]);
+            V3 wi = si.wi, wo_l = wo;
+            if (bsdf->twosided) {
+                wo_l.z = mulsign(wo_l.z, wi.z);
+                wi.z = fabsf(wi.z);
+            }
+            auto fresnel3 = [&](float c) {
+                return v3(fresnel_conductor(c, bsdf->eta[0], bsdf->k[0]), fresnel_conductor(c, bsdf->eta[1], bsdf->k[1]),
+                          fresnel_conductor(c, bsdf->eta[2], bsdf->k[2]));
+            };
+            const V3 spec = v3(bsdf->reflectance[0], bsdf->reflectance[1], bsdf->reflectance[2]);
+            if (wi.z > 0.f && wo_l.z > 0.f) {
+                V3 H = normalize3(wo_l + wi);
+                float D = distr.eval(H);
+                if (D != 0.f) {
+                    float G = distr.smith_g1(wi, H) * distr.smith_g1(wo_l, H);
+                    float result = D * G / (4.f * wi.z);
+                    V3 F = fresnel3(dot3(wi, H));
+                    bsdf_val = v3(F.x * (result * spec.x), F.y * (result * spec.y), F.z * (result * spec.z));
+                }
+                if (dot3(wi, H) > 0.f && dot3(wo_l, H) > 0.f)
+                    bsdf_pdf = distr.eval(H) * distr.smith_g1(wi, H) / (4.f * wi.z);
+            }
+            if (wi.z > 0.f) {
+                float pdf_m;
+                V3 m = distr.sample(wi, s2x, s2y, pdf_m);
+                float dwm = dot3(wi, m);
+                bs_wo = v3(fmaf(2.f * dwm, m.x, -wi.x), fmaf(2.f * dwm, m.y, -wi.y), fmaf(2.f * dwm, m.z, -wi.z)); // reflect(wi, m)
+                bs_eta = 1.f;
+                bool ok = pdf_m != 0.f && bs_wo.z > 0.f;
+                float weight = distr.smith_g1(bs_wo, m);
+                bs_pdf = pdf_m / (4.f * dot3(bs_wo, m));
+                V3 F = fresnel3(dwm);
+                if (ok)
+                    bsdf_weight = v3(F.x * (weight * spec.x), F.y * (weight * spec.y), F.z * (weight * spec.z));
+                if (bsdf->twosided)
+                    bs_wo.z = mulsign(bs_wo.z, si.wi.z);
+            }
+        } else if (valid && bsdf->kind == DTOF_BSDF_PLASTIC) { // SmoothPlastic::eval / pdf / sample, plastic.cpp:210-345
             const PlasticParams pp(*bsdf);
             float wi_z = si.wi.z, wo_z = wo.z;
             if (bsdf->twosided) {

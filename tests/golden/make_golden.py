@@ -67,6 +67,9 @@ CASES = {
     # smooth plastic: the floor (nonlinear, tinted coat, one-sided) and the short box (two-sided, int_ior 1.9)
     "c11_plastic": ("c11_plastic", {"max_depth": 6, "pcd": 6}, 0, True),
     "c11_plastic_homodyne": ("c11_plastic", {"hetero_frequency": 0.0, "max_depth": 8, "rr_depth": 3}, 3, True),
+    # rough conductors: GGX (two-sided, copper-like), anisotropic Beckmann (default distribution), Beckmann back wall
+    "c12_roughconductor": ("c12_roughconductor", {"max_depth": 6, "pcd": 6}, 0, True),
+    "c12_roughconductor_homodyne": ("c12_roughconductor", {"hetero_frequency": 0.0, "max_depth": 8, "rr_depth": 3}, 7, True),
     "c7_constant_homodyne": ("c7_constant", {"hetero_frequency": 0.0, "tsm": "uniform", "shift": 0.0, "rr_depth": 2, "max_depth": 8}, 6, True),
 }
 # the stock path tracer (src/integrators/path.cpp) on the same scenes: the integrator element is swapped (golden_util.swap_integrator)
@@ -81,6 +84,7 @@ PATH_CASES = {
     "path_c9_dielectric": ("c9_dielectric", {"max_depth": 8}, 2, True),
     "path_c10_thinglass": ("c10_thinglass", {"max_depth": 6}, 0, True),
     "path_c11_plastic": ("c11_plastic", {"max_depth": 6}, 4, True),
+    "path_c12_roughconductor": ("c12_roughconductor", {"max_depth": 6}, 5, True),
 }
 # the ground-truth radial velocity integrator (src/integrators/velocity.cpp). Its value (t2 - t1) / time scales by exactly
 # 2^20 under the time scaling; golden_util.load_case undoes it.

@@ -59,7 +59,8 @@ CASES = [
     ("c8_conductor.xml", {"max_depth": 6}),         # smooth conductors (explicit eta / k, and the two-sided mirror)
     ("c9_dielectric.xml", {"max_depth": 8}),        # smooth dielectrics (named and numeric indices of refraction, tints)
     ("c10_thinglass.xml", {"max_depth": 8}),        # + a thin dielectric pane
-    ("c11_plastic.xml", {"max_depth": 6}),          # smooth plastic (one- and two-sided, nonlinear, tinted coat)                      # `serialized` shape: zlib container, sub-mesh 1, double precision
+    ("c11_plastic.xml", {"max_depth": 6}),          # smooth plastic (one- and two-sided, nonlinear, tinted coat)
+    ("c12_roughconductor.xml", {"max_depth": 6}),   # rough conductors (GGX, anisotropic Beckmann)                      # `serialized` shape: zlib container, sub-mesh 1, double precision
 ]
 
 
