@@ -882,6 +882,20 @@ struct Loader {
             if (!known.count(kv.first))
                 throw Error(who + ": unreferenced property \"" + kv.first + "\"");
     }
+    // RGB eta / k of the reference's named conductor materials (generated table, host/dtof_conductor_ior.inc)
+    struct ConductorIor {
+        const char *name;
+        float eta[3], k[3];
+    };
+    static const ConductorIor *conductor_ior(const std::string &material) {
+        static const ConductorIor table[] = {
+#include "dtof_conductor_ior.inc"
+        };
+        for (const ConductorIor &e : table)
+            if (material == e.name)
+                return &e;
+        throw Error("conductor material \"" + material + "\" is not in the table of named materials");
+    }
     // lookup_ior (include/mitsuba/render/ior.h:23-98): a number, or a material of the table
     static float lookup_ior(const std::string &value) {
         static const std::pair<const char *, float> table[] = {
@@ -934,17 +948,18 @@ struct Loader {
             auto p = props(node);
             reject_unknown(p, { "specular_reflectance", "material", "eta", "k" }, "conductor");
             const std::string material = p.count("material") ? p["material"].value : "none";
-            if (material != "none") {
+            const ConductorIor *named = nullptr;
+            if (material != "none") {   // conductor.cpp:221-229: a named material replaces eta / k
                 if (p.count("eta"))
                     throw Error("Should specify either (eta, k) or material, not both.");
-                throw Error("conductor material '" + material + "' (measured spectra) is outside the hot-path scope: give eta / k");
+                named = conductor_ior(material);
             }
             Bsdf b;
             b.kind = DTOF_BSDF_CONDUCTOR;
             for (int i = 0; i < 3; ++i) {
                 b.reflectance[i] = p.count("specular_reflectance") ? (float) p["specular_reflectance"].vec[i] : 1.f;
-                b.eta[i] = p.count("eta") ? (float) p["eta"].vec[i] : 0.f;
-                b.k[i] = p.count("k") ? (float) p["k"].vec[i] : 1.f;
+                b.eta[i] = named ? named->eta[i] : p.count("eta") ? (float) p["eta"].vec[i] : 0.f;
+                b.k[i] = named ? named->k[i] : p.count("k") ? (float) p["k"].vec[i] : 1.f;
             }
             return b;
         }
@@ -953,10 +968,11 @@ struct Loader {
             reject_unknown(p, { "specular_reflectance", "material", "eta", "k", "distribution", "alpha", "alpha_u", "alpha_v", "sample_visible" },
                            "roughconductor");
             const std::string material = p.count("material") ? p["material"].value : "none";
-            if (material != "none") {
+            const ConductorIor *named = nullptr;
+            if (material != "none") {   // conductor.cpp:221-229: a named material replaces eta / k
                 if (p.count("eta"))
                     throw Error("Should specify either (eta, k) or material, not both.");
-                throw Error("conductor material '" + material + "' (measured spectra) is outside the hot-path scope: give eta / k");
+                named = conductor_ior(material);
             }
             const std::string distr = p.count("distribution") ? p["distribution"].value : "beckmann";
             if (distr != "beckmann" && distr != "ggx")
@@ -977,8 +993,8 @@ struct Loader {
             }
             for (int i = 0; i < 3; ++i) {
                 b.reflectance[i] = p.count("specular_reflectance") ? (float) p["specular_reflectance"].vec[i] : 1.f;
-                b.eta[i] = p.count("eta") ? (float) p["eta"].vec[i] : 0.f;
-                b.k[i] = p.count("k") ? (float) p["k"].vec[i] : 1.f;
+                b.eta[i] = named ? named->eta[i] : p.count("eta") ? (float) p["eta"].vec[i] : 0.f;
+                b.k[i] = named ? named->k[i] : p.count("k") ? (float) p["k"].vec[i] : 1.f;
             }
             return b;
         }

@@ -139,10 +139,10 @@ class _Loader:
             if unknown:
                 raise ValueError(f"conductor: unreferenced property {sorted(unknown)}")
             material = p.get("material", "none")
-            if material != "none":
+            if material != "none":   # conductor.cpp:221-229: a named material replaces eta / k
                 if "eta" in p:
                     raise ValueError("Should specify either (eta, k) or material, not both.")
-                raise ValueError(f"conductor material '{material}' (measured spectra) is outside the hot-path scope: give eta / k")
+                p["eta"], p["k"] = conductor_ior(material)
             return Bsdf(p.get("specular_reflectance", (1.0, 1.0, 1.0)), False, _abi.BSDF_CONDUCTOR,
                         p.get("eta", (0.0, 0.0, 0.0)), p.get("k", (1.0, 1.0, 1.0)))
         if typ == "roughconductor":   # RoughConductor ctor, src/bsdfs/roughconductor.cpp:160-211
@@ -153,10 +153,10 @@ class _Loader:
             if unknown:
                 raise ValueError(f"roughconductor: unreferenced property {sorted(unknown)}")
             material = p.get("material", "none")
-            if material != "none":
+            if material != "none":   # conductor.cpp:221-229: a named material replaces eta / k
                 if "eta" in p:
                     raise ValueError("Should specify either (eta, k) or material, not both.")
-                raise ValueError(f"conductor material '{material}' (measured spectra) is outside the hot-path scope: give eta / k")
+                p["eta"], p["k"] = conductor_ior(material)
             distr = p.get("distribution", "beckmann")
             if distr not in ("beckmann", "ggx"):
                 raise ValueError(f'Specified an invalid distribution "{distr}", must be "beckmann" or "ggx"!')
@@ -365,6 +365,23 @@ _IOR = {"vacuum": 1.0, "helium": 1.000036, "hydrogen": 1.000132, "air": 1.000277
         "benzene": 1.501, "silicone oil": 1.52045, "bromine": 1.661, "water ice": 1.31, "fused quartz": 1.458,
         "pyrex": 1.470, "acrylic glass": 1.49, "polypropylene": 1.49, "bk7": 1.5046, "sodium chloride": 1.544,
         "amber": 1.55, "pet": 1.5750, "diamond": 2.419}
+
+
+_CONDUCTORS = None
+
+
+def conductor_ior(material: str):
+    """RGB (eta, k) of a named conductor material: the table the reference derives from its measured spectra
+    (complex_ior_from_file, include/mitsuba/render/ior.h:100-143), generated by tests/golden/make_conductor_table.py."""
+    global _CONDUCTORS
+    if _CONDUCTORS is None:
+        import json
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "conductor_ior.json")) as f:
+            _CONDUCTORS = json.load(f)
+    if material not in _CONDUCTORS:
+        raise ValueError(f'conductor material "{material}" is not in the table of named materials: ' + ", ".join(sorted(_CONDUCTORS)))
+    v = _CONDUCTORS[material]
+    return tuple(v["eta"]), tuple(v["k"])
 
 
 def lookup_ior(value) -> float:

@@ -26,5 +26,7 @@ cmake -G Ninja "$REF" -DCMAKE_BUILD_TYPE=Release -DMI_ENABLE_PYTHON=OFF -DMI_DEF
       -DCMAKE_PROJECT_INCLUDE="$BUILD/noipo.cmake"
 ninja -j"${JOBS:-6}"
 cp -a mitsuba lib*.so plugins include "$OUT"/
+# measured spectra of the named conductor materials (data, resolved as data/ior/<name>.{eta,k}.spd next to the executable)
+mkdir -p "$OUT/data" && cp -a "$REF/resources/data/ior" "$OUT/data/"
 make -C "$HERE"        # replay_harness, header_vectors, plugins/dopplertofpath_b200.so
 echo "reference runtime + harness + plugin in $OUT"

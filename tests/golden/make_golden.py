@@ -70,6 +70,8 @@ CASES = {
     # rough conductors: GGX (two-sided, copper-like), anisotropic Beckmann (default distribution), Beckmann back wall
     "c12_roughconductor": ("c12_roughconductor", {"max_depth": 6, "pcd": 6}, 0, True),
     "c12_roughconductor_homodyne": ("c12_roughconductor", {"hetero_frequency": 0.0, "max_depth": 8, "rr_depth": 3}, 7, True),
+    # named conductor materials (measured spectra -> RGB by the reference): gold mirror box, rough aluminium box
+    "c13_named_metals": ("c13_named_metals", {"max_depth": 6, "pcd": 6, "hetero_frequency": 0.0}, 2, True),
     "c7_constant_homodyne": ("c7_constant", {"hetero_frequency": 0.0, "tsm": "uniform", "shift": 0.0, "rr_depth": 2, "max_depth": 8}, 6, True),
 }
 # the stock path tracer (src/integrators/path.cpp) on the same scenes: the integrator element is swapped (golden_util.swap_integrator)

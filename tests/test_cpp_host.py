@@ -60,7 +60,8 @@ CASES = [
     ("c9_dielectric.xml", {"max_depth": 8}),        # smooth dielectrics (named and numeric indices of refraction, tints)
     ("c10_thinglass.xml", {"max_depth": 8}),        # + a thin dielectric pane
     ("c11_plastic.xml", {"max_depth": 6}),          # smooth plastic (one- and two-sided, nonlinear, tinted coat)
-    ("c12_roughconductor.xml", {"max_depth": 6}),   # rough conductors (GGX, anisotropic Beckmann)                      # `serialized` shape: zlib container, sub-mesh 1, double precision
+    ("c12_roughconductor.xml", {"max_depth": 6}),   # rough conductors (GGX, anisotropic Beckmann)
+    ("c13_named_metals.xml", {"max_depth": 6}),     # named conductor materials (Au, Al) from the generated table                      # `serialized` shape: zlib container, sub-mesh 1, double precision
 ]
 
 

@@ -215,3 +215,18 @@ def test_conductor_bsdf_properties_follow_the_reference():
     with pytest.raises(ValueError, match="either"):
         dt.load_string(base.replace('<bsdf type="conductor" />',
                                     '<bsdf type="conductor"><string name="material" value="Au"/><rgb name="eta" value="1"/></bsdf>'), gu.SCENES)
+
+
+def test_named_conductor_materials_come_from_the_reference_table():
+    """conductor.cpp:221-229: `material` replaces eta / k. The table (conductor_ior.json, generated from the reference's
+    own plugin by tests/golden/make_conductor_table.py) holds every material the reference itself can load."""
+    from mitsuba3dopplertof_b200.xml_loader import conductor_ior
+    eta, k = conductor_ior("Cu")
+    np.testing.assert_allclose(eta, (0.201005474, 0.923749506, 1.10221541), rtol=1e-7)
+    np.testing.assert_allclose(k, (3.91326213, 2.45304513, 2.14208984), rtol=1e-7)
+    with pytest.raises(ValueError, match="not in the table"):
+        conductor_ior("Unobtainium")
+    flat = dt.load_file(os.path.join(gu.SCENES, "c13_named_metals.xml"), resx=16, resy=16, spp=4).flatten()
+    by_kind = {b.kind: (tuple(b.eta), tuple(b.k)) for b in (flat.desc.bsdfs[i] for i in range(flat.desc.n_bsdfs))}
+    np.testing.assert_allclose(by_kind[_abi.BSDF_CONDUCTOR][0], conductor_ior("Au")[0], rtol=1e-7)
+    np.testing.assert_allclose(by_kind[_abi.BSDF_ROUGHCONDUCTOR][1], conductor_ior("Al")[1], rtol=1e-7)
