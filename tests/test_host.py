@@ -199,7 +199,7 @@ def test_serialized_scene_equals_the_ply_scene():
 
 def test_conductor_bsdf_properties_follow_the_reference():
     """SmoothConductor ctor (src/bsdfs/conductor.cpp:213-230): material "none" = (eta 0, k 1); eta/k and a material
-    together throw; measured material profiles are outside the scope and say so."""
+    together throw; unknown material names say so."""
     base = open(os.path.join(gu.SCENES, "c8_conductor.xml")).read()
     flat = dt.load_string(base, gu.SCENES, resx=16, resy=16, spp=4).flatten()
     kinds = {(b.kind, b.twosided): (tuple(b.eta), tuple(b.k), tuple(b.reflectance))
@@ -209,8 +209,8 @@ def test_conductor_bsdf_properties_follow_the_reference():
     copper = kinds[(_abi.BSDF_CONDUCTOR, 0)]
     np.testing.assert_allclose(copper[0], (0.2004, 0.9240, 1.1022), rtol=1e-6)
     np.testing.assert_allclose(copper[2], (0.9, 0.95, 1.0), rtol=1e-6)
-    with pytest.raises(ValueError, match="outside the hot-path scope"):
-        dt.load_string(base.replace('<bsdf type="conductor" />', '<bsdf type="conductor"><string name="material" value="Au"/></bsdf>'),
+    with pytest.raises(ValueError, match="not in the table"):
+        dt.load_string(base.replace('<bsdf type="conductor" />', '<bsdf type="conductor"><string name="material" value="Xx"/></bsdf>'),
                        gu.SCENES)
     with pytest.raises(ValueError, match="either"):
         dt.load_string(base.replace('<bsdf type="conductor" />',
