@@ -102,6 +102,10 @@ struct PointLight {
     float position[3] = { 0, 0, 0 };
     float intensity[3] = { 1, 1, 1 };
     bool constant_env = false;
+    // `spot` (src/emitters/spot.cpp, no projection texture): linear part of to_world^-1 and the two angles in radians
+    bool spot = false;
+    float to_local[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 };
+    float cutoff_angle = 0.f, beam_width = 0.f;
 };
 
 struct Film {

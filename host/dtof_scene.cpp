@@ -728,7 +728,11 @@ std::unique_ptr<FlatScene> Scene::flatten() const {
         } else {
             const PointLight &pl = emitters[o.second];
             dtof_emitter e{};
-            e.kind = pl.constant_env ? DTOF_EMITTER_CONSTANT : DTOF_EMITTER_POINT;
+            e.kind = pl.constant_env ? DTOF_EMITTER_CONSTANT : pl.spot ? DTOF_EMITTER_SPOT : DTOF_EMITTER_POINT;
+            if (pl.spot) {
+                memcpy(e.to_local, pl.to_local, sizeof(e.to_local));
+                e.cutoff_angle = pl.cutoff_angle, e.beam_width = pl.beam_width;
+            }
             if (pl.constant_env)
                 for (const dtof_emitter &prev : fs->emitters)
                     if (prev.kind == DTOF_EMITTER_CONSTANT)
@@ -1204,10 +1208,36 @@ struct Loader {
                 sc.shapes.push_back(shape(*node));
             } else if (node->tag == "emitter") {
                 std::string typ = attr(*node, "type");
-                if (typ != "point" && typ != "constant")
-                    throw Error("emitter '" + typ + "' is outside the hot-path scope (point|area|constant)");
+                if (typ != "point" && typ != "constant" && typ != "spot")
+                    throw Error("emitter '" + typ + "' is outside the hot-path scope (point|spot|area|constant)");
                 auto p = props(*node);
                 PointLight pl;
+                if (typ == "spot") {   // SpotLight ctor, src/emitters/spot.cpp:89-114
+                    pl.spot = true;
+                    for (auto &kv : p)
+                        if (kv.first != "intensity" && kv.first != "cutoff_angle" && kv.first != "beam_width")
+                            throw Error("emitter 'spot': unreferenced property \"" + kv.first + "\" (projection textures are out of scope)");
+                    Transform4 tw = Transform4::identity();
+                    for (auto &ch : node->children) {
+                        const std::string *nm = ch->attr("name");
+                        if (ch->tag == "transform" && nm && *nm == "to_world")
+                            tw = transform(*ch);
+                    }
+                    for (int i = 0; i < 3; ++i) {
+                        pl.position[i] = (float) tw.m[4 * i + 3];
+                        for (int j = 0; j < 3; ++j)
+                            pl.to_local[3 * i + j] = (float) tw.it[4 * j + i];   // inverse = (inverse transpose)^T
+                        if (p.count("intensity"))
+                            pl.intensity[i] = (float) p["intensity"].vec[i];
+                    }
+                    const float cutoff = p.count("cutoff_angle") ? (float) parse_float(p["cutoff_angle"].value) : 20.f;
+                    const float beam = p.count("beam_width") ? (float) parse_float(p["beam_width"].value) : cutoff * 3.f / 4.f;
+                    const float deg = (float) (M_PI / 180.0);
+                    pl.cutoff_angle = cutoff * deg, pl.beam_width = beam * deg;
+                    sc.order.emplace_back('e', (uint32_t) sc.emitters.size());
+                    sc.emitters.push_back(pl);
+                    continue;
+                }
                 if (typ == "constant") {
                     pl.constant_env = true;
                     for (auto &kv : p)

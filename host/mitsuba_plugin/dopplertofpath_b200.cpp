@@ -365,12 +365,38 @@ private:
                     }
                 Spectrum L = e->eval(si);
                 d.value[0] = L[0], d.value[1] = L[1], d.value[2] = L[2];
+            } else if (e->class_()->name() == "SpotLight") {               // spot.cpp:89-114
+                d.kind = DTOF_EMITTER_SPOT;
+                const ScalarTransform4f tw = e->world_transform();   // scalar_rgb: Transform4f is the scalar transform
+                const ScalarTransform4f inv = tw.inverse();
+                for (int r = 0; r < 3; ++r) {
+                    d.position[r] = tw.matrix(r, 3);
+                    for (int cc = 0; cc < 3; ++cc)
+                        d.to_local[3 * r + cc] = inv.matrix(r, cc);
+                }
+                for (auto &o : c.objects)
+                    if (o.first == "intensity") {
+                        Spectrum I = ((const Texture<Float, Spectrum> *) o.second)->eval(si);
+                        d.value[0] = I[0], d.value[1] = I[1], d.value[2] = I[2];
+                    } else if (o.first == "texture" && ((const Texture<Float, Spectrum> *) o.second)->is_spatially_varying()) {
+                        Throw("spot emitter with a projection texture is outside the accelerated path");
+                    }
+                // the two angles are not traversed; the plugin prints them in radians (to_string, spot.cpp:265-276)
+                const std::string descr = e->to_string();
+                auto angle = [&](const char *key) -> float {
+                    size_t at = descr.find(key);
+                    if (at == std::string::npos)
+                        Throw("spot emitter: cannot read %s", key);
+                    return std::strtof(descr.c_str() + at + strlen(key), nullptr);
+                };
+                d.cutoff_angle = angle("cutoff_angle = ");
+                d.beam_width = angle("beam_width = ");
             } else if (e->class_()->name() == "ConstantBackgroundEmitter") {
                 d.kind = DTOF_EMITTER_CONSTANT;                          // the library derives the bounding sphere itself
                 Spectrum L = e->eval(si);
                 d.value[0] = L[0], d.value[1] = L[1], d.value[2] = L[2];
             } else {
-                Throw("emitter \"%s\" is outside the accelerated path (point | area | constant)", e->class_()->name());
+                Throw("emitter \"%s\" is outside the accelerated path (point | spot | area | constant)", e->class_()->name());
             }
             emitters.push_back(d);
         }

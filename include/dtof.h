@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define DTOF_ABI_VERSION 5
+#define DTOF_ABI_VERSION 6
 
 typedef struct dtof_ctx dtof_ctx;
 
@@ -88,7 +88,9 @@ typedef enum dtof_bsdf_kind {
     DTOF_BSDF_DIFFUSE = 0, DTOF_BSDF_NULL_BLACK = 1, DTOF_BSDF_CONDUCTOR = 2, DTOF_BSDF_DIELECTRIC = 3,
     DTOF_BSDF_THINDIELECTRIC = 4, DTOF_BSDF_PLASTIC = 5, DTOF_BSDF_ROUGHCONDUCTOR = 6
 } dtof_bsdf_kind;
-typedef enum dtof_emitter_kind { DTOF_EMITTER_POINT = 0, DTOF_EMITTER_AREA = 1, DTOF_EMITTER_CONSTANT = 2 } dtof_emitter_kind;
+typedef enum dtof_emitter_kind {
+    DTOF_EMITTER_POINT = 0, DTOF_EMITTER_AREA = 1, DTOF_EMITTER_CONSTANT = 2, DTOF_EMITTER_SPOT = 3
+} dtof_emitter_kind;
 
 /* ---- scene description ------------------------------------------------------------------ */
 
@@ -153,7 +155,12 @@ typedef struct dtof_emitter {
     uint32_t kind;            /* dtof_emitter_kind */
     uint32_t mesh;            /* AREA: index of the emitting mesh (must be in the static group) */
     float position[3];        /* POINT */
-    float value[3];           /* POINT: intensity; AREA, CONSTANT: radiance */
+    float value[3];           /* POINT, SPOT: intensity; AREA, CONSTANT: radiance */
+    /* SPOT (src/emitters/spot.cpp; no projection texture): `position` = translation of to_world; the linear part of
+     * to_world^-1, row-major, takes world directions into the light's frame (it looks along +z); angles in radians:
+     * the intensity ramps linearly from 0 at cutoff_angle to its full value at beam_width (spot.cpp:146-154) */
+    float to_local[9];
+    float cutoff_angle, beam_width;
 } dtof_emitter;
 
 /* PerspectiveCamera, src/sensors/perspective.cpp:172-279. sample_to_camera is

@@ -6,13 +6,14 @@ Host-side mirror of the reference's plugin surface (scene XML subset, integrator
 needs neither the CUDA library nor a GPU; rendering does, and fails loudly without them.
 """
 from .integrator import DopplerToFPathIntegrator, DTOFError, PathIntegrator, VelocityIntegrator
-from .scene import (Bsdf, ConstantEmitter, CorrelatedSampler, Film, PerspectiveSensor, PointLight, Scene, Shape, cube, mesh,
+from .scene import (Bsdf, ConstantEmitter, CorrelatedSampler, Film, PerspectiveSensor, PointLight, Scene, Shape, SpotLight,
+                    cube, mesh,
                     rectangle)
 from .transform import AnimatedTransform, Transform4
 from .xml_loader import load_file, load_string
 from . import tof  # noqa: E402  (tutorial post-processing and drivers; needs the renderer only when called)
 
 __all__ = [
-    "DopplerToFPathIntegrator", "VelocityIntegrator", "PathIntegrator", "DTOFError", "Bsdf", "CorrelatedSampler", "Film", "PerspectiveSensor", "PointLight", "ConstantEmitter",
+    "DopplerToFPathIntegrator", "VelocityIntegrator", "PathIntegrator", "DTOFError", "Bsdf", "CorrelatedSampler", "Film", "PerspectiveSensor", "PointLight", "SpotLight", "ConstantEmitter",
     "Scene", "Shape", "cube", "mesh", "rectangle", "AnimatedTransform", "Transform4", "load_file", "load_string", "tof",
 ]

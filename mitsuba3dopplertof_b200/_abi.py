@@ -8,7 +8,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 # enums (include/dtof.h)
 TIME_UNIFORM, TIME_STRATIFIED, TIME_ANTITHETIC, TIME_ANTITHETIC_MIRROR = range(4)
@@ -17,7 +17,7 @@ RFILTER_BOX, RFILTER_TENT, RFILTER_GAUSSIAN = range(3)
 SHAPE_MESH, SHAPE_RECTANGLE = range(2)
 BSDF_DIFFUSE, BSDF_NULL_BLACK, BSDF_CONDUCTOR, BSDF_DIELECTRIC, BSDF_THINDIELECTRIC, BSDF_PLASTIC, \
     BSDF_ROUGHCONDUCTOR = range(7)
-EMITTER_POINT, EMITTER_AREA, EMITTER_CONSTANT = range(3)
+EMITTER_POINT, EMITTER_AREA, EMITTER_CONSTANT, EMITTER_SPOT = range(4)
 INTEGRATOR_DOPPLERTOFPATH, INTEGRATOR_VELOCITY, INTEGRATOR_PATH = range(3)
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED, ERR_STATE = range(6)
@@ -50,7 +50,8 @@ class Bsdf(C.Structure):
 
 
 class Emitter(C.Structure):
-    _fields_ = [("kind", C.c_uint32), ("mesh", C.c_uint32), ("position", C.c_float * 3), ("value", C.c_float * 3)]
+    _fields_ = [("kind", C.c_uint32), ("mesh", C.c_uint32), ("position", C.c_float * 3), ("value", C.c_float * 3),
+                ("to_local", C.c_float * 9), ("cutoff_angle", C.c_float), ("beam_width", C.c_float)]
 
 
 class Camera(C.Structure):

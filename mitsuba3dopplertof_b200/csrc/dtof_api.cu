@@ -234,7 +234,7 @@ struct dtof_ctx {
     int forced_mode = -1;       // DTOF_MODE env / stats runs: -1 = automatic
     int last_mode = -1;
     void *d_nodes = nullptr, *d_tris = nullptr, *d_shade = nullptr, *d_insts = nullptr, *d_meshes = nullptr,
-         *d_bsdfs = nullptr, *d_emitters = nullptr, *d_cdf = nullptr, *d_pmf = nullptr;
+         *d_bsdfs = nullptr, *d_emitters = nullptr, *d_spots = nullptr, *d_cdf = nullptr, *d_pmf = nullptr;
     std::vector<InstRec> h_insts;
     std::vector<TlasEntry> h_tlas;   // per instance: motion, object-space bounds, BLAS root (TLAS rebuild on keyframe updates)
     uint32_t tlas_begin = 0, n_tlas_nodes = 0;
@@ -289,7 +289,7 @@ dtof_status fail(dtof_ctx *c, dtof_status s, const char *fmt, ...) {
 
 void free_scene(dtof_ctx *c) {
     void **ptrs[] = { &c->d_tris_flat, &c->d_boxes, &c->d_nodes, &c->d_tris, &c->d_shade, &c->d_insts, &c->d_meshes, &c->d_bsdfs,
-                      &c->d_emitters, &c->d_cdf, &c->d_pmf };
+                      &c->d_emitters, &c->d_spots, &c->d_cdf, &c->d_pmf };
     for (void **p : ptrs) {
         if (*p)
             cudaFree(*p);
@@ -736,6 +736,7 @@ struct HostScene {
     std::vector<MeshRec> meshes;
     std::vector<BsdfRec> bsdfs;
     std::vector<EmitterRec> emitters;
+    std::vector<SpotRec> spots;   // empty unless the scene has a spot light
     std::vector<TriShade> shade;
     std::vector<float> cdf, pmf;
     std::vector<InstRec> insts;
@@ -926,8 +927,20 @@ dtof_status prepare_scene(dtof_ctx *ctx, const dtof_scene_desc *sc, HostScene &H
     bool all_point = true;
     for (uint32_t i = 0; i < sc->n_emitters; ++i) {
         const dtof_emitter &e = sc->emitters[i];
-        if (e.kind > DTOF_EMITTER_CONSTANT)
+        if (e.kind > DTOF_EMITTER_SPOT)
             return fail(ctx, DTOF_ERR_UNSUPPORTED, "emitter kind %u is outside the hot-path scope", e.kind);
+        if (e.kind == DTOF_EMITTER_SPOT) {   // SpotLight ctor, spot.cpp:102-112
+            if (!(e.cutoff_angle >= e.beam_width) || !(e.cutoff_angle > 0.f))
+                return fail(ctx, DTOF_ERR_INVALID, "spot emitter %u: cutoff_angle must be positive and >= beam_width", i);
+            if (H.spots.empty())
+                H.spots.assign(sc->n_emitters, SpotRec{});
+            SpotRec &sr = H.spots[i];
+            memcpy(sr.to_local, e.to_local, sizeof(sr.to_local));
+            sr.cutoff_angle = e.cutoff_angle;
+            sr.cos_cutoff = std::cos(e.cutoff_angle), sr.cos_beam = std::cos(e.beam_width);
+            sr.inv_transition = 1.f / (e.cutoff_angle - e.beam_width);
+            H.extended = true;
+        }
         if (e.kind == DTOF_EMITTER_CONSTANT) {
             if (H.env_emitter >= 0)
                 return fail(ctx, DTOF_ERR_INVALID, "Only one environment emitter can be specified per scene.");   // scene.cpp:53-55
@@ -1091,6 +1104,7 @@ dtof_status dtof_upload_scene(dtof_ctx *ctx, const dtof_scene_desc *sc) {
     if ((s = upload_vec(ctx, meshes, &ctx->d_meshes)) != DTOF_OK) return s;
     if ((s = upload_vec(ctx, bsdfs, &ctx->d_bsdfs)) != DTOF_OK) return s;
     if ((s = upload_vec(ctx, emitters, &ctx->d_emitters)) != DTOF_OK) return s;
+    if ((s = upload_vec(ctx, H.spots, &ctx->d_spots)) != DTOF_OK) return s;
     if ((s = upload_vec(ctx, cdf, &ctx->d_cdf)) != DTOF_OK) return s;
     if ((s = upload_vec(ctx, pmf, &ctx->d_pmf)) != DTOF_OK) return s;
     ctx->h_insts = insts;
@@ -1118,6 +1132,7 @@ dtof_status dtof_upload_scene(dtof_ctx *ctx, const dtof_scene_desc *sc) {
     D.meshes = (const MeshRec *) ctx->d_meshes;
     D.bsdfs = (const BsdfRec *) ctx->d_bsdfs;
     D.emitters = (const EmitterRec *) ctx->d_emitters;
+    D.spots = (const SpotRec *) ctx->d_spots;
     D.area_cdf = (const float *) ctx->d_cdf;
     D.area_pmf = (const float *) ctx->d_pmf;
     D.root = built.root;

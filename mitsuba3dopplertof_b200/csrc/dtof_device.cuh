@@ -543,6 +543,7 @@ struct DeviceScene {
     const MeshRec *meshes;
     const BsdfRec *bsdfs;
     const EmitterRec *emitters;
+    const SpotRec *spots;    // parallel to `emitters` when the scene has a spot light, else NULL
     const float *area_cdf, *area_pmf;
     int32_t root;
     uint32_t n_emitters, n_insts, n_nodes, n_tris, has_geometry;

@@ -92,6 +92,12 @@ struct alignas(16) BsdfRec {
     float k_r, k_g, k_b, pad1;         // dielectric: specular_transmittance; plastic: specular_reflectance, nonlinear (0 / 1)
 };
 
+struct alignas(16) SpotRec {   // per emitter index, read only for DTOF_EMITTER_SPOT (src/emitters/spot.cpp)
+    float to_local[9];
+    float cutoff_angle, cos_cutoff, cos_beam, inv_transition;
+    float pad[3];
+};
+
 struct EmitterRec {
     uint32_t kind;         // dtof_emitter_kind
     uint32_t mesh;

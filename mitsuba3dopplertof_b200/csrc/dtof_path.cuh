@@ -174,7 +174,7 @@ DTOF_DEV void shade_bounce(const DeviceScene &S, const float4 *__restrict__ I, c
         float sx = 0.f, sy = 0.f;
         V3 ds_p, ds_n, spec, ds_d;
         EmitterRec em = S.emitters[0];
-        if (n_em > 1 || em.kind != DTOF_EMITTER_POINT) {
+        if (n_em > 1 || (em.kind != DTOF_EMITTER_POINT && em.kind != DTOF_EMITTER_SPOT)) {
             sx = u32_to_float(pcg_output(correlate ? e1a : e1b));
             sy = u32_to_float(pcg_output(correlate ? e2a : e2b));
         }
@@ -193,6 +193,24 @@ DTOF_DEV void shade_bounce(const DeviceScene &S, const float4 *__restrict__ I, c
             ds_dist = fsqrt(dist2);
             ds_d = ds_d * inv_dist;
             float f = inv_dist * inv_dist;
+            spec = v3(em.vr * f, em.vg * f, em.vb * f);
+        } else if (ENV && em.kind == DTOF_EMITTER_SPOT) {               // SpotLight::sample_direction (spot.cpp:180-215), falloff_curve (:146-154)
+            const SpotRec &sr = S.spots[index];
+            ds_p = v3(em.px, em.py, em.pz);
+            ds_pdf = 1.f;
+            ds_delta = true;
+            ds_d = ds_p - si.p;
+            ds_dist = fsqrt(dot3(ds_d, ds_d));
+            const float inv_dist = frcp(ds_dist);
+            ds_d = ds_d * inv_dist;
+            const V3 nd = -ds_d;
+            const float *M = sr.to_local;
+            const V3 local = v3(fmaf(M[2], nd.z, fmaf(M[1], nd.y, M[0] * nd.x)), fmaf(M[5], nd.z, fmaf(M[4], nd.y, M[3] * nd.x)),
+                                fmaf(M[8], nd.z, fmaf(M[7], nd.y, M[6] * nd.x)));
+            const float cos_theta = normalize3(local).z;
+            const float beam_res = cos_theta >= sr.cos_beam ? 1.f : (sr.cutoff_angle - acosf(cos_theta)) * sr.inv_transition;
+            const float falloff = cos_theta > sr.cos_cutoff ? beam_res : 0.f;
+            const float f = falloff * (inv_dist * inv_dist);
             spec = v3(em.vr * f, em.vg * f, em.vb * f);
         } else if (ENV && em.kind == DTOF_EMITTER_CONSTANT) {                  // ConstantBackgroundEmitter::sample_direction, constant.cpp:112-139
             ds_d = square_to_uniform_sphere(sx, sy);

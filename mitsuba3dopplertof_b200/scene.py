@@ -23,7 +23,7 @@ from . import _abi
 from .transform import AnimatedTransform, Transform4, perspective_projection
 
 __all__ = [
-    "Bsdf", "Shape", "PointLight", "ConstantEmitter", "Film", "CorrelatedSampler", "PerspectiveSensor", "Scene", "FlatScene",
+    "Bsdf", "Shape", "PointLight", "SpotLight", "ConstantEmitter", "Film", "CorrelatedSampler", "PerspectiveSensor", "Scene", "FlatScene",
     "rectangle", "cube", "mesh",
 ]
 
@@ -85,6 +85,16 @@ class PointLight:
     """src/emitters/point.cpp:65-85: position = ``position`` or translation of ``to_world``."""
     position: Sequence[float] = (0.0, 0.0, 0.0)
     intensity: Sequence[float] = (1.0, 1.0, 1.0)
+
+
+@dataclass
+class SpotLight:
+    """src/emitters/spot.cpp (without a projection texture): `to_world` places the light (it looks along +z);
+    `cutoff_angle` / `beam_width` in degrees (defaults 20 and 3/4 of the cutoff angle, spot.cpp:102-106)."""
+    to_world: Transform4 = field(default_factory=Transform4.identity)
+    intensity: Sequence[float] = (1.0, 1.0, 1.0)
+    cutoff_angle: float = 20.0
+    beam_width: Optional[float] = None
 
 
 @dataclass
@@ -371,7 +381,16 @@ class Scene:
                     emitters.append(_abi.Emitter(_abi.EMITTER_AREA, mi_, (C.c_float * 3)(0, 0, 0), rgb3(s.radiance)))
             else:
                 e = self.emitters[i]
-                if isinstance(e, ConstantEmitter):
+                if isinstance(e, SpotLight):
+                    m = np.asarray(e.to_world.matrix, np.float64)
+                    inv = np.asarray(e.to_world.inverse_transpose, np.float64).T[:3, :3].astype(f32)   # tracked inverse
+                    cutoff = f32(e.cutoff_angle)
+                    beam = f32(e.beam_width) if e.beam_width is not None else cutoff * f32(3.0) / f32(4.0)
+                    deg = f32(np.pi / 180.0)
+                    emitters.append(_abi.Emitter(_abi.EMITTER_SPOT, 0, (C.c_float * 3)(*[float(f32(x)) for x in m[:3, 3]]),
+                                                 rgb3(e.intensity), (C.c_float * 9)(*inv.reshape(-1).tolist()),
+                                                 float(cutoff * deg), float(beam * deg)))
+                elif isinstance(e, ConstantEmitter):
                     if any(em.kind == _abi.EMITTER_CONSTANT for em in emitters):
                         raise ValueError("Only one environment emitter can be specified per scene.")   # scene.cpp:53-55
                     emitters.append(_abi.Emitter(_abi.EMITTER_CONSTANT, 0, (C.c_float * 3)(0, 0, 0), rgb3(e.radiance)))

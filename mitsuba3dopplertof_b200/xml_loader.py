@@ -17,7 +17,7 @@ from typing import Dict, Optional
 import numpy as np
 
 from .integrator import DopplerToFPathIntegrator, PathIntegrator, VelocityIntegrator
-from .scene import (Bsdf, ConstantEmitter, CorrelatedSampler, Film, PerspectiveSensor, PointLight, Scene, Shape)
+from .scene import (Bsdf, ConstantEmitter, CorrelatedSampler, Film, PerspectiveSensor, PointLight, Scene, Shape, SpotLight)
 from .transform import AnimatedTransform, Transform4
 
 __all__ = ["load_file", "load_string"]
@@ -322,9 +322,21 @@ class _Loader:
                 sc.shapes.append(self.shape(node))
             elif node.tag == "emitter":
                 typ = self.attr(node, "type")
-                if typ not in ("point", "constant"):
-                    raise ValueError(f"emitter '{typ}' is outside the hot-path scope (point|area|constant)")
+                if typ not in ("point", "constant", "spot"):
+                    raise ValueError(f"emitter '{typ}' is outside the hot-path scope (point|spot|area|constant)")
                 p = self.props(node)
+                if typ == "spot":   # SpotLight ctor, src/emitters/spot.cpp:89-114
+                    unknown = set(p) - {"intensity", "cutoff_angle", "beam_width"}
+                    if unknown:
+                        raise ValueError(f"emitter 'spot': unreferenced property {sorted(unknown)} (projection textures are out of scope)")
+                    tw = Transform4.identity()
+                    for ch in node:
+                        if ch.tag == "transform" and ch.get("name") == "to_world":
+                            tw = self.transform(ch)
+                    order.append(("emitter", len(sc.emitters)))
+                    sc.emitters.append(SpotLight(tw, p.get("intensity", (1.0,) * 3), float(p.get("cutoff_angle", 20.0)),
+                                                 float(p["beam_width"]) if "beam_width" in p else None))
+                    continue
                 if typ == "constant":
                     unknown = set(p) - {"radiance"}
                     if unknown:

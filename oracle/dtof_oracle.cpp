@@ -1153,6 +1153,26 @@ PathResult trace_path(const dtof_oracle_scene &sc, const dtof_params &P, const M
                 ds.d = ds.d * inv_dist;
                 float f = inv_dist * inv_dist;
                 spec = v3(em.value[0] * f, em.value[1] * f, em.value[2] * f);
+            } else if (em.kind == DTOF_EMITTER_SPOT) { // SpotLight::sample_direction (spot.cpp:180-215), falloff_curve (:146-154)
+                ds.p = v3(em.position[0], em.position[1], em.position[2]);
+                ds.n = v3(0, 0, 0);
+                ds.pdf = 1.f;
+                ds.delta = true;
+                ds.d = ds.p - si.p;
+                ds.dist = sqrtf(dot3(ds.d, ds.d));
+                float inv_dist = 1.f / ds.dist;
+                ds.d = ds.d * inv_dist;
+                V3 nd = v3(-ds.d.x, -ds.d.y, -ds.d.z);
+                const float *M = em.to_local; // Transform * Vector, column by column
+                V3 local = v3(fmaf(M[2], nd.z, fmaf(M[1], nd.y, M[0] * nd.x)), fmaf(M[5], nd.z, fmaf(M[4], nd.y, M[3] * nd.x)),
+                              fmaf(M[8], nd.z, fmaf(M[7], nd.y, M[6] * nd.x)));
+                float cos_theta = normalize3(local).z;
+                float cos_cutoff = cosf(em.cutoff_angle), cos_beam = cosf(em.beam_width);
+                float inv_transition = 1.f / (em.cutoff_angle - em.beam_width);
+                float beam_res = cos_theta >= cos_beam ? 1.f : (em.cutoff_angle - acosf(cos_theta)) * inv_transition;
+                float falloff = cos_theta > cos_cutoff ? beam_res : 0.f;
+                float f = falloff * (inv_dist * inv_dist);
+                spec = falloff > 0.f ? v3(em.value[0] * f, em.value[1] * f, em.value[2] * f) : v3(0, 0, 0);
             } else if (em.kind == DTOF_EMITTER_CONSTANT) { // ConstantBackgroundEmitter::sample_direction, constant.cpp:112-139
                 ds.d = square_to_uniform_sphere(sx, sy);
                 V3 rel = si.p - sc.env_center;

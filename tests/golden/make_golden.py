@@ -72,6 +72,9 @@ CASES = {
     "c12_roughconductor_homodyne": ("c12_roughconductor", {"hetero_frequency": 0.0, "max_depth": 8, "rr_depth": 3}, 7, True),
     # named conductor materials (measured spectra -> RGB by the reference): gold mirror box, rough aluminium box
     "c13_named_metals": ("c13_named_metals", {"max_depth": 6, "pcd": 6, "hetero_frequency": 0.0}, 2, True),
+    # the ToF illuminator as a spot light next to the camera (falloff between beam_width and cutoff_angle)
+    "c14_spot": ("c14_spot", {"max_depth": 4}, 0, True),
+    "c14_spot_homodyne": ("c14_spot", {"hetero_frequency": 0.0, "max_depth": 5, "pcd": 5}, 8, True),
     "c7_constant_homodyne": ("c7_constant", {"hetero_frequency": 0.0, "tsm": "uniform", "shift": 0.0, "rr_depth": 2, "max_depth": 8}, 6, True),
 }
 # the stock path tracer (src/integrators/path.cpp) on the same scenes: the integrator element is swapped (golden_util.swap_integrator)
@@ -87,6 +90,7 @@ PATH_CASES = {
     "path_c10_thinglass": ("c10_thinglass", {"max_depth": 6}, 0, True),
     "path_c11_plastic": ("c11_plastic", {"max_depth": 6}, 4, True),
     "path_c12_roughconductor": ("c12_roughconductor", {"max_depth": 6}, 5, True),
+    "path_c14_spot": ("c14_spot", {}, 6, True),
 }
 # the ground-truth radial velocity integrator (src/integrators/velocity.cpp). Its value (t2 - t1) / time scales by exactly
 # 2^20 under the time scaling; golden_util.load_case undoes it.

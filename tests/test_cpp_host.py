@@ -61,7 +61,8 @@ CASES = [
     ("c10_thinglass.xml", {"max_depth": 8}),        # + a thin dielectric pane
     ("c11_plastic.xml", {"max_depth": 6}),          # smooth plastic (one- and two-sided, nonlinear, tinted coat)
     ("c12_roughconductor.xml", {"max_depth": 6}),   # rough conductors (GGX, anisotropic Beckmann)
-    ("c13_named_metals.xml", {"max_depth": 6}),     # named conductor materials (Au, Al) from the generated table                      # `serialized` shape: zlib container, sub-mesh 1, double precision
+    ("c13_named_metals.xml", {"max_depth": 6}),     # named conductor materials (Au, Al) from the generated table
+    ("c14_spot.xml", {}),                            # spot light (lookat to_world, cutoff / beam angles)                      # `serialized` shape: zlib container, sub-mesh 1, double precision
 ]
 
 

@@ -30,7 +30,7 @@ def test_cuda_lanes_match_reference_and_oracle(ctx, name):
     flat = ctx.upload(scene)
     rec = ctx.trace_samples(params, ref["lanes"])
     frac, worst, bad = gu.compare(rec, ref)
-    assert frac >= 0.99, f"{name}: {len(bad)} lanes differ from the reference run: {ref['lanes'][bad][:8]}"
+    assert frac >= gu.min_fraction(name, 0.99), f"{name}: {len(bad)} lanes differ from the reference run: {ref['lanes'][bad][:8]}"
     assert worst <= gu.REL_TOL
     # against the oracle: identical streams and hit arithmetic; the shading arithmetic after the hit uses the SFU
     # approximations the reference's CUDA variants use (<= 2 ulp per op, csrc/dtof_device.cuh), so the comparison is
@@ -41,7 +41,7 @@ def test_cuda_lanes_match_reference_and_oracle(ctx, name):
     d = np.abs(rec["rgb"].astype(np.float64) - orc["rgb"])
     scale = np.maximum(np.abs(orc["rgb"]), gu.ABS_FLOOR)
     ok = (d <= gu.REL_TOL * scale).all(axis=1)
-    assert ok.mean() >= 0.99, f"{name}: CUDA vs oracle mismatch on lanes {ref['lanes'][~ok][:8]}"
+    assert ok.mean() >= gu.min_fraction(name, 0.99), f"{name}: CUDA vs oracle mismatch on lanes {ref['lanes'][~ok][:8]}"
     rel = (d / scale).max(axis=1)
     assert np.median(rel) <= 1e-6 and np.quantile(rel, 0.9) <= 1e-5, (np.median(rel), np.quantile(rel, 0.9))
     assert np.array_equal(rec["depth"][ok], orc["depth"][ok])
@@ -73,6 +73,7 @@ def test_cuda_full_waveform_mode_matches_oracle(ctx, name):
     ("c10_thinglass", dict(resx=40, resy=40, spp=32, hetero_frequency=0.0, max_depth=8)),  # thin pane: Null transmission
     ("c11_plastic", dict(resx=40, resy=40, spp=32, hetero_frequency=0.0, max_depth=6)),  # plastic: smooth + delta lobe
     ("c12_roughconductor", dict(resx=40, resy=40, spp=32, hetero_frequency=0.0, max_depth=6)),  # microfacets
+    ("c14_spot", dict(resx=40, resy=40, spp=32, hetero_frequency=0.0)),                         # spot light falloff
 ])
 def test_cuda_film_matches_oracle(ctx, scene_name, kw):
     import oracle_lib

@@ -60,6 +60,7 @@ CASES = [
     ("c10_thinglass", dict(resx=40, resy=40, spp=32, hetero_frequency=0.0, max_depth=8)),  # thin pane: Null transmission
     ("c11_plastic", dict(resx=40, resy=40, spp=32, hetero_frequency=0.0, max_depth=6)),  # plastic: smooth + delta lobe
     ("c12_roughconductor", dict(resx=40, resy=40, spp=32, hetero_frequency=0.0, max_depth=6)),  # microfacets
+    ("c14_spot", dict(resx=40, resy=40, spp=32, hetero_frequency=0.0)),                         # spot light falloff
 ]
 
 
