@@ -200,14 +200,16 @@ DTOF_DEV void shade_bounce(const DeviceScene &S, const float4 *__restrict__ I, c
             ds_pdf = 1.f;
             ds_delta = true;
             ds_d = ds_p - si.p;
-            ds_dist = fsqrt(dot3(ds_d, ds_d));
-            const float inv_dist = frcp(ds_dist);
+            // IEEE square root / division here: inside the falloff ramp one ulp of cos_theta (~0.99) is 4e-7 rad of angle,
+            // i.e. up to 1.5e-4 of a small falloff value; the SFU approximations (2 ulp) would double that
+            ds_dist = sqrtf(dot3(ds_d, ds_d));
+            const float inv_dist = 1.f / ds_dist;
             ds_d = ds_d * inv_dist;
             const V3 nd = -ds_d;
             const float *M = sr.to_local;
             const V3 local = v3(fmaf(M[2], nd.z, fmaf(M[1], nd.y, M[0] * nd.x)), fmaf(M[5], nd.z, fmaf(M[4], nd.y, M[3] * nd.x)),
                                 fmaf(M[8], nd.z, fmaf(M[7], nd.y, M[6] * nd.x)));
-            const float cos_theta = normalize3(local).z;
+            const float cos_theta = local.z * (1.f / sqrtf(dot3(local, local)));
             const float beam_res = cos_theta >= sr.cos_beam ? 1.f : (sr.cutoff_angle - acosf(cos_theta)) * sr.inv_transition;
             const float falloff = cos_theta > sr.cos_cutoff ? beam_res : 0.f;
             const float f = falloff * (inv_dist * inv_dist);

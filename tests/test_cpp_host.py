@@ -62,7 +62,7 @@ CASES = [
     ("c11_plastic.xml", {"max_depth": 6}),          # smooth plastic (one- and two-sided, nonlinear, tinted coat)
     ("c12_roughconductor.xml", {"max_depth": 6}),   # rough conductors (GGX, anisotropic Beckmann)
     ("c13_named_metals.xml", {"max_depth": 6}),     # named conductor materials (Au, Al) from the generated table
-    ("c14_spot.xml", {}),                            # spot light (lookat to_world, cutoff / beam angles)                      # `serialized` shape: zlib container, sub-mesh 1, double precision
+    ("c14_spot.xml", {}),                            # spot light (lookat to_world, cutoff / beam angles)
 ]
 
 
@@ -82,7 +82,8 @@ def test_cpp_host_flattens_like_python_host(cli, tmp_path, scene, params):
         a, b = a[:n].view(np.uint32), b[:n].view(np.uint32)
         diff = np.nonzero(a != b)[0]
         fa, fb = a.view(np.float32)[diff], b.view(np.float32)[diff]
-        assert np.all(np.abs(fa - fb) <= 2e-7 * np.maximum(np.abs(fb), 1e-30)), f"{len(diff)} words differ"
+        # (+ 1e-15 absolute: an exactly-zero matrix entry of one host may be 1e-20 rounding noise in the other)
+        assert np.all(np.abs(fa - fb) <= 2e-7 * np.maximum(np.abs(fb), 1e-30) + 1e-15), f"{len(diff)} words differ"
         assert len(diff) <= 8, f"{len(diff)} words differ between the C++ and the Python host"
 
 
