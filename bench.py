@@ -228,6 +228,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--spp", type=int, default=0, help="override the workload's spp (profiling under ncu only)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong-slots", "strong-tiles"],
+                    help="N > 1: weak = one seed per rank (default, the contract's line); strong-* = ONE render of the workload "
+                         "sharded over the ranks by sample slots / pixel tiles (SURVEY.md 8e), films summed by one all-reduce")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -260,9 +263,14 @@ def main():
     H, W = flat.height, flat.width
     spp = sampler.sample_count
     samples_per_step = H * W * spp
-    seed = rank     # weak scaling: one seed per rank
+    strong = args.scaling != "weak" and world > 1
+    seed = 0 if strong else rank     # weak scaling: one seed per rank
     params = scene.integrator.params(sampler, seed=seed)
     pi = ctx.pass_info(params)
+    full_params = params
+    if strong:   # this rank's share of the one wavefront (interleaved shards, whole correlate groups / whole tiles)
+        from mitsuba3dopplertof_b200.distributed import shard_params
+        params = shard_params(params, pi, world, rank, "slots" if args.scaling == "strong-slots" else "tiles", tile_pixels=64)
 
     stream = torch.cuda.current_stream()
     film = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
@@ -308,7 +316,8 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
-    value = world * samples_per_step * args.steps / (total_ms * 1e-3) / 1e6
+    jobs = 1 if strong else world     # strong scaling: the ranks share ONE render
+    value = jobs * samples_per_step * args.steps / (total_ms * 1e-3) / 1e6
 
     # ---- e2e through the host-buffer C ABI (what a plugin calls)
     anim = [(i, flat.instances[i]) for i in range(flat.desc.n_instances) if flat.instances[i].animated]
@@ -329,7 +338,7 @@ def main():
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * samples_per_step * args.steps / float(t.item()) / 1e6
+    e2e_value = jobs * samples_per_step * args.steps / float(t.item()) / 1e6
 
     if rank != 0:
         if world > 1:
@@ -343,6 +352,7 @@ def main():
     # the counters are per-sample averages: every K-th pixel (all its sample slots) is plenty, ~16 M lanes
     K = max(1, int(pi.wavefront_size // (1 << 24))) | 1
     ps = scene.integrator.params(sampler, seed=seed)
+    params = full_params   # the roofline counters describe the whole workload
     if K > 1:
         ps.shard_block, ps.shard_count, ps.shard_index = pi.spp_per_pass, K, 0
     film.zero_()
@@ -357,7 +367,8 @@ def main():
     kms = float(np.mean(kernel_ms))
     mode_name = {0: "bvh_global", 1: "bvh_smem", 2: "flat_smem"}.get(prod_mode, str(prod_mode))
     peaks, peak_src = measured_peaks()
-    achieved = bytes_per_sample * samples_per_step / (kms * 1e-3) / 1e9
+    samples_per_launch = samples_per_step / (world if strong else 1)   # rank 0's share of the render under strong scaling
+    achieved = bytes_per_sample * samples_per_launch / (kms * 1e-3) / 1e9
     clk = clocks.summary()
     issue_peak = 148 * 4 * 32 * (clk["sm_mhz"] or peaks.get("sm_max_mhz", 1965.0)) * 1e6
     traffic, ncu_issue = None, None
@@ -387,9 +398,9 @@ def main():
             "; the wavefront pipeline additionally moves its ray / hit queues and per-lane path state through HBM, "
             "which is part of `traffic`, not of the algorithmic bytes" if prod_pipeline == 1 else "")),
         "issue": {"instr_per_sample_model": instr_per_sample,
-                  "achieved_lane_instr_per_s": instr_per_sample * samples_per_step / (kms * 1e-3),
+                  "achieved_lane_instr_per_s": instr_per_sample * samples_per_launch / (kms * 1e-3),
                   "peak_lane_instr_per_s": issue_peak,
-                  "frac": instr_per_sample * samples_per_step / (kms * 1e-3) / issue_peak,
+                  "frac": instr_per_sample * samples_per_launch / (kms * 1e-3) / issue_peak,
                   "ncu_issue_active_pct": ncu_issue},
     }
 
@@ -416,11 +427,12 @@ def main():
     os.dup2(stdout_fd, 1)
     print(json.dumps({
         "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "strong" if strong else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc, "width": W, "height": H, "spp": spp, "spp_per_pass": pi.spp_per_pass,
                    "n_passes": pi.n_passes, "triangles": flat.n_triangles, "instances": flat.desc.n_instances,
-                   "seed": "rank index (multi-seed averaging)", "l2_flush": "256 MiB write between steps, outside the timed events",
+                   "seed": "0, one render sharded by " + args.scaling[7:] if strong else "rank index (multi-seed averaging)", "l2_flush": "256 MiB write between steps, outside the timed events",
                    "scene_upload_s": upload_s},
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
