@@ -934,7 +934,7 @@ struct Loader {
             if (n != 1)
                 throw Error("twosided with two different BRDFs is outside the hot-path scope");
             Bsdf b = bsdf_or_ref(*inner);
-            if (b.kind == DTOF_BSDF_DIELECTRIC || b.kind == DTOF_BSDF_THINDIELECTRIC)   // twosided.cpp:102-103
+            if (b.kind == DTOF_BSDF_DIELECTRIC || b.kind == DTOF_BSDF_THINDIELECTRIC || b.kind == DTOF_BSDF_ROUGHDIELECTRIC)   // twosided.cpp:102-103
                 throw Error("Only materials without a transmission component can be nested!");
             b.twosided = true;
             return b;
@@ -1002,6 +1002,40 @@ struct Loader {
             }
             return b;
         }
+        if (typ == "roughdielectric") {   // RoughDielectric ctor, src/bsdfs/roughdielectric.cpp:161-213
+            auto p = props(node);
+            reject_unknown(p, { "int_ior", "ext_ior", "specular_reflectance", "specular_transmittance", "distribution", "alpha", "alpha_u",
+                                "alpha_v", "sample_visible" }, "roughdielectric");
+            const float int_ior = lookup_ior(p.count("int_ior") ? p["int_ior"].value : "bk7");
+            const float ext_ior = lookup_ior(p.count("ext_ior") ? p["ext_ior"].value : "air");
+            if (int_ior < 0.f || ext_ior < 0.f || int_ior == ext_ior)
+                throw Error("The interior and exterior indices of refraction must be positive and differ!");
+            std::string distr = p.count("distribution") ? p["distribution"].value : "beckmann";
+            for (char &ch : distr)
+                ch = (char) std::tolower((unsigned char) ch);
+            if (distr != "beckmann" && distr != "ggx")
+                throw Error("Specified an invalid distribution \"" + distr + "\", must be \"beckmann\" or \"ggx\"!");
+            if (p.count("sample_visible") && !parse_bool(p["sample_visible"].value))
+                throw Error("roughdielectric with sample_visible=false is outside the hot-path scope");
+            Bsdf b;
+            b.kind = DTOF_BSDF_ROUGHDIELECTRIC;
+            b.distribution = distr == "ggx" ? 1u : 0u;
+            if (p.count("alpha_u") || p.count("alpha_v")) {
+                if (!p.count("alpha_u") || !p.count("alpha_v"))
+                    throw Error("Microfacet model: both 'alpha_u' and 'alpha_v' must be specified.");
+                if (p.count("alpha"))
+                    throw Error("Microfacet model: please specifyeither 'alpha' or 'alpha_u'/'alpha_v'.");
+                b.alpha[0] = (float) parse_float(p["alpha_u"].value), b.alpha[1] = (float) parse_float(p["alpha_v"].value);
+            } else {
+                b.alpha[0] = b.alpha[1] = p.count("alpha") ? (float) parse_float(p["alpha"].value) : 0.1f;
+            }
+            b.eta[0] = int_ior / ext_ior, b.eta[1] = b.eta[2] = 0.f;
+            for (int i = 0; i < 3; ++i) {
+                b.reflectance[i] = p.count("specular_reflectance") ? (float) p["specular_reflectance"].vec[i] : 1.f;
+                b.k[i] = p.count("specular_transmittance") ? (float) p["specular_transmittance"].vec[i] : 1.f;
+            }
+            return b;
+        }
         if (typ == "plastic") {   // SmoothPlastic ctor, src/bsdfs/plastic.cpp:157-183
             auto p = props(node);
             reject_unknown(p, { "int_ior", "ext_ior", "diffuse_reflectance", "specular_reflectance", "nonlinear" }, "plastic");
@@ -1036,7 +1070,7 @@ struct Loader {
             }
             return b;
         }
-        throw Error("bsdf type '" + typ + "' is outside the hot-path scope (diffuse|conductor|roughconductor|dielectric|thindielectric|plastic|twosided)");
+        throw Error("bsdf type '" + typ + "' is outside the hot-path scope (diffuse|conductor|roughconductor|dielectric|thindielectric|roughdielectric|plastic|twosided)");
     }
     Bsdf bsdf_or_ref(const XmlNode &node) {
         if (node.tag == "ref") {

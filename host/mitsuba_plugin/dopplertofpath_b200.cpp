@@ -242,6 +242,32 @@ private:
                         dst[0] = v[0], dst[1] = v[1], dst[2] = v[2];
                 }
             }
+        } else if (inner->class_()->name() == "RoughDielectric") {        // roughdielectric.cpp:161-238
+            b.kind = DTOF_BSDF_ROUGHDIELECTRIC;
+            Collector c;
+            const_cast<BSDF *>(inner)->traverse(&c);
+            const std::string descr = inner->to_string();              // distribution / sample_visible are not traversed
+            b.distribution = descr.find("distribution = ggx") != std::string::npos ? 1u : 0u;
+            if (descr.find("sample_visible = 0") != std::string::npos)
+                Throw("roughdielectric with sample_visible=false is outside the accelerated path");
+            b.eta[0] = (float) *c.param<ScalarFloat>("eta");
+            for (int i = 0; i < 3; ++i)
+                b.reflectance[i] = b.k[i] = 1.f;
+            for (auto &o : c.objects) {
+                const Texture<Float, Spectrum> *t = (const Texture<Float, Spectrum> *) o.second;
+                if (o.first == "alpha")
+                    b.alpha[0] = b.alpha[1] = t->eval_1(si);
+                else if (o.first == "alpha_u")
+                    b.alpha[0] = t->eval_1(si);
+                else if (o.first == "alpha_v")
+                    b.alpha[1] = t->eval_1(si);
+                else {
+                    Spectrum v = t->eval(si);
+                    float *dst = o.first == "specular_reflectance" ? b.reflectance : o.first == "specular_transmittance" ? b.k : nullptr;
+                    if (dst)
+                        dst[0] = v[0], dst[1] = v[1], dst[2] = v[2];
+                }
+            }
         } else if (inner->class_()->name() == "SmoothPlastic") {          // plastic.cpp:157-208
             b.kind = DTOF_BSDF_PLASTIC;
             Collector c;
@@ -259,7 +285,7 @@ private:
             }
         } else {
             if (inner->class_()->name() != "SmoothDiffuse")
-                Throw("BSDF \"%s\" is outside the accelerated path (diffuse | conductor | roughconductor | dielectric | thindielectric | plastic | twosided(...))", inner->class_()->name());
+                Throw("BSDF \"%s\" is outside the accelerated path (diffuse | conductor | roughconductor | dielectric | thindielectric | roughdielectric | plastic | twosided(...))", inner->class_()->name());
             Spectrum r = inner->eval_diffuse_reflectance(si);            // constant RGB reflectance
             b.reflectance[0] = r[0], b.reflectance[1] = r[1], b.reflectance[2] = r[2];
         }

@@ -86,7 +86,7 @@ typedef enum dtof_rfilter { DTOF_RFILTER_BOX = 0, DTOF_RFILTER_TENT = 1, DTOF_RF
 typedef enum dtof_shape_kind { DTOF_SHAPE_MESH = 0, DTOF_SHAPE_RECTANGLE = 1 } dtof_shape_kind;
 typedef enum dtof_bsdf_kind {
     DTOF_BSDF_DIFFUSE = 0, DTOF_BSDF_NULL_BLACK = 1, DTOF_BSDF_CONDUCTOR = 2, DTOF_BSDF_DIELECTRIC = 3,
-    DTOF_BSDF_THINDIELECTRIC = 4, DTOF_BSDF_PLASTIC = 5, DTOF_BSDF_ROUGHCONDUCTOR = 6
+    DTOF_BSDF_THINDIELECTRIC = 4, DTOF_BSDF_PLASTIC = 5, DTOF_BSDF_ROUGHCONDUCTOR = 6, DTOF_BSDF_ROUGHDIELECTRIC = 7
 } dtof_bsdf_kind;
 typedef enum dtof_emitter_kind {
     DTOF_EMITTER_POINT = 0, DTOF_EMITTER_AREA = 1, DTOF_EMITTER_CONSTANT = 2, DTOF_EMITTER_SPOT = 3
@@ -142,8 +142,9 @@ typedef struct dtof_bsdf {
                                * int_ior / ext_ior; PLASTIC: eta[1] != 0 = `nonlinear` */
     float k[3];               /* CONDUCTOR: extinction coefficient (RGB); DIELECTRIC: specular_transmittance;
                                * PLASTIC: specular_reflectance */
-    float alpha[2];           /* ROUGHCONDUCTOR: alpha_u, alpha_v (reflectance / eta / k as for CONDUCTOR) */
-    uint32_t distribution;    /* ROUGHCONDUCTOR: 0 = beckmann, 1 = ggx (MicrofacetType) */
+    float alpha[2];           /* ROUGHCONDUCTOR, ROUGHDIELECTRIC (src/bsdfs/roughdielectric.cpp; other fields as for
+                               * CONDUCTOR / DIELECTRIC): alpha_u, alpha_v */
+    uint32_t distribution;    /* ROUGHCONDUCTOR, ROUGHDIELECTRIC: 0 = beckmann, 1 = ggx (MicrofacetType) */
     uint32_t reserved;        /* 0 */
 } dtof_bsdf;
 

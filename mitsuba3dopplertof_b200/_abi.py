@@ -16,7 +16,7 @@ WAVE_SINUSOIDAL, WAVE_RECTANGULAR, WAVE_TRIANGULAR, WAVE_TRAPEZOIDAL = range(4)
 RFILTER_BOX, RFILTER_TENT, RFILTER_GAUSSIAN = range(3)
 SHAPE_MESH, SHAPE_RECTANGLE = range(2)
 BSDF_DIFFUSE, BSDF_NULL_BLACK, BSDF_CONDUCTOR, BSDF_DIELECTRIC, BSDF_THINDIELECTRIC, BSDF_PLASTIC, \
-    BSDF_ROUGHCONDUCTOR = range(7)
+    BSDF_ROUGHCONDUCTOR, BSDF_ROUGHDIELECTRIC = range(8)
 EMITTER_POINT, EMITTER_AREA, EMITTER_CONSTANT, EMITTER_SPOT = range(4)
 INTEGRATOR_DOPPLERTOFPATH, INTEGRATOR_VELOCITY, INTEGRATOR_PATH = range(3)
 

@@ -769,9 +769,12 @@ dtof_status prepare_scene(dtof_ctx *ctx, const dtof_scene_desc *sc, HostScene &H
     std::vector<uint32_t> mesh_first_gid(sc->n_meshes, 0xffffffffu);
     for (uint32_t i = 0; i < sc->n_bsdfs; ++i) {
         const dtof_bsdf &b = sc->bsdfs[i];
-        if (b.kind > DTOF_BSDF_ROUGHCONDUCTOR)
+        if (b.kind > DTOF_BSDF_ROUGHDIELECTRIC)
             return fail(ctx, DTOF_ERR_UNSUPPORTED, "bsdf kind %u is outside the hot-path scope", b.kind);
         const bool dielectric = b.kind == DTOF_BSDF_DIELECTRIC || b.kind == DTOF_BSDF_THINDIELECTRIC;
+        if (b.kind == DTOF_BSDF_ROUGHDIELECTRIC && (b.twosided || !(b.eta[0] > 0.f) || b.eta[0] == 1.f))
+            return fail(ctx, DTOF_ERR_INVALID, b.twosided ? "Only materials without a transmission component can be nested!"
+                                                          : "The interior and exterior indices of refraction must be positive and differ!");
         if (dielectric && b.twosided)
             return fail(ctx, DTOF_ERR_INVALID, "Only materials without a transmission component can be nested!");   // twosided.cpp:102-103
         if (dielectric && !(b.eta[0] > 0.f))
@@ -782,6 +785,14 @@ dtof_status prepare_scene(dtof_ctx *ctx, const dtof_scene_desc *sc, HostScene &H
                                 (b.kind == DTOF_BSDF_THINDIELECTRIC ? 16u : 0u),
                             b.eta[0], b.eta[1], b.eta[2], 0.f, b.k[0], b.k[1], b.k[2], 0.f };
         H.extended = H.extended || b.kind == DTOF_BSDF_CONDUCTOR || dielectric || b.kind == DTOF_BSDF_PLASTIC;
+        if (b.kind == DTOF_BSDF_ROUGHDIELECTRIC) {
+            if (b.distribution > 1u)
+                return fail(ctx, DTOF_ERR_INVALID, "Specified an invalid distribution, must be \"beckmann\" or \"ggx\"!");
+            BsdfRec &r = bsdfs[i];
+            r.flags |= 2u | 256u | (b.distribution == 1u ? 128u : 0u);
+            r.pad0 = std::max(b.alpha[0], 1e-4f), r.pad1 = std::max(b.alpha[1], 1e-4f);
+            H.extended = true;
+        }
         if (b.kind == DTOF_BSDF_ROUGHCONDUCTOR) {   // MicrofacetDistribution::configure: alpha >= 1e-4 (microfacet.h:420-423)
             if (b.distribution > 1u)
                 return fail(ctx, DTOF_ERR_INVALID, "Specified an invalid distribution, must be \"beckmann\" or \"ggx\"!");

@@ -86,7 +86,8 @@ struct alignas(16) BsdfRec {
                            // bit3: smooth dielectric (delta reflection + refraction), bit4: thin dielectric (+ bit3),
                            // bit5: smooth plastic (+ bit1: its diffuse base is a smooth lobe),
                            // bit6: rough conductor (+ bit1: glossy lobe), bit7: its microfacet distribution is GGX
-                           // (pad0 / pad1 = alpha_u / alpha_v)
+                           // (pad0 / pad1 = alpha_u / alpha_v), bit8: rough dielectric (+ bit1, bit7; eta_r = eta,
+                           // k = specular_transmittance)
     float eta_r, eta_g, eta_b, pad0;   // conductor: complex index of refraction eta + i k; dielectric: eta_r = int_ior / ext_ior;
                                        // plastic: eta, fdr_int, 1 / eta^2, specular sampling weight (plastic.cpp:193-208)
     float k_r, k_g, k_b, pad1;         // dielectric: specular_transmittance; plastic: specular_reflectance, nonlinear (0 / 1)

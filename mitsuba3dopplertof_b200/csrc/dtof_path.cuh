@@ -260,7 +260,63 @@ DTOF_DEV void shade_bounce(const DeviceScene &S, const float4 *__restrict__ I, c
     V3 bsdf_val = v3(0, 0, 0), bsdf_weight = v3(0, 0, 0), bs_wo = v3(0, 0, 0);
     float bsdf_pdf = 0.f, bs_pdf = 0.f;                                 // zero-initialised BSDFSample3f
     bool sampled_delta = false;
-    if (ENV && valid && (bsdf_flags & 64u)) {                            // RoughConductor::eval / pdf / sample, roughconductor.cpp:226-390
+    float bs_eta = 1.f;
+    if (ENV && valid && (bsdf_flags & 256u)) {                           // RoughDielectric::eval / pdf / sample, roughdielectric.cpp:240-490
+        const BsdfRec &br = S.bsdfs[bsdf_id];
+        Microfacet distr;
+        distr.ggx = (bsdf_flags & 128u) != 0, distr.au = br.pad0, distr.av = br.pad1;
+        const float m_eta = br.eta_r, m_inv_eta = frcp(m_eta);
+        const V3 wi = si.wi, wi_up = wi.z >= 0.f ? wi : -wi;             // mulsign(wi, cos_theta_i)
+        if (wi.z != 0.f) {
+            // ---- eval + pdf for the emitter sample
+            const bool reflect = wi.z * wo.z > 0.f;
+            const float eta = wi.z > 0.f ? m_eta : m_inv_eta, inv_eta = wi.z > 0.f ? m_inv_eta : m_eta;
+            V3 m = normalize3(wi + wo * (reflect ? 1.f : eta));
+            if (m.z < 0.f)
+                m = -m;
+            const float D = distr.eval(m), F = fresnel_r(dot3(wi, m), m_eta);
+            const float G = distr.smith_g1(wi, m) * distr.smith_g1(wo, m);
+            const float wim = dot3(wi, m), wom = dot3(wo, m), denom = wim + eta * wom;
+            if (reflect) {
+                bsdf_val = refl * fdiv(F * D * G, 4.f * fabsf(wi.z));
+            } else {
+                const float value = fabsf(fdiv(inv_eta * inv_eta * (1.f - F) * D * G * eta * eta * wim * wom, wi.z * (denom * denom)));
+                bsdf_val = v3(br.k_r * value, br.k_g * value, br.k_b * value);
+            }
+            if (wim * wi.z > 0.f && wom * wo.z > 0.f) {
+                const float dwh_dwo = reflect ? frcp(4.f * wom) : fdiv(eta * eta * wom, denom * denom);
+                float prob = fdiv(D * distr.smith_g1(wi_up, m) * fabsf(dot3(wi_up, m)), wi_up.z);
+                prob *= reflect ? F : 1.f - F;
+                bsdf_pdf = prob * fabsf(dwh_dwo);
+            }
+            // ---- sample
+            float pdf_m;
+            const V3 ms = distr.sample(wi_up, s2x, s2y, pdf_m);
+            float Fs, cos_theta_t, eta_it, eta_ti;
+            const float wims = dot3(wi, ms);
+            fresnel_dielectric(wims, m_eta, Fs, cos_theta_t, eta_it, eta_ti);
+            const bool selected_r = s1 <= Fs;
+            bs_pdf = pdf_m * (selected_r ? Fs : 1.f - Fs);
+            float dwh;
+            V3 weight;
+            if (selected_r) {
+                bs_wo = v3(fmaf(2.f * wims, ms.x, -wi.x), fmaf(2.f * wims, ms.y, -wi.y), fmaf(2.f * wims, ms.z, -wi.z));   // reflect(wi, m)
+                weight = refl;
+                dwh = frcp(4.f * dot3(bs_wo, ms));
+            } else {
+                const float c = fmaf(wims, eta_ti, cos_theta_t);          // refract(wi, m, cos_theta_t, eta_ti)
+                bs_wo = v3(fmaf(ms.x, c, -(wi.x * eta_ti)), fmaf(ms.y, c, -(wi.y * eta_ti)), fmaf(ms.z, c, -(wi.z * eta_ti)));
+                bs_eta = eta_it;
+                const float f2 = eta_ti * eta_ti;
+                weight = v3(br.k_r * f2, br.k_g * f2, br.k_b * f2);
+                const float dn = wims + bs_eta * dot3(bs_wo, ms);
+                dwh = fdiv(bs_eta * bs_eta * dot3(bs_wo, ms), dn * dn);
+            }
+            bs_pdf *= fabsf(dwh);
+            if (pdf_m != 0.f)
+                bsdf_weight = weight * distr.smith_g1(bs_wo, ms);
+        }
+    } else if (ENV && valid && (bsdf_flags & 64u)) {                            // RoughConductor::eval / pdf / sample, roughconductor.cpp:226-390
         const BsdfRec &br = S.bsdfs[bsdf_id];
         Microfacet distr;
         distr.ggx = (bsdf_flags & 128u) != 0, distr.au = br.pad0, distr.av = br.pad1;
@@ -360,7 +416,6 @@ DTOF_DEV void shade_bounce(const DeviceScene &S, const float4 *__restrict__ I, c
             sampled_delta = true;                                        // bs.sampled_type = DeltaReflection
         }
     }
-    float bs_eta = 1.f;
     bool sampled_null = false;
     if (ENV && valid && (bsdf_flags & 8u)) {     // SmoothDielectric::sample (dielectric.cpp:250-366), ThinDielectric (thindielectric.cpp:140-189)
         const BsdfRec &br = S.bsdfs[bsdf_id];

@@ -123,7 +123,7 @@ class _Loader:
                 raise ValueError("twosided with two different BRDFs is outside the hot-path scope")
             b = self.bsdf_or_ref(inner[0])
             from . import _abi
-            if b.kind in (_abi.BSDF_DIELECTRIC, _abi.BSDF_THINDIELECTRIC):   # twosided.cpp:102-103
+            if b.kind in (_abi.BSDF_DIELECTRIC, _abi.BSDF_THINDIELECTRIC, _abi.BSDF_ROUGHDIELECTRIC):   # twosided.cpp:102-103
                 raise ValueError("Only materials without a transmission component can be nested!")
             return Bsdf(b.reflectance, True, b.kind, b.eta, b.k, b.alpha, b.distribution)
         if typ == "diffuse":
@@ -172,6 +172,32 @@ class _Loader:
                 alpha = (float(p.get("alpha", 0.1)),) * 2
             return Bsdf(p.get("specular_reflectance", (1.0, 1.0, 1.0)), False, _abi.BSDF_ROUGHCONDUCTOR,
                         p.get("eta", (0.0, 0.0, 0.0)), p.get("k", (1.0, 1.0, 1.0)), alpha, 1 if distr == "ggx" else 0)
+        if typ == "roughdielectric":   # RoughDielectric ctor, src/bsdfs/roughdielectric.cpp:161-213
+            from . import _abi
+            p = self.props(node)
+            unknown = set(p) - {"int_ior", "ext_ior", "specular_reflectance", "specular_transmittance", "distribution", "alpha",
+                                "alpha_u", "alpha_v", "sample_visible"}
+            if unknown:
+                raise ValueError(f"roughdielectric: unreferenced property {sorted(unknown)}")
+            int_ior, ext_ior = lookup_ior(p.get("int_ior", "bk7")), lookup_ior(p.get("ext_ior", "air"))
+            if int_ior < 0 or ext_ior < 0 or int_ior == ext_ior:
+                raise ValueError("The interior and exterior indices of refraction must be positive and differ!")
+            distr = str(p.get("distribution", "beckmann")).lower()
+            if distr not in ("beckmann", "ggx"):
+                raise ValueError(f'Specified an invalid distribution "{distr}", must be "beckmann" or "ggx"!')
+            if not p.get("sample_visible", True):
+                raise ValueError("roughdielectric with sample_visible=false is outside the hot-path scope")
+            if "alpha_u" in p or "alpha_v" in p:
+                if "alpha_u" not in p or "alpha_v" not in p:
+                    raise ValueError("Microfacet model: both 'alpha_u' and 'alpha_v' must be specified.")
+                if "alpha" in p:
+                    raise ValueError("Microfacet model: please specifyeither 'alpha' or 'alpha_u'/'alpha_v'.")
+                alpha = (float(p["alpha_u"]), float(p["alpha_v"]))
+            else:
+                alpha = (float(p.get("alpha", 0.1)),) * 2
+            eta = float(np.float32(int_ior) / np.float32(ext_ior))
+            return Bsdf(p.get("specular_reflectance", (1.0, 1.0, 1.0)), False, _abi.BSDF_ROUGHDIELECTRIC, (eta, 0.0, 0.0),
+                        p.get("specular_transmittance", (1.0, 1.0, 1.0)), alpha, 1 if distr == "ggx" else 0)
         if typ == "plastic":   # SmoothPlastic ctor, src/bsdfs/plastic.cpp:157-183
             from . import _abi
             p = self.props(node)
@@ -197,7 +223,7 @@ class _Loader:
             return Bsdf(p.get("specular_reflectance", (1.0, 1.0, 1.0)), False,
                         _abi.BSDF_DIELECTRIC if typ == "dielectric" else _abi.BSDF_THINDIELECTRIC, (eta, 0.0, 0.0),
                         p.get("specular_transmittance", (1.0, 1.0, 1.0)))
-        raise ValueError(f"bsdf type '{typ}' is outside the hot-path scope (diffuse|conductor|roughconductor|dielectric|thindielectric|plastic|twosided)")
+        raise ValueError(f"bsdf type '{typ}' is outside the hot-path scope (diffuse|conductor|roughconductor|dielectric|thindielectric|roughdielectric|plastic|twosided)")
 
     def bsdf_or_ref(self, node) -> Bsdf:
         if node.tag == "ref":

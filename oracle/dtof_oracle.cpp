@@ -1123,7 +1123,8 @@ PathResult trace_path(const dtof_oracle_scene &sc, const dtof_params &P, const M
         float e1 = smp.next_1d(correlate), e2 = smp.next_1d(correlate);
         const dtof_bsdf *bsdf = valid ? &sc.bsdfs[sc.meshes[si.mesh].bsdf] : nullptr;
         bool smooth = bsdf && (bsdf->kind == DTOF_BSDF_DIFFUSE || bsdf->kind == DTOF_BSDF_PLASTIC ||
-                               bsdf->kind == DTOF_BSDF_ROUGHCONDUCTOR); // BSDFFlags::Smooth (diffuse or glossy lobe)
+                               bsdf->kind == DTOF_BSDF_ROUGHCONDUCTOR ||
+                               bsdf->kind == DTOF_BSDF_ROUGHDIELECTRIC); // BSDFFlags::Smooth (diffuse or glossy lobe)
         bool active_em = active_next && smooth;
         DirSample ds{};
         V3 em_weight = v3(0, 0, 0), wo = v3(0, 0, 0);
@@ -1227,7 +1228,71 @@ PathResult trace_path(const dtof_oracle_scene &sc, const dtof_params &P, const M
         V3 bsdf_val = v3(0, 0, 0), bsdf_weight = v3(0, 0, 0), bs_wo = v3(0, 0, 0);
         float bsdf_pdf = 0.f, bs_pdf = 0.f, bs_eta = 0.f; // zero-initialised BSDFSample3f when nothing is sampled
         bool sampled_delta = false;
-        if (valid && bsdf->kind == DTOF_BSDF_ROUGHCONDUCTOR) { // RoughConductor::eval / pdf / sample, roughconductor.cpp:226-390
+        if (valid && bsdf->kind == DTOF_BSDF_ROUGHDIELECTRIC) { // RoughDielectric::eval / pdf / sample, roughdielectric.cpp:240-490
+            const Microfacet distr(bsdf->distribution == 1, bsdf->alpha[0], bsdf->alpha[1]);
+            const float m_eta = bsdf->eta[0], m_inv_eta = 1.f / m_eta;
+            const V3 wi = si.wi;
+            const float cos_theta_i = wi.z;
+            const V3 spec_r = v3(bsdf->reflectance[0], bsdf->reflectance[1], bsdf->reflectance[2]);
+            const V3 spec_t = v3(bsdf->k[0], bsdf->k[1], bsdf->k[2]);
+            const V3 wi_up = cos_theta_i >= 0.f ? wi : v3(-wi.x, -wi.y, -wi.z); // mulsign(wi, cos_theta_i)
+            if (cos_theta_i != 0.f) {
+                // ---- eval + pdf for the emitter sample `wo`
+                const float cos_theta_o = wo.z;
+                const bool reflect = cos_theta_i * cos_theta_o > 0.f;
+                const float eta = cos_theta_i > 0.f ? m_eta : m_inv_eta, inv_eta = cos_theta_i > 0.f ? m_inv_eta : m_eta;
+                V3 m = normalize3(wi + wo * (reflect ? 1.f : eta));
+                if (std::signbit(m.z))
+                    m = v3(-m.x, -m.y, -m.z); // mulsign(m, cos_theta(m))
+                const float D = distr.eval(m);
+                const float F = fresnel_r(dot3(wi, m), m_eta);
+                const float G = distr.smith_g1(wi, m) * distr.smith_g1(wo, m);
+                if (reflect) {
+                    float value = F * D * G / (4.f * fabsf(cos_theta_i));
+                    bsdf_val = spec_r * value;
+                } else {
+                    float scale = inv_eta * inv_eta;
+                    float denom = dot3(wi, m) + eta * dot3(wo, m);
+                    float value = fabsf((scale * (1.f - F) * D * G * eta * eta * dot3(wi, m) * dot3(wo, m)) / (cos_theta_i * (denom * denom)));
+                    bsdf_val = spec_t * value;
+                }
+                if (dot3(wi, m) * wi.z > 0.f && dot3(wo, m) * wo.z > 0.f) { // pdf(), :432-490
+                    float denom = dot3(wi, m) + eta * dot3(wo, m);
+                    float dwh_dwo = reflect ? 1.f / (4.f * dot3(wo, m)) : (eta * eta * dot3(wo, m)) / (denom * denom);
+                    float prob = distr.eval(m) * distr.smith_g1(wi_up, m) * fabsf(dot3(wi_up, m)) / wi_up.z; // distr.pdf(wi_up, m)
+                    prob *= reflect ? F : 1.f - F;
+                    bsdf_pdf = prob * fabsf(dwh_dwo);
+                }
+                // ---- sample
+                float pdf_m;
+                V3 ms = distr.sample(wi_up, s2x, s2y, pdf_m);
+                bool ok = pdf_m != 0.f;
+                float Fs, cos_theta_t, eta_it, eta_ti;
+                fresnel_dielectric(dot3(wi, ms), m_eta, Fs, cos_theta_t, eta_it, eta_ti);
+                const bool selected_r = s1 <= Fs;
+                bs_pdf = pdf_m * (selected_r ? Fs : 1.f - Fs);
+                float dwh;
+                V3 weight;
+                if (selected_r) {
+                    float dwm = dot3(wi, ms);
+                    bs_wo = v3(fmaf(2.f * dwm, ms.x, -wi.x), fmaf(2.f * dwm, ms.y, -wi.y), fmaf(2.f * dwm, ms.z, -wi.z)); // reflect(wi, m)
+                    bs_eta = 1.f;
+                    weight = spec_r;
+                    dwh = 1.f / (4.f * dot3(bs_wo, ms));
+                } else {
+                    float c = fmaf(dot3(wi, ms), eta_ti, cos_theta_t); // refract(wi, m, cos_theta_t, eta_ti), fresnel.h:311-315
+                    bs_wo = v3(fmaf(ms.x, c, -(wi.x * eta_ti)), fmaf(ms.y, c, -(wi.y * eta_ti)), fmaf(ms.z, c, -(wi.z * eta_ti)));
+                    bs_eta = eta_it;
+                    weight = spec_t * (eta_ti * eta_ti);
+                    float denom = dot3(wi, ms) + bs_eta * dot3(bs_wo, ms);
+                    dwh = (bs_eta * bs_eta * dot3(bs_wo, ms)) / (denom * denom);
+                }
+                weight = weight * distr.smith_g1(bs_wo, ms);
+                bs_pdf *= fabsf(dwh);
+                if (ok)
+                    bsdf_weight = weight;
+            }
+        } else if (valid && bsdf->kind == DTOF_BSDF_ROUGHCONDUCTOR) { // RoughConductor::eval / pdf / sample, roughconductor.cpp:226-390
             const Microfacet distr(bsdf->distribution == 1, bsdf->alpha[0], bsdf->alpha[1]);
             V3 wi = si.wi, wo_l = wo;
             if (bsdf->twosided) {

@@ -61,6 +61,7 @@ CASES = [
     ("c11_plastic", dict(resx=40, resy=40, spp=32, hetero_frequency=0.0, max_depth=6)),  # plastic: smooth + delta lobe
     ("c12_roughconductor", dict(resx=40, resy=40, spp=32, hetero_frequency=0.0, max_depth=6)),  # microfacets
     ("c14_spot", dict(resx=40, resy=40, spp=32, hetero_frequency=0.0)),                         # spot light falloff
+    ("c15_roughdielectric", dict(resx=40, resy=40, spp=32, hetero_frequency=0.0, max_depth=8)),  # frosted glass
 ]
 
 
@@ -82,7 +83,7 @@ def test_wavefront_film_matches_fused_and_oracle(ctx, env, scene_name, kw, mode)
     ref = oracle_lib.OracleScene(flat).render(params, develop=False)
     assert np.abs(wave[..., 3] - ref[..., 3]).max() <= 1e-4 * ref[..., 3].max()
     err = np.abs(wave[..., :3] - ref[..., :3]).max(axis=2)
-    allowed = 0.005 * err.size if scene_name == "c12_roughconductor" else 0   # see test_gpu_parity.test_cuda_film_matches_oracle
+    allowed = 0.005 * err.size if scene_name in ("c12_roughconductor", "c15_roughdielectric") else 0   # see test_gpu_parity
     assert (err > 2e-4 * np.abs(ref[..., :3]).max()).sum() <= allowed
 
 
