@@ -106,6 +106,8 @@ struct PointLight {
     bool spot = false;
     float to_local[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 };
     float cutoff_angle = 0.f, beam_width = 0.f;
+    // `directional` (src/emitters/directional.cpp): `position` holds to_world * (0, 0, 1), `intensity` the irradiance
+    bool directional = false;
 };
 
 struct Film {

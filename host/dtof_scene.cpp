@@ -728,7 +728,7 @@ std::unique_ptr<FlatScene> Scene::flatten() const {
         } else {
             const PointLight &pl = emitters[o.second];
             dtof_emitter e{};
-            e.kind = pl.constant_env ? DTOF_EMITTER_CONSTANT : pl.spot ? DTOF_EMITTER_SPOT : DTOF_EMITTER_POINT;
+            e.kind = pl.constant_env ? DTOF_EMITTER_CONSTANT : pl.spot ? DTOF_EMITTER_SPOT : pl.directional ? DTOF_EMITTER_DIRECTIONAL : DTOF_EMITTER_POINT;
             if (pl.spot) {
                 memcpy(e.to_local, pl.to_local, sizeof(e.to_local));
                 e.cutoff_angle = pl.cutoff_angle, e.beam_width = pl.beam_width;
@@ -1242,10 +1242,43 @@ struct Loader {
                 sc.shapes.push_back(shape(*node));
             } else if (node->tag == "emitter") {
                 std::string typ = attr(*node, "type");
-                if (typ != "point" && typ != "constant" && typ != "spot")
-                    throw Error("emitter '" + typ + "' is outside the hot-path scope (point|spot|area|constant)");
+                if (typ != "point" && typ != "constant" && typ != "spot" && typ != "directional")
+                    throw Error("emitter '" + typ + "' is outside the hot-path scope (point|spot|directional|area|constant)");
                 auto p = props(*node);
                 PointLight pl;
+                if (typ == "directional") {   // DirectionalEmitter ctor, src/emitters/directional.cpp:65-91
+                    pl.directional = true;
+                    for (auto &kv : p)
+                        if (kv.first != "irradiance" && kv.first != "direction")
+                            throw Error("emitter 'directional': unreferenced property \"" + kv.first + "\"");
+                    bool have_tw = false;
+                    Transform4 tw = Transform4::identity();
+                    for (auto &ch : node->children) {
+                        const std::string *nm = ch->attr("name");
+                        if (ch->tag == "transform" && nm && *nm == "to_world")
+                            tw = transform(*ch), have_tw = true;
+                    }
+                    if (p.count("direction")) {
+                        if (have_tw)
+                            throw Error("Only one of the parameters 'direction' and 'to_world' can be specified at the same time!'");
+                        float d[3] = { (float) p["direction"].vec[0], (float) p["direction"].vec[1], (float) p["direction"].vec[2] };
+                        for (int rep = 0; rep < 2; ++rep) {   // normalize(direction); look_at(0, direction, up) normalises again
+                            const float inv = 1.f / std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+                            for (int i = 0; i < 3; ++i)
+                                d[i] *= inv;
+                        }
+                        memcpy(pl.position, d, sizeof(d));
+                    } else {
+                        for (int i = 0; i < 3; ++i)
+                            pl.position[i] = (float) tw.m[4 * i + 2];   // to_world.transform_affine((0, 0, 1))
+                    }
+                    if (p.count("irradiance"))
+                        for (int i = 0; i < 3; ++i)
+                            pl.intensity[i] = (float) p["irradiance"].vec[i];
+                    sc.order.emplace_back('e', (uint32_t) sc.emitters.size());
+                    sc.emitters.push_back(pl);
+                    continue;
+                }
                 if (typ == "spot") {   // SpotLight ctor, src/emitters/spot.cpp:89-114
                     pl.spot = true;
                     for (auto &kv : p)

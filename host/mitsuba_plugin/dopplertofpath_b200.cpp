@@ -417,12 +417,22 @@ private:
                 };
                 d.cutoff_angle = angle("cutoff_angle = ");
                 d.beam_width = angle("beam_width = ");
+            } else if (e->class_()->name() == "DirectionalEmitter") {      // directional.cpp:65-91, 149-176
+                d.kind = DTOF_EMITTER_DIRECTIONAL;                       // the library derives the bounding sphere itself
+                const ScalarTransform4f tw = e->world_transform();
+                for (int r = 0; r < 3; ++r)
+                    d.position[r] = tw.matrix(r, 2);                     // to_world * (0, 0, 1)
+                for (auto &o : c.objects)
+                    if (o.first == "irradiance") {
+                        Spectrum I = ((const Texture<Float, Spectrum> *) o.second)->eval(si);
+                        d.value[0] = I[0], d.value[1] = I[1], d.value[2] = I[2];
+                    }
             } else if (e->class_()->name() == "ConstantBackgroundEmitter") {
                 d.kind = DTOF_EMITTER_CONSTANT;                          // the library derives the bounding sphere itself
                 Spectrum L = e->eval(si);
                 d.value[0] = L[0], d.value[1] = L[1], d.value[2] = L[2];
             } else {
-                Throw("emitter \"%s\" is outside the accelerated path (point | spot | area | constant)", e->class_()->name());
+                Throw("emitter \"%s\" is outside the accelerated path (point | spot | directional | area | constant)", e->class_()->name());
             }
             emitters.push_back(d);
         }

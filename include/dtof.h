@@ -89,7 +89,8 @@ typedef enum dtof_bsdf_kind {
     DTOF_BSDF_THINDIELECTRIC = 4, DTOF_BSDF_PLASTIC = 5, DTOF_BSDF_ROUGHCONDUCTOR = 6, DTOF_BSDF_ROUGHDIELECTRIC = 7
 } dtof_bsdf_kind;
 typedef enum dtof_emitter_kind {
-    DTOF_EMITTER_POINT = 0, DTOF_EMITTER_AREA = 1, DTOF_EMITTER_CONSTANT = 2, DTOF_EMITTER_SPOT = 3
+    DTOF_EMITTER_POINT = 0, DTOF_EMITTER_AREA = 1, DTOF_EMITTER_CONSTANT = 2, DTOF_EMITTER_SPOT = 3,
+    DTOF_EMITTER_DIRECTIONAL = 4
 } dtof_emitter_kind;
 
 /* ---- scene description ------------------------------------------------------------------ */
@@ -155,8 +156,9 @@ typedef struct dtof_bsdf {
 typedef struct dtof_emitter {
     uint32_t kind;            /* dtof_emitter_kind */
     uint32_t mesh;            /* AREA: index of the emitting mesh (must be in the static group) */
-    float position[3];        /* POINT */
-    float value[3];           /* POINT, SPOT: intensity; AREA, CONSTANT: radiance */
+    float position[3];        /* POINT, SPOT: position; DIRECTIONAL (src/emitters/directional.cpp): the direction the light
+                               * travels in, to_world * (0, 0, 1); like CONSTANT it uses the scene's bounding sphere */
+    float value[3];           /* POINT, SPOT: intensity; AREA, CONSTANT: radiance; DIRECTIONAL: irradiance */
     /* SPOT (src/emitters/spot.cpp; no projection texture): `position` = translation of to_world; the linear part of
      * to_world^-1, row-major, takes world directions into the light's frame (it looks along +z); angles in radians:
      * the intensity ramps linearly from 0 at cutoff_angle to its full value at beam_width (spot.cpp:146-154) */

@@ -7,13 +7,13 @@ needs neither the CUDA library nor a GPU; rendering does, and fails loudly witho
 """
 from .integrator import DopplerToFPathIntegrator, DTOFError, PathIntegrator, VelocityIntegrator
 from .scene import (Bsdf, ConstantEmitter, CorrelatedSampler, Film, PerspectiveSensor, PointLight, Scene, Shape, SpotLight,
-                    cube, mesh,
+                    DirectionalLight, cube, mesh,
                     rectangle)
 from .transform import AnimatedTransform, Transform4
 from .xml_loader import load_file, load_string
 from . import tof  # noqa: E402  (tutorial post-processing and drivers; needs the renderer only when called)
 
 __all__ = [
-    "DopplerToFPathIntegrator", "VelocityIntegrator", "PathIntegrator", "DTOFError", "Bsdf", "CorrelatedSampler", "Film", "PerspectiveSensor", "PointLight", "SpotLight", "ConstantEmitter",
+    "DopplerToFPathIntegrator", "VelocityIntegrator", "PathIntegrator", "DTOFError", "Bsdf", "CorrelatedSampler", "Film", "PerspectiveSensor", "PointLight", "SpotLight", "DirectionalLight", "ConstantEmitter",
     "Scene", "Shape", "cube", "mesh", "rectangle", "AnimatedTransform", "Transform4", "load_file", "load_string", "tof",
 ]

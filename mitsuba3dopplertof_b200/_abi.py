@@ -17,7 +17,7 @@ RFILTER_BOX, RFILTER_TENT, RFILTER_GAUSSIAN = range(3)
 SHAPE_MESH, SHAPE_RECTANGLE = range(2)
 BSDF_DIFFUSE, BSDF_NULL_BLACK, BSDF_CONDUCTOR, BSDF_DIELECTRIC, BSDF_THINDIELECTRIC, BSDF_PLASTIC, \
     BSDF_ROUGHCONDUCTOR, BSDF_ROUGHDIELECTRIC = range(8)
-EMITTER_POINT, EMITTER_AREA, EMITTER_CONSTANT, EMITTER_SPOT = range(4)
+EMITTER_POINT, EMITTER_AREA, EMITTER_CONSTANT, EMITTER_SPOT, EMITTER_DIRECTIONAL = range(5)
 INTEGRATOR_DOPPLERTOFPATH, INTEGRATOR_VELOCITY, INTEGRATOR_PATH = range(3)
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED, ERR_STATE = range(6)

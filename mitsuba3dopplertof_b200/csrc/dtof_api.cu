@@ -935,10 +935,10 @@ dtof_status prepare_scene(dtof_ctx *ctx, const dtof_scene_desc *sc, HostScene &H
             r.inv_area = (float) (1.0 / sum);
         }
     }
-    bool all_point = true;
+    bool all_point = true, need_bsphere = false;
     for (uint32_t i = 0; i < sc->n_emitters; ++i) {
         const dtof_emitter &e = sc->emitters[i];
-        if (e.kind > DTOF_EMITTER_SPOT)
+        if (e.kind > DTOF_EMITTER_DIRECTIONAL)
             return fail(ctx, DTOF_ERR_UNSUPPORTED, "emitter kind %u is outside the hot-path scope", e.kind);
         if (e.kind == DTOF_EMITTER_SPOT) {   // SpotLight ctor, spot.cpp:102-112
             if (!(e.cutoff_angle >= e.beam_width) || !(e.cutoff_angle > 0.f))
@@ -952,7 +952,10 @@ dtof_status prepare_scene(dtof_ctx *ctx, const dtof_scene_desc *sc, HostScene &H
             sr.inv_transition = 1.f / (e.cutoff_angle - e.beam_width);
             H.extended = true;
         }
+        if (e.kind == DTOF_EMITTER_DIRECTIONAL)   // distant light: needs the scene's bounding sphere like the environment emitter
+            H.extended = need_bsphere = true;
         if (e.kind == DTOF_EMITTER_CONSTANT) {
+            need_bsphere = true;
             if (H.env_emitter >= 0)
                 return fail(ctx, DTOF_ERR_INVALID, "Only one environment emitter can be specified per scene.");   // scene.cpp:53-55
             H.env_emitter = (int32_t) i;
@@ -970,7 +973,7 @@ dtof_status prepare_scene(dtof_ctx *ctx, const dtof_scene_desc *sc, HostScene &H
     build_scene_bvh(groups, built);
     if (built.max_depth + built.tlas_depth + 4 > kStackSize)
         return fail(ctx, DTOF_ERR_UNSUPPORTED, "BVH too deep for the traversal stack (%d + %d)", built.max_depth, built.tlas_depth);
-    if (H.env_emitter >= 0) {
+    if (need_bsphere) {
         // Scene::bbox (scene.cpp:36): union of the shapes' boxes -- static shapes: their vertices; an instance: the 8
         // corners of its group's box under both keyframes (instance.cpp:101-114). Then ConstantBackgroundEmitter::
         // set_scene: bounding sphere, radius * (1 + RayEpsilon), at least RayEpsilon; an empty scene gives (0, 1).
@@ -1157,9 +1160,9 @@ dtof_status dtof_upload_scene(dtof_ctx *ctx, const dtof_scene_desc *sc) {
     if (H.env_emitter >= 0) {
         const dtof_emitter &e = sc->emitters[H.env_emitter];
         D.env_r = e.value[0], D.env_g = e.value[1], D.env_b = e.value[2];
-        D.env_cx = H.env_center[0], D.env_cy = H.env_center[1], D.env_cz = H.env_center[2];
-        D.env_radius = H.env_radius;
     }
+    D.env_cx = H.env_center[0], D.env_cy = H.env_center[1], D.env_cz = H.env_center[2];
+    D.env_radius = H.env_radius;
     ctx->cam = sc->camera;
     ctx->film = sc->film;
     ctx->film_px = (size_t) sc->film.width * sc->film.height;

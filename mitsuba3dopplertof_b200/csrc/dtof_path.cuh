@@ -214,6 +214,16 @@ DTOF_DEV void shade_bounce(const DeviceScene &S, const float4 *__restrict__ I, c
             const float falloff = cos_theta > sr.cos_cutoff ? beam_res : 0.f;
             const float f = falloff * (inv_dist * inv_dist);
             spec = v3(em.vr * f, em.vg * f, em.vb * f);
+        } else if (ENV && em.kind == DTOF_EMITTER_DIRECTIONAL) {        // DirectionalEmitter::sample_direction, directional.cpp:149-176
+            const V3 d = v3(em.px, em.py, em.pz);
+            V3 rel = si.p - v3(S.env_cx, S.env_cy, S.env_cz);
+            float radius = fmaxf(S.env_radius, fsqrt(dot3(rel, rel)));
+            ds_dist = 2.f * radius;
+            ds_p = si.p - d * ds_dist;
+            ds_pdf = 1.f;
+            ds_delta = true;
+            ds_d = -d;
+            spec = v3(em.vr, em.vg, em.vb);
         } else if (ENV && em.kind == DTOF_EMITTER_CONSTANT) {                  // ConstantBackgroundEmitter::sample_direction, constant.cpp:112-139
             ds_d = square_to_uniform_sphere(sx, sy);
             V3 rel = si.p - v3(S.env_cx, S.env_cy, S.env_cz);

@@ -23,7 +23,7 @@ from . import _abi
 from .transform import AnimatedTransform, Transform4, perspective_projection
 
 __all__ = [
-    "Bsdf", "Shape", "PointLight", "SpotLight", "ConstantEmitter", "Film", "CorrelatedSampler", "PerspectiveSensor", "Scene", "FlatScene",
+    "Bsdf", "Shape", "PointLight", "SpotLight", "DirectionalLight", "ConstantEmitter", "Film", "CorrelatedSampler", "PerspectiveSensor", "Scene", "FlatScene",
     "rectangle", "cube", "mesh",
 ]
 
@@ -95,6 +95,14 @@ class SpotLight:
     intensity: Sequence[float] = (1.0, 1.0, 1.0)
     cutoff_angle: float = 20.0
     beam_width: Optional[float] = None
+
+
+@dataclass
+class DirectionalLight:
+    """src/emitters/directional.cpp: distant light; `direction` is the direction the light travels in
+    (to_world * (0, 0, 1), or the normalised `direction` property)."""
+    direction: Sequence[float] = (0.0, 0.0, 1.0)
+    irradiance: Sequence[float] = (1.0, 1.0, 1.0)
 
 
 @dataclass
@@ -381,7 +389,10 @@ class Scene:
                     emitters.append(_abi.Emitter(_abi.EMITTER_AREA, mi_, (C.c_float * 3)(0, 0, 0), rgb3(s.radiance)))
             else:
                 e = self.emitters[i]
-                if isinstance(e, SpotLight):
+                if isinstance(e, DirectionalLight):
+                    emitters.append(_abi.Emitter(_abi.EMITTER_DIRECTIONAL, 0, (C.c_float * 3)(*[float(f32(x)) for x in e.direction]),
+                                                 rgb3(e.irradiance)))
+                elif isinstance(e, SpotLight):
                     m = np.asarray(e.to_world.matrix, np.float64)
                     inv = np.asarray(e.to_world.inverse_transpose, np.float64).T[:3, :3].astype(f32)   # tracked inverse
                     cutoff = f32(e.cutoff_angle)

@@ -17,7 +17,8 @@ from typing import Dict, Optional
 import numpy as np
 
 from .integrator import DopplerToFPathIntegrator, PathIntegrator, VelocityIntegrator
-from .scene import (Bsdf, ConstantEmitter, CorrelatedSampler, Film, PerspectiveSensor, PointLight, Scene, Shape, SpotLight)
+from .scene import (Bsdf, ConstantEmitter, CorrelatedSampler, DirectionalLight, Film, PerspectiveSensor, PointLight, Scene, Shape,
+                    SpotLight)
 from .transform import AnimatedTransform, Transform4
 
 __all__ = ["load_file", "load_string"]
@@ -348,9 +349,29 @@ class _Loader:
                 sc.shapes.append(self.shape(node))
             elif node.tag == "emitter":
                 typ = self.attr(node, "type")
-                if typ not in ("point", "constant", "spot"):
-                    raise ValueError(f"emitter '{typ}' is outside the hot-path scope (point|spot|area|constant)")
+                if typ not in ("point", "constant", "spot", "directional"):
+                    raise ValueError(f"emitter '{typ}' is outside the hot-path scope (point|spot|directional|area|constant)")
                 p = self.props(node)
+                if typ == "directional":   # DirectionalEmitter ctor, src/emitters/directional.cpp:65-91
+                    unknown = set(p) - {"irradiance", "direction"}
+                    if unknown:
+                        raise ValueError(f"emitter 'directional': unreferenced property {sorted(unknown)}")
+                    tw = None
+                    for ch in node:
+                        if ch.tag == "transform" and ch.get("name") == "to_world":
+                            tw = self.transform(ch)
+                    if "direction" in p:
+                        if tw is not None:
+                            raise ValueError("Only one of the parameters 'direction' and 'to_world' can be specified at the same time!'")
+                        d = np.asarray(p["direction"], np.float32)
+                        for _ in range(2):   # normalize(direction), then look_at(0, direction, up) normalises again; column 2 = d
+                            d = d * (np.float32(1) / np.sqrt(np.float32(d[0] * d[0] + d[1] * d[1] + d[2] * d[2])))
+                    else:
+                        m = np.asarray((tw or Transform4.identity()).matrix, np.float64).astype(np.float32)
+                        d = m[:3, 2]                                                   # to_world.transform_affine((0, 0, 1))
+                    order.append(("emitter", len(sc.emitters)))
+                    sc.emitters.append(DirectionalLight(tuple(float(x) for x in d), p.get("irradiance", (1.0,) * 3)))
+                    continue
                 if typ == "spot":   # SpotLight ctor, src/emitters/spot.cpp:89-114
                     unknown = set(p) - {"intensity", "cutoff_angle", "beam_width"}
                     if unknown:

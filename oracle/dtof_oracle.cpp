@@ -1154,6 +1154,17 @@ PathResult trace_path(const dtof_oracle_scene &sc, const dtof_params &P, const M
                 ds.d = ds.d * inv_dist;
                 float f = inv_dist * inv_dist;
                 spec = v3(em.value[0] * f, em.value[1] * f, em.value[2] * f);
+            } else if (em.kind == DTOF_EMITTER_DIRECTIONAL) { // DirectionalEmitter::sample_direction, directional.cpp:149-176
+                V3 d = v3(em.position[0], em.position[1], em.position[2]);
+                V3 rel = si.p - sc.env_center;
+                float radius = std::max(sc.env_radius, sqrtf(dot3(rel, rel)));
+                ds.dist = 2.f * radius;
+                ds.p = si.p - d * ds.dist;
+                ds.n = d;
+                ds.pdf = 1.f;
+                ds.delta = true;
+                ds.d = v3(-d.x, -d.y, -d.z);
+                spec = v3(em.value[0], em.value[1], em.value[2]);
             } else if (em.kind == DTOF_EMITTER_SPOT) { // SpotLight::sample_direction (spot.cpp:180-215), falloff_curve (:146-154)
                 ds.p = v3(em.position[0], em.position[1], em.position[2]);
                 ds.n = v3(0, 0, 0);
@@ -1790,10 +1801,13 @@ dtof_oracle_scene *dtof_oracle_scene_create(const dtof_scene_desc *d, int use_bv
         if (bvh && g.n_tris > 0)
             build_bvh(s->tris, g);
     }
-    for (uint32_t i = 0; i < d->n_emitters; ++i)
+    bool need_bsphere = false;
+    for (uint32_t i = 0; i < d->n_emitters; ++i) {
         if (d->emitters[i].kind == DTOF_EMITTER_CONSTANT)
             s->env_emitter = (int) i;
-    if (s->env_emitter >= 0) {
+        need_bsphere = need_bsphere || d->emitters[i].kind == DTOF_EMITTER_CONSTANT || d->emitters[i].kind == DTOF_EMITTER_DIRECTIONAL;
+    }
+    if (need_bsphere) { // ConstantBackgroundEmitter / DirectionalEmitter::set_scene (constant.cpp:73-82, directional.cpp:98-108)
         // Scene::bbox (scene.cpp:36) = union of the shapes' boxes: static shapes by their vertices, an instance by the
         // 8 corners of its group's box under both keyframes (instance.cpp:101-114); then the bounding sphere with
         // radius * (1 + RayEpsilon), at least RayEpsilon (constant.cpp:73-82); an empty scene gives ((0,0,0), 1)

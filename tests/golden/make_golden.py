@@ -78,6 +78,9 @@ CASES = {
     # rough dielectrics (frosted glass): GGX bk7 box, anisotropic Beckmann water box with tinted lobes
     "c15_roughdielectric": ("c15_roughdielectric", {"max_depth": 8, "pcd": 8}, 0, True),
     "c15_roughdielectric_homodyne": ("c15_roughdielectric", {"hetero_frequency": 0.0, "max_depth": 10, "rr_depth": 4}, 9, True),
+    # two directional (distant) lights: `direction` property and a lookat to_world; shadows through the open front
+    "c16_directional": ("c16_directional", {"max_depth": 4}, 0, True),
+    "c16_directional_homodyne": ("c16_directional", {"hetero_frequency": 0.0, "max_depth": 6, "pcd": 6, "rr_depth": 3}, 4, True),
     "c7_constant_homodyne": ("c7_constant", {"hetero_frequency": 0.0, "tsm": "uniform", "shift": 0.0, "rr_depth": 2, "max_depth": 8}, 6, True),
 }
 # the stock path tracer (src/integrators/path.cpp) on the same scenes: the integrator element is swapped (golden_util.swap_integrator)
@@ -94,6 +97,7 @@ PATH_CASES = {
     "path_c11_plastic": ("c11_plastic", {"max_depth": 6}, 4, True),
     "path_c12_roughconductor": ("c12_roughconductor", {"max_depth": 6}, 5, True),
     "path_c14_spot": ("c14_spot", {}, 6, True),
+    "path_c16_directional": ("c16_directional", {}, 8, True),
     "path_c15_roughdielectric": ("c15_roughdielectric", {"max_depth": 8}, 7, True),
 }
 # the ground-truth radial velocity integrator (src/integrators/velocity.cpp). Its value (t2 - t1) / time scales by exactly

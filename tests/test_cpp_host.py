@@ -64,6 +64,7 @@ CASES = [
     ("c13_named_metals.xml", {"max_depth": 6}),     # named conductor materials (Au, Al) from the generated table
     ("c14_spot.xml", {}),                            # spot light (lookat to_world, cutoff / beam angles)
     ("c15_roughdielectric.xml", {"max_depth": 8}),   # rough dielectrics (GGX, anisotropic Beckmann, tinted lobes)
+    ("c16_directional.xml", {}),                     # directional lights (`direction` property and lookat to_world)
 ]
 
 

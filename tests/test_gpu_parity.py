@@ -75,6 +75,7 @@ def test_cuda_full_waveform_mode_matches_oracle(ctx, name):
     ("c12_roughconductor", dict(resx=40, resy=40, spp=32, hetero_frequency=0.0, max_depth=6)),  # microfacets
     ("c14_spot", dict(resx=40, resy=40, spp=32, hetero_frequency=0.0)),                         # spot light falloff
     ("c15_roughdielectric", dict(resx=40, resy=40, spp=32, hetero_frequency=0.0, max_depth=8)),  # frosted glass
+    ("c16_directional", dict(resx=40, resy=40, spp=32, hetero_frequency=0.0)),                  # distant lights
 ])
 def test_cuda_film_matches_oracle(ctx, scene_name, kw):
     import oracle_lib

@@ -230,3 +230,24 @@ def test_named_conductor_materials_come_from_the_reference_table():
     by_kind = {b.kind: (tuple(b.eta), tuple(b.k)) for b in (flat.desc.bsdfs[i] for i in range(flat.desc.n_bsdfs))}
     np.testing.assert_allclose(by_kind[_abi.BSDF_CONDUCTOR][0], conductor_ior("Au")[0], rtol=1e-7)
     np.testing.assert_allclose(by_kind[_abi.BSDF_ROUGHCONDUCTOR][1], conductor_ior("Al")[1], rtol=1e-7)
+
+
+def test_directional_emitter_properties_follow_the_reference():
+    """DirectionalEmitter ctor (src/emitters/directional.cpp:65-91): `direction` is normalised and becomes the third column
+    of to_world; `direction` and `to_world` together throw; unknown properties are reported."""
+    base = open(os.path.join(gu.SCENES, "c16_directional.xml")).read()
+    flat = dt.load_string(base, gu.SCENES, resx=16, resy=16, spp=4).flatten()
+    assert flat.desc.n_emitters == 2
+    e0, e1 = flat.desc.emitters[0], flat.desc.emitters[1]
+    assert e0.kind == e1.kind == _abi.EMITTER_DIRECTIONAL
+    want = np.array([0.35, -1.0, -0.6]) / np.linalg.norm([0.35, -1.0, -0.6])
+    np.testing.assert_allclose(list(e0.position), want, rtol=3e-7)
+    aim = np.array([0.05, 0.8, 0.0]) - np.array([0.1, 1.1, 6.8])
+    np.testing.assert_allclose(list(e1.position), aim / np.linalg.norm(aim), rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(list(e0.value), (6, 5.5, 5), rtol=1e-7)
+    both = base.replace('<vector name="direction" value="0.35, -1.0, -0.6" />',
+                        '<vector name="direction" value="0, -1, 0" /><transform name="to_world"><translate x="1" /></transform>')
+    with pytest.raises(ValueError, match="Only one of the parameters"):
+        dt.load_string(both, gu.SCENES)
+    with pytest.raises(ValueError, match="unreferenced"):
+        dt.load_string(base.replace('<vector name="direction" value="0.35, -1.0, -0.6" />', '<float name="radius" value="1" />'), gu.SCENES)

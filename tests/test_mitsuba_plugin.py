@@ -108,6 +108,7 @@ def test_plugin_fails_loudly_without_a_gpu(tmp_path):
     ("c13_named_metals.xml", {"resx": 64, "resy": 64, "spp": 32, "hetero_frequency": 0.0, "max_depth": 6}),
     ("c14_spot.xml", {"resx": 64, "resy": 64, "spp": 32, "hetero_frequency": 0.0}),      # spot light
     ("c15_roughdielectric.xml", {"resx": 64, "resy": 64, "spp": 32, "hetero_frequency": 0.0, "max_depth": 8}),   # frosted glass
+    ("c16_directional.xml", {"resx": 64, "resy": 64, "spp": 32, "hetero_frequency": 0.0}),     # distant lights
 ])
 def test_reference_cli_renders_through_the_plugin(tmp_path, name, defs):
     """`mitsuba -m scalar_rgb scene.xml` with integrator dopplertofpath_b200 == the Python host's render of the same

@@ -62,6 +62,7 @@ CASES = [
     ("c12_roughconductor", dict(resx=40, resy=40, spp=32, hetero_frequency=0.0, max_depth=6)),  # microfacets
     ("c14_spot", dict(resx=40, resy=40, spp=32, hetero_frequency=0.0)),                         # spot light falloff
     ("c15_roughdielectric", dict(resx=40, resy=40, spp=32, hetero_frequency=0.0, max_depth=8)),  # frosted glass
+    ("c16_directional", dict(resx=40, resy=40, spp=32, hetero_frequency=0.0)),                  # distant lights
 ]
 
 
