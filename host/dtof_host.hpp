@@ -117,6 +117,8 @@ struct Film {
     std::string rfilter = "gaussian";   // src/render/film.cpp:49-54
     bool has_radius = false;
     double radius = 1.0, stddev = 0.5;
+    double mitchell_b = 1.0 / 3.0, mitchell_c = 1.0 / 3.0;   // src/rfilters/mitchell.cpp:52-60
+    int lanczos_lobes = 3;                                   // src/rfilters/lanczos.cpp:38-42
     dtof_film abi() const;
 };
 

@@ -284,10 +284,17 @@ dtof_film Film::abi() const {
     } else if (rfilter == "gaussian") {
         f.rfilter = DTOF_RFILTER_GAUSSIAN;
         f.rfilter_radius = (float) (4.0 * stddev);   // src/rfilters/gaussian.cpp:50-53
+    } else if (rfilter == "mitchell" || rfilter == "catmullrom") {
+        f.rfilter = rfilter == "mitchell" ? DTOF_RFILTER_MITCHELL : DTOF_RFILTER_CATMULLROM;
+        f.rfilter_radius = 2.f;
+    } else if (rfilter == "lanczos") {
+        f.rfilter = DTOF_RFILTER_LANCZOS;
+        f.rfilter_radius = (float) lanczos_lobes;   // src/rfilters/lanczos.cpp:38-42
     } else {
-        throw Error("rfilter '" + rfilter + "' is outside the hot-path scope (box|tent|gaussian)");
+        throw Error("rfilter '" + rfilter + "' is not a reconstruction filter (box|tent|gaussian|mitchell|catmullrom|lanczos)");
     }
     f.gaussian_stddev = (float) stddev;
+    f.mitchell_b = (float) mitchell_b, f.mitchell_c = (float) mitchell_c;
     return f;
 }
 
@@ -1198,6 +1205,19 @@ struct Loader {
                         }
                         if (rp.count("stddev"))
                             f.stddev = parse_float(rp["stddev"].value);
+                        if (rp.count("B"))
+                            f.mitchell_b = parse_float(rp["B"].value);
+                        if (rp.count("C"))
+                            f.mitchell_c = parse_float(rp["C"].value);
+                        if (rp.count("lobes"))
+                            f.lanczos_lobes = (int) parse_int(rp["lobes"].value);
+                        for (auto &kv : rp) {
+                            const std::string &k = kv.first;
+                            const bool ok = (f.rfilter == "tent" && k == "radius") || (f.rfilter == "gaussian" && k == "stddev") ||
+                                            (f.rfilter == "mitchell" && (k == "B" || k == "C")) || (f.rfilter == "lanczos" && k == "lobes");
+                            if (!ok)
+                                throw Error("rfilter '" + f.rfilter + "': unreferenced property \"" + k + "\"");
+                        }
                     }
                 s.film = f;
             }

@@ -464,11 +464,34 @@ private:
         d.film.width = film->crop_size().x(), d.film.height = film->crop_size().y();
         d.film.crop_offset_x = film->crop_offset().x(), d.film.crop_offset_y = film->crop_offset().y();
         const std::string rf = film->rfilter()->class_()->name();
-        d.film.rfilter = rf == "BoxFilter" ? DTOF_RFILTER_BOX : rf == "TentFilter" ? DTOF_RFILTER_TENT : DTOF_RFILTER_GAUSSIAN;
-        if (rf != "BoxFilter" && rf != "TentFilter" && rf != "GaussianFilter")
-            Throw("reconstruction filter \"%s\" is outside the accelerated path (box | tent | gaussian)", rf);
+        static const std::pair<const char *, uint32_t> filters[] = {
+            { "BoxFilter", DTOF_RFILTER_BOX }, { "TentFilter", DTOF_RFILTER_TENT }, { "GaussianFilter", DTOF_RFILTER_GAUSSIAN },
+            { "MitchellNetravaliFilter", DTOF_RFILTER_MITCHELL }, { "CatmullRomFilter", DTOF_RFILTER_CATMULLROM },
+            { "LanczosSincFilter", DTOF_RFILTER_LANCZOS } };
+        bool known = false;
+        for (auto &f : filters)
+            if (rf == f.first)
+                d.film.rfilter = f.second, known = true;
+        if (!known)
+            Throw("reconstruction filter \"%s\" is not one the accelerated path knows", rf);
         d.film.rfilter_radius = film->rfilter()->radius();
         d.film.gaussian_stddev = d.film.rfilter_radius / 4.f;            // gaussian.cpp:50-53: radius = 4 * stddev
+        d.film.mitchell_b = d.film.mitchell_c = 1.f / 3.f;
+        if (d.film.rfilter == DTOF_RFILTER_MITCHELL) {
+            // B and C are not traversed; to_string prints them with six decimals (mitchell.cpp:85-87). Thirds, the usual
+            // choice, are not representable in six decimals and are snapped back.
+            const std::string descr = film->rfilter()->to_string();
+            auto value = [&](const char *key) -> float {
+                size_t at = descr.find(key);
+                if (at == std::string::npos)
+                    Throw("mitchell filter: cannot read %s", key);
+                double v = std::strtod(descr.c_str() + at + strlen(key), nullptr);
+                double thirds = std::round(v * 3.0) / 3.0;
+                return (float) (std::abs(v - thirds) < 1e-6 ? thirds : v);
+            };
+            d.film.mitchell_b = value("B=");
+            d.film.mitchell_c = value("C=");
+        }
         if (dtof_upload_scene(m_ctx, &d) != DTOF_OK)
             Throw("dtof_upload_scene: %s", dtof_last_error(m_ctx));
     }

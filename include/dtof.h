@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define DTOF_ABI_VERSION 6
+#define DTOF_ABI_VERSION 7
 
 typedef struct dtof_ctx dtof_ctx;
 
@@ -82,7 +82,10 @@ typedef enum dtof_integrator_kind {
     DTOF_INTEGRATOR_PATH = 2
 } dtof_integrator_kind;
 
-typedef enum dtof_rfilter { DTOF_RFILTER_BOX = 0, DTOF_RFILTER_TENT = 1, DTOF_RFILTER_GAUSSIAN = 2 } dtof_rfilter;
+typedef enum dtof_rfilter {
+    DTOF_RFILTER_BOX = 0, DTOF_RFILTER_TENT = 1, DTOF_RFILTER_GAUSSIAN = 2,
+    DTOF_RFILTER_MITCHELL = 3, DTOF_RFILTER_CATMULLROM = 4, DTOF_RFILTER_LANCZOS = 5
+} dtof_rfilter;
 typedef enum dtof_shape_kind { DTOF_SHAPE_MESH = 0, DTOF_SHAPE_RECTANGLE = 1 } dtof_shape_kind;
 typedef enum dtof_bsdf_kind {
     DTOF_BSDF_DIFFUSE = 0, DTOF_BSDF_NULL_BLACK = 1, DTOF_BSDF_CONDUCTOR = 2, DTOF_BSDF_DIELECTRIC = 3,
@@ -175,13 +178,15 @@ typedef struct dtof_camera {
     float shutter_open, shutter_open_time;
 } dtof_camera;
 
-/* HDRFilm geometry + reconstruction filter (src/films/hdrfilm.cpp:235-297, src/rfilters/{box,tent,gaussian}.cpp). */
+/* HDRFilm geometry + reconstruction filter (src/films/hdrfilm.cpp:235-297,
+ * src/rfilters/{box,tent,gaussian,mitchell,catmullrom,lanczos}.cpp). */
 typedef struct dtof_film {
     uint32_t width, height;            /* crop size == size of the rendered tensor */
     uint32_t crop_offset_x, crop_offset_y;
     uint32_t rfilter;                  /* dtof_rfilter */
-    float rfilter_radius;              /* tent: radius; gaussian: 4*stddev; box: 0.5 */
+    float rfilter_radius;              /* tent: radius; gaussian: 4*stddev; box: 0.5; mitchell, catmullrom: 2; lanczos: lobes */
     float gaussian_stddev;
+    float mitchell_b, mitchell_c;      /* MITCHELL only (defaults 1/3, 1/3; mitchell.cpp:52-60) */
 } dtof_film;
 
 typedef struct dtof_scene_desc {

@@ -8,12 +8,12 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 # enums (include/dtof.h)
 TIME_UNIFORM, TIME_STRATIFIED, TIME_ANTITHETIC, TIME_ANTITHETIC_MIRROR = range(4)
 WAVE_SINUSOIDAL, WAVE_RECTANGULAR, WAVE_TRIANGULAR, WAVE_TRAPEZOIDAL = range(4)
-RFILTER_BOX, RFILTER_TENT, RFILTER_GAUSSIAN = range(3)
+RFILTER_BOX, RFILTER_TENT, RFILTER_GAUSSIAN, RFILTER_MITCHELL, RFILTER_CATMULLROM, RFILTER_LANCZOS = range(6)
 SHAPE_MESH, SHAPE_RECTANGLE = range(2)
 BSDF_DIFFUSE, BSDF_NULL_BLACK, BSDF_CONDUCTOR, BSDF_DIELECTRIC, BSDF_THINDIELECTRIC, BSDF_PLASTIC, \
     BSDF_ROUGHCONDUCTOR, BSDF_ROUGHDIELECTRIC = range(8)
@@ -67,6 +67,7 @@ class Film(C.Structure):
         ("width", C.c_uint32), ("height", C.c_uint32),
         ("crop_offset_x", C.c_uint32), ("crop_offset_y", C.c_uint32),
         ("rfilter", C.c_uint32), ("rfilter_radius", C.c_float), ("gaussian_stddev", C.c_float),
+        ("mitchell_b", C.c_float), ("mitchell_c", C.c_float),
     ]
 
 

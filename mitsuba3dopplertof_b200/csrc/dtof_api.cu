@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(kBlock, DTOF_MIN_CTAS) render_kernel(const __g
                     if (uniform && A.film.rfilter == DTOF_RFILTER_TENT && A.film.n == 1)
                         splat_tent3_warp(A.film, lx, ly, spx, spy, rgb, lane_on, lane);
                     else if (lane_on)
-                        splat_generic(A.film, spx, spy, rgb);
+                        splat_generic<ENV>(A.film, spx, spy, rgb);
                 }
             }
         }
@@ -649,6 +649,7 @@ dtof_status launch_render(dtof_ctx *ctx, const dtof_params *p, float *d_rgbw, cu
     F.g_alpha = -1.f / (2.f * ctx->film.gaussian_stddev * ctx->film.gaussian_stddev);
     F.g_bias = expf(F.g_alpha * F.radius * F.radius);
     F.n = (int) ceilf(F.radius - .5f);
+    F.mitchell_b = ctx->film.mitchell_b, F.mitchell_c = ctx->film.mitchell_c;
     A.work_counter = ctx->d_counter;
     A.stats = ctx->d_stats;
     A.rec_lanes = d_lanes;
@@ -752,10 +753,11 @@ struct HostScene {
 dtof_status prepare_scene(dtof_ctx *ctx, const dtof_scene_desc *sc, HostScene &H) {
     if (sc->film.width == 0 || sc->film.height == 0)
         return fail(ctx, DTOF_ERR_INVALID, "empty film");
-    if (sc->film.rfilter > DTOF_RFILTER_GAUSSIAN)
+    if (sc->film.rfilter > DTOF_RFILTER_LANCZOS)
         return fail(ctx, DTOF_ERR_INVALID, "unknown rfilter %u", sc->film.rfilter);
     if (sc->film.rfilter != DTOF_RFILTER_BOX && !(sc->film.rfilter_radius > 0.f && sc->film.rfilter_radius <= 7.5f))
         return fail(ctx, DTOF_ERR_INVALID, "rfilter radius out of range");
+    H.extended = sc->film.rfilter >= DTOF_RFILTER_MITCHELL;   // filters with negative lobes live in the ENV = true instantiations
     // ---- validate + flatten
     std::vector<MeshRec> &meshes = H.meshes;
     std::vector<BsdfRec> &bsdfs = H.bsdfs;

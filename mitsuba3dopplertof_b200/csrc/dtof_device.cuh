@@ -973,16 +973,45 @@ struct FilmParams {
     uint32_t width, height, crop_x, crop_y, rfilter;
     float radius, inv_radius, g_alpha, g_bias;
     int n;                     // ceil(radius - .5)
+    float mitchell_b, mitchell_c;
 };
 
-DTOF_DEV float rfilter_eval(const FilmParams &F, float x) {
+// The filters with negative lobes (src/rfilters/{mitchell,catmullrom,lanczos}.cpp). Out of line, and reachable only from
+// the LOBED = true instantiations (a film with such a filter makes the scene "extended", the kernels' ENV parameter): the
+// common kernels' code must stay as it is.
+__device__ __noinline__ float rfilter_eval_lobed(uint32_t kind, float radius, float B, float Cc, float x) {
+    x = fabsf(x);
+    if (kind == DTOF_RFILTER_LANCZOS) {            // LanczosSincFilter::eval, lanczos.cpp:44-54 (radius = lobes)
+        float x1 = 3.14159265358979323846f * x, x2 = x1 / radius, s1, s2, c;
+        dr_sincos(x1, s1, c);
+        dr_sincos(x2, s2, c);
+        float result = (s1 * s2) / (x1 * x2);
+        return x < 0x1p-24f ? 1.f : (x > radius ? 0.f : result);
+    }
+    float x2 = x * x, x3 = x2 * x, result;
+    if (kind == DTOF_RFILTER_MITCHELL) {           // MitchellNetravaliFilter::eval, mitchell.cpp:62-83
+        const float a3 = 12.f - 9.f * B - 6.f * Cc, a2 = -18.f + 12.f * B + 6.f * Cc, a0 = 6.f - 2.f * B;
+        const float b3 = -B - 6.f * Cc, b2 = 6.f * B + 30.f * Cc, b1 = -12.f * B - 48.f * Cc, b0 = 8.f * B + 24.f * Cc;
+        result = (1.f / 6.f) * (x < 1.f ? fmaf(a3, x3, fmaf(a2, x2, a0)) : fmaf(b3, x3, fmaf(b2, x2, fmaf(b1, x, b0))));
+    } else {                                       // CatmullRomFilter::eval, catmullrom.cpp:40-55 (B = 0, C = 1/2, no fused ops)
+        B = 0.f, Cc = .5f;
+        result = (1.f / 6.f) * (x < 1.f ? (12.f - 9.f * B - 6.f * Cc) * x3 + (-18.f + 12.f * B + 6.f * Cc) * x2 + (6.f - 2.f * B)
+                                        : (-B - 6.f * Cc) * x3 + (6.f * B + 30.f * Cc) * x2 + (-12.f * B - 48.f * Cc) * x +
+                                              (8.f * B + 24.f * Cc));
+    }
+    return x < 2.f ? result : 0.f;
+}
+
+template <bool LOBED = false> DTOF_DEV float rfilter_eval(const FilmParams &F, float x) {
     if (F.rfilter == DTOF_RFILTER_TENT)
         return fmaxf(0.f, 1.f - fabsf(x * F.inv_radius));
+    if (LOBED && F.rfilter >= DTOF_RFILTER_MITCHELL)
+        return rfilter_eval_lobed(F.rfilter, F.radius, F.mitchell_b, F.mitchell_c, x);
     return fmaxf(0.f, expf(F.g_alpha * x * x) - F.g_bias);
 }
 
 // generic path: per-lane atomics (any filter, lanes of a warp on different pixels)
-DTOF_DEV void splat_generic(const FilmParams &F, float px, float py, V3 rgb) {
+template <bool LOBED> DTOF_DEV void splat_generic(const FilmParams &F, float px, float py, V3 rgb) {
     if (F.rfilter == DTOF_RFILTER_BOX) {
         int x = (int) floorf(px) - (int) F.crop_x, y = (int) floorf(py) - (int) F.crop_y;
         if ((uint32_t) x < F.width && (uint32_t) y < F.height) {
@@ -999,14 +1028,14 @@ DTOF_DEV void splat_generic(const FilmParams &F, float px, float py, V3 rgb) {
     float rx = (float) pix + .5f - px, ry0 = (float) piy + .5f - py;
     int lx = pix - (int) F.crop_x, ly = piy - (int) F.crop_y;
     for (int xs = 0; xs < count; ++xs) {
-        float wx = rfilter_eval(F, rx);
+        float wx = rfilter_eval<LOBED>(F, rx);
         rx += 1.f;
         uint32_t x = (uint32_t) (lx + xs);
         if (x >= F.width)
             continue;
         float ry = ry0;
         for (int ys = 0; ys < count; ++ys) {
-            float wy = rfilter_eval(F, ry);
+            float wy = rfilter_eval<LOBED>(F, ry);
             ry += 1.f;
             uint32_t y = (uint32_t) (ly + ys);
             if (y >= F.height)

@@ -497,7 +497,7 @@ __global__ void __launch_bounds__(kWfBlock) wf_splat_kernel(const __grid_constan
         if (uniform && A.film.rfilter == DTOF_RFILTER_TENT && A.film.n == 1)
             splat_tent3_warp(A.film, lx, ly, spx, spy, rgb, lane_on, lane);
         else if (lane_on)
-            splat_generic(A.film, spx, spy, rgb);
+            splat_generic<true>(A.film, spx, spy, rgb);
     }
 }
 

@@ -122,20 +122,28 @@ class Film:
     rfilter: str = "gaussian"          # film.cpp:49-54: default reconstruction filter is 'gaussian'
     rfilter_radius: Optional[float] = None   # tent 'radius' (default 1)
     gaussian_stddev: float = 0.5
+    mitchell_b: float = 1.0 / 3.0      # mitchell 'B', 'C' (src/rfilters/mitchell.cpp:52-60)
+    mitchell_c: float = 1.0 / 3.0
+    lanczos_lobes: int = 3             # lanczos 'lobes' = its radius (src/rfilters/lanczos.cpp:38-42)
 
     def abi(self) -> _abi.Film:
         cw, ch = self.crop_size if self.crop_size is not None else (self.width, self.height)
-        kinds = {"box": _abi.RFILTER_BOX, "tent": _abi.RFILTER_TENT, "gaussian": _abi.RFILTER_GAUSSIAN}
+        kinds = {"box": _abi.RFILTER_BOX, "tent": _abi.RFILTER_TENT, "gaussian": _abi.RFILTER_GAUSSIAN,
+                 "mitchell": _abi.RFILTER_MITCHELL, "catmullrom": _abi.RFILTER_CATMULLROM, "lanczos": _abi.RFILTER_LANCZOS}
         if self.rfilter not in kinds:
-            raise ValueError(f"rfilter '{self.rfilter}' is outside the hot-path scope (box|tent|gaussian)")
+            raise ValueError(f"rfilter '{self.rfilter}' is not a reconstruction filter (box|tent|gaussian|mitchell|catmullrom|lanczos)")
         if self.rfilter == "box":
             radius = 0.5
         elif self.rfilter == "tent":
             radius = 1.0 if self.rfilter_radius is None else float(self.rfilter_radius)
+        elif self.rfilter in ("mitchell", "catmullrom"):
+            radius = 2.0
+        elif self.rfilter == "lanczos":
+            radius = float(int(self.lanczos_lobes))
         else:
             radius = 4.0 * float(self.gaussian_stddev)     # src/rfilters/gaussian.cpp:50-53
         return _abi.Film(int(cw), int(ch), int(self.crop_offset[0]), int(self.crop_offset[1]), kinds[self.rfilter],
-                         radius, float(self.gaussian_stddev))
+                         radius, float(self.gaussian_stddev), float(self.mitchell_b), float(self.mitchell_c))
 
 
 @dataclass

@@ -307,6 +307,13 @@ class _Loader:
                         rp = self.props(rf)
                         f.rfilter_radius = rp.get("radius")
                         f.gaussian_stddev = float(rp.get("stddev", 0.5))
+                        f.mitchell_b = float(rp.get("B", 1.0 / 3.0))
+                        f.mitchell_c = float(rp.get("C", 1.0 / 3.0))
+                        f.lanczos_lobes = int(rp.get("lobes", 3))
+                        allowed = {"tent": {"radius"}, "gaussian": {"stddev"}, "mitchell": {"B", "C"}, "lanczos": {"lobes"}}
+                        unknown = set(rp) - allowed.get(f.rfilter, set())
+                        if unknown:
+                            raise ValueError(f"rfilter '{f.rfilter}': unreferenced property {sorted(unknown)}")
                 s.film = f
         s.fov = float(p.pop("fov", 45.0)) if "fov" in p else s.fov
         s.fov_axis = p.pop("fov_axis", "x")

@@ -1511,9 +1511,13 @@ inline void camera_ray(const dtof_camera &c, float u, float v, V3 &o, V3 &d, flo
 
 struct FilmSplat {
     float radius, inv_radius, g_alpha, g_bias;
+    float ma3 = 0, ma2 = 0, ma0 = 0, mb3 = 0, mb2 = 0, mb1 = 0, mb0 = 0;   // Mitchell-Netravali polynomial coefficients
     uint32_t kind, w, h;
     int ox, oy;
     explicit FilmSplat(const dtof_film &f) {
+        const float B = f.mitchell_b, Cc = f.mitchell_c;                  // mitchell.cpp:66-72
+        ma3 = 12.f - 9.f * B - 6.f * Cc, ma2 = -18.f + 12.f * B + 6.f * Cc, ma0 = 6.f - 2.f * B;
+        mb3 = -B - 6.f * Cc, mb2 = 6.f * B + 30.f * Cc, mb1 = -12.f * B - 48.f * Cc, mb0 = 8.f * B + 24.f * Cc;
         kind = f.rfilter;
         radius = f.rfilter_radius;
         inv_radius = 1.f / radius;
@@ -1527,6 +1531,29 @@ struct FilmSplat {
     float eval(float x) const {
         if (kind == DTOF_RFILTER_TENT) // TentFilter::eval, src/rfilters/tent.cpp:53-55
             return std::max(0.f, 1.f - fabsf(x * inv_radius));
+        if (kind == DTOF_RFILTER_MITCHELL) { // MitchellNetravaliFilter::eval, src/rfilters/mitchell.cpp:62-83
+            x = fabsf(x);
+            float x2 = x * x, x3 = x2 * x;
+            float result = (1.f / 6.f) * (x < 1.f ? fmaf(ma3, x3, fmaf(ma2, x2, ma0)) : fmaf(mb3, x3, fmaf(mb2, x2, fmaf(mb1, x, mb0))));
+            return x < 2.f ? result : 0.f;
+        }
+        if (kind == DTOF_RFILTER_CATMULLROM) { // CatmullRomFilter::eval, src/rfilters/catmullrom.cpp:40-55 (B = 0, C = 1/2)
+            x = fabsf(x);
+            float x2 = x * x, x3 = x2 * x;
+            const float B = 0.f, Cc = .5f;
+            float result = (1.f / 6.f) * (x < 1.f ? (12.f - 9.f * B - 6.f * Cc) * x3 + (-18.f + 12.f * B + 6.f * Cc) * x2 + (6.f - 2.f * B)
+                                                  : (-B - 6.f * Cc) * x3 + (6.f * B + 30.f * Cc) * x2 + (-12.f * B - 48.f * Cc) * x +
+                                                        (8.f * B + 24.f * Cc));
+            return x < 2.f ? result : 0.f;
+        }
+        if (kind == DTOF_RFILTER_LANCZOS) { // LanczosSincFilter::eval, src/rfilters/lanczos.cpp:44-54 (radius = lobes)
+            x = fabsf(x);
+            float x1 = 3.14159265358979323846f * x, x2 = x1 / radius, s1, s2, c;
+            dr_sincos(x1, s1, c);
+            dr_sincos(x2, s2, c);
+            float result = (s1 * s2) / (x1 * x2);
+            return x < 0x1p-24f ? 1.f : (x > radius ? 0.f : result);
+        }
         // GaussianFilter (src/rfilters/gaussian.cpp:94-103): exp(alpha x^2) - exp(alpha r^2), clamped at 0
         return std::max(0.f, expf(g_alpha * x * x) - g_bias);
     }
@@ -1687,6 +1714,7 @@ uint32_t dtof_oracle_permute_kensler(uint32_t index, uint32_t sample_count, uint
     return permute_kensler(index, sample_count, seed);
 }
 void dtof_oracle_sincos(float x, float *s, float *c) { dr_sincos(x, *s, *c); }
+float dtof_oracle_rfilter_eval(const dtof_film *film, float x) { return FilmSplat(*film).eval(x); }
 float dtof_oracle_waveform_lowpass(float t, uint32_t type) { return waveform_lowpass(t, type); }
 float dtof_oracle_waveform(float t, uint32_t type) { return waveform_full(t, type); }
 float dtof_oracle_modulation_weight(const dtof_params *p, float ray_time, float path_length) {

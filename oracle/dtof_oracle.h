@@ -33,6 +33,8 @@ void dtof_oracle_pcg32(uint64_t initstate, uint64_t initseq, uint32_t n, uint32_
                        uint64_t *state_inc_after_seed /* [2] */);
 uint32_t dtof_oracle_permute_kensler(uint32_t index, uint32_t sample_count, uint32_t seed);
 void dtof_oracle_sincos(float x, float *s, float *c);
+/* ReconstructionFilter::eval of the film's filter (src/rfilters/*.cpp); box filters are not evaluated by the film */
+float dtof_oracle_rfilter_eval(const dtof_film *film, float x);
 float dtof_oracle_waveform_lowpass(float t, uint32_t type);
 float dtof_oracle_waveform(float t, uint32_t type);
 float dtof_oracle_modulation_weight(const dtof_params *p, float ray_time, float path_length);

@@ -32,6 +32,7 @@ def lib() -> C.CDLL:
             "dtof_oracle_pcg32": (None, [u64, u64, u32, C.POINTER(u32), fp, C.POINTER(u64)]),
             "dtof_oracle_permute_kensler": (u32, [u32, u32, u32]),
             "dtof_oracle_sincos": (None, [f, fp, fp]),
+            "dtof_oracle_rfilter_eval": (f, [C.POINTER(_abi.Film), f]),
             "dtof_oracle_waveform_lowpass": (f, [f, u32]),
             "dtof_oracle_waveform": (f, [f, u32]),
             "dtof_oracle_modulation_weight": (f, [C.POINTER(_abi.Params), f, f]),

@@ -136,6 +136,40 @@ def test_reference_cli_renders_through_the_plugin(tmp_path, name, defs):
 
 @pytest.mark.gpu
 @needs_runtime
+@pytest.mark.parametrize("rfilter", [
+    '<rfilter type="mitchell" />',
+    '<rfilter type="mitchell"><float name="B" value="0.2" /><float name="C" value="0.6" /></rfilter>',
+    '<rfilter type="catmullrom" />',
+    '<rfilter type="lanczos"><integer name="lobes" value="2" /></rfilter>',
+    '<rfilter type="gaussian"><float name="stddev" value="0.8" /></rfilter>',
+])
+def test_reference_cli_filters_through_the_plugin(tmp_path, rfilter):
+    """The film's reconstruction filter as the reference's scene graph holds it (class name, radius, Mitchell's B / C)
+    reaches the kernels like the Python host's reading of the same XML."""
+    if not _runnable():
+        pytest.skip("reference runtime cannot execute on this CPU")
+    src = open(os.path.join(SCENES, "c1_example.xml")).read()
+    assert '<rfilter type="tent" />' in src
+    plain = os.path.join(str(tmp_path), "plain.xml")
+    open(plain, "w").write(src.replace('<rfilter type="tent" />', rfilter))
+    scene_path = _plugin_scene(tmp_path, "c1_example.xml")
+    xml = open(scene_path).read().replace('<rfilter type="tent" />', rfilter)
+    open(scene_path, "w").write(xml)
+    defs = {"resx": 48, "resy": 48, "spp": 32}
+    out = os.path.join(str(tmp_path), "out.pfm")
+    r = _run([f"-D{k}={v}" for k, v in defs.items()] + ["-o", out, scene_path])
+    assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
+    img = _read_pfm(out)
+    scene = dt.load_file(plain, **defs)
+    ref = scene.integrator.render(scene, seed=0)
+    assert img.shape == ref.shape
+    scale = np.abs(ref).max()
+    err = np.abs(img - ref).max(axis=2)
+    assert int((err > 2e-4 * scale).sum()) <= 1e-3 * err.size, f"max {err.max():.3e}, scale {scale:.3e}"
+
+
+@pytest.mark.gpu
+@needs_runtime
 def test_plugin_image_agrees_with_the_reference_integrator(tmp_path):
     """Same executable, same scene file, integrator `dopplertofpath` (the reference's CPU code) vs `dopplertofpath_b200`.
     The scalar reference is not stream-identical (per-pixel seeding, no pair correlation), so the check
