@@ -1185,6 +1185,11 @@ struct Loader {
                 auto fp = props(*ch);
                 reject_unknown(fp, { "width", "height", "crop_width", "crop_height", "crop_offset_x", "crop_offset_y", "file_format",
                                      "pixel_format", "component_format", "sample_border", "compensate" }, "hdrfilm");
+                // sample_border (film.cpp:35, integrator.cpp:176-178) would change the border pixels if ignored: refuse
+                if (fp.count("sample_border") && parse_bool(fp["sample_border"].value))
+                    throw Error("hdrfilm: sample_border=true is outside the hot-path scope");
+                if (fp.count("pixel_format") && fp["pixel_format"].value != "rgb")
+                    throw Error("hdrfilm: only pixel_format=\"rgb\" is inside the hot-path scope");
                 Film f;
                 if (fp.count("width")) f.width = (uint32_t) parse_int(fp["width"].value);
                 if (fp.count("height")) f.height = (uint32_t) parse_int(fp["height"].value);

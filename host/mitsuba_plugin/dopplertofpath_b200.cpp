@@ -463,6 +463,8 @@ private:
         d.camera.shutter_open = sensor->shutter_open(), d.camera.shutter_open_time = sensor->shutter_open_time();
         d.film.width = film->crop_size().x(), d.film.height = film->crop_size().y();
         d.film.crop_offset_x = film->crop_offset().x(), d.film.crop_offset_y = film->crop_offset().y();
+        if (film->sample_border())   // integrator.cpp:176-178 samples a larger region then; not built, do not ignore it
+            Throw("a film with sample_border=true is outside the accelerated path");
         const std::string rf = film->rfilter()->class_()->name();
         static const std::pair<const char *, uint32_t> filters[] = {
             { "BoxFilter", DTOF_RFILTER_BOX }, { "TentFilter", DTOF_RFILTER_TENT }, { "GaussianFilter", DTOF_RFILTER_GAUSSIAN },

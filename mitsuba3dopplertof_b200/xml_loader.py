@@ -297,7 +297,13 @@ class _Loader:
                 if "crop_width" in fp or "crop_height" in fp:
                     f.crop_size = (int(fp.pop("crop_width", f.width)), int(fp.pop("crop_height", f.height)))
                     f.crop_offset = (int(fp.pop("crop_offset_x", 0)), int(fp.pop("crop_offset_y", 0)))
-                for k in ("file_format", "pixel_format", "component_format", "sample_border", "compensate"):
+                # sample_border (film.cpp:35, integrator.cpp:176-178) enlarges the sampled region by the filter's border: not
+                # built, and silently ignoring it would change the border pixels -- refuse. The kernels produce RGB (+ weight).
+                if fp.pop("sample_border", False):
+                    raise ValueError("hdrfilm: sample_border=true is outside the hot-path scope")
+                if fp.pop("pixel_format", "rgb") != "rgb":
+                    raise ValueError("hdrfilm: only pixel_format=\"rgb\" is inside the hot-path scope")
+                for k in ("file_format", "component_format", "compensate"):
                     fp.pop(k, None)
                 if fp:
                     raise ValueError(f"hdrfilm: unreferenced property {sorted(fp)}")

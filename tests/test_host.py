@@ -251,3 +251,29 @@ def test_directional_emitter_properties_follow_the_reference():
         dt.load_string(both, gu.SCENES)
     with pytest.raises(ValueError, match="unreferenced"):
         dt.load_string(base.replace('<vector name="direction" value="0.35, -1.0, -0.6" />', '<float name="radius" value="1" />'), gu.SCENES)
+
+
+def test_film_options_that_would_change_the_image_are_refused():
+    """sample_border (film.cpp:35, integrator.cpp:176-178) and a non-RGB pixel_format change what the reference writes;
+    they are not built, and both hosts refuse them instead of ignoring them."""
+    import subprocess
+    base = open(os.path.join(gu.SCENES, "c1_example.xml")).read()
+    fmt = '<string name="pixel_format" value="rgb" />'
+    assert fmt in base
+    border = base.replace(fmt, fmt + '<boolean name="sample_border" value="true" />')
+    lum = base.replace(fmt, '<string name="pixel_format" value="luminance" />')
+    off = base.replace(fmt, fmt + '<boolean name="sample_border" value="false" />')
+    dt.load_string(off, gu.SCENES)
+    with pytest.raises(ValueError, match="sample_border"):
+        dt.load_string(border, gu.SCENES)
+    with pytest.raises(ValueError, match="pixel_format"):
+        dt.load_string(lum, gu.SCENES)
+    cli = os.path.join(ROOT, "host", "dtof_render")
+    assert subprocess.run(["make", "-C", os.path.join(ROOT, "host")], capture_output=True).returncode == 0
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        for xml, word in ((border, "sample_border"), (lum, "pixel_format")):
+            path = os.path.join(tmp, "s.xml")
+            open(path, "w").write(xml)
+            r = subprocess.run([cli, "--dump-desc", os.path.join(tmp, "d.bin"), path], capture_output=True, text=True)
+            assert r.returncode == 1 and word in r.stderr
