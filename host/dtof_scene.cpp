@@ -486,8 +486,15 @@ dtof_params DopplerToFPathIntegrator::params(const CorrelatedSampler &s, uint32_
     p.path_correlate_number = s.path_correlate_number;
     p.seed = seed;
     p.integrator = kind;
-    if (kind == DTOF_INTEGRATOR_DOPPLERTOFPATH && !s.correlated)
-        throw Error("dopplertofpath is driven by the 'correlated' sampler (README.md:61)");
+    if (kind == DTOF_INTEGRATOR_DOPPLERTOFPATH && !s.correlated) {
+        // the base-class next_1d_time / next_*_correlate (sampler.h:131-144) draw from the one independent stream: the
+        // correlated sampler's `rng` stream under uniform time sampling without path correlation (correlated.cpp:92-97)
+        p.time_sampling_method = DTOF_TIME_UNIFORM;
+        p.use_stratified_sampling_for_each_interval = 0;
+        p.path_correlation_depth = 0;
+        p.time_correlate_number = p.path_correlate_number = 1;
+        return p;
+    }
     if (time_sampling_method == DTOF_TIME_ANTITHETIC_MIRROR && s.time_correlate_number != 2)
         throw Error("antithetic_mirror requires time_correlate_number == 2");   // correlated.cpp:141-142
     if (s.time_correlate_number < 1 || s.path_correlate_number < 1)
@@ -1369,8 +1376,6 @@ struct Loader {
                 throw Error("Unused parameter \"" + k + "\"!");   // xml.cpp:1069
         if (!have_integrator)
             throw Error("scene has no integrator");
-        if (sc.integrator.kind == DTOF_INTEGRATOR_DOPPLERTOFPATH && !sc.sensor.sampler.correlated)
-            throw Error("dopplertofpath is driven by the 'correlated' sampler (README.md:61)");
         return sc;
     }
 };

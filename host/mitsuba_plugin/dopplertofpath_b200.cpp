@@ -133,14 +133,23 @@ public:
         const Sampler *sampler = sensor->sampler();
         p.sample_count = spp ? spp : sampler->sample_count();            // integrator.cpp:121-124
         p.base_seed = SamplerPeek<Float, Spectrum>::base_seed(sampler);   // sampler.cpp:13-14
-        if (sampler->class_()->name() != "CorrelatedSampler")
-            Throw("dopplertofpath_b200 needs the 'correlated' sampler (got %s)", sampler->class_()->name());
-        auto *cs = reinterpret_cast<const CorrelatedSamplerLayout<Float, Spectrum> *>(sampler);
-        p.time_correlate_number = (uint32_t) cs->m_time_correlate_number;   // correlated.cpp:18-19
-        p.path_correlate_number = (uint32_t) cs->m_path_correlate_number;
-        if (p.time_correlate_number - 1u > 4095u || p.path_correlate_number - 1u > 4095u)
-            Throw("implausible correlate numbers (%u, %u): the CorrelatedSampler layout differs from the mirrored one",
-                  p.time_correlate_number, p.path_correlate_number);
+        if (sampler->class_()->name() == "IndependentSampler") {
+            // base-class next_1d_time / next_*_correlate (sampler.h:131-144): one independent stream, i.e. the correlated
+            // sampler's `rng` stream under uniform time sampling without path correlation (correlated.cpp:92-97, 156-161)
+            p.time_sampling_method = DTOF_TIME_UNIFORM;
+            p.use_stratified_sampling_for_each_interval = 0;
+            p.path_correlation_depth = 0;
+            p.time_correlate_number = p.path_correlate_number = 1;
+        } else {
+            if (sampler->class_()->name() != "CorrelatedSampler")
+                Throw("dopplertofpath_b200 needs the 'correlated' or 'independent' sampler (got %s)", sampler->class_()->name());
+            auto *cs = reinterpret_cast<const CorrelatedSamplerLayout<Float, Spectrum> *>(sampler);
+            p.time_correlate_number = (uint32_t) cs->m_time_correlate_number;   // correlated.cpp:18-19
+            p.path_correlate_number = (uint32_t) cs->m_path_correlate_number;
+            if (p.time_correlate_number - 1u > 4095u || p.path_correlate_number - 1u > 4095u)
+                Throw("implausible correlate numbers (%u, %u): the CorrelatedSampler layout differs from the mirrored one",
+                      p.time_correlate_number, p.path_correlate_number);
+        }
         p.seed = seed;
 
         ScalarVector2u size = film->crop_size();

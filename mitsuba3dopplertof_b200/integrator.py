@@ -122,7 +122,15 @@ class DopplerToFPathIntegrator:
         p.lane_begin, p.lane_end = int(lane_begin), int(lane_end)
         p.integrator = self.KIND
         if self.KIND == _abi.INTEGRATOR_DOPPLERTOFPATH and getattr(sampler, "kind", "correlated") != "correlated":
-            raise ValueError("dopplertofpath is driven by the 'correlated' sampler (README.md:61)")
+            # Any other sampler answers the Doppler branch's calls with the base-class defaults (include/mitsuba/render/
+            # sampler.h:131-144): next_1d_time, next_1d_correlate and next_2d_correlate all draw from the one independent
+            # stream whatever strategy / correlate flag is passed. That is the correlated sampler's `rng` stream under
+            # uniform time sampling with no path correlation (correlated.cpp:92-97, 156-161): same seeding, same order.
+            p.time_sampling_method = _TIME["uniform"]
+            p.use_stratified_sampling_for_each_interval = 0
+            p.path_correlation_depth = 0
+            p.time_correlate_number = p.path_correlate_number = 1
+            return p
         if self.time_sampling_method == "antithetic_mirror" and p.time_correlate_number != 2:
             raise ValueError("antithetic_mirror requires time_correlate_number == 2")  # correlated.cpp:141-142
         if p.time_correlate_number < 1 or p.path_correlate_number < 1:

@@ -420,8 +420,6 @@ class _Loader:
         sc.scene_order = order
         if sc.integrator is None:
             raise ValueError("scene has no integrator")
-        if type(sc.integrator) is DopplerToFPathIntegrator and sc.sensor is not None and sc.sensor.sampler.kind != "correlated":
-            raise ValueError("dopplertofpath is driven by the 'correlated' sampler (README.md:61)")
         return sc
 
 

@@ -277,3 +277,34 @@ def test_film_options_that_would_change_the_image_are_refused():
             open(path, "w").write(xml)
             r = subprocess.run([cli, "--dump-desc", os.path.join(tmp, "d.bin"), path], capture_output=True, text=True)
             assert r.returncode == 1 and word in r.stderr
+
+
+def _independent_xml():
+    base = open(os.path.join(gu.SCENES, "c1_example.xml")).read()
+    i = base.index('<sampler type="correlated">')
+    j = base.index('</sampler>', i) + len('</sampler>')
+    return base[:i] + '<sampler type="independent"><integer name="sample_count" value="$spp" /></sampler>' + base[j:]
+
+
+def test_dopplertofpath_with_the_independent_sampler_is_the_uniform_uncorrelated_stream():
+    """With any sampler but `correlated`, the Doppler branch's next_1d_time / next_*_correlate calls hit the base-class
+    defaults (include/mitsuba/render/sampler.h:131-144): one independent stream, whatever the integrator's
+    time_sampling_method / path_correlation_depth say. That is bit for bit the correlated sampler's `rng` stream with
+    uniform time sampling and no path correlation (src/samplers/correlated.cpp:92-97, 156-161)."""
+    ind = dt.load_string(_independent_xml(), gu.SCENES, tsm="antithetic", pcd=4)
+    assert ind.sensor.sampler.kind == "independent"
+    cor = dt.load_file(os.path.join(gu.SCENES, "c1_example.xml"), tsm="uniform", pcd=0, tcn=1, pcn=1, strat="false")
+    a = ind.integrator.params(ind.sensor.sampler, seed=3)
+    b = cor.integrator.params(cor.sensor.sampler, seed=3)
+    assert bytes(a) == bytes(b)
+    assert bytes(ind.flatten().desc.camera) == bytes(cor.flatten().desc.camera)
+    # the C++ host accepts the same scene
+    import subprocess
+    import tempfile
+    cli = os.path.join(ROOT, "host", "dtof_render")
+    assert subprocess.run(["make", "-C", os.path.join(ROOT, "host")], capture_output=True).returncode == 0
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "s.xml")
+        open(path, "w").write(_independent_xml())
+        r = subprocess.run([cli, "--dump-desc", os.path.join(tmp, "d.bin"), path], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr

@@ -170,6 +170,37 @@ def test_reference_cli_filters_through_the_plugin(tmp_path, rfilter):
 
 @pytest.mark.gpu
 @needs_runtime
+def test_reference_cli_independent_sampler_through_the_plugin(tmp_path):
+    """`independent` sampler + Doppler integrator: the plugin (reading the reference's IndependentSampler) and the Python
+    host must choose the same stream -- the correlated sampler's independent stream, uniform in time, uncorrelated."""
+    if not _runnable():
+        pytest.skip("reference runtime cannot execute on this CPU")
+    def swap(xml):
+        i = xml.index('<sampler type="correlated">')
+        j = xml.index('</sampler>', i) + len('</sampler>')
+        return xml[:i] + '<sampler type="independent"><integer name="sample_count" value="$spp" /></sampler>' + xml[j:]
+    scene_path = _plugin_scene(tmp_path, "c1_example.xml")
+    open(scene_path, "w").write(swap(open(scene_path).read()))
+    plain = os.path.join(str(tmp_path), "plain.xml")
+    open(plain, "w").write(swap(open(os.path.join(SCENES, "c1_example.xml")).read()))
+    defs = {"resx": 48, "resy": 48, "spp": 32, "tcn": 2, "pcn": 2}
+    out = os.path.join(str(tmp_path), "out.pfm")
+    r = _run([f"-D{k}={v}" for k, v in defs.items() if k not in ("tcn", "pcn")] + ["-o", out, scene_path])
+    assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
+    img = _read_pfm(out)
+    scene = dt.load_file(plain, **{k: v for k, v in defs.items() if k not in ("tcn", "pcn")})
+    ref = scene.integrator.render(scene, seed=0)
+    same = dt.load_file(os.path.join(SCENES, "c1_example.xml"), tsm="uniform", pcd=0, tcn=1, pcn=1, strat="false",
+                        **{k: v for k, v in defs.items() if k not in ("tcn", "pcn")})
+    ref2 = same.integrator.render(same, seed=0)
+    scale = np.abs(ref).max()
+    assert np.abs(ref - ref2).max() <= 2e-4 * scale
+    err = np.abs(img - ref).max(axis=2)
+    assert int((err > 2e-4 * scale).sum()) <= 1e-3 * err.size, f"max {err.max():.3e}, scale {scale:.3e}"
+
+
+@pytest.mark.gpu
+@needs_runtime
 def test_plugin_image_agrees_with_the_reference_integrator(tmp_path):
     """Same executable, same scene file, integrator `dopplertofpath` (the reference's CPU code) vs `dopplertofpath_b200`.
     The scalar reference is not stream-identical (per-pixel seeding, no pair correlation), so the check

@@ -39,9 +39,11 @@ def test_path_property_surface():
     assert "PathIntegrator" in repr(dt.PathIntegrator(max_depth=3))
 
 
-def test_path_accepts_the_independent_sampler_and_dopplertofpath_does_not():
+def test_path_and_dopplertofpath_accept_the_independent_sampler():
     """Sampler::next_1d of `correlated` IS the independent sampler's stream (src/samplers/correlated.cpp:78-90,
-    src/render/sampler.cpp:115-134): the same lanes give the same values under either sampler."""
+    src/render/sampler.cpp:115-134): the same lanes give the same values under either sampler. Under `dopplertofpath`
+    the independent sampler answers with the base-class defaults (sampler.h:131-144), which is the correlated sampler
+    with uniform time sampling and no path correlation -- lane for lane."""
     a = dt.load_string(_path_xml(), base_dir=gu.SCENES, resx=16, resy=16, spp=8)
     b = dt.load_string(_path_xml(sampler="independent"), base_dir=gu.SCENES, resx=16, resy=16, spp=8)
     assert b.sensor.sampler.kind == "independent"
@@ -53,10 +55,11 @@ def test_path_accepts_the_independent_sampler_and_dopplertofpath_does_not():
     import re
     xml = re.sub(r'<sampler type="correlated">.*?</sampler>', '<sampler type="independent">\n<integer name="sample_count" value="$spp" />\n</sampler>',
                  xml, flags=re.S)
-    with pytest.raises(ValueError, match="correlated"):
-        dt.load_string(xml, base_dir=gu.SCENES, resx=8, resy=8, spp=4)
-    with pytest.raises(ValueError, match="correlated"):
-        dt.DopplerToFPathIntegrator().params(b.sensor.sampler)
+    c = dt.load_string(xml, base_dir=gu.SCENES, resx=16, resy=16, spp=8)                      # antithetic, pcd 4 in the file
+    d = dt.load_file(os.path.join(gu.SCENES, "c1_example.xml"), resx=16, resy=16, spp=8, tsm="uniform", pcd=0, strat="false")
+    rc = oracle_lib.OracleScene(c.flatten()).trace(c.integrator.params(c.sensor.sampler, seed=1), lanes)
+    rd = oracle_lib.OracleScene(d.flatten()).trace(d.integrator.params(d.sensor.sampler, seed=1), lanes)
+    assert np.array_equal(rc["rgb"], rd["rgb"]) and np.array_equal(rc["time"], rd["time"]) and np.abs(rc["rgb"]).max() > 0
 
 
 def test_path_is_dopplertofpath_without_modulation():
@@ -93,8 +96,7 @@ def test_cpp_host_path_property_surface(tmp_path):
     assert r.returncode == 1 and "unreferenced property" in r.stderr
     xml = open(os.path.join(gu.SCENES, "c1_example.xml")).read().replace('<sampler type="correlated">', '<sampler type="independent">')
     xml = xml.replace('<integer name="time_correlate_number" value="$tcn" />', '').replace('<integer name="path_correlate_number" value="$pcn" />', '')
-    r = run(xml)
-    assert r.returncode == 1 and "correlated" in r.stderr
+    assert run(xml).returncode == 0   # dopplertofpath + independent: the uniform, uncorrelated stream (sampler.h:131-144)
 
 
 @pytest.mark.gpu
