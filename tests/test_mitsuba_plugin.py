@@ -180,7 +180,8 @@ def test_reference_cli_independent_sampler_through_the_plugin(tmp_path):
         j = xml.index('</sampler>', i) + len('</sampler>')
         return xml[:i] + '<sampler type="independent"><integer name="sample_count" value="$spp" /></sampler>' + xml[j:]
     scene_path = _plugin_scene(tmp_path, "c1_example.xml")
-    open(scene_path, "w").write(swap(open(scene_path).read()))
+    swapped = swap(open(scene_path).read())
+    open(scene_path, "w").write(swapped)
     plain = os.path.join(str(tmp_path), "plain.xml")
     open(plain, "w").write(swap(open(os.path.join(SCENES, "c1_example.xml")).read()))
     defs = {"resx": 48, "resy": 48, "spp": 32, "tcn": 2, "pcn": 2}
