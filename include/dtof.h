@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define DTOF_ABI_VERSION 7
+#define DTOF_ABI_VERSION 8
 
 typedef struct dtof_ctx dtof_ctx;
 
@@ -328,6 +328,12 @@ dtof_status dtof_develop_device(dtof_ctx *ctx, const float *d_rgbw, float *d_ima
 /* Evaluate n wavefront lanes of pass 0 (host arrays in, host records out). */
 dtof_status dtof_trace_samples(dtof_ctx *ctx, const dtof_params *params, const uint64_t *lanes, uint32_t n,
                                dtof_sample_record *out);
+
+/* The same for the lanes' samples of pass `pass` (0 <= pass < n_passes): the sampler streams of a lane continue from
+ * pass to pass (src/render/integrator.cpp:299-308, Sampler::advance / current_sample_index src/render/sampler.cpp:52-55,
+ * 94-103), so passes 0 .. pass - 1 of each lane are replayed first and the record describes the last one. */
+dtof_status dtof_trace_samples_pass(dtof_ctx *ctx, const dtof_params *params, const uint64_t *lanes, uint32_t n,
+                                    uint32_t pass, dtof_sample_record *out);
 
 /* Enable/disable traversal counters (slower kernel variant) and read them back after a render. */
 dtof_status dtof_set_stats(dtof_ctx *ctx, int enabled);

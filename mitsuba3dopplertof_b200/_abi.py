@@ -8,7 +8,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 # enums (include/dtof.h)
 TIME_UNIFORM, TIME_STRATIFIED, TIME_ANTITHETIC, TIME_ANTITHETIC_MIRROR = range(4)
@@ -149,6 +149,8 @@ DTOF_SYMBOLS = {
     "dtof_develop_device": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dtof_trace_samples": (C.c_int, [_ctx, C.POINTER(Params), C.POINTER(C.c_uint64), C.c_uint32,
                                      C.POINTER(SampleRecord)]),
+    "dtof_trace_samples_pass": (C.c_int, [_ctx, C.POINTER(Params), C.POINTER(C.c_uint64), C.c_uint32, C.c_uint32,
+                                          C.POINTER(SampleRecord)]),
     "dtof_set_stats": (C.c_int, [_ctx, C.c_int]),
     "dtof_get_stats": (C.c_int, [_ctx, C.POINTER(Stats)]),
     "dtof_last_traversal_mode": (C.c_int, [_ctx]),

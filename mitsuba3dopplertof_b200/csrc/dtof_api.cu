@@ -56,6 +56,8 @@ struct RenderArgs {
     dtof_sample_record *rec_out;
     uint32_t n_rec;
     uint32_t nodes_bytes, tris_bytes, insts_bytes, boxes_bytes;
+    uint32_t stack_levels;                       // BVH_SMEM mode: rows of the shared-memory traversal stack (BVH depth + 4)
+    uint32_t rec_pass;                           // record mode: the pass whose lanes are recorded (passes before it are replayed)
 };
 
 template <int MODE, bool STATS, bool RECORD, int KIND, bool ENV>
@@ -63,6 +65,7 @@ __global__ void __launch_bounds__(kBlock, DTOF_MIN_CTAS) render_kernel(const __g
     extern __shared__ float4 smem[];
     TravPtrs TP;
     TP.N = A.scene.nodes, TP.T = A.scene.tris, TP.TF = A.tris_flat, TP.I = A.scene.insts, TP.B = A.inst_box;
+    TP.S = SmemScene{ 0u, 0u, 0u, 0u };
     if (MODE != MODE_BVH_GLOBAL) {
         // stage the traversal data into shared memory (128-bit copies): [nodes | tris] or [flat tris], insts, boxes
         const uint32_t nn = MODE == MODE_BVH_SMEM ? A.nodes_bytes / 16 : 0, nt = A.tris_bytes / 16,
@@ -76,6 +79,11 @@ __global__ void __launch_bounds__(kBlock, DTOF_MIN_CTAS) render_kernel(const __g
         for (uint32_t i = threadIdx.x; i < nb; i += kBlock) sB[i] = A.inst_box[i];
         __syncthreads();
         TP.N = sN, TP.T = sT, TP.TF = sT, TP.I = sI, TP.B = sB;
+        if (MODE == MODE_BVH_SMEM) {   // after the scene: the traversal stacks, stack_levels rows of 128 B per warp
+            const uint32_t base = opaque_u32((uint32_t) __cvta_generic_to_shared(smem));
+            TP.S.N = base, TP.S.T = base + A.nodes_bytes, TP.S.I = TP.S.T + A.tris_bytes;
+            TP.S.stack = TP.S.I + A.insts_bytes + A.boxes_bytes + (threadIdx.x >> 5) * (A.stack_levels * 128u) + (threadIdx.x & 31) * 4u;
+        }
     }
     constexpr bool VELOCITY = KIND == DTOF_INTEGRATOR_VELOCITY;
     constexpr bool STOCK_SAMPLE = KIND != DTOF_INTEGRATOR_DOPPLERTOFPATH;   // stock render_sample branch (integrator.cpp:409-472)
@@ -112,7 +120,7 @@ __global__ void __launch_bounds__(kBlock, DTOF_MIN_CTAS) render_kernel(const __g
             LaneSampler smp;
             smp.seed(A.p, idx);
 
-            for (uint32_t pass = 0; pass < (RECORD ? 1u : A.n_passes); ++pass) {
+            for (uint32_t pass = 0; pass < (RECORD ? A.rec_pass + 1u : A.n_passes); ++pass) {
                 // render_sample(): Doppler branch (src/render/integrator.cpp:476-542), or the stock branch (:409-472)
                 // for the velocity and path integrators -- jitter and time from the independent stream only
                 const bool correlate_pixel = A.p.path_correlation_depth > 0;
@@ -150,7 +158,7 @@ __global__ void __launch_bounds__(kBlock, DTOF_MIN_CTAS) render_kernel(const __g
                 }
                 if (STATS && lane_on) st.samples++;
                 if (RECORD) {
-                    if (lane_on) {
+                    if (lane_on && pass == A.rec_pass) {
                         dtof_sample_record &rec = A.rec_out[li];
                         rec.sample_pos[0] = spx, rec.sample_pos[1] = spy;
                         rec.time = time;
@@ -388,7 +396,7 @@ template <int MODE, bool STATS, bool RECORD, int KIND, bool ENV>
 dtof_status launch_variant(dtof_ctx *ctx, RenderArgs &A, int grid, cudaStream_t stream) {
     size_t smem = 0;
     if (MODE == MODE_BVH_SMEM)
-        smem = (size_t) A.nodes_bytes + A.tris_bytes + A.insts_bytes + A.boxes_bytes;
+        smem = (size_t) A.nodes_bytes + A.tris_bytes + A.insts_bytes + A.boxes_bytes + (size_t) A.stack_levels * 128u * (kBlock / 32);
     else if (MODE == MODE_FLAT_SMEM)
         smem = (size_t) A.tris_bytes + A.insts_bytes + A.boxes_bytes;
     auto k = render_kernel<MODE, STATS, RECORD, KIND, ENV>;
@@ -608,7 +616,7 @@ dtof_status launch_wavefront(dtof_ctx *ctx, const RenderArgs &A, int mode, cudaS
 }
 
 dtof_status launch_render(dtof_ctx *ctx, const dtof_params *p, float *d_rgbw, cudaStream_t stream,
-                          const unsigned long long *d_lanes, dtof_sample_record *d_rec, uint32_t n_rec) {
+                          const unsigned long long *d_lanes, dtof_sample_record *d_rec, uint32_t n_rec, uint32_t rec_pass = 0) {
     dtof_pass_info pi;
     int rc = pass_info(ctx->film, *p, &pi);
     if (rc)
@@ -659,7 +667,10 @@ dtof_status launch_render(dtof_ctx *ctx, const dtof_params *p, float *d_rgbw, cu
     A.inst_box = (const float4 *) ctx->d_boxes;
     const bool record = d_rec != nullptr;
     // ---- traversal mode: flat coherent walk for tiny scenes, BVH in shared memory while it fits, else BVH from HBM
-    const size_t bvh_bytes = ctx->nodes_bytes + ctx->tris_bytes + ctx->insts_bytes + ctx->boxes_bytes;
+    A.stack_levels = (uint32_t) ctx->bvh_depth + 4u;
+    A.rec_pass = rec_pass;
+    const size_t stack_bytes = (size_t) A.stack_levels * 128u * (kBlock / 32);   // shared-memory traversal stacks of one CTA
+    const size_t bvh_bytes = ctx->nodes_bytes + ctx->tris_bytes + ctx->insts_bytes + ctx->boxes_bytes + stack_bytes;
     const size_t flat_bytes = ctx->flat_bytes + ctx->insts_bytes + ctx->boxes_bytes;
     int mode = MODE_BVH_GLOBAL;
     if (bvh_bytes <= kSmemSceneLimit && bvh_bytes + 1024 <= ctx->smem_optin)
@@ -1341,6 +1352,11 @@ dtof_status dtof_render_multi_pass(dtof_ctx *ctx, const dtof_params *params, uin
 
 dtof_status dtof_trace_samples(dtof_ctx *ctx, const dtof_params *params, const uint64_t *lanes, uint32_t n,
                                dtof_sample_record *out) {
+    return dtof_trace_samples_pass(ctx, params, lanes, n, 0, out);
+}
+
+dtof_status dtof_trace_samples_pass(dtof_ctx *ctx, const dtof_params *params, const uint64_t *lanes, uint32_t n, uint32_t pass,
+                                    dtof_sample_record *out) {
     if (!ctx)
         return DTOF_ERR_INVALID;
     if (!ctx->has_scene)
@@ -1355,6 +1371,8 @@ dtof_status dtof_trace_samples(dtof_ctx *ctx, const dtof_params *params, const u
     dtof_pass_info pi;
     if (pass_info(ctx->film, *params, &pi))
         return fail(ctx, DTOF_ERR_INVALID, "sample_count should be a multiple of samples_per_wavefront!");
+    if (pass >= pi.n_passes)
+        return fail(ctx, DTOF_ERR_INVALID, "pass %u outside the %u passes of this render", pass, pi.n_passes);
     for (uint32_t i = 0; i < n; ++i)
         if (lanes[i] >= pi.wavefront_size)
             return fail(ctx, DTOF_ERR_INVALID, "lane %llu outside the wavefront", (unsigned long long) lanes[i]);
@@ -1372,7 +1390,7 @@ dtof_status dtof_trace_samples(dtof_ctx *ctx, const dtof_params *params, const u
     p.lane_begin = 0;
     p.lane_end = 0;
     p.shard_block = 0;
-    s = launch_render(ctx, &p, ctx->d_rgbw, 0, d_lanes, d_rec, n);
+    s = launch_render(ctx, &p, ctx->d_rgbw, 0, d_lanes, d_rec, n, pass);
     if (s == DTOF_OK) {
         e = cudaMemcpy(out, d_rec, n * sizeof(dtof_sample_record), cudaMemcpyDeviceToHost);
         if (e != cudaSuccess)

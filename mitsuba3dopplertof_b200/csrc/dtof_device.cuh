@@ -45,7 +45,8 @@ DTOF_DEV V3 operator*(V3 a, V3 b) { return v3(a.x * b.x, a.y * b.y, a.z * b.z); 
 // Sampler, camera ray and the accepted-hit arithmetic of the triangle test are IEEE (they decide WHICH pixel / time /
 // triangle a sample sees and are compared bit for bit with the oracle). Everything after the hit -- surface frame,
 // emitter / BSDF sampling, MIS, modulation argument reduction, Russian roulette -- uses the SFU approximations below
-// (<= 2 ulp per operation), exactly the operations the reference's own CUDA variants emit (div/rcp/sqrt/rsqrt
+// (<= 2 ulp per operation; `.ftz` like the reference: the non-ftz forms wrap every MUFU in four instructions of
+// denormal scaling), exactly the operations the reference's own CUDA variants emit (div/rcp/sqrt/rsqrt
 // `.approx.ftz`, ext/drjit/ext/drjit-core/src/cuda_eval.cpp:433-655). They are ~1e-7 relative per operation against
 // the 1e-4 per-sample tolerance, and shrink the kernel by a fifth (an IEEE division is ~10 SASS instructions plus a
 // slow-path call, an approximate one 1-4), which matters because the kernel is instruction-cache / issue bound
@@ -64,17 +65,17 @@ DTOF_DEV float fdiv(float a, float b) {
 }
 DTOF_DEV float frcp(float a) {
     float r;
-    asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(a));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
     return r;
 }
 DTOF_DEV float fsqrt(float a) {
     float r;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(a));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
     return r;
 }
 DTOF_DEV float frsqrt(float a) {
     float r;
-    asm("rsqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(a));
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
     return r;
 }
 DTOF_DEV V3 operator/(V3 a, float s) {
@@ -744,6 +745,175 @@ DTOF_DEV bool trace_bvh(const float4 *__restrict__ N, const float4 *__restrict__
         DTOF_POP();
     }
 #undef DTOF_POP
+    return found;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Traversal of a scene that is staged in SHARED memory (BVH_SMEM mode). Same walk as trace_bvh (same child order,
+// triangle test and tie-break, so hits are identical), rebuilt around what the issue-bound fused kernel pays for:
+//  * 32-bit shared-window addresses + ld.shared: no generic-to-shared base is re-derived inside the loops;
+//  * the traversal stack lives in shared memory, one 128-byte row per level and warp (slot = lane): a push / pop is
+//    conflict-free whatever the lanes' depths are (an L1-resident local-memory stack serialises over the distinct
+//    levels of a warp) and no stack traffic reaches L2 / DRAM;
+//  * the slab test is one fma per plane, b * idir - o * idir. Its ABSOLUTE error (<= ulp(o * idir) per plane) is
+//    bounded per ray by `e2` and added to the far side / the best distance, so the test stays conservative for any
+//    origin without relying on how much the builder padded the boxes;
+//  * the world-space reciprocal direction is recomputed when a lane leaves an instance instead of being kept live.
+struct SmemScene {
+    uint32_t N, T, I;   // byte addresses (shared window) of nodes, leaf-order triangles, instance records
+    uint32_t stack;     // this lane's slot of stack level 0; level l is at stack + 128 * l
+};
+DTOF_DEV float4 lds128(uint32_t a) {
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+DTOF_DEV int lds_stack(uint32_t a) {
+    int v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+DTOF_DEV void sts_stack(uint32_t a, int v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+// a value the compiler must keep in a register as it is (it would otherwise re-derive the shared-window base from
+// %cluster_ctaid inside the traversal loop)
+DTOF_DEV uint32_t opaque_u32(uint32_t v) {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
+// rcp.approx that stays where it is written: leaving an instance recomputes the world-space reciprocal direction there
+// (rare) instead of keeping nine loop-invariant values live through the whole walk
+DTOF_DEV float frcp_here(float a) {
+    float r;
+    asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+    return r;
+}
+
+constexpr float kSlabAbsErr = 2.4e-7f;   // 4 x 2^-24: both sides of the interval, with a factor 2 in hand
+
+template <bool STATS>
+DTOF_DEV bool trace_bvh_smem(const SmemScene M, int32_t root, const bool ANY, V3 o, V3 d, float tmax, float time, Hit &hit,
+                             Counters &st) {
+    uint32_t sp = M.stack;
+    int node = root;
+    int cur_inst = -1;
+    V3 ro = o, rd = d;
+    V3 id = v3(frcp(d.x), frcp(d.y), frcp(d.z));
+    V3 nd = v3(-(o.x * id.x), -(o.y * id.y), -(o.z * id.z));
+    float e2 = kSlabAbsErr * fmaxf(fmaxf(fabsf(nd.x), fabsf(nd.y)), fabsf(nd.z));
+    float best = tmax, best_e = best + e2;
+    bool found = false;
+    if (STATS) {
+        if (ANY) st.rays_shadow++; else st.rays_closest++;
+    }
+#define DTOF_SPOP()                                                                                        \
+    do {                                                                                                   \
+        if (sp == M.stack) {                                                                               \
+            node = kDone;                                                                                  \
+        } else {                                                                                           \
+            sp -= 128u;                                                                                    \
+            node = lds_stack(sp);                                                                          \
+            if (node == kSentinel) { /* leave the instance: back to the world-space ray */                 \
+                ro = o, rd = d, cur_inst = -1;                                                             \
+                id = v3(frcp_here(d.x), frcp_here(d.y), frcp_here(d.z));                                   \
+                nd = v3(-(o.x * id.x), -(o.y * id.y), -(o.z * id.z));                                      \
+                e2 = kSlabAbsErr * fmaxf(fmaxf(fabsf(nd.x), fabsf(nd.y)), fabsf(nd.z));                    \
+                best_e = best + e2;                                                                        \
+                if (sp == M.stack) {                                                                       \
+                    node = kDone;                                                                          \
+                } else {                                                                                   \
+                    sp -= 128u;                                                                            \
+                    node = lds_stack(sp);                                                                  \
+                }                                                                                          \
+            }                                                                                              \
+        }                                                                                                  \
+    } while (0)
+
+    while (node != kDone) {
+        // ---- inner nodes
+        while ((unsigned) node < (unsigned) kDone) {
+            const uint32_t na = M.N + ((uint32_t) node << 6);
+            const float4 n0 = lds128(na), n1 = lds128(na + 16), n2 = lds128(na + 32), n3 = lds128(na + 48);
+            if (STATS) st.nodes++;
+            const float c0lx = fmaf(n0.x, id.x, nd.x), c0hx = fmaf(n0.y, id.x, nd.x);
+            const float c0ly = fmaf(n0.z, id.y, nd.y), c0hy = fmaf(n0.w, id.y, nd.y);
+            const float c0lz = fmaf(n2.x, id.z, nd.z), c0hz = fmaf(n2.y, id.z, nd.z);
+            const float c1lx = fmaf(n1.x, id.x, nd.x), c1hx = fmaf(n1.y, id.x, nd.x);
+            const float c1ly = fmaf(n1.z, id.y, nd.y), c1hy = fmaf(n1.w, id.y, nd.y);
+            const float c1lz = fmaf(n2.z, id.z, nd.z), c1hz = fmaf(n2.w, id.z, nd.z);
+            const float t0n = fmaxf(fmaxf(fminf(c0lx, c0hx), fminf(c0ly, c0hy)), fmaxf(fminf(c0lz, c0hz), 0.f));
+            const float t0f = fmaf(fminf(fminf(fmaxf(c0lx, c0hx), fmaxf(c0ly, c0hy)), fmaxf(c0lz, c0hz)), 1.000003f, e2);
+            const float t1n = fmaxf(fmaxf(fminf(c1lx, c1hx), fminf(c1ly, c1hy)), fmaxf(fminf(c1lz, c1hz), 0.f));
+            const float t1f = fmaf(fminf(fminf(fmaxf(c1lx, c1hx), fmaxf(c1ly, c1hy)), fmaxf(c1lz, c1hz)), 1.000003f, e2);
+            const bool h0 = t0n <= fminf(t0f, best_e), h1 = t1n <= fminf(t1f, best_e);
+            const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+            if (h0 && h1) {
+                const bool swap = t1n < t0n;
+                sts_stack(sp, swap ? c0 : c1);
+                sp += 128u;
+                node = swap ? c1 : c0;
+            } else if (h0 || h1) {
+                node = h0 ? c0 : c1;
+            } else {
+                DTOF_SPOP();
+            }
+        }
+        if (node == kDone)
+            break;
+        // ---- leaf
+        const uint32_t code = (uint32_t) ~node;
+        const uint32_t count = code & 15u;
+        if (count == 0) {   // animated instance (Embree semantics, see enter_instance)
+            cur_inst = (int) (code >> 4);
+            const uint32_t ia = M.I + ((uint32_t) cur_inst << 7);
+            if (STATS) st.inst++;
+            const float4 q6 = lds128(ia + 96);
+            const float f = fdiv(time - q6.x, q6.y - q6.x), s = 1.f - f;
+            M34 Mx;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float4 a = lds128(ia + 16 * k), b = lds128(ia + 48 + 16 * k);
+                Mx.m[4 * k + 0] = fmaf(b.x, f, a.x * s);
+                Mx.m[4 * k + 1] = fmaf(b.y, f, a.y * s);
+                Mx.m[4 * k + 2] = fmaf(b.z, f, a.z * s);
+                Mx.m[4 * k + 3] = fmaf(b.w, f, a.w * s);
+            }
+            const M34 inv = inverse_m34(Mx);
+            ro = xf_point(inv, o);
+            rd = xf_vector(inv, d);
+            id = v3(frcp(rd.x), frcp(rd.y), frcp(rd.z));
+            nd = v3(-(ro.x * id.x), -(ro.y * id.y), -(ro.z * id.z));
+            e2 = kSlabAbsErr * fmaxf(fmaxf(fabsf(nd.x), fabsf(nd.y)), fabsf(nd.z));
+            best_e = best + e2;
+            sts_stack(sp, kSentinel);
+            sp += 128u;
+            node = __float_as_int(q6.z);
+            continue;
+        }
+        uint32_t ta = M.T + 48u * (code >> 4);
+        for (uint32_t i = 0; i < count; ++i, ta += 48u) {
+            const float4 a = lds128(ta), b = lds128(ta + 16), c = lds128(ta + 32);
+            if (STATS) st.tris++;
+            float t, u, v;
+            if (tri_test(a, b, c, ro, rd, best, t, u, v)) {
+                if (ANY)
+                    return true;
+                const uint32_t gid = __float_as_uint(a.w);
+                if (t < best || !found || gid < hit.gid) {
+                    best = t;
+                    best_e = t + e2;
+                    hit.t = t;
+                    hit.u = u;
+                    hit.v = v;
+                    hit.gid = gid;
+                    hit.inst = cur_inst;
+                    found = true;
+                }
+            }
+        }
+        DTOF_SPOP();
+    }
+#undef DTOF_SPOP
     return found;
 }
 

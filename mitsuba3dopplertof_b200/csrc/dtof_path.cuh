@@ -25,6 +25,7 @@ struct TravPtrs {
     const float4 *TF;   // triangles in scene order (flat mode)
     const float4 *I;    // instance records (8 x float4)
     const float4 *B;    // instance world boxes (2 x float4)
+    SmemScene S;        // BVH_SMEM mode: shared-window addresses of N / T / I and of this lane's traversal stack
 };
 
 template <int MODE, bool STATS>
@@ -34,6 +35,10 @@ DTOF_DEV bool trace_any_mode(const DeviceScene &S, const TravPtrs &P, bool any, 
         return trace_flat<STATS>(P.TF, P.I, P.B, S.n_insts, any, o, d, tmax, time, lane_active, hit, st);
     if (!lane_active || !S.has_geometry)
         return false;
+#ifndef DTOF_OLD_SMEM_WALK   // A/B builds only: the round-1 walk (generic pointers, local-memory stack) on the staged copy
+    if (MODE == MODE_BVH_SMEM)
+        return trace_bvh_smem<STATS>(P.S, S.root, any, o, d, tmax, time, hit, st);
+#endif
     return trace_bvh<STATS, MODE == MODE_BVH_GLOBAL>(P.N, P.T, P.I, S.root, any, o, d, tmax, time, hit, st);
 }
 

@@ -139,11 +139,12 @@ class Context:
     def develop_device(self, d_rgbw_ptr: int, d_img_ptr: int, stream_ptr: int = 0) -> None:
         self._check(self.lib.dtof_develop_device(self.h, C.c_void_p(d_rgbw_ptr), C.c_void_p(d_img_ptr), C.c_void_p(stream_ptr)))
 
-    def trace_samples(self, params: _abi.Params, lanes) -> np.ndarray:
+    def trace_samples(self, params: _abi.Params, lanes, pass_index: int = 0) -> np.ndarray:
+        """Per-lane records of pass `pass_index` (the streams of a lane persist across passes: earlier ones are replayed)."""
         lanes = np.ascontiguousarray(lanes, np.uint64)
         out = np.zeros(lanes.size, _abi.SAMPLE_RECORD_DTYPE)
-        self._check(self.lib.dtof_trace_samples(self.h, C.byref(params), lanes.ctypes.data_as(C.POINTER(C.c_uint64)),
-                                                lanes.size, out.ctypes.data_as(C.POINTER(_abi.SampleRecord))))
+        self._check(self.lib.dtof_trace_samples_pass(self.h, C.byref(params), lanes.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                                     lanes.size, int(pass_index), out.ctypes.data_as(C.POINTER(_abi.SampleRecord))))
         return out
 
     # ---- instrumentation -----------------------------------------------------------------------

@@ -1879,9 +1879,19 @@ void dtof_oracle_scene_destroy(dtof_oracle_scene *s) { delete s; }
 
 int dtof_oracle_trace_samples(const dtof_oracle_scene *s, const dtof_params *p, const uint64_t *lanes, uint32_t n,
                               dtof_sample_record *out) {
+    return dtof_oracle_trace_samples_pass(s, p, lanes, n, 0, out);
+}
+
+// The lanes' samples of pass `pass`: the three streams of a lane persist from pass to pass (src/render/integrator.cpp:
+// 299-308), Sampler::advance() bumps the sample index and resets the dimension (src/render/sampler.cpp:52-55,94-103),
+// so the earlier passes of every lane are replayed and the last one is recorded.
+int dtof_oracle_trace_samples_pass(const dtof_oracle_scene *s, const dtof_params *p, const uint64_t *lanes, uint32_t n,
+                                   uint32_t pass, dtof_sample_record *out) {
     dtof_pass_info pi;
     if (pass_info(s->film, *p, &pi))
         return 1;
+    if (pass >= pi.n_passes)
+        return 3;
     Modulation mod(*p);
     Counters st;
     for (uint32_t i = 0; i < n; ++i) {
@@ -1892,7 +1902,10 @@ int dtof_oracle_trace_samples(const dtof_oracle_scene *s, const dtof_params *p, 
         smp.seed(*p, idx, pi.spp_per_pass);
         uint32_t pixel = (uint32_t) (idx / pi.spp_per_pass);
         uint32_t py = pixel / s->film.width, px = pixel - py * s->film.width;
-        lane_sample(*s, *p, mod, smp, px, py, out[i], st);
+        for (uint32_t k = 0; k <= pass; ++k) {
+            lane_sample(*s, *p, mod, smp, px, py, out[i], st);
+            smp.advance();
+        }
     }
     return 0;
 }

@@ -60,6 +60,9 @@ void dtof_oracle_scene_destroy(dtof_oracle_scene *s);
 /* per-lane evaluation of pass 0 (pass > 0 lanes are replayed from pass 0 internally when pass_out >= 1) */
 int dtof_oracle_trace_samples(const dtof_oracle_scene *s, const dtof_params *p, const uint64_t *lanes, uint32_t n,
                               dtof_sample_record *out);
+/* the lanes' samples of pass `pass` (earlier passes replayed; streams persist, integrator.cpp:299-308) */
+int dtof_oracle_trace_samples_pass(const dtof_oracle_scene *s, const dtof_params *p, const uint64_t *lanes, uint32_t n,
+                                   uint32_t pass, dtof_sample_record *out);
 
 /* full render: rgbw_out[h*w*4] (accumulated in double, rounded to float at the end), image_out[h*w*3] or NULL.
  * n_threads <= 0 -> all hardware threads. lane range from p->lane_begin/lane_end. */

@@ -18,6 +18,14 @@
 // pixel mapping and jitter/time prologue of render()/render_sample()
 // (src/render/integrator.cpp:273-290,476-509).
 //
+// Passes >= 1 (the streams of a lane persist across passes, integrator.cpp:299-308): the JIT variants consume the six
+// values of a loop iteration [emitter 2D, bsdf 1D, bsdf 2D, roulette 1D] whenever the iteration is ENTERED (the sampler
+// calls carry the loop mask `active`, dopplertofpath.cpp:187-270), the scalar build leaves the loop before any of them at
+// `if (dr::none_or<false>(active_next)) break;` (:173-174). Every entered iteration performs exactly one closest-hit
+// query, so this file interposes Embree's rtcIntersect1 (an undefined dynamic symbol of libmitsuba.so), counts the
+// queries of one sample() call and, when one more iteration was entered than was completed, burns the six values the
+// JIT variants would have drawn. With that the later passes of a lane see the JIT variants' streams.
+//
 // Output: one text line per (lane, pass):
 //   idx pass px py sample_pos.x sample_pos.y time ray.o(3) ray.d(3) ray.maxt R G B
 // floats printed as %.9g (round-trip exact for float32).
@@ -43,6 +51,8 @@
 #include <mitsuba/render/sensor.h>
 #undef protected
 
+#include <dlfcn.h>
+
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -51,6 +61,19 @@
 
 namespace mi = mitsuba;
 namespace dr = drjit;
+
+// closest-hit queries since the last reset (see the header comment); the real function is Embree's
+static int g_closest_queries = 0;
+struct RTCSceneTy;
+struct RTCIntersectContext;
+struct RTCRayHit;
+extern "C" __attribute__((visibility("default"))) void rtcIntersect1(RTCSceneTy *scene, RTCIntersectContext *context,
+                                                                    RTCRayHit *rayhit) {
+    using Fn = void (*)(RTCSceneTy *, RTCIntersectContext *, RTCRayHit *);
+    static Fn real = (Fn) dlsym(RTLD_NEXT, "rtcIntersect1");
+    ++g_closest_queries;
+    real(scene, context, rayhit);
+}
 
 using F = float;
 using S = mi::Color<float, 3>;
@@ -102,8 +125,25 @@ public:
     // JIT variants never do. begin_path() arms a small state machine that notices the missing 2D draw (a 1D request
     // arrives where the emitter 2D was expected) and burns the two values the JIT variants would have consumed.
     enum Expect { EM_2D, BSDF_1D, BSDF_2D, RR_1D, FREE };
-    void begin_path() { m_expect = EM_2D; }
-    void end_path() { m_expect = FREE; }
+    void begin_path() { m_expect = EM_2D; m_completed = 0; }
+    // `entered` loop iterations (= closest-hit queries) against the completed ones: the JIT variants draw the six values
+    // of an iteration the scalar build left at its early `break`
+    void end_path(int entered, bool correlated) {
+        m_expect = FREE;
+        if (entered < 0)
+            return;
+        if (entered != m_completed && entered != m_completed + 1) {
+            fprintf(stderr, "replay_harness: %d iterations entered, %d completed\n", entered, m_completed);
+            exit(3);
+        }
+        if (entered == m_completed + 1)
+            for (int i = 0; i < 6; ++i) {
+                if (correlated)
+                    raw_1d_correlate(false);
+                else
+                    raw_1d();
+            }
+    }
     float raw_1d() { return m_rng.next_float32(); }
     float raw_1d_correlate(bool correlate) {
         float r1 = m_rng_path.next_float32();
@@ -122,6 +162,8 @@ public:
             }
             m_expect = BSDF_1D;
         }
+        if (m_expect == RR_1D)
+            ++m_completed;
         m_expect = m_expect == EM_2D ? BSDF_1D : m_expect == BSDF_1D ? BSDF_2D : m_expect == BSDF_2D ? RR_1D : EM_2D;
     }
 
@@ -194,6 +236,7 @@ private:
     PCG m_rng, m_rng_time, m_rng_path;
     uint32_t m_tcn, m_pcn, m_perm_seed = 0, m_spp_pp = 1, m_idx = 0, m_pass = 0, m_dim = 0;
     Expect m_expect = FREE;
+    int m_completed = 0;
 };
 mi::Class *ReplaySampler::s_class = new mi::Class("ReplaySampler", "Sampler", "scalar_rgb", nullptr, nullptr);
 
@@ -317,8 +360,11 @@ int main(int argc, char **argv) {
                             ds.p.y(), ds.p.z(), ds.d.x(), ds.d.y(), ds.d.z(), ds.dist, ds.pdf, w.x(), w.y(), w.z());
                 }
                 sampler->begin_path();
+                g_closest_queries = 0;
                 auto [spec, valid] = integ->sample(scene, sampler.get(), ray, nullptr, aovs, true);
-                sampler->end_path();
+                // the velocity integrator has no path loop (two queries, no draws)
+                const bool has_loop = integ->class_()->name() != "VelocityIntegrator";
+                sampler->end_path(has_loop ? g_closest_queries : -1, doppler);
                 S rgb = ray_weight * spec;
                 printf("%u %u %u %u %.9g %.9g %.9g %.9g %.9g %.9g %.9g %.9g %.9g %.9g %.9g %.9g %.9g\n", idx, pass, px, py,
                        sample_pos.x(), sample_pos.y(), time, ray.o.x(), ray.o.y(), ray.o.z(), ray.d.x(), ray.d.y(),

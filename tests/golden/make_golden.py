@@ -107,6 +107,19 @@ VELOCITY_CASES = {
     "velocity_c3_rotor": ("c3_rotor", {"resx": 512, "resy": 512, "spp": 64}, 1, True),
     "velocity_c4_domino": ("c4_domino", {"resx": 512, "resy": 512, "spp": 64}, 2, True),
 }
+# Multi-pass renders (W * H * spp > 2^32 - 1 lanes, src/render/integrator.cpp:231-238): EVERY pass of the chosen lanes is
+# kept, written to lanes2p_<name>.json. The sampler streams continue from pass to pass (integrator.cpp:299-308), the sample
+# index becomes pass * spp_per_pass + idx % spp_per_pass and the dimension index restarts (src/render/sampler.cpp:52-55,94-103).
+PASS_CASES = {
+    "c4_domino": ("c4_domino", {"wave": "trapezoidal", "tsm": "antithetic_mirror", "shift": 0.0, "w_g": 150,
+                                "resx": 1024, "resy": 1024, "spp": 4096}, 1, True),                       # C4: 2 x 2048
+    "c5_antithetic": ("c5_slabroom", {"resx": 2048, "resy": 2048, "spp": 1024}, 0, True),               # C5: 2 x 512
+    "c5_uniform": ("c5_slabroom", {"resx": 2048, "resy": 2048, "spp": 1024, "tsm": "uniform", "shift": 0.0, "strat": "false"}, 2, True),
+    "c5_stratified": ("c5_slabroom", {"resx": 2048, "resy": 2048, "spp": 1024, "tsm": "stratified", "shift": 0.0, "pcn": 4,
+                                      "wave": "rectangular"}, 3, True),
+    "c5_mirror_4pass": ("c5_slabroom", {"resx": 2048, "resy": 2048, "spp": 3072, "tsm": "antithetic_mirror", "shift": 0.0,
+                                        "wave": "triangular"}, 4, True),                                   # 4 x 768
+}
 CASES.update(PATH_CASES)
 CASES.update(VELOCITY_CASES)
 SWAPPED = dict({k: "path" for k in PATH_CASES}, **{k: "velocity" for k in VELOCITY_CASES})
@@ -132,8 +145,9 @@ def lanes_for(case, params, rng):
     return lanes
 
 
-def run_case(name):
-    scene, params, seed, scaled = CASES[name]
+def run_case(name, table=None):
+    all_passes = table is not None
+    scene, params, seed, scaled = (table or CASES)[name]
     rng = np.random.default_rng(abs(hash(name)) % (2 ** 31) if False else sum(map(ord, name)))
     lanes = lanes_for(name, params, rng)
     lanes_file = f"/tmp/_dtof_lanes_{name}.txt"
@@ -159,16 +173,20 @@ def run_case(name):
     if name in SWAPPED:
         os.remove(scene_file)
     rows = [l.split() for l in out if l and l[0].isdigit()]
-    rows = [r for r in rows if int(r[1]) == 0]    # pass 0 only (later passes are not JIT-faithful in scalar mode)
-    assert len(rows) == len(lanes), (len(rows), len(lanes))
+    if all_passes:
+        assert len(rows) % len(lanes) == 0 and len(rows) > len(lanes), (len(rows), len(lanes))
+    else:
+        rows = [r for r in rows if int(r[1]) == 0]    # single-pass fixtures: pass 0 (the multi-pass ones are PASS_CASES)
+        assert len(rows) == len(lanes), (len(rows), len(lanes))
     rec = {
         "scene": scene + ".xml", "integrator": SWAPPED.get(name, "dopplertofpath"), "xml_params": params, "seed": seed, "time_scale": float(SCALE) if scaled else 1.0,
         "header": [l for l in out if l.startswith("#")][0],
         "columns": "idx px py sample_pos.x sample_pos.y time ray_o(3) ray_d(3) ray_maxt R G B",
         "lanes": [int(r[0]) for r in rows],
+        **({"pass": [int(r[1]) for r in rows]} if all_passes else {}),
         "rows": [[int(r[2]), int(r[3])] + [float(np.float32(v)) for v in r[4:]] for r in rows],
     }
-    with open(os.path.join(HERE, f"lanes_{name}.json"), "w") as f:
+    with open(os.path.join(HERE, f"lanes2p_{name}.json" if all_passes else f"lanes_{name}.json"), "w") as f:
         json.dump(rec, f, separators=(",", ":"))
     nz = sum(1 for r in rec["rows"] if any(abs(v) > 0 for v in r[-3:]))
     print(f"{name}: {len(rows)} lanes, {nz} non-zero")
@@ -177,9 +195,12 @@ def run_case(name):
 def main():
     if not os.path.exists(os.path.join(REF_RT, "replay_harness")):
         sys.exit("oracle/_ref/replay_harness missing: run `make -C oracle/ref_harness` in the build container")
-    names = sys.argv[1:] or list(CASES)
+    names = sys.argv[1:] or (list(CASES) + ["2p:" + n for n in PASS_CASES])
     for n in names:
-        run_case(n)
+        if n.startswith("2p:"):
+            run_case(n[3:], PASS_CASES)
+        else:
+            run_case(n)
     hv = os.path.join(REF_RT, "header_vectors")
     if not sys.argv[1:] and os.path.exists(hv):
         with open(os.path.join(HERE, "header_vectors.json"), "w") as f:

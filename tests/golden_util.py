@@ -53,8 +53,13 @@ def _all_case_names():
     return sorted(os.path.basename(p)[len("lanes_"):-len(".json")] for p in glob.glob(os.path.join(GOLDEN, "lanes_*.json")))
 
 
-def load_case(name):
-    with open(os.path.join(GOLDEN, f"lanes_{name}.json")) as f:
+def pass_case_names():
+    """Multi-pass fixtures (tests/golden/lanes2p_*.json): every pass of the chosen lanes, from the reference's sample()."""
+    return sorted(os.path.basename(p)[len("lanes2p_"):-len(".json")] for p in glob.glob(os.path.join(GOLDEN, "lanes2p_*.json")))
+
+
+def load_case(name, multipass=False):
+    with open(os.path.join(GOLDEN, f"lanes2p_{name}.json" if multipass else f"lanes_{name}.json")) as f:
         g = json.load(f)
     if g.get("integrator", "dopplertofpath") != "dopplertofpath":
         xml = swap_integrator(open(os.path.join(SCENES, g["scene"])).read(), g["integrator"])
@@ -69,13 +74,29 @@ def load_case(name):
         "sample_pos": rows[:, 2:4], "time": rows[:, 4] / g["time_scale"],
         "ray_o": rows[:, 5:8], "ray_d": rows[:, 8:11], "ray_maxt": rows[:, 11], "rgb": rows[:, 12:15],
     }
+    if multipass:
+        ref["pass"] = np.asarray(g["pass"], np.int64)
     if g.get("integrator") == "velocity":   # (t2 - t1) / time was computed with time * time_scale (a power of two)
         ref["rgb"] = ref["rgb"] * g["time_scale"]
     return scene, params, ref
 
 
-def compare(rec, ref):
-    """Returns (fraction of lanes whose rgb matches within tolerance, max error over matching lanes).
+REPORT = {}   # fixture -> achieved numbers, written by the tests (conftest dumps it at session end)
+OUTLIER_TOL = 1e-2
+
+
+def select(ref, mask):
+    return {k: v[mask] for k, v in ref.items()}
+
+
+def compare(rec, ref, label=None, explained=None):
+    """Per-lane radiance against the reference's values.
+
+    Returns (fraction of lanes within REL_TOL, worst relative error over ALL lanes that are not `explained`, indices of
+    the lanes outside REL_TOL). `explained` (bool per lane, optional) marks lanes whose difference has a known cause --
+    the tests pass "the CUDA path agrees with the CPU oracle on this lane", i.e. a triangle-edge decision on which
+    Embree and any other BVH differ (SURVEY.md section 7 hard part iv). The caller asserts BOTH the fraction and that
+    the worst unexplained lane stays within OUTLIER_TOL: the failing lanes are bounded, not just counted.
     Camera-side quantities must match on every lane."""
     np.testing.assert_allclose(rec["sample_pos"], ref["sample_pos"], rtol=0, atol=1e-4)   # ~ulp of 1024.x
     np.testing.assert_allclose(rec["time"], ref["time"], rtol=2e-6, atol=1e-12)
@@ -86,4 +107,11 @@ def compare(rec, ref):
     tol = REL_TOL * np.maximum(np.abs(ref["rgb"]), ABS_FLOOR)
     ok = (d <= tol).all(axis=1)
     rel = (d / np.maximum(np.abs(ref["rgb"]), ABS_FLOOR)).max(axis=1)
-    return ok.mean(), (rel[ok].max() if ok.any() else np.inf), np.nonzero(~ok)[0]
+    unexplained = ~ok if explained is None else (~ok & ~np.asarray(explained, bool))
+    worst = float(rel[ok | unexplained].max()) if (ok | unexplained).any() else 0.0
+    if label:
+        REPORT[label] = {"lanes": int(ok.size), "fraction_within_1e-4": float(ok.mean()), "worst_rel_unexplained": worst,
+                         "outside": int((~ok).sum()), "outside_explained_by_oracle_agreement": int((~ok & ~unexplained).sum()),
+                         "median_rel": float(np.median(rel)), "p99_rel": float(np.quantile(rel, 0.99))}
+        print(f"[parity] {label}: {ok.mean():.4f} of {ok.size} lanes within 1e-4, worst unexplained {worst:.2e}")
+    return ok.mean(), worst, np.nonzero(~ok)[0]

@@ -47,6 +47,8 @@ def lib() -> C.CDLL:
             "dtof_oracle_scene_destroy": (None, [C.c_void_p]),
             "dtof_oracle_trace_samples": (C.c_int, [C.c_void_p, C.POINTER(_abi.Params), C.POINTER(u64), u32,
                                                     C.POINTER(_abi.SampleRecord)]),
+            "dtof_oracle_trace_samples_pass": (C.c_int, [C.c_void_p, C.POINTER(_abi.Params), C.POINTER(u64), u32, u32,
+                                                         C.POINTER(_abi.SampleRecord)]),
             "dtof_oracle_render": (C.c_int, [C.c_void_p, C.POINTER(_abi.Params), C.c_int, fp, fp]),
             "dtof_oracle_get_stats": (None, [C.c_void_p, C.POINTER(_abi.Stats)]),
         }
@@ -65,11 +67,11 @@ class OracleScene:
             lib().dtof_oracle_scene_destroy(self.h)
             self.h = None
 
-    def trace(self, params, lanes) -> np.ndarray:
+    def trace(self, params, lanes, pass_index: int = 0) -> np.ndarray:
         lanes = np.ascontiguousarray(lanes, np.uint64)
         out = np.zeros(lanes.size, _abi.SAMPLE_RECORD_DTYPE)
-        rc = lib().dtof_oracle_trace_samples(self.h, C.byref(params), lanes.ctypes.data_as(C.POINTER(C.c_uint64)),
-                                             lanes.size, out.ctypes.data_as(C.POINTER(_abi.SampleRecord)))
+        rc = lib().dtof_oracle_trace_samples_pass(self.h, C.byref(params), lanes.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                                  lanes.size, pass_index, out.ctypes.data_as(C.POINTER(_abi.SampleRecord)))
         if rc:
             raise RuntimeError(f"oracle trace_samples failed: {rc}")
         return out

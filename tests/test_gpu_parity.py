@@ -29,26 +29,85 @@ def test_cuda_lanes_match_reference_and_oracle(ctx, name):
     scene, params, ref = gu.load_case(name)
     flat = ctx.upload(scene)
     rec = ctx.trace_samples(params, ref["lanes"])
-    frac, worst, bad = gu.compare(rec, ref)
+    orc = oracle_lib.OracleScene(flat, 0).trace(params, ref["lanes"])
+    # a lane where CUDA and the oracle agree with each other but not with the reference is a triangle-edge / tie
+    # decision on which Embree differs from any other BVH; every other lane must stay within OUTLIER_TOL
+    same_as_oracle = (np.abs(rec["rgb"].astype(np.float64) - orc["rgb"]) <=
+                      gu.REL_TOL * np.maximum(np.abs(orc["rgb"]), gu.ABS_FLOOR)).all(axis=1)
+    frac, worst, bad = gu.compare(rec, ref, label=f"cuda:{name}", explained=same_as_oracle)
     assert frac >= gu.min_fraction(name, 0.99), f"{name}: {len(bad)} lanes differ from the reference run: {ref['lanes'][bad][:8]}"
-    assert worst <= gu.REL_TOL
+    assert worst <= gu.OUTLIER_TOL, f"{name}: an unexplained lane is {worst:.2e} away from the reference"
     # against the oracle: identical streams and hit arithmetic; the shading arithmetic after the hit uses the SFU
     # approximations the reference's CUDA variants use (<= 2 ulp per op, csrc/dtof_device.cuh), so the comparison is
     # statistical: the same 1e-4 bound as against the reference on >= 99 % of lanes, a median at rounding level and
     # p90 <= 1e-5 (measured: p50 ~1e-7, p90 ~1e-6, p99 1e-5 .. 8e-5 for the 150 MHz cases -- one ulp of a 10 m path
     # length is 3e-6 rad of phase there)
-    orc = oracle_lib.OracleScene(flat, 0).trace(params, ref["lanes"])
     d = np.abs(rec["rgb"].astype(np.float64) - orc["rgb"])
     scale = np.maximum(np.abs(orc["rgb"]), gu.ABS_FLOOR)
     ok = (d <= gu.REL_TOL * scale).all(axis=1)
     assert ok.mean() >= gu.min_fraction(name, 0.99), f"{name}: CUDA vs oracle mismatch on lanes {ref['lanes'][~ok][:8]}"
     rel = (d / scale).max(axis=1)
+    # lanes outside 1e-4 of the ORACLE are bounded too, unless the two took a different decision (depth / draw count)
+    flipped = (rec["depth"] != orc["depth"]) | (rec["rng_draws"] != orc["rng_draws"])
+    assert rel[~flipped].max() <= gu.OUTLIER_TOL, f"{name}: same decisions, but {rel[~flipped].max():.2e} away from the oracle"
+    gu.REPORT[f"cuda-vs-oracle:{name}"] = {"fraction_within_1e-4": float(ok.mean()), "worst_rel_same_decisions": float(rel[~flipped].max()),
+                                           "decision_flips": int(flipped.sum()), "median_rel": float(np.median(rel))}
     assert np.median(rel) <= 1e-6 and np.quantile(rel, 0.9) <= 1e-5, (np.median(rel), np.quantile(rel, 0.9))
     assert np.array_equal(rec["depth"][ok], orc["depth"][ok])
     assert np.array_equal(rec["rng_draws"][ok], orc["rng_draws"][ok])   # identical stream consumption
     np.testing.assert_array_equal(rec["time"], orc["time"])               # sampler + camera are bit-exact
     np.testing.assert_array_equal(rec["sample_pos"], orc["sample_pos"])
     np.testing.assert_array_equal(rec["ray_d"], orc["ray_d"])
+
+
+@pytest.mark.parametrize("name", gu.pass_case_names())
+def test_cuda_every_pass_matches_reference_and_oracle(ctx, name):
+    """SURVEY 8(a) row a7 beyond pass 0: the C4 (2 x 2048 spp) and C5 (2 x 512 spp) pass structures and a 4-pass case, all
+    four time-sampling modes. dtof_trace_samples_pass replays a lane's earlier passes (streams persist, src/render/
+    integrator.cpp:299-308; sample index / dimension reset, src/render/sampler.cpp:52-55,94-103) -- the same code path
+    (LaneSampler::next_time(pass), csrc/dtof_device.cuh) the production kernels run for pass >= 1."""
+    import oracle_lib
+    scene, params, ref = gu.load_case(name, multipass=True)
+    flat = ctx.upload(scene)
+    osc = oracle_lib.OracleScene(flat, 0)
+    for k in range(int(ref["pass"].max()) + 1):
+        sub = gu.select(ref, ref["pass"] == k)
+        rec = ctx.trace_samples(params, sub["lanes"], k)
+        orc = osc.trace(params, sub["lanes"], k)
+        same = (np.abs(rec["rgb"].astype(np.float64) - orc["rgb"]) <= gu.REL_TOL * np.maximum(np.abs(orc["rgb"]), gu.ABS_FLOOR)).all(axis=1)
+        frac, worst, bad = gu.compare(rec, sub, label=f"cuda:2p:{name}:pass{k}", explained=same)
+        assert frac >= 0.99 and worst <= gu.OUTLIER_TOL, f"{name} pass {k}: lanes {sub['lanes'][bad][:8]}"
+        assert same.mean() >= 0.99
+        np.testing.assert_array_equal(rec["time"], orc["time"])            # sampler of pass k: bit-exact
+        np.testing.assert_array_equal(rec["sample_pos"], orc["sample_pos"])
+        np.testing.assert_array_equal(rec["ray_d"], orc["ray_d"])
+        assert np.array_equal(rec["rng_draws"][same], orc["rng_draws"][same])
+
+
+@pytest.mark.parametrize("scene_name,kw", [
+    ("c4_domino", dict(resx=1024, resy=1024, spp=4096, wave="trapezoidal", tsm="antithetic_mirror", shift=0.0, w_g=150)),
+    ("c5_slabroom", dict(resx=2048, resy=2048, spp=1024)),
+    ("c5_slabroom", dict(resx=2048, resy=2048, spp=1024, tsm="stratified", shift=0.0, pcn=4)),
+])
+def test_cuda_two_pass_film_window_matches_oracle(ctx, scene_name, kw):
+    """The PRODUCTION render (all passes, film splat) over a window of lanes of the full-size two-pass wavefront against
+    the oracle's render of the same window: pass >= 1 through the very kernels the bench runs."""
+    import oracle_lib
+    scene = dt.load_file(os.path.join(gu.SCENES, scene_name + ".xml"), **kw)
+    flat = ctx.upload(scene)
+    base = scene.integrator.params(scene.sensor.sampler, seed=3)
+    pi = ctx.pass_info(base)
+    assert pi.n_passes == 2
+    w = flat.width
+    first_px = (flat.height // 2) * w + w // 2 - 24      # 48 pixels of one row in the middle of the frame
+    lo, hi = first_px * pi.spp_per_pass, (first_px + 48) * pi.spp_per_pass
+    p = scene.integrator.params(scene.sensor.sampler, seed=3, lane_begin=lo, lane_end=hi)
+    rgbw = ctx.render(flat, p, develop=False)
+    ref = oracle_lib.OracleScene(flat).render(p, develop=False)
+    assert abs(float(rgbw[..., 3].sum()) - 48 * pi.spp_per_pass * 2) < 1e-3 * 48 * pi.spp_per_pass * 2   # both passes landed
+    scale = np.abs(ref[..., :3]).max()
+    assert np.abs(rgbw[..., :3] - ref[..., :3]).max() <= 2e-4 * scale
+    assert np.abs(rgbw[..., 3] - ref[..., 3]).max() <= 1e-4 * ref[..., 3].max()
 
 
 @pytest.mark.parametrize("name", FULL)

@@ -15,9 +15,9 @@ def test_oracle_matches_reference_lanes(name):
     scene, params, ref = gu.load_case(name)
     flat = scene.flatten()
     rec = oracle_lib.OracleScene(flat, 0).trace(params, ref["lanes"])
-    frac, worst, bad = gu.compare(rec, ref)
+    frac, worst, bad = gu.compare(rec, ref, label=f"oracle:{name}")
     assert frac >= gu.min_fraction(name, 1.0), f"{name}: lanes {ref['lanes'][bad][:8]} differ from the reference"
-    assert worst <= gu.REL_TOL
+    assert worst <= (gu.REL_TOL if gu.min_fraction(name, 1.0) == 1.0 else 3e-4)   # worst over ALL lanes
     # the oracle's own BVH must not change a single bit
     rec_bvh = oracle_lib.OracleScene(flat, 1).trace(params, ref["lanes"])
     assert np.array_equal(rec_bvh["rgb"], rec["rgb"])
@@ -55,3 +55,23 @@ def test_pass_split_follows_reference():
     flat.desc.film.width = flat.desc.film.height = 2048
     params.sample_count = 16384
     assert oracle_lib.lib().dtof_oracle_pass_info(C.byref(flat.desc), C.byref(params), C.byref(pi)) != 0
+
+
+@pytest.mark.parametrize("name", gu.pass_case_names())
+def test_oracle_matches_reference_in_every_pass(name):
+    """Multi-pass renders (C4: 2 x 2048 spp, C5: 2 x 512 spp, a 4-pass case; all four time-sampling modes): the streams
+    continue from pass to pass, sample_index = pass * spp_per_pass + idx % spp_per_pass, the dimension index restarts
+    (src/render/integrator.cpp:299-308, src/render/sampler.cpp:52-55,94-103, src/samplers/correlated.cpp:92-153)."""
+    scene, params, ref = gu.load_case(name, multipass=True)
+    osc = oracle_lib.OracleScene(scene.flatten(), 0)
+    assert ref["pass"].max() >= 1
+    for k in range(int(ref["pass"].max()) + 1):
+        sub = gu.select(ref, ref["pass"] == k)
+        rec = osc.trace(params, sub["lanes"], k)
+        frac, worst, bad = gu.compare(rec, sub, label=f"oracle:2p:{name}:pass{k}")
+        # the 150 MHz case (c4): one ulp of a 10 m path length is already 3e-6 rad of phase, a lane in 200 lands at 1.3e-4
+        assert frac >= 0.99 and worst <= 3e-4, f"{name} pass {k}: lanes {sub['lanes'][bad][:8]} differ"
+    # the time sample of pass k is not the time sample of pass 0 (the streams really moved on)
+    t0 = osc.trace(params, ref["lanes"][ref["pass"] == 0], 0)["time"]
+    t1 = osc.trace(params, ref["lanes"][ref["pass"] == 0], 1)["time"]
+    assert (t0 != t1).mean() > 0.9
