@@ -287,6 +287,20 @@ uint32_t dtof_abi_version(void);
 /* Create / destroy a context bound to CUDA device `device`. */
 dtof_status dtof_create(dtof_ctx **out, int device);
 void dtof_destroy(dtof_ctx *ctx);
+
+/* One context over SEVERAL GPUs of one node, driven by one host thread (what a plugin inside the reference's single
+ * `mitsuba` process needs to use the whole box; Integrator::render is one call, src/render/integrator.cpp:104-347).
+ * devices[0] is the primary device: it receives the result. The scene is replicated (dtof_upload_scene flattens and builds
+ * the BVH once, then copies it to every device); dtof_render / dtof_render_device shard ONE render over the devices --
+ * by sample slots in whole correlate groups when spp_per_pass divides by n_devices * lcm(tcn, pcn), else by interleaved
+ * 64-pixel tiles; all passes of a lane stay on one device -- and device 0 sums the partial films, reading the peers'
+ * films over NVLink (P2P) where the devices can address each other, through a staging copy otherwise.
+ * dtof_render_multi_pass deals its renders (seeds) round-robin to the devices and sums the partial means.
+ * dtof_update_instances applies to every device. Per-lane records, counters and timings refer to device 0.
+ * params->shard_block must be 0 (the context shards by itself); a lane window (lane_begin / lane_end) is honoured.
+ * n_devices == 1 is the same as dtof_create. At most 16 devices. */
+dtof_status dtof_create_multi(dtof_ctx **out, const int *devices, uint32_t n_devices);
+uint32_t dtof_device_count(const dtof_ctx *ctx);
 const char *dtof_last_error(const dtof_ctx *ctx);
 
 /* Flatten, build the two-level BVH and upload everything to HBM. May be called again to replace the scene. */

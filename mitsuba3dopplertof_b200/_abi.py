@@ -137,6 +137,8 @@ _ctx = C.c_void_p
 DTOF_SYMBOLS = {
     "dtof_abi_version": (C.c_uint32, []),
     "dtof_create": (C.c_int, [C.POINTER(_ctx), C.c_int]),
+    "dtof_create_multi": (C.c_int, [C.POINTER(_ctx), C.POINTER(C.c_int), C.c_uint32]),
+    "dtof_device_count": (C.c_uint32, [_ctx]),
     "dtof_destroy": (None, [_ctx]),
     "dtof_last_error": (C.c_char_p, [_ctx]),
     "dtof_upload_scene": (C.c_int, [_ctx, C.POINTER(SceneDesc)]),

@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/dtof.h"
@@ -225,6 +226,31 @@ __global__ void develop_accumulate_kernel(const float4 *__restrict__ rgbw, float
     img[3 * i + 2] = b;
 }
 
+// Multi-device contexts: dst += the peers' partial results. The sources are peer-device pointers read over NVLink
+// (P2P loads) or staging copies on this device; the summation order is fixed (device 0, 1, 2, ...).
+constexpr int kMaxPeers = 15;
+struct PeerPtrs {
+    const float *p[kMaxPeers];
+};
+__global__ void peer_reduce_kernel(float *__restrict__ dst, const __grid_constant__ PeerPtrs src, int n_src, size_t n) {
+    const size_t stride = (size_t) gridDim.x * blockDim.x;
+    const size_t n4 = n / 4;
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 a = reinterpret_cast<float4 *>(dst)[i];
+        for (int k = 0; k < n_src; ++k) {
+            const float4 b = reinterpret_cast<const float4 *>(src.p[k])[i];
+            a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
+        }
+        reinterpret_cast<float4 *>(dst)[i] = a;
+    }
+    for (size_t i = n4 * 4 + (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float a = dst[i];
+        for (int k = 0; k < n_src; ++k)
+            a += src.p[k][i];
+        dst[i] = a;
+    }
+}
+
 } // namespace
 
 // ==================================================================================================
@@ -273,6 +299,13 @@ struct dtof_ctx {
     cudaEvent_t wf_ev_start = nullptr, wf_ev_done[kWfMaxSets] = {};
     uint32_t *wf_host_count = nullptr;   // pinned, one word per set
     int last_pipeline = 0;               // 0 = fused kernel, 1 = wavefront
+    // multi-device context (dtof_create_multi): this context is device 0 of the group and owns one full context per
+    // further device; the scene is replicated, a render is sharded over all of them and summed here
+    std::vector<dtof_ctx *> peers;
+    std::vector<int> peer_access;        // per peer: 1 = device 0 reads its film directly over NVLink (P2P), 0 = staged copy
+    void *d_stage = nullptr;             // staging film on device 0 for peers without P2P access
+    cudaEvent_t ev_done = nullptr;       // "this device's share of the render is complete"
+    int last_shard_mode = -1;            // 0 = sample slots, 1 = pixel tiles (multi-device renders)
 };
 
 namespace {
@@ -739,6 +772,113 @@ dtof_status launch_render(dtof_ctx *ctx, const dtof_params *p, float *d_rgbw, cu
     return DTOF_OK;
 }
 
+// ---- multi-device contexts (dtof_create_multi) -------------------------------------------------------------------------
+// dst (on device 0, `n_floats` floats) += the same buffer of every peer, after the peer has signalled ev_done. Peers the
+// device can address are read in place over NVLink; the others are copied into a staging buffer first.
+dtof_status reduce_from_peers(dtof_ctx *ctx, float *dst, size_t n_floats, bool image, cudaStream_t stream) {
+    CU(cudaSetDevice(ctx->device));
+    PeerPtrs src{};
+    size_t n_staged = 0;
+    for (size_t k = 0; k < ctx->peers.size(); ++k)
+        n_staged += ctx->peer_access[k] ? 0 : 1;
+    if (n_staged && !ctx->d_stage)
+        CU(cudaMalloc(&ctx->d_stage, n_staged * ctx->film_px * 4 * sizeof(float)));
+    size_t staged = 0;
+    for (size_t k = 0; k < ctx->peers.size(); ++k) {
+        dtof_ctx *p = ctx->peers[k];
+        const float *buf = image ? p->d_img : p->d_rgbw;
+        CU(cudaStreamWaitEvent(stream, p->ev_done, 0));
+        if (ctx->peer_access[k]) {
+            src.p[k] = buf;
+        } else {
+            float *st = (float *) ctx->d_stage + staged++ * ctx->film_px * 4;
+            CU(cudaMemcpyPeerAsync(st, ctx->device, buf, p->device, n_floats * sizeof(float), stream));
+            src.p[k] = st;
+        }
+    }
+    const int grid = (int) std::min<size_t>((n_floats / 4 + 255) / 256 + 1, (size_t) ctx->sm_count * 8);
+    peer_reduce_kernel<<<grid, 256, 0, stream>>>(dst, src, (int) ctx->peers.size(), n_floats);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(ctx->ev_done, stream));   // on device 0: "the peers' buffers have been read"
+    return DTOF_OK;
+}
+
+// Runs job(i, context of device i) for every device of the group: device 0 on the calling thread, the peers on one
+// thread each (enqueueing a render is thousands of launches for the wavefront pipeline; the devices must not wait for
+// each other's host work). Every job starts by waiting for device 0's last reduce, which read the peer's buffers.
+template <typename Job> dtof_status for_each_device(dtof_ctx *ctx, Job job) {
+    const size_t n = 1 + ctx->peers.size();
+    std::vector<dtof_status> st(n, DTOF_OK);
+    auto run = [&](size_t i) {
+        dtof_ctx *c = i ? ctx->peers[i - 1] : ctx;
+        if (cudaSetDevice(c->device) != cudaSuccess) {
+            st[i] = DTOF_ERR_CUDA;
+            return;
+        }
+        if (i)
+            cudaStreamWaitEvent(0, ctx->ev_done, 0);
+        st[i] = job(i, c);
+        if (i && st[i] == DTOF_OK && cudaEventRecord(c->ev_done, 0) != cudaSuccess)
+            st[i] = DTOF_ERR_CUDA;
+    };
+    std::vector<std::thread> th;
+    for (size_t i = 1; i < n; ++i)
+        th.emplace_back(run, i);
+    run(0);
+    for (auto &t : th)
+        t.join();
+    cudaSetDevice(ctx->device);
+    for (size_t i = 0; i < n; ++i)
+        if (st[i] != DTOF_OK)
+            return i ? fail(ctx, st[i], "device %d: %s", ctx->peers[i - 1]->device, ctx->peers[i - 1]->error.c_str()) : st[i];
+    return DTOF_OK;
+}
+
+// ONE render sharded over the devices of the group: by sample slots -- every device renders
+// spp_per_pass / n slots of every pixel, whole correlate groups -- when spp_per_pass divides that way, else by
+// interleaved 64-pixel tiles. All passes of a lane stay on one device. Device 0 accumulates into `d_rgbw0` (zeroed first if
+// `zero0`), the peers into their own films; then device 0 adds the peers' films to `d_rgbw0`. Asynchronous.
+dtof_status render_sharded(dtof_ctx *ctx, const dtof_params *params, float *d_rgbw0, bool zero0, cudaStream_t stream0) {
+    const uint32_t n = 1u + (uint32_t) ctx->peers.size();
+    if (params->shard_block)
+        return fail(ctx, DTOF_ERR_INVALID, "a multi-device context shards the render itself: shard_block must be 0");
+    dtof_pass_info pi;
+    if (pass_info(ctx->film, *params, &pi))
+        return fail(ctx, DTOF_ERR_INVALID, "sample_count should be a multiple of samples_per_wavefront!");
+    uint64_t a = params->time_correlate_number, b = params->path_correlate_number, g = a, h = b;
+    while (h) {
+        const uint64_t t = g % h;
+        g = h, h = t;
+    }
+    const uint64_t group = a / g * b;   // lcm(tcn, pcn): antithetic / correlated groups stay on one device
+    dtof_params base = *params;
+    base.shard_count = n;
+    if (pi.spp_per_pass % (n * group) == 0) {
+        base.shard_block = pi.spp_per_pass / n;
+        ctx->last_shard_mode = 0;
+    } else {
+        base.shard_block = (uint64_t) pi.spp_per_pass * 64u;
+        ctx->last_shard_mode = 1;
+    }
+    dtof_status s = for_each_device(ctx, [&](size_t i, dtof_ctx *c) -> dtof_status {
+        dtof_ctx *ctx = c;   // for CU()
+        dtof_params p = base;
+        p.shard_index = (uint32_t) i;
+        float *film = i ? c->d_rgbw : d_rgbw0;
+        cudaStream_t st = i ? (cudaStream_t) 0 : stream0;
+        if (i || zero0)
+            CU(cudaMemsetAsync(film, 0, c->film_px * 4 * sizeof(float), st));
+        return launch_render(c, &p, film, st, nullptr, nullptr, 0);
+    });
+    if (s != DTOF_OK)
+        return s;
+    if ((s = reduce_from_peers(ctx, d_rgbw0, ctx->film_px * 4, false, stream0)) != DTOF_OK)
+        return s;
+    CU(cudaEventRecord(ctx->ev1, stream0));   // dtof_last_kernel_ms: device 0's share + waiting for the peers + the reduce
+    return DTOF_OK;
+}
+
 } // namespace
 
 namespace {
@@ -1054,6 +1194,43 @@ extern "C" {
 
 uint32_t dtof_abi_version(void) { return DTOF_ABI_VERSION; }
 
+dtof_status dtof_create_multi(dtof_ctx **out, const int *devices, uint32_t n_devices) {
+    if (!out || !devices || n_devices == 0 || n_devices > (uint32_t) kMaxPeers + 1)
+        return DTOF_ERR_INVALID;
+    *out = nullptr;
+    for (uint32_t i = 0; i < n_devices; ++i)
+        for (uint32_t j = 0; j < i; ++j)
+            if (devices[i] == devices[j])
+                return DTOF_ERR_INVALID;
+    dtof_ctx *ctx = nullptr;
+    dtof_status s = dtof_create(&ctx, devices[0]);
+    if (s != DTOF_OK)
+        return s;
+    for (uint32_t i = 1; i < n_devices; ++i) {
+        dtof_ctx *p = nullptr;
+        if ((s = dtof_create(&p, devices[i])) != DTOF_OK) {
+            dtof_destroy(ctx);
+            return s;
+        }
+        ctx->peers.push_back(p);
+        // device 0 reads the peer's film directly when the two can address each other (NVLink / NVSwitch)
+        int can = 0;
+        cudaSetDevice(devices[0]);
+        if (cudaDeviceCanAccessPeer(&can, devices[0], devices[i]) == cudaSuccess && can) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(devices[i], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                can = 0;
+            cudaGetLastError();
+        }
+        ctx->peer_access.push_back(can ? 1 : 0);
+    }
+    cudaSetDevice(devices[0]);
+    *out = ctx;
+    return DTOF_OK;
+}
+
+uint32_t dtof_device_count(const dtof_ctx *ctx) { return ctx ? 1u + (uint32_t) ctx->peers.size() : 0u; }
+
 dtof_status dtof_create(dtof_ctx **out, int device) {
     if (!out)
         return DTOF_ERR_INVALID;
@@ -1068,7 +1245,8 @@ dtof_status dtof_create(dtof_ctx **out, int device) {
     if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess ||
         cudaMalloc(&ctx->d_counter, sizeof(unsigned long long)) != cudaSuccess ||
         cudaMalloc(&ctx->d_stats, sizeof(Counters)) != cudaSuccess || cudaEventCreate(&ctx->ev0) != cudaSuccess ||
-        cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+        cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming) != cudaSuccess) {
         delete ctx;
         return DTOF_ERR_CUDA;
     }
@@ -1081,7 +1259,12 @@ dtof_status dtof_create(dtof_ctx **out, int device) {
 void dtof_destroy(dtof_ctx *ctx) {
     if (!ctx)
         return;
+    for (dtof_ctx *p : ctx->peers)
+        dtof_destroy(p);
+    ctx->peers.clear();
     cudaSetDevice(ctx->device);
+    if (ctx->d_stage) cudaFree(ctx->d_stage);
+    if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
     free_scene(ctx);
     free_wavefront(ctx);
     if (ctx->wf_host_count) cudaFreeHost(ctx->wf_host_count);
@@ -1099,14 +1282,10 @@ void dtof_destroy(dtof_ctx *ctx) {
 
 const char *dtof_last_error(const dtof_ctx *ctx) { return ctx ? ctx->error.c_str() : "null context"; }
 
-dtof_status dtof_upload_scene(dtof_ctx *ctx, const dtof_scene_desc *sc) {
-    if (!ctx || !sc)
-        return DTOF_ERR_INVALID;
+// Device half of dtof_upload_scene: copies a prepared (flattened, BVH built) scene to this context's GPU.
+static dtof_status upload_prepared(dtof_ctx *ctx, const dtof_scene_desc *sc, HostScene &H) {
+    dtof_status s;
     CU(cudaSetDevice(ctx->device));
-    HostScene H;
-    dtof_status s = prepare_scene(ctx, sc, H);
-    if (s != DTOF_OK)
-        return s;
     std::vector<MeshRec> &meshes = H.meshes;
     std::vector<BsdfRec> &bsdfs = H.bsdfs;
     std::vector<EmitterRec> &emitters = H.emitters;
@@ -1185,6 +1364,21 @@ dtof_status dtof_upload_scene(dtof_ctx *ctx, const dtof_scene_desc *sc) {
     return DTOF_OK;
 }
 
+dtof_status dtof_upload_scene(dtof_ctx *ctx, const dtof_scene_desc *sc) {
+    if (!ctx || !sc)
+        return DTOF_ERR_INVALID;
+    HostScene H;   // flattened + BVH built ONCE, then copied to every device of the context
+    dtof_status s = prepare_scene(ctx, sc, H);
+    if (s != DTOF_OK)
+        return s;
+    if ((s = upload_prepared(ctx, sc, H)) != DTOF_OK)
+        return s;
+    for (dtof_ctx *p : ctx->peers)
+        if ((s = upload_prepared(p, sc, H)) != DTOF_OK)
+            return fail(ctx, s, "device %d: %s", p->device, p->error.c_str());
+    return DTOF_OK;
+}
+
 dtof_status dtof_scene_info_for(const dtof_scene_desc *sc, dtof_scene_info *out, char *err, uint32_t err_len) {
     if (!sc || !out)
         return DTOF_ERR_INVALID;
@@ -1255,6 +1449,12 @@ dtof_status dtof_update_instances(dtof_ctx *ctx, uint32_t first, uint32_t n, con
         CU(cudaMemcpy(ctx->d_boxes, tl.inst_box.data(), tl.inst_box.size() * sizeof(InstBox), cudaMemcpyHostToDevice));
     ctx->ds.root = tl.root;
     ctx->bvh_depth = ctx->blas_depth + tl.tlas_depth;
+    for (dtof_ctx *p : ctx->peers) {
+        dtof_status ps = dtof_update_instances(p, first, n, instances);
+        if (ps != DTOF_OK)
+            return fail(ctx, ps, "device %d: %s", p->device, p->error.c_str());
+    }
+    CU(cudaSetDevice(ctx->device));
     return DTOF_OK;
 }
 
@@ -1282,6 +1482,8 @@ dtof_status dtof_render_device(dtof_ctx *ctx, const dtof_params *params, float *
     if (s != DTOF_OK)
         return s;
     CU(cudaSetDevice(ctx->device));
+    if (!ctx->peers.empty())
+        return render_sharded(ctx, params, d_rgbw, false, (cudaStream_t) stream);
     return launch_render(ctx, params, d_rgbw, (cudaStream_t) stream, nullptr, nullptr, 0);
 }
 
@@ -1309,9 +1511,14 @@ dtof_status dtof_render(dtof_ctx *ctx, const dtof_params *params, float *rgbw_ou
     if (s != DTOF_OK)
         return s;
     CU(cudaSetDevice(ctx->device));
-    CU(cudaMemsetAsync(ctx->d_rgbw, 0, ctx->film_px * 4 * sizeof(float), 0));
-    if ((s = launch_render(ctx, params, ctx->d_rgbw, 0, nullptr, nullptr, 0)) != DTOF_OK)
-        return s;
+    if (!ctx->peers.empty()) {
+        if ((s = render_sharded(ctx, params, ctx->d_rgbw, true, 0)) != DTOF_OK)
+            return s;
+    } else {
+        CU(cudaMemsetAsync(ctx->d_rgbw, 0, ctx->film_px * 4 * sizeof(float), 0));
+        if ((s = launch_render(ctx, params, ctx->d_rgbw, 0, nullptr, nullptr, 0)) != DTOF_OK)
+            return s;
+    }
     if (image_out && (s = dtof_develop_device(ctx, ctx->d_rgbw, ctx->d_img, nullptr)) != DTOF_OK)
         return s;
     if (rgbw_out)
@@ -1335,16 +1542,31 @@ dtof_status dtof_render_multi_pass(dtof_ctx *ctx, const dtof_params *params, uin
     CU(cudaSetDevice(ctx->device));
     const size_t n = ctx->film_px;
     const float scale = 1.f / (float) n_renders;
-    for (uint32_t i = 0; i < n_renders; ++i) {
-        dtof_params p = *params;
-        p.seed = params->seed + i;
-        CU(cudaMemsetAsync(ctx->d_rgbw, 0, n * 4 * sizeof(float), 0));
-        if ((s = launch_render(ctx, &p, ctx->d_rgbw, 0, nullptr, nullptr, 0)) != DTOF_OK)
-            return s;
-        develop_accumulate_kernel<<<(unsigned) ((n + 255) / 256), 256>>>((const float4 *) ctx->d_rgbw, ctx->d_img, n, scale, i == 0);
-        ctx->launches++;
-        CU(cudaGetLastError());
-    }
+    // a multi-device context deals the renders (seeds) round-robin: device i develops and averages renders i, i + D, ...
+    // into its own image, device 0 then adds the partial means (mean of DEVELOPED images, as the tutorials' driver does)
+    const uint32_t n_dev = 1u + (uint32_t) ctx->peers.size();
+    s = for_each_device(ctx, [&](size_t dev, dtof_ctx *c) -> dtof_status {
+        dtof_ctx *ctx = c;   // for CU()
+        bool first = true;
+        for (uint32_t i = (uint32_t) dev; i < n_renders; i += n_dev, first = false) {
+            dtof_params p = *params;
+            p.seed = params->seed + i;
+            CU(cudaMemsetAsync(c->d_rgbw, 0, n * 4 * sizeof(float), 0));
+            dtof_status r = launch_render(c, &p, c->d_rgbw, 0, nullptr, nullptr, 0);
+            if (r != DTOF_OK)
+                return r;
+            develop_accumulate_kernel<<<(unsigned) ((n + 255) / 256), 256>>>((const float4 *) c->d_rgbw, c->d_img, n, scale, first);
+            c->launches++;
+            CU(cudaGetLastError());
+        }
+        if (first)   // more devices than renders: this one contributes nothing
+            CU(cudaMemsetAsync(c->d_img, 0, n * 3 * sizeof(float), 0));
+        return DTOF_OK;
+    });
+    if (s != DTOF_OK)
+        return s;
+    if (n_dev > 1 && (s = reduce_from_peers(ctx, ctx->d_img, n * 3, true, 0)) != DTOF_OK)
+        return s;
     CU(cudaMemcpyAsync(image_out, ctx->d_img, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, 0));
     CU(cudaStreamSynchronize(0));
     return DTOF_OK;

@@ -54,14 +54,27 @@ inline void pad_box(Box &b) {
     }
 }
 
+// centre / half extent of [lo, hi], the half extent rounded up so that [m - h, m + h] contains the interval
+inline void centre_half(float lo, float hi, float &m, float &h) {
+    if (!(lo <= hi)) {   // empty box: never hit
+        m = 0.f, h = -1.f;
+        return;
+    }
+    m = 0.5f * lo + 0.5f * hi;
+    h = std::max(hi - m, m - lo);
+    h = h * (1.f + 4.f * FLT_EPSILON) + FLT_MIN;
+}
+
 inline void set_child(BvhNode &n, int which, const Box &b, int32_t ref) {
     if (which == 0) {
-        n.c0_lox = b.lo[0], n.c0_hix = b.hi[0], n.c0_loy = b.lo[1], n.c0_hiy = b.hi[1];
-        n.c0_loz = b.lo[2], n.c0_hiz = b.hi[2];
+        centre_half(b.lo[0], b.hi[0], n.c0_mx, n.c0_hx);
+        centre_half(b.lo[1], b.hi[1], n.c0_my, n.c0_hy);
+        centre_half(b.lo[2], b.hi[2], n.c0_mz, n.c0_hz);
         n.child0 = ref;
     } else {
-        n.c1_lox = b.lo[0], n.c1_hix = b.hi[0], n.c1_loy = b.lo[1], n.c1_hiy = b.hi[1];
-        n.c1_loz = b.lo[2], n.c1_hiz = b.hi[2];
+        centre_half(b.lo[0], b.hi[0], n.c1_mx, n.c1_hx);
+        centre_half(b.lo[1], b.hi[1], n.c1_my, n.c1_hy);
+        centre_half(b.lo[2], b.hi[2], n.c1_mz, n.c1_hz);
         n.child1 = ref;
     }
 }

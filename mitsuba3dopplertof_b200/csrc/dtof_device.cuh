@@ -83,6 +83,13 @@ DTOF_DEV V3 operator/(V3 a, float s) {
     return v3(a.x * r, a.y * r, a.z * r);
 }
 #endif
+// rcp.approx that stays where it is written: leaving an instance recomputes the world-space reciprocal direction there
+// (rare) instead of keeping nine loop-invariant values live through the whole walk
+DTOF_DEV float frcp_here(float a) {
+    float r;
+    asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+    return r;
+}
 DTOF_DEV V3 fma3(V3 a, float s, V3 b) { return v3(fmaf(a.x, s, b.x), fmaf(a.y, s, b.y), fmaf(a.z, s, b.z)); }
 DTOF_DEV float dot3(V3 a, V3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
 DTOF_DEV V3 cross3(V3 a, V3 b) {
@@ -565,6 +572,40 @@ struct Hit {
     int32_t inst;
 };
 
+// ---- box test of one BVH node (both children) ----------------------------------------------------------------------
+// A child box is stored as centre m and half extent h per axis (dtof_layout.h). Per axis the ray's parameter interval is
+//     c = m * idir - o * idir  (one fma, `nd` = -o * idir),   [c - h |idir|, c + h |idir|]   (two fmas)
+// -- no min / max per axis: the lower end is the lower end whatever the sign of the direction. The fused kernel's walk
+// is bound by the half-rate ALU pipe that executes FMNMX / FSETP / SEL, not by issue slots (ncu: ALU 54 %, FMA 29 % of
+// peak over the whole kernel): the lo / hi form costs 20 min / max per node, this form 8, for 6 more fmas.
+// Conservative: the ABSOLUTE error of c (<= ulp(o * idir)) is bounded per ray by e2 = kSlabAbsErr * max |o * idir| and
+// added to the far side and to the best distance; the relative errors are covered by widening the far side by 3e-6
+// (the builder already rounds the half extents up and pads the boxes).
+constexpr float kSlabAbsErr = 2.4e-7f;   // 4 x 2^-24: both ends of the interval, with a factor 2 in hand
+constexpr float kSlabWiden = 1.000003f;
+struct RaySlab {
+    V3 id, nd, aid;
+    float e2;
+    DTOF_DEV void set(V3 o, V3 rid) {
+        id = rid;
+        nd = v3(-(o.x * rid.x), -(o.y * rid.y), -(o.z * rid.z));
+        aid = v3(fabsf(rid.x), fabsf(rid.y), fabsf(rid.z));
+        e2 = kSlabAbsErr * fmaxf(fmaxf(fabsf(nd.x), fabsf(nd.y)), fabsf(nd.z));
+    }
+};
+// n0 = child 0 {mx, hx, my, hy}, n1 = child 1 {mx, hx, my, hy}, n2 = {c0 mz, c0 hz, c1 mz, c1 hz}; `best_e` = best + e2
+DTOF_DEV void node_test(const float4 n0, const float4 n1, const float4 n2, const RaySlab &R, float best_e, bool &h0, bool &h1,
+                        float &t0n, float &t1n) {
+    const float c0x = fmaf(n0.x, R.id.x, R.nd.x), c0y = fmaf(n0.z, R.id.y, R.nd.y), c0z = fmaf(n2.x, R.id.z, R.nd.z);
+    const float c1x = fmaf(n1.x, R.id.x, R.nd.x), c1y = fmaf(n1.z, R.id.y, R.nd.y), c1z = fmaf(n2.z, R.id.z, R.nd.z);
+    t0n = fmaxf(fmaxf(fmaf(-n0.y, R.aid.x, c0x), fmaf(-n0.w, R.aid.y, c0y)), fmaxf(fmaf(-n2.y, R.aid.z, c0z), 0.f));
+    t1n = fmaxf(fmaxf(fmaf(-n1.y, R.aid.x, c1x), fmaf(-n1.w, R.aid.y, c1y)), fmaxf(fmaf(-n2.w, R.aid.z, c1z), 0.f));
+    const float t0f = fminf(fminf(fmaf(n0.y, R.aid.x, c0x), fmaf(n0.w, R.aid.y, c0y)), fmaf(n2.y, R.aid.z, c0z));
+    const float t1f = fminf(fminf(fmaf(n1.y, R.aid.x, c1x), fmaf(n1.w, R.aid.y, c1y)), fmaf(n2.w, R.aid.z, c1z));
+    h0 = t0n <= fminf(fmaf(t0f, kSlabWiden, R.e2), best_e);
+    h1 = t1n <= fminf(fmaf(t1f, kSlabWiden, R.e2), best_e);
+}
+
 // Moeller-Trumbore (include/mitsuba/render/mesh.h:342-365) against one stored triangle (p0 | e1 | e2), split into a
 // conservative pre-test and the exact reference arithmetic. The pre-test works on the un-normalised numerators
 // (U = tvec.pvec, V = d.qvec, D = det), never rejects a triangle the exact test accepts (margins >> the 2 ulp that
@@ -630,9 +671,8 @@ constexpr int kDone = 0x7fffffff;
 // "instance leaf": the ray is moved into the instance's space, a sentinel marks the way back.
 // Loop shape after Aila & Laine: a lane stays in the inner-node loop (popping included) until it holds a leaf.
 // `N`, `T`, `I` are the node / triangle / instance arrays (global memory, or their shared-memory copies).
-// SLAB_FMA selects the one-fma-per-plane slab test: it pays where node fetches come from L2 / HBM (+3.7 % on the
-// 4.2 M-triangle scene) and does nothing for the shared-memory scenes, whose walk then only loses registers.
-template <bool STATS, bool SLAB_FMA>
+// The box test is node_test() above.
+template <bool STATS>
 DTOF_DEV bool trace_bvh(const float4 *__restrict__ N, const float4 *__restrict__ T, const float4 *__restrict__ I,
                         int32_t root, const bool ANY, V3 o, V3 d, float tmax, float time, Hit &hit, Counters &st) {
     int stack[kStackSize];
@@ -640,11 +680,9 @@ DTOF_DEV bool trace_bvh(const float4 *__restrict__ N, const float4 *__restrict__
     int node = root;
     int cur_inst = -1;
     V3 ro = o, rd = d;                                       // ray in the current (world / instance) space
-    const V3 wid = v3(frcp(d.x), frcp(d.y), frcp(d.z));   // boxes are padded by 1e-5 relative: 1 ulp is immaterial
-    V3 id = wid;
-    const V3 wnd = v3(-(o.x * wid.x), -(o.y * wid.y), -(o.z * wid.z));   // SLAB_FMA only (dead code otherwise)
-    V3 nd = wnd;
-    float best = tmax;
+    RaySlab R;
+    R.set(o, v3(frcp(d.x), frcp(d.y), frcp(d.z)));
+    float best = tmax, best_e = best + R.e2;
     bool found = false;
     if (STATS) {
         if (ANY) st.rays_shadow++; else st.rays_closest++;
@@ -656,7 +694,9 @@ DTOF_DEV bool trace_bvh(const float4 *__restrict__ N, const float4 *__restrict__
         } else {                                                                                           \
             node = stack[--sp];                                                                            \
             if (node == kSentinel) { /* leave the instance: back to the world-space ray */                 \
-                ro = o, rd = d, id = wid, nd = wnd, cur_inst = -1;                                                   \
+                ro = o, rd = d, cur_inst = -1;                                                             \
+                R.set(o, v3(frcp_here(d.x), frcp_here(d.y), frcp_here(d.z)));                              \
+                best_e = best + R.e2;                                                                      \
                 node = sp ? stack[--sp] : kDone;                                                           \
             }                                                                                              \
         }                                                                                                  \
@@ -666,37 +706,14 @@ DTOF_DEV bool trace_bvh(const float4 *__restrict__ N, const float4 *__restrict__
         // ---- inner nodes (node in [0, kDone))
         while ((unsigned) node < (unsigned) kDone) {
             const float4 *np = N + 4 * (size_t) node;
-            float4 n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3];
+            const float4 n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3];
             if (STATS) st.nodes++;
-            float c0lx, c0hx, c0ly, c0hy, c0lz, c0hz, c1lx, c1hx, c1ly, c1hy, c1lz, c1hz, widen;
-            if (SLAB_FMA) {
-                // one fma per plane: b * idir - o * idir. Its absolute error (~6e-8 |o * idir|) is covered by the box
-                // padding where the origin is close to the plane and by the (wider) interval widening elsewhere.
-                c0lx = fmaf(n0.x, id.x, nd.x), c0hx = fmaf(n0.y, id.x, nd.x);
-                c0ly = fmaf(n0.z, id.y, nd.y), c0hy = fmaf(n0.w, id.y, nd.y);
-                c0lz = fmaf(n2.x, id.z, nd.z), c0hz = fmaf(n2.y, id.z, nd.z);
-                c1lx = fmaf(n1.x, id.x, nd.x), c1hx = fmaf(n1.y, id.x, nd.x);
-                c1ly = fmaf(n1.z, id.y, nd.y), c1hy = fmaf(n1.w, id.y, nd.y);
-                c1lz = fmaf(n2.z, id.z, nd.z), c1hz = fmaf(n2.w, id.z, nd.z);
-                widen = 1.000003f;
-            } else {
-                // (b - o) * idir form: purely relative rounding error, absorbed by the widened far side
-                c0lx = (n0.x - ro.x) * id.x, c0hx = (n0.y - ro.x) * id.x;
-                c0ly = (n0.z - ro.y) * id.y, c0hy = (n0.w - ro.y) * id.y;
-                c0lz = (n2.x - ro.z) * id.z, c0hz = (n2.y - ro.z) * id.z;
-                c1lx = (n1.x - ro.x) * id.x, c1hx = (n1.y - ro.x) * id.x;
-                c1ly = (n1.z - ro.y) * id.y, c1hy = (n1.w - ro.y) * id.y;
-                c1lz = (n2.z - ro.z) * id.z, c1hz = (n2.w - ro.z) * id.z;
-                widen = 1.0000005f;
-            }
-            float t0n = fmaxf(fmaxf(fminf(c0lx, c0hx), fminf(c0ly, c0hy)), fmaxf(fminf(c0lz, c0hz), 0.f));
-            float t0f = fminf(fminf(fmaxf(c0lx, c0hx), fmaxf(c0ly, c0hy)), fmaxf(c0lz, c0hz)) * widen;
-            float t1n = fmaxf(fmaxf(fminf(c1lx, c1hx), fminf(c1ly, c1hy)), fmaxf(fminf(c1lz, c1hz), 0.f));
-            float t1f = fminf(fminf(fmaxf(c1lx, c1hx), fmaxf(c1ly, c1hy)), fmaxf(c1lz, c1hz)) * widen;
-            bool h0 = t0n <= fminf(t0f, best), h1 = t1n <= fminf(t1f, best);
-            int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+            bool h0, h1;
+            float t0n, t1n;
+            node_test(n0, n1, n2, R, best_e, h0, h1, t0n, t1n);
+            const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
             if (h0 && h1) {
-                bool swap = t1n < t0n;
+                const bool swap = t1n < t0n;
                 stack[sp++] = swap ? c0 : c1;
                 node = swap ? c1 : c0;
             } else if (h0 || h1) {
@@ -715,8 +732,8 @@ DTOF_DEV bool trace_bvh(const float4 *__restrict__ N, const float4 *__restrict__
             const float4 *ip = I + 8 * (size_t) cur_inst;
             if (STATS) st.inst++;
             enter_instance(ip, o, d, time, ro, rd);
-            id = v3(frcp(rd.x), frcp(rd.y), frcp(rd.z));
-            nd = v3(-(ro.x * id.x), -(ro.y * id.y), -(ro.z * id.z));
+            R.set(ro, v3(frcp(rd.x), frcp(rd.y), frcp(rd.z)));
+            best_e = best + R.e2;
             stack[sp++] = kSentinel;
             node = __float_as_int(ip[6].z);
             continue;
@@ -733,6 +750,7 @@ DTOF_DEV bool trace_bvh(const float4 *__restrict__ N, const float4 *__restrict__
                 uint32_t gid = __float_as_uint(a.w);
                 if (t < best || !found || gid < hit.gid) {
                     best = t;
+                    best_e = t + R.e2;
                     hit.t = t;
                     hit.u = u;
                     hit.v = v;
@@ -755,9 +773,7 @@ DTOF_DEV bool trace_bvh(const float4 *__restrict__ N, const float4 *__restrict__
 //  * the traversal stack lives in shared memory, one 128-byte row per level and warp (slot = lane): a push / pop is
 //    conflict-free whatever the lanes' depths are (an L1-resident local-memory stack serialises over the distinct
 //    levels of a warp) and no stack traffic reaches L2 / DRAM;
-//  * the slab test is one fma per plane, b * idir - o * idir. Its ABSOLUTE error (<= ulp(o * idir) per plane) is
-//    bounded per ray by `e2` and added to the far side / the best distance, so the test stays conservative for any
-//    origin without relying on how much the builder padded the boxes;
+//  * the box test is node_test() above (centre / half-extent boxes, no per-axis min / max);
 //  * the world-space reciprocal direction is recomputed when a lane leaves an instance instead of being kept live.
 struct SmemScene {
     uint32_t N, T, I;   // byte addresses (shared window) of nodes, leaf-order triangles, instance records
@@ -781,15 +797,6 @@ DTOF_DEV uint32_t opaque_u32(uint32_t v) {
     asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
     return r;
 }
-// rcp.approx that stays where it is written: leaving an instance recomputes the world-space reciprocal direction there
-// (rare) instead of keeping nine loop-invariant values live through the whole walk
-DTOF_DEV float frcp_here(float a) {
-    float r;
-    asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
-    return r;
-}
-
-constexpr float kSlabAbsErr = 2.4e-7f;   // 4 x 2^-24: both sides of the interval, with a factor 2 in hand
 
 template <bool STATS>
 DTOF_DEV bool trace_bvh_smem(const SmemScene M, int32_t root, const bool ANY, V3 o, V3 d, float tmax, float time, Hit &hit,
@@ -798,10 +805,9 @@ DTOF_DEV bool trace_bvh_smem(const SmemScene M, int32_t root, const bool ANY, V3
     int node = root;
     int cur_inst = -1;
     V3 ro = o, rd = d;
-    V3 id = v3(frcp(d.x), frcp(d.y), frcp(d.z));
-    V3 nd = v3(-(o.x * id.x), -(o.y * id.y), -(o.z * id.z));
-    float e2 = kSlabAbsErr * fmaxf(fmaxf(fabsf(nd.x), fabsf(nd.y)), fabsf(nd.z));
-    float best = tmax, best_e = best + e2;
+    RaySlab R;
+    R.set(o, v3(frcp(d.x), frcp(d.y), frcp(d.z)));
+    float best = tmax, best_e = best + R.e2;
     bool found = false;
     if (STATS) {
         if (ANY) st.rays_shadow++; else st.rays_closest++;
@@ -815,10 +821,8 @@ DTOF_DEV bool trace_bvh_smem(const SmemScene M, int32_t root, const bool ANY, V3
             node = lds_stack(sp);                                                                          \
             if (node == kSentinel) { /* leave the instance: back to the world-space ray */                 \
                 ro = o, rd = d, cur_inst = -1;                                                             \
-                id = v3(frcp_here(d.x), frcp_here(d.y), frcp_here(d.z));                                   \
-                nd = v3(-(o.x * id.x), -(o.y * id.y), -(o.z * id.z));                                      \
-                e2 = kSlabAbsErr * fmaxf(fmaxf(fabsf(nd.x), fabsf(nd.y)), fabsf(nd.z));                    \
-                best_e = best + e2;                                                                        \
+                R.set(o, v3(frcp_here(d.x), frcp_here(d.y), frcp_here(d.z)));                              \
+                best_e = best + R.e2;                                                                      \
                 if (sp == M.stack) {                                                                       \
                     node = kDone;                                                                          \
                 } else {                                                                                   \
@@ -835,17 +839,9 @@ DTOF_DEV bool trace_bvh_smem(const SmemScene M, int32_t root, const bool ANY, V3
             const uint32_t na = M.N + ((uint32_t) node << 6);
             const float4 n0 = lds128(na), n1 = lds128(na + 16), n2 = lds128(na + 32), n3 = lds128(na + 48);
             if (STATS) st.nodes++;
-            const float c0lx = fmaf(n0.x, id.x, nd.x), c0hx = fmaf(n0.y, id.x, nd.x);
-            const float c0ly = fmaf(n0.z, id.y, nd.y), c0hy = fmaf(n0.w, id.y, nd.y);
-            const float c0lz = fmaf(n2.x, id.z, nd.z), c0hz = fmaf(n2.y, id.z, nd.z);
-            const float c1lx = fmaf(n1.x, id.x, nd.x), c1hx = fmaf(n1.y, id.x, nd.x);
-            const float c1ly = fmaf(n1.z, id.y, nd.y), c1hy = fmaf(n1.w, id.y, nd.y);
-            const float c1lz = fmaf(n2.z, id.z, nd.z), c1hz = fmaf(n2.w, id.z, nd.z);
-            const float t0n = fmaxf(fmaxf(fminf(c0lx, c0hx), fminf(c0ly, c0hy)), fmaxf(fminf(c0lz, c0hz), 0.f));
-            const float t0f = fmaf(fminf(fminf(fmaxf(c0lx, c0hx), fmaxf(c0ly, c0hy)), fmaxf(c0lz, c0hz)), 1.000003f, e2);
-            const float t1n = fmaxf(fmaxf(fminf(c1lx, c1hx), fminf(c1ly, c1hy)), fmaxf(fminf(c1lz, c1hz), 0.f));
-            const float t1f = fmaf(fminf(fminf(fmaxf(c1lx, c1hx), fmaxf(c1ly, c1hy)), fmaxf(c1lz, c1hz)), 1.000003f, e2);
-            const bool h0 = t0n <= fminf(t0f, best_e), h1 = t1n <= fminf(t1f, best_e);
+            bool h0, h1;
+            float t0n, t1n;
+            node_test(n0, n1, n2, R, best_e, h0, h1, t0n, t1n);
             const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
             if (h0 && h1) {
                 const bool swap = t1n < t0n;
@@ -881,10 +877,8 @@ DTOF_DEV bool trace_bvh_smem(const SmemScene M, int32_t root, const bool ANY, V3
             const M34 inv = inverse_m34(Mx);
             ro = xf_point(inv, o);
             rd = xf_vector(inv, d);
-            id = v3(frcp(rd.x), frcp(rd.y), frcp(rd.z));
-            nd = v3(-(ro.x * id.x), -(ro.y * id.y), -(ro.z * id.z));
-            e2 = kSlabAbsErr * fmaxf(fmaxf(fabsf(nd.x), fabsf(nd.y)), fabsf(nd.z));
-            best_e = best + e2;
+            R.set(ro, v3(frcp(rd.x), frcp(rd.y), frcp(rd.z)));
+            best_e = best + R.e2;
             sts_stack(sp, kSentinel);
             sp += 128u;
             node = __float_as_int(q6.z);
@@ -901,7 +895,7 @@ DTOF_DEV bool trace_bvh_smem(const SmemScene M, int32_t root, const bool ANY, V3
                 const uint32_t gid = __float_as_uint(a.w);
                 if (t < best || !found || gid < hit.gid) {
                     best = t;
-                    best_e = t + e2;
+                    best_e = t + R.e2;
                     hit.t = t;
                     hit.u = u;
                     hit.v = v;

@@ -16,10 +16,13 @@ namespace dtof {
 //   triangle leaf : code = (first_tri << 4) | count, count in [1, 15]
 //   instance leaf : code = (instance  << 4) | 0      (animated instances only; the static group's BLAS is linked
 //                                                     into the TLAS directly, so static geometry is single-level)
+// A child box is stored per axis as centre m and half extent h (rounded up: [m - h, m + h] contains the padded box):
+// the traversal's interval per axis is then c -/+ h |1/d| with c = (m - o) / d, without a min / max per axis
+// (dtof_device.cuh: node_test). An empty box (never hit) has h < 0.
 struct alignas(16) BvhNode {
-    float c0_lox, c0_hix, c0_loy, c0_hiy;   // child 0 box x/y
-    float c1_lox, c1_hix, c1_loy, c1_hiy;   // child 1 box x/y
-    float c0_loz, c0_hiz, c1_loz, c1_hiz;   // z of both
+    float c0_mx, c0_hx, c0_my, c0_hy;   // child 0 box x/y
+    float c1_mx, c1_hx, c1_my, c1_hy;   // child 1 box x/y
+    float c0_mz, c0_hz, c1_mz, c1_hz;   // z of both
     int32_t child0, child1, pad0, pad1;
 };
 static_assert(sizeof(BvhNode) == 64, "BvhNode must be 64 bytes");

@@ -39,7 +39,7 @@ DTOF_DEV bool trace_any_mode(const DeviceScene &S, const TravPtrs &P, bool any, 
     if (MODE == MODE_BVH_SMEM)
         return trace_bvh_smem<STATS>(P.S, S.root, any, o, d, tmax, time, hit, st);
 #endif
-    return trace_bvh<STATS, MODE == MODE_BVH_GLOBAL>(P.N, P.T, P.I, S.root, any, o, d, tmax, time, hit, st);
+    return trace_bvh<STATS>(P.N, P.T, P.I, S.root, any, o, d, tmax, time, hit, st);
 }
 
 // VelocityIntegrator::sample (src/integrators/velocity.cpp:113-127): the camera ray is intersected at t = 0 and at

@@ -176,7 +176,6 @@ __global__ void __launch_bounds__(kWfBlock) wf_generate_kernel(const __grid_cons
 // it is re-read from the queue when the lane leaves it.
 template <int MODE, bool ANY>
 __global__ void __launch_bounds__(kWfBlock, DTOF_WF_TRACE_CTAS) wf_trace_kernel(const __grid_constant__ WfArgs A) {
-    constexpr bool SLAB_FMA = MODE == MODE_BVH_GLOBAL;
     extern __shared__ float4 wf_smem[];
     const float4 *__restrict__ N = A.scene.nodes, *__restrict__ T = A.scene.tris, *__restrict__ I = A.scene.insts;
     if (MODE == MODE_BVH_SMEM) {
@@ -201,8 +200,10 @@ __global__ void __launch_bounds__(kWfBlock, DTOF_WF_TRACE_CTAS) wf_trace_kernel(
     int stack[kStackSize];
     int sp = 0, node = kDone, cur_inst = -1;
     uint32_t k = kWfMiss;
-    V3 ro = v3(0, 0, 0), rd = v3(0, 0, 1), id = v3(0, 0, 0), nd = v3(0, 0, 0);
-    float best = 0.f;
+    V3 ro = v3(0, 0, 0), rd = v3(0, 0, 1);
+    RaySlab R;
+    R.set(ro, v3(0, 0, 0));
+    float best = 0.f, best_e = 0.f;
     Hit hit;
     hit.t = 0.f, hit.u = 0.f, hit.v = 0.f, hit.gid = 0, hit.inst = -1;
     bool found = false, exhausted = false;
@@ -252,8 +253,8 @@ __global__ void __launch_bounds__(kWfBlock, DTOF_WF_TRACE_CTAS) wf_trace_kernel(
                     const float4 a = qo[k], b = qd[k];
                     ro = v3(a.x, a.y, a.z), rd = v3(b.x, b.y, b.z);
                     best = a.w;
-                    id = v3(frcp(rd.x), frcp(rd.y), frcp(rd.z));
-                    nd = v3(-(ro.x * id.x), -(ro.y * id.y), -(ro.z * id.z));
+                    R.set(ro, v3(frcp(rd.x), frcp(rd.y), frcp(rd.z)));
+                    best_e = best + R.e2;
                     sp = 0, cur_inst = -1, found = false;
                     hit.gid = 0, hit.inst = -1;
                     node = A.scene.root;
@@ -275,30 +276,10 @@ __global__ void __launch_bounds__(kWfBlock, DTOF_WF_TRACE_CTAS) wf_trace_kernel(
             for (int step = 0; step < steps; ++step)
             if ((unsigned) node < (unsigned) kDone) {
                 const float4 *np = N + 4 * (size_t) node;
-                float4 n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3];
-                float c0lx, c0hx, c0ly, c0hy, c0lz, c0hz, c1lx, c1hx, c1ly, c1hy, c1lz, c1hz, widen;
-                if (SLAB_FMA) {
-                    c0lx = fmaf(n0.x, id.x, nd.x), c0hx = fmaf(n0.y, id.x, nd.x);
-                    c0ly = fmaf(n0.z, id.y, nd.y), c0hy = fmaf(n0.w, id.y, nd.y);
-                    c0lz = fmaf(n2.x, id.z, nd.z), c0hz = fmaf(n2.y, id.z, nd.z);
-                    c1lx = fmaf(n1.x, id.x, nd.x), c1hx = fmaf(n1.y, id.x, nd.x);
-                    c1ly = fmaf(n1.z, id.y, nd.y), c1hy = fmaf(n1.w, id.y, nd.y);
-                    c1lz = fmaf(n2.z, id.z, nd.z), c1hz = fmaf(n2.w, id.z, nd.z);
-                    widen = 1.000003f;
-                } else {
-                    c0lx = (n0.x - ro.x) * id.x, c0hx = (n0.y - ro.x) * id.x;
-                    c0ly = (n0.z - ro.y) * id.y, c0hy = (n0.w - ro.y) * id.y;
-                    c0lz = (n2.x - ro.z) * id.z, c0hz = (n2.y - ro.z) * id.z;
-                    c1lx = (n1.x - ro.x) * id.x, c1hx = (n1.y - ro.x) * id.x;
-                    c1ly = (n1.z - ro.y) * id.y, c1hy = (n1.w - ro.y) * id.y;
-                    c1lz = (n2.z - ro.z) * id.z, c1hz = (n2.w - ro.z) * id.z;
-                    widen = 1.0000005f;
-                }
-                float t0n = fmaxf(fmaxf(fminf(c0lx, c0hx), fminf(c0ly, c0hy)), fmaxf(fminf(c0lz, c0hz), 0.f));
-                float t0f = fminf(fminf(fmaxf(c0lx, c0hx), fmaxf(c0ly, c0hy)), fmaxf(c0lz, c0hz)) * widen;
-                float t1n = fmaxf(fmaxf(fminf(c1lx, c1hx), fminf(c1ly, c1hy)), fmaxf(fminf(c1lz, c1hz), 0.f));
-                float t1f = fminf(fminf(fmaxf(c1lx, c1hx), fmaxf(c1ly, c1hy)), fmaxf(c1lz, c1hz)) * widen;
-                bool h0 = t0n <= fminf(t0f, best), h1 = t1n <= fminf(t1f, best);
+                const float4 n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3];
+                bool h0, h1;
+                float t0n, t1n;
+                node_test(n0, n1, n2, R, best_e, h0, h1, t0n, t1n);
                 int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
                 if (h0 && h1) {
                     bool swap = t1n < t0n;
@@ -317,8 +298,8 @@ __global__ void __launch_bounds__(kWfBlock, DTOF_WF_TRACE_CTAS) wf_trace_kernel(
             if (node == kSentinel) {   // leave the instance: back to the world-space ray
                 const float4 a = qo[k], b = qd[k];
                 ro = v3(a.x, a.y, a.z), rd = v3(b.x, b.y, b.z);
-                id = v3(frcp(rd.x), frcp(rd.y), frcp(rd.z));
-                nd = v3(-(ro.x * id.x), -(ro.y * id.y), -(ro.z * id.z));
+                R.set(ro, v3(frcp(rd.x), frcp(rd.y), frcp(rd.z)));
+                best_e = best + R.e2;
                 cur_inst = -1;
                 DTOF_WF_POP();
             } else if (count == 0) {   // animated instance: move the ray into its space (Embree semantics, enter_instance)
@@ -326,8 +307,8 @@ __global__ void __launch_bounds__(kWfBlock, DTOF_WF_TRACE_CTAS) wf_trace_kernel(
                 const float4 *ip = I + 8 * (size_t) cur_inst;
                 const float4 a = qo[k], b = qd[k];
                 enter_instance(ip, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), b.w, ro, rd);
-                id = v3(frcp(rd.x), frcp(rd.y), frcp(rd.z));
-                nd = v3(-(ro.x * id.x), -(ro.y * id.y), -(ro.z * id.z));
+                R.set(ro, v3(frcp(rd.x), frcp(rd.y), frcp(rd.z)));
+                best_e = best + R.e2;
                 stack[sp++] = kSentinel;
                 node = __float_as_int(ip[6].z);
             } else {
@@ -346,6 +327,7 @@ __global__ void __launch_bounds__(kWfBlock, DTOF_WF_TRACE_CTAS) wf_trace_kernel(
                         uint32_t gid = __float_as_uint(a.w);
                         if (t < best || !found || gid < hit.gid) {
                             best = t;
+                            best_e = t + R.e2;
                             hit.t = t, hit.u = u, hit.v = v;
                             hit.gid = gid;
                             hit.inst = cur_inst;

@@ -67,18 +67,29 @@ def scene_info(scene_or_flat) -> _abi.SceneInfo:
 
 
 class Context:
-    """One dtof_ctx (one GPU). Thread-compatible, like the C ABI."""
+    """One dtof_ctx: one GPU, or -- `devices=[0, 1, ...]` -- one context over several GPUs of the node (dtof_create_multi:
+    the scene is replicated, one render is sharded over the devices and summed on devices[0]). Thread-compatible, like
+    the C ABI."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, devices=None):
         self.lib = load_library()
-        self.device = int(device)
         h = C.c_void_p()
-        rc = self.lib.dtof_create(C.byref(h), self.device)
+        if devices is not None:
+            devices = [int(d) for d in devices]
+            self.device = devices[0]
+            arr = (C.c_int * len(devices))(*devices)
+            rc = self.lib.dtof_create_multi(C.byref(h), arr, len(devices))
+        else:
+            self.device = int(device)
+            rc = self.lib.dtof_create(C.byref(h), self.device)
         if rc != _abi.OK:
-            raise DTOFError(f"dtof_create(device={device}) failed with status {rc}: no usable CUDA device "
+            raise DTOFError(f"dtof_create(device={devices or device}) failed with status {rc}: no usable CUDA device "
                             "(the product path has no CPU fallback)")
         self.h = h
         self._flat = None
+
+    def device_count(self) -> int:
+        return int(self.lib.dtof_device_count(self.h))
 
     def close(self):
         if getattr(self, "h", None):

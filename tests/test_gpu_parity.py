@@ -103,7 +103,7 @@ def test_cuda_two_pass_film_window_matches_oracle(ctx, scene_name, kw):
     lo, hi = first_px * pi.spp_per_pass, (first_px + 48) * pi.spp_per_pass
     p = scene.integrator.params(scene.sensor.sampler, seed=3, lane_begin=lo, lane_end=hi)
     rgbw = ctx.render(flat, p, develop=False)
-    ref = oracle_lib.OracleScene(flat).render(p, develop=False)
+    ref = oracle_lib.OracleScene(flat).render(p, 4, develop=False)   # 4 threads: each holds a full-frame accumulator
     assert abs(float(rgbw[..., 3].sum()) - 48 * pi.spp_per_pass * 2) < 1e-3 * 48 * pi.spp_per_pass * 2   # both passes landed
     scale = np.abs(ref[..., :3]).max()
     assert np.abs(rgbw[..., :3] - ref[..., :3]).max() <= 2e-4 * scale
