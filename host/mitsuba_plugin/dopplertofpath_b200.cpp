@@ -1,5 +1,7 @@
 // Mitsuba-side binding of libdtof_b200.so: the plugin a maintainer of juhyeonkim95/Mitsuba3DopplerToF adds as
-// src/integrators/dopplertofpath_b200.cpp (plugin name "dopplertofpath_b200", or installed over "dopplertofpath").
+// src/integrators/dopplertofpath_b200.cpp (plugin file "dopplertofpath_b200.so"; the SAME source installed as
+// plugins/dopplertofpath.so answers <integrator type="dopplertofpath"> of an untouched scene file: the plugin manager
+// goes by the file name, src/core/plugin.cpp:93-127 -- oracle/ref_harness/Makefile builds that drop-in view too).
 // It keeps the reference's property surface, walks the loaded mitsuba::Scene, hands plain arrays to the C ABI
 // (include/dtof.h) and puts the returned RGBW tensor into the film, i.e. it replaces
 //   SamplingIntegrator::render            src/render/integrator.cpp:104-347
@@ -13,6 +15,7 @@
 // (src/samplers/correlated.cpp:179-183). They are read through layout mirrors of those two classes (below), checked
 // against the class name; upstream would rather add the accessors listed in INTEGRATION.md section 2.
 #include <cmath>
+#include <cstdlib>
 
 #include <mitsuba/core/properties.h>
 #include <mitsuba/core/transform.h>
@@ -110,9 +113,46 @@ public:
         else if (wave == "trapezoidal") m_p.wave_function_type = DTOF_WAVE_TRAPEZOIDAL;
         else Throw("unknown wave_function_type \"%s\"", wave);
         m_p.low_frequency_component_only = props.get<bool>("low_frequency_component_only", true);
+        // `device` (one GPU) or `devices` = "0,1,2,3" / "all": one context over several GPUs of the node; one render is
+        // sharded over them behind the C ABI and summed on the first (dtof_create_multi). The environment variable
+        // DTOF_DEVICES supplies the list for a scene file that must stay untouched.
         m_device = props.get<int>("device", 0);
-        if (dtof_create(&m_ctx, m_device) != DTOF_OK)
-            Throw("dtof_create(device=%i) failed: no usable CUDA device (there is no CPU fallback)", m_device);
+        std::string devices = props.get<std::string>("devices", "");
+        if (devices.empty() && getenv("DTOF_DEVICES"))
+            devices = getenv("DTOF_DEVICES");
+        std::vector<int> list;
+        if (devices == "all") {
+            list.push_back(-1);
+        } else {
+            for (size_t at = 0; at < devices.size();) {
+                size_t end = devices.find(',', at);
+                if (end == std::string::npos)
+                    end = devices.size();
+                list.push_back(std::atoi(devices.substr(at, end - at).c_str()));
+                at = end + 1;
+            }
+        }
+        if (list.size() == 1 && list[0] == -1) {   // "all": as many as dtof_create accepts
+            list.clear();
+            for (int d = 0; d < 16; ++d) {
+                dtof_ctx *probe = nullptr;
+                if (dtof_create(&probe, d) != DTOF_OK)
+                    break;
+                dtof_destroy(probe);
+                list.push_back(d);
+            }
+        }
+        Log(Info, "dopplertofpath on B200: CUDA library libdtof_b200 (ABI %u) on %u device(s)", dtof_abi_version(),
+            (uint32_t) std::max<size_t>(list.size(), 1));
+        if (list.size() > 1) {
+            if (dtof_create_multi(&m_ctx, list.data(), (uint32_t) list.size()) != DTOF_OK)
+                Throw("dtof_create_multi(devices=%s) failed: no usable CUDA devices (there is no CPU fallback)", devices);
+        } else {
+            if (list.size() == 1)
+                m_device = list[0];
+            if (dtof_create(&m_ctx, m_device) != DTOF_OK)
+                Throw("dtof_create(device=%i) failed: no usable CUDA device (there is no CPU fallback)", m_device);
+        }
     }
     ~DopplerToFPathB200() { dtof_destroy(m_ctx); }
 
@@ -120,9 +160,13 @@ public:
         m_stop = false;
         m_render_timer.reset();
         Film *film = sensor->film();
-        if (m_uploaded != scene) {          // flatten + BVH build + H2D once per scene
+        // flatten + BVH build + H2D once per (scene, sensor, film geometry). parameters_changed() on this integrator (what
+        // mi.traverse(...).update() ends with) drops the cache: an edited scene is flattened again.
+        const ScalarVector2u csize = film->crop_size();
+        const ScalarPoint2u coff = film->crop_offset();
+        if (m_uploaded != scene || m_uploaded_sensor != sensor || m_uploaded_size != csize || m_uploaded_offset != coff) {
             upload(scene, sensor);
-            m_uploaded = scene;
+            m_uploaded = scene, m_uploaded_sensor = sensor, m_uploaded_size = csize, m_uploaded_offset = coff;
         }
         dtof_params p = m_p;
         p.max_depth = (int32_t) m_max_depth, p.rr_depth = (int32_t) m_rr_depth, p.hide_emitters = m_hide_emitters;
@@ -156,8 +200,26 @@ public:
         film->prepare({});                                               // channels R,G,B,W (hdrfilm.cpp:235-279)
         size_t n = (size_t) size.x() * size.y() * 4;
         std::unique_ptr<float[]> rgbw(new float[n]);
-        if (dtof_render(m_ctx, &p, rgbw.get(), nullptr) != DTOF_OK)      // H2D params, kernels, D2H film inside
-            Throw("dtof_render: %s", dtof_last_error(m_ctx));
+        // The wavefront is submitted in chunks of whole pixels (~2^28 lanes, a fraction of a second of GPU time) so that
+        // cancel() and the `timeout` property are honoured between them (should_stop(), include/mitsuba/render/
+        // integrator.h:106-108); a stopped render keeps what was accumulated so far, like the reference's block loop.
+        dtof_pass_info pi;
+        if (dtof_pass_info_for(m_ctx, &p, &pi) != DTOF_OK)
+            Throw("dtof_pass_info_for: %s", dtof_last_error(m_ctx));
+        const uint64_t chunk = std::max<uint64_t>(1, (uint64_t(1) << 28) / pi.spp_per_pass) * pi.spp_per_pass;
+        bool first = true;
+        for (uint64_t begin = 0; begin < pi.wavefront_size && !should_stop(); begin += chunk, first = false) {
+            dtof_params q = p;
+            q.lane_begin = begin, q.lane_end = std::min<uint64_t>(pi.wavefront_size, begin + chunk);
+            if (dtof_render_accumulate(m_ctx, &q, first) != DTOF_OK)     // H2D params, kernels
+                Throw("dtof_render_accumulate: %s", dtof_last_error(m_ctx));
+        }
+        if (first)                                                       // stopped before the first chunk
+            std::fill(rgbw.get(), rgbw.get() + n, 0.f);
+        else if (dtof_read_film(m_ctx, rgbw.get(), nullptr) != DTOF_OK)  // D2H film
+            Throw("dtof_read_film: %s", dtof_last_error(m_ctx));
+        if (should_stop())
+            Log(Warn, "Rendering stopped early (cancel / timeout): the film holds the chunks rendered so far.");
         // hand the accumulation tensor to the film exactly as the JIT branch does (integrator.cpp:266,310-323)
         size_t shape[3] = { size.y(), size.x(), 4 };
         TensorXf tensor(dr::load<DynamicBuffer<Float>>(rgbw.get(), n), 3, shape);
@@ -174,9 +236,18 @@ public:
         Throw("dopplertofpath_b200 renders whole images through render(); use 'dopplertofpath' for per-ray sample()");
     }
 
+    void parameters_changed(const std::vector<std::string> & /*keys*/ = {}) override { m_uploaded = nullptr; }
+
     MI_DECLARE_CLASS()
 
 private:
+    // A constant RGB value is all the accelerated path knows: a bitmap / checkerboard / mesh-attribute texture must not
+    // be silently evaluated at one point.
+    template <typename Tex> static const Tex *uniform(const Tex *t, const char *what) {
+        if (t && t->is_spatially_varying())
+            Throw("a spatially varying texture (%s of %s) is outside the accelerated path", what, t->class_()->name());
+        return t;
+    }
     static void m34(const ScalarTransform4f &t, float *out) {
         for (int r = 0; r < 3; ++r)
             for (int c = 0; c < 4; ++c)
@@ -206,7 +277,7 @@ private:
             auto tex = [&](const char *name) -> Spectrum {
                 for (auto &o : c.objects)
                     if (o.first == name)
-                        return ((const Texture<Float, Spectrum> *) o.second)->eval(si);
+                        return uniform((const Texture<Float, Spectrum> *) o.second, name)->eval(si);
                 Throw("conductor without '%s'", name);
             };
             Spectrum e = tex("eta"), k = tex("k"), r = tex("specular_reflectance");
@@ -221,7 +292,7 @@ private:
             for (int i = 0; i < 3; ++i)
                 b.reflectance[i] = b.k[i] = 1.f;
             for (auto &o : c.objects) {
-                Spectrum v = ((const Texture<Float, Spectrum> *) o.second)->eval(si);
+                Spectrum v = uniform((const Texture<Float, Spectrum> *) o.second, o.first.c_str())->eval(si);
                 float *dst = o.first == "specular_reflectance" ? b.reflectance : o.first == "specular_transmittance" ? b.k : nullptr;
                 if (dst)
                     dst[0] = v[0], dst[1] = v[1], dst[2] = v[2];
@@ -237,7 +308,7 @@ private:
             for (int i = 0; i < 3; ++i)
                 b.reflectance[i] = 1.f;
             for (auto &o : c.objects) {
-                const Texture<Float, Spectrum> *t = (const Texture<Float, Spectrum> *) o.second;
+                const Texture<Float, Spectrum> *t = uniform((const Texture<Float, Spectrum> *) o.second, o.first.c_str());
                 if (o.first == "alpha")
                     b.alpha[0] = b.alpha[1] = t->eval_1(si);
                 else if (o.first == "alpha_u")
@@ -263,7 +334,7 @@ private:
             for (int i = 0; i < 3; ++i)
                 b.reflectance[i] = b.k[i] = 1.f;
             for (auto &o : c.objects) {
-                const Texture<Float, Spectrum> *t = (const Texture<Float, Spectrum> *) o.second;
+                const Texture<Float, Spectrum> *t = uniform((const Texture<Float, Spectrum> *) o.second, o.first.c_str());
                 if (o.first == "alpha")
                     b.alpha[0] = b.alpha[1] = t->eval_1(si);
                 else if (o.first == "alpha_u")
@@ -287,7 +358,7 @@ private:
             for (int i = 0; i < 3; ++i)
                 b.reflectance[i] = 0.5f, b.k[i] = 1.f;
             for (auto &o : c.objects) {
-                Spectrum v = ((const Texture<Float, Spectrum> *) o.second)->eval(si);
+                Spectrum v = uniform((const Texture<Float, Spectrum> *) o.second, o.first.c_str())->eval(si);
                 float *dst = o.first == "diffuse_reflectance" ? b.reflectance : o.first == "specular_reflectance" ? b.k : nullptr;
                 if (dst)
                     dst[0] = v[0], dst[1] = v[1], dst[2] = v[2];
@@ -295,6 +366,10 @@ private:
         } else {
             if (inner->class_()->name() != "SmoothDiffuse")
                 Throw("BSDF \"%s\" is outside the accelerated path (diffuse | conductor | roughconductor | dielectric | thindielectric | roughdielectric | plastic | twosided(...))", inner->class_()->name());
+            Collector c;
+            const_cast<BSDF *>(inner)->traverse(&c);
+            for (auto &o : c.objects)
+                uniform((const Texture<Float, Spectrum> *) o.second, o.first.c_str());
             Spectrum r = inner->eval_diffuse_reflectance(si);            // constant RGB reflectance
             b.reflectance[0] = r[0], b.reflectance[1] = r[1], b.reflectance[2] = r[2];
         }
@@ -389,7 +464,7 @@ private:
                 d.kind = DTOF_EMITTER_POINT;
                 const ScalarPoint3f &p = *c.param<ScalarPoint3f>("position");
                 d.position[0] = p.x(), d.position[1] = p.y(), d.position[2] = p.z();
-                Spectrum I = ((const Texture<Float, Spectrum> *) c.objects[0].second)->eval(si);
+                Spectrum I = uniform((const Texture<Float, Spectrum> *) c.objects[0].second, "intensity")->eval(si);
                 d.value[0] = I[0], d.value[1] = I[1], d.value[2] = I[2];
             } else if (e->class_()->name() == "AreaLight") {
                 d.kind = DTOF_EMITTER_AREA;
@@ -398,6 +473,9 @@ private:
                         d.mesh = mo.second;
                         meshes[mo.second].emitter = (int32_t) emitters.size();
                     }
+                for (auto &o : c.objects)
+                    if (o.first == "radiance")
+                        uniform((const Texture<Float, Spectrum> *) o.second, "radiance");
                 Spectrum L = e->eval(si);
                 d.value[0] = L[0], d.value[1] = L[1], d.value[2] = L[2];
             } else if (e->class_()->name() == "SpotLight") {               // spot.cpp:89-114
@@ -411,7 +489,7 @@ private:
                 }
                 for (auto &o : c.objects)
                     if (o.first == "intensity") {
-                        Spectrum I = ((const Texture<Float, Spectrum> *) o.second)->eval(si);
+                        Spectrum I = uniform((const Texture<Float, Spectrum> *) o.second, o.first.c_str())->eval(si);
                         d.value[0] = I[0], d.value[1] = I[1], d.value[2] = I[2];
                     } else if (o.first == "texture" && ((const Texture<Float, Spectrum> *) o.second)->is_spatially_varying()) {
                         Throw("spot emitter with a projection texture is outside the accelerated path");
@@ -433,7 +511,7 @@ private:
                     d.position[r] = tw.matrix(r, 2);                     // to_world * (0, 0, 1)
                 for (auto &o : c.objects)
                     if (o.first == "irradiance") {
-                        Spectrum I = ((const Texture<Float, Spectrum> *) o.second)->eval(si);
+                        Spectrum I = uniform((const Texture<Float, Spectrum> *) o.second, o.first.c_str())->eval(si);
                         d.value[0] = I[0], d.value[1] = I[1], d.value[2] = I[2];
                     }
             } else if (e->class_()->name() == "ConstantBackgroundEmitter") {
@@ -510,6 +588,9 @@ private:
     dtof_params m_p;
     dtof_ctx *m_ctx = nullptr;
     const Scene *m_uploaded = nullptr;
+    const Sensor *m_uploaded_sensor = nullptr;
+    ScalarVector2u m_uploaded_size = ScalarVector2u(0, 0);
+    ScalarPoint2u m_uploaded_offset = ScalarPoint2u(0, 0);
     int m_device = 0;
 };
 

@@ -325,6 +325,14 @@ dtof_status dtof_pass_info_for(const dtof_ctx *ctx, const dtof_params *params, d
  * image_out: height*width*3 floats (developed RGB = RGB/W); either may be NULL. Copies are inside. */
 dtof_status dtof_render(dtof_ctx *ctx, const dtof_params *params, float *rgbw_out, float *image_out);
 
+/* A render in pieces, for callers that must be able to stop between them (Integrator::cancel / the `timeout` property,
+ * include/mitsuba/render/integrator.h:106-108): dtof_render_accumulate renders the lanes [lane_begin, lane_end) of
+ * `params` (all their passes) INTO the context's own device film -- zeroed first if `zero_first` -- and returns when
+ * they are done; dtof_read_film develops and copies that film to host buffers (either may be NULL). dtof_render is
+ * accumulate(all lanes, zero_first = 1) + read_film. */
+dtof_status dtof_render_accumulate(dtof_ctx *ctx, const dtof_params *params, int zero_first);
+dtof_status dtof_read_film(dtof_ctx *ctx, float *rgbw_out, float *image_out);
+
 /* The tutorials' multi-pass driver (render_image_multi_pass, doppler_tutorials/src/program_runner.py:11-31):
  * n_renders renders with seed = params->seed + i (i = 0 .. n_renders-1), each developed (RGB / W), averaged ON THE
  * DEVICE; the scene stays resident and only the final H*W*3 image crosses to the host. This is also how a 16k-spp
@@ -348,6 +356,23 @@ dtof_status dtof_trace_samples(dtof_ctx *ctx, const dtof_params *params, const u
  * 94-103), so passes 0 .. pass - 1 of each lane are replayed first and the record describes the last one. */
 dtof_status dtof_trace_samples_pass(dtof_ctx *ctx, const dtof_params *params, const uint64_t *lanes, uint32_t n,
                                     uint32_t pass, dtof_sample_record *out);
+
+/* Scene::ray_intersect_preliminary / Scene::ray_test (src/render/scene.cpp:125-154) for caller-supplied rays, with the
+ * per-ray time of the motion-blurred instances: closest hit (any_hit == 0; ties resolve to the lowest triangle id) or any
+ * hit (any_hit != 0; only `hit` is meaningful). Host arrays in and out. `nodes_visited` / `tris_tested` count the BVH
+ * walk of that ray (a traversal-quality probe: an axis-parallel ray must not cost more than its neighbours). */
+typedef struct dtof_ray {
+    float o[3], tmax;
+    float d[3], time;
+} dtof_ray;
+typedef struct dtof_ray_hit {
+    float t, u, v;            /* distance and barycentric coordinates (b1, b2) of the hit */
+    uint32_t prim;            /* global triangle id = position in the order of the scene description */
+    int32_t instance;         /* animated instance the triangle belongs to, -1 = static geometry */
+    uint32_t hit;             /* 1 = hit / occluded */
+    uint32_t nodes_visited, tris_tested;
+} dtof_ray_hit;
+dtof_status dtof_trace_rays(dtof_ctx *ctx, const dtof_ray *rays, uint32_t n, int any_hit, dtof_ray_hit *out);
 
 /* Enable/disable traversal counters (slower kernel variant) and read them back after a render. */
 dtof_status dtof_set_stats(dtof_ctx *ctx, int enabled);

@@ -123,6 +123,20 @@ class Stats(C.Structure):
     ]
 
 
+class Ray(C.Structure):
+    _fields_ = [("o", C.c_float * 3), ("tmax", C.c_float), ("d", C.c_float * 3), ("time", C.c_float)]
+
+
+class RayHit(C.Structure):
+    _fields_ = [("t", C.c_float), ("u", C.c_float), ("v", C.c_float), ("prim", C.c_uint32), ("instance", C.c_int32),
+                ("hit", C.c_uint32), ("nodes_visited", C.c_uint32), ("tris_tested", C.c_uint32)]
+
+
+RAY_DTYPE = np.dtype([("o", "<f4", 3), ("tmax", "<f4"), ("d", "<f4", 3), ("time", "<f4")])
+RAY_HIT_DTYPE = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("prim", "<u4"), ("instance", "<i4"), ("hit", "<u4"),
+                          ("nodes_visited", "<u4"), ("tris_tested", "<u4")])
+
+
 class PassInfo(C.Structure):
     _fields_ = [("spp_per_pass", C.c_uint32), ("n_passes", C.c_uint32), ("wavefront_size", C.c_uint64)]
 
@@ -146,6 +160,8 @@ DTOF_SYMBOLS = {
     "dtof_update_instances": (C.c_int, [_ctx, C.c_uint32, C.c_uint32, C.POINTER(Instance)]),
     "dtof_pass_info_for": (C.c_int, [_ctx, C.POINTER(Params), C.POINTER(PassInfo)]),
     "dtof_render": (C.c_int, [_ctx, C.POINTER(Params), _fp, _fp]),
+    "dtof_render_accumulate": (C.c_int, [_ctx, C.POINTER(Params), C.c_int]),
+    "dtof_read_film": (C.c_int, [_ctx, _fp, _fp]),
     "dtof_render_multi_pass": (C.c_int, [_ctx, C.POINTER(Params), C.c_uint32, _fp]),
     "dtof_render_device": (C.c_int, [_ctx, C.POINTER(Params), C.c_void_p, C.c_void_p]),
     "dtof_develop_device": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -153,6 +169,7 @@ DTOF_SYMBOLS = {
                                      C.POINTER(SampleRecord)]),
     "dtof_trace_samples_pass": (C.c_int, [_ctx, C.POINTER(Params), C.POINTER(C.c_uint64), C.c_uint32, C.c_uint32,
                                           C.POINTER(SampleRecord)]),
+    "dtof_trace_rays": (C.c_int, [_ctx, C.POINTER(Ray), C.c_uint32, C.c_int, C.POINTER(RayHit)]),
     "dtof_set_stats": (C.c_int, [_ctx, C.c_int]),
     "dtof_get_stats": (C.c_int, [_ctx, C.POINTER(Stats)]),
     "dtof_last_traversal_mode": (C.c_int, [_ctx]),

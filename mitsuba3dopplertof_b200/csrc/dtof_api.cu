@@ -196,6 +196,47 @@ __global__ void __launch_bounds__(kBlock, DTOF_MIN_CTAS) render_kernel(const __g
     }
 }
 
+// dtof_trace_rays: one caller-supplied ray per thread through the traversal the render kernels use
+template <int MODE>
+__global__ void __launch_bounds__(kBlock) rays_kernel(const __grid_constant__ RenderArgs A, const dtof_ray *__restrict__ rays, uint32_t n,
+                                                      int any_hit, dtof_ray_hit *__restrict__ out) {
+    extern __shared__ float4 smem[];
+    TravPtrs TP;
+    TP.N = A.scene.nodes, TP.T = A.scene.tris, TP.TF = A.tris_flat, TP.I = A.scene.insts, TP.B = A.inst_box;
+    TP.S = SmemScene{ 0u, 0u, 0u, 0u };
+    if (MODE == MODE_BVH_SMEM) {
+        const uint32_t nn = A.nodes_bytes / 16, nt = A.tris_bytes / 16, ni = A.insts_bytes / 16;
+        float4 *sN = smem, *sT = sN + nn, *sI = sT + nt;
+        for (uint32_t i = threadIdx.x; i < nn; i += kBlock) sN[i] = A.scene.nodes[i];
+        for (uint32_t i = threadIdx.x; i < nt; i += kBlock) sT[i] = A.scene.tris[i];
+        for (uint32_t i = threadIdx.x; i < ni; i += kBlock) sI[i] = A.scene.insts[i];
+        __syncthreads();
+        const uint32_t base = opaque_u32((uint32_t) __cvta_generic_to_shared(smem));
+        TP.S.N = base, TP.S.T = base + A.nodes_bytes, TP.S.I = TP.S.T + A.tris_bytes;
+        TP.S.stack = TP.S.I + A.insts_bytes + A.boxes_bytes + (threadIdx.x >> 5) * (A.stack_levels * 128u) + (threadIdx.x & 31) * 4u;
+    }
+    const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+    const bool on = i < n;
+    dtof_ray r{};
+    if (on)
+        r = rays[i];
+    Counters st = {};
+    Hit h;
+    h.t = 0.f, h.u = 0.f, h.v = 0.f, h.gid = 0, h.inst = -1;
+    const bool hit = trace_any_mode<MODE, true>(A.scene, TP, any_hit != 0, v3(r.o[0], r.o[1], r.o[2]), v3(r.d[0], r.d[1], r.d[2]), r.tmax,
+                                                r.time, on, h, st);
+    if (on) {
+        dtof_ray_hit o{};
+        o.hit = hit ? 1u : 0u;
+        if (hit && !any_hit)
+            o.t = h.t, o.u = h.u, o.v = h.v, o.prim = h.gid, o.instance = h.inst;
+        else
+            o.instance = -1;
+        o.nodes_visited = (uint32_t) st.nodes, o.tris_tested = (uint32_t) st.tris;
+        out[i] = o;
+    }
+}
+
 // HDRFilm::develop (src/films/hdrfilm.cpp:305-419): RGB / W, W == 0 -> divide by 1
 __global__ void develop_kernel(const float4 *__restrict__ rgbw, float *__restrict__ img, size_t n) {
     size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -701,6 +742,9 @@ dtof_status launch_render(dtof_ctx *ctx, const dtof_params *p, float *d_rgbw, cu
     const bool record = d_rec != nullptr;
     // ---- traversal mode: flat coherent walk for tiny scenes, BVH in shared memory while it fits, else BVH from HBM
     A.stack_levels = (uint32_t) ctx->bvh_depth + 4u;
+#ifdef DTOF_LOCAL_STACK
+    A.stack_levels = 0;   // A/B builds: no shared-memory stack rows
+#endif
     A.rec_pass = rec_pass;
     const size_t stack_bytes = (size_t) A.stack_levels * 128u * (kBlock / 32);   // shared-memory traversal stacks of one CTA
     const size_t bvh_bytes = ctx->nodes_bytes + ctx->tris_bytes + ctx->insts_bytes + ctx->boxes_bytes + stack_bytes;
@@ -1529,6 +1573,48 @@ dtof_status dtof_render(dtof_ctx *ctx, const dtof_params *params, float *rgbw_ou
     return DTOF_OK;
 }
 
+dtof_status dtof_render_accumulate(dtof_ctx *ctx, const dtof_params *params, int zero_first) {
+    if (!ctx)
+        return DTOF_ERR_INVALID;
+    if (!ctx->has_scene)
+        return fail(ctx, DTOF_ERR_STATE, "no scene uploaded");
+    dtof_status s = check_params(ctx, params);
+    if (s != DTOF_OK)
+        return s;
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->peers.empty()) {
+        // the peers' partial films are summed into device 0's film after every chunk (their films restart from zero)
+        if (zero_first)
+            CU(cudaMemsetAsync(ctx->d_rgbw, 0, ctx->film_px * 4 * sizeof(float), 0));
+        if ((s = render_sharded(ctx, params, ctx->d_rgbw, false, 0)) != DTOF_OK)
+            return s;
+    } else {
+        if (zero_first)
+            CU(cudaMemsetAsync(ctx->d_rgbw, 0, ctx->film_px * 4 * sizeof(float), 0));
+        if ((s = launch_render(ctx, params, ctx->d_rgbw, 0, nullptr, nullptr, 0)) != DTOF_OK)
+            return s;
+    }
+    CU(cudaStreamSynchronize(0));
+    return DTOF_OK;
+}
+
+dtof_status dtof_read_film(dtof_ctx *ctx, float *rgbw_out, float *image_out) {
+    if (!ctx)
+        return DTOF_ERR_INVALID;
+    if (!ctx->has_scene)
+        return fail(ctx, DTOF_ERR_STATE, "no scene uploaded");
+    CU(cudaSetDevice(ctx->device));
+    dtof_status s;
+    if (image_out && (s = dtof_develop_device(ctx, ctx->d_rgbw, ctx->d_img, nullptr)) != DTOF_OK)
+        return s;
+    if (rgbw_out)
+        CU(cudaMemcpyAsync(rgbw_out, ctx->d_rgbw, ctx->film_px * 4 * sizeof(float), cudaMemcpyDeviceToHost, 0));
+    if (image_out)
+        CU(cudaMemcpyAsync(image_out, ctx->d_img, ctx->film_px * 3 * sizeof(float), cudaMemcpyDeviceToHost, 0));
+    CU(cudaStreamSynchronize(0));
+    return DTOF_OK;
+}
+
 dtof_status dtof_render_multi_pass(dtof_ctx *ctx, const dtof_params *params, uint32_t n_renders, float *image_out) {
     if (!ctx)
         return DTOF_ERR_INVALID;
@@ -1621,6 +1707,56 @@ dtof_status dtof_trace_samples_pass(dtof_ctx *ctx, const dtof_params *params, co
     cudaFree(d_lanes);
     cudaFree(d_rec);
     return s;
+}
+
+dtof_status dtof_trace_rays(dtof_ctx *ctx, const dtof_ray *rays, uint32_t n, int any_hit, dtof_ray_hit *out) {
+    if (!ctx)
+        return DTOF_ERR_INVALID;
+    if (!ctx->has_scene)
+        return fail(ctx, DTOF_ERR_STATE, "no scene uploaded");
+    if (n == 0)
+        return DTOF_OK;
+    if (!rays || !out)
+        return fail(ctx, DTOF_ERR_INVALID, "NULL rays/out");
+    CU(cudaSetDevice(ctx->device));
+    RenderArgs A{};
+    A.scene = ctx->ds;
+    A.tris_flat = (const float4 *) ctx->d_tris_flat;
+    A.inst_box = (const float4 *) ctx->d_boxes;
+    A.stack_levels = (uint32_t) ctx->bvh_depth + 4u;
+    A.nodes_bytes = (uint32_t) ctx->nodes_bytes, A.tris_bytes = (uint32_t) ctx->tris_bytes;
+    A.insts_bytes = (uint32_t) ctx->insts_bytes, A.boxes_bytes = (uint32_t) ctx->boxes_bytes;
+    const size_t smem = ctx->nodes_bytes + ctx->tris_bytes + ctx->insts_bytes + ctx->boxes_bytes +
+                        (size_t) A.stack_levels * 128u * (kBlock / 32);
+    int mode = (smem <= kSmemSceneLimit && smem + 1024 <= ctx->smem_optin) ? MODE_BVH_SMEM : MODE_BVH_GLOBAL;
+    if (const char *e = getenv("DTOF_MODE"))
+        if (atoi(e) == MODE_BVH_GLOBAL)
+            mode = MODE_BVH_GLOBAL;
+    dtof_ray *d_rays = nullptr;
+    dtof_ray_hit *d_out = nullptr;
+    CU(cudaMalloc(&d_rays, n * sizeof(dtof_ray)));
+    if (cudaMalloc(&d_out, n * sizeof(dtof_ray_hit)) != cudaSuccess) {
+        cudaFree(d_rays);
+        return fail(ctx, DTOF_ERR_NOMEM, "cudaMalloc failed");
+    }
+    cudaMemcpy(d_rays, rays, n * sizeof(dtof_ray), cudaMemcpyHostToDevice);
+    const unsigned grid = (n + kBlock - 1) / kBlock;
+    if (mode == MODE_BVH_SMEM) {
+        cudaFuncSetAttribute(rays_kernel<MODE_BVH_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        rays_kernel<MODE_BVH_SMEM><<<grid, kBlock, smem>>>(A, d_rays, n, any_hit, d_out);
+    } else {
+        rays_kernel<MODE_BVH_GLOBAL><<<grid, kBlock>>>(A, d_rays, n, any_hit, d_out);
+    }
+    ctx->launches++;
+    ctx->last_mode = mode;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess)
+        e = cudaMemcpy(out, d_out, n * sizeof(dtof_ray_hit), cudaMemcpyDeviceToHost);
+    cudaFree(d_rays);
+    cudaFree(d_out);
+    if (e != cudaSuccess)
+        return fail(ctx, DTOF_ERR_CUDA, "dtof_trace_rays: %s", cudaGetErrorString(e));
+    return DTOF_OK;
 }
 
 dtof_status dtof_set_stats(dtof_ctx *ctx, int enabled) {

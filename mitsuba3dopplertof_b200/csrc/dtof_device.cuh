@@ -574,36 +574,39 @@ struct Hit {
 
 // ---- box test of one BVH node (both children) ----------------------------------------------------------------------
 // A child box is stored as centre m and half extent h per axis (dtof_layout.h). Per axis the ray's parameter interval is
-//     c = m * idir - o * idir  (one fma, `nd` = -o * idir),   [c - h |idir|, c + h |idir|]   (two fmas)
+//     c = (m - o) * idir,   [c - h |idir|, c + h |idir|]      (sub, mul, two fmas)
 // -- no min / max per axis: the lower end is the lower end whatever the sign of the direction. The fused kernel's walk
-// is bound by the half-rate ALU pipe that executes FMNMX / FSETP / SEL, not by issue slots (ncu: ALU 54 %, FMA 29 % of
-// peak over the whole kernel): the lo / hi form costs 20 min / max per node, this form 8, for 6 more fmas.
-// Conservative: the ABSOLUTE error of c (<= ulp(o * idir)) is bounded per ray by e2 = kSlabAbsErr * max |o * idir| and
-// added to the far side and to the best distance; the relative errors are covered by widening the far side by 3e-6
-// (the builder already rounds the half extents up and pads the boxes).
-constexpr float kSlabAbsErr = 2.4e-7f;   // 4 x 2^-24: both ends of the interval, with a factor 2 in hand
+// is bound by the half-rate ALU pipe that executes FMNMX / FSETP / SEL (ncu, round 1: ALU 54 %, FMA 29 % of peak over the
+// whole kernel): the lo / hi form costs 20 min / max per node, this form 8.
+// Conservative for any origin: every rounding error is RELATIVE to the value it affects ((m - o) is one rounding, the
+// product another, each fma one more; idir is 1 ulp off per axis), covered by widening the far side by 3e-6 and by the
+// builder, which rounds the half extents up and pads the boxes by 1e-5. (A form with one fma per plane, m * idir - o *
+// idir, carries an ABSOLUTE error of ulp(o * idir); bounding it per ray loosens every axis by the error of the axis the
+// ray is most parallel to -- a ray with a zero direction component then accepts every box of a 1.3 M-node BVH.)
+// An infinite idir (zero direction component) gives inf / NaN on that axis; fminf / fmaxf drop NaN operands, so the
+// axis is at worst not used for culling.
 constexpr float kSlabWiden = 1.000003f;
 struct RaySlab {
-    V3 id, nd, aid;
-    float e2;
-    DTOF_DEV void set(V3 o, V3 rid) {
+    V3 o, id, aid;
+    DTOF_DEV void set(V3 ro, V3 rid) {
+        o = ro;
         id = rid;
-        nd = v3(-(o.x * rid.x), -(o.y * rid.y), -(o.z * rid.z));
         aid = v3(fabsf(rid.x), fabsf(rid.y), fabsf(rid.z));
-        e2 = kSlabAbsErr * fmaxf(fmaxf(fabsf(nd.x), fabsf(nd.y)), fabsf(nd.z));
     }
 };
-// n0 = child 0 {mx, hx, my, hy}, n1 = child 1 {mx, hx, my, hy}, n2 = {c0 mz, c0 hz, c1 mz, c1 hz}; `best_e` = best + e2
-DTOF_DEV void node_test(const float4 n0, const float4 n1, const float4 n2, const RaySlab &R, float best_e, bool &h0, bool &h1,
+// n0 = child 0 {mx, hx, my, hy}, n1 = child 1 {mx, hx, my, hy}, n2 = {c0 mz, c0 hz, c1 mz, c1 hz}
+DTOF_DEV void node_test(const float4 n0, const float4 n1, const float4 n2, const RaySlab &R, float best, bool &h0, bool &h1,
                         float &t0n, float &t1n) {
-    const float c0x = fmaf(n0.x, R.id.x, R.nd.x), c0y = fmaf(n0.z, R.id.y, R.nd.y), c0z = fmaf(n2.x, R.id.z, R.nd.z);
-    const float c1x = fmaf(n1.x, R.id.x, R.nd.x), c1y = fmaf(n1.z, R.id.y, R.nd.y), c1z = fmaf(n2.z, R.id.z, R.nd.z);
+    const float c0x = (n0.x - R.o.x) * R.id.x, c0y = (n0.z - R.o.y) * R.id.y, c0z = (n2.x - R.o.z) * R.id.z;
+    const float c1x = (n1.x - R.o.x) * R.id.x, c1y = (n1.z - R.o.y) * R.id.y, c1z = (n2.z - R.o.z) * R.id.z;
     t0n = fmaxf(fmaxf(fmaf(-n0.y, R.aid.x, c0x), fmaf(-n0.w, R.aid.y, c0y)), fmaxf(fmaf(-n2.y, R.aid.z, c0z), 0.f));
     t1n = fmaxf(fmaxf(fmaf(-n1.y, R.aid.x, c1x), fmaf(-n1.w, R.aid.y, c1y)), fmaxf(fmaf(-n2.w, R.aid.z, c1z), 0.f));
     const float t0f = fminf(fminf(fmaf(n0.y, R.aid.x, c0x), fmaf(n0.w, R.aid.y, c0y)), fmaf(n2.y, R.aid.z, c0z));
     const float t1f = fminf(fminf(fmaf(n1.y, R.aid.x, c1x), fmaf(n1.w, R.aid.y, c1y)), fmaf(n2.w, R.aid.z, c1z));
-    h0 = t0n <= fminf(fmaf(t0f, kSlabWiden, R.e2), best_e);
-    h1 = t1n <= fminf(fmaf(t1f, kSlabWiden, R.e2), best_e);
+    // the widening applies to `best` as well: for a far origin one ulp of t exceeds the boxes' padding, and a box whose
+    // entry distance ties with the best hit so far must still be visited (the triangle test itself compares exactly)
+    h0 = t0n <= fminf(t0f, best) * kSlabWiden;
+    h1 = t1n <= fminf(t1f, best) * kSlabWiden;
 }
 
 // Moeller-Trumbore (include/mitsuba/render/mesh.h:342-365) against one stored triangle (p0 | e1 | e2), split into a
@@ -682,7 +685,7 @@ DTOF_DEV bool trace_bvh(const float4 *__restrict__ N, const float4 *__restrict__
     V3 ro = o, rd = d;                                       // ray in the current (world / instance) space
     RaySlab R;
     R.set(o, v3(frcp(d.x), frcp(d.y), frcp(d.z)));
-    float best = tmax, best_e = best + R.e2;
+    float best = tmax;
     bool found = false;
     if (STATS) {
         if (ANY) st.rays_shadow++; else st.rays_closest++;
@@ -696,7 +699,6 @@ DTOF_DEV bool trace_bvh(const float4 *__restrict__ N, const float4 *__restrict__
             if (node == kSentinel) { /* leave the instance: back to the world-space ray */                 \
                 ro = o, rd = d, cur_inst = -1;                                                             \
                 R.set(o, v3(frcp_here(d.x), frcp_here(d.y), frcp_here(d.z)));                              \
-                best_e = best + R.e2;                                                                      \
                 node = sp ? stack[--sp] : kDone;                                                           \
             }                                                                                              \
         }                                                                                                  \
@@ -710,7 +712,7 @@ DTOF_DEV bool trace_bvh(const float4 *__restrict__ N, const float4 *__restrict__
             if (STATS) st.nodes++;
             bool h0, h1;
             float t0n, t1n;
-            node_test(n0, n1, n2, R, best_e, h0, h1, t0n, t1n);
+            node_test(n0, n1, n2, R, best, h0, h1, t0n, t1n);
             const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
             if (h0 && h1) {
                 const bool swap = t1n < t0n;
@@ -733,7 +735,6 @@ DTOF_DEV bool trace_bvh(const float4 *__restrict__ N, const float4 *__restrict__
             if (STATS) st.inst++;
             enter_instance(ip, o, d, time, ro, rd);
             R.set(ro, v3(frcp(rd.x), frcp(rd.y), frcp(rd.z)));
-            best_e = best + R.e2;
             stack[sp++] = kSentinel;
             node = __float_as_int(ip[6].z);
             continue;
@@ -750,7 +751,6 @@ DTOF_DEV bool trace_bvh(const float4 *__restrict__ N, const float4 *__restrict__
                 uint32_t gid = __float_as_uint(a.w);
                 if (t < best || !found || gid < hit.gid) {
                     best = t;
-                    best_e = t + R.e2;
                     hit.t = t;
                     hit.u = u;
                     hit.v = v;
@@ -801,34 +801,38 @@ DTOF_DEV uint32_t opaque_u32(uint32_t v) {
 template <bool STATS>
 DTOF_DEV bool trace_bvh_smem(const SmemScene M, int32_t root, const bool ANY, V3 o, V3 d, float tmax, float time, Hit &hit,
                              Counters &st) {
+#ifdef DTOF_LOCAL_STACK   // A/B builds only: the stack in (L1-resident) local memory, the shared-memory carve-out stays small
+    int lstack[40];
+    uint32_t sp = 0;
+#define DTOF_STK_EMPTY() (sp == 0u)
+#define DTOF_STK_PUSH(v) (lstack[sp++] = (v))
+#define DTOF_STK_POP() (lstack[--sp])
+#else
     uint32_t sp = M.stack;
+#define DTOF_STK_EMPTY() (sp == M.stack)
+#define DTOF_STK_PUSH(v) (sts_stack(sp, (v)), sp += 128u)
+#define DTOF_STK_POP() (sp -= 128u, lds_stack(sp))
+#endif
     int node = root;
     int cur_inst = -1;
     V3 ro = o, rd = d;
     RaySlab R;
     R.set(o, v3(frcp(d.x), frcp(d.y), frcp(d.z)));
-    float best = tmax, best_e = best + R.e2;
+    float best = tmax;
     bool found = false;
     if (STATS) {
         if (ANY) st.rays_shadow++; else st.rays_closest++;
     }
 #define DTOF_SPOP()                                                                                        \
     do {                                                                                                   \
-        if (sp == M.stack) {                                                                               \
+        if (DTOF_STK_EMPTY()) {                                                                            \
             node = kDone;                                                                                  \
         } else {                                                                                           \
-            sp -= 128u;                                                                                    \
-            node = lds_stack(sp);                                                                          \
+            node = DTOF_STK_POP();                                                                         \
             if (node == kSentinel) { /* leave the instance: back to the world-space ray */                 \
                 ro = o, rd = d, cur_inst = -1;                                                             \
                 R.set(o, v3(frcp_here(d.x), frcp_here(d.y), frcp_here(d.z)));                              \
-                best_e = best + R.e2;                                                                      \
-                if (sp == M.stack) {                                                                       \
-                    node = kDone;                                                                          \
-                } else {                                                                                   \
-                    sp -= 128u;                                                                            \
-                    node = lds_stack(sp);                                                                  \
-                }                                                                                          \
+                node = DTOF_STK_EMPTY() ? kDone : DTOF_STK_POP();                                          \
             }                                                                                              \
         }                                                                                                  \
     } while (0)
@@ -841,12 +845,11 @@ DTOF_DEV bool trace_bvh_smem(const SmemScene M, int32_t root, const bool ANY, V3
             if (STATS) st.nodes++;
             bool h0, h1;
             float t0n, t1n;
-            node_test(n0, n1, n2, R, best_e, h0, h1, t0n, t1n);
+            node_test(n0, n1, n2, R, best, h0, h1, t0n, t1n);
             const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
             if (h0 && h1) {
                 const bool swap = t1n < t0n;
-                sts_stack(sp, swap ? c0 : c1);
-                sp += 128u;
+                DTOF_STK_PUSH(swap ? c0 : c1);
                 node = swap ? c1 : c0;
             } else if (h0 || h1) {
                 node = h0 ? c0 : c1;
@@ -878,9 +881,7 @@ DTOF_DEV bool trace_bvh_smem(const SmemScene M, int32_t root, const bool ANY, V3
             ro = xf_point(inv, o);
             rd = xf_vector(inv, d);
             R.set(ro, v3(frcp(rd.x), frcp(rd.y), frcp(rd.z)));
-            best_e = best + R.e2;
-            sts_stack(sp, kSentinel);
-            sp += 128u;
+            DTOF_STK_PUSH(kSentinel);
             node = __float_as_int(q6.z);
             continue;
         }
@@ -895,7 +896,6 @@ DTOF_DEV bool trace_bvh_smem(const SmemScene M, int32_t root, const bool ANY, V3
                 const uint32_t gid = __float_as_uint(a.w);
                 if (t < best || !found || gid < hit.gid) {
                     best = t;
-                    best_e = t + R.e2;
                     hit.t = t;
                     hit.u = u;
                     hit.v = v;
@@ -908,6 +908,9 @@ DTOF_DEV bool trace_bvh_smem(const SmemScene M, int32_t root, const bool ANY, V3
         DTOF_SPOP();
     }
 #undef DTOF_SPOP
+#undef DTOF_STK_EMPTY
+#undef DTOF_STK_PUSH
+#undef DTOF_STK_POP
     return found;
 }
 

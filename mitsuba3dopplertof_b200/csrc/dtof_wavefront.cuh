@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(kWfBlock, DTOF_WF_TRACE_CTAS) wf_trace_kernel(
     V3 ro = v3(0, 0, 0), rd = v3(0, 0, 1);
     RaySlab R;
     R.set(ro, v3(0, 0, 0));
-    float best = 0.f, best_e = 0.f;
+    float best = 0.f;
     Hit hit;
     hit.t = 0.f, hit.u = 0.f, hit.v = 0.f, hit.gid = 0, hit.inst = -1;
     bool found = false, exhausted = false;
@@ -254,7 +254,6 @@ __global__ void __launch_bounds__(kWfBlock, DTOF_WF_TRACE_CTAS) wf_trace_kernel(
                     ro = v3(a.x, a.y, a.z), rd = v3(b.x, b.y, b.z);
                     best = a.w;
                     R.set(ro, v3(frcp(rd.x), frcp(rd.y), frcp(rd.z)));
-                    best_e = best + R.e2;
                     sp = 0, cur_inst = -1, found = false;
                     hit.gid = 0, hit.inst = -1;
                     node = A.scene.root;
@@ -279,7 +278,7 @@ __global__ void __launch_bounds__(kWfBlock, DTOF_WF_TRACE_CTAS) wf_trace_kernel(
                 const float4 n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3];
                 bool h0, h1;
                 float t0n, t1n;
-                node_test(n0, n1, n2, R, best_e, h0, h1, t0n, t1n);
+                node_test(n0, n1, n2, R, best, h0, h1, t0n, t1n);
                 int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
                 if (h0 && h1) {
                     bool swap = t1n < t0n;
@@ -299,7 +298,6 @@ __global__ void __launch_bounds__(kWfBlock, DTOF_WF_TRACE_CTAS) wf_trace_kernel(
                 const float4 a = qo[k], b = qd[k];
                 ro = v3(a.x, a.y, a.z), rd = v3(b.x, b.y, b.z);
                 R.set(ro, v3(frcp(rd.x), frcp(rd.y), frcp(rd.z)));
-                best_e = best + R.e2;
                 cur_inst = -1;
                 DTOF_WF_POP();
             } else if (count == 0) {   // animated instance: move the ray into its space (Embree semantics, enter_instance)
@@ -308,7 +306,6 @@ __global__ void __launch_bounds__(kWfBlock, DTOF_WF_TRACE_CTAS) wf_trace_kernel(
                 const float4 a = qo[k], b = qd[k];
                 enter_instance(ip, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), b.w, ro, rd);
                 R.set(ro, v3(frcp(rd.x), frcp(rd.y), frcp(rd.z)));
-                best_e = best + R.e2;
                 stack[sp++] = kSentinel;
                 node = __float_as_int(ip[6].z);
             } else {
@@ -327,7 +324,6 @@ __global__ void __launch_bounds__(kWfBlock, DTOF_WF_TRACE_CTAS) wf_trace_kernel(
                         uint32_t gid = __float_as_uint(a.w);
                         if (t < best || !found || gid < hit.gid) {
                             best = t;
-                            best_e = t + R.e2;
                             hit.t = t, hit.u = u, hit.v = v;
                             hit.gid = gid;
                             hit.inst = cur_inst;

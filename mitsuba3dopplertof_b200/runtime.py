@@ -137,6 +137,30 @@ class Context:
             return img, rgbw
         return img if develop else rgbw
 
+    def render_chunked(self, flat, params: _abi.Params, chunk_lanes: int, should_stop=None, develop: bool = True, both: bool = False):
+        """dtof_render_accumulate over lane chunks + dtof_read_film: what the Mitsuba plugin does so that cancel() / the
+        `timeout` property can stop a render between chunks. Returns like render()."""
+        pi = self.pass_info(params)
+        begin = int(params.lane_begin)
+        end = int(params.lane_end) or int(pi.wavefront_size)
+        chunk_lanes = max(int(pi.spp_per_pass), int(chunk_lanes) // int(pi.spp_per_pass) * int(pi.spp_per_pass))   # whole pixels
+        first = True
+        while begin < end and not (should_stop and should_stop()):
+            p = _abi.Params.from_buffer_copy(params)
+            p.lane_begin, p.lane_end = begin, min(end, begin + chunk_lanes)
+            self._check(self.lib.dtof_render_accumulate(self.h, C.byref(p), int(first)))
+            first = False
+            begin += chunk_lanes
+        h, w = flat.height, flat.width
+        rgbw = np.zeros((h, w, 4), np.float32) if (both or not develop) else None
+        img = np.zeros((h, w, 3), np.float32) if (both or develop) else None
+        if not first:
+            self._check(self.lib.dtof_read_film(self.h, _abi.as_fp(rgbw) if rgbw is not None else None,
+                                                _abi.as_fp(img) if img is not None else None))
+        if both:
+            return img, rgbw
+        return img if develop else rgbw
+
     def render_multi_pass(self, flat, params: _abi.Params, n_renders: int) -> np.ndarray:
         """Mean of `n_renders` developed renders with seed, seed+1, ... (averaged on the device)."""
         img = np.empty((flat.height, flat.width, 3), np.float32)
@@ -156,6 +180,15 @@ class Context:
         out = np.zeros(lanes.size, _abi.SAMPLE_RECORD_DTYPE)
         self._check(self.lib.dtof_trace_samples_pass(self.h, C.byref(params), lanes.ctypes.data_as(C.POINTER(C.c_uint64)),
                                                      lanes.size, int(pass_index), out.ctypes.data_as(C.POINTER(_abi.SampleRecord))))
+        return out
+
+    def trace_rays(self, rays: np.ndarray, any_hit: bool = False) -> np.ndarray:
+        """Scene::ray_intersect_preliminary / ray_test for caller-supplied rays (structured arrays _abi.RAY_DTYPE ->
+        _abi.RAY_HIT_DTYPE)."""
+        rays = np.ascontiguousarray(rays, _abi.RAY_DTYPE)
+        out = np.zeros(rays.size, _abi.RAY_HIT_DTYPE)
+        self._check(self.lib.dtof_trace_rays(self.h, rays.ctypes.data_as(C.POINTER(_abi.Ray)), rays.size, int(any_hit),
+                                             out.ctypes.data_as(C.POINTER(_abi.RayHit))))
         return out
 
     # ---- instrumentation -----------------------------------------------------------------------

@@ -643,6 +643,7 @@ struct OMesh {
 struct OTri {
     V3 p0, p1, p2;
     uint32_t mesh, face;
+    uint32_t gid; // position in the order of the scene description (stable under the BVH's reordering)
 };
 
 struct ONode {
@@ -782,9 +783,10 @@ inline bool box_test(const ONode &n, V3 o, V3 id, float maxt) {
         float ta = (n.bmin[a] - oo[a]) * ii[a], tb = (n.bmax[a] - oo[a]) * ii[a];
         float tn = fminf(ta, tb), tf = fmaxf(ta, tb);
         t0 = fmaxf(t0, tn);
-        t1 = fminf(t1, tf * 1.0000005f);
+        t1 = fminf(t1, tf);
     }
-    return t0 <= t1;
+    // maxt (the best hit so far) is widened too: far from the origin one ulp of t exceeds the padding of the boxes
+    return t0 <= t1 * 1.000001f;
 }
 
 // Embree-style instance entry (ext/embree/kernels/common/scene_instance.h:133-138,186-206):
@@ -817,7 +819,7 @@ bool intersect_closest(const dtof_oracle_scene &sc, V3 o, V3 d, float maxt, floa
             float t, u, v;
             st.tris++;
             if (tri_test(oo, dd, best, sc.tris[ti], t, u, v)) {
-                if (t < best || !found || (t == best && ti < hit.tri)) {
+                if (t < best || !found || (t == best && sc.tris[ti].gid < sc.tris[hit.tri].gid)) {
                     best = t;
                     hit = Hit{ t, u, v, gi, ti };
                     found = true;
@@ -1817,7 +1819,8 @@ dtof_oracle_scene *dtof_oracle_scene_create(const dtof_scene_desc *d, int use_bv
         for (uint32_t mi = in.first_mesh; mi < in.first_mesh + in.n_meshes; ++mi) {
             const OMesh &m = s->meshes[mi];
             for (uint32_t f = 0; f < m.faces.size() / 3; ++f)
-                s->tris.push_back(OTri{ m.pos[m.faces[3 * f]], m.pos[m.faces[3 * f + 1]], m.pos[m.faces[3 * f + 2]], mi, f });
+                s->tris.push_back(OTri{ m.pos[m.faces[3 * f]], m.pos[m.faces[3 * f + 1]], m.pos[m.faces[3 * f + 2]], mi, f,
+                                        (uint32_t) s->tris.size() });
         }
         g.n_tris = (uint32_t) s->tris.size() - g.first_tri;
         g.animated = in.animated != 0;
@@ -1906,6 +1909,30 @@ int dtof_oracle_trace_samples_pass(const dtof_oracle_scene *s, const dtof_params
             lane_sample(*s, *p, mod, smp, px, py, out[i], st);
             smp.advance();
         }
+    }
+    return 0;
+}
+
+int dtof_oracle_trace_rays(const dtof_oracle_scene *s, const dtof_ray *rays, uint32_t n, int any_hit, dtof_ray_hit *out) {
+    for (uint32_t i = 0; i < n; ++i) {
+        const dtof_ray &r = rays[i];
+        Counters st;
+        dtof_ray_hit o{};
+        o.instance = -1;
+        const V3 ro = v3(r.o[0], r.o[1], r.o[2]), rd = v3(r.d[0], r.d[1], r.d[2]);
+        if (any_hit) {
+            o.hit = intersect_any(*s, ro, rd, r.tmax, r.time, st) ? 1u : 0u;
+        } else {
+            Hit h;
+            if (intersect_closest(*s, ro, rd, r.tmax, r.time, h, st)) {
+                o.hit = 1;
+                o.t = h.t, o.u = h.u, o.v = h.v;
+                o.prim = s->tris[h.tri].gid;
+                o.instance = s->groups[h.inst].animated ? (int32_t) h.inst : -1;
+            }
+        }
+        o.nodes_visited = (uint32_t) st.nodes, o.tris_tested = (uint32_t) st.tris;
+        out[i] = o;
     }
     return 0;
 }

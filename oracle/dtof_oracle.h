@@ -60,6 +60,9 @@ void dtof_oracle_scene_destroy(dtof_oracle_scene *s);
 /* per-lane evaluation of pass 0 (pass > 0 lanes are replayed from pass 0 internally when pass_out >= 1) */
 int dtof_oracle_trace_samples(const dtof_oracle_scene *s, const dtof_params *p, const uint64_t *lanes, uint32_t n,
                               dtof_sample_record *out);
+/* Scene::ray_intersect_preliminary / ray_test (src/render/scene.cpp:125-154) for caller-supplied rays; prim = global
+ * triangle id in scene order, instance = index of the animated instance or -1 */
+int dtof_oracle_trace_rays(const dtof_oracle_scene *s, const dtof_ray *rays, uint32_t n, int any_hit, dtof_ray_hit *out);
 /* the lanes' samples of pass `pass` (earlier passes replayed; streams persist, integrator.cpp:299-308) */
 int dtof_oracle_trace_samples_pass(const dtof_oracle_scene *s, const dtof_params *p, const uint64_t *lanes, uint32_t n,
                                    uint32_t pass, dtof_sample_record *out);

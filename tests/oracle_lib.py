@@ -49,6 +49,7 @@ def lib() -> C.CDLL:
                                                     C.POINTER(_abi.SampleRecord)]),
             "dtof_oracle_trace_samples_pass": (C.c_int, [C.c_void_p, C.POINTER(_abi.Params), C.POINTER(u64), u32, u32,
                                                          C.POINTER(_abi.SampleRecord)]),
+            "dtof_oracle_trace_rays": (C.c_int, [C.c_void_p, C.POINTER(_abi.Ray), u32, C.c_int, C.POINTER(_abi.RayHit)]),
             "dtof_oracle_render": (C.c_int, [C.c_void_p, C.POINTER(_abi.Params), C.c_int, fp, fp]),
             "dtof_oracle_get_stats": (None, [C.c_void_p, C.POINTER(_abi.Stats)]),
         }
@@ -74,6 +75,15 @@ class OracleScene:
                                                   lanes.size, pass_index, out.ctypes.data_as(C.POINTER(_abi.SampleRecord)))
         if rc:
             raise RuntimeError(f"oracle trace_samples failed: {rc}")
+        return out
+
+    def trace_rays(self, rays, any_hit: bool = False) -> np.ndarray:
+        rays = np.ascontiguousarray(rays, _abi.RAY_DTYPE)
+        out = np.zeros(rays.size, _abi.RAY_HIT_DTYPE)
+        rc = lib().dtof_oracle_trace_rays(self.h, rays.ctypes.data_as(C.POINTER(_abi.Ray)), rays.size, int(any_hit),
+                                          out.ctypes.data_as(C.POINTER(_abi.RayHit)))
+        if rc:
+            raise RuntimeError(f"oracle trace_rays failed: {rc}")
         return out
 
     def render(self, params, n_threads: int = 0, develop: bool = True):

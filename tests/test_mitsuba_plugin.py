@@ -74,7 +74,7 @@ def test_plugin_exports_the_mitsuba_plugin_abi():
     assert re.search(r"\bplugin_name\b", out) and re.search(r"\bplugin_descr\b", out)
     # it binds the product through the C ABI only
     und = subprocess.run(["nm", "-D", "--undefined-only", PLUGIN], capture_output=True, text=True).stdout
-    for sym in ("dtof_create", "dtof_upload_scene", "dtof_render", "dtof_last_error", "dtof_destroy"):
+    for sym in ("dtof_create", "dtof_upload_scene", "dtof_render_accumulate", "dtof_read_film", "dtof_last_error", "dtof_destroy"):
         assert re.search(rf"\b{sym}\b", und), sym
 
 
@@ -225,3 +225,123 @@ def test_plugin_image_agrees_with_the_reference_integrator(tmp_path):
             sb = b[16 * ry:16 * ry + 16, 16 * rx:16 * rx + 16, 1]
             sem = np.sqrt((sa.var() + sb.var()) / sa.size) + 1e-7
             assert abs(sa.mean() - sb.mean()) < 6 * sem + 0.02 * abs(sa.mean()), (ry, rx, sa.mean(), sb.mean(), sem)
+
+
+# ---- the drop-in NAME: an untouched scene file through the reference's executable -------------------------------------
+DROPIN = os.path.join(REF, "dropin")
+DROPIN_EXE = os.path.join(DROPIN, "mitsuba")
+DROPIN_PLUGIN = os.path.join(DROPIN, "plugins", "dopplertofpath.so")
+REFERENCE_SCENE = os.path.join(HERE, "golden", "reference_scene.xml")   # configs_example/scene.xml, byte for byte
+needs_dropin = pytest.mark.skipif(not (os.path.exists(DROPIN_EXE) and os.path.exists(DROPIN_PLUGIN)),
+                                  reason="no drop-in view of the reference runtime in oracle/_ref/dropin (git-ignored build artefact)")
+
+
+def _run_dropin(args, timeout=600, env_extra=None):
+    """The reference's executable started from the drop-in view: libmitsuba.so is found there, so plugins/<type>.so
+    resolves there too (src/mitsuba/mitsuba.cpp:315-318) and plugins/dopplertofpath.so is the product's plugin."""
+    env = dict(os.environ, LD_LIBRARY_PATH=DROPIN + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    env.update(env_extra or {})
+    return subprocess.run([DROPIN_EXE, "-m", "scalar_rgb"] + args, capture_output=True, text=True, env=env, timeout=timeout)
+
+
+def _read_exr(path):
+    os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
+    import cv2
+    img = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+    assert img is not None, path
+    return np.ascontiguousarray(img[..., :3][..., ::-1]).astype(np.float32)   # BGR -> RGB
+
+
+def test_reference_scene_fixture_is_the_reference_file():
+    """tests/golden/reference_scene.xml is configs_example/scene.xml byte for byte (checked where the reference is present)."""
+    ref = "/root/reference/configs_example/scene.xml"
+    if not os.path.exists(ref):
+        pytest.skip("no reference checkout here")
+    assert open(ref, "rb").read() == open(REFERENCE_SCENE, "rb").read()
+    assert b'<integrator type="dopplertofpath">' in open(REFERENCE_SCENE, "rb").read()
+
+
+@needs_dropin
+def test_dropin_view_shadows_only_the_integrator():
+    names = set(os.listdir(os.path.join(DROPIN, "plugins")))
+    assert "dopplertofpath.so" in names and "correlated.so" in names and "hdrfilm.so" in names
+    assert not os.path.islink(DROPIN_PLUGIN)                                   # the product's plugin, a real file
+    assert os.path.islink(os.path.join(DROPIN, "plugins", "correlated.so"))    # everything else is the reference's
+    und = subprocess.run(["nm", "-D", "--undefined-only", DROPIN_PLUGIN], capture_output=True, text=True).stdout
+    for sym in ("dtof_create", "dtof_create_multi", "dtof_render_accumulate", "dtof_read_film"):
+        assert re.search(rf"\b{sym}\b", und), sym
+
+
+@pytest.mark.gpu
+@needs_dropin
+def test_untouched_reference_scene_renders_through_the_dropin_plugin(tmp_path):
+    """`mitsuba scene.xml` with configs_example/scene.xml UNCHANGED (integrator type "dopplertofpath", 256 x 256 @ 1024
+    spp, OpenEXR output): XML parsing, the correlated sampler, film and file writing are the reference's code, the
+    integrator is the B200 plugin. The image is compared with the reference's own committed render of this file
+    (configs_example/scene.exr, tests/golden/scene_exr.npy)."""
+    if not _runnable():
+        pytest.skip("reference runtime cannot execute on this CPU")
+    scene = os.path.join(str(tmp_path), "scene.xml")
+    with open(scene, "wb") as f:
+        f.write(open(REFERENCE_SCENE, "rb").read())
+    out = os.path.join(str(tmp_path), "scene.exr")
+    r = _run_dropin(["-o", out, scene])
+    log = r.stdout + r.stderr
+    assert r.returncode == 0, log[-2000:]
+    assert "dopplertofpath on B200" in log and "Rendering finished." in log
+    img = _read_exr(out)
+    gold = np.load(os.path.join(HERE, "golden", "scene_exr.npy")).astype(np.float32)
+    assert img.shape == gold.shape == (256, 256, 3)
+    rel_mse = float(((img - gold) ** 2).mean() / (gold ** 2).mean())
+    assert rel_mse < 5e-3, f"relative MSE vs configs_example/scene.exr = {rel_mse:.3e}"
+
+
+@pytest.mark.gpu
+@needs_dropin
+def test_dropin_plugin_honours_timeout(tmp_path):
+    """`timeout` (include/mitsuba/render/integrator.h:106-108) is checked between the chunks the plugin submits: a
+    2 x 2048-spp render of the domino scene (16 chunks of 2^28 lanes) with a 50 ms budget stops early and still writes a
+    (partially accumulated) image."""
+    if not _runnable():
+        pytest.skip("reference runtime cannot execute on this CPU")
+    xml = open(os.path.join(SCENES, "c4_domino.xml")).read()
+    xml = xml.replace('<integrator type="dopplertofpath">', '<integrator type="dopplertofpath">\n<float name="timeout" value="0.05" />')
+    xml = xml.replace('<string name="file_format" value="openexr" />',
+                      '<string name="file_format" value="pfm" />\n<string name="component_format" value="float32" />')
+    scene = os.path.join(str(tmp_path), "c4.xml")
+    open(scene, "w").write(xml)
+    out = os.path.join(str(tmp_path), "out.pfm")
+    defs = {"resx": 1024, "resy": 1024, "spp": 4096, "wave": "trapezoidal", "tsm": "antithetic_mirror", "shift": 0.0, "w_g": 150}
+    r = _run_dropin([f"-D{k}={v}" for k, v in defs.items()] + ["-o", out, scene])
+    log = r.stdout + r.stderr
+    assert r.returncode == 0, log[-2000:]
+    assert "Rendering stopped early" in log
+    img = _read_pfm(out)
+    assert np.isfinite(img).all()
+    # the first chunks cover the top rows; the bottom of the frame was never reached
+    assert np.abs(img[:32]).max() > 0 and np.abs(img[-32:]).max() == 0
+
+
+@pytest.mark.gpu
+@needs_dropin
+def test_dropin_plugin_on_all_gpus_equals_one_gpu(tmp_path):
+    """DTOF_DEVICES=all: the reference's single `mitsuba` process renders the untouched scene on every GPU of the box
+    (one context, sharded behind the C ABI); the image equals the one-GPU image to float summation order."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    if not _runnable():
+        pytest.skip("reference runtime cannot execute on this CPU")
+    scene = os.path.join(str(tmp_path), "scene.xml")
+    with open(scene, "wb") as f:
+        f.write(open(REFERENCE_SCENE, "rb").read())
+    imgs = []
+    for devs in ("0", "all"):
+        out = os.path.join(str(tmp_path), f"scene_{devs}.exr")
+        r = _run_dropin(["-Dspp=256", "-o", out, scene], env_extra={"DTOF_DEVICES": devs})
+        log = r.stdout + r.stderr
+        assert r.returncode == 0, log[-2000:]
+        assert f"on {torch.cuda.device_count() if devs == 'all' else 1} device(s)" in log
+        imgs.append(_read_exr(out))
+    scale = np.abs(imgs[0]).max()
+    assert np.abs(imgs[0] - imgs[1]).max() <= 2e-3 * scale    # fp16 EXR: half-precision rounding of each image
