@@ -4,22 +4,33 @@
 Metric: Msamples/s = camera samples (pixels x spp, each a full path of <= max_depth bounces incl. NEE) per second
 of render(), scene resident on the GPU.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3|c4|c5] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload all|c1|c2|c3|c4|c5] [--impl reference]
 
+* headline     C1 = configs_example/scene.xml verbatim (BASELINE.json configs[0], the "example scene" the north_star target
+               is quoted on), exactly K timed steps after W >= 3 warm-up steps. With --workload all (the default) the same
+               line carries a `workloads` array with one record per configuration of BASELINE.json:
+                 N = 1: C1, C2, C3, C4 (1024^2 @ 4096 spp, 2 passes), C5 (4.2 M triangles, 2048^2 @ 2 x 512 spp), full size;
+                 N > 1: C1 and C2 weak (one seed per rank), C4 STRONG by pixel tiles, C5 STRONG by sample slots
+               each with value / e2e / roofline / clocks; secondary workloads run min(K, budget / step time) >= 3 timed steps
 * step         one render() of the workload (film zeroed, all passes, film all-reduce when N > 1, develop)
 * value        whole-job samples / device time (CUDA events per step on the render stream, max over ranks);
                an L2 flush (256 MiB write) runs between steps outside the timed events
 * e2e          same metric through the host-buffer C ABI call (`dtof_update_instances` + `dtof_render`):
                H2D of the animated-instance keyframes + parameters, D2H of the RGBW film and the developed image
-* roofline     traversal bytes: (64 B x nodes + 48 B x triangles + 112 B x instance entries) per sample, counted by a
-               separate stats launch of the fused kernel (same walk), + 16 B film; / measured HBM copy bandwidth.
-               Scenes whose BVH is walked from HBM (c5) render through the wavefront pipeline (csrc/dtof_wavefront.cuh)
+* roofline     the BINDING bound per workload: `issue` (lane-instructions of the DESIGN.md 4.1 model and, from the committed
+               ncu capture, executed thread-instructions, against 148 x 4 x 32 x SM clock) where the traversal data is
+               shared-memory resident (C1-C4); `hbm` (algorithmic traversal bytes 64 B x nodes + 48 B x triangles + 112 B x
+               instance entries + 16 B film per sample, and the DRAM bytes ncu measured, against the measured HBM copy
+               bandwidth) where the BVH is walked from HBM (C5, wavefront pipeline). Per-sample counts come from a stats
+               launch of the same walk; both sub-records are always present
 * cpu_baseline the reference's own CPU build (oracle/_ref/mitsuba, scalar_rgb + Embree) on all host threads when it is
-               present, else the CPU oracle (oracle/, a port of the reference algorithm); bounded sample
+               present, else the CPU oracle (oracle/, a port of the reference algorithm); bounded sample; headline only
 * N > 1        weak scaling: rank r renders the workload with seed r (the tutorials' multi-seed averaging,
-               doppler_tutorials/src/program_runner.py:11-31), films are summed with one NCCL all-reduce per step
+               doppler_tutorials/src/program_runner.py:11-31), films are summed with one NCCL all-reduce per step;
+               strong scaling: ONE render sharded over the ranks inside the C ABI, same all-reduce
 * --impl reference   the reference's own CPU build (oracle/_ref/mitsuba, scalar_rgb + Embree; llvm_rgb cannot load
-               libLLVM in this image) on a bounded sample; falls back to the oracle port if the binary cannot run
+               libLLVM in this image) on a bounded sample of the headline workload; falls back to the oracle port if the
+               binary cannot run
 """
 import argparse
 import ctypes as C
@@ -53,6 +64,9 @@ WORKLOADS = {
            "C5 slab room + 4.2 M-triangle displaced sphere as one animated instance, 2048x2048 @ 1024 spp per render "
            "(2 passes x 512; 16 renders with seed 0..15 make the 16k-spp image)"),
 }
+
+
+HEADLINE = "c1"   # configs_example/scene.xml verbatim: the scene BASELINE.json's target is quoted on
 
 
 def measured_peaks():
@@ -219,42 +233,23 @@ def run_reference_arm(args):
     }))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--spp", type=int, default=0, help="override the workload's spp (profiling under ncu only)")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong-slots", "strong-tiles"],
-                    help="N > 1: weak = one seed per rank (default, the contract's line); strong-* = ONE render of the workload "
-                         "sharded over the ranks by sample slots / pixel tiles (SURVEY.md 8e), films summed by one all-reduce")
-    args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference_arm(args)
+def _counters(workload, pipeline):
+    """ncu-measured per-sample counters of the shipped library (profiles/r02_counters.json, written from the committed
+    ncu captures by profiles/tools/counters.py); None where no capture of this workload / pipeline exists."""
+    for fn in ("r02_counters.json", "r01_traffic.json"):
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", fn))).get(workload + ("_wavefront" if pipeline == 1 else ""))
+            if tj:
+                return dict(tj, file="profiles/" + fn)
+        except Exception:   # noqa: BLE001
+            pass
+    return None
 
-    # stdout carries exactly ONE line, the JSON record: anything libraries print to fd 1 meanwhile (NCCL's version
-    # banner under NCCL_DEBUG=VERSION, for one) is sent to stderr until the record is written
-    sys.stdout.flush()
-    stdout_fd = os.dup(1)
-    os.dup2(2, 1)
 
-    import torch
-    import torch.distributed as dist
+def bench_workload(name, args, steps, warmup, scaling, world, rank, local, dist, torch, budget_s=None, cpu_baseline=False):
+    """One workload, one JSON-able record (rank 0; other ranks return None). `scaling`: weak | strong-slots | strong-tiles."""
     from mitsuba3dopplertof_b200 import _abi, runtime
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    scene, desc = load_workload(args.workload, args.spp)
+    scene, desc = load_workload(name, args.spp)
     ctx = runtime.Context(local)
     t0 = time.perf_counter()
     flat = ctx.upload(scene)
@@ -263,20 +258,19 @@ def main():
     H, W = flat.height, flat.width
     spp = sampler.sample_count
     samples_per_step = H * W * spp
-    strong = args.scaling != "weak" and world > 1
+    strong = scaling != "weak" and world > 1
     seed = 0 if strong else rank     # weak scaling: one seed per rank
     params = scene.integrator.params(sampler, seed=seed)
     pi = ctx.pass_info(params)
     full_params = params
     if strong:   # this rank's share of the one wavefront (interleaved shards, whole correlate groups / whole tiles)
         from mitsuba3dopplertof_b200.distributed import shard_params
-        params = shard_params(params, pi, world, rank, "slots" if args.scaling == "strong-slots" else "tiles", tile_pixels=64)
+        params = shard_params(params, pi, world, rank, "slots" if scaling == "strong-slots" else "tiles", tile_pixels=64)
 
     stream = torch.cuda.current_stream()
     film = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
     img = torch.empty((H, W, 3), dtype=torch.float32, device="cuda")
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
-    launches_before = ctx.launch_count()
 
     def step():
         film.zero_()
@@ -285,15 +279,24 @@ def main():
             dist.all_reduce(film)    # sum of the RGBW films over NVLink (NCCL)
         ctx.develop_device(film.data_ptr(), img.data_ptr(), stream.cuda_stream)
 
-    for _ in range(max(args.warmup, 3)):
+    warmup = max(warmup, 3)
+    t0 = time.perf_counter()
+    for _ in range(warmup):
         step()
     torch.cuda.synchronize()
+    est_step_s = (time.perf_counter() - t0) / warmup
+    if budget_s:    # secondary workloads: a bounded number of timed steps (>= 3), stated in the record
+        steps = int(max(3, min(steps, budget_s / max(est_step_s, 1e-6))))
+        if world > 1:
+            tt = torch.tensor([steps], dtype=torch.int64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MIN)
+            steps = int(tt.item())
     if world > 1:
         dist.barrier()
     clocks = ClockSampler(local)
     clocks.start()
     torch.cuda.synchronize()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     kernel_ms = []
     launches0 = ctx.launch_count()
     for s0, s1 in ev:
@@ -308,7 +311,7 @@ def main():
     prod_pipeline = ctx.last_pipeline()      # 0 = fused kernel, 1 = wavefront pipeline (HBM-resident scenes)
     if world > 1:
         dist.barrier()
-    launches = ctx.launch_count() - launches0 + args.steps   # ours + one film memset per step
+    launches = ctx.launch_count() - launches0 + steps   # ours + one film memset per step
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
     clocks.stop_flag = True
     clocks.join(timeout=2)
@@ -317,12 +320,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     jobs = 1 if strong else world     # strong scaling: the ranks share ONE render
-    value = jobs * samples_per_step * args.steps / (total_ms * 1e-3) / 1e6
+    value = jobs * samples_per_step * steps / (total_ms * 1e-3) / 1e6
 
     # ---- e2e through the host-buffer C ABI (what a plugin calls)
     anim = [(i, flat.instances[i]) for i in range(flat.desc.n_instances) if flat.instances[i].animated]
     h2d = len(anim) * C.sizeof(_abi.Instance) + C.sizeof(_abi.Params)
     d2h = H * W * (4 + 3) * 4
+
     def e2e_step():
         for i, inst in anim:     # per-frame keyframe upload, as an animation loop would do
             ctx.update_instances(i, [inst])
@@ -332,27 +336,25 @@ def main():
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_img, e2e_rgbw = e2e_step()
+    for _ in range(steps):
+        e2e_step()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = jobs * samples_per_step * args.steps / float(t.item()) / 1e6
+    e2e_value = jobs * samples_per_step * steps / float(t.item()) / 1e6
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        sys.stdout.flush()
-        os.dup2(stdout_fd, 1)
-        return
+        ctx.close()
+        del film, img, flush
+        torch.cuda.empty_cache()
+        return None
 
-    # ---- roofline of the dominant kernel (render_kernel): algorithmic traversal bytes / kernel time
+    # ---- roofline of the dominant kernel: per-sample counts of the BVH walk from a stats launch of the same walk
     ctx.set_stats(True)
     # the counters are per-sample averages: every K-th pixel (all its sample slots) is plenty, ~16 M lanes
     K = max(1, int(pi.wavefront_size // (1 << 24))) | 1
     ps = scene.integrator.params(sampler, seed=seed)
-    params = full_params   # the roofline counters describe the whole workload
     if K > 1:
         ps.shard_block, ps.shard_count, ps.shard_index = pi.spp_per_pass, K, 0
     film.zero_()
@@ -368,53 +370,60 @@ def main():
     mode_name = {0: "bvh_global", 1: "bvh_smem", 2: "flat_smem"}.get(prod_mode, str(prod_mode))
     peaks, peak_src = measured_peaks()
     samples_per_launch = samples_per_step / (world if strong else 1)   # rank 0's share of the render under strong scaling
-    achieved = bytes_per_sample * samples_per_launch / (kms * 1e-3) / 1e9
+    rate = samples_per_launch / (kms * 1e-3)                           # samples / s of the dominant kernel(s)
     clk = clocks.summary()
     issue_peak = 148 * 4 * 32 * (clk["sm_mhz"] or peaks.get("sm_max_mhz", 1965.0)) * 1e6
-    traffic, ncu_issue = None, None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(
-            args.workload + ("_wavefront" if prod_pipeline == 1 else ""))
-        if tj:
-            traffic = tj["bytes_per_sample"] * samples_per_step
-            ncu_issue = tj.get("issue_active_pct")
-    except Exception:   # noqa: BLE001
-        pass
+    cnt = _counters(name, prod_pipeline)
+    hbm = {"algorithmic_bytes_per_sample": bytes_per_sample, "achieved": bytes_per_sample * rate / 1e9, "peak": peaks["hbm_gbs"],
+           "unit": "GB/s", "frac": bytes_per_sample * rate / 1e9 / peaks["hbm_gbs"],
+           "measured_dram_bytes_per_sample": cnt.get("bytes_per_sample") if cnt else None,
+           "measured_dram_frac": cnt["bytes_per_sample"] * rate / 1e9 / peaks["hbm_gbs"] if cnt and cnt.get("bytes_per_sample") else None,
+           "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})"}
+    issue = {"model_lane_instr_per_sample": instr_per_sample, "achieved": instr_per_sample * rate / 1e9, "peak": issue_peak / 1e9,
+             "unit": "Glane-instr/s", "frac": instr_per_sample * rate / issue_peak,
+             "executed_thread_instr_per_sample": cnt.get("thread_inst_per_sample") if cnt else None,
+             "executed_frac": cnt["thread_inst_per_sample"] * rate / issue_peak if cnt and cnt.get("thread_inst_per_sample") else None,
+             "ncu_active_lanes_per_inst": cnt.get("lanes_per_inst") if cnt else None,
+             "ncu_issue_active_pct": cnt.get("issue_active_pct") if cnt else None,
+             "peak_source": "148 SMs x 4 SMSPs x 32 lanes x SM clock sampled under load"}
+    smem_resident = mode_name != "bvh_global"
+    # the BINDING bound: instruction issue where the traversal data is shared-memory resident (DRAM traffic ~ 0), HBM where
+    # the BVH is walked from HBM / L2. Both sub-records are always present; the top-level fields repeat the binding one.
+    top = issue if smem_resident else hbm
     roofline = {
-        "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-        "traffic": traffic, "traffic_source": "profiles/r01_traffic.json (ncu dram bytes per sample x samples per launch)" if traffic else None,
-        "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})",
+        "bound": "issue" if smem_resident else "hbm", "achieved": top["achieved"], "peak": top["peak"], "unit": top["unit"],
+        "frac": top["frac"],
+        "traffic": cnt["bytes_per_sample"] * samples_per_launch if cnt and cnt.get("bytes_per_sample") else None,
+        "traffic_source": f"{cnt['file']}: ncu dram__bytes_read.sum + dram__bytes_write.sum per sample x samples per launch ({cnt.get('source')})" if cnt else None,
         "kernel": ("wavefront pipeline: wf_generate + per bounce wf_trace<closest> / wf_shade / wf_trace<any> + wf_splat, "
                    "several batches in flight (kernel_ms spans the whole pipeline of one render)") if prod_pipeline == 1
         else "render_kernel",
         "pipeline": "wavefront" if prod_pipeline == 1 else "fused",
-        "kernel_ms": kms, "bytes_per_sample": bytes_per_sample,
+        "kernel_ms": kms, "samples_per_launch": samples_per_launch,
         "per_sample": {"rays_closest": st.rays_closest / n, "rays_shadow": st.rays_shadow / n, "nodes": st.nodes_visited / n,
                        "tris": st.tris_tested / n, "inst": st.inst_visits / n},
         "traversal_mode": mode_name,
-        "note": ("counts are those of the BVH walk (closest + shadow rays); " + (
-            "the traversal data of this workload is staged in shared memory, so the byte rate is served by SMEM, not HBM"
-            if mode_name != "bvh_global" else "nodes/triangles are read through L1/L2 from HBM") + (
-            "; the wavefront pipeline additionally moves its ray / hit queues and per-lane path state through HBM, "
-            "which is part of `traffic`, not of the algorithmic bytes" if prod_pipeline == 1 else "")),
-        "issue": {"instr_per_sample_model": instr_per_sample,
-                  "achieved_lane_instr_per_s": instr_per_sample * samples_per_launch / (kms * 1e-3),
-                  "peak_lane_instr_per_s": issue_peak,
-                  "frac": instr_per_sample * samples_per_launch / (kms * 1e-3) / issue_peak,
-                  "ncu_issue_active_pct": ncu_issue},
+        "issue": issue, "hbm": hbm,
+        "note": ("per-sample counts are those of the BVH walk (closest + shadow rays). " + (
+            "The traversal data of this workload is staged in shared memory: DRAM traffic is ~0 and the `hbm` sub-record is "
+            "only the formal byte rate; the kernel is bound by instruction issue (`frac` = algorithmic lane-instructions of "
+            "the DESIGN.md 4.1 model / peak issue rate, `issue.executed_frac` = thread-instructions ncu counted / peak)"
+            if smem_resident else
+            "Nodes / triangles are read through L1 / L2 from HBM: `frac` = algorithmic traversal bytes / measured HBM peak, "
+            "`hbm.measured_dram_frac` = DRAM bytes ncu counted (incl. the pipeline's own queues and per-lane state) / peak")),
     }
 
     cpu = None
-    if not args.no_cpu_baseline and world == 1:
+    if cpu_baseline:
         # the reference's own CPU build when oracle/_ref holds one (it is the faster of the two), else the oracle port
         try:
             cores = os.cpu_count() or 1
-            fn, wl_params, _ = WORKLOADS[args.workload]
+            fn, wl_params, _ = WORKLOADS[name]
             wp = dict({"resx": 256, "resy": 256, "spp": 1024}, **wl_params)
             px = int(wp["resx"]) * int(wp["resy"])
-            probe = reference_binary_throughput(args.workload, 4, cores)
+            probe = reference_binary_throughput(name, 4, cores)
             ref_spp = int(max(4, min(int(args.spp or wp["spp"]), (probe * 1e6 * 12.0 / px) // 4 * 4)))
-            v = reference_binary_throughput(args.workload, ref_spp, cores)
+            v = reference_binary_throughput(name, ref_spp, cores)
             cpu = {"value": v, "unit": "Msamples/s", "cores": cores, "kind": "reference",
                    "sample": f"{wp['resx']}x{wp['resy']} @ {ref_spp} spp of the same scene, reference scalar_rgb+Embree binary "
                              f"(oracle/_ref/mitsuba wrapped in `moment`, -t {cores}; llvm_rgb cannot load libLLVM in this image)"}
@@ -423,24 +432,100 @@ def main():
             v, cores, sample = cpu_oracle_throughput(scene, seed)
             cpu = {"value": v, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample}
 
-    sys.stdout.flush()
-    os.dup2(stdout_fd, 1)
-    print(json.dumps({
-        "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-        "scaling": "strong" if strong else "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+    rec = {
+        "workload": name, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": total_ms / steps, "scaling": "strong" if strong else "weak",
+        "sharding": scaling[7:] if strong else ("seeds" if world > 1 else None),
         "config": {"workload": desc, "width": W, "height": H, "spp": spp, "spp_per_pass": pi.spp_per_pass,
                    "n_passes": pi.n_passes, "triangles": flat.n_triangles, "instances": flat.desc.n_instances,
-                   "seed": "0, one render sharded by " + args.scaling[7:] if strong else "rank index (multi-seed averaging)", "l2_flush": "256 MiB write between steps, outside the timed events",
-                   "scene_upload_s": upload_s},
+                   "seed": "0, one render sharded by " + scaling[7:] if strong else "rank index (multi-seed averaging)",
+                   "l2_flush": "256 MiB write between steps, outside the timed events", "scene_upload_s": upload_s},
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,
-    }), flush=True)
+    }
+    ctx.close()
+    del film, img, flush
+    torch.cuda.empty_cache()
+    return rec
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="all", choices=["all"] + sorted(WORKLOADS),
+                    help="all (default): the headline line is C1, the example scene the north_star target is quoted on, and a "
+                         "`workloads` array carries every configuration of BASELINE.json (N = 1: C1..C5; N > 1: C1 and C2 weak, "
+                         "C4 strong by tiles, C5 strong by sample slots); cN: that workload alone")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--spp", type=int, default=0, help="override the workload's spp (profiling under ncu only)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong-slots", "strong-tiles"],
+                    help="with --workload cN and N > 1: weak = one seed per rank; strong-* = ONE render of the workload "
+                         "sharded over the ranks by sample slots / pixel tiles (SURVEY.md 8e), films summed by one all-reduce")
+    ap.add_argument("--secondary-budget", type=float, default=10.0,
+                    help="seconds of timed steps per secondary workload of --workload all (>= 3 steps each)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.workload == "all":
+            args.workload = HEADLINE
+        return run_reference_arm(args)
+
+    # stdout carries exactly ONE line, the JSON record: anything libraries print to fd 1 meanwhile (NCCL's version
+    # banner under NCCL_DEBUG=VERSION, for one) is sent to stderr until the record is written
+    sys.stdout.flush()
+    stdout_fd = os.dup(1)
     os.dup2(2, 1)
+
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    common = dict(world=world, rank=rank, local=local, dist=dist, torch=torch)
+    if args.workload != "all":
+        plan = [(args.workload, args.scaling, None)]
+    elif world == 1:
+        plan = [(HEADLINE, "weak", None)] + [(w, "weak", args.secondary_budget) for w in sorted(WORKLOADS) if w != HEADLINE]
+    else:
+        plan = [(HEADLINE, "weak", None), ("c2", "weak", args.secondary_budget),
+                ("c4", "strong-tiles", args.secondary_budget), ("c5", "strong-slots", args.secondary_budget)]
+    records = []
+    for i, (name, scaling, budget) in enumerate(plan):
+        rec = bench_workload(name, args, args.steps, args.warmup, scaling, budget_s=budget,
+                             cpu_baseline=(i == 0 and world == 1 and not args.no_cpu_baseline), **common)
+        records.append(rec)
+        if rank == 0:
+            sys.stderr.write(f"[bench] {name} {scaling} N={world}: {rec['value']:.1f} Msamples/s, e2e {rec['e2e']['value']:.1f} "
+                             f"({rec['steps']} steps, {rec['ms_per_step']:.2f} ms)\n")
+
+    if rank == 0:
+        h = records[0]
+        line = {
+            "metric": "Msamples/s", "value": h["value"], "unit": "Msamples/s", "n_gpus": world, "steps": h["steps"],
+            "warmup": h["warmup"], "ms_per_step": h["ms_per_step"], "higher_is_better": True, "scaling": h["scaling"],
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": h["config"], "clocks": h["clocks"], "e2e": h["e2e"], "gpu_launches": h["gpu_launches"],
+            "roofline": h["roofline"], "cpu_baseline": h["cpu_baseline"],
+        }
+        if len(records) > 1:
+            line["gpu_launches"] = int(sum(r["gpu_launches"] for r in records))
+            line["workloads"] = [{k: v for k, v in r.items() if k != "cpu_baseline"} for r in records]
+        sys.stdout.flush()
+        os.dup2(stdout_fd, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 

@@ -79,14 +79,28 @@ def render_distributed(scene, seed: int = 0, spp: int = 0, mode: str = "slots", 
         pi = _pass_info_host(flat, base)
     p = shard_params(base, pi, world, rank, mode, tile_pixels)
     film = render_fn(flat, p)
+
+    def _develop(f):   # HDRFilm::develop
+        w = f[..., 3:4]
+        return f[..., :3] / torch.where(w == 0, torch.ones_like(w), w)
+
+    if mode == "seeds" and develop:
+        # the tutorials' estimator (program_runner.py:11-31) and dtof_render_multi_pass: the MEAN OF THE DEVELOPED
+        # images, mean_r(rgb_r / w_r) -- not sum(rgb) / sum(w), which differs as soon as the filter weights of two seeds
+        # differ (tent, gaussian and the lobed filters)
+        img = _develop(film)
+        if world > 1:
+            dist.all_reduce(img)
+            img /= world
+        return img
     if world > 1:
-        dist.all_reduce(film)            # sum of RGBW films
+        dist.all_reduce(film)            # sum of RGBW films: slots / tiles are shards of ONE film
         if mode == "seeds":
-            film /= world
+            film /= world                # develop=False: the mean RGBW film over the seeds (a different estimator than
+                                         # the developed mean above; documented, the caller asked for raw films)
     if not develop:
         return film
-    w = film[..., 3:4]
-    return film[..., :3] / torch.where(w == 0, torch.ones_like(w), w)    # HDRFilm::develop
+    return _develop(film)
 
 
 def _pass_info_host(flat, p):

