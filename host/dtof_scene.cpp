@@ -817,6 +817,8 @@ struct Loader {
                 if (t == "boolean") parse_bool(p.value);
                 out[attr(*ch, "name")] = p;
             } else if (t == "rgb" || t == "spectrum") {
+                if (!has(*ch, "value"))   // <spectrum filename=...>: a tabulated spectrum, not a constant
+                    throw Error("<" + t + "> '" + attr(*ch, "name", "") + "' without a constant value is outside the supported subset");
                 Prop p{ t, attr(*ch, "value"), {} };
                 p.vec = parse_floats(p.value);
                 if (p.vec.size() != 1 && p.vec.size() != 3)
@@ -827,6 +829,22 @@ struct Loader {
             } else if (t == "point" || t == "vector") {
                 Prop p{ t, "", vec(*ch, 0.0) };
                 out[attr(*ch, "name")] = p;
+            } else {
+                // child objects are handled (or refused) by the code that walks the parent; a <texture>, a NAMED <ref> (a
+                // texture / spectrum bound to a property) or an unknown tag would silently fall back to the plugin's
+                // default value (0.5 reflectance, unit radiance ...): refuse it
+                static const char *structural[] = { "transform", "animation", "bsdf", "emitter", "ref", "sampler", "film",
+                                                    "rfilter", "shape", "sensor", "integrator", "default", "include", "alias" };
+                bool ok = false;
+                for (const char *k : structural)
+                    ok = ok || t == k;
+                if (t == "ref" && has(*ch, "name"))
+                    ok = false;
+                if (!ok)
+                    throw Error("<" + t + (has(*ch, "name") ? " name='" + attr(*ch, "name") + "'" : std::string()) + "> inside <" +
+                                node.tag + "> is outside the supported subset: only constant float / integer / boolean / string / "
+                                "rgb / spectrum / point / vector properties are read (textures and spatially varying values are "
+                                "not in scope)");
             }
         }
         return out;
@@ -1165,6 +1183,9 @@ struct Loader {
             throw Error("only the 'perspective' sensor is in the hot-path scope");
         auto p = props(node);
         PerspectiveSensor s;
+        // a sensor without a <sampler> gets the reference's default: `independent`, 4 spp (src/render/sensor.cpp:47-48)
+        s.sampler.correlated = false;
+        s.sampler.time_correlate_number = s.sampler.path_correlate_number = 1;
         for (auto &ch : node.children) {
             const std::string *nm = ch->attr("name");
             if (ch->tag == "transform" && nm && *nm == "to_world") {

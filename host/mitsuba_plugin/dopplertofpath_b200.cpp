@@ -208,7 +208,9 @@ public:
             Throw("dtof_pass_info_for: %s", dtof_last_error(m_ctx));
         const uint64_t chunk = std::max<uint64_t>(1, (uint64_t(1) << 28) / pi.spp_per_pass) * pi.spp_per_pass;
         bool first = true;
-        for (uint64_t begin = 0; begin < pi.wavefront_size && !should_stop(); begin += chunk, first = false) {
+        // (the first chunk is always submitted: scene upload counts towards the timer, and the reference's block loop has
+        // rendered its first blocks too by the time should_stop() turns true)
+        for (uint64_t begin = 0; begin < pi.wavefront_size && (first || !should_stop()); begin += chunk, first = false) {
             dtof_params q = p;
             q.lane_begin = begin, q.lane_end = std::min<uint64_t>(pi.wavefront_size, begin + chunk);
             if (dtof_render_accumulate(m_ctx, &q, first) != DTOF_OK)     // H2D params, kernels

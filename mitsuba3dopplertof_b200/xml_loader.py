@@ -28,6 +28,11 @@ def _floats(s: str):
     return [float(t) for t in re.split(r"[\s,]+", s.strip()) if t]
 
 
+# child tags that are objects or structure, handled by the code that walks the parent (never property values)
+_STRUCTURAL = frozenset(("transform", "animation", "bsdf", "emitter", "ref", "sampler", "film", "rfilter", "shape", "sensor",
+                         "integrator", "default", "include", "alias"))
+
+
 class _Loader:
     def __init__(self, params: Optional[Dict[str, str]], base_dir: str):
         self.defaults: Dict[str, str] = dict(params or {})
@@ -63,12 +68,23 @@ class _Loader:
             elif ch.tag == "string":
                 out[n] = self.attr(ch, "value")
             elif ch.tag in ("rgb", "spectrum"):
+                if ch.get("value") is None:   # <spectrum filename=...>: a tabulated spectrum, not a constant
+                    raise ValueError(f"<{ch.tag}> '{n}' without a constant value is outside the supported subset")
                 v = _floats(self.attr(ch, "value"))
                 if len(v) not in (1, 3):
                     raise ValueError(f"<{ch.tag}> '{n}': only constant / RGB values are in scope")
                 out[n] = tuple(v * 3) if len(v) == 1 else tuple(v)
             elif ch.tag in ("point", "vector"):
                 out[n] = self.vec(ch)
+            elif ch.tag in _STRUCTURAL and not (ch.tag == "ref" and n is not None):
+                continue   # child objects: the caller handles them (or refuses them)
+            else:
+                # a <texture>, a named <ref> (a texture / spectrum bound to a property) or any tag this subset does not
+                # know: the value would silently fall back to the plugin's default (0.5 reflectance, unit radiance ...)
+                raise ValueError(f"<{ch.tag}{' name=' + repr(n) if n else ''}> inside <{node.tag}"
+                                 f"{' type=' + repr(node.get('type')) if node.get('type') else ''}> is outside the supported "
+                                 "subset: only constant float / integer / boolean / string / rgb / spectrum / point / vector "
+                                 "properties are read (textures and spatially varying values are not in scope)")
         return out
 
     def vec(self, node, default=0.0):
@@ -276,6 +292,8 @@ class _Loader:
             raise ValueError("only the 'perspective' sensor is in the hot-path scope")
         p = self.props(node)
         s = PerspectiveSensor()
+        # a sensor without a <sampler> gets the reference's default: `independent`, 4 spp (src/render/sensor.cpp:47-48)
+        s.sampler = CorrelatedSampler(4, 0, 1, 1, kind="independent")
         for ch in node:
             if ch.tag == "transform" and ch.get("name") == "to_world":
                 s.to_world = self.transform(ch)

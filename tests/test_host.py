@@ -279,6 +279,34 @@ def test_film_options_that_would_change_the_image_are_refused():
             assert r.returncode == 1 and word in r.stderr
 
 
+def test_textured_and_unknown_property_values_are_refused_not_defaulted():
+    """A <texture>, a named <ref> or a <spectrum filename=...> bound to a BSDF / emitter property is outside the subset.
+    Silently dropping it would render with the plugin's default (0.5 reflectance, src/bsdfs/diffuse.cpp:83): both hosts
+    refuse instead."""
+    import subprocess
+    import tempfile
+    base = open(os.path.join(gu.SCENES, "c1_example.xml")).read()
+    i = base.index('<bsdf type="diffuse"')
+    j = base.index('>', i) + 1
+    k = base.index('</bsdf>', j)
+    variants = {
+        "texture": base[:j] + '<texture name="reflectance" type="checkerboard"/>' + base[k:],
+        "ref": base[:j] + '<ref name="reflectance" id="some_texture"/>' + base[k:],
+        "spectrum": base[:j] + '<spectrum name="reflectance" filename="x.spd"/>' + base[k:],
+        "unknown": base[:j] + '<volume name="reflectance" type="constvolume"/>' + base[k:],
+    }
+    cli = os.path.join(ROOT, "host", "dtof_render")
+    assert subprocess.run(["make", "-C", os.path.join(ROOT, "host")], capture_output=True).returncode == 0
+    with tempfile.TemporaryDirectory() as tmp:
+        for what, xml in variants.items():
+            with pytest.raises(ValueError, match="outside the supported subset"):
+                dt.load_string(xml, gu.SCENES)
+            path = os.path.join(tmp, "s.xml")
+            open(path, "w").write(xml)
+            r = subprocess.run([cli, "--dump-desc", os.path.join(tmp, "d.bin"), path], capture_output=True, text=True)
+            assert r.returncode == 1 and "outside the supported subset" in r.stderr, (what, r.stderr)
+
+
 def _independent_xml():
     base = open(os.path.join(gu.SCENES, "c1_example.xml")).read()
     i = base.index('<sampler type="correlated">')
@@ -308,3 +336,30 @@ def test_dopplertofpath_with_the_independent_sampler_is_the_uniform_uncorrelated
         open(path, "w").write(_independent_xml())
         r = subprocess.run([cli, "--dump-desc", os.path.join(tmp, "d.bin"), path], capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
+
+
+def test_a_sensor_without_a_sampler_gets_the_reference_default():
+    """src/render/sensor.cpp:47-48: no <sampler> child -> `independent`, 4 spp. Under dopplertofpath that is the uniform,
+    uncorrelated stream (previous test), not this repo's correlated default."""
+    import subprocess
+    import tempfile
+    base = open(os.path.join(gu.SCENES, "c1_example.xml")).read()
+    i = base.index('<sampler type="correlated">')
+    j = base.index('</sampler>', i) + len('</sampler>')
+    bare = base[:i] + base[j:]
+    no = dt.load_string(bare, gu.SCENES)
+    explicit = dt.load_string(_independent_xml(), gu.SCENES, spp=4)
+    assert no.sensor.sampler.kind == "independent" and no.sensor.sampler.sample_count == 4
+    assert bytes(no.integrator.params(no.sensor.sampler, seed=1)) == bytes(explicit.integrator.params(explicit.sensor.sampler, seed=1))
+    cli = os.path.join(ROOT, "host", "dtof_render")
+    assert subprocess.run(["make", "-C", os.path.join(ROOT, "host")], capture_output=True).returncode == 0
+    with tempfile.TemporaryDirectory() as tmp:
+        outs = []
+        for name, xml, extra in (("bare", bare, []), ("explicit", _independent_xml(), ["-Dspp=4"])):
+            path = os.path.join(tmp, name + ".xml")
+            open(path, "w").write(xml)
+            out = os.path.join(tmp, name + ".bin")
+            r = subprocess.run([cli] + extra + ["--dump-desc", out, path], capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr
+            outs.append(open(out, "rb").read())
+        assert outs[0] == outs[1]

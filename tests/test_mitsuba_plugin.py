@@ -338,7 +338,7 @@ def test_dropin_plugin_on_all_gpus_equals_one_gpu(tmp_path):
     imgs = []
     for devs in ("0", "all"):
         out = os.path.join(str(tmp_path), f"scene_{devs}.exr")
-        r = _run_dropin(["-Dspp=256", "-o", out, scene], env_extra={"DTOF_DEVICES": devs})
+        r = _run_dropin(["-o", out, scene], env_extra={"DTOF_DEVICES": devs})    # the file is untouched: no -D parameters
         log = r.stdout + r.stderr
         assert r.returncode == 0, log[-2000:]
         assert f"on {torch.cuda.device_count() if devs == 'all' else 1} device(s)" in log
