@@ -7,6 +7,7 @@
 // BVH, huge ones through L1/L2 with 128-bit loads. Film accumulation is warp-aggregated (36 atomics per warp
 // instead of 36 per lane).
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges cost nothing unless a profiler (nsys / ncu --nvtx) is attached
 
 #include <chrono>
 #include <cmath>
@@ -29,12 +30,28 @@ using namespace dtof;
 
 namespace {
 
-constexpr int kBlock = 256;
+// NVTX range per stage (the reference marks its stages with ScopedPhase, include/mitsuba/core/profiler.h:20-49): host-side
+// push / pop around the enqueueing calls, which is what nsys needs to attribute the kernels of a stage to it.
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
+
+// CTA shape of the fused kernel: ONE CTA of 1024 threads per SM (64 registers / thread = the whole register file). Measured
+// against 4 x 256 and 2 x 512 at the same occupancy (profiles/r02_tuning.md): +3.2 .. +4.7 % on C1-C3 -- the scene is staged
+// once per SM instead of four times and the 32 warps of an SM share one set of shared-memory structures.
+#ifndef DTOF_BLOCK
+#define DTOF_BLOCK 1024
+#endif
+constexpr int kBlock = DTOF_BLOCK;
 #ifndef DTOF_MIN_CTAS
-#define DTOF_MIN_CTAS 4
+#define DTOF_MIN_CTAS 1
 #endif
 constexpr unsigned long long kUnit = 256;       // lanes per work unit fetched by one warp (8 warp iterations)
-constexpr size_t kSmemSceneLimit = 96 * 1024;   // traversal data up to this size is staged in shared memory
+// traversal data + traversal stacks of one CTA up to this size are staged in shared memory (227 KB opt-in per SM)
+constexpr size_t kSmemSceneLimit = (DTOF_MIN_CTAS == 1 ? 200 : 96) * 1024;
 constexpr uint32_t kFlatMaxTris = 0;            // flat coherent walk: never automatic (DTOF_MODE=2 only), see r01_tuning.md
 
 struct RenderArgs {
@@ -635,20 +652,27 @@ dtof_status launch_wavefront(dtof_ctx *ctx, const RenderArgs &A, int mode, cudaS
             W.pass = pass;
             W.bounce = 0;
             CU(cudaMemsetAsync(W.buf.ring, 0, kWfRing * 4 * sizeof(uint32_t), st));
+            {
+            NvtxRange r_gen("dtof.wf_generate");
             if (doppler)
                 wf_generate_kernel<DTOF_INTEGRATOR_DOPPLERTOFPATH><<<stream_grid, kWfBlock, 0, st>>>(W);
             else
                 wf_generate_kernel<DTOF_INTEGRATOR_PATH><<<stream_grid, kWfBlock, 0, st>>>(W);
+            }
             ctx->launches++;
             CU(cudaGetLastError());
             for (uint32_t b = 0; !bounded || b < (uint32_t) A.p.max_depth; ++b) {
                 W.bounce = b;
                 if (b + 1 >= (uint32_t) kWfRing)   // recycle the ring slot the next bounce will count into
                     CU(cudaMemsetAsync(W.buf.ring + 4 * ((b + 1) % kWfRing), 0, 4 * sizeof(uint32_t), st));
-                s = mode == MODE_BVH_SMEM ? launch_wf_trace<MODE_BVH_SMEM, false>(ctx, W, trace_grid, smem, st)
-                                          : launch_wf_trace<MODE_BVH_GLOBAL, false>(ctx, W, trace_grid, 0, st);
+                {
+                    NvtxRange r_tc("dtof.wf_trace_closest");
+                    s = mode == MODE_BVH_SMEM ? launch_wf_trace<MODE_BVH_SMEM, false>(ctx, W, trace_grid, smem, st)
+                                              : launch_wf_trace<MODE_BVH_GLOBAL, false>(ctx, W, trace_grid, 0, st);
+                }
                 if (s != DTOF_OK)
                     return s;
+                nvtxRangePushA("dtof.wf_shade");
                 // ENV: environment emitter / non-diffuse BSDFs compiled in only for the scenes that use them
                 if (A.scene.extended) {
                     if (doppler)
@@ -661,10 +685,14 @@ dtof_status launch_wavefront(dtof_ctx *ctx, const RenderArgs &A, int mode, cudaS
                     else
                         wf_shade_kernel<false, false><<<shade_grid, kWfShadeBlock, 0, st>>>(W);
                 }
+                nvtxRangePop();
                 ctx->launches++;
                 CU(cudaGetLastError());
-                s = mode == MODE_BVH_SMEM ? launch_wf_trace<MODE_BVH_SMEM, true>(ctx, W, trace_grid, smem, st)
-                                          : launch_wf_trace<MODE_BVH_GLOBAL, true>(ctx, W, trace_grid, 0, st);
+                {
+                    NvtxRange r_ts("dtof.wf_trace_shadow");
+                    s = mode == MODE_BVH_SMEM ? launch_wf_trace<MODE_BVH_SMEM, true>(ctx, W, trace_grid, smem, st)
+                                              : launch_wf_trace<MODE_BVH_GLOBAL, true>(ctx, W, trace_grid, 0, st);
+                }
                 if (s != DTOF_OK)
                     return s;
                 // bounded depth: every bounce is enqueued blind (an empty queue costs one idle launch). Unbounded or
@@ -677,7 +705,10 @@ dtof_status launch_wavefront(dtof_ctx *ctx, const RenderArgs &A, int mode, cudaS
                         break;
                 }
             }
-            wf_splat_kernel<<<stream_grid, kWfBlock, 0, st>>>(W);
+            {
+                NvtxRange r_sp("dtof.wf_splat");
+                wf_splat_kernel<<<stream_grid, kWfBlock, 0, st>>>(W);
+            }
             ctx->launches++;
             CU(cudaGetLastError());
         }
@@ -691,6 +722,7 @@ dtof_status launch_wavefront(dtof_ctx *ctx, const RenderArgs &A, int mode, cudaS
 
 dtof_status launch_render(dtof_ctx *ctx, const dtof_params *p, float *d_rgbw, cudaStream_t stream,
                           const unsigned long long *d_lanes, dtof_sample_record *d_rec, uint32_t n_rec, uint32_t rec_pass = 0) {
+    NvtxRange r_render(d_rec ? "dtof.trace_samples" : "dtof.render");
     dtof_pass_info pi;
     int rc = pass_info(ctx->film, *p, &pi);
     if (rc)
@@ -820,6 +852,7 @@ dtof_status launch_render(dtof_ctx *ctx, const dtof_params *p, float *d_rgbw, cu
 // dst (on device 0, `n_floats` floats) += the same buffer of every peer, after the peer has signalled ev_done. Peers the
 // device can address are read in place over NVLink; the others are copied into a staging buffer first.
 dtof_status reduce_from_peers(dtof_ctx *ctx, float *dst, size_t n_floats, bool image, cudaStream_t stream) {
+    NvtxRange r_reduce("dtof.film_reduce_peers");
     CU(cudaSetDevice(ctx->device));
     PeerPtrs src{};
     size_t n_staged = 0;
@@ -1411,10 +1444,16 @@ static dtof_status upload_prepared(dtof_ctx *ctx, const dtof_scene_desc *sc, Hos
 dtof_status dtof_upload_scene(dtof_ctx *ctx, const dtof_scene_desc *sc) {
     if (!ctx || !sc)
         return DTOF_ERR_INVALID;
+    NvtxRange r_upload("dtof.upload_scene");
     HostScene H;   // flattened + BVH built ONCE, then copied to every device of the context
-    dtof_status s = prepare_scene(ctx, sc, H);
+    dtof_status s;
+    {
+        NvtxRange r_bvh("dtof.bvh_build");
+        s = prepare_scene(ctx, sc, H);
+    }
     if (s != DTOF_OK)
         return s;
+    NvtxRange r_h2d("dtof.scene_h2d");
     if ((s = upload_prepared(ctx, sc, H)) != DTOF_OK)
         return s;
     for (dtof_ctx *p : ctx->peers)

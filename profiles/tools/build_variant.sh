@@ -7,5 +7,5 @@ name=$1; shift
 mkdir -p exp_build
 cd mitsuba3dopplertof_b200/csrc
 /usr/local/cuda/bin/nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -Xcompiler -fPIC,-O2,-Wall -Xptxas -v \
-  "$@" -shared dtof_api.cu dtof_bvh.cpp -o ../../exp_build/$name.so -lcudart 2> ../../exp_build/$name.ptxas.txt
+  "$@" -shared dtof_api.cu dtof_bvh.cpp -o ../../exp_build/$name.so -lcudart -ldl 2> ../../exp_build/$name.ptxas.txt
 grep -A2 "render_kernelILi1ELb0ELb0ELi0ELb0" ../../exp_build/$name.ptxas.txt | tail -2
