@@ -42,10 +42,7 @@ struct NvtxRange {
 // CTA shape of the fused kernel: ONE CTA of 1024 threads per SM (64 registers / thread = the whole register file). Measured
 // against 4 x 256 and 2 x 512 at the same occupancy (profiles/r02_tuning.md): +3.2 .. +4.7 % on C1-C3 -- the scene is staged
 // once per SM instead of four times and the 32 warps of an SM share one set of shared-memory structures.
-#ifndef DTOF_BLOCK
-#define DTOF_BLOCK 1024
-#endif
-constexpr int kBlock = DTOF_BLOCK;
+constexpr int kBlock = DTOF_BLOCK;   // dtof_device.cuh (1024 unless an A/B build overrides it)
 #ifndef DTOF_MIN_CTAS
 #define DTOF_MIN_CTAS 1
 #endif

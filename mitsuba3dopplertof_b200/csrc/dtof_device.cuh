@@ -29,6 +29,10 @@ namespace dtof {
 
 constexpr int kStackSize = 96;
 constexpr int kSentinel = (int) 0x80000000;
+// CTA size of the fused kernel (dtof_api.cu explains the choice); device code needs it for per-thread shared-memory layouts
+#ifndef DTOF_BLOCK
+#define DTOF_BLOCK 1024
+#endif
 constexpr unsigned kFullMask = 0xffffffffu;
 
 // ------------------------------------------------------------------------------------------------
