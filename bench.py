@@ -383,6 +383,8 @@ def bench_workload(name, args, steps, warmup, scaling, world, rank, local, dist,
              "unit": "Glane-instr/s", "frac": instr_per_sample * rate / issue_peak,
              "executed_thread_instr_per_sample": cnt.get("thread_inst_per_sample") if cnt else None,
              "executed_frac": cnt["thread_inst_per_sample"] * rate / issue_peak if cnt and cnt.get("thread_inst_per_sample") else None,
+             # warp-instructions ncu counted x the live sample rate / (148 x 4 issue slots x clock): how full the schedulers are
+             "warp_issue_slot_frac": cnt["warp_inst_per_sample"] * rate / (issue_peak / 32) if cnt and cnt.get("warp_inst_per_sample") else None,
              "ncu_active_lanes_per_inst": cnt.get("lanes_per_inst") if cnt else None,
              "ncu_issue_active_pct": cnt.get("issue_active_pct") if cnt else None,
              "peak_source": "148 SMs x 4 SMSPs x 32 lanes x SM clock sampled under load"}
@@ -409,8 +411,11 @@ def bench_workload(name, args, steps, warmup, scaling, world, rank, local, dist,
             "only the formal byte rate; the kernel is bound by instruction issue (`frac` = algorithmic lane-instructions of "
             "the DESIGN.md 4.1 model / peak issue rate, `issue.executed_frac` = thread-instructions ncu counted / peak)"
             if smem_resident else
-            "Nodes / triangles are read through L1 / L2 from HBM: `frac` = algorithmic traversal bytes / measured HBM peak, "
-            "`hbm.measured_dram_frac` = DRAM bytes ncu counted (incl. the pipeline's own queues and per-lane state) / peak")),
+            "Nodes / triangles are read through L1 / L2 from HBM: `frac` = algorithmic traversal bytes / measured HBM peak -- a "
+            "byte RATE most of which the caches serve (L1 80 %, L2 65 % hit rate); `hbm.measured_dram_frac` = DRAM bytes ncu "
+            "counted (incl. the pipeline's own queues and per-lane state) / peak, `issue.warp_issue_slot_frac` = how full the "
+            "warp schedulers are. Neither is near 1: the pipeline is bound by warp-instructions issued for few lanes in the leaf "
+            "phases of the walk (profiles/r02_tuning.md)")),
     }
 
     cpu = None

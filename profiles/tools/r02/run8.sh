@@ -3,7 +3,7 @@
 set -u
 cd "$GRAFT_REPO_ROOT"
 mkdir -p gpurun_out
-python -m pytest tests/test_rays.py -m gpu -q -rs -p no:cacheprovider > gpurun_out/r02_run8_pytest.log 2>&1
+python -m pytest tests -m gpu -q -rs -p no:cacheprovider > gpurun_out/r02_run8_pytest.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/r02_run8_pytest.log
 tail -5 gpurun_out/r02_run8_pytest.log
 python bench.py > gpurun_out/r02_bench_default_n1.json 2> gpurun_out/r02_bench_default_n1.err
