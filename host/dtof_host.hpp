@@ -93,6 +93,7 @@ struct Shape {
     bool flip_normals = false;
     std::vector<float> positions, normals, texcoords;   // Mesh payload (object space)
     std::vector<uint32_t> faces;
+    bool smooth_normals = false;   // the file had no normals: computed at flatten time, after to_world (mesh.cpp:283-345)
     bool animated() const { return has_anim && anim.size() > 1; }
 };
 
@@ -187,10 +188,14 @@ Scene load_file(const std::string &path, const std::map<std::string, std::string
 Scene load_string(const std::string &xml, const std::string &base_dir, const std::map<std::string, std::string> &params = {});
 
 // mesh files
+// `compute_missing = false` leaves `normals` empty when the file has none (the caller computes them after to_world)
 void load_mesh_file(const std::string &path, bool face_normals, std::vector<float> &pos, std::vector<uint32_t> &faces,
-                    std::vector<float> &normals, std::vector<float> &uvs);
+                    std::vector<float> &normals, std::vector<float> &uvs, bool compute_missing = true,
+                    bool flip_tex_coords = true);   // obj only (obj.cpp:151)
 void load_serialized_file(const std::string &path, int shape_index, bool face_normals, std::vector<float> &pos,
-                          std::vector<uint32_t> &faces, std::vector<float> &normals, std::vector<float> &uvs);
+                          std::vector<uint32_t> &faces, std::vector<float> &normals, std::vector<float> &uvs,
+                          bool compute_missing = true);
+void vertex_normals(const std::vector<float> &pos, const std::vector<uint32_t> &faces, std::vector<float> &out);
 
 // ---------------------------------------------------------------------------------------------- renderer
 // RAII wrapper of one dtof_ctx; errors become exceptions carrying dtof_last_error(). No CPU fallback.

@@ -183,7 +183,7 @@ void load_ply(const std::string &path, std::vector<float> &pos, std::vector<uint
 }
 
 void load_obj(const std::string &path, std::vector<float> &pos, std::vector<uint32_t> &faces, std::vector<float> &nrm,
-              std::vector<float> &uv) {
+              std::vector<float> &uv, bool flip_tex_coords) {
     std::ifstream f(path);
     if (!f)
         throw Error("\"" + path + "\": file does not exist!");
@@ -238,7 +238,8 @@ void load_obj(const std::string &path, std::vector<float> &pos, std::vector<uint
                         pos.push_back((float) v[(size_t) k[0] - 1][c]);
                     if (k[1]) {
                         uv.push_back((float) vt.at((size_t) k[1] - 1)[0]);
-                        uv.push_back((float) vt.at((size_t) k[1] - 1)[1]);   // obj.cpp keeps v as is (no flip)
+                        const float tv = (float) vt.at((size_t) k[1] - 1)[1];
+                        uv.push_back(flip_tex_coords ? 1.f - tv : tv);   // obj.cpp:151,266-267 (default true)
                     } else {
                         uv.push_back(0.f), uv.push_back(0.f);
                         all_uv = false;
@@ -261,6 +262,8 @@ void load_obj(const std::string &path, std::vector<float> &pos, std::vector<uint
     if (!all_n || pos.empty())
         nrm.clear();
 }
+
+} // namespace
 
 // Angle-weighted smooth normals (Thuermer & Wuethrich), as Mesh::recompute_vertex_normals; double accumulation
 // in the order k = 0, 1, 2 over all faces (the Python host's np.add.at order).
@@ -307,13 +310,15 @@ void vertex_normals(const std::vector<float> &pos, const std::vector<uint32_t> &
     }
 }
 
+namespace {
+
 } // namespace
 
 // One sub-mesh of a Mitsuba `.serialized` file (src/shapes/serialized.cpp:229-392): header 0x041C, version 3 / 4, one
 // zlib stream per sub-mesh, end-of-file offset dictionary; float or double payload narrowed to float, optional
 // normals / texture coordinates, vertex colours skipped, uint32 indices. Error texts are the reference's.
 void load_serialized_file(const std::string &path, int shape_index, bool face_normals, std::vector<float> &pos,
-                          std::vector<uint32_t> &faces, std::vector<float> &normals, std::vector<float> &uvs) {
+                          std::vector<uint32_t> &faces, std::vector<float> &normals, std::vector<float> &uvs, bool compute_missing) {
     auto fail = [&](const std::string &descr) -> void {
         throw Error("Error while loading serialized file \"" + path + "\": " + descr + "!");
     };
@@ -417,23 +422,23 @@ void load_serialized_file(const std::string &path, int shape_index, bool face_no
     for (uint32_t i : faces)
         if ((size_t) i >= pos.size() / 3)
             throw Error(path + ": face references a vertex out of range");
-    if (normals.empty() && !face_normals)
+    if (normals.empty() && !face_normals && compute_missing)
         vertex_normals(pos, faces, normals);
 }
 
 void load_mesh_file(const std::string &path, bool face_normals, std::vector<float> &pos, std::vector<uint32_t> &faces,
-                    std::vector<float> &normals, std::vector<float> &uvs) {
+                    std::vector<float> &normals, std::vector<float> &uvs, bool compute_missing, bool flip_tex_coords) {
     std::string lower = path;
     for (char &c : lower)
         c = (char) std::tolower((unsigned char) c);
     if (lower.size() >= 4 && lower.compare(lower.size() - 4, 4, ".ply") == 0)
         load_ply(path, pos, faces, normals, uvs);
     else
-        load_obj(path, pos, faces, normals, uvs);
+        load_obj(path, pos, faces, normals, uvs, flip_tex_coords);
     for (uint32_t i : faces)
         if ((size_t) i >= pos.size() / 3)
             throw Error(path + ": face references a vertex out of range");
-    if (normals.empty() && !face_normals)
+    if (normals.empty() && !face_normals && compute_missing)
         vertex_normals(pos, faces, normals);
 }
 

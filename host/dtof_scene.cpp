@@ -590,6 +590,11 @@ FlatMesh flatten_shape(const Shape &sh, const Transform4 &trafo) {
             }
         }
     }
+    if (sh.smooth_normals && !fm.has_normals) {
+        // Mesh::recompute_vertex_normals (src/render/mesh.cpp:283-345) runs after the loader applied to_world
+        vertex_normals(fm.buf.positions, fm.buf.faces, fm.buf.normals);
+        fm.has_normals = true;
+    }
     return fm;
 }
 
@@ -1167,12 +1172,18 @@ struct Loader {
                     shape_index = (int) parse_int(p["shape_index"].value);
                     p.erase("shape_index");
                 }
-                load_serialized_file(path, shape_index, face_normals, sh.positions, sh.faces, sh.normals, sh.texcoords);
+                load_serialized_file(path, shape_index, face_normals, sh.positions, sh.faces, sh.normals, sh.texcoords, false);
             } else {
-                load_mesh_file(path, face_normals, sh.positions, sh.faces, sh.normals, sh.texcoords);
+                bool flip_uv = true;   // obj.cpp:151 (ply.cpp has no such property)
+                if (typ == "obj" && p.count("flip_tex_coords")) {
+                    flip_uv = parse_bool(p["flip_tex_coords"].value);
+                    p.erase("flip_tex_coords");
+                }
+                load_mesh_file(path, face_normals, sh.positions, sh.faces, sh.normals, sh.texcoords, false, flip_uv);
             }
             if (face_normals)
                 sh.normals.clear();
+            sh.smooth_normals = sh.normals.empty() && !face_normals;   // computed at flatten time, after to_world
         }
         if (!p.empty())
             throw Error("shape '" + typ + "': unreferenced property \"" + p.begin()->first + "\"");

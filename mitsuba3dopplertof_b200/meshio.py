@@ -113,7 +113,8 @@ def load_ply(path: str):
     return pos, np.asarray(faces, np.uint32).reshape(-1, 3), nrm, uv
 
 
-def load_obj(path: str):
+def load_obj(path: str, flip_tex_coords: bool = True):
+    """`flip_tex_coords` (default true, obj.cpp:151,266-267): v = 1 - v in single precision."""
     v, vt, vn, keys, faces = [], [], [], {}, []
     out_p, out_t, out_n = [], [], []
     with open(path, "r") as f:
@@ -124,7 +125,8 @@ def load_obj(path: str):
             if tok[0] == "v":
                 v.append([float(x) for x in tok[1:4]])
             elif tok[0] == "vt":
-                vt.append([float(tok[1]), float(tok[2])])   # obj.cpp keeps v as is (no flip)
+                tv = np.float32(tok[2])
+                vt.append([float(tok[1]), float(np.float32(1.0) - tv if flip_tex_coords else tv)])
             elif tok[0] == "vn":
                 vn.append([float(x) for x in tok[1:4]])
             elif tok[0] == "f":
@@ -239,14 +241,18 @@ def write_serialized(path: str, meshes: Sequence[dict], version: int = 4, double
         f.write(blob)
 
 
-def load_mesh(path: str, face_normals: bool = False, shape_index: int = 0) -> Tuple[np.ndarray, np.ndarray, Optional[np.ndarray], Optional[np.ndarray]]:
+def load_mesh(path: str, face_normals: bool = False, shape_index: int = 0,
+              compute_missing: bool = True, flip_tex_coords: bool = True) -> Tuple[np.ndarray, np.ndarray, Optional[np.ndarray], Optional[np.ndarray]]:
+    """`compute_missing=False` leaves the normals None when the file has none, so that the caller can run
+    recompute_vertex_normals where the reference runs it: on the positions AFTER to_world (obj.cpp:237,401-403,
+    ply.cpp:288,435-437) -- angle weights are not preserved under non-uniform scale or shear."""
     low = path.lower()
     if low.endswith(".serialized"):
         pos, faces, nrm, uv = load_serialized(path, shape_index)
         if face_normals:
             nrm = None                            # serialized.cpp:341-346: normals in the file are skipped
     else:
-        pos, faces, nrm, uv = load_ply(path) if low.endswith(".ply") else load_obj(path)
-    if nrm is None and not face_normals:
+        pos, faces, nrm, uv = load_ply(path) if low.endswith(".ply") else load_obj(path, flip_tex_coords)
+    if nrm is None and not face_normals and compute_missing:
         nrm = vertex_normals(pos, faces)
     return pos, faces, nrm, uv

@@ -59,6 +59,9 @@ class Shape:
     texcoords: Optional[np.ndarray] = None
     faces: Optional[np.ndarray] = None
     id: str = ""
+    # the mesh file had no normals and face_normals is false: smooth vertex normals are computed when the shape is
+    # flattened, on the positions in the space the reference computes them in (world space for a static shape)
+    smooth_normals: bool = False
 
     @property
     def animated(self) -> bool:
@@ -278,7 +281,11 @@ def _flatten_shape(sh: Shape, trafo: Transform4) -> _FlatMesh:
         ident = np.array_equal(t32.matrix, np.eye(4, dtype=f32))
         pos = sh.positions.astype(f32) if ident else np.stack([t32.transform_affine_point(v) for v in sh.positions])
         nrm = None
-        if sh.normals is not None:
+        if sh.smooth_normals and sh.normals is None:
+            # Mesh::recompute_vertex_normals (src/render/mesh.cpp:283-345) runs after the loader applied to_world
+            from .meshio import vertex_normals
+            nrm = vertex_normals(np.ascontiguousarray(pos, f32), np.ascontiguousarray(sh.faces, np.uint32))
+        elif sh.normals is not None:
             nrm = sh.normals.astype(f32) if ident else _normalize_rows(
                 np.stack([t32.transform_normal(n) for n in sh.normals]))
         uv = None if sh.texcoords is None else sh.texcoords.astype(f32)

@@ -273,14 +273,14 @@ class _Loader:
             face_normals = bool(p.pop("face_normals", False))
             if typ == "serialized":   # the plugin, not the file extension, selects the loader (serialized.cpp:229-248)
                 pos, faces, nrm, uv = load_serialized(os.path.join(self.base_dir, fn), int(p.pop("shape_index", 0)))
-                if nrm is None and not face_normals:
-                    from .meshio import vertex_normals
-                    nrm = vertex_normals(pos, faces)
             else:
-                pos, faces, nrm, uv = load_mesh(os.path.join(self.base_dir, fn), face_normals=face_normals)
+                flip_uv = bool(p.pop("flip_tex_coords", True)) if typ == "obj" else True   # obj.cpp:151 (ply.cpp has no such property)
+                pos, faces, nrm, uv = load_mesh(os.path.join(self.base_dir, fn), face_normals=face_normals, compute_missing=False,
+                                                flip_tex_coords=flip_uv)
             if face_normals:
                 nrm = None
             sh.positions, sh.faces, sh.normals, sh.texcoords = pos, faces, nrm, uv
+            sh.smooth_normals = nrm is None and not face_normals   # computed at flatten time, after to_world
         elif typ not in ("rectangle", "cube"):
             raise ValueError(f"shape type '{typ}' is outside the hot-path scope (rectangle|cube|obj|ply|serialized)")
         if p:

@@ -130,3 +130,45 @@ def test_cli_render_matches_python_path(cli, tmp_path):
     assert got.shape == want.shape == (48, 64, 4)
     # same inputs, same kernel: only the order of the float atomics differs
     assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
+
+
+def test_missing_vertex_normals_are_computed_after_to_world(cli, tmp_path):
+    """A static obj / ply / serialized mesh without normals: the reference's loaders apply to_world to the positions and then
+    run Mesh::recompute_vertex_normals on the WORLD-space vertices (obj.cpp:237,401-403, ply.cpp:288,435-437). Angle weights
+    change under non-uniform scale, so transforming object-space normals is not the same. Both hosts, byte for byte."""
+    from mitsuba3dopplertof_b200.meshio import vertex_normals
+    base = open(os.path.join(gu.SCENES, "c5_slabroom.xml")).read()
+    old = '<boolean name="face_normals" value="true" />'
+    assert old in base
+    xml = base.replace(old, "").replace('<scale value="0.22" />', '<scale x="0.4" y="0.1" z="0.22" />')
+    for f in ("gem.ply",):
+        os.symlink(os.path.join(gu.SCENES, f), str(tmp_path / f))
+    path = str(tmp_path / "smooth.xml")
+    open(path, "w").write(xml)
+    scene = dt.load_file(path)
+    flat = scene.flatten()
+    gem = [i for i, sh in enumerate(scene.shapes) if sh.id == "Gem"]
+    assert gem and scene.shapes[gem[0]].smooth_normals
+    # the flattened mesh that has 6 vertices and 8 faces is the gem
+    k = [i for i in range(flat.desc.n_meshes) if flat.meshes[i].n_vertices == 6 and flat.meshes[i].n_faces == 8]
+    assert len(k) == 1
+    m = flat.meshes[k[0]]
+    pos = np.ctypeslib.as_array(m.positions, (18,)).reshape(6, 3).copy()
+    nrm = np.ctypeslib.as_array(m.normals, (18,)).reshape(6, 3).copy()
+    faces = np.ctypeslib.as_array(m.faces, (24,)).reshape(8, 3).copy()
+    np.testing.assert_array_equal(nrm, vertex_normals(pos, faces))              # computed on the world-space positions
+    sh = scene.shapes[gem[0]]
+    obj_n = vertex_normals(sh.positions.astype(np.float32), sh.faces)
+    t32 = sh.to_world.astype(np.float32)
+    moved = np.stack([t32.transform_normal(n) for n in obj_n])
+    moved /= np.linalg.norm(moved, axis=1, keepdims=True)
+    assert np.abs(moved - nrm).max() > 1e-2                                     # ... which is not the transformed object-space result
+    dump = str(tmp_path / "desc.bin")
+    r = subprocess.run([cli, "--dump-desc", dump, path], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got, want = open(dump, "rb").read(), _serialize_python(flat)
+    assert len(got) == len(want)
+    a, b = np.frombuffer(got[10:len(got) // 4 * 4 + 2][: (len(got) - 10) // 4 * 4], np.uint8), np.frombuffer(want[10:][: (len(want) - 10) // 4 * 4], np.uint8)
+    fa, fb = a.view(np.float32), b.view(np.float32)
+    diff = np.nonzero(a.view(np.uint32) != b.view(np.uint32))[0]
+    assert len(diff) <= 8 and np.all(np.abs(fa[diff] - fb[diff]) <= 2e-7 * np.maximum(np.abs(fb[diff]), 1e-30) + 1e-15)

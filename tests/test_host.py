@@ -126,6 +126,9 @@ def test_mesh_loaders(tmp_path):
                    "f 1/1/1 2/2/1 3/3/1 4/4/1\n")
     pos, faces, nrm, uv = load_mesh(str(obj))
     assert faces.tolist() == [[0, 1, 2], [0, 2, 3]] and uv.shape == (4, 2) and nrm.shape == (4, 3)
+    # flip_tex_coords defaults to true in the reference's obj loader (obj.cpp:151,266-267): v -> 1 - v
+    assert uv.tolist() == [[0, 1], [1, 1], [1, 0], [0, 0]]
+    assert load_mesh(str(obj), flip_tex_coords=False)[3].tolist() == [[0, 0], [1, 0], [1, 1], [0, 1]]
 
 
 # ---- `.serialized` meshes (src/shapes/serialized.cpp) -----------------------------------------------------------------
