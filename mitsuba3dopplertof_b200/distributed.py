@@ -64,10 +64,8 @@ def render_distributed(scene, seed: int = 0, spp: int = 0, mode: str = "slots", 
     if render_fn is None:
         from .runtime import get_context
         ctx = get_context()
-        cached = getattr(scene, "_dtof_uploaded", None)
-        if cached is None or cached[0] is not ctx or ctx._flat is not cached[1]:
-            scene._dtof_uploaded = (ctx, ctx.upload(scene))
-        flat = scene._dtof_uploaded[1]
+        from .integrator import _uploaded
+        flat = _uploaded(ctx, scene)   # uploaded again when the scene changed (Scene.fingerprint)
         pi = ctx.pass_info(base)
 
         def render_fn(flat_, p_):   # noqa: ANN001

@@ -150,10 +150,7 @@ class DopplerToFPathIntegrator:
         from .runtime import get_context   # deferred: importing the package must not need a GPU
         self._stop = False
         ctx = get_context(device)
-        cached = getattr(scene, "_dtof_uploaded", None)
-        if cached is None or cached[0] is not ctx or ctx._flat is not cached[1]:
-            scene._dtof_uploaded = (ctx, ctx.upload(scene))   # flatten + BVH build + H2D once per scene
-        flat = scene._dtof_uploaded[1]
+        flat = _uploaded(ctx, scene)   # flatten + BVH build + H2D once per scene STATE (Scene.fingerprint)
         p = self.params(scene.sensor.sampler, seed, spp)
         return ctx.render(flat, p, develop=develop)
 
@@ -163,15 +160,22 @@ class DopplerToFPathIntegrator:
         the scene stays on the GPU and the mean is formed there."""
         from .runtime import get_context
         ctx = get_context(device)
-        cached = getattr(scene, "_dtof_uploaded", None)
-        if cached is None or cached[0] is not ctx or ctx._flat is not cached[1]:
-            scene._dtof_uploaded = (ctx, ctx.upload(scene))
-        flat = scene._dtof_uploaded[1]
+        flat = _uploaded(ctx, scene)
         return ctx.render_multi_pass(flat, self.params(scene.sensor.sampler, seed, spp_per_pass), passes)
 
     def __repr__(self):
         return (f"DopplerToFPathIntegrator[\n  max_depth = {self.max_depth & 0xFFFFFFFF},\n"
                 f"  rr_depth = {self.rr_depth}\n]")
+
+
+def _uploaded(ctx, scene):
+    """The flattened scene resident on `ctx`, uploaded again when the scene changed since (shapes, transforms, materials,
+    emitters, the sensor, its film or sampler: Scene.fingerprint) or another scene took the context over."""
+    key = scene.fingerprint()
+    cached = getattr(scene, "_dtof_uploaded", None)
+    if cached is None or cached[0] is not ctx or ctx._flat is not cached[1] or cached[2] != key:
+        scene._dtof_uploaded = (ctx, ctx.upload(scene), key)
+    return scene._dtof_uploaded[1]
 
 
 class VelocityIntegrator(DopplerToFPathIntegrator):

@@ -334,6 +334,57 @@ class Scene:
     sensor: PerspectiveSensor = field(default_factory=PerspectiveSensor)
     integrator: object = None   # DopplerToFPathIntegrator (integrator.py)
 
+    def fingerprint(self) -> bytes:
+        """Digest of everything flatten() reads (shapes, transforms, BSDFs, emitters, sensor, film, sampler): the key of the
+        upload cache in integrator.render / render_distributed, so that an edited scene (a moved shape, another film size,
+        another sensor) is flattened and uploaded again instead of silently rendering the stale copy. Arrays above 1 MiB are
+        identified by buffer address, shape and their first / last elements instead of being hashed."""
+        import dataclasses
+        import hashlib
+        h = hashlib.blake2b(digest_size=16)
+        seen = set()
+
+        def walk(x):
+            if isinstance(x, np.ndarray):
+                h.update(repr((x.shape, str(x.dtype))).encode())
+                if x.nbytes <= (1 << 20):
+                    h.update(np.ascontiguousarray(x).tobytes())
+                elif x.size:
+                    flat = x.reshape(-1)
+                    h.update(repr((x.__array_interface__["data"][0], flat[0].item(), flat[-1].item())).encode())
+            elif dataclasses.is_dataclass(x) and not isinstance(x, type):
+                if id(x) in seen:
+                    return
+                seen.add(id(x))
+                h.update(type(x).__name__.encode())
+                for f in dataclasses.fields(x):
+                    h.update(f.name.encode())
+                    walk(getattr(x, f.name))
+            elif isinstance(x, (list, tuple)):
+                h.update(b"[")
+                for y in x:
+                    walk(y)
+                h.update(b"]")
+            elif isinstance(x, dict):
+                for k in sorted(x):
+                    h.update(repr(k).encode())
+                    walk(x[k])
+            elif hasattr(x, "matrix") and isinstance(getattr(x, "matrix"), np.ndarray):     # Transform4
+                walk(x.matrix)
+            elif hasattr(x, "times") and hasattr(x, "transforms"):                         # AnimatedTransform
+                walk(list(x.times))
+                walk(list(x.transforms))
+            elif hasattr(x, "__dict__") and not callable(x):
+                h.update(type(x).__name__.encode())
+                walk({k: v for k, v in vars(x).items() if not k.startswith("_")})
+            else:
+                h.update(repr(x).encode())
+
+        walk(self.shapes)
+        walk(self.emitters)
+        walk(self.sensor)
+        return h.digest()
+
     def flatten(self) -> FlatScene:
         bsdfs: List[_abi.Bsdf] = []
         bsdf_index = {}

@@ -96,6 +96,11 @@ def update_motion(ctx: runtime.Context, scene, flat, motions) -> None:
                              (C.c_float * 12)(*m0.tolist()), (C.c_float * 12)(*m1.tolist()))
         flat.instances[inst_index] = inst
         ctx.update_instances(inst_index, [inst])
+    # the resident copy now matches the edited scene: keep integrator.render()'s upload cache (keyed on
+    # Scene.fingerprint) from re-uploading what was just updated in place
+    cached = getattr(scene, "_dtof_uploaded", None)
+    if cached is not None and cached[0] is ctx and cached[1] is flat:
+        scene._dtof_uploaded = (ctx, flat, scene.fingerprint())
 
 
 # ---- drivers (program_runner.py) ---------------------------------------------------------------------------------

@@ -366,3 +366,32 @@ def test_a_sensor_without_a_sampler_gets_the_reference_default():
             assert r.returncode == 0, r.stderr
             outs.append(open(out, "rb").read())
         assert outs[0] == outs[1]
+
+
+def test_upload_cache_follows_scene_edits():
+    """integrator.render() caches the upload per scene STATE: editing a shape, a material, the film or the sensor changes
+    Scene.fingerprint(), so the stale resident copy is not rendered again (no GPU needed: a recording context stands in)."""
+    from mitsuba3dopplertof_b200 import integrator as integ
+
+    class FakeCtx:
+        def __init__(self):
+            self.uploads, self._flat = 0, None
+        def upload(self, scene):
+            self.uploads += 1
+            self._flat = object()
+            return self._flat
+
+    scene = dt.load_file(os.path.join(gu.SCENES, "c1_example.xml"), resx=16, resy=16, spp=4)
+    ctx = FakeCtx()
+    a = integ._uploaded(ctx, scene)
+    assert integ._uploaded(ctx, scene) is a and ctx.uploads == 1            # unchanged scene: one upload
+    scene.sensor.film.width = 24
+    b = integ._uploaded(ctx, scene)
+    assert b is not a and ctx.uploads == 2                                   # another film size: uploaded again
+    scene.shapes[0].bsdf = dt.scene.Bsdf(reflectance=(0.2, 0.3, 0.4)) if hasattr(dt, "scene") else scene.shapes[0].bsdf
+    moved = [sh for sh in scene.shapes if sh.kind == "mesh" or sh.kind == "cube" or sh.kind == "rectangle"][0]
+    moved.flip_normals = not moved.flip_normals
+    assert integ._uploaded(ctx, scene) is not b and ctx.uploads == 3         # an edited shape: uploaded again
+    other = FakeCtx()
+    integ._uploaded(other, scene)
+    assert other.uploads == 1                                                # another context: its own upload
