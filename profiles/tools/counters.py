@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Writes profiles/r02_counters.json: per workload the counters ncu measured on the shipped library, per sample.
-Inputs (gpurun_out/, produced by profiles/tools/r02/run12.sh and run10.sh):
+Inputs (gpurun_out/, produced by profiles/tools/r02/run22.sh and run10.sh):
   r02_counters_<wl>.csv            one render_kernel launch of `bench.py --workload <wl> --spp 64` (fused kernel)
   r02_launches_c5_wavefront.csv    launch list of `bench.py --workload c5 --spp 64` (wavefront pipeline, every wf_* launch)
 bench.py reads the file for roofline.traffic / issue.executed_* (numbers measured under ncu are never bench values; these are
@@ -29,7 +29,7 @@ for wl in ("c1", "c2", "c3", "c4"):
     m = {n: v for _, k, n, v in rows(p)}
     n = PIX[wl] * SPP
     out[wl] = {
-        "source": f"ncu --metrics ... -k regex:render_kernel -s 3 -c 1 python bench.py --workload {wl} --spp 64 (profiles/tools/r02/run12.sh)",
+        "source": f"ncu --metrics ... -k regex:render_kernel -s 3 -c 1 python bench.py --workload {wl} --spp 64 (profiles/tools/r02/run22.sh)",
         "samples": n, "kernel_ms_under_ncu": m["gpu__time_duration.sum"] / 1e6,
         "bytes_per_sample": (m["dram__bytes_read.sum"] + m["dram__bytes_write.sum"]) / n,
         "dram_read_bytes_per_sample": m["dram__bytes_read.sum"] / n, "dram_write_bytes_per_sample": m["dram__bytes_write.sum"] / n,
