@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(kBlock) rays_kernel(const __grid_constant__ Re
     Counters st = {};
     Hit h;
     h.t = 0.f, h.u = 0.f, h.v = 0.f, h.gid = 0, h.inst = -1;
-    const bool hit = trace_any_mode<MODE, true>(A.scene, TP, any_hit != 0, v3(r.o[0], r.o[1], r.o[2]), v3(r.d[0], r.d[1], r.d[2]), r.tmax,
+    const bool hit = trace_any_mode<MODE, true, true>(A.scene, TP, any_hit != 0, v3(r.o[0], r.o[1], r.o[2]), v3(r.d[0], r.d[1], r.d[2]), r.tmax,
                                                 r.time, on, h, st);
     if (on) {
         dtof_ray_hit o{};

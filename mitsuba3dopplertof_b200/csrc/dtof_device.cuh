@@ -587,15 +587,32 @@ struct Hit {
 // builder, which rounds the half extents up and pads the boxes by 1e-5. (A form with one fma per plane, m * idir - o *
 // idir, carries an ABSOLUTE error of ulp(o * idir); bounding it per ray loosens every axis by the error of the axis the
 // ray is most parallel to -- a ray with a zero direction component then accepts every box of a 1.3 M-node BVH.)
-// An infinite idir (zero direction component) gives inf / NaN on that axis; fminf / fmaxf drop NaN operands, so the
-// axis is at worst not used for culling.
+// An infinite idir (zero direction component) gives inf / NaN on that axis; fminf / fmaxf drop NaN operands, so the axis is
+// at worst not used for culling -- unless the reciprocal direction is clamped (RaySlab::set<ROBUST> below).
 constexpr float kSlabWiden = 1.000003f;
+// A direction component that is exactly zero (or denormal: rcp.approx.ftz) has 1 / d = inf, and (m - o) * inf -/+ h * inf
+// is NaN on one side: the axis would drop out of the test and an axis-parallel ray would walk every node whose OTHER two
+// slabs it crosses. Clamping |1 / d| to 1e18 keeps the arithmetic finite: inside the slab (|m - o| <= h) the interval is
+// [-huge, +huge], outside it lies entirely beyond any finite t, which is exactly what the limit d -> 0 means. For a
+// component with |d| < 1e-18 the clamp rescales that axis' interval, whose ends are beyond 1e18 * (distance to the slab
+// planes) either way -- farther than anything the other axes or `best` can produce unless the ray starts within 1e-18 of
+// the plane, far below the boxes' 1e-5 padding.
+// The clamp is compiled in where rays come from a CALLER (`ROBUST`: dtof_trace_rays, where axis-parallel probe rays are the
+// common case); the render kernels' rays have continuous random directions, an exactly zero component has probability
+// ~2^-23 per ray and only costs that ray a longer walk, so they skip the three extra instructions per ray set-up (measured:
+// 1 % of the fused kernel).
+constexpr float kSlabMaxInvDir = 1e18f;
 struct RaySlab {
     V3 o, id, aid;
-    DTOF_DEV void set(V3 ro, V3 rid) {
+    template <bool ROBUST = false> DTOF_DEV void set(V3 ro, V3 rid) {
         o = ro;
-        id = rid;
-        aid = v3(fabsf(rid.x), fabsf(rid.y), fabsf(rid.z));
+        if (ROBUST) {
+            aid = v3(fminf(fabsf(rid.x), kSlabMaxInvDir), fminf(fabsf(rid.y), kSlabMaxInvDir), fminf(fabsf(rid.z), kSlabMaxInvDir));
+            id = v3(copysignf(aid.x, rid.x), copysignf(aid.y, rid.y), copysignf(aid.z, rid.z));
+        } else {
+            id = rid;
+            aid = v3(fabsf(rid.x), fabsf(rid.y), fabsf(rid.z));
+        }
     }
 };
 // n0 = child 0 {mx, hx, my, hy}, n1 = child 1 {mx, hx, my, hy}, n2 = {c0 mz, c0 hz, c1 mz, c1 hz}
@@ -679,7 +696,7 @@ constexpr int kDone = 0x7fffffff;
 // Loop shape after Aila & Laine: a lane stays in the inner-node loop (popping included) until it holds a leaf.
 // `N`, `T`, `I` are the node / triangle / instance arrays (global memory, or their shared-memory copies).
 // The box test is node_test() above.
-template <bool STATS>
+template <bool STATS, bool ROBUST = false>
 DTOF_DEV bool trace_bvh(const float4 *__restrict__ N, const float4 *__restrict__ T, const float4 *__restrict__ I,
                         int32_t root, const bool ANY, V3 o, V3 d, float tmax, float time, Hit &hit, Counters &st) {
     int stack[kStackSize];
@@ -688,7 +705,7 @@ DTOF_DEV bool trace_bvh(const float4 *__restrict__ N, const float4 *__restrict__
     int cur_inst = -1;
     V3 ro = o, rd = d;                                       // ray in the current (world / instance) space
     RaySlab R;
-    R.set(o, v3(frcp(d.x), frcp(d.y), frcp(d.z)));
+    R.template set<ROBUST>(o, v3(frcp(d.x), frcp(d.y), frcp(d.z)));
     float best = tmax;
     bool found = false;
     if (STATS) {
@@ -702,7 +719,7 @@ DTOF_DEV bool trace_bvh(const float4 *__restrict__ N, const float4 *__restrict__
             node = stack[--sp];                                                                            \
             if (node == kSentinel) { /* leave the instance: back to the world-space ray */                 \
                 ro = o, rd = d, cur_inst = -1;                                                             \
-                R.set(o, v3(frcp_here(d.x), frcp_here(d.y), frcp_here(d.z)));                              \
+                R.template set<ROBUST>(o, v3(frcp_here(d.x), frcp_here(d.y), frcp_here(d.z)));                              \
                 node = sp ? stack[--sp] : kDone;                                                           \
             }                                                                                              \
         }                                                                                                  \
@@ -738,7 +755,7 @@ DTOF_DEV bool trace_bvh(const float4 *__restrict__ N, const float4 *__restrict__
             const float4 *ip = I + 8 * (size_t) cur_inst;
             if (STATS) st.inst++;
             enter_instance(ip, o, d, time, ro, rd);
-            R.set(ro, v3(frcp(rd.x), frcp(rd.y), frcp(rd.z)));
+            R.template set<ROBUST>(ro, v3(frcp(rd.x), frcp(rd.y), frcp(rd.z)));
             stack[sp++] = kSentinel;
             node = __float_as_int(ip[6].z);
             continue;
@@ -802,7 +819,7 @@ DTOF_DEV uint32_t opaque_u32(uint32_t v) {
     return r;
 }
 
-template <bool STATS>
+template <bool STATS, bool ROBUST = false>
 DTOF_DEV bool trace_bvh_smem(const SmemScene M, int32_t root, const bool ANY, V3 o, V3 d, float tmax, float time, Hit &hit,
                              Counters &st) {
 #ifdef DTOF_LOCAL_STACK   // A/B builds only: the stack in (L1-resident) local memory, the shared-memory carve-out stays small
@@ -821,7 +838,7 @@ DTOF_DEV bool trace_bvh_smem(const SmemScene M, int32_t root, const bool ANY, V3
     int cur_inst = -1;
     V3 ro = o, rd = d;
     RaySlab R;
-    R.set(o, v3(frcp(d.x), frcp(d.y), frcp(d.z)));
+    R.template set<ROBUST>(o, v3(frcp(d.x), frcp(d.y), frcp(d.z)));
     float best = tmax;
     bool found = false;
     if (STATS) {
@@ -835,7 +852,7 @@ DTOF_DEV bool trace_bvh_smem(const SmemScene M, int32_t root, const bool ANY, V3
             node = DTOF_STK_POP();                                                                         \
             if (node == kSentinel) { /* leave the instance: back to the world-space ray */                 \
                 ro = o, rd = d, cur_inst = -1;                                                             \
-                R.set(o, v3(frcp_here(d.x), frcp_here(d.y), frcp_here(d.z)));                              \
+                R.template set<ROBUST>(o, v3(frcp_here(d.x), frcp_here(d.y), frcp_here(d.z)));                              \
                 node = DTOF_STK_EMPTY() ? kDone : DTOF_STK_POP();                                          \
             }                                                                                              \
         }                                                                                                  \
@@ -884,7 +901,7 @@ DTOF_DEV bool trace_bvh_smem(const SmemScene M, int32_t root, const bool ANY, V3
             const M34 inv = inverse_m34(Mx);
             ro = xf_point(inv, o);
             rd = xf_vector(inv, d);
-            R.set(ro, v3(frcp(rd.x), frcp(rd.y), frcp(rd.z)));
+            R.template set<ROBUST>(ro, v3(frcp(rd.x), frcp(rd.y), frcp(rd.z)));
             DTOF_STK_PUSH(kSentinel);
             node = __float_as_int(q6.z);
             continue;

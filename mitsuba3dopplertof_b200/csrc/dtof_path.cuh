@@ -28,7 +28,7 @@ struct TravPtrs {
     SmemScene S;        // BVH_SMEM mode: shared-window addresses of N / T / I and of this lane's traversal stack
 };
 
-template <int MODE, bool STATS>
+template <int MODE, bool STATS, bool ROBUST = false>   // ROBUST: caller-supplied rays (RaySlab::set)
 DTOF_DEV bool trace_any_mode(const DeviceScene &S, const TravPtrs &P, bool any, V3 o, V3 d, float tmax, float time,
                              bool lane_active, Hit &hit, Counters &st) {
     if (MODE == MODE_FLAT_SMEM)
@@ -37,9 +37,9 @@ DTOF_DEV bool trace_any_mode(const DeviceScene &S, const TravPtrs &P, bool any, 
         return false;
 #ifndef DTOF_OLD_SMEM_WALK   // A/B builds only: the round-1 walk (generic pointers, local-memory stack) on the staged copy
     if (MODE == MODE_BVH_SMEM)
-        return trace_bvh_smem<STATS>(P.S, S.root, any, o, d, tmax, time, hit, st);
+        return trace_bvh_smem<STATS, ROBUST>(P.S, S.root, any, o, d, tmax, time, hit, st);
 #endif
-    return trace_bvh<STATS>(P.N, P.T, P.I, S.root, any, o, d, tmax, time, hit, st);
+    return trace_bvh<STATS, ROBUST>(P.N, P.T, P.I, S.root, any, o, d, tmax, time, hit, st);
 }
 
 // VelocityIntegrator::sample (src/integrators/velocity.cpp:113-127): the camera ray is intersected at t = 0 and at

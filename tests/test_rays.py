@@ -113,13 +113,14 @@ def test_cuda_ray_queries_match_the_oracle(which):
     # turns the box test into "accept everything" walks the whole BVH (round 2 found exactly that in a draft of the box test)
     nodes = got["nodes_visited"].astype(np.float64)
     info = runtime.scene_info(flat)
-    # the tight bound holds for rays a renderer produces. Two kinds of test rays walk further, correctly but slowly: far
-    # origins (one ulp of t spans many small boxes) and EXACTLY axis-parallel rays (a zero / denormal direction component:
-    # 1 / d = inf, that axis cannot cull in the centre / half-extent form) -- for those only the absolute bound below
-    near_o = (np.abs(rays["o"]).max(axis=1) <= 100.0) & (np.abs(rays["d"]).min(axis=1) > 1e-37)
+    # the tight bound holds for every ray that starts near the scene, INCLUDING exactly axis-parallel ones (zero / denormal
+    # direction components: the reciprocal direction is clamped to +-1e18, so such an axis still culls). Only far origins walk
+    # further, correctly but slowly (one ulp of t spans many small boxes): for those the absolute bound below
+    near_o = np.abs(rays["o"]).max(axis=1) <= 100.0
     worst = int(np.argmax(np.where(near_o, nodes, 0)))
-    assert nodes[near_o].max() <= max(40 * np.median(nodes[nodes > 0]), 64), (
-        nodes[near_o].max(), np.median(nodes), info.n_nodes, worst, worst // (rays.size // 8), rays["o"][worst].tolist(),
+    typical = np.median(nodes[got["hit"] == 1])          # (most of the random rays miss the scene after one node)
+    assert nodes[near_o].max() <= max(40 * typical, 64), (
+        nodes[near_o].max(), typical, info.n_nodes, worst, worst // (rays.size // 8), rays["o"][worst].tolist(),
         rays["d"][worst].tolist(), float(rays["tmax"][worst]), int(got["hit"][worst]), float(got["t"][worst]))
     assert nodes.max() < 0.25 * info.n_nodes or info.n_nodes < 256
     gu.REPORT[f"cuda-rays:{which}"] = {"rays": int(rays.size), "hit_agreement": float(same_hit.mean()),
