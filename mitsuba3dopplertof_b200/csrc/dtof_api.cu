@@ -325,6 +325,7 @@ struct dtof_ctx {
     void *d_nodes = nullptr, *d_tris = nullptr, *d_shade = nullptr, *d_insts = nullptr, *d_meshes = nullptr,
          *d_bsdfs = nullptr, *d_emitters = nullptr, *d_spots = nullptr, *d_cdf = nullptr, *d_pmf = nullptr;
     std::vector<InstRec> h_insts;
+    std::vector<InstBox> h_boxes;    // padded world bounds per instance (host copy: ray binning of the wavefront pipeline)
     std::vector<TlasEntry> h_tlas;   // per instance: motion, object-space bounds, BLAS root (TLAS rebuild on keyframe updates)
     uint32_t tlas_begin = 0, n_tlas_nodes = 0;
     int blas_depth = 0;
@@ -550,7 +551,7 @@ dtof_status ensure_wavefront(dtof_ctx *ctx, size_t cap, int sets) {
                  o_ql0 = carve(4), o_ql1 = carve(4), o_hit = carve(16), o_hi = carve(4), o_so = carve(16), o_sd = carve(16),
                  o_st = carve(16), o_sc = carve(16), o_sl = carve(4), o_eta = carve(4);
     const size_t o_ring = off;
-    off += 256;
+    off += (kWfRing * kWfSlotWords * sizeof(uint32_t) + 255) / 256 * 256;
     for (int i = 0; i < sets; ++i) {
         if (cudaMalloc(&ctx->wf_block[i], off) != cudaSuccess) {
             ctx->wf_block[i] = nullptr;
@@ -592,7 +593,7 @@ dtof_status launch_wavefront(dtof_ctx *ctx, const RenderArgs &A, int mode, cudaS
     size_t batch = kWfDefaultBatch;
     if (const char *e = getenv("DTOF_WF_BATCH"))
         batch = std::max<size_t>(1024, (size_t) atoll(e));
-    uint32_t threshold = 24;
+    uint32_t threshold = 20;   // refill when 12 lanes are idle (re-swept in round 2: 16 / 20 / 24 / 28 -> 825 / 846 / 834 / 806, with binning 868 at 20)
     if (const char *e = getenv("DTOF_WF_THRESHOLD"))
         threshold = (uint32_t) atoi(e);
     int n_streams = kWfMaxSets;
@@ -625,6 +626,26 @@ dtof_status launch_wavefront(dtof_ctx *ctx, const RenderArgs &A, int mode, cudaS
     if (const char *e = getenv("DTOF_WF_DOUBLE"))
         W.double_step = (uint32_t) atoi(e);
     W.nodes_bytes = A.nodes_bytes, W.tris_bytes = A.tris_bytes, W.insts_bytes = A.insts_bytes;
+    // ray binning (dtof_wavefront.cuh): only where the walk is from HBM and a few animated instances carry the geometry
+    W.n_cls = 0;
+    {
+        bool bins = mode == MODE_BVH_GLOBAL;
+        if (const char *e = getenv("DTOF_WF_BINS"))
+            bins = bins && atoi(e) != 0;
+        uint32_t n_anim = 0;
+        for (const InstRec &r : ctx->h_insts)
+            n_anim += r.animated ? 1u : 0u;
+        if (bins && n_anim >= 1 && n_anim <= (uint32_t) kWfMaxCls && ctx->h_boxes.size() == ctx->h_insts.size()) {
+            for (size_t g = 0; g < ctx->h_insts.size(); ++g) {
+                if (!ctx->h_insts[g].animated)
+                    continue;
+                const InstBox &b = ctx->h_boxes[g];
+                W.cls_lo[W.n_cls] = make_float4(b.lox, b.loy, b.loz, 0.f);
+                W.cls_hi[W.n_cls] = make_float4(b.hix, b.hiy, b.hiz, 0.f);
+                W.n_cls++;
+            }
+        }
+    }
     const bool doppler = A.p.integrator == DTOF_INTEGRATOR_DOPPLERTOFPATH;
     const size_t smem = mode == MODE_BVH_SMEM ? (size_t) A.nodes_bytes + A.tris_bytes + A.insts_bytes : 0;
     // with two batches in flight a traversal kernel leaves room for the other batch's CTAs
@@ -648,7 +669,7 @@ dtof_status launch_wavefront(dtof_ctx *ctx, const RenderArgs &A, int mode, cudaS
         for (uint32_t pass = 0; pass < A.n_passes; ++pass) {
             W.pass = pass;
             W.bounce = 0;
-            CU(cudaMemsetAsync(W.buf.ring, 0, kWfRing * 4 * sizeof(uint32_t), st));
+            CU(cudaMemsetAsync(W.buf.ring, 0, kWfRing * kWfSlotWords * sizeof(uint32_t), st));
             {
             NvtxRange r_gen("dtof.wf_generate");
             if (doppler)
@@ -661,7 +682,7 @@ dtof_status launch_wavefront(dtof_ctx *ctx, const RenderArgs &A, int mode, cudaS
             for (uint32_t b = 0; !bounded || b < (uint32_t) A.p.max_depth; ++b) {
                 W.bounce = b;
                 if (b + 1 >= (uint32_t) kWfRing)   // recycle the ring slot the next bounce will count into
-                    CU(cudaMemsetAsync(W.buf.ring + 4 * ((b + 1) % kWfRing), 0, 4 * sizeof(uint32_t), st));
+                    CU(cudaMemsetAsync(W.buf.ring + kWfSlotWords * ((b + 1) % kWfRing), 0, kWfSlotWords * sizeof(uint32_t), st));
                 {
                     NvtxRange r_tc("dtof.wf_trace_closest");
                     s = mode == MODE_BVH_SMEM ? launch_wf_trace<MODE_BVH_SMEM, false>(ctx, W, trace_grid, smem, st)
@@ -695,10 +716,12 @@ dtof_status launch_wavefront(dtof_ctx *ctx, const RenderArgs &A, int mode, cudaS
                 // bounded depth: every bounce is enqueued blind (an empty queue costs one idle launch). Unbounded or
                 // deep paths (Russian roulette ends them): from the 8th bounce on, look at the next queue's length.
                 if (b >= 7 && (!bounded || (uint32_t) A.p.max_depth > 8)) {
-                    uint32_t *h = ctx->wf_host_count + set;
-                    CU(cudaMemcpyAsync(h, W.buf.ring + 4 * ((b + 1) % kWfRing), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+                    uint32_t *h = ctx->wf_host_count + 2 * set;   // both classes of the next path-ray queue
+                    const uint32_t *nx = W.buf.ring + kWfSlotWords * ((b + 1) % kWfRing);
+                    CU(cudaMemcpyAsync(h, nx + WF_N_RAY, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+                    CU(cudaMemcpyAsync(h + 1, nx + WF_N_RAY_B, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
                     CU(cudaStreamSynchronize(st));
-                    if (*h == 0)
+                    if (h[0] + h[1] == 0)
                         break;
                 }
             }
@@ -1388,6 +1411,7 @@ static dtof_status upload_prepared(dtof_ctx *ctx, const dtof_scene_desc *sc, Hos
     if ((s = upload_vec(ctx, cdf, &ctx->d_cdf)) != DTOF_OK) return s;
     if ((s = upload_vec(ctx, pmf, &ctx->d_pmf)) != DTOF_OK) return s;
     ctx->h_insts = insts;
+    ctx->h_boxes = built.inst_box;
     ctx->nodes_bytes = built.nodes.size() * sizeof(BvhNode);
     ctx->tris_bytes = built.tris.size() * sizeof(TriIsect);
     ctx->insts_bytes = insts.size() * sizeof(InstRec);
@@ -1527,6 +1551,7 @@ dtof_status dtof_update_instances(dtof_ctx *ctx, uint32_t first, uint32_t n, con
                       cudaMemcpyHostToDevice));
     if (!tl.inst_box.empty())
         CU(cudaMemcpy(ctx->d_boxes, tl.inst_box.data(), tl.inst_box.size() * sizeof(InstBox), cudaMemcpyHostToDevice));
+    ctx->h_boxes = tl.inst_box;
     ctx->ds.root = tl.root;
     ctx->bvh_depth = ctx->blas_depth + tl.tlas_depth;
     for (dtof_ctx *p : ctx->peers) {

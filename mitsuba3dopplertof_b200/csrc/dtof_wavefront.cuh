@@ -34,8 +34,19 @@ constexpr uint32_t kWfChunk = 256;    // rays a warp reserves from a queue per a
 #endif
 constexpr int kWfShadeBlock = 256;
 
-// counters of bounce b live at ring + 4 * (b % kWfRing)
-enum : int { WF_N_RAY = 0, WF_N_SHADOW = 1, WF_FETCH_CLOSEST = 2, WF_FETCH_SHADOW = 3 };
+// counters of bounce b live at ring + kWfSlotWords * (b % kWfRing)
+//
+// RAY BINNING. A queue is filled from both ends: rays that cross the world box of an animated instance (class A: they will
+// enter that instance and walk its BLAS -- in a scene with a multi-million-triangle instance that is a 5x longer walk that
+// starts with a matrix inverse) are appended at the front, all other rays (class B: the static part only) at the back.
+// Entry i of the queue lives at position wf_pos(i): i < nA ? i : n_slots - 1 - (i - nA). A traversal warp reserves chunks of
+// consecutive entries, so its 32 lanes hold rays of ONE class: class-A warps enter the instance together (the entry ran at
+// 3.6 of 32 lanes in mixed warps) and descend the same deep tree, class-B warps turn over short rays. Per-lane results do not
+// depend on queue order. With no classifier boxes (WfArgs::n_cls = 0: shared-memory scenes, many instances) every ray is
+// class A and the layout is the plain compacted queue.
+constexpr int kWfSlotWords = 8;
+enum : int { WF_N_RAY = 0, WF_N_SHADOW = 1, WF_FETCH_CLOSEST = 2, WF_FETCH_SHADOW = 3, WF_N_RAY_B = 4, WF_N_SHADOW_B = 5 };
+constexpr int kWfMaxCls = 4;           // animated-instance boxes the classifier tests
 
 struct WfBuffers {
     // per-lane path state, indexed by the lane's slot in the batch
@@ -54,7 +65,7 @@ struct WfBuffers {
     // shadow-ray queue with the pending emitter-sampling term
     float4 *s_o, *s_d, *s_thr, *s_c;
     uint32_t *s_lane;
-    uint32_t *ring;                 // kWfRing x 4 counters
+    uint32_t *ring;                 // kWfRing x kWfSlotWords counters
 };
 
 struct WfArgs {
@@ -74,9 +85,33 @@ struct WfArgs {
     uint32_t inner_threshold;         // phase scheduling: inner-node steps run while this many lanes want one
     uint32_t double_step;             // ... and two steps per vote while this many want one (33 = never)
     uint32_t nodes_bytes, tris_bytes, insts_bytes;
+    // ray binning: padded world boxes of the animated instances (over both keyframes), n_cls = 0 turns binning off
+    uint32_t n_cls;
+    float4 cls_lo[kWfMaxCls], cls_hi[kWfMaxCls];
 };
 
-DTOF_DEV uint32_t *wf_slot(const WfArgs &A, uint32_t bounce) { return A.buf.ring + 4 * (bounce % kWfRing); }
+DTOF_DEV uint32_t *wf_slot(const WfArgs &A, uint32_t bounce) { return A.buf.ring + kWfSlotWords * (bounce % kWfRing); }
+// position of queue entry i (see RAY BINNING above)
+DTOF_DEV uint32_t wf_pos(uint32_t i, uint32_t n_a, uint32_t n_slots) { return i < n_a ? i : n_slots - 1u - (i - n_a); }
+// does the segment o + t d, t in [0, maxt], cross the box of an animated instance? (conservative slab test; class A)
+DTOF_DEV bool wf_class_a(const WfArgs &A, V3 o, V3 d, float maxt) {
+    if (A.n_cls == 0u)
+        return true;
+    const V3 id = v3(frcp(d.x), frcp(d.y), frcp(d.z));
+    bool hit = false;
+#pragma unroll
+    for (int g = 0; g < kWfMaxCls; ++g) {
+        if ((uint32_t) g < A.n_cls) {
+            const float4 lo = A.cls_lo[g], hi = A.cls_hi[g];
+            const float ax = (lo.x - o.x) * id.x, bx = (hi.x - o.x) * id.x, ay = (lo.y - o.y) * id.y, by = (hi.y - o.y) * id.y,
+                        az = (lo.z - o.z) * id.z, bz = (hi.z - o.z) * id.z;
+            const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.f));
+            const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), maxt));
+            hit = hit || tn <= tf * 1.00001f;
+        }
+    }
+    return hit;
+}
 
 // ------------------------------------------------------------------------------------------------
 // Stage 1: render_sample() up to the camera ray (Doppler branch src/render/integrator.cpp:476-542, stock branch
@@ -189,7 +224,7 @@ __global__ void __launch_bounds__(kWfBlock, DTOF_WF_TRACE_CTAS) wf_trace_kernel(
     }
     const WfBuffers &B = A.buf;
     uint32_t *slot = wf_slot(A, A.bounce);
-    const uint32_t n = slot[ANY ? WF_N_SHADOW : WF_N_RAY];
+    const uint32_t n_a = slot[ANY ? WF_N_SHADOW : WF_N_RAY], n = n_a + slot[ANY ? WF_N_SHADOW_B : WF_N_RAY_B];
     uint32_t *fetch = slot + (ANY ? WF_FETCH_SHADOW : WF_FETCH_CLOSEST);
     const int q = A.bounce & 1;
     const float4 *__restrict__ qo = ANY ? B.s_o : B.q_o[q], *__restrict__ qd = ANY ? B.s_d : B.q_d[q];
@@ -249,7 +284,7 @@ __global__ void __launch_bounds__(kWfBlock, DTOF_WF_TRACE_CTAS) wf_trace_kernel(
                 const uint32_t give = min((uint32_t) __popc(m_idle), w_end - w_next);
                 const uint32_t rank = __popc(m_idle & ((1u << lane) - 1u));
                 if (idle && rank < give) {
-                    k = w_next + rank;
+                    k = wf_pos(w_next + rank, n_a, A.n_slots);
                     const float4 a = qo[k], b = qd[k];
                     ro = v3(a.x, a.y, a.z), rd = v3(b.x, b.y, b.z);
                     best = a.w;
@@ -348,16 +383,16 @@ __global__ void __launch_bounds__(kWfShadeBlock, DTOF_WF_SHADE_CTAS * (kWfBlock 
 wf_shade_kernel(const __grid_constant__ WfArgs A) {
     const WfBuffers &B = A.buf;
     uint32_t *slot = wf_slot(A, A.bounce), *next = wf_slot(A, A.bounce + 1);
-    const uint32_t n = slot[WF_N_RAY];
+    const uint32_t n_a = slot[WF_N_RAY], n = n_a + slot[WF_N_RAY_B];
     const int q = A.bounce & 1, qn = q ^ 1;
     const int lane = threadIdx.x & 31;
     const float emitter_pmf = A.scene.n_emitters ? 1.f / (float) A.scene.n_emitters : 0.f;
     const uint32_t stride = gridDim.x * kWfShadeBlock;
-    __shared__ uint32_t sh_count[2][kWfShadeBlock / 32], sh_base[2];
+    __shared__ uint32_t sh_count[4][kWfShadeBlock / 32], sh_base[4];   // next path queue A / B, shadow queue A / B
     const int warp = threadIdx.x >> 5;
     for (uint32_t bbase = blockIdx.x * kWfShadeBlock; bbase < n; bbase += stride) {   // block-uniform trip count
-        const uint32_t k = bbase + threadIdx.x;
-        const bool on = k < n;
+        const bool on = bbase + threadIdx.x < n;
+        const uint32_t k = wf_pos(bbase + threadIdx.x, n_a, A.n_slots);
         PathState ps;
         PendingNee nee;
         nee.want = false;
@@ -409,36 +444,44 @@ wf_shade_kernel(const __grid_constant__ WfArgs A) {
         // ---- compaction: one atomicAdd per CTA and queue. All warps of the machine count into the same two words, and
         // same-address atomics serialise in L2: with one atomicAdd per warp the kernel spent 46 % of its stall samples
         // waiting for them (profiles/r01_tuning.md).
-        const unsigned m_next = __ballot_sync(kFullMask, on && ps.active);
-        const unsigned m_shadow = __ballot_sync(kFullMask, on && nee.want);
+        // class of the two new rays (RAY BINNING): A = crosses an animated instance's box
+        const bool want_next = on && ps.active, want_shadow = on && nee.want;
+        const bool next_a = want_next && wf_class_a(A, ray_o, ray_d, ray_maxt);
+        const bool shadow_a = want_shadow && wf_class_a(A, nee.o, nee.d, nee.maxt);
+        const unsigned m[4] = { __ballot_sync(kFullMask, next_a), __ballot_sync(kFullMask, want_next && !next_a),
+                                __ballot_sync(kFullMask, shadow_a), __ballot_sync(kFullMask, want_shadow && !shadow_a) };
         if (lane == 0) {
-            sh_count[0][warp] = __popc(m_next);
-            sh_count[1][warp] = __popc(m_shadow);
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                sh_count[c][warp] = __popc(m[c]);
         }
         __syncthreads();
-        if (threadIdx.x < 2) {
+        if (threadIdx.x < 4) {
             uint32_t total = 0;
 #pragma unroll
             for (int w = 0; w < kWfShadeBlock / 32; ++w)
                 total += sh_count[threadIdx.x][w];
-            sh_base[threadIdx.x] = total ? atomicAdd(threadIdx.x == 0 ? next + WF_N_RAY : slot + WF_N_SHADOW, total) : 0u;
+            uint32_t *ctr = threadIdx.x == 0 ? next + WF_N_RAY : threadIdx.x == 1 ? next + WF_N_RAY_B
+                          : threadIdx.x == 2 ? slot + WF_N_SHADOW : slot + WF_N_SHADOW_B;
+            sh_base[threadIdx.x] = total ? atomicAdd(ctr, total) : 0u;
         }
         __syncthreads();
-        uint32_t b_next = sh_base[0], b_shadow = sh_base[1];
+        uint32_t base[4] = { sh_base[0], sh_base[1], sh_base[2], sh_base[3] };
         for (int w = 0; w < warp; ++w) {
-            b_next += sh_count[0][w];
-            b_shadow += sh_count[1][w];
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                base[c] += sh_count[c][w];
         }
         __syncthreads();   // sh_count / sh_base are rewritten by the next iteration
         const unsigned lt = (1u << lane) - 1u;
-        if (on && ps.active) {
-            const uint32_t j = b_next + __popc(m_next & lt);
+        if (want_next) {
+            const uint32_t j = next_a ? base[0] + __popc(m[0] & lt) : A.n_slots - 1u - (base[1] + __popc(m[1] & lt));
             B.q_o[qn][j] = make_float4(ray_o.x, ray_o.y, ray_o.z, ray_maxt);
             B.q_d[qn][j] = make_float4(ray_d.x, ray_d.y, ray_d.z, ray_time);
             B.q_lane[qn][j] = s;
         }
-        if (on && nee.want) {
-            const uint32_t j = b_shadow + __popc(m_shadow & lt);
+        if (want_shadow) {
+            const uint32_t j = shadow_a ? base[2] + __popc(m[2] & lt) : A.n_slots - 1u - (base[3] + __popc(m[3] & lt));
             B.s_o[j] = make_float4(nee.o.x, nee.o.y, nee.o.z, nee.maxt);
             B.s_d[j] = make_float4(nee.d.x, nee.d.y, nee.d.z, ray_time);
             B.s_thr[j] = make_float4(nee.thr.x, nee.thr.y, nee.thr.z, 0.f);

@@ -67,7 +67,7 @@ if os.path.exists(p):
         stages[k] = st
     thread = sum(s["warp_inst_per_sample"] * s["lanes_per_inst"] for s in stages.values())
     out["c5_wavefront"] = {
-        "source": "ncu launch list of python bench.py --workload c5 --spp 64 (profiles/r02_launches_c5_wavefront.csv, profiles/tools/r02/run10.sh)",
+        "source": "ncu launch list of python bench.py --workload c5 --spp 64 (profiles/r02_launches_c5_wavefront.csv, profiles/tools/r02/run29.sh)",
         "samples": PIX["c5"] * SPP, "renders_in_capture": renders,
         "bytes_per_sample": tot["dram_read_bytes_per_sample"] + tot["dram_write_bytes_per_sample"],
         "dram_read_bytes_per_sample": tot["dram_read_bytes_per_sample"], "dram_write_bytes_per_sample": tot["dram_write_bytes_per_sample"],
