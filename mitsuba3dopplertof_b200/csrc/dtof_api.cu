@@ -630,8 +630,8 @@ dtof_status launch_wavefront(dtof_ctx *ctx, const RenderArgs &A, int mode, cudaS
     W.n_cls = 0;
     {
         bool bins = mode == MODE_BVH_GLOBAL;
-        if (const char *e = getenv("DTOF_WF_BINS"))
-            bins = bins && atoi(e) != 0;
+        if (const char *e = getenv("DTOF_WF_BINS"))   // 0: off, 1: default rule, 2: also for shared-memory scenes (experiments)
+            bins = atoi(e) == 2 || (bins && atoi(e) != 0);
         uint32_t n_anim = 0;
         for (const InstRec &r : ctx->h_insts)
             n_anim += r.animated ? 1u : 0u;
