@@ -89,6 +89,6 @@ def test_single_device_multi_context_is_the_plain_context():
     fa, fb = a.upload(scene), b.upload(scene)
     ra, rb = a.render(fa, params, develop=False), b.render(fb, params, develop=False)
     assert b.device_count() == 1
-    assert np.abs(ra - rb).max() <= 1e-6 * np.abs(ra).max()
+    assert np.abs(ra - rb).max() <= 5e-6 * np.abs(ra).max()   # two renders: float atomics arrive in any order
     a.close()
     b.close()
